@@ -1,0 +1,334 @@
+#!/usr/bin/env python
+"""
+bench.py - BASELINE.json metric: line-images/s (48 px height) of the rpred hot path on N B200s.
+
+Workload (config.workload "cfg2"): VGSL [1,48,0,1 Cr3,3,32 Mp2,2 Cr3,3,64 Mp2,2 S1(1x0)1,3 Lbx256 O1c200], random-init
+weights (reference init distributions), one step = ONE batch of 64 synthetic 48x800 lines through
+`kb_recognize` (net -> softmax -> arg-max -> CTC collapse -> label tuples on the host).
+
+  value  lines/s with the line batch already resident in HBM (device pointers), decoded labels returned to the host.
+  e2e    the same call with pinned HOST buffers: H2D of the 64x48x800 fp32 batch and D2H of the label block are
+         inside the timed region.
+  roofline      the dominant kernel stage of the step, timed with CUDA events on the launching stream inside the
+                timed region (kb_set_timing), against MEASURED_PEAKS.json.
+  cpu_baseline  the oracle (torch-CPU restatement of the reference, `kind: "port"`; the reference is a Python package
+                whose dependencies are not installed on the GPU box) on all host cores, bounded sample.
+  --impl reference   times that same CPU implementation as its own arm.
+
+N > 1 (torchrun): line batches shard embarrassingly - every rank runs its own replica on its own shard (weak
+scaling, fixed 64 lines per step per GPU); weights are broadcast once from rank 0 over NCCL before the timed
+region and the decoded label blocks of all steps are gathered to rank 0 once at its end.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np
+import torch
+
+CFG2 = '[1,48,0,1 Cr3,3,32 Mp2,2 Cr3,3,64 Mp2,2 S1(1x0)1,3 Lbx256 O1c200]'
+BATCH, HEIGHT, WIDTH, NCLS = 64, 48, 800, 200
+METRIC = 'line-images/sec (48px height)'
+UNIT = 'lines/s'
+
+
+# ---------------------------------------------------------------------------------------------------------
+# algorithmic work per line (DESIGN.md "roofline accounting")
+# ---------------------------------------------------------------------------------------------------------
+def stage_work(W=WIDTH):
+    w2, T = W // 2, (W // 2) // 2
+    f = 4  # fp32 bytes
+    return {  # stage -> (FLOPs per line, algorithmic HBM bytes per line = unique input + output of the stage)
+        'C_0': (2 * 48 * W * 32 * 9, f * (48 * W + 48 * W * 32)),
+        'Mp_1': (0, f * (48 * W * 32 + 24 * w2 * 32)),
+        'C_2': (2 * 24 * w2 * 64 * 288, f * (24 * w2 * 32 + 24 * w2 * 64)),
+        'Mp_3': (0, f * (24 * w2 * 64 + 12 * T * 64)),
+        'S_4': (0, f * 2 * 768 * T),
+        'L_5.xproj': (2 * T * 768 * 2048, f * (768 * T + 2048 * T)),
+        'L_5.rec': (2 * T * 2 * 1024 * 256, f * (2048 * T + 512 * T)),
+        'O_6': (2 * T * 512 * 200, f * (512 * T + 200 * T)),
+        'decode': (0, f * (200 * T) + 16 * T),
+    }
+
+
+def peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {'hbm_gbs': d['hbm_gbs'], 'tf_burst': d['bf16_tflops'], 'tf_sustained': d['bf16_tflops_sustained'], 'src': 'measured'}
+    return {'hbm_gbs': 6650.0, 'tf_burst': 1590.0, 'tf_sustained': 1400.0, 'src': 'fallback'}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits', '-lms', '100',
+                                          '-i', str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(',')]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), f[5:9]):
+                if v.lower().startswith('active'):
+                    reasons.add(name)
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
+                'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+def make_batches(count, seed):
+    g = torch.Generator().manual_seed(seed)
+    return [torch.rand(BATCH, 1, HEIGHT, WIDTH, generator=g) for _ in range(count)]
+
+
+def oracle_model(seed=0):
+    sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+    import vgsl_oracle as vo
+    om = vo.OracleModel(CFG2)
+    w = om.init_like_reference(seed)
+    return vo, om, w
+
+
+def time_cpu(steps, warmup, threads=None):
+    """The reference's CPU path for one step: nn(x, lens) + softmax + greedy_decoder on a batch of 64 (rpred.py:225-228)."""
+    vo, om, _ = oracle_model()
+    threads = threads or os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    xs = make_batches(2, 100)
+    lens = torch.full((BATCH,), WIDTH, dtype=torch.long)
+    for i in range(warmup):
+        vo.rec_predict(om, xs[i % 2], lens)
+    t0 = time.perf_counter()
+    for i in range(steps):
+        vo.rec_predict(om, xs[i % 2], lens)
+    dt = time.perf_counter() - t0
+    return BATCH * steps / dt, dt / steps * 1e3, threads
+
+
+def cpu_model_name():
+    try:
+        for ln in open('/proc/cpuinfo'):
+            if ln.startswith('model name'):
+                return ln.split(':', 1)[1].strip()
+    except Exception:
+        pass
+    return 'unknown'
+
+
+def run_reference_arm(args, rank):
+    if rank != 0:
+        return
+    lps, ms, threads = time_cpu(args.steps, args.warmup)
+    line = {'impl': 'reference', 'metric': METRIC, 'value': lps, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
+            'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': 'f32', 'data': 'synthetic',
+            'config': {'workload': 'cfg2', 'spec': CFG2, 'batch': BATCH, 'line': f'{HEIGHT}x{WIDTH}', 'device': 'host CPU'},
+            'cpu_baseline': {'value': lps, 'unit': UNIT, 'cores': threads, 'kind': 'port', 'cpu': cpu_model_name(),
+                             'sample': f'{args.steps} batches of {BATCH} lines {HEIGHT}x{WIDTH} after {args.warmup} warm-up; '
+                                       'torch-CPU restatement of the reference path (oracle/vgsl_oracle.py), fp32, all host threads'},
+            'e2e': {'value': lps, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=30)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--cpu-steps', type=int, default=6)
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == 'b200' else args.warmup
+
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if args.impl == 'reference':
+        run_reference_arm(args, rank)
+        return
+
+    import __graft_entry__ as ge
+    if rank == 0:
+        ge.build()
+    import torch.distributed as dist
+    if world > 1:
+        torch.cuda.set_device(local)
+        dist.init_process_group('nccl', device_id=torch.device(f'cuda:{local}'))
+        dist.barrier()
+    import kraken_b200 as kb
+    dev = f'cuda:{local}'
+    torch.cuda.set_device(local)
+
+    # ---- weights: rank 0 initialises, one NCCL broadcast of the packed blob, every rank loads its replica
+    m = kb.TorchVGSLModel(vgsl=CFG2, model_type=['recognition'])
+    if rank == 0:
+        _, _, w = oracle_model(0)                        # same seeded weights the parity tests use
+        m.load_state_dict(w)
+    if world > 1:
+        sd = m.state_dict()
+        blob = torch.cat([sd[k].flatten() for k in sd]).to(dev)
+        dist.broadcast(blob, src=0)
+        off = 0
+        new = {}
+        for k, v in sd.items():
+            new[k] = blob[off:off + v.numel()].view(v.shape).cpu()
+            off += v.numel()
+        m.load_state_dict(new)
+    rec = kb.TorchSeqRecognizer(m, device=dev)
+    lens = torch.full((BATCH,), WIDTH, dtype=torch.long)
+
+    NB = 4                                               # distinct input batches rotated through the steps
+    host = [b.pin_memory() for b in make_batches(NB, 1000 + rank)]
+    devb = [b.to(dev) for b in host]
+    T = WIDTH // 4
+
+    def step(x):
+        return rec._recognize(x, lens, want_probs=False)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(batches, steps, sink, on_step=None):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            dec, _ = step(batches[i % NB])
+            sink.append(dec)
+            if on_step is not None:
+                on_step()
+        if world > 1:
+            # the single gather of the run's decoded label sequences to rank 0 (fixed-stride pack per line:
+            # count + (label, start, end) x T); payload is bandwidth-trivial over NVLink
+            pack = torch.zeros((len(sink), BATCH, 1 + 3 * T), dtype=torch.int32)
+            for si, stepdec in enumerate(sink):
+                for li, d in enumerate(stepdec):
+                    pack[si, li, 0] = len(d)
+                    if d:
+                        pack[si, li, 1:1 + 3 * len(d)] = torch.tensor([v for t in d for v in t[:3]], dtype=torch.int32)
+            pack = pack.to(dev)
+            out = [torch.empty_like(pack) for _ in range(world)] if rank == 0 else None
+            dist.gather(pack, out, dst=0)
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    for i in range(args.warmup):
+        step(devb[i % NB]); step(host[i % NB])
+
+    # ---- timed region 1: inputs resident in HBM; per-stage CUDA-event timing on the launching stream
+    m.set_timing(True)
+    stage_ms = {}
+
+    results_buf = []
+
+    def on_step():
+        for name, ms in m.last_timing():
+            stage_ms[name] = stage_ms.get(name, 0.0) + ms
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    m.reset_launch_count()
+    ms_total = timed(devb, args.steps, results_buf, on_step)
+    launches = m.launch_count
+    clocks = sampler.stop() if rank == 0 else None
+    m.set_timing(False)
+    # ---- timed region 2: end to end through the public API with pinned host buffers
+    results_buf2 = []
+    ms_e2e = timed(host, args.steps, results_buf2)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    ms_step = ms_total / args.steps
+    value = world * BATCH * args.steps / (ms_total / 1e3)
+    e2e = world * BATCH * args.steps / (ms_e2e / 1e3)
+    pk = peaks()
+    work = stage_work()
+    per_stage = {k: v / args.steps for k, v in stage_ms.items()}
+    dom = max((k for k in per_stage if k in work), key=lambda k: per_stage[k])
+    flops, byts = work[dom][0] * BATCH, work[dom][1] * BATCH
+    t_tensor, t_hbm = flops / (pk['tf_sustained'] * 1e12), byts / (pk['hbm_gbs'] * 1e9)
+    dur = per_stage[dom] / 1e3
+    if t_tensor >= t_hbm:
+        roof = {'bound': 'tensor', 'achieved': flops / dur / 1e12, 'peak': pk['tf_sustained'], 'unit': 'TFLOP/s'}
+    else:
+        roof = {'bound': 'hbm', 'achieved': byts / dur / 1e9, 'peak': pk['hbm_gbs'], 'unit': 'GB/s'}
+    roof.update({'frac': roof['achieved'] / roof['peak'], 'traffic': None, 'kernel': dom, 'kernel_ms': per_stage[dom],
+                 'share_of_step': per_stage[dom] / ms_step, 'peak_source': pk['src'] + (' (sustained bf16 GEMM)' if roof['bound'] == 'tensor' else ' (copy bandwidth)'),
+                 'algorithmic_per_launch': {'flops': flops, 'bytes': byts},
+                 'stages_ms': {k: round(v, 4) for k, v in per_stage.items()}})
+    tot_f = sum(v[0] for v in work.values()) * BATCH
+    tot_b = (4 * 48 * WIDTH + 2 * 4 * 768 * T + 2 * 4 * 2048 * T + 2 * 4 * 512 * T + 8 * T) * BATCH
+    roof['whole_step'] = {'tensor_frac': tot_f / (ms_step / 1e3) / (pk['tf_sustained'] * 1e12),
+                          'hbm_frac': tot_b / (ms_step / 1e3) / (pk['hbm_gbs'] * 1e9)}
+
+    cpu = None
+    if not args.no_cpu_baseline and world == 1:
+        lps, cms, threads = time_cpu(args.cpu_steps, 2)
+        cpu = {'value': lps, 'unit': UNIT, 'cores': threads, 'kind': 'port', 'cpu': cpu_model_name(),
+               'sample': f'{args.cpu_steps} batches of {BATCH} lines {HEIGHT}x{WIDTH} after 2 warm-up ({cms:.0f} ms/batch); '
+                         'oracle/vgsl_oracle.py = torch-CPU restatement of rpred.py:225-228 + ctc_decoder.py, fp32, all host threads'}
+
+    d2h = BATCH * T * 16 + BATCH * 4
+    line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+            'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
+            'data': 'synthetic',
+            'config': {'workload': 'cfg2', 'spec': CFG2, 'batch_per_gpu': BATCH, 'global_batch': BATCH * world, 'line': f'{HEIGHT}x{WIDTH}',
+                       'parallelism': f'replicas x{world} (independent line shards, 1 weight broadcast + 1 result gather)',
+                       'l2': f'{NB} rotating input batches; ~0.77 GB of activations per step > 126 MB L2'},
+            'e2e': {'value': e2e, 'unit': UNIT, 'ms_per_step': ms_e2e / args.steps,
+                    'h2d_bytes_per_step': BATCH * HEIGHT * WIDTH * 4, 'd2h_bytes_per_step': d2h},
+            'gpu_launches': int(launches), 'clocks': clocks, 'roofline': roof, 'cpu_baseline': cpu,
+            'decoded_labels_last_step': int(sum(len(d) for d in results_buf[-1])) if results_buf else 0}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

@@ -1,0 +1,158 @@
+/*
+ * kraken_b200.h - C ABI of the B200-native line-recognition / segmentation-forward engine.
+ *
+ * This is the drop-in boundary for ONE hot path of mittagessen/kraken (paths relative to the
+ * reference checkout):
+ *
+ *   rpred :  batched line images -> VGSL conv stack -> BiLSTM -> linear -> softmax -> CTC greedy decode
+ *            kraken/lib/vgsl/rpred.py:210-229 (_rec_predict), kraken/lib/models.py:93-136
+ *   blla  :  page -> VGSL net -> nearest upsample -> sigmoid
+ *            kraken/lib/vgsl/spred.py:268-272, kraken/blla.py:121-125
+ *
+ * The reference has no FFI (it is pure Python over ATen); the narrowest operator boundary it has is
+ * the callable `TorchVGSLModel.nn(x[N,C,H,W], seq_lens[N]) -> (y[N,C',H',W'], seq_lens')`
+ * (kraken/lib/vgsl/layers.py:44-53, kraken/lib/vgsl/model.py:488-489) plus the decoder hook
+ * `decoder(probs[N,C,W], seq_lens) -> [[(label,start,end,conf)]]` (kraken/lib/ctc_decoder.py:35-72).
+ * Every entry point below names the reference interface it replaces.  INTEGRATION.md shows the
+ * ctypes stub a kraken maintainer would add.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch types.  All tensors are fp32, NCHW, dense, as in the reference.
+ *   - `*_on_device` flags say whether a data pointer is a CUDA device pointer (of the model's device) or
+ *     a host pointer (pinned or pageable).  Host pointers are copied inside the call.
+ *   - every function returns KB_OK or an error code; kb_last_error() returns a thread-local message.
+ *     No exceptions cross the ABI.  Error codes map onto the reference's Python exceptions:
+ *       KB_ERR_SPEC        -> ValueError            (model.py:160,187,194,230,239,796-804,870,898)
+ *       KB_ERR_SHAPE       -> KrakenInputException  (models.py:113-114) / the layer's own Exception
+ *       KB_ERR_ARG/STATE   -> ValueError / RuntimeError at the Python surface
+ *       KB_ERR_CUDA        -> RuntimeError - there is NO CPU fallback: without a usable GPU every
+ *                             compute entry point fails with this code.
+ *   - a model handle is internally serialised (one call at a time per handle); different handles are
+ *     independent and may be driven from different threads/streams.  The engine owns weights and
+ *     workspaces; the caller owns every buffer it passes in.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = the legacy default stream).  Calls that return
+ *     host results synchronise that stream before returning; device-output calls do not.
+ */
+#ifndef KRAKEN_B200_H
+#define KRAKEN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KB_ABI_VERSION 1
+
+enum {
+    KB_OK = 0,
+    KB_ERR_SPEC = 1,
+    KB_ERR_ARG = 2,
+    KB_ERR_CUDA = 3,
+    KB_ERR_UNSUPPORTED = 4,
+    KB_ERR_STATE = 5,
+    KB_ERR_SHAPE = 6
+};
+
+/* layer kinds reported by kb_model_layer_info (leaf layers only, in execution order) */
+enum {
+    KB_LAYER_CONV = 1, KB_LAYER_MAXPOOL = 2, KB_LAYER_RESHAPE = 3, KB_LAYER_LSTM = 4, KB_LAYER_DROPOUT = 5,
+    KB_LAYER_GROUPNORM = 6, KB_LAYER_LINEAR = 7, KB_LAYER_ADDITION = 8, KB_LAYER_IDENTITY = 9
+};
+
+typedef struct kb_model kb_model;
+
+typedef struct kb_layer_info {
+    int32_t kind;            /* KB_LAYER_*                                                        */
+    int32_t out_shape[4];    /* static (batch, C, H, W) as the reference's get_shape(); 0 = variable */
+    char    name[64];        /* e.g. "C_0"                                                         */
+    char    path[256];       /* state-dict prefix below "nn.", e.g. "C_2 C_3 I_4.C_2 C_3.C_2"      */
+    char    block[128];      /* named block, e.g. "Cr{C_0}3,3,32"                                  */
+} kb_layer_info;
+
+/* ---- library ------------------------------------------------------------------------------------ */
+int         kb_abi_version(void);
+const char *kb_last_error(void);
+/* number of visible CUDA devices (0 when there is no driver/GPU; never fails) */
+int         kb_device_count(void);
+
+/* ---- spec -> graph (host only, usable without a GPU) ---------------------------------------------
+ * replaces TorchVGSLModel.__init__/_parse/build_* (kraken/lib/vgsl/model.py:109-243, 570-902).        */
+int  kb_model_create(const char *vgsl_spec, kb_model **out);
+void kb_model_destroy(kb_model *m);
+/* named spec "[1,48,0,1 Cr{C_0}3,3,32 ...]" == user_metadata['vgsl'] (model.py:198-199).
+ * Returns the length needed (excluding NUL) or a negative error; writes at most cap bytes.          */
+int  kb_model_named_spec(const kb_model *m, char *buf, size_t cap);
+int  kb_model_input_shape(const kb_model *m, int32_t shape[4]);    /* (batch, channels, height, width) model.py:196 */
+int  kb_model_output_shape(const kb_model *m, int32_t shape[4]);   /* TorchVGSLModel.output                         */
+int  kb_model_num_layers(const kb_model *m);
+int  kb_model_layer_info(const kb_model *m, int index, kb_layer_info *info);
+/* parameters in state_dict() order; names are the reference's keys ("nn.C_0.co.weight", ...) */
+int  kb_model_num_tensors(const kb_model *m);
+int  kb_model_tensor_info(const kb_model *m, int index, char *name, size_t cap, int64_t shape[4], int32_t *ndim);
+/* runtime shape of nn(x) for an input of n x C x h x w, and the seq_len arithmetic of every layer
+ * (layers.py:334,387,858-859) applied to `widths`; pure integer/host work.                          */
+int  kb_model_infer_dims(const kb_model *m, int32_t n, int32_t h, int32_t w, int32_t out_nchw[4]);
+int  kb_model_infer_lens(const kb_model *m, int32_t n, int32_t h, int32_t w, const int32_t *widths, int32_t *out_lens);
+
+/* ---- weights ------------------------------------------------------------------------------------
+ * replaces load_state_dict(); data is fp32 host memory, copied.                                     */
+int  kb_model_load_tensor(kb_model *m, const char *name, const float *data, const int64_t *shape, int32_t ndim);
+/* uploads + repacks weights (HWIO conv filters, gate-interleaved LSTM matrices, folded biases) on
+ * `device`.  Needs a GPU.  Must be called again after load_tensor().  replaces nn.to(device)
+ * (kraken/lib/models.py:84-91, model.py:518-523).                                                  */
+int  kb_model_finalize(kb_model *m, int device);
+int  kb_model_device(const kb_model *m);            /* -1 before finalize */
+
+/* ---- nn(x, seq_lens) -----------------------------------------------------------------------------
+ * replaces `self.nn(line, lens)` (layers.py:44-53; callers rpred.py:225, models.py:112, spred.py:268,
+ * blla.py:121).  x: n x C x h x w.  widths: n int32 or NULL (seq_lens=None).  out: the NCHW result
+ * with the dims kb_model_infer_dims() reports; out_lens (n, may be NULL) receives seq_lens'.         */
+int  kb_forward(kb_model *m, const float *x, int x_on_device, int32_t n, int32_t h, int32_t w,
+                const int32_t *widths, float *out, int out_on_device, int32_t *out_lens, void *stream);
+
+/* ---- fused recognition --------------------------------------------------------------------------
+ * replaces _rec_predict up to (not including) codec.decode: nn -> (logits/T).softmax(1) -> greedy
+ * decoder (rpred.py:225-228, models.py:112-136, ctc_decoder.py:55-72).
+ * Outputs (host memory, caller allocated; max_out = capacity per line, use the output width T):
+ *   labels/starts/ends [n*max_out] int32, confs [n*max_out] float, counts [n], out_lens [n].
+ *   probs (optional, may be NULL): (n, C, T) like `self.outputs` (rpred.py:227); probs_on_device
+ *   selects where it lives.  Fails with KB_ERR_SHAPE if the net's output height is not 1.            */
+int  kb_recognize(kb_model *m, const float *lines, int lines_on_device, int32_t n, int32_t h, int32_t w,
+                  const int32_t *widths, float temperature,
+                  int32_t *labels, int32_t *starts, int32_t *ends, float *confs, int32_t *counts,
+                  int32_t max_out, int32_t *out_lens, float *probs, int probs_on_device, void *stream);
+
+/* ---- decoder hook -------------------------------------------------------------------------------
+ * replaces kraken.lib.ctc_decoder.greedy_decoder (ctc_decoder.py:35-72) for a (N, C, W) probability
+ * tensor; lens: n int32 (NULL => all W, as the reference allows for N == 1).                        */
+int  kb_ctc_greedy_decode(const float *probs, int probs_on_device, int32_t n, int32_t c, int32_t w,
+                          const int32_t *lens, int32_t *labels, int32_t *starts, int32_t *ends,
+                          float *confs, int32_t *counts, int32_t max_out, int device, void *stream);
+
+/* ---- segmentation forward -----------------------------------------------------------------------
+ * replaces nn(page) -> F.interpolate(o, size) -> sigmoid (spred.py:268-272, blla.py:121-125), batched.
+ * pages: n x C x h x w.  heatmap: n x C' x out_h x out_w fp32.                                      */
+int  kb_segment(kb_model *m, const float *pages, int pages_on_device, int32_t n, int32_t h, int32_t w,
+                int32_t out_h, int32_t out_w, float *heatmap, int heatmap_on_device, void *stream);
+
+/* ---- introspection for tests / profiling -------------------------------------------------------- */
+/* output of leaf layer `name` from the most recent forward on this handle, as NCHW host fp32.
+ * dims_only != 0: only fills dims.  Valid until the next call on the handle.                        */
+int  kb_debug_layer_output(kb_model *m, const char *name, int32_t dims[4], float *out_host, int dims_only);
+/* number of kernels this handle launched since creation / last reset (bench `gpu_launches`) */
+int64_t kb_launch_count(const kb_model *m);
+void    kb_reset_launch_count(kb_model *m);
+/* device-side stage timing of the most recent compute call on this handle.  With kb_set_timing(m, 1) every
+ * stage (one per leaf layer; LSTMs as "<name>.xproj" + "<name>.rec"; "stage_in", "decode", "emit",
+ * "upsample_sigmoid") is bracketed by CUDA events on the launching stream.  kb_timing_count() returns the number
+ * of stages recorded, kb_timing_entry() name + milliseconds of one of them (in execution order).            */
+int  kb_set_timing(kb_model *m, int enabled);
+int  kb_timing_count(kb_model *m);
+int  kb_timing_entry(kb_model *m, int index, char *name, size_t cap, float *ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KRAKEN_B200_H */

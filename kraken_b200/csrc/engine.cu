@@ -1,0 +1,855 @@
+// engine.cu - model object, weight repacking, layer executor and the C ABI of libkraken_b200.so.
+// See include/kraken_b200.h for the contract and the reference interfaces each entry point replaces.
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "../../include/kraken_b200.h"
+#include "kernels.cuh"
+#include "vgsl_plan.hpp"
+
+namespace kb {
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string &msg) { g_err = msg; return code; }
+
+struct CudaError : std::runtime_error { using std::runtime_error::runtime_error; };
+#define CK(call)                                                                                                   \
+    do {                                                                                                           \
+        cudaError_t _e = (call);                                                                                   \
+        if (_e != cudaSuccess)                                                                                     \
+            throw CudaError(std::string(#call) + " failed: " + cudaGetErrorString(_e) + " (" __FILE__ ":" + std::to_string(__LINE__) + ")"); \
+    } while (0)
+
+struct Tensor { float *p = nullptr; int64_t n = 0, h = 0, w = 0, c = 0; int64_t numel() const { return n * h * w * c; } };
+
+struct LeafWeights {
+    std::vector<std::vector<float>> host;      // by slot, reference layout
+    std::vector<bool> loaded;
+    // device (engine layout)
+    float *wt = nullptr;    // [K][Ncp]  conv/linear/lstm-x projection
+    float *bias = nullptr;  // [Cout] / folded LSTM bias / GN beta
+    float *aux = nullptr;   // W_hh [dirs][4h][h] / GN gamma
+    int ncp = 0, K = 0, ncols = 0;
+};
+
+struct Arena {
+    char *base = nullptr; size_t cap = 0, off = 0; bool dry = false;
+    void *alloc(size_t bytes) {
+        size_t a = (off + 255) & ~size_t(255);
+        off = a + bytes;
+        if (dry) return reinterpret_cast<void *>(uintptr_t(256) + a);     // fake, never dereferenced
+        if (off > cap) throw CudaError("internal: arena overflow");
+        return base + a;
+    }
+};
+
+struct Lens { bool has = false; std::vector<int32_t> v; };
+
+}  // namespace kb
+
+using namespace kb;
+
+struct kb_model {
+    std::unique_ptr<Plan> plan;
+    std::vector<LeafWeights> lw;
+    int device = -1;
+    bool finalized = false;
+    std::mutex mu;
+    Arena arena;
+    std::vector<void *> dev_allocs;              // weights
+    void *pinned = nullptr; size_t pinned_cap = 0;
+    int64_t launches = 0;
+    std::map<std::string, Tensor> taps;
+    bool timing = false;
+    struct Stage { std::string name; cudaEvent_t a = nullptr, b = nullptr; float ms = 0.f; };
+    std::vector<Stage> stages;       // event pool, reused across calls
+    size_t n_stages = 0;             // entries used by the most recent call
+    int sm_count = 148;
+    ~kb_model() {
+        if (device >= 0) {
+            cudaSetDevice(device);
+            for (void *p : dev_allocs) cudaFree(p);
+            if (arena.base) cudaFree(arena.base);
+            if (pinned) cudaFreeHost(pinned);
+            for (auto &e : stages) { if (e.a) cudaEventDestroy(e.a); if (e.b) cudaEventDestroy(e.b); }
+        }
+    }
+};
+
+namespace kb {
+
+#define LAUNCH(m, kern, grid, block, smem, st, ...)                                 \
+    do {                                                                            \
+        kern<<<grid, block, smem, st>>>(__VA_ARGS__);                               \
+        ++(m)->launches;                                                            \
+        CK(cudaPeekAtLastError());                                                  \
+    } while (0)
+
+// RAII device timer for one named stage of a call (only when kb_set_timing(m, 1)); events are recorded on the
+// launching stream, so the elapsed time is what the stream spent between the two records.
+struct StageTimer {
+    kb_model *m; cudaStream_t st; int idx = -1;
+    StageTimer(kb_model *m_, cudaStream_t st_, const std::string &name, bool active) : m(m_), st(st_) {
+        if (!active || !m->timing) return;
+        if (m->n_stages == m->stages.size()) {
+            kb_model::Stage s; CK(cudaEventCreate(&s.a)); CK(cudaEventCreate(&s.b)); m->stages.push_back(s);
+        }
+        idx = (int)m->n_stages++;
+        m->stages[idx].name = name; m->stages[idx].ms = 0.f;
+        CK(cudaEventRecord(m->stages[idx].a, st));
+    }
+    ~StageTimer() { if (idx >= 0) cudaEventRecord(m->stages[idx].b, st); }
+};
+
+static inline unsigned grid1d(long long total, int block, int sm_count) {
+    long long g = (total + block - 1) / block;
+    long long cap = (long long)sm_count * 16;
+    return (unsigned)std::max<long long>(1, std::min(g, cap));
+}
+
+// -------------------------------------------------------------------------------------------------
+// weights
+// -------------------------------------------------------------------------------------------------
+static float *upload(kb_model *m, const std::vector<float> &h) {
+    float *d = nullptr;
+    CK(cudaMalloc(&d, std::max<size_t>(h.size(), 1) * sizeof(float)));
+    m->dev_allocs.push_back(d);
+    if (!h.empty()) CK(cudaMemcpy(d, h.data(), h.size() * sizeof(float), cudaMemcpyHostToDevice));
+    return d;
+}
+
+static void finalize_weights(kb_model *m) {
+    for (void *p : m->dev_allocs) cudaFree(p);
+    m->dev_allocs.clear();
+    for (size_t li = 0; li < m->plan->leaf_nodes.size(); ++li) {
+        const Node &n = *m->plan->leaf_nodes[li];
+        LeafWeights &w = m->lw[li];
+        w.wt = w.bias = w.aux = nullptr;
+        auto need = [&](int slots) {
+            for (int s = 0; s < slots; ++s)
+                if ((int)w.loaded.size() <= s || !w.loaded[s]) throw SpecError("weights of layer " + n.name + " not loaded (missing tensor for nn." + n.path + ")");
+        };
+        if (n.kind == K_CONV) {
+            need(2);
+            const int K = n.kh * n.kw * n.cin, ncp = (n.cout + 63) / 64 * 64;
+            std::vector<float> wt((size_t)K * ncp, 0.f);
+            const std::vector<float> &src = w.host[0];       // [Cout][Cin][kh][kw]
+            for (int co = 0; co < n.cout; ++co)
+                for (int ci = 0; ci < n.cin; ++ci)
+                    for (int ky = 0; ky < n.kh; ++ky)
+                        for (int kx = 0; kx < n.kw; ++kx)
+                            wt[(size_t)((ky * n.kw + kx) * n.cin + ci) * ncp + co] = src[(((size_t)co * n.cin + ci) * n.kh + ky) * n.kw + kx];
+            w.wt = upload(m, wt); w.bias = upload(m, w.host[1]); w.ncp = ncp; w.K = K; w.ncols = n.cout;
+        } else if (n.kind == K_LINEAR) {
+            need(2);
+            const int K = n.cin, ncp = (n.cout + 63) / 64 * 64, ld = n.cin + (n.aug ? 1 : 0);
+            std::vector<float> wt((size_t)K * ncp, 0.f), b(w.host[1]);
+            for (int co = 0; co < n.cout; ++co) {
+                for (int ci = 0; ci < n.cin; ++ci) wt[(size_t)ci * ncp + co] = w.host[0][(size_t)co * ld + ci + (n.aug ? 1 : 0)];
+                if (n.aug) b[co] += w.host[0][(size_t)co * ld];          // the constant-one input column (layers.py:718-719)
+            }
+            w.wt = upload(m, wt); w.bias = upload(m, b); w.ncp = ncp; w.K = K; w.ncols = n.cout;
+        } else if (n.kind == K_GN) {
+            need(2);
+            w.aux = upload(m, w.host[0]); w.bias = upload(m, w.host[1]);
+        } else if (n.kind == K_LSTM) {
+            if (n.legacy) throw Unsupported(n.name + ": legacy clstm/ocropy LSTM variants are not implemented by the engine");
+            const int dirs = n.bidi ? 2 : 1, h = n.hidden, gc = dirs * 4 * h;
+            need(4 * dirs);
+            if (h > 256) throw Unsupported(n.name + ": hidden sizes above 256 are not supported by the register-resident recurrence kernel yet");
+            const int K = n.cin, ncp = (gc + 63) / 64 * 64;
+            std::vector<float> wt((size_t)K * ncp, 0.f), b((size_t)gc, 0.f), whh((size_t)dirs * 4 * h * h);
+            for (int d = 0; d < dirs; ++d) {
+                const std::vector<float> &wih = w.host[d * 4 + 0], &wh = w.host[d * 4 + 1], &bih = w.host[d * 4 + 2], &bhh = w.host[d * 4 + 3];
+                for (int g = 0; g < 4; ++g)
+                    for (int u = 0; u < h; ++u) {
+                        const int col = d * 4 * h + u * 4 + g, row = g * h + u;      // torch gate order i,f,g,o
+                        for (int ci = 0; ci < K; ++ci) wt[(size_t)ci * ncp + col] = wih[(size_t)row * K + ci];
+                        b[col] = bih[row] + bhh[row];
+                    }
+                std::copy(wh.begin(), wh.end(), whh.begin() + (size_t)d * 4 * h * h);
+            }
+            w.wt = upload(m, wt); w.bias = upload(m, b); w.aux = upload(m, whh); w.ncp = ncp; w.K = K; w.ncols = gc;
+        }
+    }
+}
+
+// -------------------------------------------------------------------------------------------------
+// executor
+// -------------------------------------------------------------------------------------------------
+struct Exec {
+    kb_model *m; cudaStream_t st; bool dry;
+    int leaf_counter = 0;
+
+    int *dev_lens(const Lens &l) {
+        if (!l.has) return nullptr;
+        int *d = (int *)m->arena.alloc(l.v.size() * sizeof(int));
+        if (!dry) CK(cudaMemcpyAsync(d, l.v.data(), l.v.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+        return d;
+    }
+    Tensor mk(const Dims &d) {
+        Tensor t; t.n = d.n; t.c = d.c; t.h = d.h; t.w = d.w;
+        t.p = (float *)m->arena.alloc((size_t)std::max<int64_t>(t.numel(), 1) * sizeof(float));
+        return t;
+    }
+    static Dims dims_of(const Tensor &t) { Dims d; d.n = t.n; d.c = t.c; d.h = t.h; d.w = t.w; return d; }
+
+    void gemm(const Tensor &x, const LeafWeights &w, const Node *conv, int act, float *y, int64_t Ho, int64_t Wo) {
+        ConvParams p;
+        p.x = x.p; p.wt = w.wt; p.bias = w.bias; p.y = y;
+        p.N = (int)x.n; p.H = (int)x.h; p.W = (int)x.w; p.Cin = (int)x.c; p.Ho = (int)Ho; p.Wo = (int)Wo;
+        p.Cout = w.ncols; p.Ncp = w.ncp;
+        if (conv) { p.kh = conv->kh; p.kw = conv->kw; p.sy = conv->sy; p.sx = conv->sx; p.dy = conv->dy; p.dx = conv->dx; p.py = conv->py; p.px = conv->px; }
+        else { p.kh = p.kw = p.sy = p.sx = p.dy = p.dx = 1; p.py = p.px = 0; }
+        p.K = w.K; p.M = (long long)x.n * Ho * Wo; p.act = act;
+        if (p.M == 0) return;
+        dim3 grid((unsigned)((p.M + CG_BM - 1) / CG_BM), (unsigned)(w.ncp / CG_BN));
+        if ((x.c & 3) == 0) LAUNCH(m, k_conv_gemm<true>, grid, CG_NT, 0, st, p);
+        else LAUNCH(m, k_conv_gemm<false>, grid, CG_NT, 0, st, p);
+    }
+
+    Tensor leaf(const Node &n, const Tensor &x, Lens &lens) {
+        const Dims din = dims_of(x);
+        const Dims dout = leaf_dims(n, din);
+        const LeafWeights &w = m->lw[n.leaf_index];
+        Tensor y;
+        const int sm = m->sm_count;
+        switch (n.kind) {
+        case K_CONV: {
+            y = mk(dout);
+            if (!dry) {
+                gemm(x, w, &n, n.act, y.p, dout.h, dout.w);
+                if (n.act == ACT_SOFTMAX) {
+                    long long rows = (long long)y.n * y.h * y.w;
+                    LAUNCH(m, k_softmax_rows, (unsigned)((rows + 7) / 8), 256, 0, st, y.p, rows, (int)y.c);
+                }
+            }
+            break;
+        }
+        case K_LINEAR: {
+            y = mk(dout);
+            if (!dry) gemm(x, w, nullptr, ACT_LINEAR, y.p, x.h, x.w);
+            break;
+        }
+        case K_POOL: {
+            y = mk(dout);
+            if (!dry && y.numel()) {
+                long long total = y.numel() / (((int)x.c & 3) == 0 ? 4 : 1);
+                LAUNCH(m, k_maxpool, grid1d(total, 256, sm), 256, 0, st, x.p, y.p, (int)x.n, (int)x.h, (int)x.w, (int)x.c,
+                       (int)y.h, (int)y.w, n.kh, n.kw, n.sy, n.sx);
+            }
+            break;
+        }
+        case K_RESHAPE: {
+            y = mk(dout);
+            ReshapeParams rp;
+            int64_t i4[4] = {din.n, din.c, din.h, din.w}, o4[4], s5[5]; int dest;
+            reshape_dims(i4, n, o4, rp.perm, &dest, s5);
+            for (int i = 0; i < 4; ++i) { rp.in_dims[i] = i4[i]; rp.out_dims[i] = o4[i]; }
+            for (int i = 0; i < 5; ++i) rp.shape5[i] = s5[i];
+            rp.src = n.rs_src; rp.dest = dest;
+            if (!dry && y.numel()) LAUNCH(m, k_reshape, grid1d(y.numel(), 256, sm), 256, 0, st, x.p, y.p, rp);
+            break;
+        }
+        case K_DROPOUT: case K_IDENTITY: y = x; break;
+        case K_ADD: {
+            y = mk(dout);
+            if (!dry && y.numel()) LAUNCH(m, k_addition, grid1d(y.numel(), 256, sm), 256, 0, st, x.p, y.p, (long long)x.n, (long long)x.c,
+                                          (long long)x.h, (long long)x.w, n.add_dim, n.add_chunk);
+            break;
+        }
+        case K_GN: {
+            y = mk(dout);
+            const int N = (int)x.n, H = (int)x.h, W = (int)x.w, C = (int)x.c, G = n.groups;
+            const long long npix = (long long)H * W;
+            int chunks = (int)std::min<long long>(std::max<long long>(1, npix * C / 16384), (long long)std::max(1, 8 * sm / std::max(N, 1)));
+            const int cthreads = std::min(C, 256), rows = std::max(1, 256 / cthreads), cpt = (C + cthreads - 1) / cthreads;
+            double *partial = (double *)m->arena.alloc((size_t)N * chunks * G * 2 * sizeof(double));
+            float2 *stats = (float2 *)m->arena.alloc((size_t)N * G * sizeof(float2));
+            bool ragged = false;
+            if (lens.has) for (int32_t l : lens.v) if (l < W) ragged = true;
+            int *dl = ragged ? dev_lens(lens) : nullptr;
+            if (!dry && y.numel()) {
+                const int bt = rows * cthreads;
+                LAUNCH(m, k_gn_partial, dim3(chunks, N), bt, (size_t)bt * cpt * 2 * sizeof(double), st, x.p, partial, H, W, C, G, dl, chunks, rows, cthreads, cpt);
+                LAUNCH(m, k_gn_finalize, (unsigned)((N * G + 127) / 128), 128, 0, st, partial, stats, N, G, chunks, H, W, C, dl, 1e-5f);
+                LAUNCH(m, k_gn_apply, grid1d(y.numel(), 256, sm), 256, 0, st, x.p, y.p, stats, w.aux, w.bias, (long long)y.numel(), H, W, C, G, dl);
+            }
+            break;
+        }
+        case K_LSTM: {
+            const int dirs = n.bidi ? 2 : 1, hid = n.hidden;
+            const bool packed = !n.transpose && lens.has;
+            if (packed && x.h != 1)
+                throw ShapeError("Height has to be 1 (not " + std::to_string(x.h) + ") for batching/multi-sequences.");   // layers.py:529-530
+            if (n.summarize && !n.transpose && lens.has) {
+                int32_t mx = 0; for (int32_t l : lens.v) mx = std::max(mx, l);
+                if (mx > 1) throw ShapeError("Do not use summarizing layer in x-axis with batching/sequences");           // layers.py:545-546
+            }
+            Dims dg = din; dg.c = dirs * 4 * hid;
+            Tensor gx = mk(dg);
+            Dims dfull = din; dfull.c = dirs * hid;
+            Tensor full = mk(dfull);
+            int *dl = packed ? dev_lens(lens) : nullptr;
+            if (!dry && full.numel()) {
+                { StageTimer tt(m, st, n.name + ".xproj", true); gemm(x, w, nullptr, ACT_LINEAR, gx.p, x.h, x.w); }
+                StageTimer tt(m, st, n.name + ".rec", true);
+                LstmParams lp;
+                lp.gx = gx.p; lp.whh = w.aux; lp.out = full.p; lp.lens = dl; lp.hid = hid; lp.dirs = dirs;
+                if (!n.transpose) { lp.nseq = (int)(x.n * x.h); lp.T = (int)x.w; lp.q2 = 1; lp.s_outer = x.w; lp.s_inner = 0; lp.step = 1; }
+                else { lp.nseq = (int)(x.n * x.w); lp.T = (int)x.h; lp.q2 = (int)x.w; lp.s_outer = x.h * x.w; lp.s_inner = 1; lp.step = x.w; }
+                const int ks = hid <= 32 ? 1 : hid <= 64 ? 2 : hid <= 128 ? 4 : 8;
+                lp.U = (hid + ks - 1) / ks;
+                const int BL = 64 / ks;
+                const int nchunks = (lp.nseq + BL - 1) / BL;
+                cudaLaunchConfig_t cfg = {};
+                cfg.gridDim = dim3((unsigned)(ks * nchunks), (unsigned)dirs, 1);
+                cfg.blockDim = dim3(256, 1, 1);
+                cfg.dynamicSmemBytes = 0; cfg.stream = st;
+                cudaLaunchAttribute at[1];
+                at[0].id = cudaLaunchAttributeClusterDimension;
+                at[0].val.clusterDim.x = (unsigned)ks; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+                cfg.attrs = at; cfg.numAttrs = 1;
+                switch (ks) {
+                case 1: CK(cudaLaunchKernelEx(&cfg, k_lstm_rec<1>, lp)); break;
+                case 2: CK(cudaLaunchKernelEx(&cfg, k_lstm_rec<2>, lp)); break;
+                case 4: CK(cudaLaunchKernelEx(&cfg, k_lstm_rec<4>, lp)); break;
+                default: CK(cudaLaunchKernelEx(&cfg, k_lstm_rec<8>, lp)); break;
+                }
+                ++m->launches;
+                CK(cudaPeekAtLastError());
+            }
+            if (n.summarize) {
+                y = mk(dout);
+                if (!dry && y.numel()) LAUNCH(m, k_take_last, grid1d(y.numel(), 256, sm), 256, 0, st, full.p, y.p, (int)full.n, (int)full.h, (int)full.w, (int)full.c, n.transpose ? 1 : 0);
+            } else y = full;
+            break;
+        }
+        default: throw Unsupported("layer kind not implemented");
+        }
+        if (lens.has) for (auto &l : lens.v) l = leaf_len(n, l, din, dout);
+        return y;
+    }
+
+    Tensor run(const Node &n, const Tensor &x, Lens &lens) {
+        if (n.kind == K_SERIES) {
+            Tensor cur = x;
+            for (auto &c : n.children) cur = run(*c, cur, lens);
+            return cur;
+        }
+        if (n.kind == K_PARALLEL) {
+            std::vector<Tensor> outs; Lens last = lens; int64_t ctot = 0;
+            for (auto &c : n.children) {
+                Lens l = lens;
+                outs.push_back(run(*c, x, l));
+                last = l; ctot += outs.back().c;
+            }
+            for (auto &o : outs)
+                if (o.n != outs[0].n || o.h != outs[0].h || o.w != outs[0].w) throw ShapeError("Output shape in parallel block not equal!");
+            Dims d = dims_of(outs[0]); d.c = ctot;
+            Tensor y = mk(d);
+            int64_t off = 0;
+            for (auto &o : outs) {
+                if (!dry && o.numel()) LAUNCH(m, k_concat, grid1d(o.numel(), 256, m->sm_count), 256, 0, st, o.p, y.p, (long long)(o.n * o.h * o.w), (int)o.c, (int)ctot, (int)off);
+                off += o.c;
+            }
+            lens = last;
+            return y;
+        }
+        // leaf
+        Tensor y;
+        {
+            StageTimer tt(m, st, n.name, !dry && n.kind != K_LSTM && n.kind != K_DROPOUT && n.kind != K_IDENTITY);
+            y = leaf(n, x, lens);
+        }
+        if (!dry) m->taps[n.name] = y;
+        return y;
+    }
+};
+
+static void ensure_ready(kb_model *m) {
+    if (!m->finalized) throw SpecError("model not finalized: call kb_model_finalize() after loading weights");
+    CK(cudaSetDevice(m->device));
+}
+
+static void ensure_pinned(kb_model *m, size_t bytes) {
+    if (bytes <= m->pinned_cap) return;
+    if (m->pinned) cudaFreeHost(m->pinned);
+    m->pinned = nullptr; m->pinned_cap = 0;
+    CK(cudaHostAlloc(&m->pinned, bytes, cudaHostAllocDefault));
+    m->pinned_cap = bytes;
+}
+
+struct ForwardResult { Tensor y; Lens lens; };
+
+// Stages the NCHW input into the arena as NHWC, runs the net.  `extra_bytes`: additional arena space the
+// caller will allocate after the forward (decode buffers etc.).
+static ForwardResult forward_impl(kb_model *m, const float *x, int x_on_device, int n, int h, int w, const int32_t *widths,
+                                  cudaStream_t st, size_t extra_bytes) {
+    const Plan &pl = *m->plan;
+    const int C = pl.input[1];
+    if (n <= 0 || h <= 0 || w <= 0) throw ShapeError("empty input batch");
+    if (pl.input[2] > 0 && h != pl.input[2] && pl.input[2] != 1)
+        ;   // the reference does not check the declared height either; convs accept any H
+    Lens lens0;
+    if (widths) { lens0.has = true; lens0.v.assign(widths, widths + n); }
+    const size_t in_elems = (size_t)n * C * h * w;
+    // ---- pass 1: plan the arena
+    size_t need;
+    {
+        Arena saved = m->arena;
+        m->arena.dry = true; m->arena.off = 0;
+        Exec ex{m, st, true};
+        if (!x_on_device || C > 1) m->arena.alloc(in_elems * sizeof(float));      // staging of the raw input
+        if (C > 1) m->arena.alloc(in_elems * sizeof(float));
+        Tensor t; t.p = nullptr; t.n = n; t.c = C; t.h = h; t.w = w;
+        Lens l = lens0;
+        try { ex.run(*pl.root, t, l); } catch (...) { m->arena = saved; throw; }
+        need = m->arena.off + extra_bytes + (1 << 20);
+        m->arena = saved;
+    }
+    if (need > m->arena.cap) {
+        CK(cudaStreamSynchronize(st));
+        if (m->arena.base) CK(cudaFree(m->arena.base));
+        m->arena.base = nullptr; m->arena.cap = 0;
+        size_t cap = need + need / 4;
+        CK(cudaMalloc((void **)&m->arena.base, cap));
+        m->arena.cap = cap;
+    }
+    m->arena.dry = false; m->arena.off = 0;
+    m->taps.clear();
+    m->n_stages = 0;
+    // ---- stage input
+    Tensor t; t.n = n; t.c = C; t.h = h; t.w = w;
+    const float *src = x;
+    std::unique_ptr<StageTimer> t_in(new StageTimer(m, st, "stage_in", true));
+    if (!x_on_device) {
+        float *stg = (float *)m->arena.alloc(in_elems * sizeof(float));
+        CK(cudaMemcpyAsync(stg, x, in_elems * sizeof(float), cudaMemcpyHostToDevice, st));
+        src = stg;
+    } else if (C > 1) m->arena.alloc(in_elems * sizeof(float));   // keep offsets identical to the dry pass
+    if (C > 1) {
+        float *nhwc = (float *)m->arena.alloc(in_elems * sizeof(float));
+        dim3 grid((unsigned)((h * (long long)w + 31) / 32), (unsigned)((C + 31) / 32), (unsigned)n);
+        LAUNCH(m, k_transpose, grid, dim3(32, 8), 0, st, src, nhwc, C, h * w);
+        t.p = nhwc;
+    } else t.p = const_cast<float *>(src);
+    t_in.reset();
+    Exec ex{m, st, false};
+    ForwardResult r; r.lens = lens0;
+    r.y = ex.run(*pl.root, t, r.lens);
+    return r;
+}
+
+static void collect_timing(kb_model *m) {
+    if (!m->timing) return;
+    for (size_t i = 0; i < m->n_stages; ++i) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, m->stages[i].a, m->stages[i].b) == cudaSuccess) m->stages[i].ms = ms;
+        else { cudaGetLastError(); m->stages[i].ms = 0.f; }
+    }
+}
+
+// NHWC device tensor -> NCHW destination (device or host)
+static void emit_nchw(kb_model *m, const Tensor &y, float *out, int out_on_device, cudaStream_t st) {
+    const size_t elems = (size_t)y.numel();
+    if (!elems) return;
+    float *dst = out_on_device ? out : (float *)m->arena.alloc(elems * sizeof(float));
+    if (y.c == 1) CK(cudaMemcpyAsync(dst, y.p, elems * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    else {
+        const int R = (int)(y.h * y.w), Cc = (int)y.c;
+        dim3 grid((unsigned)((Cc + 31) / 32), (unsigned)((R + 31) / 32), (unsigned)y.n);
+        LAUNCH(m, k_transpose, grid, dim3(32, 8), 0, st, y.p, dst, R, Cc);
+    }
+    if (!out_on_device) CK(cudaMemcpyAsync(out, dst, elems * sizeof(float), cudaMemcpyDeviceToHost, st));
+}
+
+template <typename F>
+static int guarded(F &&f) {
+    try { return f(); }
+    catch (const SpecError &e) { return fail(KB_ERR_SPEC, e.what()); }
+    catch (const ShapeError &e) { return fail(KB_ERR_SHAPE, e.what()); }
+    catch (const Unsupported &e) { return fail(KB_ERR_UNSUPPORTED, e.what()); }
+    catch (const CudaError &e) { cudaGetLastError(); return fail(KB_ERR_CUDA, e.what()); }
+    catch (const std::bad_alloc &) { return fail(KB_ERR_STATE, "out of host memory"); }
+    catch (const std::exception &e) { return fail(KB_ERR_STATE, e.what()); }
+}
+
+struct DecodeBufs { int *lab; float *conf; int *o_lab, *o_start, *o_end; float *o_conf; int *o_cnt; size_t out_bytes; };
+
+static size_t decode_bytes(int n, int T, int max_out) {
+    return (size_t)n * T * 8 + (size_t)n * max_out * 16 + (size_t)n * 4 + 8 * 256;
+}
+
+// runs the collapse and copies the fixed-stride result block back to the caller's host arrays
+static void decode_and_fetch(kb_model *m, int dev_sm, int n, int T, int max_out, const int *d_lab, const float *d_conf, const int *d_lens,
+                             int32_t *labels, int32_t *starts, int32_t *ends, float *confs, int32_t *counts, cudaStream_t st,
+                             Arena &arena, void **pinned, size_t *pinned_cap, int64_t *launches, StageTimer *timer = nullptr) {
+    (void)dev_sm; (void)m;
+    const size_t per = (size_t)n * max_out;
+    const size_t blk = per * 16 + (size_t)n * 4;
+    char *d = (char *)arena.alloc(blk);
+    int *o_lab = (int *)d, *o_start = (int *)(d + per * 4), *o_end = (int *)(d + per * 8);
+    float *o_conf = (float *)(d + per * 12); int *o_cnt = (int *)(d + per * 16);
+    k_ctc_collapse<<<(unsigned)((n + 3) / 4), 128, 0, st>>>(d_lab, d_conf, d_lens, n, T, max_out, o_lab, o_start, o_end, o_conf, o_cnt);
+    ++*launches;
+    CK(cudaPeekAtLastError());
+    if (blk > *pinned_cap) {
+        if (*pinned) cudaFreeHost(*pinned);
+        *pinned = nullptr; *pinned_cap = 0;
+        CK(cudaHostAlloc(pinned, blk, cudaHostAllocDefault));
+        *pinned_cap = blk;
+    }
+    CK(cudaMemcpyAsync(*pinned, d, blk, cudaMemcpyDeviceToHost, st));
+    if (timer && timer->idx >= 0) { cudaEventRecord(timer->m->stages[timer->idx].b, st); timer->idx = -1; }
+    CK(cudaStreamSynchronize(st));
+    const char *hsrc = (const char *)*pinned;
+    // only the valid prefix of every line is defined on the device; zero the rest for the caller
+    const int32_t *h_cnt = (const int32_t *)(hsrc + per * 16);
+    for (int i = 0; i < n; ++i) {
+        const int c = std::min<int>(h_cnt[i], max_out);
+        counts[i] = h_cnt[i];
+        const size_t o = (size_t)i * max_out;
+        memcpy(labels + o, hsrc + o * 4, (size_t)c * 4); memset(labels + o + c, 0, (size_t)(max_out - c) * 4);
+        memcpy(starts + o, hsrc + per * 4 + o * 4, (size_t)c * 4); memset(starts + o + c, 0, (size_t)(max_out - c) * 4);
+        memcpy(ends + o, hsrc + per * 8 + o * 4, (size_t)c * 4); memset(ends + o + c, 0, (size_t)(max_out - c) * 4);
+        memcpy(confs + o, hsrc + per * 12 + o * 4, (size_t)c * 4); memset(confs + o + c, 0, (size_t)(max_out - c) * 4);
+    }
+}
+
+}  // namespace kb
+
+// =================================================================================================
+// C ABI
+// =================================================================================================
+extern "C" {
+
+int kb_abi_version(void) { return KB_ABI_VERSION; }
+const char *kb_last_error(void) { return g_err.c_str(); }
+int kb_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int kb_model_create(const char *vgsl_spec, kb_model **out) {
+    if (!out) return fail(KB_ERR_ARG, "out is NULL");
+    *out = nullptr;
+    if (!vgsl_spec) return fail(KB_ERR_SPEC, "vgsl specification argument is missing in args.");
+    return guarded([&]() {
+        auto m = std::make_unique<kb_model>();
+        m->plan = parse_spec(vgsl_spec);
+        m->lw.resize(m->plan->leaf_nodes.size());
+        for (auto &t : m->plan->tensors) {
+            LeafWeights &w = m->lw[t.leaf];
+            if ((int)w.host.size() <= t.slot) { w.host.resize(t.slot + 1); w.loaded.resize(t.slot + 1, false); }
+        }
+        *out = m.release();
+        return KB_OK;
+    });
+}
+void kb_model_destroy(kb_model *m) { delete m; }
+
+int kb_model_named_spec(const kb_model *m, char *buf, size_t cap) {
+    if (!m) return -fail(KB_ERR_ARG, "model is NULL");
+    const std::string &s = m->plan->named_spec;
+    if (buf && cap) { size_t k = std::min(cap - 1, s.size()); memcpy(buf, s.data(), k); buf[k] = 0; }
+    return (int)s.size();
+}
+int kb_model_input_shape(const kb_model *m, int32_t shape[4]) {
+    if (!m || !shape) return fail(KB_ERR_ARG, "NULL argument");
+    for (int i = 0; i < 4; ++i) shape[i] = m->plan->input[i];
+    return KB_OK;
+}
+int kb_model_output_shape(const kb_model *m, int32_t shape[4]) {
+    if (!m || !shape) return fail(KB_ERR_ARG, "NULL argument");
+    for (int i = 0; i < 4; ++i) shape[i] = m->plan->output[i];
+    return KB_OK;
+}
+int kb_model_num_layers(const kb_model *m) { return m ? (int)m->plan->leaf_nodes.size() : -1; }
+int kb_model_layer_info(const kb_model *m, int index, kb_layer_info *info) {
+    if (!m || !info) return fail(KB_ERR_ARG, "NULL argument");
+    if (index < 0 || index >= (int)m->plan->leaf_nodes.size()) return fail(KB_ERR_ARG, "layer index out of range");
+    const Node &n = *m->plan->leaf_nodes[index];
+    memset(info, 0, sizeof(*info));
+    info->kind = n.kind;
+    for (int i = 0; i < 4; ++i) info->out_shape[i] = n.out_shape[i];
+    snprintf(info->name, sizeof(info->name), "%s", n.name.c_str());
+    snprintf(info->path, sizeof(info->path), "%s", n.path.c_str());
+    snprintf(info->block, sizeof(info->block), "%s", n.block.c_str());
+    return KB_OK;
+}
+int kb_model_num_tensors(const kb_model *m) { return m ? (int)m->plan->tensors.size() : -1; }
+int kb_model_tensor_info(const kb_model *m, int index, char *name, size_t cap, int64_t shape[4], int32_t *ndim) {
+    if (!m) return fail(KB_ERR_ARG, "NULL argument");
+    if (index < 0 || index >= (int)m->plan->tensors.size()) return fail(KB_ERR_ARG, "tensor index out of range");
+    const TensorDecl &t = m->plan->tensors[index];
+    if (name && cap) snprintf(name, cap, "%s", t.name.c_str());
+    if (shape) for (size_t i = 0; i < 4; ++i) shape[i] = i < t.shape.size() ? t.shape[i] : 1;
+    if (ndim) *ndim = (int)t.shape.size();
+    return KB_OK;
+}
+
+static void infer(const Node &n, Dims &d, Lens &l) {
+    if (n.kind == K_SERIES) { for (auto &c : n.children) infer(*c, d, l); return; }
+    if (n.kind == K_PARALLEL) {
+        Dims first; Lens last = l; int64_t ctot = 0; bool have = false;
+        for (auto &c : n.children) {
+            Dims dc = d; Lens lc = l; infer(*c, dc, lc);
+            if (have && (dc.h != first.h || dc.w != first.w)) throw ShapeError("Output shape in parallel block not equal!");
+            first = dc; have = true; ctot += dc.c; last = lc;
+        }
+        d = first; d.c = ctot; l = last; return;
+    }
+    Dims o = leaf_dims(n, d);
+    if (n.kind == K_LSTM && !n.transpose && l.has && d.h != 1)
+        throw ShapeError("Height has to be 1 (not " + std::to_string(d.h) + ") for batching/multi-sequences.");
+    if (l.has) for (auto &v : l.v) v = leaf_len(n, v, d, o);
+    d = o;
+}
+
+int kb_model_infer_dims(const kb_model *m, int32_t n, int32_t h, int32_t w, int32_t out_nchw[4]) {
+    if (!m || !out_nchw) return fail(KB_ERR_ARG, "NULL argument");
+    return guarded([&]() {
+        Dims d; d.n = n; d.c = m->plan->input[1]; d.h = h; d.w = w; Lens l;
+        infer(*m->plan->root, d, l);
+        out_nchw[0] = (int32_t)d.n; out_nchw[1] = (int32_t)d.c; out_nchw[2] = (int32_t)d.h; out_nchw[3] = (int32_t)d.w;
+        return KB_OK;
+    });
+}
+int kb_model_infer_lens(const kb_model *m, int32_t n, int32_t h, int32_t w, const int32_t *widths, int32_t *out_lens) {
+    if (!m || !widths || !out_lens) return fail(KB_ERR_ARG, "NULL argument");
+    return guarded([&]() {
+        Dims d; d.n = n; d.c = m->plan->input[1]; d.h = h; d.w = w; Lens l; l.has = true; l.v.assign(widths, widths + n);
+        infer(*m->plan->root, d, l);
+        for (int i = 0; i < n; ++i) out_lens[i] = l.v[i];
+        return KB_OK;
+    });
+}
+
+int kb_model_load_tensor(kb_model *m, const char *name, const float *data, const int64_t *shape, int32_t ndim) {
+    if (!m || !name || !data || !shape) return fail(KB_ERR_ARG, "NULL argument");
+    std::lock_guard<std::mutex> lk(m->mu);
+    for (auto &t : m->plan->tensors) {
+        if (t.name != name) continue;
+        if ((int)t.shape.size() != ndim) return fail(KB_ERR_ARG, std::string("size mismatch for ") + name + ": wrong rank");
+        size_t elems = 1;
+        for (int i = 0; i < ndim; ++i) {
+            if (t.shape[i] != shape[i]) return fail(KB_ERR_ARG, std::string("size mismatch for ") + name);
+            elems *= (size_t)shape[i];
+        }
+        LeafWeights &w = m->lw[t.leaf];
+        w.host[t.slot].assign(data, data + elems);
+        w.loaded[t.slot] = true;
+        m->finalized = false;
+        return KB_OK;
+    }
+    return fail(KB_ERR_ARG, std::string("unexpected key ") + name);
+}
+
+int kb_model_finalize(kb_model *m, int device) {
+    if (!m) return fail(KB_ERR_ARG, "model is NULL");
+    std::lock_guard<std::mutex> lk(m->mu);
+    return guarded([&]() {
+        int cnt = 0;
+        if (cudaGetDeviceCount(&cnt) != cudaSuccess || cnt == 0) {
+            cudaGetLastError();
+            throw CudaError("no CUDA device available: kraken_b200 has no CPU fallback");
+        }
+        if (device < 0 || device >= cnt) throw CudaError("invalid device ordinal " + std::to_string(device));
+        if (m->device >= 0 && m->device != device) {
+            CK(cudaSetDevice(m->device));
+            for (void *p : m->dev_allocs) cudaFree(p);
+            m->dev_allocs.clear();
+            if (m->arena.base) cudaFree(m->arena.base);
+            m->arena = Arena();
+            if (m->pinned) cudaFreeHost(m->pinned);
+            m->pinned = nullptr; m->pinned_cap = 0;
+            for (auto &e : m->stages) { if (e.a) cudaEventDestroy(e.a); if (e.b) cudaEventDestroy(e.b); }
+            m->stages.clear(); m->n_stages = 0;
+        }
+        CK(cudaSetDevice(device));
+        cudaDeviceProp prop;
+        CK(cudaGetDeviceProperties(&prop, device));
+        if (prop.major < 10) throw CudaError(std::string("device ") + prop.name + " is not a Blackwell (sm_100) GPU; this library only carries sm_100a code");
+        m->sm_count = prop.multiProcessorCount;
+        m->device = device;
+        finalize_weights(m);
+        m->finalized = true;
+        return KB_OK;
+    });
+}
+int kb_model_device(const kb_model *m) { return m && m->finalized ? m->device : -1; }
+
+int kb_forward(kb_model *m, const float *x, int x_on_device, int32_t n, int32_t h, int32_t w, const int32_t *widths,
+               float *out, int out_on_device, int32_t *out_lens, void *stream) {
+    if (!m || !x || !out) return fail(KB_ERR_ARG, "NULL argument");
+    std::lock_guard<std::mutex> lk(m->mu);
+    return guarded([&]() {
+        ensure_ready(m);
+        cudaStream_t st = (cudaStream_t)stream;
+        Dims d; d.n = n; d.c = m->plan->input[1]; d.h = h; d.w = w; Lens l;
+        infer(*m->plan->root, d, l);
+        ForwardResult r = forward_impl(m, x, x_on_device, n, h, w, widths, st, out_on_device ? 0 : (size_t)(d.n * d.c * d.h * d.w) * 4 + 4096);
+        { StageTimer tt(m, st, "emit", true); emit_nchw(m, r.y, out, out_on_device, st); }
+        if (out_lens) {
+            if (r.lens.has) for (int i = 0; i < n; ++i) out_lens[i] = r.lens.v[i];
+            else for (int i = 0; i < n; ++i) out_lens[i] = (int32_t)r.y.w;
+        }
+        if (!out_on_device || m->timing) CK(cudaStreamSynchronize(st));
+        collect_timing(m);
+        return KB_OK;
+    });
+}
+
+int kb_recognize(kb_model *m, const float *lines, int lines_on_device, int32_t n, int32_t h, int32_t w, const int32_t *widths,
+                 float temperature, int32_t *labels, int32_t *starts, int32_t *ends, float *confs, int32_t *counts,
+                 int32_t max_out, int32_t *out_lens, float *probs, int probs_on_device, void *stream) {
+    if (!m || !lines || !labels || !starts || !ends || !confs || !counts) return fail(KB_ERR_ARG, "NULL argument");
+    if (max_out <= 0) return fail(KB_ERR_ARG, "max_out must be positive");
+    if (!(temperature > 0.f)) return fail(KB_ERR_ARG, "temperature must be positive");
+    std::lock_guard<std::mutex> lk(m->mu);
+    return guarded([&]() {
+        ensure_ready(m);
+        cudaStream_t st = (cudaStream_t)stream;
+        Dims d; d.n = n; d.c = m->plan->input[1]; d.h = h; d.w = w; Lens l;
+        infer(*m->plan->root, d, l);
+        if (d.h != 1)
+            throw ShapeError("Expected dimension 3 to be 1, actual (" + std::to_string(d.n) + ", " + std::to_string(d.c) + ", " + std::to_string(d.h) + ", " + std::to_string(d.w) + ")");
+        const int T = (int)d.w, C = (int)d.c;
+        size_t extra = decode_bytes(n, T, max_out) + (probs && !probs_on_device ? (size_t)n * C * T * 4 + 4096 : 0);
+        ForwardResult r = forward_impl(m, lines, lines_on_device, n, h, w, widths, st, extra);
+        std::unique_ptr<StageTimer> t_dec(new StageTimer(m, st, "decode", true));
+        const long long rows = (long long)n * T;
+        int *d_lab = (int *)m->arena.alloc((size_t)rows * 4);
+        float *d_conf = (float *)m->arena.alloc((size_t)rows * 4);
+        LAUNCH(m, k_row_argmax_softmax, (unsigned)((rows + 7) / 8), 256, 0, st, r.y.p, rows, C, temperature, d_lab, d_conf);
+        std::vector<int32_t> olens(n);
+        for (int i = 0; i < n; ++i) olens[i] = r.lens.has ? r.lens.v[i] : T;
+        int *d_lens = (int *)m->arena.alloc((size_t)n * 4);
+        CK(cudaMemcpyAsync(d_lens, olens.data(), (size_t)n * 4, cudaMemcpyHostToDevice, st));
+        if (probs) {
+            float *dp = probs_on_device ? probs : (float *)m->arena.alloc((size_t)n * C * T * 4);
+            const size_t smem = (size_t)32 * (C + 1) * 4;
+            if (smem <= 48 * 1024) LAUNCH(m, k_probs_nct, dim3((unsigned)((T + 31) / 32), (unsigned)n), 256, smem, st, r.y.p, dp, T, C, temperature);
+            else LAUNCH(m, k_probs_nct_simple, (unsigned)((rows + 7) / 8), 256, 0, st, r.y.p, dp, n, T, C, temperature);
+            if (!probs_on_device) CK(cudaMemcpyAsync(probs, dp, (size_t)n * C * T * 4, cudaMemcpyDeviceToHost, st));
+        }
+        decode_and_fetch(m, m->sm_count, n, T, max_out, d_lab, d_conf, d_lens, labels, starts, ends, confs, counts, st,
+                         m->arena, &m->pinned, &m->pinned_cap, &m->launches, t_dec.get());
+        if (out_lens) for (int i = 0; i < n; ++i) out_lens[i] = olens[i];
+        collect_timing(m);
+        return KB_OK;
+    });
+}
+
+int kb_ctc_greedy_decode(const float *probs, int probs_on_device, int32_t n, int32_t c, int32_t w, const int32_t *lens,
+                         int32_t *labels, int32_t *starts, int32_t *ends, float *confs, int32_t *counts, int32_t max_out,
+                         int device, void *stream) {
+    if (!probs || !labels || !starts || !ends || !confs || !counts) return fail(KB_ERR_ARG, "NULL argument");
+    if (n <= 0 || c <= 0 || w < 0 || max_out <= 0) return fail(KB_ERR_ARG, "invalid sizes");
+    if (!lens && n != 1) return fail(KB_ERR_ARG, "seq_lens need to be set for batch decoding.");    // ctc_decoder.py:60-61
+    return guarded([&]() {
+        int cnt = 0;
+        if (cudaGetDeviceCount(&cnt) != cudaSuccess || cnt == 0) { cudaGetLastError(); throw CudaError("no CUDA device available: kraken_b200 has no CPU fallback"); }
+        CK(cudaSetDevice(device));
+        cudaStream_t st = (cudaStream_t)stream;
+        if (w == 0) { for (int i = 0; i < n; ++i) counts[i] = 0; return (int)KB_OK; }
+        Arena ar;
+        const size_t in_bytes = (size_t)n * c * w * 4;
+        size_t total = (probs_on_device ? 0 : in_bytes) + decode_bytes(n, w, max_out) + 8192;
+        CK(cudaMalloc((void **)&ar.base, total)); ar.cap = total;
+        void *pinned = nullptr; size_t pcap = 0; int64_t launches = 0;
+        try {
+            const float *dp = probs;
+            if (!probs_on_device) { float *t = (float *)ar.alloc(in_bytes); CK(cudaMemcpyAsync(t, probs, in_bytes, cudaMemcpyHostToDevice, st)); dp = t; }
+            int *d_lab = (int *)ar.alloc((size_t)n * w * 4); float *d_conf = (float *)ar.alloc((size_t)n * w * 4);
+            int *d_lens = nullptr;
+            if (lens) { d_lens = (int *)ar.alloc((size_t)n * 4); CK(cudaMemcpyAsync(d_lens, lens, (size_t)n * 4, cudaMemcpyHostToDevice, st)); }
+            k_col_argmax<<<(unsigned)(((long long)n * w + 255) / 256), 256, 0, st>>>(dp, n, c, w, d_lab, d_conf);
+            CK(cudaPeekAtLastError());
+            decode_and_fetch(nullptr, 0, n, w, max_out, d_lab, d_conf, d_lens, labels, starts, ends, confs, counts, st, ar, &pinned, &pcap, &launches);
+        } catch (...) { cudaFree(ar.base); if (pinned) cudaFreeHost(pinned); throw; }
+        cudaFree(ar.base); if (pinned) cudaFreeHost(pinned);
+        return (int)KB_OK;
+    });
+}
+
+int kb_segment(kb_model *m, const float *pages, int pages_on_device, int32_t n, int32_t h, int32_t w, int32_t out_h, int32_t out_w,
+               float *heatmap, int heatmap_on_device, void *stream) {
+    if (!m || !pages || !heatmap) return fail(KB_ERR_ARG, "NULL argument");
+    if (out_h <= 0 || out_w <= 0) return fail(KB_ERR_ARG, "invalid output size");
+    std::lock_guard<std::mutex> lk(m->mu);
+    return guarded([&]() {
+        ensure_ready(m);
+        cudaStream_t st = (cudaStream_t)stream;
+        Dims d; d.n = n; d.c = m->plan->input[1]; d.h = h; d.w = w; Lens l;
+        infer(*m->plan->root, d, l);
+        const size_t out_elems = (size_t)n * d.c * out_h * out_w;
+        ForwardResult r = forward_impl(m, pages, pages_on_device, n, h, w, nullptr, st, heatmap_on_device ? 0 : out_elems * 4 + 4096);
+        std::unique_ptr<StageTimer> t_up(new StageTimer(m, st, "upsample_sigmoid", true));
+        float *dst = heatmap_on_device ? heatmap : (float *)m->arena.alloc(out_elems * 4);
+        LAUNCH(m, k_upsample_sigmoid, grid1d((long long)n * out_h * out_w, 256, m->sm_count), 256, 0, st, r.y.p, dst, (int)r.y.n, (int)r.y.h,
+               (int)r.y.w, (int)r.y.c, out_h, out_w);
+        if (!heatmap_on_device) CK(cudaMemcpyAsync(heatmap, dst, out_elems * 4, cudaMemcpyDeviceToHost, st));
+        t_up.reset();
+        if (!heatmap_on_device || m->timing) CK(cudaStreamSynchronize(st));
+        collect_timing(m);
+        return KB_OK;
+    });
+}
+
+int kb_debug_layer_output(kb_model *m, const char *name, int32_t dims[4], float *out_host, int dims_only) {
+    if (!m || !name || !dims) return fail(KB_ERR_ARG, "NULL argument");
+    std::lock_guard<std::mutex> lk(m->mu);
+    return guarded([&]() {
+        ensure_ready(m);
+        auto it = m->taps.find(name);
+        if (it == m->taps.end()) throw SpecError(std::string("no output recorded for layer ") + name);
+        const Tensor &t = it->second;
+        dims[0] = (int32_t)t.n; dims[1] = (int32_t)t.c; dims[2] = (int32_t)t.h; dims[3] = (int32_t)t.w;
+        if (dims_only || !out_host) return (int)KB_OK;
+        const size_t elems = (size_t)t.numel();
+        if (!elems) return (int)KB_OK;
+        float *tmp = nullptr;
+        CK(cudaMalloc(&tmp, elems * 4));
+        cudaError_t e = cudaSuccess;
+        if (t.c == 1) e = cudaMemcpy(tmp, t.p, elems * 4, cudaMemcpyDeviceToDevice);
+        else {
+            const int R = (int)(t.h * t.w), Cc = (int)t.c;
+            dim3 grid((unsigned)((Cc + 31) / 32), (unsigned)((R + 31) / 32), (unsigned)t.n);
+            k_transpose<<<grid, dim3(32, 8)>>>(t.p, tmp, R, Cc);
+            e = cudaDeviceSynchronize();
+        }
+        if (e == cudaSuccess) e = cudaMemcpy(out_host, tmp, elems * 4, cudaMemcpyDeviceToHost);
+        cudaFree(tmp);
+        if (e != cudaSuccess) throw CudaError(std::string("layer output copy failed: ") + cudaGetErrorString(e));
+        return (int)KB_OK;
+    });
+}
+
+int64_t kb_launch_count(const kb_model *m) { return m ? m->launches : 0; }
+void kb_reset_launch_count(kb_model *m) { if (m) m->launches = 0; }
+int kb_set_timing(kb_model *m, int enabled) { if (!m) return fail(KB_ERR_ARG, "model is NULL"); m->timing = enabled != 0; return KB_OK; }
+int kb_timing_count(kb_model *m) {
+    if (!m) return -1;
+    std::lock_guard<std::mutex> lk(m->mu);
+    return m->timing ? (int)m->n_stages : 0;
+}
+int kb_timing_entry(kb_model *m, int index, char *name, size_t cap, float *ms) {
+    if (!m) return fail(KB_ERR_ARG, "model is NULL");
+    std::lock_guard<std::mutex> lk(m->mu);
+    if (index < 0 || index >= (int)m->n_stages) return fail(KB_ERR_ARG, "timing index out of range");
+    if (name && cap) snprintf(name, cap, "%s", m->stages[index].name.c_str());
+    if (ms) *ms = m->stages[index].ms;
+    return KB_OK;
+}
+
+}  // extern "C"

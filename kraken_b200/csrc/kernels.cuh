@@ -1,0 +1,647 @@
+// kernels.cuh - sm_100a device code of the kraken_b200 engine (fp32-exact path).
+//
+// Activations are NHWC fp32 in HBM ("pixel-major, feature-minor"): that is the layout in which
+//   * a VGSL conv is an implicit GEMM  [N*Ho*Wo pixels] x [kh*kw*Cin] x [Cout]   with unit-stride K,
+//   * the LSTM input projection and the output Linear are plain per-pixel GEMMs,
+//   * an `Lbx`/`Lby` recurrence walks pixels with a constant stride,
+//   * `S1(1x0)1,3` (fold H into the feature axis) is a permutation of whole feature rows.
+// The reference is NCHW (kraken/lib/vgsl/layers.py:34-35); conversion happens once at the ABI edge.
+//
+// Arithmetic: everything here is IEEE fp32 FMA with accurate expf/tanhf, because CTC label sequences
+// have to be bit-identical to the fp32 reference and a random-weight model has top-2 logit gaps down to
+// 1e-4 (SURVEY.md 7 "hard parts").  The tensor-core GEMM (3xTF32 split on tcgen05) lives in
+// gemm_tc.cuh and replaces k_conv_gemm for the shapes it supports.
+#pragma once
+#include <cooperative_groups.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace kb {
+namespace cg = cooperative_groups;
+
+enum { DACT_LINEAR = 0, DACT_SIGMOID_LOGITS = 1, DACT_TANH = 2, DACT_SOFTMAX = 3, DACT_RELU = 4, DACT_LEAKY = 5 };
+
+__device__ __forceinline__ float act_apply(float v, int act) {
+    switch (act) {
+    case DACT_RELU: return v > 0.f ? v : 0.f;                 // torch.relu: NaN propagates through the compare as in ATen
+    case DACT_TANH: return tanhf(v);
+    case DACT_LEAKY: return v > 0.f ? v : 0.01f * v;          // nn.LeakyReLU() default slope (layers.py:821)
+    default: return v;                                        // linear, sigmoid-as-logits (layers.py:850-852), softmax (separate pass)
+    }
+}
+__device__ __forceinline__ float sigmoidf_acc(float x) { return 1.f / (1.f + expf(-x)); }
+
+// =============================================================================================
+// batched transpose  in[B][R][C] -> out[B][C][R]   (NCHW <-> NHWC at the ABI edge)
+// =============================================================================================
+__global__ void k_transpose(const float *__restrict__ in, float *__restrict__ out, int R, int C) {
+    __shared__ float tile[32][33];
+    const size_t b = blockIdx.z;
+    const float *src = in + b * (size_t)R * C;
+    float *dst = out + b * (size_t)R * C;
+    int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        int r = r0 + i, c = c0 + threadIdx.x;
+        if (r < R && c < C) tile[i][threadIdx.x] = src[(size_t)r * C + c];
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        int c = c0 + i, r = r0 + threadIdx.x;
+        if (r < R && c < C) dst[(size_t)c * R + r] = tile[threadIdx.x][i];
+    }
+}
+
+// =============================================================================================
+// implicit-GEMM convolution / per-pixel linear  (fp32 FFMA)
+//   y[m][n] = act( sum_k A[m][k] * Wt[k][n] + bias[n] ),  m = (img, ho, wo), k = (ky, kx, ci)
+// ActConv2D.forward (layers.py:842-852) incl. zero padding (dil*(k-1))//2, stride, dilation;
+// LinSoftmax (layers.py:710-722) and the LSTM input projection are the kh=kw=1 case.
+// =============================================================================================
+struct ConvParams {
+    const float *x; const float *wt; const float *bias; float *y;
+    int N, H, W, Cin, Ho, Wo, Cout, Ncp;
+    int kh, kw, sy, sx, dy, dx, py, px;
+    int K; long long M; int act;
+};
+
+constexpr int CG_BM = 128, CG_BN = 64, CG_BK = 16, CG_NT = 256, CG_LDA = CG_BK + 4;
+
+template <bool VEC4>
+__global__ void __launch_bounds__(CG_NT, 2) k_conv_gemm(ConvParams p) {
+    __shared__ __align__(16) float As[2][CG_BM][CG_LDA];
+    __shared__ __align__(16) float Bs[2][CG_BK][CG_BN];
+    const int tid = threadIdx.x;
+    const long long m0 = (long long)blockIdx.x * CG_BM;
+    const int n0 = blockIdx.y * CG_BN;
+    const int tx = tid & 15, ty = tid >> 4;
+
+    // ---- A-load bookkeeping: VEC4 -> 2 rows x one k-quad per thread; scalar -> 8 rows x one k per thread
+    constexpr int AR = VEC4 ? 2 : 8;
+    const int a_k = VEC4 ? (tid & 3) * 4 : (tid & 15);
+    const int a_r0 = VEC4 ? (tid >> 2) : (tid >> 4);
+    constexpr int a_rstep = VEC4 ? 64 : 16;
+    long long a_base[AR]; int a_hi0[AR], a_wi0[AR]; bool a_ok[AR];
+#pragma unroll
+    for (int j = 0; j < AR; ++j) {
+        long long m = m0 + a_r0 + j * a_rstep;
+        a_ok[j] = m < p.M;
+        long long mm = a_ok[j] ? m : 0;
+        int wo = (int)(mm % p.Wo); long long t = mm / p.Wo;
+        int ho = (int)(t % p.Ho); long long img = t / p.Ho;
+        a_base[j] = img * (long long)p.H * p.W * p.Cin;
+        a_hi0[j] = ho * p.sy - p.py; a_wi0[j] = wo * p.sx - p.px;
+    }
+    const int b_k = tid >> 4, b_n = (tid & 15) * 4;
+
+    float4 ra4[VEC4 ? 2 : 1]; float ra1[VEC4 ? 1 : 8]; float4 rb;
+
+    auto load_tile = [&](int kt) {
+        const int k = kt * CG_BK + a_k;
+        int ci = 0, kx = 0, ky = 0;
+        const bool kok = k < p.K;
+        if (kok) { ci = k % p.Cin; int kk = k / p.Cin; kx = kk % p.kw; ky = kk / p.kw; }
+#pragma unroll
+        for (int j = 0; j < AR; ++j) {
+            const int hi = a_hi0[j] + ky * p.dy, wi = a_wi0[j] + kx * p.dx;
+            const bool ok = kok && a_ok[j] && hi >= 0 && hi < p.H && wi >= 0 && wi < p.W;
+            const float *src = p.x + a_base[j] + ((long long)hi * p.W + wi) * p.Cin + ci;
+            if constexpr (VEC4) ra4[j] = ok ? __ldg(reinterpret_cast<const float4 *>(src)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            else ra1[j] = ok ? __ldg(src) : 0.f;
+        }
+        const int kb = kt * CG_BK + b_k;
+        rb = kb < p.K ? __ldg(reinterpret_cast<const float4 *>(p.wt + (size_t)kb * p.Ncp + n0 + b_n)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    };
+    auto store_tile = [&](int buf) {
+#pragma unroll
+        for (int j = 0; j < AR; ++j) {
+            if constexpr (VEC4) *reinterpret_cast<float4 *>(&As[buf][a_r0 + j * a_rstep][a_k]) = ra4[j];
+            else As[buf][a_r0 + j * a_rstep][a_k] = ra1[j];
+        }
+        *reinterpret_cast<float4 *>(&Bs[buf][b_k][b_n]) = rb;
+    };
+
+    float acc[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f; }
+
+    const int nk = (p.K + CG_BK - 1) / CG_BK;
+    load_tile(0); store_tile(0); __syncthreads();
+    for (int kt = 0; kt < nk; ++kt) {
+        const int cur = kt & 1;
+        if (kt + 1 < nk) load_tile(kt + 1);
+#pragma unroll
+        for (int kk = 0; kk < CG_BK; kk += 4) {
+            float4 a[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) a[i] = *reinterpret_cast<const float4 *>(&As[cur][ty + 16 * i][kk]);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float4 b = *reinterpret_cast<const float4 *>(&Bs[cur][kk + j][tx * 4]);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const float av = j == 0 ? a[i].x : j == 1 ? a[i].y : j == 2 ? a[i].z : a[i].w;
+                    acc[i][0] = fmaf(av, b.x, acc[i][0]); acc[i][1] = fmaf(av, b.y, acc[i][1]);
+                    acc[i][2] = fmaf(av, b.z, acc[i][2]); acc[i][3] = fmaf(av, b.w, acc[i][3]);
+                }
+            }
+        }
+        if (kt + 1 < nk) store_tile(cur ^ 1);
+        __syncthreads();
+    }
+    // ---- epilogue: bias + activation, NHWC store
+    const int n = n0 + tx * 4;
+    float bv[4] = {0.f, 0.f, 0.f, 0.f};
+    if (p.bias) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) if (n + c < p.Cout) bv[c] = __ldg(p.bias + n + c);
+    }
+    const bool vec_store = (p.Cout & 3) == 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const long long m = m0 + ty + 16 * i;
+        if (m >= p.M) continue;
+        float v[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) v[c] = act_apply(acc[i][c] + bv[c], p.act);
+        float *dst = p.y + (size_t)m * p.Cout + n;
+        if (vec_store) { if (n < p.Cout) *reinterpret_cast<float4 *>(dst) = make_float4(v[0], v[1], v[2], v[3]); }
+        else {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) if (n + c < p.Cout) dst[c] = v[c];
+        }
+    }
+}
+
+// softmax over the feature axis of NHWC rows, in place ('m' convs, layers.py:817-818). One warp per pixel.
+__global__ void k_softmax_rows(float *__restrict__ x, long long rows, int C) {
+    long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const int lane = threadIdx.x & 31;
+    float *r = x + (size_t)row * C;
+    float m = -INFINITY;
+    for (int c = lane; c < C; c += 32) m = fmaxf(m, r[c]);
+    for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    float s = 0.f;
+    for (int c = lane; c < C; c += 32) s += expf(r[c] - m);
+    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    for (int c = lane; c < C; c += 32) r[c] = expf(r[c] - m) / s;
+}
+
+// =============================================================================================
+// max pooling, NHWC, floor mode, no padding (layers.py:379-388)
+// =============================================================================================
+__global__ void k_maxpool(const float *__restrict__ x, float *__restrict__ y, int N, int H, int W, int C,
+                          int Ho, int Wo, int kh, int kw, int sy, int sx) {
+    const int cv = (C & 3) == 0 ? 4 : 1;
+    const int Cq = C / cv;
+    const long long total = (long long)N * Ho * Wo * Cq;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        int cq = (int)(idx % Cq); long long t = idx / Cq;
+        int wo = (int)(t % Wo); t /= Wo;
+        int ho = (int)(t % Ho); long long n = t / Ho;
+        const float *base = x + ((n * H + (long long)ho * sy) * W + (long long)wo * sx) * C + cq * cv;
+        if (cv == 4) {
+            float4 m = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+            for (int i = 0; i < kh; ++i)
+                for (int j = 0; j < kw; ++j) {
+                    float4 v = __ldg(reinterpret_cast<const float4 *>(base + ((long long)i * W + j) * C));
+                    m.x = fmaxf(m.x, v.x); m.y = fmaxf(m.y, v.y); m.z = fmaxf(m.z, v.z); m.w = fmaxf(m.w, v.w);
+                }
+            *reinterpret_cast<float4 *>(y + idx * 4) = m;
+        } else {
+            float m = -INFINITY;
+            for (int i = 0; i < kh; ++i)
+                for (int j = 0; j < kw; ++j) m = fmaxf(m, __ldg(base + ((long long)i * W + j) * C));
+            y[idx] = m;
+        }
+    }
+}
+
+// =============================================================================================
+// generic Reshape (layers.py:313-333) as a gather on NHWC storage with NCHW index semantics
+// =============================================================================================
+struct ReshapeParams {
+    long long in_dims[4], out_dims[4];  // NCHW
+    long long shape5[5];                // split input shape
+    int perm[5];                        // permuted[i] = shape5[perm[i]]
+    int src, dest;
+};
+__global__ void k_reshape(const float *__restrict__ x, float *__restrict__ y, ReshapeParams p) {
+    const long long oN = p.out_dims[0], oC = p.out_dims[1], oH = p.out_dims[2], oW = p.out_dims[3];
+    const long long total = oN * oC * oH * oW;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        // idx enumerates the NHWC output: c fastest
+        long long o[4];
+        o[1] = idx % oC; long long t = idx / oC;
+        o[3] = t % oW; t /= oW;
+        o[2] = t % oH; o[0] = t / oH;
+        // 4-D out coord -> 5-D permuted coord
+        long long q[5]; int j = 0;
+        for (int i = 0; i < 4; ++i) {
+            if (i == p.dest) { long long inner = p.shape5[p.perm[i + 1]]; q[j++] = o[i] / inner; q[j++] = o[i] % inner; }
+            else q[j++] = o[i];
+        }
+        long long s5[5];
+        for (int i = 0; i < 5; ++i) s5[p.perm[i]] = q[i];
+        long long in4[4]; j = 0;
+        for (int i = 0; i < 4; ++i) {
+            if (i == p.src) { in4[i] = s5[j] * p.shape5[j + 1] + s5[j + 1]; j += 2; }
+            else in4[i] = s5[j++];
+        }
+        const long long src = ((in4[0] * p.in_dims[2] + in4[2]) * p.in_dims[3] + in4[3]) * p.in_dims[1] + in4[1];
+        y[idx] = __ldg(x + src);
+    }
+}
+
+// Addition (layers.py:205-212): out[.., j, ..] = sum_win in[.., win*chunk + j, ..] along NCHW dim `dim`
+__global__ void k_addition(const float *__restrict__ x, float *__restrict__ y, long long iN, long long iC, long long iH, long long iW,
+                           int dim, int chunk) {
+    long long od[4] = {iN, iC, iH, iW};
+    const long long D = od[dim];
+    od[dim] = chunk;
+    const long long nwin = D / chunk;
+    const long long total = od[0] * od[1] * od[2] * od[3];
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        long long o[4];
+        o[1] = idx % od[1]; long long t = idx / od[1];
+        o[3] = t % od[3]; t /= od[3];
+        o[2] = t % od[2]; o[0] = t / od[2];
+        float s = 0.f;
+        for (long long wdx = 0; wdx < nwin; ++wdx) {
+            long long i4[4] = {o[0], o[1], o[2], o[3]};
+            i4[dim] = wdx * chunk + o[dim];
+            s += __ldg(x + ((i4[0] * iH + i4[2]) * iW + i4[3]) * iC + i4[1]);
+        }
+        y[idx] = s;
+    }
+}
+
+// channel concat for MultiParamParallel (layers.py:60-71): y[pix][coff + c] = x[pix][c]
+__global__ void k_concat(const float *__restrict__ x, float *__restrict__ y, long long pixels, int C, int Ctot, int coff) {
+    const long long total = pixels * C;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        long long pix = idx / C; int c = (int)(idx % C);
+        y[pix * Ctot + coff + c] = __ldg(x + idx);
+    }
+}
+
+// summarising RNN (layers.py:539-541): keep the last step along W (x) or H (y)
+__global__ void k_take_last(const float *__restrict__ x, float *__restrict__ y, int N, int H, int W, int C, int along_h) {
+    const int oH = along_h ? 1 : H, oW = along_h ? W : 1;
+    const long long total = (long long)N * oH * oW * C;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        int c = (int)(idx % C); long long t = idx / C;
+        int w = (int)(t % oW); t /= oW;
+        int h = (int)(t % oH); long long n = t / oH;
+        int sh = along_h ? H - 1 : h, sw = along_h ? w : W - 1;
+        y[idx] = __ldg(x + ((n * H + sh) * W + sw) * C + c);
+    }
+}
+
+// =============================================================================================
+// GroupNorm (layers.py:967-984): per-(sample, group) statistics over (C/G, H, W[:len]); outputs beyond
+// a line's valid width are zero.  Three deterministic passes: block partials -> finalize -> apply.
+// =============================================================================================
+__global__ void k_gn_partial(const float *__restrict__ x, double *__restrict__ partial, int H, int W, int C, int G,
+                             const int *__restrict__ lens, int chunks, int rows, int cthreads, int cpt) {
+    // block = rows x cthreads threads; thread (r, ct) accumulates channels ct + j*cthreads (j < cpt) over pixels r, r+rows, ...
+    extern __shared__ double gn_sm[];                        // [blockDim.x * cpt][2]
+    const int n = blockIdx.y, chunk = blockIdx.x;
+    const int len = lens ? min(max(lens[n], 1), W) : W;  // seq_len.clamp(min=1, max=W)
+    const long long npix = (long long)H * W;
+    const long long per = (npix + chunks - 1) / chunks;
+    const long long p0 = chunk * per, p1 = min(npix, p0 + per);
+    const int r = threadIdx.x / cthreads, ct = threadIdx.x % cthreads;
+    const float *base = x + (size_t)n * npix * C;
+    for (int j = 0; j < cpt; ++j) {
+        const int c = ct + j * cthreads;
+        double s = 0.0, ss = 0.0;
+        if (c < C && r < rows) {
+            for (long long pix = p0 + r; pix < p1; pix += rows) {
+                if ((int)(pix % W) < len) { const double v = (double)__ldg(base + pix * C + c); s += v; ss += v * v; }
+            }
+        }
+        gn_sm[(threadIdx.x * cpt + j) * 2] = s; gn_sm[(threadIdx.x * cpt + j) * 2 + 1] = ss;
+    }
+    __syncthreads();
+    const int cg_sz = C / G;
+    for (int g = threadIdx.x; g < G; g += blockDim.x) {
+        double s = 0.0, ss = 0.0;
+        for (int c = g * cg_sz; c < (g + 1) * cg_sz; ++c) {
+            const int ctc = c % cthreads, j = c / cthreads;
+            for (int rr = 0; rr < rows; ++rr) {
+                const int t = rr * cthreads + ctc;
+                s += gn_sm[(t * cpt + j) * 2]; ss += gn_sm[(t * cpt + j) * 2 + 1];
+            }
+        }
+        partial[(((size_t)n * chunks + chunk) * G + g) * 2] = s;
+        partial[(((size_t)n * chunks + chunk) * G + g) * 2 + 1] = ss;
+    }
+}
+__global__ void k_gn_finalize(const double *__restrict__ partial, float2 *__restrict__ stats, int N, int G, int chunks,
+                              int H, int W, int C, const int *__restrict__ lens, float eps) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= N * G) return;
+    const int n = idx / G, g = idx % G;
+    double s = 0.0, ss = 0.0;
+    for (int c = 0; c < chunks; ++c) { s += partial[(((size_t)n * chunks + c) * G + g) * 2]; ss += partial[(((size_t)n * chunks + c) * G + g) * 2 + 1]; }
+    const int len = lens ? min(max(lens[n], 1), W) : W;
+    const double cnt = (double)(C / G) * H * len;
+    const double mean = s / cnt;
+    double var = ss / cnt - mean * mean;
+    if (var < 0.0) var = 0.0;
+    stats[idx] = make_float2((float)mean, (float)(1.0 / sqrt(var + (double)eps)));
+}
+__global__ void k_gn_apply(const float *__restrict__ x, float *__restrict__ y, const float2 *__restrict__ stats,
+                           const float *__restrict__ gamma, const float *__restrict__ beta, long long total,
+                           int H, int W, int C, int G, const int *__restrict__ lens) {
+    const int cg_sz = C / G;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(idx % C); long long t = idx / C;
+        const int w = (int)(t % W); const long long n = t / W / H;
+        const int len = lens ? min(max(lens[n], 1), W) : W;
+        float v = 0.f;
+        if (w < len) {
+            const float2 st = stats[n * G + c / cg_sz];
+            v = (__ldg(x + idx) - st.x) * st.y * __ldg(gamma + c) + __ldg(beta + c);
+        }
+        y[idx] = v;
+    }
+}
+
+// =============================================================================================
+// LSTM recurrence (TransposedSummarizingRNN / nn.LSTM, layers.py:513-547), one direction per blockIdx.y.
+//
+// Input  gx  : per-pixel gate pre-activations x_t W_ih^T + b_ih + b_hh from the projection GEMM,
+//              feature order [dir][unit][gate i,f,g,o]  (one float4 per (unit, pixel)).
+// Output out : per-pixel hidden states, feature order [dir][unit] (forward | reverse halves).
+// A thread-block cluster of CS = KSPLIT CTAs owns BL = 64/KSPLIT sequences of one direction for all
+// time steps.  W_hh lives in REGISTERS for the whole kernel: thread (unit, k-slice) holds the 4 gate rows
+// x 32 k of its unit (128 registers); h_{t-1} is staged in shared memory in every CTA of the cluster and
+// exchanged through distributed shared memory once per step.  fp32 cell state, accurate expf/tanhf.
+// Packed-sequence semantics (pack_padded_sequence, layers.py:528-536): line q runs len[q] steps, the
+// reverse direction starts at its own last valid column, outputs beyond len are zero.
+// =============================================================================================
+struct LstmParams {
+    const float *gx; const float *whh; float *out; const int *lens;
+    int nseq, T, hid, dirs, U;
+    int q2; long long s_outer, s_inner, step;      // pixel(q, t) = (q / q2) * s_outer + (q % q2) * s_inner + t * step
+};
+
+template <int KSPLIT>
+__global__ void __launch_bounds__(256, 1) k_lstm_rec(LstmParams p) {
+    constexpr int CS = KSPLIT, LSPLIT = 8 / KSPLIT, BL = 8 * LSPLIT, LPT = 8 / KSPLIT, HLD = 36 * KSPLIT;
+    __shared__ __align__(16) float hbuf[2][BL][HLD];
+    cg::cluster_group cluster = cg::this_cluster();
+    const int tid = threadIdx.x;
+    const int ks = tid % KSPLIT, ls = (tid / KSPLIT) % LSPLIT, rg = tid >> 3;
+    const int rank = CS > 1 ? (int)cluster.block_rank() : 0;
+    const int chunk = blockIdx.x / CS, dir = blockIdx.y;
+    const int u = rank * p.U + rg;
+    const bool uvalid = rg < p.U && u < p.hid;
+    const int hid = p.hid, GC = p.dirs * 4 * hid, OC = p.dirs * hid;
+
+    float w[4][32];
+#pragma unroll
+    for (int g = 0; g < 4; ++g)
+#pragma unroll
+        for (int kk = 0; kk < 32; ++kk) {
+            const int k = ks * 32 + kk;
+            w[g][kk] = (uvalid && k < hid) ? __ldg(p.whh + ((size_t)dir * 4 * hid + (size_t)g * hid + u) * hid + k) : 0.f;
+        }
+    for (int i = tid; i < 2 * BL * HLD; i += 256) (&hbuf[0][0][0])[i] = 0.f;
+
+    int len[LPT]; long long base[LPT]; float cst[LPT];
+#pragma unroll
+    for (int j = 0; j < LPT; ++j) {
+        const int q = chunk * BL + ls * 8 + ks * LPT + j;
+        const bool qv = q < p.nseq;
+        int l = qv ? (p.lens ? p.lens[q] : p.T) : 0;
+        len[j] = min(max(l, 0), p.T);
+        const int qq = qv ? q : 0;
+        base[j] = (long long)(qq / p.q2) * p.s_outer + (long long)(qq % p.q2) * p.s_inner;
+        cst[j] = 0.f;
+    }
+    int maxlen = 0;
+    for (int lb = 0; lb < BL; ++lb) {
+        const int q = chunk * BL + lb;
+        if (q < p.nseq) {
+            const int l = p.lens ? min(max(p.lens[q], 0), p.T) : p.T;
+            maxlen = max(maxlen, l);
+            // zero the padded tail of this CTA's units (pad_packed_sequence pads with 0)
+            if (l < p.T) {
+                const long long b0 = (long long)(q / p.q2) * p.s_outer + (long long)(q % p.q2) * p.s_inner;
+                const int nu = min(p.U, hid - rank * p.U);
+                for (int i = tid; i < (p.T - l) * max(nu, 0); i += 256) {
+                    const int t = l + i / nu, uu = rank * p.U + i % nu;
+                    p.out[(size_t)(b0 + (long long)t * p.step) * OC + dir * hid + uu] = 0.f;
+                }
+            }
+        }
+    }
+    if (CS > 1) cluster.sync(); else __syncthreads();
+
+    float4 gxc[LPT], gxn[LPT];
+    auto load_gx = [&](int s, float4 *dst) {
+#pragma unroll
+        for (int j = 0; j < LPT; ++j) {
+            if (uvalid && s < len[j]) {
+                const int t = dir ? len[j] - 1 - s : s;
+                dst[j] = __ldg(reinterpret_cast<const float4 *>(p.gx + (size_t)(base[j] + (long long)t * p.step) * GC + (size_t)dir * 4 * hid + (size_t)u * 4));
+            } else dst[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    };
+    load_gx(0, gxc);
+
+    for (int s = 0; s < maxlen; ++s) {
+        const int cur = s & 1, nxt = cur ^ 1;
+        if (s + 1 < maxlen) load_gx(s + 1, gxn);
+        float v[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = 0.f;
+#pragma unroll
+        for (int b = 0; b < 8; ++b) {
+            const float *hrow = &hbuf[cur][ls * 8 + b][ks * 36];
+#pragma unroll
+            for (int kq = 0; kq < 8; ++kq) {
+                const float4 hv = *reinterpret_cast<const float4 *>(hrow + kq * 4);
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    float a = v[b * 4 + g];
+                    a = fmaf(w[g][kq * 4 + 0], hv.x, a); a = fmaf(w[g][kq * 4 + 1], hv.y, a);
+                    a = fmaf(w[g][kq * 4 + 2], hv.z, a); a = fmaf(w[g][kq * 4 + 3], hv.w, a);
+                    v[b * 4 + g] = a;
+                }
+            }
+        }
+        // reduce-scatter across the KSPLIT k-slices (adjacent lanes): lane ks ends with lines [ks*LPT, +LPT)
+        if (KSPLIT >= 8) {
+            const bool up = ks & 4;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) { const float snd = up ? v[i] : v[i + 16], kp = up ? v[i + 16] : v[i]; v[i] = kp + __shfl_xor_sync(0xffffffffu, snd, 4); }
+        }
+        if (KSPLIT >= 4) {
+            constexpr int n = KSPLIT >= 8 ? 16 : 32;
+            const bool up = ks & 2;
+#pragma unroll
+            for (int i = 0; i < n / 2; ++i) { const float snd = up ? v[i] : v[i + n / 2], kp = up ? v[i + n / 2] : v[i]; v[i] = kp + __shfl_xor_sync(0xffffffffu, snd, 2); }
+        }
+        if (KSPLIT >= 2) {
+            constexpr int n = KSPLIT >= 8 ? 8 : (KSPLIT >= 4 ? 16 : 32);
+            const bool up = ks & 1;
+#pragma unroll
+            for (int i = 0; i < n / 2; ++i) { const float snd = up ? v[i] : v[i + n / 2], kp = up ? v[i + n / 2] : v[i]; v[i] = kp + __shfl_xor_sync(0xffffffffu, snd, 1); }
+        }
+        // gate non-linearities + state update for the (unit, line) pairs this lane owns
+#pragma unroll
+        for (int j = 0; j < LPT; ++j) {
+            if (uvalid && s < len[j]) {
+                const int t = dir ? len[j] - 1 - s : s;
+                const float ig = sigmoidf_acc(v[j * 4 + 0] + gxc[j].x);
+                const float fg = sigmoidf_acc(v[j * 4 + 1] + gxc[j].y);
+                const float gg = tanhf(v[j * 4 + 2] + gxc[j].z);
+                const float og = sigmoidf_acc(v[j * 4 + 3] + gxc[j].w);
+                cst[j] = fg * cst[j] + ig * gg;
+                const float h = og * tanhf(cst[j]);
+                p.out[(size_t)(base[j] + (long long)t * p.step) * OC + dir * hid + u] = h;
+                float *slot = &hbuf[nxt][ls * 8 + ks * LPT + j][(u >> 5) * 36 + (u & 31)];
+                if (CS > 1) {
+#pragma unroll
+                    for (int r = 0; r < CS; ++r) *cluster.map_shared_rank(slot, r) = h;
+                } else *slot = h;
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < LPT; ++j) gxc[j] = gxn[j];
+        if (CS > 1) cluster.sync(); else __syncthreads();
+    }
+}
+
+// =============================================================================================
+// softmax statistics + arg-max per time step, then CTC best-path collapse
+//   (logits / T).softmax(1) ; seq[..., :len].max(dim=0) ; groupby ; drop blank 0
+//   rpred.py:226, models.py:115, ctc_decoder.py:63-71
+// =============================================================================================
+// logits rows [rows][C] (NHWC with H == 1).  One warp per row.
+__global__ void k_row_argmax_softmax(const float *__restrict__ logits, long long rows, int C, float temperature,
+                                     int *__restrict__ lab, float *__restrict__ conf) {
+    long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const int lane = threadIdx.x & 31;
+    const float *r = logits + (size_t)row * C;
+    float m = -INFINITY;
+    for (int c = lane; c < C; c += 32) m = fmaxf(m, __fdiv_rn(__ldg(r + c), temperature));
+    for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    float s = 0.f, be = -1.f; int bi = 0x7fffffff;
+    for (int c = lane; c < C; c += 32) {
+        const float e = expf(__fdiv_rn(__ldg(r + c), temperature) - m);
+        s += e;
+        if (e > be) { be = e; bi = c; }          // strict >: first maximum within the lane's ascending indices
+    }
+    for (int o = 16; o; o >>= 1) {
+        s += __shfl_xor_sync(0xffffffffu, s, o);
+        const float oe = __shfl_xor_sync(0xffffffffu, be, o); const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (oe > be || (oe == be && oi < bi)) { be = oe; bi = oi; }   // first index on ties, as torch.max
+    }
+    if (lane == 0) { lab[row] = bi; conf[row] = be / s; }
+}
+
+// probs (N, C, W) class-major, as handed to the reference's decoder hook.  One thread per (n, t).
+__global__ void k_col_argmax(const float *__restrict__ probs, int N, int C, int W, int *__restrict__ lab, float *__restrict__ conf) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)N * W) return;
+    const int t = (int)(idx % W); const long long n = idx / W;
+    const float *p = probs + (size_t)n * C * W + t;
+    float be = __ldg(p); int bi = 0;
+    for (int c = 1; c < C; ++c) { const float v = __ldg(p + (size_t)c * W); if (v > be || (v != v && be == be)) { be = v; bi = c; } }
+    lab[idx] = bi; conf[idx] = be;
+}
+
+// One warp per line: runs of equal labels; blank (0) runs dropped; (label, first t, last t, max conf of run).
+__global__ void k_ctc_collapse(const int *__restrict__ lab, const float *__restrict__ conf, const int *__restrict__ lens,
+                               int N, int T, int max_out, int *__restrict__ o_lab, int *__restrict__ o_start,
+                               int *__restrict__ o_end, float *__restrict__ o_conf, int *__restrict__ o_cnt) {
+    const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (n >= N) return;
+    const int lane = threadIdx.x & 31;
+    const int L = lens ? min(max(lens[n], 0), T) : T;
+    const int *l = lab + (size_t)n * T; const float *cf = conf + (size_t)n * T;
+    int count = 0;
+    for (int t0 = 0; t0 < L; t0 += 32) {
+        const int t = t0 + lane;
+        int cur = -1; bool emit = false;
+        if (t < L) { cur = l[t]; emit = cur != 0 && (t == 0 || l[t - 1] != cur); }
+        const unsigned bal = __ballot_sync(0xffffffffu, emit);
+        if (emit) {
+            const int pos = count + __popc(bal & ((1u << lane) - 1));
+            int e = t; float mx = cf[t];
+            while (e + 1 < L && l[e + 1] == cur) { ++e; mx = fmaxf(mx, cf[e]); }
+            if (pos < max_out) {
+                o_lab[(size_t)n * max_out + pos] = cur; o_start[(size_t)n * max_out + pos] = t;
+                o_end[(size_t)n * max_out + pos] = e; o_conf[(size_t)n * max_out + pos] = mx;
+            }
+        }
+        count += __popc(bal);
+    }
+    if (lane == 0) o_cnt[n] = count;
+}
+
+// probabilities in the reference's (N, C, T) layout (`self.outputs`, rpred.py:227) from NHWC logits rows.
+// block = 32 time steps of one line; warp w handles rows w, w+8, ...; smem transpose for coalesced stores.
+__global__ void k_probs_nct(const float *__restrict__ logits, float *__restrict__ probs, int T, int C, float temperature) {
+    extern __shared__ float pr_sm[];                 // [32][C + 1]
+    const int n = blockIdx.y, t0 = blockIdx.x * 32;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const int ld = C + 1;
+    for (int r = wid; r < 32; r += nw) {
+        const int t = t0 + r;
+        if (t >= T) continue;
+        const float *row = logits + ((size_t)n * T + t) * C;
+        float m = -INFINITY;
+        for (int c = lane; c < C; c += 32) m = fmaxf(m, __fdiv_rn(__ldg(row + c), temperature));
+        for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+        float s = 0.f;
+        for (int c = lane; c < C; c += 32) { const float e = expf(__fdiv_rn(__ldg(row + c), temperature) - m); pr_sm[r * ld + c] = e; s += e; }
+        for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        for (int c = lane; c < C; c += 32) pr_sm[r * ld + c] = pr_sm[r * ld + c] / s;
+    }
+    __syncthreads();
+    for (int c = wid; c < C; c += nw) {
+        const int t = t0 + lane;
+        if (t < T) probs[((size_t)n * C + c) * T + t] = pr_sm[lane * ld + c];
+    }
+}
+
+// fallback for class counts whose 32-row tile does not fit shared memory: one warp per (n, t), strided stores
+__global__ void k_probs_nct_simple(const float *__restrict__ logits, float *__restrict__ probs, int N, int T, int C, float temperature) {
+    long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= (long long)N * T) return;
+    const int lane = threadIdx.x & 31;
+    const int t = (int)(row % T); const long long n = row / T;
+    const float *r = logits + (size_t)row * C;
+    float m = -INFINITY;
+    for (int c = lane; c < C; c += 32) m = fmaxf(m, __fdiv_rn(__ldg(r + c), temperature));
+    for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    float s = 0.f;
+    for (int c = lane; c < C; c += 32) s += expf(__fdiv_rn(__ldg(r + c), temperature) - m);
+    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    for (int c = lane; c < C; c += 32) probs[((size_t)n * C + c) * T + t] = expf(__fdiv_rn(__ldg(r + c), temperature) - m) / s;
+}
+
+// =============================================================================================
+// blla post-net: F.interpolate(o, size) (nearest) -> sigmoid, NHWC logits -> NCHW heat map
+// (spred.py:271-272, blla.py:124-125).  src = min(int(floorf(dst * (float)in / out)), in - 1) as ATen.
+// =============================================================================================
+__global__ void k_upsample_sigmoid(const float *__restrict__ x, float *__restrict__ y, int N, int H, int W, int C, int OH, int OW) {
+    const float sh = (float)H / (float)OH, sw = (float)W / (float)OW;
+    const long long total = (long long)N * OH * OW;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const int ox = (int)(idx % OW); long long t = idx / OW;
+        const int oy = (int)(t % OH); const long long n = t / OH;
+        const int sy = min((int)floorf(oy * sh), H - 1), sx = min((int)floorf(ox * sw), W - 1);
+        const float *src = x + ((n * H + sy) * (long long)W + sx) * C;
+        for (int c = 0; c < C; ++c) y[((n * C + c) * (long long)OH + oy) * OW + ox] = sigmoidf_acc(__ldg(src + c));
+    }
+}
+
+}  // namespace kb

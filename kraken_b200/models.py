@@ -1,0 +1,117 @@
+"""
+Mirror of kraken.lib.models.TorchSeqRecognizer / load_any (reference: kraken/lib/models.py:31-199) on top of
+the engine.  Duck-type compatible with what `kraken.rpred.mm_rpred` touches: `.nn` (with `.input`,
+`.one_channel_mode`, `.use_legacy_polygons`), `.codec`, `.seg_type`, `.predict()`, `.outputs`.
+
+With the default decoder, `predict*` run the fused device path (`kb_recognize`: net -> softmax statistics ->
+arg-max -> CTC collapse in one call, only the label tuples come back).  A user-supplied `decoder` gets the
+reference behaviour: probabilities as a (N, C, W) numpy array, then the hook.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from os.path import abspath, expanduser, expandvars
+from typing import Optional, Union
+
+import numpy as np
+import torch
+
+from . import ctc_decoder
+from ._lib import KrakenInputException, check, lib
+from .vgsl import TorchVGSLModel, _as_f32, _on_device, _ptr, _stream_for
+
+__all__ = ['TorchSeqRecognizer', 'load_any', 'KrakenInvalidModelException']
+
+
+class KrakenInvalidModelException(Exception):
+    pass
+
+
+class TorchSeqRecognizer:
+    def __init__(self, nn: TorchVGSLModel, decoder=ctc_decoder.greedy_decoder, temperature: float = 1.0,
+                 train: bool = False, device: str = 'cuda:0'):
+        if train:
+            raise NotImplementedError('kraken_b200 is an inference engine; train=True is not supported')
+        self.nn = nn
+        self.kind = ''
+        self.codec = self.nn.codec
+        self.decoder = decoder
+        self.temperature = temperature
+        self.train = train
+        self.device = device
+        if nn.model_type and 'recognition' not in nn.model_type:
+            raise ValueError(f'Models of type {nn.model_type} are not supported by TorchSeqRecognizer')
+        self.one_channel_mode = nn.one_channel_mode
+        self.seg_type = nn.seg_type
+        self.outputs = None
+        if self.device:
+            self.nn.to(device)
+
+    def to(self, device):
+        self.device = device
+        self.nn.to(device)
+
+    # -- fused device path ----------------------------------------------------------------------
+    def _recognize(self, line, lens, want_probs: bool):
+        net = self.nn
+        net._ensure_finalized(line)
+        x = _as_f32(line)
+        if x.ndim != 4:
+            raise ValueError(f'expected a 4D NCHW input, got shape {tuple(x.shape)}')
+        n, c, h, w = (int(v) for v in x.shape)
+        widths = None
+        if lens is not None:
+            widths = np.ascontiguousarray(torch.as_tensor(lens).cpu().numpy(), dtype=np.int32)
+        dims = net.infer_dims(n, h, w)
+        if dims[2] != 1:
+            raise KrakenInputException('Expected dimension 3 to be 1, actual {}'.format(tuple(dims)))
+        T, ncls = dims[3], dims[1]
+        stride = max(T, 1)
+        labels = np.zeros((n, stride), np.int32)
+        starts = np.zeros((n, stride), np.int32)
+        ends = np.zeros((n, stride), np.int32)
+        confs = np.zeros((n, stride), np.float32)
+        counts = np.zeros(n, np.int32)
+        olens = np.zeros(n, np.int32)
+        probs = np.empty((n, ncls, T), np.float32) if want_probs else None
+        on_dev = _on_device(x)
+        check(lib.kb_recognize(net._h, _ptr(x), int(on_dev), n, h, w, widths.ctypes.data if widths is not None else None,
+                               float(self.temperature), labels.ctypes.data, starts.ctypes.data, ends.ctypes.data, confs.ctypes.data,
+                               counts.ctypes.data, stride, olens.ctypes.data, probs.ctypes.data if probs is not None else None, 0,
+                               _stream_for(x)))
+        if probs is not None:
+            self.outputs = probs
+        return ctc_decoder.unpack_decoded(labels, starts, ends, confs, counts), (olens if lens is not None else None)
+
+    # -- reference surface ------------------------------------------------------------------------
+    def forward(self, line: torch.Tensor, lens: Optional[torch.Tensor] = None):
+        """(N, C, H, W) lines -> ((N, C, W) softmax numpy array, output lengths) - models.py:93-119."""
+        _, olens = self._recognize(line, lens, want_probs=True)
+        return self.outputs, olens
+
+    def _decode(self, line, lens):
+        if self.decoder is ctc_decoder.greedy_decoder:
+            dec, _ = self._recognize(line, lens, want_probs=True)      # `outputs` stays populated (mm_rpred reads its shape)
+            return dec
+        o, olens = self.forward(line, lens)
+        return self.decoder(o, olens)
+
+    def predict(self, line, lens=None) -> list[list[tuple[str, int, int, float]]]:
+        return [self.codec.decode(locs) for locs in self._decode(line, lens)]
+
+    def predict_string(self, line, lens=None) -> list[str]:
+        return [''.join(x[0] for x in self.codec.decode(locs)) for locs in self._decode(line, lens)]
+
+    def predict_labels(self, line, lens=None) -> list[list[tuple[int, int, int, float]]]:
+        return self._decode(line, lens)
+
+
+def load_any(fname: Union[str, 'object'], train: bool = False, device: str = 'cuda:0') -> TorchSeqRecognizer:
+    fname = abspath(expandvars(expanduser(str(fname))))
+    try:
+        nn = TorchVGSLModel.load_model(fname)
+    except Exception as e:
+        raise KrakenInvalidModelException('File {} not loadable by any parser.'.format(fname)) from e
+    seq = TorchSeqRecognizer(nn, train=train, device=device)
+    seq.kind = 'vgsl'
+    return seq
