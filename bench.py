@@ -35,6 +35,7 @@ import torch
 
 CFG2 = '[1,48,0,1 Cr3,3,32 Mp2,2 Cr3,3,64 Mp2,2 S1(1x0)1,3 Lbx256 O1c200]'
 BATCH, HEIGHT, WIDTH, NCLS = 64, 48, 800, 200
+CPU_NOTE = ''
 METRIC = 'line-images/sec (48px height)'
 UNIT = 'lines/s'
 
@@ -124,10 +125,60 @@ def oracle_model(seed=0):
     return vo, om, w
 
 
+def usable_cpus():
+    """Cores this process may actually use: affinity mask capped by the cgroup CPU quota (a 128-thread pool on a
+    quota-limited container is 50x slower than the right size)."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except Exception:
+        n = os.cpu_count() or 1
+    for path in ('/sys/fs/cgroup/cpu.max', '/sys/fs/cgroup/cpu/cpu.cfs_quota_us'):
+        try:
+            txt = open(path).read().split()
+            if path.endswith('cpu.max'):
+                if txt[0] != 'max':
+                    n = min(n, max(1, int(float(txt[0]) / float(txt[1]) + 0.5)))
+            else:
+                q = int(txt[0])
+                per = int(open('/sys/fs/cgroup/cpu/cpu.cfs_period_us').read())
+                if q > 0:
+                    n = min(n, max(1, int(q / per + 0.5)))
+            break
+        except Exception:
+            continue
+    return max(1, n)
+
+
+def pick_threads(vo, om):
+    """Gives the CPU arm its best shot: tries a few intra-op thread counts on a small sample and keeps the fastest."""
+    n = usable_cpus()
+    cands = sorted({c for c in (n, n // 2, 64, 32, 16, 8) if 1 <= c <= n}, reverse=True)
+    g = torch.Generator().manual_seed(5)
+    x = torch.rand(16, 1, HEIGHT, 400, generator=g)
+    lens = torch.full((16,), 400, dtype=torch.long)
+    best, best_t, tried = cands[-1], float('inf'), {}
+    t_start = time.perf_counter()
+    for c in cands:
+        torch.set_num_threads(c)
+        vo.rec_predict(om, x[:4], lens[:4])                    # thread-pool warm-up
+        t0 = time.perf_counter()
+        vo.rec_predict(om, x, lens)
+        dt = time.perf_counter() - t0
+        tried[c] = round(dt, 3)
+        if dt < best_t:
+            best, best_t = c, dt
+        if time.perf_counter() - t_start > 40:
+            break
+    return best, n, tried
+
+
 def time_cpu(steps, warmup, threads=None):
     """The reference's CPU path for one step: nn(x, lens) + softmax + greedy_decoder on a batch of 64 (rpred.py:225-228)."""
     vo, om, _ = oracle_model()
-    threads = threads or os.cpu_count() or 1
+    global CPU_NOTE
+    if threads is None:
+        threads, avail, tried = pick_threads(vo, om)
+        CPU_NOTE = f'usable cores {avail} (os.cpu_count {os.cpu_count()}); thread-count probe s/16-line sample {tried}'
     torch.set_num_threads(threads)
     xs = make_batches(2, 100)
     lens = torch.full((BATCH,), WIDTH, dtype=torch.long)
@@ -160,7 +211,7 @@ def run_reference_arm(args, rank):
             'config': {'workload': 'cfg2', 'spec': CFG2, 'batch': BATCH, 'line': f'{HEIGHT}x{WIDTH}', 'device': 'host CPU'},
             'cpu_baseline': {'value': lps, 'unit': UNIT, 'cores': threads, 'kind': 'port', 'cpu': cpu_model_name(),
                              'sample': f'{args.steps} batches of {BATCH} lines {HEIGHT}x{WIDTH} after {args.warmup} warm-up; '
-                                       'torch-CPU restatement of the reference path (oracle/vgsl_oracle.py), fp32, all host threads'},
+                                       'torch-CPU restatement of the reference path (oracle/vgsl_oracle.py), fp32; ' + CPU_NOTE},
             'e2e': {'value': lps, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
     print(json.dumps(line), flush=True)
 
@@ -312,7 +363,7 @@ def main():
         lps, cms, threads = time_cpu(args.cpu_steps, 2)
         cpu = {'value': lps, 'unit': UNIT, 'cores': threads, 'kind': 'port', 'cpu': cpu_model_name(),
                'sample': f'{args.cpu_steps} batches of {BATCH} lines {HEIGHT}x{WIDTH} after 2 warm-up ({cms:.0f} ms/batch); '
-                         'oracle/vgsl_oracle.py = torch-CPU restatement of rpred.py:225-228 + ctc_decoder.py, fp32, all host threads'}
+                         'oracle/vgsl_oracle.py = torch-CPU restatement of rpred.py:225-228 + ctc_decoder.py, fp32; ' + CPU_NOTE}
 
     d2h = BATCH * T * 16 + BATCH * 4
     line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,

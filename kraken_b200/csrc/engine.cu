@@ -317,6 +317,15 @@ struct Exec {
                 at[0].id = cudaLaunchAttributeClusterDimension;
                 at[0].val.clusterDim.x = (unsigned)ks; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
                 cfg.attrs = at; cfg.numAttrs = 1;
+                if (getenv("KB_DEBUG")) {
+                    int ncl = -1;
+                    cudaError_t oe = ks == 8 ? cudaOccupancyMaxActiveClusters(&ncl, k_lstm_rec<8>, &cfg)
+                                   : ks == 4 ? cudaOccupancyMaxActiveClusters(&ncl, k_lstm_rec<4>, &cfg)
+                                   : ks == 2 ? cudaOccupancyMaxActiveClusters(&ncl, k_lstm_rec<2>, &cfg)
+                                             : cudaOccupancyMaxActiveClusters(&ncl, k_lstm_rec<1>, &cfg);
+                    fprintf(stderr, "[kb] %s: lstm rec ks=%d clusters=%d x %d dirs, T=%d, max co-resident clusters=%d (%s)\n", n.name.c_str(), ks,
+                            nchunks, dirs, lp.T, ncl, cudaGetErrorString(oe));
+                }
                 switch (ks) {
                 case 1: CK(cudaLaunchKernelEx(&cfg, k_lstm_rec<1>, lp)); break;
                 case 2: CK(cudaLaunchKernelEx(&cfg, k_lstm_rec<2>, lp)); break;
