@@ -141,6 +141,10 @@ int  kb_segment(kb_model *m, const float *pages, int pages_on_device, int32_t n,
 /* output of leaf layer `name` from the most recent forward on this handle, as NCHW host fp32.
  * dims_only != 0: only fills dims.  Valid until the next call on the handle.                        */
 int  kb_debug_layer_output(kb_model *m, const char *name, int32_t dims[4], float *out_host, int dims_only);
+/* C[M][N] = A[M][K] * B[N][K]^T + bias through the engine's GEMM kernels (use_tc: 1 = tcgen05 3xTF32 kernel,
+ * 0 = CUDA-core fp32 kernel); host pointers.  Unit-test hook for the kernels behind Linear / LSTM projection.   */
+int  kb_debug_gemm(const float *a, const float *b, const float *bias, float *c, int32_t M, int32_t N, int32_t K,
+                   int use_tc, int device);
 /* number of kernels this handle launched since creation / last reset (bench `gpu_launches`) */
 int64_t kb_launch_count(const kb_model *m);
 void    kb_reset_launch_count(kb_model *m);

@@ -12,6 +12,7 @@
 
 #include "../../include/kraken_b200.h"
 #include "kernels.cuh"
+#include "gemm_tc.cuh"
 #include "vgsl_plan.hpp"
 
 namespace kb {
@@ -36,6 +37,7 @@ struct LeafWeights {
     float *wt = nullptr;    // [K][Ncp]  conv/linear/lstm-x projection
     float *bias = nullptr;  // [Cout] / folded LSTM bias / GN beta
     float *aux = nullptr;   // W_hh [dirs][4h][h] / GN gamma
+    float *b_hi = nullptr, *b_lo = nullptr;   // [ncols][K] TF32 split planes for the tcgen05 GEMM (K-major)
     int ncp = 0, K = 0, ncols = 0;
 };
 
@@ -72,6 +74,7 @@ struct kb_model {
     std::vector<Stage> stages;       // event pool, reused across calls
     size_t n_stages = 0;             // entries used by the most recent call
     int sm_count = 148;
+    bool use_tc = true;              // tcgen05 GEMM path (KB_GEMM=ffma forces the CUDA-core kernel)
     ~kb_model() {
         if (device >= 0) {
             cudaSetDevice(device);
@@ -125,13 +128,25 @@ static float *upload(kb_model *m, const std::vector<float> &h) {
     return d;
 }
 
+static inline float tf32_rna(float x) {
+    uint32_t u; memcpy(&u, &x, 4);
+    u = (u + 0x00001000u) & 0xFFFFE000u;         // round-to-nearest (ties away) on the magnitude bits == cvt.rna.tf32.f32
+    float r; memcpy(&r, &u, 4); return r;
+}
+// rows[N][K] (K contiguous) -> device hi / lo planes
+static void upload_split(kb_model *m, const std::vector<float> &rows, LeafWeights &w) {
+    std::vector<float> hi(rows.size()), lo(rows.size());
+    for (size_t i = 0; i < rows.size(); ++i) { hi[i] = tf32_rna(rows[i]); lo[i] = rows[i] - hi[i]; }
+    w.b_hi = upload(m, hi); w.b_lo = upload(m, lo);
+}
+
 static void finalize_weights(kb_model *m) {
     for (void *p : m->dev_allocs) cudaFree(p);
     m->dev_allocs.clear();
     for (size_t li = 0; li < m->plan->leaf_nodes.size(); ++li) {
         const Node &n = *m->plan->leaf_nodes[li];
         LeafWeights &w = m->lw[li];
-        w.wt = w.bias = w.aux = nullptr;
+        w.wt = w.bias = w.aux = w.b_hi = w.b_lo = nullptr;
         auto need = [&](int slots) {
             for (int s = 0; s < slots; ++s)
                 if ((int)w.loaded.size() <= s || !w.loaded[s]) throw SpecError("weights of layer " + n.name + " not loaded (missing tensor for nn." + n.path + ")");
@@ -147,6 +162,7 @@ static void finalize_weights(kb_model *m) {
                         for (int kx = 0; kx < n.kw; ++kx)
                             wt[(size_t)((ky * n.kw + kx) * n.cin + ci) * ncp + co] = src[(((size_t)co * n.cin + ci) * n.kh + ky) * n.kw + kx];
             w.wt = upload(m, wt); w.bias = upload(m, w.host[1]); w.ncp = ncp; w.K = K; w.ncols = n.cout;
+            if (n.kh == 1 && n.kw == 1) upload_split(m, src, w);          // [Cout][Cin] is already K-major
         } else if (n.kind == K_LINEAR) {
             need(2);
             const int K = n.cin, ncp = (n.cout + 63) / 64 * 64, ld = n.cin + (n.aug ? 1 : 0);
@@ -156,6 +172,12 @@ static void finalize_weights(kb_model *m) {
                 if (n.aug) b[co] += w.host[0][(size_t)co * ld];          // the constant-one input column (layers.py:718-719)
             }
             w.wt = upload(m, wt); w.bias = upload(m, b); w.ncp = ncp; w.K = K; w.ncols = n.cout;
+            {
+                std::vector<float> rows((size_t)n.cout * K);
+                for (int co = 0; co < n.cout; ++co)
+                    for (int ci = 0; ci < K; ++ci) rows[(size_t)co * K + ci] = w.host[0][(size_t)co * ld + ci + (n.aug ? 1 : 0)];
+                upload_split(m, rows, w);
+            }
         } else if (n.kind == K_GN) {
             need(2);
             w.aux = upload(m, w.host[0]); w.bias = upload(m, w.host[1]);
@@ -177,6 +199,14 @@ static void finalize_weights(kb_model *m) {
                 std::copy(wh.begin(), wh.end(), whh.begin() + (size_t)d * 4 * h * h);
             }
             w.wt = upload(m, wt); w.bias = upload(m, b); w.aux = upload(m, whh); w.ncp = ncp; w.K = K; w.ncols = gc;
+            {
+                std::vector<float> rows((size_t)gc * K);
+                for (int d = 0; d < dirs; ++d)
+                    for (int g = 0; g < 4; ++g)
+                        for (int u = 0; u < h; ++u)
+                            memcpy(&rows[(size_t)(d * 4 * h + u * 4 + g) * K], &w.host[d * 4][(size_t)(g * h + u) * K], (size_t)K * sizeof(float));
+                upload_split(m, rows, w);
+            }
         }
     }
 }
@@ -201,7 +231,34 @@ struct Exec {
     }
     static Dims dims_of(const Tensor &t) { Dims d; d.n = t.n; d.c = t.c; d.h = t.h; d.w = t.w; return d; }
 
+    // tcgen05 path: plain per-pixel GEMMs (1x1 stride-1 conv, Linear, LSTM input projection) whose K rows can be TMA'd
+    bool tc_eligible(const Tensor &x, const LeafWeights &w, const Node *conv) const {
+        if (!m->use_tc || !w.b_hi) return false;
+        if (conv && (conv->kh != 1 || conv->kw != 1 || conv->sy != 1 || conv->sx != 1)) return false;
+        const long long M = (long long)x.n * x.h * x.w;
+        return (w.K % 4) == 0 && w.K >= 32 && w.ncols >= 64 && M >= 128;
+    }
+    void gemm_tc(const Tensor &x, const LeafWeights &w, int act, float *y) {
+        const long long M = (long long)x.n * x.h * x.w;
+        const int K = w.K, N = w.ncols;
+        float *a_hi = (float *)m->arena.alloc((size_t)M * K * sizeof(float));
+        float *a_lo = (float *)m->arena.alloc((size_t)M * K * sizeof(float));
+        if (dry) return;
+        LAUNCH(m, tc::k_split_tf32, grid1d(M * K / 4, 256, m->sm_count), 256, 0, st, x.p, a_hi, a_lo, M * K / 4);
+        CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
+        if (!tc::make_map_2d(&ta_hi, a_hi, (uint64_t)M, (uint64_t)K, tc::BM) || !tc::make_map_2d(&ta_lo, a_lo, (uint64_t)M, (uint64_t)K, tc::BM) ||
+            !tc::make_map_2d(&tb_hi, w.b_hi, (uint64_t)N, (uint64_t)K, tc::BN) || !tc::make_map_2d(&tb_lo, w.b_lo, (uint64_t)N, (uint64_t)K, tc::BN))
+            throw CudaError("cuTensorMapEncodeTiled failed");
+        static bool attr_set = false;
+        if (!attr_set) { CK(cudaFuncSetAttribute(tc::k_gemm_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES)); attr_set = true; }
+        tc::GemmTcParams gp; gp.c = y; gp.bias = w.bias; gp.M = (int)M; gp.N = N; gp.K = K; gp.ldc = N; gp.act = act;
+        const int ntiles = (int)((M + tc::BM - 1) / tc::BM) * ((N + tc::BN - 1) / tc::BN);
+        LAUNCH(m, tc::k_gemm_tc, (unsigned)std::min(ntiles, m->sm_count), tc::THREADS, tc::SMEM_BYTES, st, ta_hi, ta_lo, tb_hi, tb_lo, gp);
+    }
+
     void gemm(const Tensor &x, const LeafWeights &w, const Node *conv, int act, float *y, int64_t Ho, int64_t Wo) {
+        if (tc_eligible(x, w, conv)) { gemm_tc(x, w, act, y); return; }
+        if (dry) return;
         ConvParams p;
         p.x = x.p; p.wt = w.wt; p.bias = w.bias; p.y = y;
         p.N = (int)x.n; p.H = (int)x.h; p.W = (int)x.w; p.Cin = (int)x.c; p.Ho = (int)Ho; p.Wo = (int)Wo;
@@ -224,8 +281,8 @@ struct Exec {
         switch (n.kind) {
         case K_CONV: {
             y = mk(dout);
+            gemm(x, w, &n, n.act, y.p, dout.h, dout.w);
             if (!dry) {
-                gemm(x, w, &n, n.act, y.p, dout.h, dout.w);
                 if (n.act == ACT_SOFTMAX) {
                     long long rows = (long long)y.n * y.h * y.w;
                     LAUNCH(m, k_softmax_rows, (unsigned)((rows + 7) / 8), 256, 0, st, y.p, rows, (int)y.c);
@@ -235,7 +292,7 @@ struct Exec {
         }
         case K_LINEAR: {
             y = mk(dout);
-            if (!dry) gemm(x, w, nullptr, ACT_LINEAR, y.p, x.h, x.w);
+            gemm(x, w, nullptr, ACT_LINEAR, y.p, x.h, x.w);
             break;
         }
         case K_POOL: {
@@ -298,8 +355,8 @@ struct Exec {
             Dims dfull = din; dfull.c = dirs * hid;
             Tensor full = mk(dfull);
             int *dl = packed ? dev_lens(lens) : nullptr;
+            if (full.numel()) { StageTimer tt(m, st, n.name + ".xproj", !dry); gemm(x, w, nullptr, ACT_LINEAR, gx.p, x.h, x.w); }
             if (!dry && full.numel()) {
-                { StageTimer tt(m, st, n.name + ".xproj", true); gemm(x, w, nullptr, ACT_LINEAR, gx.p, x.h, x.w); }
                 StageTimer tt(m, st, n.name + ".rec", true);
                 LstmParams lp;
                 lp.gx = gx.p; lp.whh = w.aux; lp.out = full.p; lp.lens = dl; lp.hid = hid; lp.dirs = dirs;
@@ -404,6 +461,7 @@ static ForwardResult forward_impl(kb_model *m, const float *x, int x_on_device, 
                                   cudaStream_t st, size_t extra_bytes) {
     const Plan &pl = *m->plan;
     const int C = pl.input[1];
+    { const char *e = getenv("KB_GEMM"); m->use_tc = !(e && strcmp(e, "ffma") == 0); }
     if (n <= 0 || h <= 0 || w <= 0) throw ShapeError("empty input batch");
     if (pl.input[2] > 0 && h != pl.input[2] && pl.input[2] != 1)
         ;   // the reference does not check the declared height either; convs accept any H
@@ -840,6 +898,34 @@ int kb_debug_layer_output(kb_model *m, const char *name, int32_t dims[4], float 
         if (e == cudaSuccess) e = cudaMemcpy(out_host, tmp, elems * 4, cudaMemcpyDeviceToHost);
         cudaFree(tmp);
         if (e != cudaSuccess) throw CudaError(std::string("layer output copy failed: ") + cudaGetErrorString(e));
+        return (int)KB_OK;
+    });
+}
+
+int kb_debug_gemm(const float *a, const float *b, const float *bias, float *c, int32_t M, int32_t N, int32_t K, int use_tc, int device) {
+    if (!a || !b || !c || M <= 0 || N <= 0 || K <= 0) return fail(KB_ERR_ARG, "invalid arguments");
+    return guarded([&]() {
+        int cnt = 0;
+        if (cudaGetDeviceCount(&cnt) != cudaSuccess || cnt == 0) { cudaGetLastError(); throw CudaError("no CUDA device available: kraken_b200 has no CPU fallback"); }
+        CK(cudaSetDevice(device));
+        kb_model tmp; tmp.device = device; tmp.use_tc = use_tc != 0;
+        cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, device)); tmp.sm_count = prop.multiProcessorCount;
+        LeafWeights w; w.K = K; w.ncols = N; w.ncp = (N + 63) / 64 * 64;
+        std::vector<float> rows(b, b + (size_t)N * K), wt((size_t)K * w.ncp, 0.f);
+        for (int n = 0; n < N; ++n) for (int k = 0; k < K; ++k) wt[(size_t)k * w.ncp + n] = rows[(size_t)n * K + k];
+        w.wt = upload(&tmp, wt);
+        if (bias) w.bias = upload(&tmp, std::vector<float>(bias, bias + N));
+        upload_split(&tmp, rows, w);
+        const size_t abytes = (size_t)M * K * 4, cbytes = (size_t)M * N * 4;
+        CK(cudaMalloc((void **)&tmp.arena.base, 3 * abytes + cbytes + 65536)); tmp.arena.cap = 3 * abytes + cbytes + 65536;
+        Tensor x; x.n = 1; x.h = 1; x.w = M; x.c = K; x.p = (float *)tmp.arena.alloc(abytes);
+        float *dc = (float *)tmp.arena.alloc(cbytes);
+        CK(cudaMemcpy(x.p, a, abytes, cudaMemcpyHostToDevice));
+        Exec ex{&tmp, nullptr, false};
+        if (use_tc && !ex.tc_eligible(x, w, nullptr)) throw Unsupported("shape not eligible for the tcgen05 GEMM (need K % 4 == 0, K >= 32, N >= 64, M >= 128)");
+        ex.gemm(x, w, nullptr, ACT_LINEAR, dc, 1, M);
+        CK(cudaDeviceSynchronize());
+        CK(cudaMemcpy(c, dc, cbytes, cudaMemcpyDeviceToHost));
         return (int)KB_OK;
     });
 }
