@@ -252,15 +252,8 @@ def main():
         _, _, w = oracle_model(0)                        # same seeded weights the parity tests use
         m.load_state_dict(w)
     if world > 1:
-        sd = m.state_dict()
-        blob = torch.cat([sd[k].flatten() for k in sd]).to(dev)
-        dist.broadcast(blob, src=0)
-        off = 0
-        new = {}
-        for k, v in sd.items():
-            new[k] = blob[off:off + v.numel()].view(v.shape).cpu()
-            off += v.numel()
-        m.load_state_dict(new)
+        from kraken_b200.dist import broadcast_state_dict
+        m.load_state_dict(broadcast_state_dict(m.state_dict(), src=0, device=torch.device(dev)))
     rec = kb.TorchSeqRecognizer(m, device=dev)
     lens = torch.full((BATCH,), WIDTH, dtype=torch.long)
 
@@ -287,17 +280,14 @@ def main():
             if on_step is not None:
                 on_step()
         if world > 1:
-            # the single gather of the run's decoded label sequences to rank 0 (fixed-stride pack per line:
-            # count + (label, start, end) x T); payload is bandwidth-trivial over NVLink
-            pack = torch.zeros((len(sink), BATCH, 1 + 3 * T), dtype=torch.int32)
-            for si, stepdec in enumerate(sink):
-                for li, d in enumerate(stepdec):
-                    pack[si, li, 0] = len(d)
-                    if d:
-                        pack[si, li, 1:1 + 3 * len(d)] = torch.tensor([v for t in d for v in t[:3]], dtype=torch.int32)
-            pack = pack.to(dev)
-            out = [torch.empty_like(pack) for _ in range(world)] if rank == 0 else None
-            dist.gather(pack, out, dst=0)
+            # the single gather of the run's decoded label sequences to rank 0 (fixed-stride int32 blocks over NCCL)
+            from kraken_b200.dist import gather_decoded
+            flat = [d for stepdec in sink for d in stepdec]
+            base = rank * len(flat)
+            gathered = gather_decoded(list(range(base, base + len(flat))), flat, total=world * len(flat), stride=T,
+                                      dst=0, device=torch.device(dev))
+            if rank == 0:
+                assert len(gathered) == world * len(flat)
         e1.record()
         barrier()
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)

@@ -42,4 +42,6 @@ def test_gemm_tc_special_values_and_no_bias():
     a[5, :] = np.linspace(-3, 3, 64, dtype=np.float32)
     b = np.eye(64, dtype=np.float32)[np.arange(128) % 64]
     c = gemm(a, b, None, True)
-    assert np.array_equal(c, a @ b.T)            # exact: products of small integers / single terms
+    ref = a @ b.T                                  # single-term sums: only the TF32 truncation of the `lo` plane (2^-22) remains
+    assert np.abs(c - ref).max() <= 1e-6 * np.abs(ref).max()
+    assert np.array_equal(c[:5], ref[:5])          # 0/1 data is exact
