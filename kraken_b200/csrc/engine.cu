@@ -74,6 +74,7 @@ struct kb_model {
     std::vector<Stage> stages;       // event pool, reused across calls
     size_t n_stages = 0;             // entries used by the most recent call
     int sm_count = 148;
+    int max_clusters8 = -1;          // co-resident 8-CTA clusters of the recurrence kernel (queried once)
     bool use_tc = true;              // tcgen05 GEMM path (KB_GEMM=ffma forces the CUDA-core kernel)
     ~kb_model() {
         if (device >= 0) {
@@ -374,20 +375,32 @@ struct Exec {
                 at[0].id = cudaLaunchAttributeClusterDimension;
                 at[0].val.clusterDim.x = (unsigned)ks; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
                 cfg.attrs = at; cfg.numAttrs = 1;
-                if (getenv("KB_DEBUG")) {
-                    int ncl = -1;
-                    cudaError_t oe = ks == 8 ? cudaOccupancyMaxActiveClusters(&ncl, k_lstm_rec<8>, &cfg)
-                                   : ks == 4 ? cudaOccupancyMaxActiveClusters(&ncl, k_lstm_rec<4>, &cfg)
-                                   : ks == 2 ? cudaOccupancyMaxActiveClusters(&ncl, k_lstm_rec<2>, &cfg)
-                                             : cudaOccupancyMaxActiveClusters(&ncl, k_lstm_rec<1>, &cfg);
-                    fprintf(stderr, "[kb] %s: lstm rec ks=%d clusters=%d x %d dirs, T=%d, max co-resident clusters=%d (%s)\n", n.name.c_str(), ks,
-                            nchunks, dirs, lp.T, ncl, cudaGetErrorString(oe));
+                bool lines10 = false;
+                if (ks == 8) {
+                    // only ~15 clusters of 8 CTAs are co-resident on a B200; with 10 lines per cluster cfg2's 64 lines x 2
+                    // directions need 14 clusters (one wave) instead of 16 (two waves)
+                    if (m->max_clusters8 < 0) {
+                        int ncl = 0;
+                        if (cudaOccupancyMaxActiveClusters(&ncl, k_lstm_rec<8, 8>, &cfg) != cudaSuccess) { cudaGetLastError(); ncl = 0; }
+                        m->max_clusters8 = ncl;
+                    }
+                    const int c8 = nchunks * dirs, c10 = ((lp.nseq + 9) / 10) * dirs;
+                    const int cap = std::max(m->max_clusters8, 1);
+                    lines10 = (c10 + cap - 1) / cap < (c8 + cap - 1) / cap;
+                    if (getenv("KB_LSTM_LINES")) lines10 = atoi(getenv("KB_LSTM_LINES")) == 10;
+                    if (lines10) cfg.gridDim = dim3((unsigned)(ks * ((lp.nseq + 9) / 10)), (unsigned)dirs, 1);
+                    if (getenv("KB_DEBUG"))
+                        fprintf(stderr, "[kb] %s: lstm rec ks=8 lines/cluster=%d clusters=%u, T=%d, max co-resident clusters=%d\n", n.name.c_str(),
+                                lines10 ? 10 : 8, cfg.gridDim.x / 8 * dirs, lp.T, m->max_clusters8);
                 }
                 switch (ks) {
-                case 1: CK(cudaLaunchKernelEx(&cfg, k_lstm_rec<1>, lp)); break;
-                case 2: CK(cudaLaunchKernelEx(&cfg, k_lstm_rec<2>, lp)); break;
-                case 4: CK(cudaLaunchKernelEx(&cfg, k_lstm_rec<4>, lp)); break;
-                default: CK(cudaLaunchKernelEx(&cfg, k_lstm_rec<8>, lp)); break;
+                case 1: CK(cudaLaunchKernelEx(&cfg, k_lstm_rec<1, 8>, lp)); break;
+                case 2: CK(cudaLaunchKernelEx(&cfg, k_lstm_rec<2, 8>, lp)); break;
+                case 4: CK(cudaLaunchKernelEx(&cfg, k_lstm_rec<4, 8>, lp)); break;
+                default:
+                    if (lines10) CK(cudaLaunchKernelEx(&cfg, k_lstm_rec<8, 10>, lp));
+                    else CK(cudaLaunchKernelEx(&cfg, k_lstm_rec<8, 8>, lp));
+                    break;
                 }
                 ++m->launches;
                 CK(cudaPeekAtLastError());

@@ -34,7 +34,9 @@ namespace tc {
 constexpr int BM = 128, BN = 256, BK = 32, STAGES = 2;
 constexpr int A_TILE = BM * BK * 4, B_TILE = BN * BK * 4;                 // bytes
 constexpr int STAGE_BYTES = 2 * A_TILE + 2 * B_TILE;                      // 96 KB
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int EPI_LD = 36;                                                // padded row of the per-warp 32x32 staging tile
+constexpr int EPI_BYTES = 4 * 32 * EPI_LD * 4;                            // 4 epilogue warps
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + EPI_BYTES;
 constexpr int THREADS = 192;
 constexpr int TMEM_COLS = 512;
 
@@ -121,6 +123,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ C
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + STAGES * STAGE_BYTES);
     uint64_t *full = bars, *empty = bars + STAGES, *tfull = bars + 2 * STAGES, *tempty = bars + 2 * STAGES + 2;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * STAGES + 4);
+    float *epi_stage = reinterpret_cast<float *>(smem + STAGES * STAGE_BYTES + 256);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tiles_m = (p.M + BM - 1) / BM, tiles_n = (p.N + BN - 1) / BN;
@@ -198,8 +201,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ C
             const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
             mbar_wait(&tfull[0], acc_phase);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const int m = m0 + q * 32 + lane;
-            float *crow = p.c + (size_t)m * p.ldc;
+            float *stg = epi_stage + (warp - 2) * 32 * EPI_LD;
             const bool vec = (p.ldc & 3) == 0 && (p.N & 3) == 0;
 #pragma unroll 1
             for (int c0 = 0; c0 < BN; c0 += 32) {
@@ -208,24 +210,33 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ C
                 const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
                 tmem_ld32(lane_base + (uint32_t)c0, v);
                 tmem_ld32(lane_base + (uint32_t)(BN + c0), cr);
+                // row = lane: main + correction (+ bias, activation), staged so that the global stores below are
+                // row-contiguous (each store instruction writes 4 rows x 128 B instead of 32 rows x 16 B)
 #pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] += cr[j];
-                if (m < p.M) {
+                for (int j = 0; j < 32; j += 4) {
+                    const int n = n0 + c0 + j;
+                    float4 o;
+                    o.x = v[j] + cr[j]; o.y = v[j + 1] + cr[j + 1]; o.z = v[j + 2] + cr[j + 2]; o.w = v[j + 3] + cr[j + 3];
+                    if (p.bias) {
+                        o.x += (n + 0 < p.N) ? __ldg(p.bias + n + 0) : 0.f; o.y += (n + 1 < p.N) ? __ldg(p.bias + n + 1) : 0.f;
+                        o.z += (n + 2 < p.N) ? __ldg(p.bias + n + 2) : 0.f; o.w += (n + 3 < p.N) ? __ldg(p.bias + n + 3) : 0.f;
+                    }
+                    o.x = act_apply(o.x, p.act); o.y = act_apply(o.y, p.act); o.z = act_apply(o.z, p.act); o.w = act_apply(o.w, p.act);
+                    *reinterpret_cast<float4 *>(stg + lane * EPI_LD + j) = o;
+                }
+                __syncwarp();
 #pragma unroll
-                    for (int j = 0; j < 32; j += 4) {
-                        const int n = n0 + c0 + j;
-                        if (vec) {
-                            if (n < p.N) {
-                                float4 b = p.bias ? __ldg(reinterpret_cast<const float4 *>(p.bias + n)) : make_float4(0.f, 0.f, 0.f, 0.f);
-                                *reinterpret_cast<float4 *>(crow + n) = make_float4(act_apply(v[j] + b.x, p.act), act_apply(v[j + 1] + b.y, p.act), act_apply(v[j + 2] + b.z, p.act), act_apply(v[j + 3] + b.w, p.act));
-                            }
-                        } else {
-#pragma unroll
-                            for (int e = 0; e < 4; ++e)
-                                if (n + e < p.N) crow[n + e] = act_apply(v[j + e] + (p.bias ? __ldg(p.bias + n + e) : 0.f), p.act);
-                        }
+                for (int i = 0; i < 8; ++i) {
+                    const int r = i * 4 + (lane >> 3), c4 = (lane & 7) * 4;
+                    const int m = m0 + q * 32 + r, n = n0 + c0 + c4;
+                    if (m < p.M && n < p.N) {
+                        const float4 o = *reinterpret_cast<const float4 *>(stg + r * EPI_LD + c4);
+                        float *dst = p.c + (size_t)m * p.ldc + n;
+                        if (vec) *reinterpret_cast<float4 *>(dst) = o;
+                        else { dst[0] = o.x; if (n + 1 < p.N) dst[1] = o.y; if (n + 2 < p.N) dst[2] = o.z; if (n + 3 < p.N) dst[3] = o.w; }
                     }
                 }
+                __syncwarp();
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();

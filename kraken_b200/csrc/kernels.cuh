@@ -388,10 +388,36 @@ struct LstmParams {
     int q2; long long s_outer, s_inner, step;      // pixel(q, t) = (q / q2) * s_outer + (q % q2) * s_inner + t * step
 };
 
-template <int KSPLIT>
+__device__ __forceinline__ uint32_t cvta_smem(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t saddr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+    return r;
+}
+// remote (or local) shared-memory store that signals `bytes` on the destination CTA's mbarrier when it lands
+__device__ __forceinline__ void st_async_f32(uint32_t raddr, float v, uint32_t rmbar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];" ::"r"(raddr), "r"(__float_as_uint(v)), "r"(rmbar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_parity(uint32_t mbar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "LW_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra LD_%=;\n\t"
+        "bra LW_%=;\n\t"
+        "LD_%=:\n\t}" ::"r"(mbar), "r"(parity) : "memory");
+}
+
+// KSPLIT = cluster size = k-slices; BLT = lines per line-slice (8, or 10 for KSPLIT == 8 so that 64 lines x 2 directions
+// need 14 clusters instead of 16 - only 15 clusters of 8 CTAs are co-resident on a B200).
+template <int KSPLIT, int BLT>
 __global__ void __launch_bounds__(256, 1) k_lstm_rec(LstmParams p) {
-    constexpr int CS = KSPLIT, LSPLIT = 8 / KSPLIT, BL = 8 * LSPLIT, LPT = 8 / KSPLIT, HLD = 36 * KSPLIT;
-    __shared__ __align__(16) float hbuf[2][BL][HLD];
+    static_assert(BLT == 8 || (BLT == 10 && KSPLIT == 8), "unsupported line blocking");
+    constexpr int CS = KSPLIT, LSPLIT = 8 / KSPLIT, BL = BLT * LSPLIT, HLD = 36 * KSPLIT;
+    constexpr int LPT = 8 / KSPLIT;                    // cells of lines 0..7 of a slice owned per lane after the reduce-scatter
+    constexpr int NOWN = BLT == 10 ? 2 : LPT;          // + lines 8,9 owned by lanes ks = 0,1
+    struct Smem { float h[2][BL][HLD]; unsigned long long mbar[2]; };
+    __shared__ __align__(16) Smem sm;
     cg::cluster_group cluster = cg::this_cluster();
     const int tid = threadIdx.x;
     const int ks = tid % KSPLIT, ls = (tid / KSPLIT) % LSPLIT, rg = tid >> 3;
@@ -409,27 +435,30 @@ __global__ void __launch_bounds__(256, 1) k_lstm_rec(LstmParams p) {
             const int k = ks * 32 + kk;
             w[g][kk] = (uvalid && k < hid) ? __ldg(p.whh + ((size_t)dir * 4 * hid + (size_t)g * hid + u) * hid + k) : 0.f;
         }
-    for (int i = tid; i < 2 * BL * HLD; i += 256) (&hbuf[0][0][0])[i] = 0.f;
+    for (int i = tid; i < 2 * BL * HLD; i += 256) (&sm.h[0][0][0])[i] = 0.f;
 
-    int len[LPT]; long long base[LPT]; float cst[LPT];
+    // cells (unit u, line) this lane owns: slot j < LPT -> line ks*LPT + j of the slice; BLT == 10: slot 1 -> line 8 + ks (ks < 2)
+    int len[NOWN], lline[NOWN]; long long base[NOWN]; float cst[NOWN], hlast[NOWN]; bool qvalid[NOWN];
 #pragma unroll
-    for (int j = 0; j < LPT; ++j) {
-        const int q = chunk * BL + ls * 8 + ks * LPT + j;
-        const bool qv = q < p.nseq;
-        int l = qv ? (p.lens ? p.lens[q] : p.T) : 0;
+    for (int j = 0; j < NOWN; ++j) {
+        const bool slot_ok = BLT == 10 ? (j == 0 || ks < 2) : true;
+        lline[j] = BLT == 10 ? (j == 0 ? ks : 8 + ks) : ls * 8 + ks * LPT + j;
+        const int q = chunk * BL + lline[j];
+        qvalid[j] = slot_ok && q < p.nseq;
+        int l = qvalid[j] ? (p.lens ? p.lens[q] : p.T) : 0;
         len[j] = min(max(l, 0), p.T);
-        const int qq = qv ? q : 0;
+        const int qq = qvalid[j] ? q : 0;
         base[j] = (long long)(qq / p.q2) * p.s_outer + (long long)(qq % p.q2) * p.s_inner;
-        cst[j] = 0.f;
+        cst[j] = 0.f; hlast[j] = 0.f;
     }
-    int maxlen = 0;
+    int maxlen = 0, nvalid = 0;
     for (int lb = 0; lb < BL; ++lb) {
         const int q = chunk * BL + lb;
         if (q < p.nseq) {
+            ++nvalid;
             const int l = p.lens ? min(max(p.lens[q], 0), p.T) : p.T;
             maxlen = max(maxlen, l);
-            // zero the padded tail of this CTA's units (pad_packed_sequence pads with 0)
-            if (l < p.T) {
+            if (l < p.T) {              // zero the padded tail of this CTA's units (pad_packed_sequence pads with 0)
                 const long long b0 = (long long)(q / p.q2) * p.s_outer + (long long)(q % p.q2) * p.s_inner;
                 const int nu = min(p.U, hid - rank * p.U);
                 for (int i = tid; i < (p.T - l) * max(nu, 0); i += 256) {
@@ -439,13 +468,29 @@ __global__ void __launch_bounds__(256, 1) k_lstm_rec(LstmParams p) {
             }
         }
     }
-    if (CS > 1) cluster.sync(); else __syncthreads();
+    // hand-off protocol (CS > 1): every owner sends its h_t to all CTAs of the cluster with st.async; the destination's
+    // mbarrier of that buffer counts bytes.  Buffer b is filled during steps s with (s+1)&1 == b and read during step s+1.
+    const uint32_t tx_bytes = (uint32_t)nvalid * (uint32_t)hid * 4u;
+    const uint32_t mbar0 = cvta_smem(&sm.mbar[0]), mbar1 = cvta_smem(&sm.mbar[1]);
+    uint32_t rbase[CS];
+    if (CS > 1) {
+        if (tid == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar0));
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar1));
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            // buffer 1 is filled during step 0
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar1), "r"(tx_bytes) : "memory");
+        }
+#pragma unroll
+        for (int r = 0; r < CS; ++r) rbase[r] = mapa_u32(cvta_smem(&sm), (uint32_t)r);
+        cluster.sync();
+    } else __syncthreads();
 
-    float4 gxc[LPT], gxn[LPT];
+    float4 gxc[NOWN], gxn[NOWN];
     auto load_gx = [&](int s, float4 *dst) {
 #pragma unroll
-        for (int j = 0; j < LPT; ++j) {
-            if (uvalid && s < len[j]) {
+        for (int j = 0; j < NOWN; ++j) {
+            if (uvalid && qvalid[j] && s < len[j]) {
                 const int t = dir ? len[j] - 1 - s : s;
                 dst[j] = __ldg(reinterpret_cast<const float4 *>(p.gx + (size_t)(base[j] + (long long)t * p.step) * GC + (size_t)dir * 4 * hid + (size_t)u * 4));
             } else dst[j] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -455,13 +500,22 @@ __global__ void __launch_bounds__(256, 1) k_lstm_rec(LstmParams p) {
 
     for (int s = 0; s < maxlen; ++s) {
         const int cur = s & 1, nxt = cur ^ 1;
+        if (CS > 1) {
+            if (s > 0) mbar_wait_parity(cur ? mbar1 : mbar0, (uint32_t)(((s - 1) >> 1) & 1));
+            // every thread of the CTA has now seen this phase complete: without this a warp that owns no cells (padding
+            // units) could fall two phases behind and alias the parity bit
+            __syncthreads();
+            // this buffer's next fill happens during step s+1; nobody can send it before receiving our step-s data
+            if (tid == 0 && s + 2 < maxlen)
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(cur ? mbar1 : mbar0), "r"(tx_bytes) : "memory");
+        }
         if (s + 1 < maxlen) load_gx(s + 1, gxn);
-        float v[32];
+        float v[BLT * 4];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = 0.f;
+        for (int i = 0; i < BLT * 4; ++i) v[i] = 0.f;
 #pragma unroll
-        for (int b = 0; b < 8; ++b) {
-            const float *hrow = &hbuf[cur][ls * 8 + b][ks * 36];
+        for (int b = 0; b < BLT; ++b) {
+            const float *hrow = &sm.h[cur][(BLT == 10 ? 0 : ls * 8) + b][ks * 36];
 #pragma unroll
             for (int kq = 0; kq < 8; ++kq) {
                 const float4 hv = *reinterpret_cast<const float4 *>(hrow + kq * 4);
@@ -474,7 +528,19 @@ __global__ void __launch_bounds__(256, 1) k_lstm_rec(LstmParams p) {
                 }
             }
         }
-        // reduce-scatter across the KSPLIT k-slices (adjacent lanes): lane ks ends with lines [ks*LPT, +LPT)
+        // lines 8,9 (BLT == 10): butterfly all-reduce over the 8 k-slices, lanes 0/1 keep line 8/9
+        float x89[4] = {0.f, 0.f, 0.f, 0.f};
+        if (BLT == 10) {
+#pragma unroll
+            for (int i = 32; i < 40; ++i) {
+                float t = v[i];
+                t += __shfl_xor_sync(0xffffffffu, t, 4); t += __shfl_xor_sync(0xffffffffu, t, 2); t += __shfl_xor_sync(0xffffffffu, t, 1);
+                v[i] = t;
+            }
+#pragma unroll
+            for (int g = 0; g < 4; ++g) x89[g] = (ks & 1) ? v[36 + g] : v[32 + g];
+        }
+        // lines 0..7: reduce-scatter across the KSPLIT k-slices (adjacent lanes): lane ks ends with lines [ks*LPT, +LPT)
         if (KSPLIT >= 8) {
             const bool up = ks & 4;
 #pragma unroll
@@ -492,29 +558,45 @@ __global__ void __launch_bounds__(256, 1) k_lstm_rec(LstmParams p) {
 #pragma unroll
             for (int i = 0; i < n / 2; ++i) { const float snd = up ? v[i] : v[i + n / 2], kp = up ? v[i + n / 2] : v[i]; v[i] = kp + __shfl_xor_sync(0xffffffffu, snd, 1); }
         }
-        // gate non-linearities + state update for the (unit, line) pairs this lane owns
+        // gate non-linearities + state update for the (unit, line) cells this lane owns, then the hand-off
+        float hout[NOWN]; bool act[NOWN];
 #pragma unroll
-        for (int j = 0; j < LPT; ++j) {
-            if (uvalid && s < len[j]) {
-                const int t = dir ? len[j] - 1 - s : s;
-                const float ig = sigmoidf_acc(v[j * 4 + 0] + gxc[j].x);
-                const float fg = sigmoidf_acc(v[j * 4 + 1] + gxc[j].y);
-                const float gg = tanhf(v[j * 4 + 2] + gxc[j].z);
-                const float og = sigmoidf_acc(v[j * 4 + 3] + gxc[j].w);
+        for (int j = 0; j < NOWN; ++j) {
+            act[j] = uvalid && qvalid[j] && s < len[j];
+            const float pi = (BLT == 10 && j == 1) ? x89[0] : v[j * 4 + 0], pf = (BLT == 10 && j == 1) ? x89[1] : v[j * 4 + 1];
+            const float pg = (BLT == 10 && j == 1) ? x89[2] : v[j * 4 + 2], po = (BLT == 10 && j == 1) ? x89[3] : v[j * 4 + 3];
+            if (act[j]) {
+                const float ig = sigmoidf_acc(pi + gxc[j].x), fg = sigmoidf_acc(pf + gxc[j].y);
+                const float gg = tanhf(pg + gxc[j].z), og = sigmoidf_acc(po + gxc[j].w);
                 cst[j] = fg * cst[j] + ig * gg;
-                const float h = og * tanhf(cst[j]);
-                p.out[(size_t)(base[j] + (long long)t * p.step) * OC + dir * hid + u] = h;
-                float *slot = &hbuf[nxt][ls * 8 + ks * LPT + j][(u >> 5) * 36 + (u & 31)];
-                if (CS > 1) {
+                hlast[j] = og * tanhf(cst[j]);
+            }
+            hout[j] = hlast[j];
+        }
+        if (s + 1 < maxlen) {
 #pragma unroll
-                    for (int r = 0; r < CS; ++r) *cluster.map_shared_rank(slot, r) = h;
-                } else *slot = h;
+            for (int j = 0; j < NOWN; ++j) {
+                if (uvalid && qvalid[j]) {          // finished lines keep sending their last h so byte counts stay constant
+                    const uint32_t off = (uint32_t)((((nxt * BL) + lline[j]) * HLD + (u >> 5) * 36 + (u & 31)) * 4);
+                    if (CS > 1) {
+                        const uint32_t mb_off = (uint32_t)(sizeof(float) * 2 * BL * HLD) + (uint32_t)nxt * 8u;
+#pragma unroll
+                        for (int r = 0; r < CS; ++r) st_async_f32(rbase[r] + off, hout[j], rbase[r] + mb_off);
+                    } else sm.h[nxt][lline[j]][(u >> 5) * 36 + (u & 31)] = hout[j];
+                }
             }
         }
 #pragma unroll
-        for (int j = 0; j < LPT; ++j) gxc[j] = gxn[j];
-        if (CS > 1) cluster.sync(); else __syncthreads();
+        for (int j = 0; j < NOWN; ++j) {
+            if (act[j]) {
+                const int t = dir ? len[j] - 1 - s : s;
+                p.out[(size_t)(base[j] + (long long)t * p.step) * OC + dir * hid + u] = hout[j];
+            }
+            gxc[j] = gxn[j];
+        }
+        if (CS == 1) __syncthreads();
     }
+    if (CS > 1) cluster.sync();          // nobody exits while a peer may still address its shared memory
 }
 
 // =============================================================================================
