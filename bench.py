@@ -56,6 +56,9 @@ def stage_work(W=WIDTH):
         'L_5.rec': (2 * T * 2 * 1024 * 256, f * (2048 * T + 512 * T)),
         'O_6': (2 * T * 512 * 200, f * (512 * T + 200 * T)),
         'decode': (0, f * (200 * T) + 16 * T),
+        # fused groups (same FLOPs, only the group's external input/output touch HBM; hi+lo TF32 planes count as output)
+        'C_0+Mp_1': (2 * 48 * W * 32 * 9, f * (48 * W + 3 * 24 * w2 * 32)),
+        'C_2+Mp_3+S_4': (2 * 24 * w2 * 64 * 288, f * (2 * 24 * w2 * 32 + 3 * 768 * T)),
     }
 
 

@@ -1,0 +1,262 @@
+// conv_tc.cuh - tcgen05 implicit-GEMM convolution (Cin = 32, stride 1, no dilation) with fused epilogue for sm_100a.
+//
+//   ActConv2D -> [Dropout] -> [MaxPool 2x2/2] -> [Dropout] -> [Reshape S1(1x0)1,3] -> (TF32 planes for the LSTM projection)
+//   kraken/lib/vgsl/layers.py:842-852, 381-388, 313-335
+//
+// Work item = one image n, one PAIR of output rows (h0, h0+1), 128 output columns.  In NHWC one pixel's 32 input
+// channels are exactly one 128-byte swizzle row, so the im2col matrix never exists:
+//   * TMA (4-D tensor map C,W,H,N; box 32 x (128+kw-1) x 1 x 1, 128B swizzle) brings the kh+1 input rows a row pair
+//     needs into shared memory ONCE; out-of-bounds coordinates are zero-filled by the TMA unit = the conv's zero padding
+//   * the A operand of tap (ky, kx) for output row r is the row buffer (ky + r) with its UMMA descriptor start address
+//     advanced by kx pixel rows (128 B each; descriptor base_offset = kx & 7 keeps the swizzle phase right)
+//   * B operand = the tap's [Cout][32] weight slice, streamed through a 3-stage TMA ring
+//   * 3xTF32 split as in gemm_tc.cuh: per tap and K=8 step  corr += a_lo*b_hi + a_hi*b_lo ; main += a_hi*b_hi, for both
+//     output rows -> 4 TMEM accumulators of Cout columns (two sets when 8*Cout <= 512, so the epilogue overlaps the MMAs)
+//   * epilogue: one thread = one output column of the tile and holds BOTH rows -> the vertical half of the 2x2 max-pool is
+//     a register max, the horizontal half one shuffle; bias/activation; the store is strided so that the `S` fold
+//     (h into the feature axis) costs nothing; optional TF32 hi/lo planes for the consumer GEMM.
+#pragma once
+#include "gemm_tc.cuh"
+
+namespace kb {
+namespace ctc {
+
+using namespace kb::tc;
+
+constexpr int TW = 128;                  // output columns per work item
+constexpr int NSTB = 3;                  // weight-tile ring stages
+constexpr int CTHREADS = 192;
+constexpr int MAX_ROWS = 8;              // kh + 1 <= 8
+
+struct ConvTcParams {
+    const float *bias; float *y; float *y_hi; float *y_lo;
+    int N, Ho, Wo, Cout, kh, kw, py, px, act, pool;
+    int items_h, items_w;                // row pairs, column segments
+    long long sN, sH, sW;                // output strides (floats) of (n, out row, out col); channel stride 1
+    int out_h, out_w;                    // valid output extent (pooled when pool)
+    int a_row_bytes;                     // bytes of one plane of one input-row buffer (multiple of 1024)
+    int acc_sets;
+};
+
+__device__ __forceinline__ void tma_load_4d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                 ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ uint64_t umma_desc_sw128_off(uint32_t saddr, uint32_t base_off) {
+    return umma_desc_sw128(saddr) | ((uint64_t)(base_off & 7) << 49);
+}
+
+__global__ void __launch_bounds__(CTHREADS, 1)
+k_conv_tc(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ CUtensorMap tm_x_lo,
+          const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant__ CUtensorMap tm_w_lo, ConvTcParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int R = p.kh + 1, taps = p.kh * p.kw;
+    const int a_plane = p.a_row_bytes, a_row = 2 * a_plane;              // hi | lo
+    const int b_plane = p.Cout * 128, b_stage = 2 * b_plane;
+    uint8_t *a_base = smem, *b_base = smem + R * a_row;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(b_base + NSTB * b_stage);
+    uint64_t *full_a = bars, *empty_a = bars + MAX_ROWS, *full_b = bars + 2 * MAX_ROWS, *empty_b = full_b + NSTB;
+    uint64_t *tfull = empty_b + NSTB, *tempty = tfull + 2;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nitems = p.N * p.items_h * p.items_w;
+    const uint32_t a_tx = (uint32_t)(2 * (TW + p.kw - 1) * 128), b_tx = (uint32_t)b_stage;
+
+    if (threadIdx.x == 0) {
+        for (int r = 0; r < R; ++r) { mbar_init(&full_a[r], 1); mbar_init(&empty_a[r], 1); }
+        for (int s = 0; s < NSTB; ++s) { mbar_init(&full_b[s], 1); mbar_init(&empty_b[s], 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (elect_one()) {
+            uint32_t a_phase = 0; int bs = 0; uint32_t b_phase = 0;
+            for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+                const int ws = item % p.items_w, hp = (item / p.items_w) % p.items_h, n = item / (p.items_w * p.items_h);
+                const int h0 = 2 * hp - p.py, w0 = ws * TW - p.px;
+                int r_loaded = 0;
+                // interleave: input row r is needed from tap row ky = r - 1 on; weight tiles in (ky, kx) order
+                for (int ky = 0; ky < p.kh; ++ky) {
+                    for (; r_loaded <= ky + 1; ++r_loaded) {
+                        mbar_wait(&empty_a[r_loaded], a_phase ^ 1);
+                        mbar_expect_tx(&full_a[r_loaded], a_tx);
+                        tma_load_4d(a_base + r_loaded * a_row, &tm_x_hi, &full_a[r_loaded], 0, w0, h0 + r_loaded, n);
+                        tma_load_4d(a_base + r_loaded * a_row + a_plane, &tm_x_lo, &full_a[r_loaded], 0, w0, h0 + r_loaded, n);
+                    }
+                    for (int kx = 0; kx < p.kw; ++kx) {
+                        mbar_wait(&empty_b[bs], b_phase ^ 1);
+                        mbar_expect_tx(&full_b[bs], b_tx);
+                        tma_load_2d(b_base + bs * b_stage, &tm_w_hi, &full_b[bs], 0, (ky * p.kw + kx) * p.Cout);
+                        tma_load_2d(b_base + bs * b_stage + b_plane, &tm_w_lo, &full_b[bs], 0, (ky * p.kw + kx) * p.Cout);
+                        if (++bs == NSTB) { bs = 0; b_phase ^= 1; }
+                    }
+                }
+                a_phase ^= 1;
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        const uint32_t idesc = idesc_tf32(128, p.Cout);
+        uint32_t a_phase = 0; int bs = 0; uint32_t b_phase = 0; int acc = 0; uint32_t acc_phase = 0;
+        for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+            mbar_wait(&tempty[acc], acc_phase ^ 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t d0 = tmem_base + (uint32_t)(acc * 4 * p.Cout);
+            for (int ky = 0; ky < p.kh; ++ky) {
+                if (ky == 0) mbar_wait(&full_a[0], a_phase);
+                mbar_wait(&full_a[ky + 1], a_phase);
+                for (int kx = 0; kx < p.kw; ++kx) {
+                    mbar_wait(&full_b[bs], b_phase);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    if (elect_one()) {
+                        const uint32_t sb = smem_u32(b_base + bs * b_stage);
+                        const uint64_t b_hi = umma_desc_sw128(sb), b_lo = umma_desc_sw128(sb + b_plane);
+                        const bool first = (ky | kx) == 0;
+#pragma unroll
+                        for (int r = 0; r < 2; ++r) {
+                            const uint32_t sa = smem_u32(a_base + (ky + r) * a_row) + (uint32_t)kx * 128u;
+                            const uint64_t a_hi = umma_desc_sw128_off(sa, (uint32_t)kx), a_lo = umma_desc_sw128_off(sa + a_plane, (uint32_t)kx);
+                            const uint32_t d_main = d0 + (uint32_t)(2 * r * p.Cout), d_corr = d_main + (uint32_t)p.Cout;
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                const uint64_t adv = (uint64_t)((k * 32) >> 4);
+                                umma_tf32(d_corr, a_lo + adv, b_hi + adv, idesc, (first && k == 0) ? 0u : 1u);
+                                umma_tf32(d_corr, a_hi + adv, b_lo + adv, idesc, 1u);
+                                umma_tf32(d_main, a_hi + adv, b_hi + adv, idesc, (first && k == 0) ? 0u : 1u);
+                            }
+                        }
+                        umma_commit(&empty_b[bs]);
+                        if (kx == p.kw - 1) {
+                            // input row buffers whose last reader was this tap row: row ky (and kh when ky == kh-1)
+                            umma_commit(&empty_a[ky]);
+                            if (ky == p.kh - 1) { umma_commit(&empty_a[p.kh]); umma_commit(&tfull[acc]); }
+                        }
+                    }
+                    __syncwarp();
+                    if (++bs == NSTB) { bs = 0; b_phase ^= 1; }
+                }
+            }
+            a_phase ^= 1;
+            if (p.acc_sets == 2) { if (++acc == 2) { acc = 0; acc_phase ^= 1; } }
+            else acc_phase ^= 1;
+        }
+    } else {
+        // ===================== epilogue (warps 2..5): thread = output column of the tile, both rows =====================
+        const int q = warp & 3;
+        int acc = 0; uint32_t acc_phase = 0;
+        for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+            const int ws = item % p.items_w, hp = (item / p.items_w) % p.items_h, n = item / (p.items_w * p.items_h);
+            mbar_wait(&tfull[acc], acc_phase);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 4 * p.Cout);
+            const int wcol = ws * TW + q * 32 + lane;                       // conv output column
+#pragma unroll 1
+            for (int c0 = 0; c0 < p.Cout; c0 += 32) {
+                float v0[32], v1[32];
+                {
+                    float t[32];
+                    tmem_ld32(lane_base + (uint32_t)c0, v0);
+                    tmem_ld32(lane_base + (uint32_t)(p.Cout + c0), t);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v0[j] += t[j];
+                    tmem_ld32(lane_base + (uint32_t)(2 * p.Cout + c0), v1);
+                    tmem_ld32(lane_base + (uint32_t)(3 * p.Cout + c0), t);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v1[j] += t[j];
+                }
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const float b = p.bias ? __ldg(p.bias + c0 + j) : 0.f;
+                    v0[j] = act_apply(v0[j] + b, p.act); v1[j] = act_apply(v1[j] + b, p.act);
+                }
+                if (p.pool) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        float mx = fmaxf(v0[j], v1[j]);
+                        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+                        v0[j] = mx;
+                    }
+                    const int wp = wcol >> 1;
+                    if ((lane & 1) == 0 && hp < p.out_h && wp < p.out_w) {
+                        const size_t off = (size_t)((long long)n * p.sN + (long long)hp * p.sH + (long long)wp * p.sW) + c0;
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            *reinterpret_cast<float4 *>(p.y + off + j) = make_float4(v0[j], v0[j + 1], v0[j + 2], v0[j + 3]);
+                            if (p.y_hi) {
+                                float h[4], l[4];
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) { uint32_t tt; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(tt) : "f"(v0[j + e])); h[e] = __uint_as_float(tt); l[e] = v0[j + e] - h[e]; }
+                                *reinterpret_cast<float4 *>(p.y_hi + off + j) = make_float4(h[0], h[1], h[2], h[3]);
+                                *reinterpret_cast<float4 *>(p.y_lo + off + j) = make_float4(l[0], l[1], l[2], l[3]);
+                            }
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int r = 0; r < 2; ++r) {
+                        const int ho = 2 * hp + r;
+                        if (ho < p.out_h && wcol < p.out_w) {
+                            const size_t off = (size_t)((long long)n * p.sN + (long long)ho * p.sH + (long long)wcol * p.sW) + c0;
+                            const float *v = r ? v1 : v0;
+#pragma unroll
+                            for (int j = 0; j < 32; j += 4) {
+                                *reinterpret_cast<float4 *>(p.y + off + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                                if (p.y_hi) {
+                                    float h[4], l[4];
+#pragma unroll
+                                    for (int e = 0; e < 4; ++e) { uint32_t tt; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(tt) : "f"(v[j + e])); h[e] = __uint_as_float(tt); l[e] = v[j + e] - h[e]; }
+                                    *reinterpret_cast<float4 *>(p.y_hi + off + j) = make_float4(h[0], h[1], h[2], h[3]);
+                                    *reinterpret_cast<float4 *>(p.y_lo + off + j) = make_float4(l[0], l[1], l[2], l[3]);
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[acc]);
+            if (p.acc_sets == 2) { if (++acc == 2) { acc = 0; acc_phase ^= 1; } }
+            else acc_phase ^= 1;
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    }
+}
+
+// NHWC fp32 activation [N][H][W][32] as a 4-D tensor map (C, W, H, N); box = 32 x box_w x 1 x 1, 128B swizzle, OOB -> 0
+inline bool make_map_nhwc32(CUtensorMap *map, const float *base, uint64_t N, uint64_t H, uint64_t W, uint32_t box_w) {
+    PFN_encodeTiled enc = get_encode();
+    if (!enc) return false;
+    cuuint64_t dims[4] = {32, W, H, N};
+    cuuint64_t strides[3] = {32 * sizeof(float), W * 32 * sizeof(float), H * W * 32 * sizeof(float)};
+    cuuint32_t box[4] = {32, box_w, 1, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+inline size_t conv_tc_smem(int kh, int kw, int cout, int *a_row_bytes) {
+    const int plane = ((TW + kw - 1) * 128 + 1023) & ~1023;
+    if (a_row_bytes) *a_row_bytes = plane;
+    return (size_t)(kh + 1) * 2 * plane + (size_t)NSTB * 2 * cout * 128 + 512 + 1024;
+}
+
+}  // namespace ctc
+}  // namespace kb

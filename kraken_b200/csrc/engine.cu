@@ -13,6 +13,7 @@
 #include "../../include/kraken_b200.h"
 #include "kernels.cuh"
 #include "gemm_tc.cuh"
+#include "conv_tc.cuh"
 #include "vgsl_plan.hpp"
 
 namespace kb {
@@ -28,7 +29,11 @@ struct CudaError : std::runtime_error { using std::runtime_error::runtime_error;
             throw CudaError(std::string(#call) + " failed: " + cudaGetErrorString(_e) + " (" __FILE__ ":" + std::to_string(__LINE__) + ")"); \
     } while (0)
 
-struct Tensor { float *p = nullptr; int64_t n = 0, h = 0, w = 0, c = 0; int64_t numel() const { return n * h * w * c; } };
+struct Tensor {
+    float *p = nullptr; int64_t n = 0, h = 0, w = 0, c = 0;
+    float *hi = nullptr, *lo = nullptr;      // optional TF32 split planes written by a fused producer (same layout as p)
+    int64_t numel() const { return n * h * w * c; }
+};
 
 struct LeafWeights {
     std::vector<std::vector<float>> host;      // by slot, reference layout
@@ -38,6 +43,7 @@ struct LeafWeights {
     float *bias = nullptr;  // [Cout] / folded LSTM bias / GN beta
     float *aux = nullptr;   // W_hh [dirs][4h][h] / GN gamma
     float *b_hi = nullptr, *b_lo = nullptr;   // [ncols][K] TF32 split planes for the tcgen05 GEMM (K-major)
+    float *c_hi = nullptr, *c_lo = nullptr;   // [tap][Cout][32] TF32 split planes for the tcgen05 convolution
     int ncp = 0, K = 0, ncols = 0;
 };
 
@@ -75,6 +81,7 @@ struct kb_model {
     size_t n_stages = 0;             // entries used by the most recent call
     int sm_count = 148;
     int max_clusters8 = -1;          // co-resident 8-CTA clusters of the recurrence kernel (queried once)
+    bool fuse = true;                // fused layer groups (KB_FUSE=0 runs every layer on its own, e.g. for layer taps)
     bool use_tc = true;              // tcgen05 GEMM path (KB_GEMM=ffma forces the CUDA-core kernel)
     ~kb_model() {
         if (device >= 0) {
@@ -147,7 +154,7 @@ static void finalize_weights(kb_model *m) {
     for (size_t li = 0; li < m->plan->leaf_nodes.size(); ++li) {
         const Node &n = *m->plan->leaf_nodes[li];
         LeafWeights &w = m->lw[li];
-        w.wt = w.bias = w.aux = w.b_hi = w.b_lo = nullptr;
+        w.wt = w.bias = w.aux = w.b_hi = w.b_lo = w.c_hi = w.c_lo = nullptr;
         auto need = [&](int slots) {
             for (int s = 0; s < slots; ++s)
                 if ((int)w.loaded.size() <= s || !w.loaded[s]) throw SpecError("weights of layer " + n.name + " not loaded (missing tensor for nn." + n.path + ")");
@@ -164,6 +171,17 @@ static void finalize_weights(kb_model *m) {
                             wt[(size_t)((ky * n.kw + kx) * n.cin + ci) * ncp + co] = src[(((size_t)co * n.cin + ci) * n.kh + ky) * n.kw + kx];
             w.wt = upload(m, wt); w.bias = upload(m, w.host[1]); w.ncp = ncp; w.K = K; w.ncols = n.cout;
             if (n.kh == 1 && n.kw == 1) upload_split(m, src, w);          // [Cout][Cin] is already K-major
+            if (n.cin == 32 && n.sy == 1 && n.sx == 1 && n.dy == 1 && n.dx == 1 && n.cout % 32 == 0 && n.cout <= 128 && n.kh + 1 <= ctc::MAX_ROWS &&
+                n.kh * n.kw > 1) {
+                std::vector<float> taps((size_t)n.kh * n.kw * n.cout * 32), hi(taps.size()), lo(taps.size());
+                for (int ky = 0; ky < n.kh; ++ky)
+                    for (int kx = 0; kx < n.kw; ++kx)
+                        for (int co = 0; co < n.cout; ++co)
+                            for (int ci = 0; ci < 32; ++ci)
+                                taps[(((size_t)(ky * n.kw + kx) * n.cout) + co) * 32 + ci] = src[(((size_t)co * 32 + ci) * n.kh + ky) * n.kw + kx];
+                for (size_t i = 0; i < taps.size(); ++i) { hi[i] = tf32_rna(taps[i]); lo[i] = taps[i] - hi[i]; }
+                w.c_hi = upload(m, hi); w.c_lo = upload(m, lo);
+            }
         } else if (n.kind == K_LINEAR) {
             need(2);
             const int K = n.cin, ncp = (n.cout + 63) / 64 * 64, ld = n.cin + (n.aug ? 1 : 0);
@@ -242,10 +260,13 @@ struct Exec {
     void gemm_tc(const Tensor &x, const LeafWeights &w, int act, float *y) {
         const long long M = (long long)x.n * x.h * x.w;
         const int K = w.K, N = w.ncols;
-        float *a_hi = (float *)m->arena.alloc((size_t)M * K * sizeof(float));
-        float *a_lo = (float *)m->arena.alloc((size_t)M * K * sizeof(float));
+        float *a_hi = x.hi, *a_lo = x.lo;
+        if (!a_hi) {
+            a_hi = (float *)m->arena.alloc((size_t)M * K * sizeof(float));
+            a_lo = (float *)m->arena.alloc((size_t)M * K * sizeof(float));
+        }
         if (dry) return;
-        LAUNCH(m, tc::k_split_tf32, grid1d(M * K / 4, 256, m->sm_count), 256, 0, st, x.p, a_hi, a_lo, M * K / 4);
+        if (!x.hi) LAUNCH(m, tc::k_split_tf32, grid1d(M * K / 4, 256, m->sm_count), 256, 0, st, x.p, a_hi, a_lo, M * K / 4);
         CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
         if (!tc::make_map_2d(&ta_hi, a_hi, (uint64_t)M, (uint64_t)K, tc::BM) || !tc::make_map_2d(&ta_lo, a_lo, (uint64_t)M, (uint64_t)K, tc::BM) ||
             !tc::make_map_2d(&tb_hi, w.b_hi, (uint64_t)N, (uint64_t)K, tc::BN) || !tc::make_map_2d(&tb_lo, w.b_lo, (uint64_t)N, (uint64_t)K, tc::BN))
@@ -417,10 +438,145 @@ struct Exec {
         return y;
     }
 
+    static bool passthrough(const Node &c) { return c.kind == K_DROPOUT || c.kind == K_IDENTITY; }
+    static bool pool22(const Node &c) { return c.kind == K_POOL && c.kh == 2 && c.kw == 2 && c.sy == 2 && c.sx == 2; }
+    // next layer after position j that is not an eval-mode no-op
+    static const Node *next_real(const Node &series, size_t j, size_t *pos = nullptr) {
+        while (j < series.children.size() && passthrough(*series.children[j])) ++j;
+        if (pos) *pos = j;
+        return j < series.children.size() ? series.children[j].get() : nullptr;
+    }
+    void advance_lens(const Node &c, Lens &lens, const Dims &din, const Dims &dout) {
+        if (lens.has) for (auto &l : lens.v) l = leaf_len(c, l, din, dout);
+    }
+
+    // Fused layer groups.  Returns the number of children of `series` consumed (0 = no pattern applies); on success `cur`
+    // and `lens` are advanced past the group.  Layers inside a group do not materialise (no kb_debug_layer_output tap).
+    size_t try_fuse(const Node &series, size_t i, Tensor &cur, Lens &lens) {
+        const Node &c0 = *series.children[i];
+        // ---- P1: conv(Cin = 1, stride 1, dilation 1) -> [Dropout/Identity]* -> MaxPool 2x2/2  (stencil + pool in one pass)
+        if (c0.kind == K_CONV && c0.cin == 1 && cur.c == 1 && c0.sy == 1 && c0.sx == 1 && c0.dy == 1 && c0.dx == 1 &&
+            (c0.cout == 8 || c0.cout == 16 || c0.cout == 32 || c0.cout == 64) &&
+            (c0.act == ACT_RELU || c0.act == ACT_LINEAR || c0.act == ACT_SIGMOID_LOGITS)) {
+            size_t j; const Node *pl = next_real(series, i + 1, &j);
+            if (!pl || !pool22(*pl)) return 0;
+            const Dims din = dims_of(cur);
+            const Dims dconv = leaf_dims(c0, din);
+            if (dconv.h < 2 || dconv.w < 2) return 0;
+            const Dims dpool = leaf_dims(*pl, dconv);
+            const LeafWeights &w = m->lw[c0.leaf_index];
+            Tensor y = mk(dpool);
+            // a tensor-core conv right behind wants the TF32 planes
+            const Node *nx = next_real(series, j + 1);
+            const bool planes = m->use_tc && nx && nx->kind == K_CONV && tc_conv_eligible(*nx, dpool);
+            if (planes) { y.hi = (float *)m->arena.alloc((size_t)y.numel() * 4); y.lo = (float *)m->arena.alloc((size_t)y.numel() * 4); }
+            if (!dry && y.numel()) {
+                StageTimer tt(m, st, c0.name + "+" + pl->name, true);
+                Conv1PoolParams cp;
+                cp.x = cur.p; cp.wt = w.wt; cp.bias = w.bias; cp.y = y.p; cp.y_hi = y.hi; cp.y_lo = y.lo;
+                cp.N = (int)cur.n; cp.H = (int)cur.h; cp.W = (int)cur.w; cp.Cout = c0.cout; cp.Ncp = w.ncp; cp.kh = c0.kh; cp.kw = c0.kw;
+                cp.py = c0.py; cp.px = c0.px; cp.Hp = (int)dpool.h; cp.Wp = (int)dpool.w; cp.act = c0.act;
+                const int cgroups = c0.cout / 8, ppb = 256 / cgroups;
+                const int tw = 2 * ppb + c0.kw - 1, th = c0.kh + 1;
+                const size_t smem = ((size_t)((th * tw + 3) & ~3) + (size_t)c0.kh * c0.kw * c0.cout) * sizeof(float);
+                if (smem > 48 * 1024) throw Unsupported(c0.name + ": filter bank too large for the fused stencil kernel");
+                dim3 grid((unsigned)((dpool.w + ppb - 1) / ppb), (unsigned)dpool.h, (unsigned)dpool.n);
+                LAUNCH(m, k_conv1_pool, grid, 256, smem, st, cp);
+            }
+            advance_lens(c0, lens, din, dconv);
+            advance_lens(*pl, lens, dconv, dpool);
+            cur = y;
+            return j + 1 - i;
+        }
+        if (c0.kind == K_CONV) return fuse_conv_tc(series, i, cur, lens);
+        return 0;
+    }
+    // tensor-core convolution (conv_tc.cuh): stride-1, undilated, Cin a multiple of 32, Cout a multiple of 16 up to 256
+    bool tc_conv_eligible(const Node &c, const Dims &in) const {
+        if (!m->use_tc || c.kind != K_CONV || in.c != 32) return false;
+        const LeafWeights &w = m->lw[c.leaf_index];
+        if (!w.c_hi) return false;
+        if (!(c.act == ACT_RELU || c.act == ACT_LINEAR || c.act == ACT_SIGMOID_LOGITS || c.act == ACT_TANH || c.act == ACT_LEAKY)) return false;
+        if (in.h < 1 || in.w < 1) return false;
+        return ctc::conv_tc_smem(c.kh, c.kw, c.cout, nullptr) <= 227 * 1024;
+    }
+    static bool fold_h(const Node &c) { return c.kind == K_RESHAPE && c.rs_src == 2 && c.rs_a == 1 && c.rs_b == -1 && c.rs_high == 2 && c.rs_low == 1; }
+
+    // ---- P2: conv(Cin = 32, stride 1) -> [Do]* -> [MaxPool 2x2/2] -> [Do]* -> [S fold of H into features] on tcgen05
+    size_t fuse_conv_tc(const Node &series, size_t i, Tensor &cur, Lens &lens) {
+        const Node &c0 = *series.children[i];
+        const Dims din = dims_of(cur);
+        if (!tc_conv_eligible(c0, din)) return 0;
+        const Dims dconv = leaf_dims(c0, din);
+        size_t j = i + 1, jpool = 0, jfold = 0;
+        const Node *pl = nullptr, *fd = nullptr;
+        { size_t k; const Node *nx = next_real(series, j, &k); if (nx && pool22(*nx) && dconv.h >= 2 && dconv.w >= 2) { pl = nx; jpool = k; j = k + 1; } }
+        Dims dpost = pl ? leaf_dims(*pl, dconv) : dconv;
+        { size_t k; const Node *nx = next_real(series, j, &k); if (nx && fold_h(*nx)) { fd = nx; jfold = k; j = k + 1; } }
+        Dims dout = fd ? leaf_dims(*fd, dpost) : dpost;
+        (void)jpool; (void)jfold;
+        Tensor y = mk(dout);
+        // consumer wants TF32 planes?  (another tensor-core conv, or an LSTM / Linear whose projection runs on k_gemm_tc)
+        bool planes = false;
+        {
+            const Node *nx = next_real(series, j);
+            if (nx && m->use_tc) {
+                if (nx->kind == K_CONV) planes = tc_conv_eligible(*nx, dout);
+                else if ((nx->kind == K_LSTM && !nx->legacy) || nx->kind == K_LINEAR) {
+                    const LeafWeights &nw = m->lw[nx->leaf_index];
+                    const long long M = (long long)dout.n * dout.h * dout.w;
+                    planes = nw.b_hi && (dout.c % 4) == 0 && dout.c >= 32 && nw.ncols >= 64 && M >= 128 && !(nx->kind == K_LINEAR && nx->aug);
+                }
+            }
+        }
+        if (planes) { y.hi = (float *)m->arena.alloc((size_t)y.numel() * 4); y.lo = (float *)m->arena.alloc((size_t)y.numel() * 4); }
+        float *x_hi = cur.hi, *x_lo = cur.lo;
+        if (!x_hi) { x_hi = (float *)m->arena.alloc((size_t)cur.numel() * 4); x_lo = (float *)m->arena.alloc((size_t)cur.numel() * 4); }
+        if (!dry && y.numel()) {
+            std::string nm = c0.name; if (pl) nm += "+" + pl->name; if (fd) nm += "+" + fd->name;
+            StageTimer tt(m, st, nm, true);
+            if (!cur.hi) LAUNCH(m, tc::k_split_tf32, grid1d(cur.numel() / 4, 256, m->sm_count), 256, 0, st, cur.p, x_hi, x_lo, (long long)(cur.numel() / 4));
+            const LeafWeights &w = m->lw[c0.leaf_index];
+            ctc::ConvTcParams cp;
+            cp.bias = w.bias; cp.y = y.p; cp.y_hi = y.hi; cp.y_lo = y.lo;
+            cp.N = (int)cur.n; cp.Ho = (int)dconv.h; cp.Wo = (int)dconv.w; cp.Cout = c0.cout; cp.kh = c0.kh; cp.kw = c0.kw; cp.py = c0.py; cp.px = c0.px;
+            cp.act = c0.act; cp.pool = pl ? 1 : 0;
+            cp.out_h = (int)dpost.h; cp.out_w = (int)dpost.w;
+            cp.items_h = pl ? (int)dpost.h : (int)((dconv.h + 1) / 2);
+            cp.items_w = (int)((dconv.w + ctc::TW - 1) / ctc::TW);
+            if (fd) { cp.sN = dpost.w * dpost.h * dpost.c; cp.sW = dpost.h * dpost.c; cp.sH = dpost.c; }
+            else { cp.sN = dpost.h * dpost.w * dpost.c; cp.sH = dpost.w * dpost.c; cp.sW = dpost.c; }
+            cp.acc_sets = 8 * c0.cout <= 512 ? 2 : 1;
+            const size_t smem = ctc::conv_tc_smem(c0.kh, c0.kw, c0.cout, &cp.a_row_bytes);
+            CUtensorMap tx_hi, tx_lo, tw_hi, tw_lo;
+            const uint32_t box_w = (uint32_t)(ctc::TW + c0.kw - 1);
+            if (!ctc::make_map_nhwc32(&tx_hi, x_hi, (uint64_t)cur.n, (uint64_t)cur.h, (uint64_t)cur.w, box_w) ||
+                !ctc::make_map_nhwc32(&tx_lo, x_lo, (uint64_t)cur.n, (uint64_t)cur.h, (uint64_t)cur.w, box_w) ||
+                !tc::make_map_2d(&tw_hi, w.c_hi, (uint64_t)c0.kh * c0.kw * c0.cout, 32, (uint32_t)c0.cout) ||
+                !tc::make_map_2d(&tw_lo, w.c_lo, (uint64_t)c0.kh * c0.kw * c0.cout, 32, (uint32_t)c0.cout))
+                throw CudaError("cuTensorMapEncodeTiled failed (conv)");
+            static bool attr_set = false;
+            if (!attr_set) { CK(cudaFuncSetAttribute(ctc::k_conv_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); attr_set = true; }
+            const int nitems = cp.N * cp.items_h * cp.items_w;
+            if (nitems > 0) LAUNCH(m, ctc::k_conv_tc, (unsigned)std::min(nitems, m->sm_count), ctc::CTHREADS, smem, st, tx_hi, tx_lo, tw_hi, tw_lo, cp);
+        }
+        advance_lens(c0, lens, din, dconv);
+        if (pl) advance_lens(*pl, lens, dconv, dpost);
+        if (fd) advance_lens(*fd, lens, dpost, dout);
+        cur = y;
+        return j - i;
+    }
+
     Tensor run(const Node &n, const Tensor &x, Lens &lens) {
         if (n.kind == K_SERIES) {
             Tensor cur = x;
-            for (auto &c : n.children) cur = run(*c, cur, lens);
+            for (size_t i = 0; i < n.children.size();) {
+                size_t used = 0;
+                if (m->fuse) used = try_fuse(n, i, cur, lens);
+                if (used) { i += used; continue; }
+                cur = run(*n.children[i], cur, lens);
+                ++i;
+            }
             return cur;
         }
         if (n.kind == K_PARALLEL) {
@@ -475,6 +631,7 @@ static ForwardResult forward_impl(kb_model *m, const float *x, int x_on_device, 
     const Plan &pl = *m->plan;
     const int C = pl.input[1];
     { const char *e = getenv("KB_GEMM"); m->use_tc = !(e && strcmp(e, "ffma") == 0); }
+    { const char *e = getenv("KB_FUSE"); m->fuse = !(e && strcmp(e, "0") == 0); }
     if (n <= 0 || h <= 0 || w <= 0) throw ShapeError("empty input batch");
     if (pl.input[2] > 0 && h != pl.input[2] && pl.input[2] != 1)
         ;   // the reference does not check the declared height either; convs accept any H

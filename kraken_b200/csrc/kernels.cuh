@@ -172,6 +172,82 @@ __global__ void __launch_bounds__(CG_NT, 2) k_conv_gemm(ConvParams p) {
     }
 }
 
+// =============================================================================================
+// fused  conv(Cin = 1, stride 1) + bias + activation + 2x2/2 max-pool   (ActConv2D -> [Dropout] -> MaxPool)
+// The first layer of every kraken recogniser reads a 1-channel line image: it is a stencil, not a GEMM, and its
+// full-resolution output (cfg2: 315 MB per batch) is only ever consumed by the pool that follows.  One block = 64 pooled
+// pixels of one pooled row x all output channels; the (kh+1) x (128+kw-1) input patch and the filter bank sit in shared
+// memory; each thread produces 8 channels of one pooled pixel (4 conv positions).  Optionally also writes the TF32 hi/lo
+// planes of the result for a tensor-core consumer.  max(relu(a), relu(b)) == relu(max(a, b)): pooling first is exact.
+// =============================================================================================
+struct Conv1PoolParams {
+    const float *x; const float *wt; const float *bias; float *y; float *y_hi; float *y_lo;
+    int N, H, W, Cout, Ncp, kh, kw, py, px, Hp, Wp, act;
+};
+__global__ void __launch_bounds__(256) k_conv1_pool(Conv1PoolParams p) {
+    extern __shared__ float c1_sm[];
+    const int cgroups = p.Cout >> 3;                                   // 8 channels per thread
+    const int ppb = 256 / cgroups;                                     // pooled pixels per block
+    const int tw = 2 * ppb + p.kw - 1, th = p.kh + 1;                  // input patch
+    float *s_in = c1_sm;                                               // [th][tw]
+    float *s_w = c1_sm + ((th * tw + 3) & ~3);                         // [kh*kw][Cout], 16-byte aligned
+    const int n = blockIdx.z, hp = blockIdx.y, wp0 = blockIdx.x * ppb;
+    const int tid = threadIdx.x;
+    for (int i = tid; i < p.kh * p.kw * p.Cout; i += 256) s_w[i] = __ldg(p.wt + (size_t)(i / p.Cout) * p.Ncp + (i % p.Cout));
+    const int h0 = 2 * hp - p.py, w0 = 2 * wp0 - p.px;
+    const float *img = p.x + (size_t)n * p.H * p.W;
+    for (int i = tid; i < th * tw; i += 256) {
+        const int r = i / tw, c = i % tw, hi = h0 + r, wi = w0 + c;
+        s_in[i] = (hi >= 0 && hi < p.H && wi >= 0 && wi < p.W) ? __ldg(img + (size_t)hi * p.W + wi) : 0.f;
+    }
+    __syncthreads();
+    const int cg_i = tid % cgroups, px = tid / cgroups, wp = wp0 + px;
+    if (wp >= p.Wp) return;
+    float acc[4][8];
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+#pragma unroll
+        for (int c = 0; c < 8; ++c) acc[q][c] = 0.f;
+    for (int ky = 0; ky < p.kh; ++ky)
+        for (int kx = 0; kx < p.kw; ++kx) {
+            const float *wv = s_w + (ky * p.kw + kx) * p.Cout + cg_i * 8;
+            const float4 wa = *reinterpret_cast<const float4 *>(wv), wb = *reinterpret_cast<const float4 *>(wv + 4);
+            const float *ip = s_in + ky * tw + 2 * px + kx;
+            const float i00 = ip[0], i01 = ip[1], i10 = ip[tw], i11 = ip[tw + 1];
+            const float in4[4] = {i00, i01, i10, i11};
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                acc[q][0] = fmaf(in4[q], wa.x, acc[q][0]); acc[q][1] = fmaf(in4[q], wa.y, acc[q][1]);
+                acc[q][2] = fmaf(in4[q], wa.z, acc[q][2]); acc[q][3] = fmaf(in4[q], wa.w, acc[q][3]);
+                acc[q][4] = fmaf(in4[q], wb.x, acc[q][4]); acc[q][5] = fmaf(in4[q], wb.y, acc[q][5]);
+                acc[q][6] = fmaf(in4[q], wb.z, acc[q][6]); acc[q][7] = fmaf(in4[q], wb.w, acc[q][7]);
+            }
+        }
+    float o[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        const float b = p.bias ? __ldg(p.bias + cg_i * 8 + c) : 0.f;
+        const float m = fmaxf(fmaxf(acc[0][c], acc[1][c]), fmaxf(acc[2][c], acc[3][c])) + b;   // + b commutes with max
+        o[c] = act_apply(m, p.act);
+    }
+    const size_t off = (((size_t)n * p.Hp + hp) * p.Wp + wp) * p.Cout + cg_i * 8;
+    *reinterpret_cast<float4 *>(p.y + off) = make_float4(o[0], o[1], o[2], o[3]);
+    *reinterpret_cast<float4 *>(p.y + off + 4) = make_float4(o[4], o[5], o[6], o[7]);
+    if (p.y_hi) {
+        float h[8], l[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            uint32_t t;
+            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(o[c]));
+            h[c] = __uint_as_float(t); l[c] = o[c] - h[c];
+        }
+        *reinterpret_cast<float4 *>(p.y_hi + off) = make_float4(h[0], h[1], h[2], h[3]);
+        *reinterpret_cast<float4 *>(p.y_hi + off + 4) = make_float4(h[4], h[5], h[6], h[7]);
+        *reinterpret_cast<float4 *>(p.y_lo + off) = make_float4(l[0], l[1], l[2], l[3]);
+        *reinterpret_cast<float4 *>(p.y_lo + off + 4) = make_float4(l[4], l[5], l[6], l[7]);
+    }
+}
+
 // softmax over the feature axis of NHWC rows, in place ('m' convs, layers.py:817-818). One warp per pixel.
 __global__ void k_softmax_rows(float *__restrict__ x, long long rows, int C) {
     long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);

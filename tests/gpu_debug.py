@@ -13,6 +13,7 @@ sys.path.insert(0, os.path.join(ROOT, 'tests'))
 import numpy as np
 import torch
 
+os.environ.setdefault('KB_FUSE', '0')       # per-layer taps need every layer materialised
 import __graft_entry__ as ge
 
 ge.build()

@@ -3,7 +3,9 @@ reference, the CPU oracle on fresh seeded inputs, and size-independent propertie
 
 Bars (BASELINE.json north_star): logits within 1e-3 relative (fp32), CTC label tuples (label, start, end) identical,
 confidences within 1e-3."""
+import contextlib
 import json
+import os
 
 import numpy as np
 import pytest
@@ -19,6 +21,20 @@ pytestmark = pytest.mark.gpu
 REL_TOL = 1e-3          # the contract
 TIGHT = 2e-5            # what an fp32-exact implementation actually achieves; guards against silent precision loss
 CFG2 = '[1,48,0,1 Cr3,3,32 Mp2,2 Cr3,3,64 Mp2,2 S1(1x0)1,3 Lbx256 O1c200]'
+
+
+@contextlib.contextmanager
+def env(**kw):
+    old = {k: os.environ.get(k) for k in kw}
+    os.environ.update({k: str(v) for k, v in kw.items()})
+    try:
+        yield
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
 
 
 def rel_err(a, b):
@@ -109,10 +125,17 @@ def test_cfg2_vs_oracle_layerwise(seed, n, w):
     m = kb.TorchVGSLModel(vgsl=CFG2)
     m.load_state_dict(wts)
     m.to('cuda:0')
-    logits, olens = m.nn(x.cuda(), lens)
-    for name, t in taps.items():
-        e = rel_err(m.nn.layer_output(name), t)
-        assert e <= TIGHT, (name, e)
+    with env(KB_FUSE=0):                               # every layer on its own so that each one leaves a tap
+        logits, olens = m.nn(x.cuda(), lens)
+        for name, t in taps.items():
+            e = rel_err(m.nn.layer_output(name), t)
+            assert e <= TIGHT, (name, e)
+    assert rel_err(logits, ref_logits) <= TIGHT
+    assert olens.tolist() == ref_olens.tolist()
+    with env(KB_FUSE=0, KB_GEMM='ffma'):               # all-CUDA-core path
+        l2, _ = m.nn(x.cuda(), lens)
+    assert rel_err(l2, ref_logits) <= TIGHT
+    logits, olens = m.nn(x.cuda(), lens)               # production path: fused groups + tcgen05
     assert rel_err(logits, ref_logits) <= TIGHT
     assert olens.tolist() == ref_olens.tolist()
     _, _, _, ref_dec = vo.rec_predict(om, x, lens)
@@ -239,11 +262,48 @@ def test_blla_architecture_properties():
     m.to('cuda:0')
     taps = {}
     ref, _ = om.forward(x, None, taps)
+    with env(KB_FUSE=0):
+        out, _ = m.nn(x.cuda())
+        for name, t in taps.items():
+            assert rel_err(m.nn.layer_output(name), t) <= 5e-5, name
+    assert rel_err(out, ref) <= 5e-5
     out, _ = m.nn(x.cuda())
-    for name, t in taps.items():
-        assert rel_err(m.nn.layer_output(name), t) <= 5e-5, name
     assert rel_err(out, ref) <= 5e-5
     hm = segmentation_heatmap(m, x.cuda(), (300, 228))
     hm1 = segmentation_heatmap(m, x[1:2].cuda(), (300, 228))
     assert float((hm[1:2] - hm1).abs().max()) <= 1e-5
     assert 0.0 <= float(hm.min()) and float(hm.max()) <= 1.0
+
+
+FUSE_SPECS = [
+    # (spec, H, W list) - exercise the fused stencil and the tcgen05 convolution on awkward shapes
+    ('[1,48,0,1 Cr3,3,32 Mp2,2 Cr3,3,64 Mp2,2 S1(1x0)1,3 Lbx32 O1c20]', 48, (401, 130, 64)),
+    ('[1,20,0,1 Cr3,3,32 Mp2,2 Cr3,5,32 Ct5,3,64 S1(1x0)1,3 Lbx16 O1c12]', 20, (300, 257)),          # conv_tc w/o pool, tanh, kw/kh 5, fold
+    ('[1,21,0,1 Cl5,7,32 Do0.1,2 Mp2,2 Cr3,3,32 Do0.1,2 Mp2,2 Cr3,3,96 Gn4 Cr1,1,64 Mp2,2 S1(1x0)1,3 O1c9]', 21, (200,)),  # odd H, Cout 96, GN after
+    ('[1,16,0,1 Cr3,3,8 Mp2,2 Cr3,3,32 Cr3,9,32 Mp2,2 S1(1x0)1,3 Lfx24 O1c7]', 16, (513,)),         # Cin 8 -> FFMA, then conv_tc chain
+]
+
+
+@pytest.mark.parametrize('spec,h,widths', FUSE_SPECS)
+def test_fused_groups_and_conv_tc(spec, h, widths):
+    om = vo.OracleModel(spec)
+    wts = om.init_like_reference(41)
+    m = kb.TorchVGSLModel(vgsl=spec)
+    m.load_state_dict(wts)
+    m.to('cuda:0')
+    g = torch.Generator().manual_seed(41)
+    for w in widths:
+        n = 3
+        lens = torch.tensor([w, max(8, w // 2 + 1), max(8, w // 3)])
+        x = torch.rand(n, 1, h, w, generator=g)
+        for i, l in enumerate(lens.tolist()):
+            x[i, ..., l:] = 0
+        for sl in (lens, None):
+            ref, rl = om.forward(x, sl)
+            out, ol = m.nn(x.cuda(), sl)
+            assert tuple(out.shape) == tuple(ref.shape)
+            assert rel_err(out, ref) <= TIGHT, (spec, w, rel_err(out, ref))
+            assert (rl is None and ol is None) or ol.tolist() == rl.tolist()
+            with env(KB_FUSE=0, KB_GEMM='ffma'):
+                out2, _ = m.nn(x.cuda(), sl)
+            assert rel_err(out2, ref) <= TIGHT
