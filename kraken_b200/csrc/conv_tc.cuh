@@ -8,7 +8,9 @@
 //   * TMA (4-D tensor map C,W,H,N; box 32 x (128+kw-1) x 1 x 1, 128B swizzle) brings the kh+1 input rows a row pair
 //     needs into shared memory ONCE; out-of-bounds coordinates are zero-filled by the TMA unit = the conv's zero padding
 //   * the A operand of tap (ky, kx) for output row r is the row buffer (ky + r) with its UMMA descriptor start address
-//     advanced by kx pixel rows (128 B each; descriptor base_offset = kx & 7 keeps the swizzle phase right)
+//     advanced by kx pixel rows (128 B each).  Measured on B200: the 128B-swizzle XOR is taken from the ABSOLUTE shared-
+//     memory address bits [7:9], exactly as TMA wrote it, so a descriptor may start at any 128-byte row of a 1024-byte
+//     aligned buffer with base_offset = 0 (setting base_offset = kx gives garbage - tests/gpu_fuse_debug.py)
 //   * B operand = the tap's [Cout][32] weight slice, streamed through a 3-stage TMA ring
 //   * 3xTF32 split as in gemm_tc.cuh: per tap and K=8 step  corr += a_lo*b_hi + a_hi*b_lo ; main += a_hi*b_hi, for both
 //     output rows -> 4 TMEM accumulators of Cout columns (two sets when 8*Cout <= 512, so the epilogue overlaps the MMAs)
@@ -42,16 +44,13 @@ __device__ __forceinline__ void tma_load_4d(void *dst, const CUtensorMap *map, u
     asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
                  ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
 }
-__device__ __forceinline__ uint64_t umma_desc_sw128_off(uint32_t saddr, uint32_t base_off) {
-    return umma_desc_sw128(saddr) | ((uint64_t)(base_off & 7) << 49);
-}
 
 __global__ void __launch_bounds__(CTHREADS, 1)
 k_conv_tc(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ CUtensorMap tm_x_lo,
           const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant__ CUtensorMap tm_w_lo, ConvTcParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    const int R = p.kh + 1, taps = p.kh * p.kw;
+    const int R = p.kh + 1;
     const int a_plane = p.a_row_bytes, a_row = 2 * a_plane;              // hi | lo
     const int b_plane = p.Cout * 128, b_stage = 2 * b_plane;
     uint8_t *a_base = smem, *b_base = smem + R * a_row;
@@ -127,7 +126,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ C
 #pragma unroll
                         for (int r = 0; r < 2; ++r) {
                             const uint32_t sa = smem_u32(a_base + (ky + r) * a_row) + (uint32_t)kx * 128u;
-                            const uint64_t a_hi = umma_desc_sw128_off(sa, (uint32_t)kx), a_lo = umma_desc_sw128_off(sa + a_plane, (uint32_t)kx);
+                            const uint64_t a_hi = umma_desc_sw128(sa), a_lo = umma_desc_sw128(sa + a_plane);
                             const uint32_t d_main = d0 + (uint32_t)(2 * r * p.Cout), d_corr = d_main + (uint32_t)p.Cout;
 #pragma unroll
                             for (int k = 0; k < 4; ++k) {
