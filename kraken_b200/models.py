@@ -53,6 +53,12 @@ class TorchSeqRecognizer:
 
     # -- fused device path ----------------------------------------------------------------------
     def _recognize(self, line, lens, want_probs: bool):
+        r = self._recognize_raw(line, lens, want_probs)
+        return ctc_decoder.unpack_decoded(r['labels'], r['starts'], r['ends'], r['confs'], r['counts']), r['olens']
+
+    def _recognize_raw(self, line, lens, want_probs: bool) -> dict:
+        """One `kb_recognize` call; returns the ABI's fixed-stride output blocks as numpy arrays
+        (labels/starts/ends/confs [N, T], counts [N], olens [N] or None)."""
         net = self.nn
         net._ensure_finalized(line)
         x = _as_f32(line)
@@ -81,7 +87,8 @@ class TorchSeqRecognizer:
                                _stream_for(x)))
         if probs is not None:
             self.outputs = probs
-        return ctc_decoder.unpack_decoded(labels, starts, ends, confs, counts), (olens if lens is not None else None)
+        return {'labels': labels, 'starts': starts, 'ends': ends, 'confs': confs, 'counts': counts,
+                'olens': olens if lens is not None else None}
 
     # -- reference surface ------------------------------------------------------------------------
     def forward(self, line: torch.Tensor, lens: Optional[torch.Tensor] = None):
