@@ -30,6 +30,21 @@ __device__ __forceinline__ float act_apply(float v, int act) {
     }
 }
 __device__ __forceinline__ float sigmoidf_acc(float x) { return 1.f / (1.f + expf(-x)); }
+// Blackwell packed fp32 FMA: (acc.lo, acc.hi) += (w.lo, w.hi) * s.  ptxas folds the {s, s} pack into FFMA2's scalar-broadcast
+// operand form (`FFMA2 Rd, Ra.F32x2.HI_LO, Rb.F32, Rc.F32x2.HI_LO`), so this is ONE issue slot for two IEEE fmas.
+__device__ __forceinline__ void ffma2_bcast(unsigned long long &acc, unsigned long long w, float s) {
+    unsigned long long sp;
+    asm("mov.b64 %0, {%1, %1};" : "=l"(sp) : "f"(s));
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(w), "l"(sp));
+}
+__device__ __forceinline__ unsigned long long pack2f(float lo, float hi) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack2f(unsigned long long v, float &lo, float &hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
 
 // =============================================================================================
 // batched transpose  in[B][R][C] -> out[B][C][R]   (NCHW <-> NHWC at the ABI edge)
@@ -120,9 +135,9 @@ __global__ void __launch_bounds__(CG_NT, 2) k_conv_gemm(ConvParams p) {
         *reinterpret_cast<float4 *>(&Bs[buf][b_k][b_n]) = rb;
     };
 
-    float acc[8][4];
+    unsigned long long acc01[8], acc23[8];       // 8 rows x 4 columns as FFMA2 pairs
 #pragma unroll
-    for (int i = 0; i < 8; ++i) { acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f; }
+    for (int i = 0; i < 8; ++i) { acc01[i] = 0ull; acc23[i] = 0ull; }
 
     const int nk = (p.K + CG_BK - 1) / CG_BK;
     load_tile(0); store_tile(0); __syncthreads();
@@ -136,12 +151,11 @@ __global__ void __launch_bounds__(CG_NT, 2) k_conv_gemm(ConvParams p) {
             for (int i = 0; i < 8; ++i) a[i] = *reinterpret_cast<const float4 *>(&As[cur][ty + 16 * i][kk]);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                const float4 b = *reinterpret_cast<const float4 *>(&Bs[cur][kk + j][tx * 4]);
+                const ulonglong2 b = *reinterpret_cast<const ulonglong2 *>(&Bs[cur][kk + j][tx * 4]);   // (b0,b1), (b2,b3)
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     const float av = j == 0 ? a[i].x : j == 1 ? a[i].y : j == 2 ? a[i].z : a[i].w;
-                    acc[i][0] = fmaf(av, b.x, acc[i][0]); acc[i][1] = fmaf(av, b.y, acc[i][1]);
-                    acc[i][2] = fmaf(av, b.z, acc[i][2]); acc[i][3] = fmaf(av, b.w, acc[i][3]);
+                    ffma2_bcast(acc01[i], b.x, av); ffma2_bcast(acc23[i], b.y, av);
                 }
             }
         }
@@ -161,8 +175,9 @@ __global__ void __launch_bounds__(CG_NT, 2) k_conv_gemm(ConvParams p) {
         const long long m = m0 + ty + 16 * i;
         if (m >= p.M) continue;
         float v[4];
+        unpack2f(acc01[i], v[0], v[1]); unpack2f(acc23[i], v[2], v[3]);
 #pragma unroll
-        for (int c = 0; c < 4; ++c) v[c] = act_apply(acc[i][c] + bv[c], p.act);
+        for (int c = 0; c < 4; ++c) v[c] = act_apply(v[c] + bv[c], p.act);
         float *dst = p.y + (size_t)m * p.Cout + n;
         if (vec_store) { if (n < p.Cout) *reinterpret_cast<float4 *>(dst) = make_float4(v[0], v[1], v[2], v[3]); }
         else {
@@ -503,13 +518,16 @@ __global__ void __launch_bounds__(256, 1) k_lstm_rec(LstmParams p) {
     const bool uvalid = rg < p.U && u < p.hid;
     const int hid = p.hid, GC = p.dirs * 4 * hid, OC = p.dirs * hid;
 
-    float w[4][32];
+    unsigned long long w2[2][32];               // gate pairs (i,f) and (g,o) of this thread's unit, packed for FFMA2
 #pragma unroll
-    for (int g = 0; g < 4; ++g)
+    for (int gp = 0; gp < 2; ++gp)
 #pragma unroll
         for (int kk = 0; kk < 32; ++kk) {
             const int k = ks * 32 + kk;
-            w[g][kk] = (uvalid && k < hid) ? __ldg(p.whh + ((size_t)dir * 4 * hid + (size_t)g * hid + u) * hid + k) : 0.f;
+            const bool ok = uvalid && k < hid;
+            const float a = ok ? __ldg(p.whh + ((size_t)dir * 4 * hid + (size_t)(2 * gp) * hid + u) * hid + k) : 0.f;
+            const float b = ok ? __ldg(p.whh + ((size_t)dir * 4 * hid + (size_t)(2 * gp + 1) * hid + u) * hid + k) : 0.f;
+            w2[gp][kk] = pack2f(a, b);
         }
     for (int i = tid; i < 2 * BL * HLD; i += 256) (&sm.h[0][0][0])[i] = 0.f;
 
@@ -588,21 +606,19 @@ __global__ void __launch_bounds__(256, 1) k_lstm_rec(LstmParams p) {
         if (s + 1 < maxlen) load_gx(s + 1, gxn);
         float v[BLT * 4];
 #pragma unroll
-        for (int i = 0; i < BLT * 4; ++i) v[i] = 0.f;
-#pragma unroll
         for (int b = 0; b < BLT; ++b) {
             const float *hrow = &sm.h[cur][(BLT == 10 ? 0 : ls * 8) + b][ks * 36];
+            unsigned long long a01 = 0ull, a23 = 0ull;          // (i,f) and (g,o) partial sums of line b
 #pragma unroll
             for (int kq = 0; kq < 8; ++kq) {
                 const float4 hv = *reinterpret_cast<const float4 *>(hrow + kq * 4);
-#pragma unroll
-                for (int g = 0; g < 4; ++g) {
-                    float a = v[b * 4 + g];
-                    a = fmaf(w[g][kq * 4 + 0], hv.x, a); a = fmaf(w[g][kq * 4 + 1], hv.y, a);
-                    a = fmaf(w[g][kq * 4 + 2], hv.z, a); a = fmaf(w[g][kq * 4 + 3], hv.w, a);
-                    v[b * 4 + g] = a;
-                }
+                ffma2_bcast(a01, w2[0][kq * 4 + 0], hv.x); ffma2_bcast(a23, w2[1][kq * 4 + 0], hv.x);
+                ffma2_bcast(a01, w2[0][kq * 4 + 1], hv.y); ffma2_bcast(a23, w2[1][kq * 4 + 1], hv.y);
+                ffma2_bcast(a01, w2[0][kq * 4 + 2], hv.z); ffma2_bcast(a23, w2[1][kq * 4 + 2], hv.z);
+                ffma2_bcast(a01, w2[0][kq * 4 + 3], hv.w); ffma2_bcast(a23, w2[1][kq * 4 + 3], hv.w);
             }
+            unpack2f(a01, v[b * 4 + 0], v[b * 4 + 1]);
+            unpack2f(a23, v[b * 4 + 2], v[b * 4 + 3]);
         }
         // lines 8,9 (BLT == 10): butterfly all-reduce over the 8 k-slices, lanes 0/1 keep line 8/9
         float x89[4] = {0.f, 0.f, 0.f, 0.f};
