@@ -30,7 +30,7 @@ def segmentation_heatmap(model: TorchVGSLModel, pages, size: Optional[Sequence[i
     oc = model.infer_dims(n, h, w)[1]
     on_dev = _on_device(x)
     out = torch.empty((n, oc, int(size[0]), int(size[1])), dtype=torch.float32, device=x.device if on_dev else 'cpu')
-    check(lib.kb_segment(model._h, _ptr(x), int(on_dev), n, h, w, int(size[0]), int(size[1]), out.data_ptr(), int(on_dev), _stream_for(x)))
+    check(lib.kb_segment(model._h, _ptr(x), int(on_dev), n, h, w, int(size[0]), int(size[1]), out.data_ptr(), int(on_dev), _stream_for(x, model._device)))
     return out
 
 

@@ -192,7 +192,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ C
                         const size_t off = (size_t)((long long)n * p.sN + (long long)hp * p.sH + (long long)wp * p.sW) + c0;
 #pragma unroll
                         for (int j = 0; j < 32; j += 4) {
-                            *reinterpret_cast<float4 *>(p.y + off + j) = make_float4(v0[j], v0[j + 1], v0[j + 2], v0[j + 3]);
+                            if (p.y) *reinterpret_cast<float4 *>(p.y + off + j) = make_float4(v0[j], v0[j + 1], v0[j + 2], v0[j + 3]);
                             if (p.y_hi) {
                                 float h[4], l[4];
 #pragma unroll
@@ -211,7 +211,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ C
                             const float *v = r ? v1 : v0;
 #pragma unroll
                             for (int j = 0; j < 32; j += 4) {
-                                *reinterpret_cast<float4 *>(p.y + off + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                                if (p.y) *reinterpret_cast<float4 *>(p.y + off + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
                                 if (p.y_hi) {
                                     float h[4], l[4];
 #pragma unroll

@@ -82,6 +82,7 @@ struct kb_model {
     int sm_count = 148;
     int max_clusters8 = -1;          // co-resident 8-CTA clusters of the recurrence kernel (queried once)
     int fuse_mask = 3;               // bit 0: stencil+pool group, bit 1: tcgen05 conv group
+    bool keep_fp32 = false;          // KB_KEEP_FP32=1: fused producers also write the fp32 tensor their TF32-plane consumer ignores (taps)
     bool fuse = true;                // fused layer groups (KB_FUSE=0 runs every layer on its own, e.g. for layer taps)
     bool use_tc = true;              // tcgen05 GEMM path (KB_GEMM=ffma forces the CUDA-core kernel)
     ~kb_model() {
@@ -474,7 +475,7 @@ struct Exec {
             if (!dry && y.numel()) {
                 StageTimer tt(m, st, c0.name + "+" + pl->name, true);
                 Conv1PoolParams cp;
-                cp.x = cur.p; cp.wt = w.wt; cp.bias = w.bias; cp.y = y.p; cp.y_hi = y.hi; cp.y_lo = y.lo;
+                cp.x = cur.p; cp.wt = w.wt; cp.bias = w.bias; cp.y = (planes && !m->keep_fp32) ? nullptr : y.p; cp.y_hi = y.hi; cp.y_lo = y.lo;
                 cp.N = (int)cur.n; cp.H = (int)cur.h; cp.W = (int)cur.w; cp.Cout = c0.cout; cp.Ncp = w.ncp; cp.kh = c0.kh; cp.kw = c0.kw;
                 cp.py = c0.py; cp.px = c0.px; cp.Hp = (int)dpool.h; cp.Wp = (int)dpool.w; cp.act = c0.act;
                 const int cgroups = c0.cout / 8, ppb = 256 / cgroups;
@@ -540,7 +541,7 @@ struct Exec {
             if (!cur.hi) LAUNCH(m, tc::k_split_tf32, grid1d(cur.numel() / 4, 256, m->sm_count), 256, 0, st, cur.p, x_hi, x_lo, (long long)(cur.numel() / 4));
             const LeafWeights &w = m->lw[c0.leaf_index];
             ctc::ConvTcParams cp;
-            cp.bias = w.bias; cp.y = y.p; cp.y_hi = y.hi; cp.y_lo = y.lo;
+            cp.bias = w.bias; cp.y = (planes && !m->keep_fp32) ? nullptr : y.p; cp.y_hi = y.hi; cp.y_lo = y.lo;
             cp.N = (int)cur.n; cp.Ho = (int)dconv.h; cp.Wo = (int)dconv.w; cp.Cout = c0.cout; cp.kh = c0.kh; cp.kw = c0.kw; cp.py = c0.py; cp.px = c0.px;
             cp.act = c0.act; cp.pool = pl ? 1 : 0;
             cp.out_h = (int)dpost.h; cp.out_w = (int)dpost.w;
@@ -634,6 +635,7 @@ static ForwardResult forward_impl(kb_model *m, const float *x, int x_on_device, 
     const Plan &pl = *m->plan;
     const int C = pl.input[1];
     { const char *e = getenv("KB_GEMM"); m->use_tc = !(e && strcmp(e, "ffma") == 0); }
+    { const char *e = getenv("KB_KEEP_FP32"); m->keep_fp32 = e && strcmp(e, "0") != 0; }
     { const char *e = getenv("KB_FUSE"); m->fuse_mask = e ? atoi(e) : 3; m->fuse = m->fuse_mask != 0; }
     if (n <= 0 || h <= 0 || w <= 0) throw ShapeError("empty input batch");
     if (pl.input[2] > 0 && h != pl.input[2] && pl.input[2] != 1)

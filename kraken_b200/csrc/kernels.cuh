@@ -246,8 +246,10 @@ __global__ void __launch_bounds__(256) k_conv1_pool(Conv1PoolParams p) {
         o[c] = act_apply(m, p.act);
     }
     const size_t off = (((size_t)n * p.Hp + hp) * p.Wp + wp) * p.Cout + cg_i * 8;
-    *reinterpret_cast<float4 *>(p.y + off) = make_float4(o[0], o[1], o[2], o[3]);
-    *reinterpret_cast<float4 *>(p.y + off + 4) = make_float4(o[4], o[5], o[6], o[7]);
+    if (p.y) {            // the fp32 tensor is skipped when the only consumer reads the TF32 planes
+        *reinterpret_cast<float4 *>(p.y + off) = make_float4(o[0], o[1], o[2], o[3]);
+        *reinterpret_cast<float4 *>(p.y + off + 4) = make_float4(o[4], o[5], o[6], o[7]);
+    }
     if (p.y_hi) {
         float h[8], l[8];
 #pragma unroll

@@ -84,7 +84,7 @@ class TorchSeqRecognizer:
         check(lib.kb_recognize(net._h, _ptr(x), int(on_dev), n, h, w, widths.ctypes.data if widths is not None else None,
                                float(self.temperature), labels.ctypes.data, starts.ctypes.data, ends.ctypes.data, confs.ctypes.data,
                                counts.ctypes.data, stride, olens.ctypes.data, probs.ctypes.data if probs is not None else None, 0,
-                               _stream_for(x)))
+                               _stream_for(x, net._device)))
         if probs is not None:
             self.outputs = probs
         return {'labels': labels, 'starts': starts, 'ends': ends, 'confs': confs, 'counts': counts,

@@ -51,9 +51,13 @@ def _on_device(t) -> bool:
     return isinstance(t, torch.Tensor) and t.is_cuda
 
 
-def _stream_for(t) -> Optional[int]:
+def _stream_for(t, device: Optional[int] = None) -> Optional[int]:
+    """The caller's current CUDA stream (thread-local in torch) - also for host inputs, so that several handles can be driven
+    concurrently from different threads/streams."""
     if _on_device(t):
         return torch.cuda.current_stream(t.device).cuda_stream
+    if device is not None and torch.cuda.is_available():
+        return torch.cuda.current_stream(device).cuda_stream
     return None
 
 
@@ -89,7 +93,7 @@ class EngineNet:
             out = torch.empty(tuple(dims), dtype=torch.float32)
         olens = np.zeros(n, dtype=np.int32)
         check(lib.kb_forward(o._h, _ptr(x), int(on_dev), n, h, w, widths.ctypes.data if widths is not None else None,
-                             out.data_ptr(), int(on_dev), olens.ctypes.data, _stream_for(x)))
+                             out.data_ptr(), int(on_dev), olens.ctypes.data, _stream_for(x, o._device)))
         return out, (torch.from_numpy(olens.astype(np.int64)) if seq_lens is not None else None)
 
     # state-dict style access used by tests / tooling

@@ -3,6 +3,7 @@ import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, 'oracle'))
 import torch
+os.environ['KB_KEEP_FP32'] = '1'
 import __graft_entry__ as ge
 ge.build()
 import kraken_b200 as kb
