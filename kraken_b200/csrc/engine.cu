@@ -421,8 +421,7 @@ struct Exec {
                 case 2: CK(cudaLaunchKernelEx(&cfg, k_lstm_rec<2, 8>, lp)); break;
                 case 4: CK(cudaLaunchKernelEx(&cfg, k_lstm_rec<4, 8>, lp)); break;
                 default:
-                    if (lines10 && !(getenv("KB_LSTM_PP") && atoi(getenv("KB_LSTM_PP")) == 0)) CK(cudaLaunchKernelEx(&cfg, k_lstm_rec_pp, lp));
-                    else if (lines10) CK(cudaLaunchKernelEx(&cfg, k_lstm_rec<8, 10>, lp));
+                    if (lines10) CK(cudaLaunchKernelEx(&cfg, k_lstm_rec<8, 10>, lp));
                     else CK(cudaLaunchKernelEx(&cfg, k_lstm_rec<8, 8>, lp));
                     break;
                 }

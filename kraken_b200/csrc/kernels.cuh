@@ -695,158 +695,6 @@ __global__ void __launch_bounds__(256, 1) k_lstm_rec(LstmParams p) {
     if (CS > 1) cluster.sync();          // nobody exits while a peer may still address its shared memory
 }
 
-// ---------------------------------------------------------------------------------------------
-// Ping-pong variant for hidden sizes 129..256 (cluster of 8): the cluster's 10 lines are split into two groups of 5 that
-// alternate.  While group A's h_t travels through distributed shared memory (st.async -> remote mbarrier, ~1000 cycles
-// of latency + pointwise work per step), the FMA pipe runs group B's mat-vec, and vice versa.  Same arithmetic and the same
-// register-resident W_hh as k_lstm_rec<8, 10>; per group an 8-lane butterfly all-reduce replaces the reduce-scatter
-// (5 lines do not divide over 8 k-slices) and lanes ks < 5 own one (unit, line) cell per group.
-// ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256, 1) k_lstm_rec_pp(LstmParams p) {
-    constexpr int CS = 8, GL = 5, BL = 2 * GL, HLD = 36 * 8;
-    struct Smem { float h[2][2][GL][HLD]; unsigned long long mbar[2][2]; };      // [group][buffer]
-    __shared__ __align__(16) Smem sm;
-    cg::cluster_group cluster = cg::this_cluster();
-    const int tid = threadIdx.x;
-    const int ks = tid & 7, rg = tid >> 3;
-    const int rank = (int)cluster.block_rank();
-    const int chunk = blockIdx.x / CS, dir = blockIdx.y;
-    const int u = rank * p.U + rg;
-    const bool uvalid = rg < p.U && u < p.hid;
-    const int hid = p.hid, GC = p.dirs * 4 * hid, OC = p.dirs * hid;
-
-    unsigned long long w2[2][32];
-#pragma unroll
-    for (int gp = 0; gp < 2; ++gp)
-#pragma unroll
-        for (int kk = 0; kk < 32; ++kk) {
-            const int k = ks * 32 + kk;
-            const bool ok = uvalid && k < hid;
-            const float a = ok ? __ldg(p.whh + ((size_t)dir * 4 * hid + (size_t)(2 * gp) * hid + u) * hid + k) : 0.f;
-            const float b = ok ? __ldg(p.whh + ((size_t)dir * 4 * hid + (size_t)(2 * gp + 1) * hid + u) * hid + k) : 0.f;
-            w2[gp][kk] = pack2f(a, b);
-        }
-    for (int i = tid; i < 2 * 2 * GL * HLD; i += 256) (&sm.h[0][0][0][0])[i] = 0.f;
-
-    int len[2]; long long base[2]; float cst[2], hlast[2]; bool cell[2];
-    uint32_t tx_bytes[2];
-    int maxlen = 0;
-#pragma unroll
-    for (int g = 0; g < 2; ++g) {
-        const int q = chunk * BL + g * GL + ks;
-        cell[g] = uvalid && ks < GL && q < p.nseq;
-        const int l = (ks < GL && q < p.nseq) ? (p.lens ? p.lens[q] : p.T) : 0;
-        len[g] = min(max(l, 0), p.T);
-        const int qq = q < p.nseq ? q : 0;
-        base[g] = (long long)(qq / p.q2) * p.s_outer + (long long)(qq % p.q2) * p.s_inner;
-        cst[g] = 0.f; hlast[g] = 0.f;
-        int nvalid = 0;
-        for (int lb = 0; lb < GL; ++lb) {
-            const int ql = chunk * BL + g * GL + lb;
-            if (ql < p.nseq) {
-                ++nvalid;
-                const int ll = p.lens ? min(max(p.lens[ql], 0), p.T) : p.T;
-                maxlen = max(maxlen, ll);
-                if (ll < p.T) {          // zero the padded tail of this CTA's units
-                    const long long b0 = (long long)(ql / p.q2) * p.s_outer + (long long)(ql % p.q2) * p.s_inner;
-                    const int nu = min(p.U, hid - rank * p.U);
-                    for (int i = tid; i < (p.T - ll) * max(nu, 0); i += 256) {
-                        const int t = ll + i / nu, uu = rank * p.U + i % nu;
-                        p.out[(size_t)(b0 + (long long)t * p.step) * OC + dir * hid + uu] = 0.f;
-                    }
-                }
-            }
-        }
-        tx_bytes[g] = (uint32_t)nvalid * (uint32_t)hid * 4u;
-    }
-    uint32_t mb[2][2];
-#pragma unroll
-    for (int g = 0; g < 2; ++g) { mb[g][0] = cvta_smem(&sm.mbar[g][0]); mb[g][1] = cvta_smem(&sm.mbar[g][1]); }
-    if (tid == 0) {
-#pragma unroll
-        for (int g = 0; g < 2; ++g) {
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mb[g][0]));
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mb[g][1]));
-        }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-#pragma unroll
-        for (int g = 0; g < 2; ++g)      // buffer 1 of each group is filled during step 0
-            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb[g][1]), "r"(tx_bytes[g]) : "memory");
-    }
-    uint32_t rbase[CS];
-#pragma unroll
-    for (int r = 0; r < CS; ++r) rbase[r] = mapa_u32(cvta_smem(&sm), (uint32_t)r);
-    cluster.sync();
-
-    float4 gxc[2], gxn[2];
-    auto load_gx = [&](int g, int s) -> float4 {
-        if (cell[g] && s < len[g]) {
-            const int t = dir ? len[g] - 1 - s : s;
-            return __ldg(reinterpret_cast<const float4 *>(p.gx + (size_t)(base[g] + (long long)t * p.step) * GC + (size_t)dir * 4 * hid + (size_t)u * 4));
-        }
-        return make_float4(0.f, 0.f, 0.f, 0.f);
-    };
-    gxc[0] = load_gx(0, 0); gxc[1] = load_gx(1, 0);
-
-    for (int s = 0; s < maxlen; ++s) {
-        const int cur = s & 1, nxt = cur ^ 1;
-#pragma unroll
-        for (int g = 0; g < 2; ++g) {
-            if (s > 0) mbar_wait_parity(mb[g][cur], (uint32_t)(((s - 1) >> 1) & 1));
-            __syncthreads();             // all threads have seen the phase flip before it can be re-armed / re-filled
-            if (tid == 0 && s + 2 < maxlen)
-                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb[g][cur]), "r"(tx_bytes[g]) : "memory");
-            if (s + 1 < maxlen) gxn[g] = load_gx(g, s + 1);
-            float v[GL * 4];
-#pragma unroll
-            for (int b = 0; b < GL; ++b) {
-                const float *hrow = &sm.h[g][cur][b][ks * 36];
-                unsigned long long a01 = 0ull, a23 = 0ull;
-#pragma unroll
-                for (int kq = 0; kq < 8; ++kq) {
-                    const float4 hv = *reinterpret_cast<const float4 *>(hrow + kq * 4);
-                    ffma2_bcast(a01, w2[0][kq * 4 + 0], hv.x); ffma2_bcast(a23, w2[1][kq * 4 + 0], hv.x);
-                    ffma2_bcast(a01, w2[0][kq * 4 + 1], hv.y); ffma2_bcast(a23, w2[1][kq * 4 + 1], hv.y);
-                    ffma2_bcast(a01, w2[0][kq * 4 + 2], hv.z); ffma2_bcast(a23, w2[1][kq * 4 + 2], hv.z);
-                    ffma2_bcast(a01, w2[0][kq * 4 + 3], hv.w); ffma2_bcast(a23, w2[1][kq * 4 + 3], hv.w);
-                }
-                unpack2f(a01, v[b * 4 + 0], v[b * 4 + 1]);
-                unpack2f(a23, v[b * 4 + 2], v[b * 4 + 3]);
-            }
-            // k-slice sum: butterfly over the 8 adjacent lanes; every lane ends with all 5 lines, lane ks keeps line ks
-#pragma unroll
-            for (int i = 0; i < GL * 4; ++i) {
-                float t = v[i];
-                t += __shfl_xor_sync(0xffffffffu, t, 4); t += __shfl_xor_sync(0xffffffffu, t, 2); t += __shfl_xor_sync(0xffffffffu, t, 1);
-                v[i] = t;
-            }
-            float pre[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-            for (int b = 0; b < GL; ++b)
-                if (ks == b) { pre[0] = v[b * 4 + 0]; pre[1] = v[b * 4 + 1]; pre[2] = v[b * 4 + 2]; pre[3] = v[b * 4 + 3]; }
-            const bool act = cell[g] && s < len[g];
-            if (act) {
-                const float ig = sigmoidf_acc(pre[0] + gxc[g].x), fg = sigmoidf_acc(pre[1] + gxc[g].y);
-                const float gg = tanhf(pre[2] + gxc[g].z), og = sigmoidf_acc(pre[3] + gxc[g].w);
-                cst[g] = fg * cst[g] + ig * gg;
-                hlast[g] = og * tanhf(cst[g]);
-            }
-            if (s + 1 < maxlen && cell[g]) {        // finished lines keep sending their last h: byte counts stay constant
-                const uint32_t off = (uint32_t)(((((g * 2 + nxt) * GL) + ks) * HLD + (u >> 5) * 36 + (u & 31)) * 4);
-                const uint32_t mb_off = (uint32_t)(sizeof(float) * 2 * 2 * GL * HLD) + (uint32_t)(g * 2 + nxt) * 8u;
-#pragma unroll
-                for (int r = 0; r < CS; ++r) st_async_f32(rbase[r] + off, hlast[g], rbase[r] + mb_off);
-            }
-            if (act) {
-                const int t = dir ? len[g] - 1 - s : s;
-                p.out[(size_t)(base[g] + (long long)t * p.step) * OC + dir * hid + u] = hlast[g];
-            }
-            gxc[g] = gxn[g];
-        }
-    }
-    cluster.sync();
-}
-
 // =============================================================================================
 // softmax statistics + arg-max per time step, then CTC best-path collapse
 //   (logits / T).softmax(1) ; seq[..., :len].max(dim=0) ; groupby ; drop blank 0
