@@ -14,6 +14,7 @@
 #include "kernels.cuh"
 #include "gemm_tc.cuh"
 #include "conv_tc.cuh"
+#include "lstm_tc.cuh"
 #include "vgsl_plan.hpp"
 
 namespace kb {
@@ -44,6 +45,7 @@ struct LeafWeights {
     float *aux = nullptr;   // W_hh [dirs][4h][h] / GN gamma
     float *b_hi = nullptr, *b_lo = nullptr;   // [ncols][K] TF32 split planes for the tcgen05 GEMM (K-major)
     float *c_hi = nullptr, *c_lo = nullptr;   // [tap][Cout][32] TF32 split planes for the tcgen05 convolution
+    void *wpk = nullptr;                      // W_hh as pre-swizzled bf16x3 UMMA tiles [dir][rank][split][k-atom][128][64] (tcgen05 recurrence)
     int ncp = 0, K = 0, ncols = 0;
 };
 
@@ -156,7 +158,7 @@ static void finalize_weights(kb_model *m) {
     for (size_t li = 0; li < m->plan->leaf_nodes.size(); ++li) {
         const Node &n = *m->plan->leaf_nodes[li];
         LeafWeights &w = m->lw[li];
-        w.wt = w.bias = w.aux = w.b_hi = w.b_lo = w.c_hi = w.c_lo = nullptr;
+        w.wt = w.bias = w.aux = w.b_hi = w.b_lo = w.c_hi = w.c_lo = nullptr; w.wpk = nullptr;
         auto need = [&](int slots) {
             for (int s = 0; s < slots; ++s)
                 if ((int)w.loaded.size() <= s || !w.loaded[s]) throw SpecError("weights of layer " + n.name + " not loaded (missing tensor for nn." + n.path + ")");
@@ -227,6 +229,40 @@ static void finalize_weights(kb_model *m) {
                         for (int u = 0; u < h; ++u)
                             memcpy(&rows[(size_t)(d * 4 * h + u * 4 + g) * K], &w.host[d * 4][(size_t)(g * h + u) * K], (size_t)K * sizeof(float));
                 upload_split(m, rows, w);
+            }
+            if (h > 128 && h <= 256) {
+                // tcgen05 recurrence operand: per (dir, cluster rank) 128 gate rows (row = 4*slot + gate, 32 unit slots per CTA)
+                // x K = 256 (k = 32*rank' + slot'), three bf16 planes, 64-wide k-atoms, 128B swizzle applied here
+                const int U = (h + 7) / 8;
+                auto f2bf = [](float f) { uint32_t u; memcpy(&u, &f, 4); const uint32_t lsb = (u >> 16) & 1u; u += 0x7FFFu + lsb; return (uint16_t)(u >> 16); };
+                auto bf2f = [](uint16_t b) { uint32_t u = (uint32_t)b << 16; float f; memcpy(&f, &u, 4); return f; };
+                std::vector<uint16_t> pk((size_t)dirs * 8 * 3 * 4 * 128 * 64, 0);
+                for (int d = 0; d < dirs; ++d) {
+                    const std::vector<float> &wh = w.host[d * 4 + 1];      // [4h][h]
+                    for (int r = 0; r < 8; ++r)
+                        for (int mrow = 0; mrow < 128; ++mrow) {
+                            const int slot = mrow >> 2, gate = mrow & 3, u = r * U + slot;
+                            if (slot >= U || u >= h) continue;
+                            for (int kp = 0; kp < 256; ++kp) {
+                                const int r2 = kp >> 5, s2 = kp & 31, u2 = r2 * U + s2;
+                                if (s2 >= U || u2 >= h) continue;
+                                const float x = wh[(size_t)(gate * h + u) * h + u2];
+                                const uint16_t b1 = f2bf(x); const float r1 = x - bf2f(b1);
+                                const uint16_t b2 = f2bf(r1); const float rr = r1 - bf2f(b2);
+                                const uint16_t b3 = f2bf(rr);
+                                const int ka = kp >> 6, kk = kp & 63, cch = kk >> 3, e = kk & 7;
+                                const size_t in_tile = (size_t)mrow * 64 + (size_t)((cch ^ (mrow & 7)) * 8) + e;
+                                const uint16_t bs[3] = {b1, b2, b3};
+                                for (int sp = 0; sp < 3; ++sp)
+                                    pk[((((size_t)d * 8 + r) * 3 + sp) * 4 + ka) * (128 * 64) + in_tile] = bs[sp];
+                            }
+                        }
+                }
+                void *dp = nullptr;
+                CK(cudaMalloc(&dp, pk.size() * sizeof(uint16_t)));
+                m->dev_allocs.push_back(dp);
+                CK(cudaMemcpy(dp, pk.data(), pk.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+                w.wpk = dp;
             }
         }
     }
@@ -388,6 +424,25 @@ struct Exec {
                 else { lp.nseq = (int)(x.n * x.w); lp.T = (int)x.h; lp.q2 = (int)x.w; lp.s_outer = x.h * x.w; lp.s_inner = 1; lp.step = x.w; }
                 const int ks = hid <= 32 ? 1 : hid <= 64 ? 2 : hid <= 128 ? 4 : 8;
                 lp.U = (hid + ks - 1) / ks;
+                const bool rec_tc = ks == 8 && w.wpk && m->use_tc && !(getenv("KB_LSTM_TC") && atoi(getenv("KB_LSTM_TC")) == 0);
+                if (rec_tc) {
+                    ltc::LstmTcParams tp;
+                    tp.gx = lp.gx; tp.wpk = (const __nv_bfloat16 *)w.wpk; tp.out = lp.out; tp.lens = lp.lens; tp.nseq = lp.nseq; tp.T = lp.T;
+                    tp.hid = hid; tp.dirs = dirs; tp.U = lp.U; tp.q2 = lp.q2; tp.s_outer = lp.s_outer; tp.s_inner = lp.s_inner; tp.step = lp.step;
+                    static bool attr_set = false;
+                    if (!attr_set) { CK(cudaFuncSetAttribute(ltc::k_lstm_rec_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, ltc::LSMEM_BYTES)); attr_set = true; }
+                    cudaLaunchConfig_t tcfg = {};
+                    tcfg.gridDim = dim3((unsigned)(ltc::LCS * ((lp.nseq + ltc::NL - 1) / ltc::NL)), (unsigned)dirs, 1);
+                    tcfg.blockDim = dim3(ltc::LTHREADS, 1, 1);
+                    tcfg.dynamicSmemBytes = ltc::LSMEM_BYTES; tcfg.stream = st;
+                    cudaLaunchAttribute tat[1];
+                    tat[0].id = cudaLaunchAttributeClusterDimension;
+                    tat[0].val.clusterDim.x = ltc::LCS; tat[0].val.clusterDim.y = 1; tat[0].val.clusterDim.z = 1;
+                    tcfg.attrs = tat; tcfg.numAttrs = 1;
+                    CK(cudaLaunchKernelEx(&tcfg, ltc::k_lstm_rec_tc, tp));
+                    ++m->launches;
+                    CK(cudaPeekAtLastError());
+                } else {
                 const int BL = 64 / ks;
                 const int nchunks = (lp.nseq + BL - 1) / BL;
                 cudaLaunchConfig_t cfg = {};
@@ -427,6 +482,7 @@ struct Exec {
                 }
                 ++m->launches;
                 CK(cudaPeekAtLastError());
+                }
             }
             if (n.summarize) {
                 y = mk(dout);
