@@ -1,4 +1,8 @@
 // lstm_tc.cuh - LSTM recurrence on tcgen05 tensor cores for hidden sizes 129..256 (sm_100a).
+// EXPERIMENTAL, opt-in with KB_LSTM_TC=1: bit-for-bit label parity like the default kernel (tests/test_gpu_parity.py::
+// test_tensor_core_recurrence) but measured 2.4x SLOWER on cfg2 (1.63 ms vs 0.69 ms per 64 x 200 steps): a step is 96
+// dependent M128xN16xK16 MMAs on two accumulators (accumulator-latency bound, ~12k cycles) followed by the serialised
+// pointwise + all-to-all exchange.  Kept as the starting point for the N=48 merged-operand variant described in DESIGN.md.
 //
 // Same contract as k_lstm_rec (kernels.cuh): per-pixel gate pre-activations gx in, hidden states out, packed-sequence
 // semantics, one direction per blockIdx.y.  What changes is where  W_hh . h_{t-1}  is computed:

@@ -307,3 +307,29 @@ def test_fused_groups_and_conv_tc(spec, h, widths):
             with env(KB_FUSE=0, KB_GEMM='ffma'):
                 out2, _ = m.nn(x.cuda(), sl)
             assert rel_err(out2, ref) <= TIGHT
+
+
+@pytest.mark.parametrize('hid', [256, 200, 136])
+def test_tensor_core_recurrence(hid):
+    """Opt-in tcgen05 recurrence (KB_LSTM_TC=1, csrc/lstm_tc.cuh): bf16x3 split W_hh / h, main+correction accumulators."""
+    spec = f'[1,16,0,1 Cr3,3,32 Mp2,2 S1(1x0)1,3 Lbx{hid} O1c30]'
+    om = vo.OracleModel(spec)
+    wts = om.init_like_reference(51)
+    g = torch.Generator().manual_seed(51)
+    n, w = 21, 150
+    lens = torch.randint(20, w + 1, (n,), generator=g)
+    lens[0] = w
+    x = torch.rand(n, 1, 16, w, generator=g)
+    for i, l in enumerate(lens.tolist()):
+        x[i, ..., l:] = 0
+    ref, rl = om.forward(x, lens)
+    _, _, _, ref_dec = vo.rec_predict(om, x, lens)
+    m = kb.TorchVGSLModel(vgsl=spec)
+    m.load_state_dict(wts)
+    m.to('cuda:0')
+    with env(KB_LSTM_TC=1):
+        out, ol = m.nn(x.cuda(), lens)
+        dec = kb.TorchSeqRecognizer(m, device='cuda:0').predict_labels(x.cuda(), lens)
+    assert rel_err(out, ref) <= TIGHT
+    assert ol.tolist() == rl.tolist()
+    assert triples(dec) == triples(ref_dec)
