@@ -219,6 +219,62 @@ def run_reference_arm(args, rank):
     print(json.dumps(line), flush=True)
 
 
+BLLA = ('[1,1800,0,3 Cr7,7,64,2,2 Gn32 Cr3,3,128,2,2 Gn32 Cr3,3,128 Gn32 Cr3,3,256 Gn32 Cr3,3,256 Gn32 '
+        'Lbx32 Lby32 Cr1,1,32 Gn32 Lby32 Lbx32 O2l4]')
+
+
+def run_cfg3(args):
+    """BASELINE configs[2]: blla.mlmodel architecture, 2400x3200 pages (-> 3x1800x1350 net input), batch 8, 1 GPU:
+    nn -> nearest upsample to the input size -> sigmoid (`kb_segment`).  Reports pages/s next to the oracle on the CPU."""
+    import __graft_entry__ as ge
+    ge.build()
+    import kraken_b200 as kb
+    from kraken_b200.blla import segmentation_heatmap
+    sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+    import vgsl_oracle as vo
+    N, H, W = args.pages, 1800, 1350
+    om = vo.OracleModel(BLLA)
+    w = om.init_like_reference(3)
+    m = kb.TorchVGSLModel(vgsl=BLLA, model_type=['segmentation'])
+    m.load_state_dict(w)
+    m.to('cuda:0')
+    g = torch.Generator().manual_seed(3)
+    pages = [torch.rand(N, 3, H, W, generator=g).cuda() for _ in range(2)]
+    for i in range(max(2, args.warmup)):
+        segmentation_heatmap(m, pages[i % 2], (H, W))
+    m.set_timing(True)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    stage = {}
+    m.reset_launch_count()
+    e0.record()
+    for i in range(args.steps):
+        hm = segmentation_heatmap(m, pages[i % 2], (H, W))
+        for k, v in m.last_timing():
+            stage[k] = stage.get(k, 0.0) + v
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / args.steps
+    cpu = None
+    if not args.no_cpu_baseline:
+        torch.set_num_threads(usable_cpus())
+        x1 = pages[0][:1].cpu()
+        vo.seg_heatmap(om, x1, (H, W))
+        t0 = time.perf_counter()
+        for _ in range(2):
+            vo.seg_heatmap(om, x1, (H, W))          # the reference never batches pages (spred.py:268)
+        cpu = {'value': 2 / (time.perf_counter() - t0), 'unit': 'pages/s', 'cores': usable_cpus(), 'kind': 'port', 'cpu': cpu_model_name(),
+               'sample': '2 pages 3x1800x1350 after 1 warm-up, oracle seg_heatmap (nn + interpolate + sigmoid), batch 1'}
+    flops = 390.9e9 * N
+    line = {'metric': 'pages/sec (blla forward, 2400x3200 pages)', 'value': N / (ms / 1e3), 'unit': 'pages/s', 'n_gpus': 1, 'steps': args.steps,
+            'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
+            'data': 'synthetic', 'config': {'workload': 'cfg3', 'spec': BLLA, 'batch': N, 'page': f'3x{H}x{W}', 'heatmap': f'4x{H}x{W}'},
+            'gpu_launches': int(m.launch_count), 'stages_ms': {k: round(v / args.steps, 3) for k, v in stage.items()},
+            'whole_step_tflops_fp32_equiv': flops / (ms / 1e3) / 1e12, 'cpu_baseline': cpu,
+            'heatmap_range': [float(hm.min()), float(hm.max())]}
+    print(json.dumps(line), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -228,6 +284,8 @@ def main():
     ap.add_argument('--cpu-steps', type=int, default=6)
     ap.add_argument('--inflight', type=int, default=2, help='engine handles driven concurrently in the e2e arm')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--workload', default='cfg2', choices=['cfg2', 'cfg3'])
+    ap.add_argument('--pages', type=int, default=8)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'b200' else args.warmup
 
@@ -236,6 +294,10 @@ def main():
     local = int(os.environ.get('LOCAL_RANK', '0'))
     if args.impl == 'reference':
         run_reference_arm(args, rank)
+        return
+    if args.workload == 'cfg3':
+        if rank == 0:
+            run_cfg3(args)
         return
 
     import __graft_entry__ as ge
