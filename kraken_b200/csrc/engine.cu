@@ -231,12 +231,13 @@ static void finalize_weights(kb_model *m) {
                 upload_split(m, rows, w);
             }
             if (h > 128 && h <= 256) {
-                // tcgen05 recurrence operand: per (dir, cluster rank) 128 gate rows (row = 4*slot + gate, 32 unit slots per CTA)
-                // x K = 256 (k = 32*rank' + slot'), three bf16 planes, 64-wide k-atoms, 128B swizzle applied here
+                // tcgen05 recurrence operand (lstm_tc.cuh): per (dir, cluster rank) 128 gate rows (row = 4*slot + gate, 32 unit slots per
+                // CTA) x K = 256 (k = 32*rank' + slot'); plane 0 = bf16(W), plane 1 = fp16((W - plane0) * 2^8); 64-wide k-atoms with the
+                // 128B swizzle applied here so that plain bulk copies land in UMMA layout
                 const int U = (h + 7) / 8;
                 auto f2bf = [](float f) { uint32_t u; memcpy(&u, &f, 4); const uint32_t lsb = (u >> 16) & 1u; u += 0x7FFFu + lsb; return (uint16_t)(u >> 16); };
                 auto bf2f = [](uint16_t b) { uint32_t u = (uint32_t)b << 16; float f; memcpy(&f, &u, 4); return f; };
-                std::vector<uint16_t> pk((size_t)dirs * 8 * 3 * 4 * 128 * 64, 0);
+                std::vector<uint16_t> pk((size_t)dirs * 8 * 2 * 4 * 128 * 64, 0);
                 for (int d = 0; d < dirs; ++d) {
                     const std::vector<float> &wh = w.host[d * 4 + 1];      // [4h][h]
                     for (int r = 0; r < 8; ++r)
@@ -247,14 +248,12 @@ static void finalize_weights(kb_model *m) {
                                 const int r2 = kp >> 5, s2 = kp & 31, u2 = r2 * U + s2;
                                 if (s2 >= U || u2 >= h) continue;
                                 const float x = wh[(size_t)(gate * h + u) * h + u2];
-                                const uint16_t b1 = f2bf(x); const float r1 = x - bf2f(b1);
-                                const uint16_t b2 = f2bf(r1); const float rr = r1 - bf2f(b2);
-                                const uint16_t b3 = f2bf(rr);
+                                const uint16_t b1 = f2bf(x);
+                                const uint16_t b2 = __half_as_ushort(__float2half_rn((x - bf2f(b1)) * ltc::W2_SCALE));
                                 const int ka = kp >> 6, kk = kp & 63, cch = kk >> 3, e = kk & 7;
                                 const size_t in_tile = (size_t)mrow * 64 + (size_t)((cch ^ (mrow & 7)) * 8) + e;
-                                const uint16_t bs[3] = {b1, b2, b3};
-                                for (int sp = 0; sp < 3; ++sp)
-                                    pk[((((size_t)d * 8 + r) * 3 + sp) * 4 + ka) * (128 * 64) + in_tile] = bs[sp];
+                                pk[((((size_t)d * 8 + r) * 2 + 0) * 4 + ka) * (128 * 64) + in_tile] = b1;
+                                pk[((((size_t)d * 8 + r) * 2 + 1) * 4 + ka) * (128 * 64) + in_tile] = b2;
                             }
                         }
                 }
@@ -429,7 +428,7 @@ struct Exec {
                 const bool rec_tc = ks == 8 && w.wpk && m->use_tc && getenv("KB_LSTM_TC") && atoi(getenv("KB_LSTM_TC")) == 1;
                 if (rec_tc) {
                     ltc::LstmTcParams tp;
-                    tp.gx = lp.gx; tp.wpk = (const __nv_bfloat16 *)w.wpk; tp.out = lp.out; tp.lens = lp.lens; tp.nseq = lp.nseq; tp.T = lp.T;
+                    tp.gx = lp.gx; tp.wpk = (const uint16_t *)w.wpk; tp.out = lp.out; tp.lens = lp.lens; tp.nseq = lp.nseq; tp.T = lp.T;
                     tp.hid = hid; tp.dirs = dirs; tp.U = lp.U; tp.q2 = lp.q2; tp.s_outer = lp.s_outer; tp.s_inner = lp.s_inner; tp.step = lp.step;
                     static bool attr_set = false;
                     if (!attr_set) { CK(cudaFuncSetAttribute(ltc::k_lstm_rec_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, ltc::LSMEM_BYTES)); attr_set = true; }

@@ -1,31 +1,29 @@
-// lstm_tc.cuh - LSTM recurrence on tcgen05 tensor cores for hidden sizes 129..256 (sm_100a).
-// EXPERIMENTAL, opt-in with KB_LSTM_TC=1: bit-for-bit label parity like the default kernel (tests/test_gpu_parity.py::
-// test_tensor_core_recurrence) but measured 2.4x SLOWER on cfg2 (1.63 ms vs 0.69 ms per 64 x 200 steps): a step is 96
-// dependent M128xN16xK16 MMAs on two accumulators (accumulator-latency bound, ~12k cycles) followed by the serialised
-// pointwise + all-to-all exchange.  Kept as the starting point for the N=48 merged-operand variant described in DESIGN.md.
+// lstm_tc.cuh - LSTM recurrence on tcgen05 tensor cores for hidden sizes 129..256 (sm_100a), version 2.
 //
 // Same contract as k_lstm_rec (kernels.cuh): per-pixel gate pre-activations gx in, hidden states out, packed-sequence
-// semantics, one direction per blockIdx.y.  What changes is where  W_hh . h_{t-1}  is computed:
+// semantics, one direction per blockIdx.y.  The CUDA-core kernel is at the 3-register-FFMA issue limit,
+// so W_hh . h_{t-1} moves to the tensor cores:
 //
-//   cluster of 8 CTAs = 16 sequences of one direction for all time steps; CTA r owns hidden units [32r, 32r+32)
-//   (unit slots are padded to 32 per CTA, so any hid <= 256 works), i.e. 128 gate rows, ordered unit-major
-//   (row = 4*unit + gate) so that the 4 gates of a unit sit in 4 adjacent TMEM lanes.
+//   cluster of 8 CTAs = 16 sequences of one direction for all time steps; CTA r owns unit slots [32r, 32r+32) (padded, any
+//   hid <= 256), i.e. 128 gate rows ordered unit-major (row = 4*slot + gate: a unit's gates sit in 4 adjacent TMEM lanes).
 //
-//   A = W_hh slice [128 rows][K = 256], split into THREE bf16 planes (w = w1 + w2 + w3, 24 significand bits), resident in
-//       shared memory for the whole kernel in the UMMA K-major 128B-swizzle layout (pre-swizzled on the host,
-//       fetched with 12 cp.async.bulk copies): 192 KB.
-//   B = h_{t-1}^T [16 lines][K = 256], three bf16 planes as well (24 KB), written REMOTELY: every CTA converts the h_t
-//       of its 32 units to bf16x3 and st.async.v4's the 16-byte chunks into all 8 CTAs' B tiles; the destination's
-//       mbarrier counts the bytes (no cluster barrier, no fence).
-//   D = 96 x tcgen05.mma.kind::f16 (M128 x N16 x K16) per step into two TMEM accumulators:
-//       main = w1*h1 (16 accumulations - keeps the tensor core's round-toward-zero chain short),
-//       corr = w1*h2 + w2*h1 + w2*h2 + w1*h3 + w3*h1   (dropped terms <= 2^-24).
-//   epilogue: tcgen05.ld -> + gx -> sigmoid/tanh (accurate expf/tanhf) -> gates regrouped through shared memory ->
-//       fp32 cell update (4 cells per thread) -> h_t to HBM and to every CTA's B operand.
-//   B is single-buffered (shared memory is full), so a CTA signals "my MMAs of this step have retired" to all CTAs
-//   (remote mbarrier arrive) and senders wait for 8 such signals before overwriting B.
+//   A (resident in shared memory, UMMA K-major 128B-swizzle tiles, pre-swizzled on the host, 8 cp.async.bulk copies, 128 KB):
+//       W1 = bf16(W)                     and     W2s = fp16((W - W1) * 2^8)      (|W - W1 - W2s/2^8| <= 2^-20 |W|)
+//   B (double buffered, 2 x 24 KB): h_{t-1} as three bf16 planes stacked along N: rows [0,16) h1, [16,32) h2, [32,48) h3,
+//       written REMOTELY by every CTA of the cluster with st.async.v4 (16-byte chunks = 8 unit slots), byte-counted by
+//       the destination's mbarrier (no cluster barrier, no fence, no "buffer free" handshake thanks to the double buffer).
+//   D: per step 32 MMAs   W1 x [h1|h2|h3]  (kind::f16 bf16 x bf16, M128 x N48 x K16)   and
+//                         W2s x [h1|h2]    (kind::f16 fp16 x bf16, M128 x N32 x K16)
+//       into FOUR independent TMEM accumulator chains (k-atoms {0,1} / {2,3} x {W1, W2s}), issued round-robin: version 1
+//       issued 96 dependent N=16 MMAs on two accumulators and measured ~125 cycles per dependent MMA (accumulator
+//       latency), 12 k cycles per step, 1.63 ms on cfg2.  Every fp32 accumulator element sees only 8 accumulations.
+//       pre = D1[:, h1] + (D1[:, h2] + D1[:, h3] + 2^-8 (D2[:, h1] + D2[:, h2]))        (dropped: W2*h3 ~ 2^-25)
+//   epilogue: 8 warps (TMEM lane quarter x line half): tcgen05.ld -> + gx -> sigmoid / tanh (accurate expf / tanhf) ->
+//       gates regrouped through shared memory -> fp32 cell update (2 cells per thread) -> h_t to HBM and, split into
+//       bf16 x 3, to every CTA's next B buffer.
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include "gemm_tc.cuh"
 
@@ -34,42 +32,41 @@ namespace ltc {
 
 using namespace kb::tc;
 
-constexpr int NL = 16;                                   // lines per cluster (= MMA N)
+constexpr int NL = 16;                                   // lines per cluster
 constexpr int LCS = 8;                                   // cluster size
-constexpr int A_TILE_B = 128 * 128;                      // one (split, k-atom) tile of A: 128 rows x 128 B
-constexpr int A_BYTES = 3 * 4 * A_TILE_B;                // 196608
-constexpr int B_TILE_B = NL * 128;                       // one (split, k-atom) tile of B: 16 rows x 128 B
-constexpr int B_BYTES = 3 * 4 * B_TILE_B;                // 24576
-constexpr int STG_BYTES = 4 * NL * 8 * 4 * 4;            // per warp [16 lines][8 units][4 gates] fp32 = 2 KB -> 8 KB
-constexpr int LSMEM_BYTES = A_BYTES + B_BYTES + STG_BYTES + 128 + 1024;
-constexpr int LTHREADS = 160;                            // warp 0: MMA issue / TMEM; warps 1..4: epilogue
+constexpr int A_TILE_B = 128 * 128;                      // one (plane, k-atom) tile of A: 128 rows x 128 B
+constexpr int A_BYTES = 2 * 4 * A_TILE_B;                // 131072: W1 (bf16) and W2s (fp16)
+constexpr int B_ROWS = 3 * NL;                           // 48 rows: h1 | h2 | h3
+constexpr int B_TILE_B = B_ROWS * 128;                   // 6144 bytes per k-atom
+constexpr int B_BUF_B = 4 * B_TILE_B;                    // 24576 bytes per buffer
+constexpr int SG_FLOATS = NL * 8 * 4;                    // per TMEM-lane quarter: [line][unit][gate]
+constexpr int SH_FLOATS = NL * 8;                        // per quarter: [line][unit]
+constexpr int STG_BYTES = 4 * (SG_FLOATS + SH_FLOATS) * 4;
+constexpr int LSMEM_BYTES = A_BYTES + 2 * B_BUF_B + STG_BYTES + 128 + 1024;
+constexpr int LTHREADS = 32 + 8 * 32;                    // warp 0: MMA issue / TMEM; warps 1..8: epilogue
+constexpr int TM_COLS = 256;                             // D1a @0 (48), D1b @48, D2a @96 (32), D2b @128
+constexpr float W2_SCALE = 256.f;
 
 struct LstmTcParams {
-    const float *gx; const __nv_bfloat16 *wpk; float *out; const int *lens;
+    const float *gx; const uint16_t *wpk; float *out; const int *lens;
     int nseq, T, hid, dirs, U;
     int q2; long long s_outer, s_inner, step;
 };
 
-__device__ __forceinline__ uint32_t idesc_bf16(int m, int n) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+// kind::f16 instruction descriptor: fp32 accumulate, K-major operands; a_fmt/b_fmt: 0 = fp16, 1 = bf16
+__device__ __forceinline__ uint32_t idesc_f16(int a_fmt, int b_fmt, int m, int n) {
+    return (1u << 4) | ((uint32_t)a_fmt << 7) | ((uint32_t)b_fmt << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
-__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float *v) {
-    uint32_t r[16];
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
-          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-        : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+__device__ __forceinline__ void tmem_ld8_nowait(uint32_t taddr, uint32_t *r) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "r"(taddr));
 }
 __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -84,10 +81,7 @@ __device__ __forceinline__ void st_async_v4(uint32_t raddr, uint4 v, uint32_t rm
     asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];"
                  ::"r"(raddr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "r"(rmbar) : "memory");
 }
-__device__ __forceinline__ void remote_arrive(uint32_t rmbar) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(rmbar) : "memory");
-}
-__device__ __forceinline__ void mbar_wait_cluster(uint64_t *bar, uint32_t parity) {      // acquire at cluster scope (remote arrivals)
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t *bar, uint32_t parity) {      // acquire at cluster scope (remote st.async)
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "CW_%=:\n\t"
@@ -96,22 +90,15 @@ __device__ __forceinline__ void mbar_wait_cluster(uint64_t *bar, uint32_t parity
         "bra CW_%=;\n\t"
         "CD_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
-// x -> three bf16 terms, x == b1 + b2 + b3 up to 2^-24 |x|
-__device__ __forceinline__ void split3(float x, __nv_bfloat16 &b1, __nv_bfloat16 &b2, __nv_bfloat16 &b3) {
-    b1 = __float2bfloat16_rn(x);
-    const float r1 = x - __bfloat162float(b1);
-    b2 = __float2bfloat16_rn(r1);
-    const float r2 = r1 - __bfloat162float(b2);
-    b3 = __float2bfloat16_rn(r2);
-}
+__device__ __forceinline__ void named_bar(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 
 __global__ void __launch_bounds__(LTHREADS, 1) k_lstm_rec_tc(LstmTcParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t *sA = smem, *sB = smem + A_BYTES;
-    float *stg = reinterpret_cast<float *>(sB + B_BYTES);
-    uint64_t *bars = reinterpret_cast<uint64_t *>(sB + B_BYTES + STG_BYTES);
-    uint64_t *a_full = bars, *b_full = bars + 1, *b_free = bars + 2, *mma_done = bars + 3;
+    float *stg = reinterpret_cast<float *>(sB + 2 * B_BUF_B);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sB + 2 * B_BUF_B + STG_BYTES);
+    uint64_t *a_full = bars, *b_full = bars + 1 /* [2] */, *mma_done = bars + 3;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 4);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -121,28 +108,26 @@ __global__ void __launch_bounds__(LTHREADS, 1) k_lstm_rec_tc(LstmTcParams p) {
     const int hid = p.hid, GC = p.dirs * 4 * hid, OC = p.dirs * hid;
 
     if (threadIdx.x == 0) {
-        mbar_init(a_full, 1); mbar_init(b_full, 1); mbar_init(b_free, LCS); mbar_init(mma_done, 1);
+        mbar_init(a_full, 1); mbar_init(&b_full[0], 1); mbar_init(&b_full[1], 1); mbar_init(mma_done, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         mbar_expect_tx(a_full, A_BYTES);
         const uint8_t *src = reinterpret_cast<const uint8_t *>(p.wpk) + ((size_t)dir * LCS + rank) * A_BYTES;
-        for (int i = 0; i < 12; ++i) bulk_g2s(sA + i * A_TILE_B, src + (size_t)i * A_TILE_B, A_TILE_B, a_full);
-        mbar_expect_tx(b_full, B_BYTES);                 // first fill: the h_0 every CTA sends at the end of step 0
+        for (int i = 0; i < 8; ++i) bulk_g2s(sA + i * A_TILE_B, src + (size_t)i * A_TILE_B, A_TILE_B, a_full);
+        mbar_expect_tx(&b_full[1], B_BUF_B);             // buffer 1 receives h_0 at the end of step 0
     }
-    for (int i = threadIdx.x; i < B_BYTES / 16; i += LTHREADS) reinterpret_cast<uint4 *>(sB)[i] = make_uint4(0, 0, 0, 0);   // h_{-1} = 0
+    for (int i = threadIdx.x; i < 2 * B_BUF_B / 16; i += LTHREADS) reinterpret_cast<uint4 *>(sB)[i] = make_uint4(0, 0, 0, 0);   // h_{-1} = 0
     if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(32) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    // generic-proxy zero fill of B must be visible to the async proxy (UMMA reads)
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic zero fill -> visible to UMMA reads
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 
-    // sequence lengths of the 16 lines of this cluster (uniform across the cluster)
-    int maxlen = 0;
+    int maxlen = 0;                                       // uniform across the cluster
     for (int lb = 0; lb < NL; ++lb) {
         const int q = chunk * NL + lb;
         if (q < p.nseq) maxlen = max(maxlen, p.lens ? min(max(p.lens[q], 0), p.T) : p.T);
@@ -150,28 +135,29 @@ __global__ void __launch_bounds__(LTHREADS, 1) k_lstm_rec_tc(LstmTcParams p) {
 
     if (warp == 0) {
         // ===================== MMA issuer =====================
-        const uint32_t idesc = idesc_bf16(128, NL);
-        const uint32_t d_main = tmem_base, d_corr = tmem_base + NL;
+        const uint32_t id1 = idesc_f16(1, 1, 128, 48), id2 = idesc_f16(0, 1, 128, 32);
         mbar_wait(a_full, 0);
         for (int s = 0; s < maxlen; ++s) {
-            if (s > 0) mbar_wait_cluster(b_full, (uint32_t)((s - 1) & 1));
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // st.async writes -> visible to the UMMA (async proxy) reads
+            const int cur = s & 1;
+            if (s > 0) mbar_wait_cluster(&b_full[cur], (uint32_t)(((s - 1) >> 1) & 1));
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // st.async writes -> UMMA (async proxy) reads
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             if (elect_one()) {
-                if (s > 0 && s + 1 < maxlen) mbar_expect_tx(b_full, B_BYTES);      // next fill (sent at the end of this step)
-                const uint32_t a0 = smem_u32(sA), b0 = smem_u32(sB);
-                // (A split, B split) pairs: main first, then the five correction products
-                const int pa[6] = {0, 0, 1, 1, 0, 2}, pb[6] = {0, 1, 0, 1, 2, 0};
+                // this buffer is refilled during step s+1 (nobody can send that before receiving our h_s)
+                if (s + 2 < maxlen) mbar_expect_tx(&b_full[cur], B_BUF_B);
+                const uint32_t a0 = smem_u32(sA), b0 = smem_u32(sB + cur * B_BUF_B);
 #pragma unroll
-                for (int pr = 0; pr < 6; ++pr) {
-                    const uint32_t d = pr == 0 ? d_main : d_corr;
+                for (int k = 0; k < 4; ++k) {
 #pragma unroll
-                    for (int ka = 0; ka < 4; ++ka) {
-                        const uint64_t ad = umma_desc_sw128(a0 + (uint32_t)((pa[pr] * 4 + ka) * A_TILE_B));
-                        const uint64_t bd = umma_desc_sw128(b0 + (uint32_t)((pb[pr] * 4 + ka) * B_TILE_B));
-#pragma unroll
-                        for (int k = 0; k < 4; ++k)
-                            umma_bf16(d, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (pr <= 1 && ka == 0 && k == 0) ? 0u : 1u);
+                    for (int kk = 0; kk < 4; ++kk) {
+                        const int ka = kk == 0 ? 0 : kk == 1 ? 2 : kk == 2 ? 1 : 3;      // 0,2,1,3: same-chain MMAs 4 issues apart
+                        const int half = ka >> 1;
+                        const uint64_t bd = umma_desc_sw128(b0 + (uint32_t)(ka * B_TILE_B)) + (uint64_t)(2 * k);
+                        const uint64_t a1 = umma_desc_sw128(a0 + (uint32_t)(ka * A_TILE_B)) + (uint64_t)(2 * k);
+                        const uint64_t a2 = umma_desc_sw128(a0 + (uint32_t)((4 + ka) * A_TILE_B)) + (uint64_t)(2 * k);
+                        const uint32_t first = ((ka & 1) == 0 && k == 0) ? 0u : 1u;
+                        umma_f16(tmem_base + (uint32_t)(half * 48), a1, bd, id1, first);
+                        umma_f16(tmem_base + (uint32_t)(96 + half * 32), a2, bd, id2, first);
                     }
                 }
                 umma_commit(mma_done);
@@ -179,121 +165,116 @@ __global__ void __launch_bounds__(LTHREADS, 1) k_lstm_rec_tc(LstmTcParams p) {
             __syncwarp();
         }
     } else {
-        // ===================== epilogue warps 1..4 =====================
-        const int q = warp & 3;                            // TMEM lane quarter: lanes 32q .. 32q+31 = unit slots 8q .. 8q+7
-        const int jq = lane >> 2, g = lane & 3;            // unit slot within the warp, gate (i,f,g,o) of this lane's TMEM row
-        const int slot = 8 * q + jq;                       // unit slot in the CTA (0..31)
-        const int u = (int)rank * p.U + slot;              // real hidden unit
+        // ===================== epilogue warps 1..8 =====================
+        const int q = warp & 3;                            // TMEM lane quarter: unit slots 8q .. 8q+7
+        const int lh = (warp - 1) >> 2;                    // line half: lines 8*lh .. 8*lh+7 of this thread's TMEM row
+        const int jq = lane >> 2, g = lane & 3;            // unit slot within the quarter, gate of this TMEM row
+        const int slot = 8 * q + jq, u = (int)rank * p.U + slot;
         const bool uvalid = slot < p.U && u < hid;
-        float *wstg = stg + q * (NL * 8 * 4);              // this warp's [line][unit][gate] staging
-        // the 4 cells this thread updates: unit jq, lines 4b + g  (after the regroup lane g of a unit owns lines = g mod 4)
-        int len4[4]; long long base4[4]; float cst[4]; bool lv[4];
+        float *sg = stg + q * (SG_FLOATS + SH_FLOATS), *sh = sg + SG_FLOATS;
+        const int tq = lh * 32 + lane;                     // thread index within the quarter's 64 threads
+        // cells of this thread: line cl = tq / 4, unit slots cu0 = 2*(tq % 4), cu0 + 1
+        const int cl = tq >> 2, cu0 = (tq & 3) * 2;
+        int clen; long long cbase; bool cvalid; float cst[2] = {0.f, 0.f}; int cu[2]; bool cuv[2];
+        {
+            const int ql = chunk * NL + cl;
+            cvalid = ql < p.nseq;
+            const int l = cvalid ? (p.lens ? p.lens[ql] : p.T) : 0;
+            clen = min(max(l, 0), p.T);
+            const int qq = cvalid ? ql : 0;
+            cbase = (long long)(qq / p.q2) * p.s_outer + (long long)(qq % p.q2) * p.s_inner;
 #pragma unroll
-        for (int b = 0; b < 4; ++b) {
-            const int ql = chunk * NL + 4 * b + g;
-            lv[b] = ql < p.nseq;
-            const int l = lv[b] ? (p.lens ? p.lens[ql] : p.T) : 0;
-            len4[b] = min(max(l, 0), p.T);
-            const int qq = lv[b] ? ql : 0;
-            base4[b] = (long long)(qq / p.q2) * p.s_outer + (long long)(qq % p.q2) * p.s_inner;
-            cst[b] = 0.f;
+            for (int e = 0; e < 2; ++e) {
+                const int sl = 8 * q + cu0 + e;
+                cu[e] = (int)rank * p.U + sl; cuv[e] = sl < p.U && cu[e] < hid;
+                if (cvalid && cuv[e]) for (int t = clen; t < p.T; ++t) p.out[(size_t)(cbase + (long long)t * p.step) * OC + dir * hid + cu[e]] = 0.f;
+            }
         }
-        // zero the padded tails (pad_packed_sequence) of this thread's cells
-        if (uvalid)
+        // gx addressing of this thread's TMEM row (gate g of unit u) for its 8 lines
+        int glen[8]; long long gbase[8];
 #pragma unroll
-            for (int b = 0; b < 4; ++b)
-                if (lv[b]) for (int t = len4[b]; t < p.T; ++t) p.out[(size_t)(base4[b] + (long long)t * p.step) * OC + dir * hid + u] = 0.f;
-        // lengths/bases of all 16 lines for the gx loads of this lane's TMEM row (gate g of unit jq, every line)
-        uint32_t rB[LCS], rFull[LCS], rFree[LCS];
-#pragma unroll
-        for (int r = 0; r < LCS; ++r) {
-            rB[r] = mapa32(smem_u32(sB), (uint32_t)r); rFull[r] = mapa32(smem_u32(b_full), (uint32_t)r); rFree[r] = mapa32(smem_u32(b_free), (uint32_t)r);
+        for (int i = 0; i < 8; ++i) {
+            const int ql = chunk * NL + 8 * lh + i;
+            const bool v = ql < p.nseq && uvalid;
+            glen[i] = v ? min(max(p.lens ? p.lens[ql] : p.T, 0), p.T) : 0;
+            const int qq = ql < p.nseq ? ql : 0;
+            gbase[i] = (long long)(qq / p.q2) * p.s_outer + (long long)(qq % p.q2) * p.s_inner;
         }
+        uint32_t rB[LCS], rFull[LCS];
+#pragma unroll
+        for (int r = 0; r < LCS; ++r) { rB[r] = mapa32(smem_u32(sB), (uint32_t)r); rFull[r] = mapa32(smem_u32(b_full), (uint32_t)r); }
+        const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(8 * lh);
+
         for (int s = 0; s < maxlen; ++s) {
-            // gate pre-activations of x for this row: line i at its own time index
-            float gxv[NL];
+            const int nxt = (s + 1) & 1;
+            float gxv[8];
 #pragma unroll
-            for (int i = 0; i < NL; ++i) {
-                const int ql = chunk * NL + i;
-                float v = 0.f;
-                if (uvalid && ql < p.nseq) {
-                    const int l = p.lens ? min(max(p.lens[ql], 0), p.T) : p.T;
-                    if (s < l) {
-                        const int t = dir ? l - 1 - s : s;
-                        const long long bs = (long long)(ql / p.q2) * p.s_outer + (long long)(ql % p.q2) * p.s_inner;
-                        v = __ldg(p.gx + (size_t)(bs + (long long)t * p.step) * GC + (size_t)dir * 4 * hid + (size_t)u * 4 + g);
-                    }
+            for (int i = 0; i < 8; ++i) {
+                gxv[i] = 0.f;
+                if (s < glen[i]) {
+                    const int t = dir ? glen[i] - 1 - s : s;
+                    gxv[i] = __ldg(p.gx + (size_t)(gbase[i] + (long long)t * p.step) * GC + (size_t)dir * 4 * hid + (size_t)u * 4 + g);
                 }
-                gxv[i] = v;
             }
             mbar_wait(mma_done, (uint32_t)(s & 1));
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            // this CTA's MMAs have retired: its B operand may be overwritten -> tell every CTA of the cluster
-            if (warp == 1 && lane < LCS && s + 1 < maxlen) remote_arrive(rFree[lane]);
-            float dm[NL], dc[NL];
-            const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
-            tmem_ld16(lane_base, dm);
-            tmem_ld16(lane_base + NL, dc);
+            // column blocks: D1a/D1b = [h1 | h2 | h3] x 16 lines, D2a/D2b = [h1 | h2] x 16 lines (scaled by 2^8)
+            uint32_t r1a[8], r1b[8], ra[8], rb[8], rc[8], rd[8], re[8], rf[8], rg[8], rh[8];
+            tmem_ld8_nowait(lane_base + 0, r1a);   tmem_ld8_nowait(lane_base + 48, r1b);        // main: W1 h1
+            tmem_ld8_nowait(lane_base + 16, ra);   tmem_ld8_nowait(lane_base + 64, rb);         // W1 h2
+            tmem_ld8_nowait(lane_base + 32, rc);   tmem_ld8_nowait(lane_base + 80, rd);         // W1 h3
+            tmem_ld8_nowait(lane_base + 96, re);   tmem_ld8_nowait(lane_base + 128, rf);        // W2s h1
+            tmem_ld8_nowait(lane_base + 112, rg);  tmem_ld8_nowait(lane_base + 144, rh);        // W2s h2
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
 #pragma unroll
-            for (int i = 0; i < NL; ++i) {
-                const float pre = (dm[i] + dc[i]) + gxv[i];
-                const float a = g == 2 ? tanhf(pre) : sigmoidf_acc(pre);
-                wstg[(i * 8 + jq) * 4 + g] = a;
+            for (int i = 0; i < 8; ++i) {
+                const float main_ = __uint_as_float(r1a[i]) + __uint_as_float(r1b[i]);
+                const float c1 = (__uint_as_float(ra[i]) + __uint_as_float(rb[i])) + (__uint_as_float(rc[i]) + __uint_as_float(rd[i]));
+                const float c2 = (__uint_as_float(re[i]) + __uint_as_float(rf[i])) + (__uint_as_float(rg[i]) + __uint_as_float(rh[i]));
+                const float pre = (main_ + (c1 + c2 * (1.f / W2_SCALE))) + gxv[i];
+                sg[((8 * lh + i) * 8 + jq) * 4 + g] = g == 2 ? tanhf(pre) : sigmoidf_acc(pre);
             }
-            __syncwarp();
-            float hv[4];
+            named_bar(1 + q, 64);
+            const bool act = cvalid && s < clen;
+            const int t_out = dir ? clen - 1 - s : s;
 #pragma unroll
-            for (int b = 0; b < 4; ++b) {
-                const int line = 4 * b + g;
-                const float4 gt = *reinterpret_cast<const float4 *>(&wstg[(line * 8 + jq) * 4]);     // i, f, g, o
-                const bool act = uvalid && lv[b] && s < len4[b];
-                if (act) {
-                    cst[b] = gt.y * cst[b] + gt.x * gt.z;
-                    hv[b] = gt.w * tanhf(cst[b]);
-                    const int t = dir ? len4[b] - 1 - s : s;
-                    p.out[(size_t)(base4[b] + (long long)t * p.step) * OC + dir * hid + u] = hv[b];
-                } else hv[b] = 0.f;                        // finished / padding cells feed zeros (their h is never used again)
-            }
-            __syncwarp();
-            if (s + 1 < maxlen) {
-                // h_t of the warp's 8 unit slots x 16 lines -> staging as [line][8 units] fp32, then 16-byte bf16 chunks
-                float *hst = wstg;                         // reuse: [16][8]
-#pragma unroll
-                for (int b = 0; b < 4; ++b) hst[(4 * b + g) * 8 + jq] = hv[b];
-                __syncwarp();
-                const int line = lane & 15, part = lane >> 4;      // lanes 0..15: splits 0,1 of line; lanes 16..31: split 2
-                const float4 x0 = *reinterpret_cast<const float4 *>(&hst[line * 8]), x1 = *reinterpret_cast<const float4 *>(&hst[line * 8 + 4]);
-                const float xs[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
-                __nv_bfloat16 s1[8], s2[8], s3[8];
-#pragma unroll
-                for (int e = 0; e < 8; ++e) split3(xs[e], s1[e], s2[e], s3[e]);
-                auto pack = [](const __nv_bfloat16 *v) {
-                    uint4 o;
-                    o.x = (uint32_t)__bfloat16_as_ushort(v[0]) | ((uint32_t)__bfloat16_as_ushort(v[1]) << 16);
-                    o.y = (uint32_t)__bfloat16_as_ushort(v[2]) | ((uint32_t)__bfloat16_as_ushort(v[3]) << 16);
-                    o.z = (uint32_t)__bfloat16_as_ushort(v[4]) | ((uint32_t)__bfloat16_as_ushort(v[5]) << 16);
-                    o.w = (uint32_t)__bfloat16_as_ushort(v[6]) | ((uint32_t)__bfloat16_as_ushort(v[7]) << 16);
-                    return o;
-                };
-                // position of this warp's 8 unit slots in K: k0 = 32*rank + 8*q -> k-atom ka, 16-byte chunk c, swizzled with the row
-                const int k0 = (int)rank * 32 + 8 * q, ka = k0 >> 6, c = (k0 & 63) >> 3;
-                const uint32_t off_in_tile = (uint32_t)(line * 128 + ((c ^ (line & 7)) << 4));
-                // every CTA must have finished reading its B operand for this step
-                mbar_wait_cluster(b_free, (uint32_t)(s & 1));
-                if (part == 0) {
-                    const uint4 c1 = pack(s1), c2 = pack(s2);
-#pragma unroll
-                    for (int r = 0; r < LCS; ++r) {
-                        st_async_v4(rB[r] + (uint32_t)((0 * 4 + ka) * B_TILE_B) + off_in_tile, c1, rFull[r]);
-                        st_async_v4(rB[r] + (uint32_t)((1 * 4 + ka) * B_TILE_B) + off_in_tile, c2, rFull[r]);
-                    }
-                } else {
-                    const uint4 c3 = pack(s3);
-#pragma unroll
-                    for (int r = 0; r < LCS; ++r) st_async_v4(rB[r] + (uint32_t)((2 * 4 + ka) * B_TILE_B) + off_in_tile, c3, rFull[r]);
+            for (int e = 0; e < 2; ++e) {
+                const float4 gt = *reinterpret_cast<const float4 *>(&sg[(cl * 8 + cu0 + e) * 4]);      // i, f, g, o
+                float h = 0.f;                             // finished / padding cells feed zeros (never used again)
+                if (act && cuv[e]) {
+                    cst[e] = gt.y * cst[e] + gt.x * gt.z;
+                    h = gt.w * tanhf(cst[e]);
+                    p.out[(size_t)(cbase + (long long)t_out * p.step) * OC + dir * hid + cu[e]] = h;
                 }
-                __syncwarp();
+                sh[cl * 8 + cu0 + e] = h;
+            }
+            named_bar(1 + q, 64);
+            if (s + 1 < maxlen && tq < 48) {
+                // chunk = 8 unit slots of one line in one bf16 plane: row = plane*16 + line of the k-atom tile
+                const int plane = tq >> 4, line = tq & 15;
+                const float4 x0 = *reinterpret_cast<const float4 *>(&sh[line * 8]), x1 = *reinterpret_cast<const float4 *>(&sh[line * 8 + 4]);
+                const float xs[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+                uint32_t pk[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    uint32_t two[2];
+#pragma unroll
+                    for (int f = 0; f < 2; ++f) {
+                        const float x = xs[2 * e + f];
+                        const __nv_bfloat16 b1 = __float2bfloat16_rn(x);
+                        const float r1 = x - __bfloat162float(b1);
+                        const __nv_bfloat16 b2 = __float2bfloat16_rn(r1);
+                        const __nv_bfloat16 b3 = __float2bfloat16_rn(r1 - __bfloat162float(b2));
+                        two[f] = (uint32_t)__bfloat16_as_ushort(plane == 0 ? b1 : plane == 1 ? b2 : b3);
+                    }
+                    pk[e] = two[0] | (two[1] << 16);
+                }
+                const int k0 = (int)rank * 32 + 8 * q, ka = k0 >> 6, c = (k0 & 63) >> 3, row = plane * NL + line;
+                const uint32_t off = (uint32_t)(nxt * B_BUF_B + ka * B_TILE_B + row * 128 + ((c ^ (row & 7)) << 4));
+                const uint4 v = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+#pragma unroll
+                for (int r = 0; r < LCS; ++r) st_async_v4(rB[r] + off, v, rFull[r] + (uint32_t)nxt * 8u);
             }
         }
     }
@@ -302,7 +283,7 @@ __global__ void __launch_bounds__(LTHREADS, 1) k_lstm_rec_tc(LstmTcParams p) {
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
     if (warp == 0) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(32) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TM_COLS) : "memory");
     }
 }
 
