@@ -232,11 +232,9 @@ static void finalize_weights(kb_model *m) {
             }
             if (h > 128 && h <= 256) {
                 // tcgen05 recurrence operand (lstm_tc.cuh): per (dir, cluster rank) 128 gate rows (row = 4*slot + gate, 32 unit slots per
-                // CTA) x K = 256 (k = 32*rank' + slot'); plane 0 = bf16(W), plane 1 = fp16((W - plane0) * 2^8); 64-wide k-atoms with the
+                // CTA) x K = 256 (k = 32*rank' + slot'); plane 0 = fp16(W), plane 1 = fp16((W - plane0) * 2^11); 64-wide k-atoms with the
                 // 128B swizzle applied here so that plain bulk copies land in UMMA layout
                 const int U = (h + 7) / 8;
-                auto f2bf = [](float f) { uint32_t u; memcpy(&u, &f, 4); const uint32_t lsb = (u >> 16) & 1u; u += 0x7FFFu + lsb; return (uint16_t)(u >> 16); };
-                auto bf2f = [](uint16_t b) { uint32_t u = (uint32_t)b << 16; float f; memcpy(&f, &u, 4); return f; };
                 std::vector<uint16_t> pk((size_t)dirs * 8 * 2 * 4 * 128 * 64, 0);
                 for (int d = 0; d < dirs; ++d) {
                     const std::vector<float> &wh = w.host[d * 4 + 1];      // [4h][h]
@@ -248,8 +246,9 @@ static void finalize_weights(kb_model *m) {
                                 const int r2 = kp >> 5, s2 = kp & 31, u2 = r2 * U + s2;
                                 if (s2 >= U || u2 >= h) continue;
                                 const float x = wh[(size_t)(gate * h + u) * h + u2];
-                                const uint16_t b1 = f2bf(x);
-                                const uint16_t b2 = __half_as_ushort(__float2half_rn((x - bf2f(b1)) * ltc::W2_SCALE));
+                                const __half x1 = __float2half_rn(x);
+                                const uint16_t b1 = __half_as_ushort(x1);
+                                const uint16_t b2 = __half_as_ushort(__float2half_rn((x - __half2float(x1)) * ltc::X2_SCALE));
                                 const int ka = kp >> 6, kk = kp & 63, cch = kk >> 3, e = kk & 7;
                                 const size_t in_tile = (size_t)mrow * 64 + (size_t)((cch ^ (mrow & 7)) * 8) + e;
                                 pk[((((size_t)d * 8 + r) * 2 + 0) * 4 + ka) * (128 * 64) + in_tile] = b1;

@@ -7,20 +7,23 @@
 //   cluster of 8 CTAs = 16 sequences of one direction for all time steps; CTA r owns unit slots [32r, 32r+32) (padded, any
 //   hid <= 256), i.e. 128 gate rows ordered unit-major (row = 4*slot + gate: a unit's gates sit in 4 adjacent TMEM lanes).
 //
+//   Operand precision: fp16 pairs with a power-of-two scale on the second term give 22 significand bits,
+//       x = x1 + x2s * 2^-11,   x1 = fp16(x),   x2s = fp16((x - x1) * 2^11)        (|error| <= 2^-23 |x|)
+//   (a first attempt with bf16 x bf16 / fp16 x bf16 mixed-format MMAs faulted with "illegal instruction": A and B of one
+//   kind::f16 MMA must share a format.)
 //   A (resident in shared memory, UMMA K-major 128B-swizzle tiles, pre-swizzled on the host, 8 cp.async.bulk copies, 128 KB):
-//       W1 = bf16(W)                     and     W2s = fp16((W - W1) * 2^8)      (|W - W1 - W2s/2^8| <= 2^-20 |W|)
-//   B (double buffered, 2 x 24 KB): h_{t-1} as three bf16 planes stacked along N: rows [0,16) h1, [16,32) h2, [32,48) h3,
-//       written REMOTELY by every CTA of the cluster with st.async.v4 (16-byte chunks = 8 unit slots), byte-counted by
-//       the destination's mbarrier (no cluster barrier, no fence, no "buffer free" handshake thanks to the double buffer).
-//   D: per step 32 MMAs   W1 x [h1|h2|h3]  (kind::f16 bf16 x bf16, M128 x N48 x K16)   and
-//                         W2s x [h1|h2]    (kind::f16 fp16 x bf16, M128 x N32 x K16)
+//       W1 and W2s planes of the CTA's 128 gate rows x K = 256.
+//   B (double buffered, 2 x 16 KB): h_{t-1} planes stacked along N: rows [0,16) h1, [16,32) h2s, written REMOTELY by every
+//       CTA of the cluster with st.async.v4 (16-byte chunks = 8 unit slots), byte-counted by the destination's mbarrier
+//       (no cluster barrier, no fence, no "buffer free" handshake thanks to the double buffer).
+//   D: per step 32 MMAs   W1 x [h1|h2s]  (M128 x N32 x K16)   and   W2s x [h1]  (M128 x N16 x K16)
 //       into FOUR independent TMEM accumulator chains (k-atoms {0,1} / {2,3} x {W1, W2s}), issued round-robin: version 1
 //       issued 96 dependent N=16 MMAs on two accumulators and measured ~125 cycles per dependent MMA (accumulator
 //       latency), 12 k cycles per step, 1.63 ms on cfg2.  Every fp32 accumulator element sees only 8 accumulations.
-//       pre = D1[:, h1] + (D1[:, h2] + D1[:, h3] + 2^-8 (D2[:, h1] + D2[:, h2]))        (dropped: W2*h3 ~ 2^-25)
+//       pre = D1[:, h1] + 2^-11 (D1[:, h2s] + D2[:, h1])                               (dropped: W2*h2 ~ 2^-24)
 //   epilogue: 8 warps (TMEM lane quarter x line half): tcgen05.ld -> + gx -> sigmoid / tanh (accurate expf / tanhf) ->
 //       gates regrouped through shared memory -> fp32 cell update (2 cells per thread) -> h_t to HBM and, split into
-//       bf16 x 3, to every CTA's next B buffer.
+//       the two scaled fp16 planes, to every CTA's next B buffer.
 #pragma once
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
@@ -35,17 +38,17 @@ using namespace kb::tc;
 constexpr int NL = 16;                                   // lines per cluster
 constexpr int LCS = 8;                                   // cluster size
 constexpr int A_TILE_B = 128 * 128;                      // one (plane, k-atom) tile of A: 128 rows x 128 B
-constexpr int A_BYTES = 2 * 4 * A_TILE_B;                // 131072: W1 (bf16) and W2s (fp16)
-constexpr int B_ROWS = 3 * NL;                           // 48 rows: h1 | h2 | h3
-constexpr int B_TILE_B = B_ROWS * 128;                   // 6144 bytes per k-atom
-constexpr int B_BUF_B = 4 * B_TILE_B;                    // 24576 bytes per buffer
+constexpr int A_BYTES = 2 * 4 * A_TILE_B;                // 131072: W1 and W2s
+constexpr int B_ROWS = 2 * NL;                           // 32 rows: h1 | h2s
+constexpr int B_TILE_B = B_ROWS * 128;                   // 4096 bytes per k-atom
+constexpr int B_BUF_B = 4 * B_TILE_B;                    // 16384 bytes per buffer
 constexpr int SG_FLOATS = NL * 8 * 4;                    // per TMEM-lane quarter: [line][unit][gate]
 constexpr int SH_FLOATS = NL * 8;                        // per quarter: [line][unit]
 constexpr int STG_BYTES = 4 * (SG_FLOATS + SH_FLOATS) * 4;
 constexpr int LSMEM_BYTES = A_BYTES + 2 * B_BUF_B + STG_BYTES + 128 + 1024;
 constexpr int LTHREADS = 32 + 8 * 32;                    // warp 0: MMA issue / TMEM; warps 1..8: epilogue
-constexpr int TM_COLS = 256;                             // D1a @0 (48), D1b @48, D2a @96 (32), D2b @128
-constexpr float W2_SCALE = 256.f;
+constexpr int TM_COLS = 128;                             // D1a @0 (32), D1b @32, D2a @64 (16), D2b @80
+constexpr float X2_SCALE = 2048.f;                       // 2^11 on the second fp16 term of W and of h
 
 struct LstmTcParams {
     const float *gx; const uint16_t *wpk; float *out; const int *lens;
@@ -135,7 +138,7 @@ __global__ void __launch_bounds__(LTHREADS, 1) k_lstm_rec_tc(LstmTcParams p) {
 
     if (warp == 0) {
         // ===================== MMA issuer =====================
-        const uint32_t id1 = idesc_f16(1, 1, 128, 48), id2 = idesc_f16(0, 1, 128, 32);
+        const uint32_t id1 = idesc_f16(0, 0, 128, 32), id2 = idesc_f16(0, 0, 128, 16);
         mbar_wait(a_full, 0);
         for (int s = 0; s < maxlen; ++s) {
             const int cur = s & 1;
@@ -156,8 +159,8 @@ __global__ void __launch_bounds__(LTHREADS, 1) k_lstm_rec_tc(LstmTcParams p) {
                         const uint64_t a1 = umma_desc_sw128(a0 + (uint32_t)(ka * A_TILE_B)) + (uint64_t)(2 * k);
                         const uint64_t a2 = umma_desc_sw128(a0 + (uint32_t)((4 + ka) * A_TILE_B)) + (uint64_t)(2 * k);
                         const uint32_t first = ((ka & 1) == 0 && k == 0) ? 0u : 1u;
-                        umma_f16(tmem_base + (uint32_t)(half * 48), a1, bd, id1, first);
-                        umma_f16(tmem_base + (uint32_t)(96 + half * 32), a2, bd, id2, first);
+                        umma_f16(tmem_base + (uint32_t)(half * 32), a1, bd, id1, first);          // [W1 h1 | W1 h2s]
+                        umma_f16(tmem_base + (uint32_t)(64 + half * 16), a2, bd, id2, first);     // W2s h1 (first 16 rows of B)
                     }
                 }
                 umma_commit(mma_done);
@@ -218,21 +221,18 @@ __global__ void __launch_bounds__(LTHREADS, 1) k_lstm_rec_tc(LstmTcParams p) {
             }
             mbar_wait(mma_done, (uint32_t)(s & 1));
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            // column blocks: D1a/D1b = [h1 | h2 | h3] x 16 lines, D2a/D2b = [h1 | h2] x 16 lines (scaled by 2^8)
-            uint32_t r1a[8], r1b[8], ra[8], rb[8], rc[8], rd[8], re[8], rf[8], rg[8], rh[8];
-            tmem_ld8_nowait(lane_base + 0, r1a);   tmem_ld8_nowait(lane_base + 48, r1b);        // main: W1 h1
-            tmem_ld8_nowait(lane_base + 16, ra);   tmem_ld8_nowait(lane_base + 64, rb);         // W1 h2
-            tmem_ld8_nowait(lane_base + 32, rc);   tmem_ld8_nowait(lane_base + 80, rd);         // W1 h3
-            tmem_ld8_nowait(lane_base + 96, re);   tmem_ld8_nowait(lane_base + 128, rf);        // W2s h1
-            tmem_ld8_nowait(lane_base + 112, rg);  tmem_ld8_nowait(lane_base + 144, rh);        // W2s h2
+            // column blocks: D1a/D1b = [h1 | h2s] x 16 lines, D2a/D2b = [h1] x 16 lines; the correction terms carry a factor 2^11
+            uint32_t r1a[8], r1b[8], ra[8], rb[8], rc[8], rd[8];
+            tmem_ld8_nowait(lane_base + 0, r1a);   tmem_ld8_nowait(lane_base + 32, r1b);        // main: W1 h1
+            tmem_ld8_nowait(lane_base + 16, ra);   tmem_ld8_nowait(lane_base + 48, rb);         // W1 h2s
+            tmem_ld8_nowait(lane_base + 64, rc);   tmem_ld8_nowait(lane_base + 80, rd);         // W2s h1
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const float main_ = __uint_as_float(r1a[i]) + __uint_as_float(r1b[i]);
-                const float c1 = (__uint_as_float(ra[i]) + __uint_as_float(rb[i])) + (__uint_as_float(rc[i]) + __uint_as_float(rd[i]));
-                const float c2 = (__uint_as_float(re[i]) + __uint_as_float(rf[i])) + (__uint_as_float(rg[i]) + __uint_as_float(rh[i]));
-                const float pre = (main_ + (c1 + c2 * (1.f / W2_SCALE))) + gxv[i];
+                const float corr = (__uint_as_float(ra[i]) + __uint_as_float(rb[i])) + (__uint_as_float(rc[i]) + __uint_as_float(rd[i]));
+                const float pre = (main_ + corr * (1.f / X2_SCALE)) + gxv[i];
                 sg[((8 * lh + i) * 8 + jq) * 4 + g] = g == 2 ? tanhf(pre) : sigmoidf_acc(pre);
             }
             named_bar(1 + q, 64);
@@ -250,8 +250,8 @@ __global__ void __launch_bounds__(LTHREADS, 1) k_lstm_rec_tc(LstmTcParams p) {
                 sh[cl * 8 + cu0 + e] = h;
             }
             named_bar(1 + q, 64);
-            if (s + 1 < maxlen && tq < 48) {
-                // chunk = 8 unit slots of one line in one bf16 plane: row = plane*16 + line of the k-atom tile
+            if (s + 1 < maxlen && tq < 32) {
+                // chunk = 8 unit slots of one line in one fp16 plane: row = plane*16 + line of the k-atom tile
                 const int plane = tq >> 4, line = tq & 15;
                 const float4 x0 = *reinterpret_cast<const float4 *>(&sh[line * 8]), x1 = *reinterpret_cast<const float4 *>(&sh[line * 8 + 4]);
                 const float xs[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
@@ -262,11 +262,9 @@ __global__ void __launch_bounds__(LTHREADS, 1) k_lstm_rec_tc(LstmTcParams p) {
 #pragma unroll
                     for (int f = 0; f < 2; ++f) {
                         const float x = xs[2 * e + f];
-                        const __nv_bfloat16 b1 = __float2bfloat16_rn(x);
-                        const float r1 = x - __bfloat162float(b1);
-                        const __nv_bfloat16 b2 = __float2bfloat16_rn(r1);
-                        const __nv_bfloat16 b3 = __float2bfloat16_rn(r1 - __bfloat162float(b2));
-                        two[f] = (uint32_t)__bfloat16_as_ushort(plane == 0 ? b1 : plane == 1 ? b2 : b3);
+                        const __half h1 = __float2half_rn(x);
+                        const __half h2 = __float2half_rn((x - __half2float(h1)) * X2_SCALE);
+                        two[f] = (uint32_t)__half_as_ushort(plane == 0 ? h1 : h2);
                     }
                     pk[e] = two[0] | (two[1] << 16);
                 }
