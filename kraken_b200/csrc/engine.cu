@@ -439,6 +439,7 @@ struct Exec {
                     tat[0].id = cudaLaunchAttributeClusterDimension;
                     tat[0].val.clusterDim.x = ltc::LCS; tat[0].val.clusterDim.y = 1; tat[0].val.clusterDim.z = 1;
                     tcfg.attrs = tat; tcfg.numAttrs = 1;
+                    if (getenv("KB_DEBUG")) fprintf(stderr, "[kb] %s: tcgen05 recurrence, %u clusters of 8, T=%d\n", n.name.c_str(), tcfg.gridDim.x / 8 * dirs, lp.T);
                     CK(cudaLaunchKernelEx(&tcfg, ltc::k_lstm_rec_tc, tp));
                     ++m->launches;
                     CK(cudaPeekAtLastError());

@@ -142,7 +142,7 @@ __global__ void __launch_bounds__(LTHREADS, 1) k_lstm_rec_tc(LstmTcParams p) {
         mbar_wait(a_full, 0);
         for (int s = 0; s < maxlen; ++s) {
             const int cur = s & 1;
-            if (s > 0) mbar_wait_cluster(&b_full[cur], (uint32_t)(((s - 1) >> 1) & 1));
+            if (s > 0) mbar_wait(&b_full[cur], (uint32_t)(((s - 1) >> 1) & 1));   // default acquire.cta: an acquire.cluster wait costs a CCTL.IVALL per step
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // st.async writes -> UMMA (async proxy) reads
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             if (elect_one()) {
@@ -193,31 +193,33 @@ __global__ void __launch_bounds__(LTHREADS, 1) k_lstm_rec_tc(LstmTcParams p) {
                 if (cvalid && cuv[e]) for (int t = clen; t < p.T; ++t) p.out[(size_t)(cbase + (long long)t * p.step) * OC + dir * hid + cu[e]] = 0.f;
             }
         }
-        // gx addressing of this thread's TMEM row (gate g of unit u) for its 8 lines
-        int glen[8]; long long gbase[8];
+        // gx of this thread's TMEM row (gate g of unit u) for its 8 lines: running pointers, +-one time step per iteration
+        int glen[8]; const float *gptr[8];
+        const long long gstride = (long long)(dir ? -1 : 1) * p.step * GC;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             const int ql = chunk * NL + 8 * lh + i;
             const bool v = ql < p.nseq && uvalid;
             glen[i] = v ? min(max(p.lens ? p.lens[ql] : p.T, 0), p.T) : 0;
             const int qq = ql < p.nseq ? ql : 0;
-            gbase[i] = (long long)(qq / p.q2) * p.s_outer + (long long)(qq % p.q2) * p.s_inner;
+            const long long gb = (long long)(qq / p.q2) * p.s_outer + (long long)(qq % p.q2) * p.s_inner;
+            const int t0 = dir ? max(glen[i] - 1, 0) : 0;
+            gptr[i] = p.gx + (size_t)(gb + (long long)t0 * p.step) * GC + (size_t)dir * 4 * hid + (size_t)(uvalid ? u : 0) * 4 + g;
         }
         uint32_t rB[LCS], rFull[LCS];
 #pragma unroll
         for (int r = 0; r < LCS; ++r) { rB[r] = mapa32(smem_u32(sB), (uint32_t)r); rFull[r] = mapa32(smem_u32(b_full), (uint32_t)r); }
         const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(8 * lh);
+        // gate non-linearity without divergence: sigmoid(x) for i, f, o; tanh(x) = 2*sigmoid(2x) - 1 for the candidate gate
+        const float act_k = g == 2 ? 2.f : 1.f;
 
         for (int s = 0; s < maxlen; ++s) {
             const int nxt = (s + 1) & 1;
             float gxv[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-                gxv[i] = 0.f;
-                if (s < glen[i]) {
-                    const int t = dir ? glen[i] - 1 - s : s;
-                    gxv[i] = __ldg(p.gx + (size_t)(gbase[i] + (long long)t * p.step) * GC + (size_t)dir * 4 * hid + (size_t)u * 4 + g);
-                }
+                gxv[i] = s < glen[i] ? __ldg(gptr[i]) : 0.f;
+                gptr[i] += gstride;
             }
             mbar_wait(mma_done, (uint32_t)(s & 1));
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -233,7 +235,7 @@ __global__ void __launch_bounds__(LTHREADS, 1) k_lstm_rec_tc(LstmTcParams p) {
                 const float main_ = __uint_as_float(r1a[i]) + __uint_as_float(r1b[i]);
                 const float corr = (__uint_as_float(ra[i]) + __uint_as_float(rb[i])) + (__uint_as_float(rc[i]) + __uint_as_float(rd[i]));
                 const float pre = (main_ + corr * (1.f / X2_SCALE)) + gxv[i];
-                sg[((8 * lh + i) * 8 + jq) * 4 + g] = g == 2 ? tanhf(pre) : sigmoidf_acc(pre);
+                sg[((8 * lh + i) * 8 + jq) * 4 + g] = fmaf(sigmoidf_acc(pre * act_k), act_k, 1.f - act_k);
             }
             named_bar(1 + q, 64);
             const bool act = cvalid && s < clen;
