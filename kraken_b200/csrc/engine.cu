@@ -428,7 +428,7 @@ struct Exec {
                 if (rec_tc) {
                     ltc::LstmTcParams tp;
                     tp.gx = lp.gx; tp.wpk = (const uint16_t *)w.wpk; tp.out = lp.out; tp.lens = lp.lens; tp.nseq = lp.nseq; tp.T = lp.T;
-                    tp.hid = hid; tp.dirs = dirs; tp.U = lp.U; tp.q2 = lp.q2; tp.s_outer = lp.s_outer; tp.s_inner = lp.s_inner; tp.step = lp.step;
+                    tp.dbg = getenv("KB_LSTM_DBG") ? 1 : 0; tp.hid = hid; tp.dirs = dirs; tp.U = lp.U; tp.q2 = lp.q2; tp.s_outer = lp.s_outer; tp.s_inner = lp.s_inner; tp.step = lp.step;
                     static bool attr_set = false;
                     if (!attr_set) { CK(cudaFuncSetAttribute(ltc::k_lstm_rec_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, ltc::LSMEM_BYTES)); attr_set = true; }
                     cudaLaunchConfig_t tcfg = {};

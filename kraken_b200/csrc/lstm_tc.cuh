@@ -54,6 +54,7 @@ struct LstmTcParams {
     const float *gx; const uint16_t *wpk; float *out; const int *lens;
     int nseq, T, hid, dirs, U;
     int q2; long long s_outer, s_inner, step;
+    int dbg;
 };
 
 // kind::f16 instruction descriptor: fp32 accumulate, K-major operands; a_fmt/b_fmt: 0 = fp16, 1 = bf16
@@ -93,6 +94,9 @@ __device__ __forceinline__ void mbar_wait_cluster(uint64_t *bar, uint32_t parity
         "bra CW_%=;\n\t"
         "CD_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
+// gate non-linearities on the SFU: ex2.approx + rcp, absolute error ~1e-7 (the CUDA-core kernel keeps expf/tanhf)
+__device__ __forceinline__ float sigmoid_fast(float x) { return __frcp_rn(1.f + __expf(-x)); }
+__device__ __forceinline__ float tanh_fast(float x) { return fmaf(2.f, sigmoid_fast(2.f * x), -1.f); }
 __device__ __forceinline__ void named_bar(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 
 __global__ void __launch_bounds__(LTHREADS, 1) k_lstm_rec_tc(LstmTcParams p) {
@@ -145,6 +149,7 @@ __global__ void __launch_bounds__(LTHREADS, 1) k_lstm_rec_tc(LstmTcParams p) {
             if (s > 0) mbar_wait(&b_full[cur], (uint32_t)(((s - 1) >> 1) & 1));   // default acquire.cta: an acquire.cluster wait costs a CCTL.IVALL per step
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // st.async writes -> UMMA (async proxy) reads
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const long long dbg_c0 = p.dbg ? clock64() : 0;
             if (elect_one()) {
                 // this buffer is refilled during step s+1 (nobody can send that before receiving our h_s)
                 if (s + 2 < maxlen) mbar_expect_tx(&b_full[cur], B_BUF_B);
@@ -164,6 +169,8 @@ __global__ void __launch_bounds__(LTHREADS, 1) k_lstm_rec_tc(LstmTcParams p) {
                     }
                 }
                 umma_commit(mma_done);
+                if (p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && (s == 100 || s == 101))
+                    printf("[tcrec] s=%d MMA  bfull_ready=%lld issued=%lld (issue %lld)\n", s, dbg_c0, clock64(), clock64() - dbg_c0);
             }
             __syncwarp();
         }
@@ -221,8 +228,10 @@ __global__ void __launch_bounds__(LTHREADS, 1) k_lstm_rec_tc(LstmTcParams p) {
                 gxv[i] = s < glen[i] ? __ldg(gptr[i]) : 0.f;
                 gptr[i] += gstride;
             }
+            const long long e_pre = p.dbg ? clock64() : 0;
             mbar_wait(mma_done, (uint32_t)(s & 1));
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const long long e0 = p.dbg ? clock64() : 0;
             // column blocks: D1a/D1b = [h1 | h2s] x 16 lines, D2a/D2b = [h1] x 16 lines; the correction terms carry a factor 2^11
             uint32_t r1a[8], r1b[8], ra[8], rb[8], rc[8], rd[8];
             tmem_ld8_nowait(lane_base + 0, r1a);   tmem_ld8_nowait(lane_base + 32, r1b);        // main: W1 h1
@@ -235,9 +244,11 @@ __global__ void __launch_bounds__(LTHREADS, 1) k_lstm_rec_tc(LstmTcParams p) {
                 const float main_ = __uint_as_float(r1a[i]) + __uint_as_float(r1b[i]);
                 const float corr = (__uint_as_float(ra[i]) + __uint_as_float(rb[i])) + (__uint_as_float(rc[i]) + __uint_as_float(rd[i]));
                 const float pre = (main_ + corr * (1.f / X2_SCALE)) + gxv[i];
-                sg[((8 * lh + i) * 8 + jq) * 4 + g] = fmaf(sigmoidf_acc(pre * act_k), act_k, 1.f - act_k);
+                sg[((8 * lh + i) * 8 + jq) * 4 + g] = fmaf(sigmoid_fast(pre * act_k), act_k, 1.f - act_k);
             }
+            const long long e1 = p.dbg ? clock64() : 0;
             named_bar(1 + q, 64);
+            const long long e2 = p.dbg ? clock64() : 0;
             const bool act = cvalid && s < clen;
             const int t_out = dir ? clen - 1 - s : s;
 #pragma unroll
@@ -246,11 +257,12 @@ __global__ void __launch_bounds__(LTHREADS, 1) k_lstm_rec_tc(LstmTcParams p) {
                 float h = 0.f;                             // finished / padding cells feed zeros (never used again)
                 if (act && cuv[e]) {
                     cst[e] = gt.y * cst[e] + gt.x * gt.z;
-                    h = gt.w * tanhf(cst[e]);
+                    h = gt.w * tanh_fast(cst[e]);
                     p.out[(size_t)(cbase + (long long)t_out * p.step) * OC + dir * hid + cu[e]] = h;
                 }
                 sh[cl * 8 + cu0 + e] = h;
             }
+            const long long e3 = p.dbg ? clock64() : 0;
             named_bar(1 + q, 64);
             if (s + 1 < maxlen && tq < 32) {
                 // chunk = 8 unit slots of one line in one fp16 plane: row = plane*16 + line of the k-atom tile
@@ -276,6 +288,9 @@ __global__ void __launch_bounds__(LTHREADS, 1) k_lstm_rec_tc(LstmTcParams p) {
 #pragma unroll
                 for (int r = 0; r < LCS; ++r) st_async_v4(rB[r] + off, v, rFull[r] + (uint32_t)nxt * 8u);
             }
+            if (p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && warp == 1 && lane == 0 && (s == 100 || s == 101))
+                printf("[tcrec] s=%d EPI  loop_top=%lld mma_done=%lld act_done=%lld bar1=%lld cell_done=%lld sent=%lld | wait %lld tmem+act %lld bar %lld cell %lld bar+pack+send %lld\n",
+                       s, e_pre, e0, e1, e2, e3, clock64(), e0 - e_pre, e1 - e0, e2 - e1, e3 - e2, clock64() - e3);
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
