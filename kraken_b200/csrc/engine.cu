@@ -232,10 +232,10 @@ static void finalize_weights(kb_model *m) {
             }
             if (h > 128 && h <= 256) {
                 // tcgen05 recurrence operand (lstm_tc.cuh): per (dir, cluster rank) 128 gate rows (row = 4*slot + gate, 32 unit slots per
-                // CTA) x K = 256 (k = 32*rank' + slot'); plane 0 = fp16(W), plane 1 = fp16((W - plane0) * 2^11); 64-wide k-atoms with the
-                // 128B swizzle applied here so that plain bulk copies land in UMMA layout
+                // CTA) x K = 256 (k = 32*rank' + slot'); plane 0 = fp16(W), plane 1 = fp16((W - plane0) * 2^11); plain
+                // row-major: every thread of the kernel copies its own gate row into tensor memory
                 const int U = (h + 7) / 8;
-                std::vector<uint16_t> pk((size_t)dirs * 8 * 2 * 4 * 128 * 64, 0);
+                std::vector<uint16_t> pk((size_t)dirs * 8 * 2 * 128 * 256, 0);      // [dir][rank][plane][gate row][k] fp16, plain row-major
                 for (int d = 0; d < dirs; ++d) {
                     const std::vector<float> &wh = w.host[d * 4 + 1];      // [4h][h]
                     for (int r = 0; r < 8; ++r)
@@ -247,12 +247,9 @@ static void finalize_weights(kb_model *m) {
                                 if (s2 >= U || u2 >= h) continue;
                                 const float x = wh[(size_t)(gate * h + u) * h + u2];
                                 const __half x1 = __float2half_rn(x);
-                                const uint16_t b1 = __half_as_ushort(x1);
-                                const uint16_t b2 = __half_as_ushort(__float2half_rn((x - __half2float(x1)) * ltc::X2_SCALE));
-                                const int ka = kp >> 6, kk = kp & 63, cch = kk >> 3, e = kk & 7;
-                                const size_t in_tile = (size_t)mrow * 64 + (size_t)((cch ^ (mrow & 7)) * 8) + e;
-                                pk[((((size_t)d * 8 + r) * 2 + 0) * 4 + ka) * (128 * 64) + in_tile] = b1;
-                                pk[((((size_t)d * 8 + r) * 2 + 1) * 4 + ka) * (128 * 64) + in_tile] = b2;
+                                const size_t o = ((((size_t)d * 8 + r) * 2) * 128 + mrow) * 256 + kp;
+                                pk[o] = __half_as_ushort(x1);
+                                pk[o + (size_t)128 * 256] = __half_as_ushort(__float2half_rn((x - __half2float(x1)) * ltc::X2_SCALE));
                             }
                         }
                 }

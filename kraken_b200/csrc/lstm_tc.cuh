@@ -11,8 +11,9 @@
 //       x = x1 + x2s * 2^-11,   x1 = fp16(x),   x2s = fp16((x - x1) * 2^11)        (|error| <= 2^-23 |x|)
 //   (a first attempt with bf16 x bf16 / fp16 x bf16 mixed-format MMAs faulted with "illegal instruction": A and B of one
 //   kind::f16 MMA must share a format.)
-//   A (resident in shared memory, UMMA K-major 128B-swizzle tiles, pre-swizzled on the host, 8 cp.async.bulk copies, 128 KB):
-//       W1 and W2s planes of the CTA's 128 gate rows x K = 256.
+//   A = W1 and W2s planes of the CTA's 128 gate rows x K = 256, resident in TENSOR MEMORY for the whole kernel (row = TMEM lane,
+//       two fp16 per 32-bit column, 2 x 128 columns; written once with tcgen05.st).  Version 2 kept A in shared memory: every
+//       MMA re-read its 4 KB slice, 128 KB per step = 1024 cycles at 128 B/clk, measured 1158 cycles to issue the 32 MMAs.
 //   B (double buffered, 2 x 16 KB): h_{t-1} planes stacked along N: rows [0,16) h1, [16,32) h2s, written REMOTELY by every
 //       CTA of the cluster with st.async.v4 (16-byte chunks = 8 unit slots), byte-counted by the destination's mbarrier
 //       (no cluster barrier, no fence, no "buffer free" handshake thanks to the double buffer).
@@ -21,7 +22,8 @@
 //       issued 96 dependent N=16 MMAs on two accumulators and measured ~125 cycles per dependent MMA (accumulator
 //       latency), 12 k cycles per step, 1.63 ms on cfg2.  Every fp32 accumulator element sees only 8 accumulations.
 //       pre = D1[:, h1] + 2^-11 (D1[:, h2s] + D2[:, h1])                               (dropped: W2*h2 ~ 2^-24)
-//   epilogue: 8 warps (TMEM lane quarter x line half): tcgen05.ld -> + gx -> sigmoid / tanh (accurate expf / tanhf) ->
+//   epilogue: 4 warps (one per TMEM lane quarter; v2 measured ~1300 cycles for 48 small tcgen05.ld.x8 per step, so now three
+//       x32 loads per thread): tcgen05.ld -> + gx -> sigmoid / tanh (accurate expf / tanhf) ->
 //       gates regrouped through shared memory -> fp32 cell update (2 cells per thread) -> h_t to HBM and, split into
 //       the two scaled fp16 planes, to every CTA's next B buffer.
 #pragma once
@@ -37,17 +39,17 @@ using namespace kb::tc;
 
 constexpr int NL = 16;                                   // lines per cluster
 constexpr int LCS = 8;                                   // cluster size
-constexpr int A_TILE_B = 128 * 128;                      // one (plane, k-atom) tile of A: 128 rows x 128 B
-constexpr int A_BYTES = 2 * 4 * A_TILE_B;                // 131072: W1 and W2s
+constexpr int A_PLANE_ELEMS = 128 * 256;                 // fp16 elements of one W plane of a CTA: [128 gate rows][K = 256], row-major
 constexpr int B_ROWS = 2 * NL;                           // 32 rows: h1 | h2s
 constexpr int B_TILE_B = B_ROWS * 128;                   // 4096 bytes per k-atom
 constexpr int B_BUF_B = 4 * B_TILE_B;                    // 16384 bytes per buffer
-constexpr int SG_FLOATS = NL * 8 * 4;                    // per TMEM-lane quarter: [line][unit][gate]
-constexpr int SH_FLOATS = NL * 8;                        // per quarter: [line][unit]
+constexpr int SG_FLOATS = NL * 8 * 4;                    // per warp (TMEM lane quarter): [line][unit][gate]
+constexpr int SH_FLOATS = NL * 8;                        // per warp: [line][unit]
 constexpr int STG_BYTES = 4 * (SG_FLOATS + SH_FLOATS) * 4;
-constexpr int LSMEM_BYTES = A_BYTES + 2 * B_BUF_B + STG_BYTES + 128 + 1024;
-constexpr int LTHREADS = 32 + 8 * 32;                    // warp 0: MMA issue / TMEM; warps 1..8: epilogue
-constexpr int TM_COLS = 128;                             // D1a @0 (32), D1b @32, D2a @64 (16), D2b @80
+constexpr int LSMEM_BYTES = 2 * B_BUF_B + STG_BYTES + 128 + 1024;
+constexpr int LTHREADS = 32 + 4 * 32;                    // warp 0: MMA issue / TMEM alloc; warps 1..4: epilogue (one per TMEM lane quarter)
+constexpr int TM_COLS = 512;                             // D: D1a @0 (32), D1b @32, D2a @64 (16), D2b @80;  A: W1 @128 (128), W2s @256 (128)
+constexpr int TM_A0 = 128;
 constexpr float X2_SCALE = 2048.f;                       // 2^11 on the second fp16 term of W and of h
 
 struct LstmTcParams {
@@ -67,6 +69,32 @@ __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64
         "setp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t *r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+          "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+          "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t *r) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};"
+        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+          "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]),
+          "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]),
+          "r"(r[30]), "r"(r[31]) : "memory");
 }
 __device__ __forceinline__ void tmem_ld8_nowait(uint32_t taddr, uint32_t *r) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
@@ -102,10 +130,10 @@ __device__ __forceinline__ void named_bar(int id, int nthreads) { asm volatile("
 __global__ void __launch_bounds__(LTHREADS, 1) k_lstm_rec_tc(LstmTcParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t *sA = smem, *sB = smem + A_BYTES;
+    uint8_t *sB = smem;
     float *stg = reinterpret_cast<float *>(sB + 2 * B_BUF_B);
     uint64_t *bars = reinterpret_cast<uint64_t *>(sB + 2 * B_BUF_B + STG_BYTES);
-    uint64_t *a_full = bars, *b_full = bars + 1 /* [2] */, *mma_done = bars + 3;
+    uint64_t *b_full = bars + 1 /* [2] */, *mma_done = bars + 3;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 4);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -115,11 +143,8 @@ __global__ void __launch_bounds__(LTHREADS, 1) k_lstm_rec_tc(LstmTcParams p) {
     const int hid = p.hid, GC = p.dirs * 4 * hid, OC = p.dirs * hid;
 
     if (threadIdx.x == 0) {
-        mbar_init(a_full, 1); mbar_init(&b_full[0], 1); mbar_init(&b_full[1], 1); mbar_init(mma_done, 1);
+        mbar_init(&b_full[0], 1); mbar_init(&b_full[1], 1); mbar_init(mma_done, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        mbar_expect_tx(a_full, A_BYTES);
-        const uint8_t *src = reinterpret_cast<const uint8_t *>(p.wpk) + ((size_t)dir * LCS + rank) * A_BYTES;
-        for (int i = 0; i < 8; ++i) bulk_g2s(sA + i * A_TILE_B, src + (size_t)i * A_TILE_B, A_TILE_B, a_full);
         mbar_expect_tx(&b_full[1], B_BUF_B);             // buffer 1 receives h_0 at the end of step 0
     }
     for (int i = threadIdx.x; i < 2 * B_BUF_B / 16; i += LTHREADS) reinterpret_cast<uint4 *>(sB)[i] = make_uint4(0, 0, 0, 0);   // h_{-1} = 0
@@ -132,6 +157,27 @@ __global__ void __launch_bounds__(LTHREADS, 1) k_lstm_rec_tc(LstmTcParams p) {
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
+    if (warp >= 1) {
+        // W_hh planes -> tensor memory: this thread's gate row (TMEM lane 32q + lane), K pairs packed low|high per column
+        const int m = 32 * (warp & 3) + lane;
+        const uint32_t *src = reinterpret_cast<const uint32_t *>(p.wpk) + (((size_t)dir * LCS + rank) * 2 * A_PLANE_ELEMS) / 2 + (size_t)m * 128;
+#pragma unroll 1
+        for (int pl = 0; pl < 2; ++pl)
+#pragma unroll 1
+            for (int c0 = 0; c0 < 128; c0 += 32) {
+                uint32_t r[32];
+#pragma unroll
+                for (int i = 0; i < 32; i += 4) {
+                    const uint4 v = __ldg(reinterpret_cast<const uint4 *>(src + (size_t)pl * (A_PLANE_ELEMS / 2) + c0 + i));
+                    r[i] = v.x; r[i + 1] = v.y; r[i + 2] = v.z; r[i + 3] = v.w;
+                }
+                tmem_st32(tmem_base + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)(TM_A0 + pl * 128 + c0), r);
+            }
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 
     int maxlen = 0;                                       // uniform across the cluster
@@ -143,7 +189,6 @@ __global__ void __launch_bounds__(LTHREADS, 1) k_lstm_rec_tc(LstmTcParams p) {
     if (warp == 0) {
         // ===================== MMA issuer =====================
         const uint32_t id1 = idesc_f16(0, 0, 128, 32), id2 = idesc_f16(0, 0, 128, 16);
-        mbar_wait(a_full, 0);
         for (int s = 0; s < maxlen; ++s) {
             const int cur = s & 1;
             if (s > 0) mbar_wait(&b_full[cur], (uint32_t)(((s - 1) >> 1) & 1));   // default acquire.cta: an acquire.cluster wait costs a CCTL.IVALL per step
@@ -153,7 +198,7 @@ __global__ void __launch_bounds__(LTHREADS, 1) k_lstm_rec_tc(LstmTcParams p) {
             if (elect_one()) {
                 // this buffer is refilled during step s+1 (nobody can send that before receiving our h_s)
                 if (s + 2 < maxlen) mbar_expect_tx(&b_full[cur], B_BUF_B);
-                const uint32_t a0 = smem_u32(sA), b0 = smem_u32(sB + cur * B_BUF_B);
+                const uint32_t b0 = smem_u32(sB + cur * B_BUF_B);
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
 #pragma unroll
@@ -161,11 +206,11 @@ __global__ void __launch_bounds__(LTHREADS, 1) k_lstm_rec_tc(LstmTcParams p) {
                         const int ka = kk == 0 ? 0 : kk == 1 ? 2 : kk == 2 ? 1 : 3;      // 0,2,1,3: same-chain MMAs 4 issues apart
                         const int half = ka >> 1;
                         const uint64_t bd = umma_desc_sw128(b0 + (uint32_t)(ka * B_TILE_B)) + (uint64_t)(2 * k);
-                        const uint64_t a1 = umma_desc_sw128(a0 + (uint32_t)(ka * A_TILE_B)) + (uint64_t)(2 * k);
-                        const uint64_t a2 = umma_desc_sw128(a0 + (uint32_t)((4 + ka) * A_TILE_B)) + (uint64_t)(2 * k);
+                        const uint32_t a1 = tmem_base + (uint32_t)(TM_A0 + ka * 32 + k * 8);      // K = 16 -> 8 columns of fp16 pairs
+                        const uint32_t a2 = a1 + 128u;
                         const uint32_t first = ((ka & 1) == 0 && k == 0) ? 0u : 1u;
-                        umma_f16(tmem_base + (uint32_t)(half * 32), a1, bd, id1, first);          // [W1 h1 | W1 h2s]
-                        umma_f16(tmem_base + (uint32_t)(64 + half * 16), a2, bd, id2, first);     // W2s h1 (first 16 rows of B)
+                        umma_f16_ts(tmem_base + (uint32_t)(half * 32), a1, bd, id1, first);          // [W1 h1 | W1 h2s]
+                        umma_f16_ts(tmem_base + (uint32_t)(64 + half * 16), a2, bd, id2, first);     // W2s h1 (first 16 rows of B)
                     }
                 }
                 umma_commit(mma_done);
@@ -175,37 +220,31 @@ __global__ void __launch_bounds__(LTHREADS, 1) k_lstm_rec_tc(LstmTcParams p) {
             __syncwarp();
         }
     } else {
-        // ===================== epilogue warps 1..8 =====================
-        const int q = warp & 3;                            // TMEM lane quarter: unit slots 8q .. 8q+7
-        const int lh = (warp - 1) >> 2;                    // line half: lines 8*lh .. 8*lh+7 of this thread's TMEM row
-        const int jq = lane >> 2, g = lane & 3;            // unit slot within the quarter, gate of this TMEM row
+        // ===================== epilogue warps 1..4 (one per TMEM lane quarter) =====================
+        const int q = warp & 3;                            // unit slots 8q .. 8q+7
+        const int jq = lane >> 2, g = lane & 3;            // unit slot within the quarter, gate of this thread's TMEM row
         const int slot = 8 * q + jq, u = (int)rank * p.U + slot;
         const bool uvalid = slot < p.U && u < hid;
         float *sg = stg + q * (SG_FLOATS + SH_FLOATS), *sh = sg + SG_FLOATS;
-        const int tq = lh * 32 + lane;                     // thread index within the quarter's 64 threads
-        // cells of this thread: line cl = tq / 4, unit slots cu0 = 2*(tq % 4), cu0 + 1
-        const int cl = tq >> 2, cu0 = (tq & 3) * 2;
-        int clen; long long cbase; bool cvalid; float cst[2] = {0.f, 0.f}; int cu[2]; bool cuv[2];
-        {
-            const int ql = chunk * NL + cl;
-            cvalid = ql < p.nseq;
-            const int l = cvalid ? (p.lens ? p.lens[ql] : p.T) : 0;
-            clen = min(max(l, 0), p.T);
-            const int qq = cvalid ? ql : 0;
-            cbase = (long long)(qq / p.q2) * p.s_outer + (long long)(qq % p.q2) * p.s_inner;
+        // cells of this thread: unit slot jq, lines 4b + g (b = 0..3)
+        int len4[4]; long long base4[4]; bool lv[4]; float cst[4];
 #pragma unroll
-            for (int e = 0; e < 2; ++e) {
-                const int sl = 8 * q + cu0 + e;
-                cu[e] = (int)rank * p.U + sl; cuv[e] = sl < p.U && cu[e] < hid;
-                if (cvalid && cuv[e]) for (int t = clen; t < p.T; ++t) p.out[(size_t)(cbase + (long long)t * p.step) * OC + dir * hid + cu[e]] = 0.f;
-            }
+        for (int b4 = 0; b4 < 4; ++b4) {
+            const int ql = chunk * NL + 4 * b4 + g;
+            lv[b4] = ql < p.nseq && uvalid;
+            const int l = ql < p.nseq ? (p.lens ? p.lens[ql] : p.T) : 0;
+            len4[b4] = min(max(l, 0), p.T);
+            const int qq = ql < p.nseq ? ql : 0;
+            base4[b4] = (long long)(qq / p.q2) * p.s_outer + (long long)(qq % p.q2) * p.s_inner;
+            cst[b4] = 0.f;
+            if (lv[b4]) for (int tt = len4[b4]; tt < p.T; ++tt) p.out[(size_t)(base4[b4] + (long long)tt * p.step) * OC + dir * hid + u] = 0.f;
         }
-        // gx of this thread's TMEM row (gate g of unit u) for its 8 lines: running pointers, +-one time step per iteration
-        int glen[8]; const float *gptr[8];
+        // gx of this thread's TMEM row (gate g of unit u), all 16 lines: running pointers, +-one time step per iteration
+        int glen[NL]; const float *gptr[NL];
         const long long gstride = (long long)(dir ? -1 : 1) * p.step * GC;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const int ql = chunk * NL + 8 * lh + i;
+        for (int i = 0; i < NL; ++i) {
+            const int ql = chunk * NL + i;
             const bool v = ql < p.nseq && uvalid;
             glen[i] = v ? min(max(p.lens ? p.lens[ql] : p.T, 0), p.T) : 0;
             const int qq = ql < p.nseq ? ql : 0;
@@ -216,15 +255,15 @@ __global__ void __launch_bounds__(LTHREADS, 1) k_lstm_rec_tc(LstmTcParams p) {
         uint32_t rB[LCS], rFull[LCS];
 #pragma unroll
         for (int r = 0; r < LCS; ++r) { rB[r] = mapa32(smem_u32(sB), (uint32_t)r); rFull[r] = mapa32(smem_u32(b_full), (uint32_t)r); }
-        const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(8 * lh);
+        const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
         // gate non-linearity without divergence: sigmoid(x) for i, f, o; tanh(x) = 2*sigmoid(2x) - 1 for the candidate gate
         const float act_k = g == 2 ? 2.f : 1.f;
 
         for (int s = 0; s < maxlen; ++s) {
             const int nxt = (s + 1) & 1;
-            float gxv[8];
+            float gxv[NL];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
+            for (int i = 0; i < NL; ++i) {
                 gxv[i] = s < glen[i] ? __ldg(gptr[i]) : 0.f;
                 gptr[i] += gstride;
             }
@@ -232,41 +271,39 @@ __global__ void __launch_bounds__(LTHREADS, 1) k_lstm_rec_tc(LstmTcParams p) {
             mbar_wait(mma_done, (uint32_t)(s & 1));
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const long long e0 = p.dbg ? clock64() : 0;
-            // column blocks: D1a/D1b = [h1 | h2s] x 16 lines, D2a/D2b = [h1] x 16 lines; the correction terms carry a factor 2^11
-            uint32_t r1a[8], r1b[8], ra[8], rb[8], rc[8], rd[8];
-            tmem_ld8_nowait(lane_base + 0, r1a);   tmem_ld8_nowait(lane_base + 32, r1b);        // main: W1 h1
-            tmem_ld8_nowait(lane_base + 16, ra);   tmem_ld8_nowait(lane_base + 48, rb);         // W1 h2s
-            tmem_ld8_nowait(lane_base + 64, rc);   tmem_ld8_nowait(lane_base + 80, rd);         // W2s h1
+            // D1a = cols 0..31 [W1 h1 | W1 h2s], D1b = 32..63 (k-atoms 2,3), D2a | D2b = 64..95 [W2s h1 | W2s h1]
+            uint32_t ra[32], rb[32], rc[32];
+            tmem_ld32_nowait(lane_base + 0, ra); tmem_ld32_nowait(lane_base + 32, rb); tmem_ld32_nowait(lane_base + 64, rc);
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const float main_ = __uint_as_float(r1a[i]) + __uint_as_float(r1b[i]);
-                const float corr = (__uint_as_float(ra[i]) + __uint_as_float(rb[i])) + (__uint_as_float(rc[i]) + __uint_as_float(rd[i]));
+            for (int i = 0; i < NL; ++i) {
+                const float main_ = __uint_as_float(ra[i]) + __uint_as_float(rb[i]);
+                const float corr = (__uint_as_float(ra[16 + i]) + __uint_as_float(rb[16 + i])) + (__uint_as_float(rc[i]) + __uint_as_float(rc[16 + i]));
                 const float pre = (main_ + corr * (1.f / X2_SCALE)) + gxv[i];
-                sg[((8 * lh + i) * 8 + jq) * 4 + g] = fmaf(sigmoid_fast(pre * act_k), act_k, 1.f - act_k);
+                sg[(i * 8 + jq) * 4 + g] = fmaf(sigmoid_fast(pre * act_k), act_k, 1.f - act_k);
             }
             const long long e1 = p.dbg ? clock64() : 0;
-            named_bar(1 + q, 64);
+            __syncwarp();
             const long long e2 = p.dbg ? clock64() : 0;
-            const bool act = cvalid && s < clen;
-            const int t_out = dir ? clen - 1 - s : s;
 #pragma unroll
-            for (int e = 0; e < 2; ++e) {
-                const float4 gt = *reinterpret_cast<const float4 *>(&sg[(cl * 8 + cu0 + e) * 4]);      // i, f, g, o
+            for (int b4 = 0; b4 < 4; ++b4) {
+                const int line = 4 * b4 + g;
+                const float4 gt = *reinterpret_cast<const float4 *>(&sg[(line * 8 + jq) * 4]);      // i, f, g, o
                 float h = 0.f;                             // finished / padding cells feed zeros (never used again)
-                if (act && cuv[e]) {
-                    cst[e] = gt.y * cst[e] + gt.x * gt.z;
-                    h = gt.w * tanh_fast(cst[e]);
-                    p.out[(size_t)(cbase + (long long)t_out * p.step) * OC + dir * hid + cu[e]] = h;
+                if (lv[b4] && s < len4[b4]) {
+                    cst[b4] = gt.y * cst[b4] + gt.x * gt.z;
+                    h = gt.w * tanh_fast(cst[b4]);
+                    const int t_out = dir ? len4[b4] - 1 - s : s;
+                    p.out[(size_t)(base4[b4] + (long long)t_out * p.step) * OC + dir * hid + u] = h;
                 }
-                sh[cl * 8 + cu0 + e] = h;
+                sh[line * 8 + jq] = h;
             }
             const long long e3 = p.dbg ? clock64() : 0;
-            named_bar(1 + q, 64);
-            if (s + 1 < maxlen && tq < 32) {
+            __syncwarp();
+            if (s + 1 < maxlen) {
                 // chunk = 8 unit slots of one line in one fp16 plane: row = plane*16 + line of the k-atom tile
-                const int plane = tq >> 4, line = tq & 15;
+                const int plane = lane >> 4, line = lane & 15;
                 const float4 x0 = *reinterpret_cast<const float4 *>(&sh[line * 8]), x1 = *reinterpret_cast<const float4 *>(&sh[line * 8 + 4]);
                 const float xs[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
                 uint32_t pk[4];
@@ -288,9 +325,10 @@ __global__ void __launch_bounds__(LTHREADS, 1) k_lstm_rec_tc(LstmTcParams p) {
 #pragma unroll
                 for (int r = 0; r < LCS; ++r) st_async_v4(rB[r] + off, v, rFull[r] + (uint32_t)nxt * 8u);
             }
+            __syncwarp();
             if (p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && warp == 1 && lane == 0 && (s == 100 || s == 101))
-                printf("[tcrec] s=%d EPI  loop_top=%lld mma_done=%lld act_done=%lld bar1=%lld cell_done=%lld sent=%lld | wait %lld tmem+act %lld bar %lld cell %lld bar+pack+send %lld\n",
-                       s, e_pre, e0, e1, e2, e3, clock64(), e0 - e_pre, e1 - e0, e2 - e1, e3 - e2, clock64() - e3);
+                printf("[tcrec] s=%d EPI  loop_top=%lld mma_done=%lld | wait %lld tmem+act %lld sync %lld cell %lld pack+send %lld\n",
+                       s, e_pre, e0, e0 - e_pre, e1 - e0, e2 - e1, e3 - e2, clock64() - e3);
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
