@@ -22,8 +22,8 @@
 //       issued 96 dependent N=16 MMAs on two accumulators and measured ~125 cycles per dependent MMA (accumulator
 //       latency), 12 k cycles per step, 1.63 ms on cfg2.  Every fp32 accumulator element sees only 8 accumulations.
 //       pre = D1[:, h1] + 2^-11 (D1[:, h2s] + D2[:, h1])                               (dropped: W2*h2 ~ 2^-24)
-//   epilogue: 4 warps (one per TMEM lane quarter; v2 measured ~1300 cycles for 48 small tcgen05.ld.x8 per step, so now three
-//       x32 loads per thread): tcgen05.ld -> + gx -> sigmoid / tanh (accurate expf / tanhf) ->
+//   epilogue: 16 warps (4 per TMEM lane quarter, 4 lines each; with 4 or 8 epilogue warps the phase was latency bound at 1-2
+//       warps per scheduler): tcgen05.ld -> + gx -> sigmoid / tanh (accurate expf / tanhf) ->
 //       gates regrouped through shared memory -> fp32 cell update (2 cells per thread) -> h_t to HBM and, split into
 //       the two scaled fp16 planes, to every CTA's next B buffer.
 #pragma once
@@ -47,7 +47,9 @@ constexpr int SG_FLOATS = NL * 8 * 4;                    // per warp (TMEM lane 
 constexpr int SH_FLOATS = NL * 8;                        // per warp: [line][unit]
 constexpr int STG_BYTES = 4 * (SG_FLOATS + SH_FLOATS) * 4;
 constexpr int LSMEM_BYTES = 2 * B_BUF_B + STG_BYTES + 128 + 1024;
-constexpr int LTHREADS = 32 + 4 * 32;                    // warp 0: MMA issue / TMEM alloc; warps 1..4: epilogue (one per TMEM lane quarter)
+constexpr int EW = 4;                                    // epilogue warps per TMEM lane quarter (latency hiding: v3 with 1 was 2x slower)
+constexpr int LPW = NL / EW;                             // lines per epilogue warp in the activation phase
+constexpr int LTHREADS = 32 + 4 * EW * 32;               // warp 0: MMA issue / TMEM alloc; warps 1..16: epilogue
 constexpr int TM_COLS = 512;                             // D: D1a @0 (32), D1b @32, D2a @64 (16), D2b @80;  A: W1 @128 (128), W2s @256 (128)
 constexpr int TM_A0 = 128;
 constexpr float X2_SCALE = 2048.f;                       // 2^11 on the second fp16 term of W and of h
@@ -95,6 +97,9 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t *r) {
           "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]),
           "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]),
           "r"(r[30]), "r"(r[31]) : "memory");
+}
+__device__ __forceinline__ void tmem_ld4_nowait(uint32_t taddr, uint32_t *r) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(taddr));
 }
 __device__ __forceinline__ void tmem_ld8_nowait(uint32_t taddr, uint32_t *r) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
@@ -157,7 +162,7 @@ __global__ void __launch_bounds__(LTHREADS, 1) k_lstm_rec_tc(LstmTcParams p) {
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
-    if (warp >= 1) {
+    if (warp >= 1 && warp <= 4) {
         // W_hh planes -> tensor memory: this thread's gate row (TMEM lane 32q + lane), K pairs packed low|high per column
         const int m = 32 * (warp & 3) + lane;
         const uint32_t *src = reinterpret_cast<const uint32_t *>(p.wpk) + (((size_t)dir * LCS + rank) * 2 * A_PLANE_ELEMS) / 2 + (size_t)m * 128;
@@ -220,31 +225,32 @@ __global__ void __launch_bounds__(LTHREADS, 1) k_lstm_rec_tc(LstmTcParams p) {
             __syncwarp();
         }
     } else {
-        // ===================== epilogue warps 1..4 (one per TMEM lane quarter) =====================
-        const int q = warp & 3;                            // unit slots 8q .. 8q+7
+        // ===================== epilogue warps 1..16: quarter q = warp & 3, sub-warp sw = (warp-1) >> 2 =====================
+        const int q = warp & 3;                            // TMEM lane quarter: unit slots 8q .. 8q+7
+        const int sw = (warp - 1) >> 2;                    // activation phase: lines LPW*sw .. LPW*sw + LPW-1 of this thread's TMEM row
         const int jq = lane >> 2, g = lane & 3;            // unit slot within the quarter, gate of this thread's TMEM row
         const int slot = 8 * q + jq, u = (int)rank * p.U + slot;
         const bool uvalid = slot < p.U && u < hid;
         float *sg = stg + q * (SG_FLOATS + SH_FLOATS), *sh = sg + SG_FLOATS;
-        // cells of this thread: unit slot jq, lines 4b + g (b = 0..3)
-        int len4[4]; long long base4[4]; bool lv[4]; float cst[4];
-#pragma unroll
-        for (int b4 = 0; b4 < 4; ++b4) {
-            const int ql = chunk * NL + 4 * b4 + g;
-            lv[b4] = ql < p.nseq && uvalid;
-            const int l = ql < p.nseq ? (p.lens ? p.lens[ql] : p.T) : 0;
-            len4[b4] = min(max(l, 0), p.T);
-            const int qq = ql < p.nseq ? ql : 0;
-            base4[b4] = (long long)(qq / p.q2) * p.s_outer + (long long)(qq % p.q2) * p.s_inner;
-            cst[b4] = 0.f;
-            if (lv[b4]) for (int tt = len4[b4]; tt < p.T; ++tt) p.out[(size_t)(base4[b4] + (long long)tt * p.step) * OC + dir * hid + u] = 0.f;
-        }
-        // gx of this thread's TMEM row (gate g of unit u), all 16 lines: running pointers, +-one time step per iteration
-        int glen[NL]; const float *gptr[NL];
+        const int tq = sw * 32 + lane;                     // thread index within the quarter's 128 threads
+        // the one cell this thread updates: line cl, unit slot cj of the quarter
+        const int cl = tq >> 3, cj = tq & 7;
+        const int cu = (int)rank * p.U + 8 * q + cj;
+        const int cql = chunk * NL + cl;
+        const bool cv = cql < p.nseq && (8 * q + cj) < p.U && cu < hid;
+        const int clen = cql < p.nseq ? min(max(p.lens ? p.lens[cql] : p.T, 0), p.T) : 0;
+        const int cqq = cql < p.nseq ? cql : 0;
+        const long long cbase = (long long)(cqq / p.q2) * p.s_outer + (long long)(cqq % p.q2) * p.s_inner;
+        float cst = 0.f;
+        if (cv) for (int tt = clen; tt < p.T; ++tt) p.out[(size_t)(cbase + (long long)tt * p.step) * OC + dir * hid + cu] = 0.f;
+        float *optr = p.out + (size_t)(cbase + (long long)(dir ? max(clen - 1, 0) : 0) * p.step) * OC + dir * hid + cu;
+        const long long ostride = (long long)(dir ? -1 : 1) * p.step * OC;
+        // gx of this thread's TMEM row (gate g of unit u) for its LPW lines: running pointers, +-one time step per iteration
+        int glen[LPW]; const float *gptr[LPW];
         const long long gstride = (long long)(dir ? -1 : 1) * p.step * GC;
 #pragma unroll
-        for (int i = 0; i < NL; ++i) {
-            const int ql = chunk * NL + i;
+        for (int i = 0; i < LPW; ++i) {
+            const int ql = chunk * NL + LPW * sw + i;
             const bool v = ql < p.nseq && uvalid;
             glen[i] = v ? min(max(p.lens ? p.lens[ql] : p.T, 0), p.T) : 0;
             const int qq = ql < p.nseq ? ql : 0;
@@ -255,15 +261,15 @@ __global__ void __launch_bounds__(LTHREADS, 1) k_lstm_rec_tc(LstmTcParams p) {
         uint32_t rB[LCS], rFull[LCS];
 #pragma unroll
         for (int r = 0; r < LCS; ++r) { rB[r] = mapa32(smem_u32(sB), (uint32_t)r); rFull[r] = mapa32(smem_u32(b_full), (uint32_t)r); }
-        const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
+        const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(LPW * sw);
         // gate non-linearity without divergence: sigmoid(x) for i, f, o; tanh(x) = 2*sigmoid(2x) - 1 for the candidate gate
         const float act_k = g == 2 ? 2.f : 1.f;
 
         for (int s = 0; s < maxlen; ++s) {
             const int nxt = (s + 1) & 1;
-            float gxv[NL];
+            float gxv[LPW];
 #pragma unroll
-            for (int i = 0; i < NL; ++i) {
+            for (int i = 0; i < LPW; ++i) {
                 gxv[i] = s < glen[i] ? __ldg(gptr[i]) : 0.f;
                 gptr[i] += gstride;
             }
@@ -271,37 +277,37 @@ __global__ void __launch_bounds__(LTHREADS, 1) k_lstm_rec_tc(LstmTcParams p) {
             mbar_wait(mma_done, (uint32_t)(s & 1));
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const long long e0 = p.dbg ? clock64() : 0;
-            // D1a = cols 0..31 [W1 h1 | W1 h2s], D1b = 32..63 (k-atoms 2,3), D2a | D2b = 64..95 [W2s h1 | W2s h1]
-            uint32_t ra[32], rb[32], rc[32];
-            tmem_ld32_nowait(lane_base + 0, ra); tmem_ld32_nowait(lane_base + 32, rb); tmem_ld32_nowait(lane_base + 64, rc);
+            // D1a = cols 0..31 [W1 h1 | W1 h2s], D1b = 32..63 (k-atoms 2,3), D2a = 64..79, D2b = 80..95 [W2s h1]
+            uint32_t m0[LPW], m1[LPW], c0[LPW], c1[LPW], c2[LPW], c3[LPW];
+            tmem_ld4_nowait(lane_base + 0, m0);  tmem_ld4_nowait(lane_base + 32, m1);
+            tmem_ld4_nowait(lane_base + 16, c0); tmem_ld4_nowait(lane_base + 48, c1);
+            tmem_ld4_nowait(lane_base + 64, c2); tmem_ld4_nowait(lane_base + 80, c3);
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
 #pragma unroll
-            for (int i = 0; i < NL; ++i) {
-                const float main_ = __uint_as_float(ra[i]) + __uint_as_float(rb[i]);
-                const float corr = (__uint_as_float(ra[16 + i]) + __uint_as_float(rb[16 + i])) + (__uint_as_float(rc[i]) + __uint_as_float(rc[16 + i]));
+            for (int i = 0; i < LPW; ++i) {
+                const float main_ = __uint_as_float(m0[i]) + __uint_as_float(m1[i]);
+                const float corr = (__uint_as_float(c0[i]) + __uint_as_float(c1[i])) + (__uint_as_float(c2[i]) + __uint_as_float(c3[i]));
                 const float pre = (main_ + corr * (1.f / X2_SCALE)) + gxv[i];
-                sg[(i * 8 + jq) * 4 + g] = fmaf(sigmoid_fast(pre * act_k), act_k, 1.f - act_k);
+                sg[((LPW * sw + i) * 8 + jq) * 4 + g] = fmaf(sigmoid_fast(pre * act_k), act_k, 1.f - act_k);
             }
             const long long e1 = p.dbg ? clock64() : 0;
-            __syncwarp();
+            named_bar(1 + q, 32 * EW);
             const long long e2 = p.dbg ? clock64() : 0;
-#pragma unroll
-            for (int b4 = 0; b4 < 4; ++b4) {
-                const int line = 4 * b4 + g;
-                const float4 gt = *reinterpret_cast<const float4 *>(&sg[(line * 8 + jq) * 4]);      // i, f, g, o
+            {
+                const float4 gt = *reinterpret_cast<const float4 *>(&sg[(cl * 8 + cj) * 4]);      // i, f, g, o
                 float h = 0.f;                             // finished / padding cells feed zeros (never used again)
-                if (lv[b4] && s < len4[b4]) {
-                    cst[b4] = gt.y * cst[b4] + gt.x * gt.z;
-                    h = gt.w * tanh_fast(cst[b4]);
-                    const int t_out = dir ? len4[b4] - 1 - s : s;
-                    p.out[(size_t)(base4[b4] + (long long)t_out * p.step) * OC + dir * hid + u] = h;
+                if (cv && s < clen) {
+                    cst = gt.y * cst + gt.x * gt.z;
+                    h = gt.w * tanh_fast(cst);
+                    *optr = h;
+                    optr += ostride;
                 }
-                sh[line * 8 + jq] = h;
+                sh[cl * 8 + cj] = h;
             }
             const long long e3 = p.dbg ? clock64() : 0;
-            __syncwarp();
-            if (s + 1 < maxlen) {
+            named_bar(1 + q, 32 * EW);
+            if (s + 1 < maxlen && sw == 0) {
                 // chunk = 8 unit slots of one line in one fp16 plane: row = plane*16 + line of the k-atom tile
                 const int plane = lane >> 4, line = lane & 15;
                 const float4 x0 = *reinterpret_cast<const float4 *>(&sh[line * 8]), x1 = *reinterpret_cast<const float4 *>(&sh[line * 8 + 4]);
@@ -325,9 +331,8 @@ __global__ void __launch_bounds__(LTHREADS, 1) k_lstm_rec_tc(LstmTcParams p) {
 #pragma unroll
                 for (int r = 0; r < LCS; ++r) st_async_v4(rB[r] + off, v, rFull[r] + (uint32_t)nxt * 8u);
             }
-            __syncwarp();
             if (p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && warp == 1 && lane == 0 && (s == 100 || s == 101))
-                printf("[tcrec] s=%d EPI  loop_top=%lld mma_done=%lld | wait %lld tmem+act %lld sync %lld cell %lld pack+send %lld\n",
+                printf("[tcrec] s=%d EPI  loop_top=%lld mma_done=%lld | wait %lld tmem+act %lld bar %lld cell %lld bar+pack+send %lld\n",
                        s, e_pre, e0, e0 - e_pre, e1 - e0, e2 - e1, e3 - e2, clock64() - e3);
         }
     }
