@@ -419,9 +419,9 @@ struct Exec {
                 else { lp.nseq = (int)(x.n * x.w); lp.T = (int)x.h; lp.q2 = (int)x.w; lp.s_outer = x.h * x.w; lp.s_inner = 1; lp.step = x.w; }
                 const int ks = hid <= 32 ? 1 : hid <= 64 ? 2 : hid <= 128 ? 4 : 8;
                 lp.U = (hid + ks - 1) / ks;
-                // opt-in: measured 1.63 ms vs 0.69 ms for the register-resident FFMA kernel on cfg2 (96 dependent N=16 MMAs per step are
-                // accumulator-latency bound and the pointwise + DSMEM exchange still serialise behind them) - see DESIGN.md 4.2
-                const bool rec_tc = ks == 8 && w.wpk && m->use_tc && getenv("KB_LSTM_TC") && atoi(getenv("KB_LSTM_TC")) == 1;
+                // tcgen05 recurrence (lstm_tc.cuh) for hidden sizes 129..256: 0.44 ms vs 0.69 ms for the CUDA-core kernel on cfg2 and
+                // only 64 instead of 112 SMs; KB_LSTM_TC=0 selects the CUDA-core kernel (accurate expf/tanhf, fp32 FMA)
+                const bool rec_tc = ks == 8 && w.wpk && m->use_tc && !(getenv("KB_LSTM_TC") && atoi(getenv("KB_LSTM_TC")) == 0);
                 if (rec_tc) {
                     ltc::LstmTcParams tp;
                     tp.gx = lp.gx; tp.wpk = (const uint16_t *)w.wpk; tp.out = lp.out; tp.lens = lp.lens; tp.nseq = lp.nseq; tp.T = lp.T;
