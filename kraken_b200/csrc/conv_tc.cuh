@@ -1,10 +1,11 @@
-// conv_tc.cuh - tcgen05 implicit-GEMM convolution (Cin = 32, stride 1, no dilation) with fused epilogue for sm_100a.
+// conv_tc.cuh - tcgen05 implicit-GEMM convolution (Cin a multiple of 32, stride 1, no dilation) with fused epilogue for sm_100a.
 //
 //   ActConv2D -> [Dropout] -> [MaxPool 2x2/2] -> [Dropout] -> [Reshape S1(1x0)1,3] -> (TF32 planes for the LSTM projection)
 //   kraken/lib/vgsl/layers.py:842-852, 381-388, 313-335
 //
-// Work item = one image n, one PAIR of output rows (h0, h0+1), 128 output columns.  In NHWC one pixel's 32 input
-// channels are exactly one 128-byte swizzle row, so the im2col matrix never exists:
+// Work item = one image n, one PAIR of output rows (h0, h0+1), 128 output columns, one tile of <= 128 output channels.  In
+// NHWC a 32-channel chunk of one pixel is exactly one 128-byte swizzle row, so the im2col matrix never exists (for Cin > 32
+// the item loops over the 32-channel chunks, re-using the row buffers and accumulating into the same TMEM columns):
 //   * TMA (4-D tensor map C,W,H,N; box 32 x (128+kw-1) x 1 x 1, 128B swizzle) brings the kh+1 input rows a row pair
 //     needs into shared memory ONCE; out-of-bounds coordinates are zero-filled by the TMA unit = the conv's zero padding
 //   * the A operand of tap (ky, kx) for output row r is the row buffer (ky + r) with its UMMA descriptor start address
@@ -26,14 +27,15 @@ namespace ctc {
 using namespace kb::tc;
 
 constexpr int TW = 128;                  // output columns per work item
-constexpr int NSTB = 3;                  // weight-tile ring stages
+constexpr int MAX_STB = 3;               // weight-tile ring stages (3 for channel tiles <= 64, 2 for 128)
 constexpr int CTHREADS = 192;
 constexpr int MAX_ROWS = 8;              // kh + 1 <= 8
 
 struct ConvTcParams {
     const float *bias; float *y; float *y_hi; float *y_lo;
     int N, Ho, Wo, Cout, kh, kw, py, px, act, pool;
-    int items_h, items_w;                // row pairs, column segments
+    int items_h, items_w, items_c;       // row pairs, column segments, output-channel tiles
+    int NC, CT, nstb;                    // 32-channel input chunks, output channels per tile, weight ring stages
     long long sN, sH, sW;                // output strides (floats) of (n, out row, out col); channel stride 1
     int out_h, out_w;                    // valid output extent (pooled when pool)
     int a_row_bytes;                     // bytes of one plane of one input-row buffer (multiple of 1024)
@@ -52,15 +54,16 @@ k_conv_tc(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ C
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int R = p.kh + 1;
     const int a_plane = p.a_row_bytes, a_row = 2 * a_plane;              // hi | lo
-    const int b_plane = p.Cout * 128, b_stage = 2 * b_plane;
+    const int CT = p.CT, NSTB = p.nstb;
+    const int b_plane = CT * 128, b_stage = 2 * b_plane;
     uint8_t *a_base = smem, *b_base = smem + R * a_row;
     uint64_t *bars = reinterpret_cast<uint64_t *>(b_base + NSTB * b_stage);
-    uint64_t *full_a = bars, *empty_a = bars + MAX_ROWS, *full_b = bars + 2 * MAX_ROWS, *empty_b = full_b + NSTB;
-    uint64_t *tfull = empty_b + NSTB, *tempty = tfull + 2;
+    uint64_t *full_a = bars, *empty_a = bars + MAX_ROWS, *full_b = bars + 2 * MAX_ROWS, *empty_b = full_b + MAX_STB;
+    uint64_t *tfull = empty_b + MAX_STB, *tempty = tfull + 2;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int nitems = p.N * p.items_h * p.items_w;
+    const int nitems = p.N * p.items_h * p.items_w * p.items_c;
     const uint32_t a_tx = (uint32_t)(2 * (TW + p.kw - 1) * 128), b_tx = (uint32_t)b_stage;
 
     if (threadIdx.x == 0) {
@@ -83,71 +86,77 @@ k_conv_tc(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ C
         if (elect_one()) {
             uint32_t a_phase = 0; int bs = 0; uint32_t b_phase = 0;
             for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
-                const int ws = item % p.items_w, hp = (item / p.items_w) % p.items_h, n = item / (p.items_w * p.items_h);
+                const int ct = item % p.items_c; int rest = item / p.items_c;
+                const int ws = rest % p.items_w, hp = (rest / p.items_w) % p.items_h, n = rest / (p.items_w * p.items_h);
                 const int h0 = 2 * hp - p.py, w0 = ws * TW - p.px;
-                int r_loaded = 0;
-                // interleave: input row r is needed from tap row ky = r - 1 on; weight tiles in (ky, kx) order
-                for (int ky = 0; ky < p.kh; ++ky) {
-                    for (; r_loaded <= ky + 1; ++r_loaded) {
-                        mbar_wait(&empty_a[r_loaded], a_phase ^ 1);
-                        mbar_expect_tx(&full_a[r_loaded], a_tx);
-                        tma_load_4d(a_base + r_loaded * a_row, &tm_x_hi, &full_a[r_loaded], 0, w0, h0 + r_loaded, n);
-                        tma_load_4d(a_base + r_loaded * a_row + a_plane, &tm_x_lo, &full_a[r_loaded], 0, w0, h0 + r_loaded, n);
+                for (int cc = 0; cc < p.NC; ++cc) {
+                    int r_loaded = 0;
+                    // interleave: input row r is needed from tap row ky = r - 1 on; weight tiles in (ky, kx) order
+                    for (int ky = 0; ky < p.kh; ++ky) {
+                        for (; r_loaded <= ky + 1; ++r_loaded) {
+                            mbar_wait(&empty_a[r_loaded], a_phase ^ 1);
+                            mbar_expect_tx(&full_a[r_loaded], a_tx);
+                            tma_load_4d(a_base + r_loaded * a_row, &tm_x_hi, &full_a[r_loaded], cc * 32, w0, h0 + r_loaded, n);
+                            tma_load_4d(a_base + r_loaded * a_row + a_plane, &tm_x_lo, &full_a[r_loaded], cc * 32, w0, h0 + r_loaded, n);
+                        }
+                        for (int kx = 0; kx < p.kw; ++kx) {
+                            mbar_wait(&empty_b[bs], b_phase ^ 1);
+                            mbar_expect_tx(&full_b[bs], b_tx);
+                            const int wrow = ((ky * p.kw + kx) * p.NC + cc) * p.Cout + ct * CT;
+                            tma_load_2d(b_base + bs * b_stage, &tm_w_hi, &full_b[bs], 0, wrow);
+                            tma_load_2d(b_base + bs * b_stage + b_plane, &tm_w_lo, &full_b[bs], 0, wrow);
+                            if (++bs == NSTB) { bs = 0; b_phase ^= 1; }
+                        }
                     }
+                    a_phase ^= 1;
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        const uint32_t idesc = idesc_tf32(128, CT);
+        uint32_t a_phase = 0; int bs = 0; uint32_t b_phase = 0; int acc = 0; uint32_t acc_phase = 0;
+        for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+            mbar_wait(&tempty[acc], acc_phase ^ 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t d0 = tmem_base + (uint32_t)(acc * 4 * CT);
+            for (int cc = 0; cc < p.NC; ++cc) {
+                for (int ky = 0; ky < p.kh; ++ky) {
+                    if (ky == 0) mbar_wait(&full_a[0], a_phase);
+                    mbar_wait(&full_a[ky + 1], a_phase);
                     for (int kx = 0; kx < p.kw; ++kx) {
-                        mbar_wait(&empty_b[bs], b_phase ^ 1);
-                        mbar_expect_tx(&full_b[bs], b_tx);
-                        tma_load_2d(b_base + bs * b_stage, &tm_w_hi, &full_b[bs], 0, (ky * p.kw + kx) * p.Cout);
-                        tma_load_2d(b_base + bs * b_stage + b_plane, &tm_w_lo, &full_b[bs], 0, (ky * p.kw + kx) * p.Cout);
+                        mbar_wait(&full_b[bs], b_phase);
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        if (elect_one()) {
+                            const uint32_t sb = smem_u32(b_base + bs * b_stage);
+                            const uint64_t b_hi = umma_desc_sw128(sb), b_lo = umma_desc_sw128(sb + b_plane);
+                            const bool first = (cc | ky | kx) == 0;
+#pragma unroll
+                            for (int r = 0; r < 2; ++r) {
+                                const uint32_t sa = smem_u32(a_base + (ky + r) * a_row) + (uint32_t)kx * 128u;
+                                const uint64_t a_hi = umma_desc_sw128(sa), a_lo = umma_desc_sw128(sa + a_plane);
+                                const uint32_t d_main = d0 + (uint32_t)(2 * r * CT), d_corr = d_main + (uint32_t)CT;
+#pragma unroll
+                                for (int k = 0; k < 4; ++k) {
+                                    const uint64_t adv = (uint64_t)((k * 32) >> 4);
+                                    umma_tf32(d_corr, a_lo + adv, b_hi + adv, idesc, (first && k == 0) ? 0u : 1u);
+                                    umma_tf32(d_corr, a_hi + adv, b_lo + adv, idesc, 1u);
+                                    umma_tf32(d_main, a_hi + adv, b_hi + adv, idesc, (first && k == 0) ? 0u : 1u);
+                                }
+                            }
+                            umma_commit(&empty_b[bs]);
+                            if (kx == p.kw - 1) {
+                                // input row buffers whose last reader (for this chunk) was this tap row: row ky (and kh when ky == kh-1)
+                                umma_commit(&empty_a[ky]);
+                                if (ky == p.kh - 1) { umma_commit(&empty_a[p.kh]); if (cc == p.NC - 1) umma_commit(&tfull[acc]); }
+                            }
+                        }
+                        __syncwarp();
                         if (++bs == NSTB) { bs = 0; b_phase ^= 1; }
                     }
                 }
                 a_phase ^= 1;
             }
-        }
-    } else if (warp == 1) {
-        // ===================== MMA issuer =====================
-        const uint32_t idesc = idesc_tf32(128, p.Cout);
-        uint32_t a_phase = 0; int bs = 0; uint32_t b_phase = 0; int acc = 0; uint32_t acc_phase = 0;
-        for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
-            mbar_wait(&tempty[acc], acc_phase ^ 1);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t d0 = tmem_base + (uint32_t)(acc * 4 * p.Cout);
-            for (int ky = 0; ky < p.kh; ++ky) {
-                if (ky == 0) mbar_wait(&full_a[0], a_phase);
-                mbar_wait(&full_a[ky + 1], a_phase);
-                for (int kx = 0; kx < p.kw; ++kx) {
-                    mbar_wait(&full_b[bs], b_phase);
-                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    if (elect_one()) {
-                        const uint32_t sb = smem_u32(b_base + bs * b_stage);
-                        const uint64_t b_hi = umma_desc_sw128(sb), b_lo = umma_desc_sw128(sb + b_plane);
-                        const bool first = (ky | kx) == 0;
-#pragma unroll
-                        for (int r = 0; r < 2; ++r) {
-                            const uint32_t sa = smem_u32(a_base + (ky + r) * a_row) + (uint32_t)kx * 128u;
-                            const uint64_t a_hi = umma_desc_sw128(sa), a_lo = umma_desc_sw128(sa + a_plane);
-                            const uint32_t d_main = d0 + (uint32_t)(2 * r * p.Cout), d_corr = d_main + (uint32_t)p.Cout;
-#pragma unroll
-                            for (int k = 0; k < 4; ++k) {
-                                const uint64_t adv = (uint64_t)((k * 32) >> 4);
-                                umma_tf32(d_corr, a_lo + adv, b_hi + adv, idesc, (first && k == 0) ? 0u : 1u);
-                                umma_tf32(d_corr, a_hi + adv, b_lo + adv, idesc, 1u);
-                                umma_tf32(d_main, a_hi + adv, b_hi + adv, idesc, (first && k == 0) ? 0u : 1u);
-                            }
-                        }
-                        umma_commit(&empty_b[bs]);
-                        if (kx == p.kw - 1) {
-                            // input row buffers whose last reader was this tap row: row ky (and kh when ky == kh-1)
-                            umma_commit(&empty_a[ky]);
-                            if (ky == p.kh - 1) { umma_commit(&empty_a[p.kh]); umma_commit(&tfull[acc]); }
-                        }
-                    }
-                    __syncwarp();
-                    if (++bs == NSTB) { bs = 0; b_phase ^= 1; }
-                }
-            }
-            a_phase ^= 1;
             if (p.acc_sets == 2) { if (++acc == 2) { acc = 0; acc_phase ^= 1; } }
             else acc_phase ^= 1;
         }
@@ -156,28 +165,30 @@ k_conv_tc(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ C
         const int q = warp & 3;
         int acc = 0; uint32_t acc_phase = 0;
         for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
-            const int ws = item % p.items_w, hp = (item / p.items_w) % p.items_h, n = item / (p.items_w * p.items_h);
+            const int ct = item % p.items_c; const int rest = item / p.items_c;
+            const int ws = rest % p.items_w, hp = (rest / p.items_w) % p.items_h, n = rest / (p.items_w * p.items_h);
             mbar_wait(&tfull[acc], acc_phase);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 4 * p.Cout);
+            const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 4 * CT);
+            const int cbase = ct * CT;                                     // first output channel of this tile
             const int wcol = ws * TW + q * 32 + lane;                       // conv output column
 #pragma unroll 1
-            for (int c0 = 0; c0 < p.Cout; c0 += 32) {
+            for (int c0 = 0; c0 < CT; c0 += 32) {
                 float v0[32], v1[32];
                 {
                     float t[32];
                     tmem_ld32(lane_base + (uint32_t)c0, v0);
-                    tmem_ld32(lane_base + (uint32_t)(p.Cout + c0), t);
+                    tmem_ld32(lane_base + (uint32_t)(CT + c0), t);
 #pragma unroll
                     for (int j = 0; j < 32; ++j) v0[j] += t[j];
-                    tmem_ld32(lane_base + (uint32_t)(2 * p.Cout + c0), v1);
-                    tmem_ld32(lane_base + (uint32_t)(3 * p.Cout + c0), t);
+                    tmem_ld32(lane_base + (uint32_t)(2 * CT + c0), v1);
+                    tmem_ld32(lane_base + (uint32_t)(3 * CT + c0), t);
 #pragma unroll
                     for (int j = 0; j < 32; ++j) v1[j] += t[j];
                 }
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
-                    const float b = p.bias ? __ldg(p.bias + c0 + j) : 0.f;
+                    const float b = p.bias ? __ldg(p.bias + cbase + c0 + j) : 0.f;
                     v0[j] = act_apply(v0[j] + b, p.act); v1[j] = act_apply(v1[j] + b, p.act);
                 }
                 if (p.pool) {
@@ -189,7 +200,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ C
                     }
                     const int wp = wcol >> 1;
                     if ((lane & 1) == 0 && hp < p.out_h && wp < p.out_w) {
-                        const size_t off = (size_t)((long long)n * p.sN + (long long)hp * p.sH + (long long)wp * p.sW) + c0;
+                        const size_t off = (size_t)((long long)n * p.sN + (long long)hp * p.sH + (long long)wp * p.sW) + cbase + c0;
 #pragma unroll
                         for (int j = 0; j < 32; j += 4) {
                             if (p.y) *reinterpret_cast<float4 *>(p.y + off + j) = make_float4(v0[j], v0[j + 1], v0[j + 2], v0[j + 3]);
@@ -207,7 +218,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ C
                     for (int r = 0; r < 2; ++r) {
                         const int ho = 2 * hp + r;
                         if (ho < p.out_h && wcol < p.out_w) {
-                            const size_t off = (size_t)((long long)n * p.sN + (long long)ho * p.sH + (long long)wcol * p.sW) + c0;
+                            const size_t off = (size_t)((long long)n * p.sN + (long long)ho * p.sH + (long long)wcol * p.sW) + cbase + c0;
                             const float *v = r ? v1 : v0;
 #pragma unroll
                             for (int j = 0; j < 32; j += 4) {
@@ -239,22 +250,27 @@ k_conv_tc(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ C
     }
 }
 
-// NHWC fp32 activation [N][H][W][32] as a 4-D tensor map (C, W, H, N); box = 32 x box_w x 1 x 1, 128B swizzle, OOB -> 0
-inline bool make_map_nhwc32(CUtensorMap *map, const float *base, uint64_t N, uint64_t H, uint64_t W, uint32_t box_w) {
+// NHWC fp32 activation [N][H][W][C] (C a multiple of 32) as a 4-D tensor map (C, W, H, N); box = 32 x box_w x 1 x 1, 128B swizzle, OOB -> 0
+inline bool make_map_nhwc(CUtensorMap *map, const float *base, uint64_t N, uint64_t H, uint64_t W, uint64_t C, uint32_t box_w) {
     PFN_encodeTiled enc = get_encode();
     if (!enc) return false;
-    cuuint64_t dims[4] = {32, W, H, N};
-    cuuint64_t strides[3] = {32 * sizeof(float), W * 32 * sizeof(float), H * W * 32 * sizeof(float)};
+    cuuint64_t dims[4] = {C, W, H, N};
+    cuuint64_t strides[3] = {C * sizeof(float), W * C * sizeof(float), H * W * C * sizeof(float)};
     cuuint32_t box[4] = {32, box_w, 1, 1};
     cuuint32_t estr[4] = {1, 1, 1, 1};
     return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-inline size_t conv_tc_smem(int kh, int kw, int cout, int *a_row_bytes) {
+// output-channel tile and weight-ring depth for a layer; returns the dynamic shared memory the kernel needs
+inline size_t conv_tc_plan(int kh, int kw, int cout, int *ct_out, int *nstb_out, int *a_row_bytes) {
+    const int ct = cout <= 128 ? cout : (cout % 128 == 0 ? 128 : (cout % 64 == 0 ? 64 : 32));
+    const int nstb = ct > 64 ? 2 : 3;
     const int plane = ((TW + kw - 1) * 128 + 1023) & ~1023;
+    if (ct_out) *ct_out = ct;
+    if (nstb_out) *nstb_out = nstb;
     if (a_row_bytes) *a_row_bytes = plane;
-    return (size_t)(kh + 1) * 2 * plane + (size_t)NSTB * 2 * cout * 128 + 512 + 1024;
+    return (size_t)(kh + 1) * 2 * plane + (size_t)nstb * 2 * ct * 128 + 512 + 1024;
 }
 
 }  // namespace ctc

@@ -175,14 +175,18 @@ static void finalize_weights(kb_model *m) {
                             wt[(size_t)((ky * n.kw + kx) * n.cin + ci) * ncp + co] = src[(((size_t)co * n.cin + ci) * n.kh + ky) * n.kw + kx];
             w.wt = upload(m, wt); w.bias = upload(m, w.host[1]); w.ncp = ncp; w.K = K; w.ncols = n.cout;
             if (n.kh == 1 && n.kw == 1) upload_split(m, src, w);          // [Cout][Cin] is already K-major
-            if (n.cin == 32 && n.sy == 1 && n.sx == 1 && n.dy == 1 && n.dx == 1 && n.cout % 32 == 0 && n.cout <= 128 && n.kh + 1 <= ctc::MAX_ROWS &&
+            if (n.cin % 32 == 0 && n.sy == 1 && n.sx == 1 && n.dy == 1 && n.dx == 1 && n.cout % 32 == 0 && n.kh + 1 <= ctc::MAX_ROWS &&
                 n.kh * n.kw > 1) {
-                std::vector<float> taps((size_t)n.kh * n.kw * n.cout * 32), hi(taps.size()), lo(taps.size());
+                // tcgen05 convolution operand: [tap][32-channel chunk][Cout][32] TF32 hi/lo planes
+                const int nc = n.cin / 32;
+                std::vector<float> taps((size_t)n.kh * n.kw * nc * n.cout * 32), hi(taps.size()), lo(taps.size());
                 for (int ky = 0; ky < n.kh; ++ky)
                     for (int kx = 0; kx < n.kw; ++kx)
-                        for (int co = 0; co < n.cout; ++co)
-                            for (int ci = 0; ci < 32; ++ci)
-                                taps[(((size_t)(ky * n.kw + kx) * n.cout) + co) * 32 + ci] = src[(((size_t)co * 32 + ci) * n.kh + ky) * n.kw + kx];
+                        for (int cc = 0; cc < nc; ++cc)
+                            for (int co = 0; co < n.cout; ++co)
+                                for (int ci = 0; ci < 32; ++ci)
+                                    taps[((((size_t)(ky * n.kw + kx) * nc + cc) * n.cout) + co) * 32 + ci] =
+                                        src[(((size_t)co * n.cin + cc * 32 + ci) * n.kh + ky) * n.kw + kx];
                 for (size_t i = 0; i < taps.size(); ++i) { hi[i] = tf32_rna(taps[i]); lo[i] = taps[i] - hi[i]; }
                 w.c_hi = upload(m, hi); w.c_lo = upload(m, lo);
             }
@@ -550,12 +554,12 @@ struct Exec {
     }
     // tensor-core convolution (conv_tc.cuh): stride-1, undilated, Cin a multiple of 32, Cout a multiple of 16 up to 256
     bool tc_conv_eligible(const Node &c, const Dims &in) const {
-        if (!m->use_tc || c.kind != K_CONV || in.c != 32) return false;
+        if (!m->use_tc || c.kind != K_CONV || in.c != c.cin || (in.c % 32) != 0) return false;
         const LeafWeights &w = m->lw[c.leaf_index];
         if (!w.c_hi) return false;
         if (!(c.act == ACT_RELU || c.act == ACT_LINEAR || c.act == ACT_SIGMOID_LOGITS || c.act == ACT_TANH || c.act == ACT_LEAKY)) return false;
         if (in.h < 1 || in.w < 1) return false;
-        return ctc::conv_tc_smem(c.kh, c.kw, c.cout, nullptr) <= 227 * 1024;
+        return ctc::conv_tc_plan(c.kh, c.kw, c.cout, nullptr, nullptr, nullptr) <= 227 * 1024;
     }
     static bool fold_h(const Node &c) { return c.kind == K_RESHAPE && c.rs_src == 2 && c.rs_a == 1 && c.rs_b == -1 && c.rs_high == 2 && c.rs_low == 1; }
 
@@ -603,18 +607,19 @@ struct Exec {
             cp.items_w = (int)((dconv.w + ctc::TW - 1) / ctc::TW);
             if (fd) { cp.sN = dpost.w * dpost.h * dpost.c; cp.sW = dpost.h * dpost.c; cp.sH = dpost.c; }
             else { cp.sN = dpost.h * dpost.w * dpost.c; cp.sH = dpost.w * dpost.c; cp.sW = dpost.c; }
-            cp.acc_sets = 8 * c0.cout <= 512 ? 2 : 1;
-            const size_t smem = ctc::conv_tc_smem(c0.kh, c0.kw, c0.cout, &cp.a_row_bytes);
+            const size_t smem = ctc::conv_tc_plan(c0.kh, c0.kw, c0.cout, &cp.CT, &cp.nstb, &cp.a_row_bytes);
+            cp.NC = c0.cin / 32; cp.items_c = c0.cout / cp.CT;
+            cp.acc_sets = 8 * cp.CT <= 512 ? 2 : 1;
             CUtensorMap tx_hi, tx_lo, tw_hi, tw_lo;
             const uint32_t box_w = (uint32_t)(ctc::TW + c0.kw - 1);
-            if (!ctc::make_map_nhwc32(&tx_hi, x_hi, (uint64_t)cur.n, (uint64_t)cur.h, (uint64_t)cur.w, box_w) ||
-                !ctc::make_map_nhwc32(&tx_lo, x_lo, (uint64_t)cur.n, (uint64_t)cur.h, (uint64_t)cur.w, box_w) ||
-                !tc::make_map_2d(&tw_hi, w.c_hi, (uint64_t)c0.kh * c0.kw * c0.cout, 32, (uint32_t)c0.cout) ||
-                !tc::make_map_2d(&tw_lo, w.c_lo, (uint64_t)c0.kh * c0.kw * c0.cout, 32, (uint32_t)c0.cout))
+            if (!ctc::make_map_nhwc(&tx_hi, x_hi, (uint64_t)cur.n, (uint64_t)cur.h, (uint64_t)cur.w, (uint64_t)cur.c, box_w) ||
+                !ctc::make_map_nhwc(&tx_lo, x_lo, (uint64_t)cur.n, (uint64_t)cur.h, (uint64_t)cur.w, (uint64_t)cur.c, box_w) ||
+                !tc::make_map_2d(&tw_hi, w.c_hi, (uint64_t)c0.kh * c0.kw * cp.NC * c0.cout, 32, (uint32_t)cp.CT) ||
+                !tc::make_map_2d(&tw_lo, w.c_lo, (uint64_t)c0.kh * c0.kw * cp.NC * c0.cout, 32, (uint32_t)cp.CT))
                 throw CudaError("cuTensorMapEncodeTiled failed (conv)");
             static bool attr_set = false;
             if (!attr_set) { CK(cudaFuncSetAttribute(ctc::k_conv_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); attr_set = true; }
-            const int nitems = cp.N * cp.items_h * cp.items_w;
+            const int nitems = cp.N * cp.items_h * cp.items_w * cp.items_c;
             if (nitems > 0) LAUNCH(m, ctc::k_conv_tc, (unsigned)std::min(nitems, m->sm_count), ctc::CTHREADS, smem, st, tx_hi, tx_lo, tw_hi, tw_lo, cp);
         }
         advance_lens(c0, lens, din, dconv);

@@ -281,6 +281,8 @@ FUSE_SPECS = [
     ('[1,20,0,1 Cr3,3,32 Mp2,2 Cr3,5,32 Ct5,3,64 S1(1x0)1,3 Lbx16 O1c12]', 20, (300, 257)),          # conv_tc w/o pool, tanh, kw/kh 5, fold
     ('[1,21,0,1 Cl5,7,32 Do0.1,2 Mp2,2 Cr3,3,32 Do0.1,2 Mp2,2 Cr3,3,96 Gn4 Cr1,1,64 Mp2,2 S1(1x0)1,3 O1c9]', 21, (200,)),  # odd H, Cout 96, GN after
     ('[1,16,0,1 Cr3,3,8 Mp2,2 Cr3,3,32 Cr3,9,32 Mp2,2 S1(1x0)1,3 Lfx24 O1c7]', 16, (513,)),         # Cin 8 -> FFMA, then conv_tc chain
+    ('[1,16,0,1 Cr3,3,64 Mp2,2 Cr3,3,64 Cr3,5,128 Mp2,2 S1(1x0)1,3 O1c9]', 16, (300, 131)),          # conv_tc with 2 input chunks, Cout 128
+    ('[1,12,0,1 Cr3,3,32 Mp2,2 Cr3,3,256 Cr3,3,256 Ct1,1,64 S1(1x0)1,3 O1c5]', 12, (260,)),           # 8 input chunks, 2 output-channel tiles
 ]
 
 
