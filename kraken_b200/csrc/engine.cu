@@ -262,6 +262,26 @@ static void finalize_weights(kb_model *m) {
                 m->dev_allocs.push_back(dp);
                 CK(cudaMemcpy(dp, pk.data(), pk.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
                 w.wpk = dp;
+            } else if (h <= 32) {
+                // single-CTA tcgen05 recurrence (k_lstm_rec_tc_small): [dir][plane][gate row = 4*unit + gate][k = 32] fp16
+                std::vector<uint16_t> pk((size_t)dirs * 2 * 128 * 32, 0);
+                for (int d = 0; d < dirs; ++d) {
+                    const std::vector<float> &wh = w.host[d * 4 + 1];      // [4h][h]
+                    for (int u = 0; u < h; ++u)
+                        for (int gate = 0; gate < 4; ++gate)
+                            for (int u2 = 0; u2 < h; ++u2) {
+                                const float x = wh[(size_t)(gate * h + u) * h + u2];
+                                const __half x1 = __float2half_rn(x);
+                                const size_t o = (((size_t)d * 2) * 128 + (size_t)(4 * u + gate)) * 32 + u2;
+                                pk[o] = __half_as_ushort(x1);
+                                pk[o + (size_t)128 * 32] = __half_as_ushort(__float2half_rn((x - __half2float(x1)) * ltc::X2_SCALE));
+                            }
+                }
+                void *dp = nullptr;
+                CK(cudaMalloc(&dp, pk.size() * sizeof(uint16_t)));
+                m->dev_allocs.push_back(dp);
+                CK(cudaMemcpy(dp, pk.data(), pk.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+                w.wpk = dp;
             }
         }
     }
@@ -425,8 +445,31 @@ struct Exec {
                 lp.U = (hid + ks - 1) / ks;
                 // tcgen05 recurrence (lstm_tc.cuh) for hidden sizes 129..256: 0.44 ms vs 0.69 ms for the CUDA-core kernel on cfg2 and
                 // only 64 instead of 112 SMs; KB_LSTM_TC=0 selects the CUDA-core kernel (accurate expf/tanhf, fp32 FMA)
-                const bool rec_tc = ks == 8 && w.wpk && m->use_tc && !(getenv("KB_LSTM_TC") && atoi(getenv("KB_LSTM_TC")) == 0);
-                if (rec_tc) {
+                const bool tc_on = w.wpk && m->use_tc && !(getenv("KB_LSTM_TC") && atoi(getenv("KB_LSTM_TC")) == 0);
+                const bool rec_tc = ks == 8 && tc_on;
+                if (ks == 1 && tc_on) {
+                    // hid <= 32 (blla's Lbx32 / Lby32): 64 sequences per CTA, W_hh in tensor memory, no cluster
+                    ltc::LstmTcParams tp;
+                    tp.gx = lp.gx; tp.wpk = (const uint16_t *)w.wpk; tp.out = lp.out; tp.lens = lp.lens; tp.nseq = lp.nseq; tp.T = lp.T;
+                    tp.dbg = 0; tp.hid = hid; tp.dirs = dirs; tp.U = hid; tp.q2 = lp.q2; tp.s_outer = lp.s_outer; tp.s_inner = lp.s_inner; tp.step = lp.step;
+                    int snl = lp.nseq * dirs >= 64 * 2 * sm ? 64 : lp.nseq * dirs >= 16 * 4 * sm ? 32 : 16;      // fill the SMs first, then grow the CTAs
+                    if (getenv("KB_LSTM_SNL")) snl = atoi(getenv("KB_LSTM_SNL"));
+                    if (snl != 64 && snl != 32) snl = 16;
+                    const dim3 grid((unsigned)((lp.nseq + snl - 1) / snl), (unsigned)dirs, 1);
+                    if (getenv("KB_DEBUG")) fprintf(stderr, "[kb] %s: tcgen05 recurrence (single CTA, %d lines), %u CTAs, T=%d\n", n.name.c_str(), snl, grid.x * grid.y, lp.T);
+                    static bool attr_set_s = false;
+                    if (!attr_set_s) {
+                        CK(cudaFuncSetAttribute(ltc::k_lstm_rec_tc_small<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, ltc::SmallCfg<64>::SMEM_BYTES));
+                        CK(cudaFuncSetAttribute(ltc::k_lstm_rec_tc_small<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, ltc::SmallCfg<32>::SMEM_BYTES));
+                        CK(cudaFuncSetAttribute(ltc::k_lstm_rec_tc_small<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, ltc::SmallCfg<16>::SMEM_BYTES));
+                        attr_set_s = true;
+                    }
+                    if (snl == 64) ltc::k_lstm_rec_tc_small<64><<<grid, ltc::SmallCfg<64>::THREADS, ltc::SmallCfg<64>::SMEM_BYTES, st>>>(tp);
+                    else if (snl == 32) ltc::k_lstm_rec_tc_small<32><<<grid, ltc::SmallCfg<32>::THREADS, ltc::SmallCfg<32>::SMEM_BYTES, st>>>(tp);
+                    else ltc::k_lstm_rec_tc_small<16><<<grid, ltc::SmallCfg<16>::THREADS, ltc::SmallCfg<16>::SMEM_BYTES, st>>>(tp);
+                    ++m->launches;
+                    CK(cudaPeekAtLastError());
+                } else if (rec_tc) {
                     ltc::LstmTcParams tp;
                     tp.gx = lp.gx; tp.wpk = (const uint16_t *)w.wpk; tp.out = lp.out; tp.lens = lp.lens; tp.nseq = lp.nseq; tp.T = lp.T;
                     tp.dbg = getenv("KB_LSTM_DBG") ? 1 : 0; tp.hid = hid; tp.dirs = dirs; tp.U = lp.U; tp.q2 = lp.q2; tp.s_outer = lp.s_outer; tp.s_inner = lp.s_inner; tp.step = lp.step;

@@ -345,5 +345,230 @@ __global__ void __launch_bounds__(LTHREADS, 1) k_lstm_rec_tc(LstmTcParams p) {
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------------
+// Small-hidden variant (hid <= 32: the blla 2-D BiLSTM sweeps Lbx32 / Lby32): one CTA, no cluster.
+//
+//   All 4*hid <= 128 gate rows fit one CTA (row = 4*unit + gate), K = 32, so a CTA carries SNL = 64 sequences of one direction:
+//   A: W1 | W2s planes, 128 rows x K32 -> 2 x 16 TMEM columns.    B: [h1 (64 lines) | h2s (64 lines)] x K32 in one SW128 tile
+//   (128 rows x 128 B, k-chunks 0..3 used), double buffered.  4 MMAs per step: D1 (M128 N128 K16) x2, D2 (M128 N64 K16) x2.
+//   The page's thousands of short rows/columns give 86..114 CTAs; a step is bounded by the 96 KB TMEM read-back and the
+//   8192 SFU activations, not by the MMAs.  Same arithmetic as the clustered kernel (fp16 pairs, fp32 accumulate).
+template <int NLS> struct SmallCfg {                    // NLS lines per CTA, EWS = NLS / 16 epilogue warps per TMEM lane quarter
+    static constexpr int EWS = NLS / 16;
+    static constexpr int THREADS = 32 + 4 * EWS * 32;
+    static constexpr int B_BUF_B = 2 * NLS * 128;        // [h1 | h2s] rows x 128 B
+    static constexpr int SG = NLS * 8 * 4, SH = NLS * 8;
+    static constexpr int STG_BYTES = 4 * (SG + SH) * 4;
+    static constexpr int INFO_BYTES = NLS * 8 + NLS * 4; // per line: base pixel (long long), length (int)
+    static constexpr int SMEM_BYTES = 2 * B_BUF_B + STG_BYTES + INFO_BYTES + 128 + 1024;
+    static constexpr int TM_A0 = 3 * NLS;                // D1 @0 (2 NLS cols), D2 @2 NLS (NLS cols); A: W1 @3 NLS (16 cols), W2s @3 NLS + 16
+    static constexpr int TM_ALLOC = NLS == 64 ? 256 : NLS == 32 ? 128 : 128;
+    static constexpr int MINB = NLS == 64 ? 1 : 2;
+};
+constexpr int S_LPW = 16;                                // lines per epilogue warp
+constexpr int S_A_PLANE_ELEMS = 128 * 32;
+
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t *r) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+                   "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]) : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t *r) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+                 ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+                   "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]) : "memory");
+}
+
+template <int NLS>
+__global__ void __launch_bounds__(SmallCfg<NLS>::THREADS, SmallCfg<NLS>::MINB) k_lstm_rec_tc_small(LstmTcParams p) {
+    using Cfg = SmallCfg<NLS>;
+    constexpr int SNL = NLS, S_B_BUF_B = Cfg::B_BUF_B, S_SG = Cfg::SG, S_SH = Cfg::SH, S_STG_BYTES = Cfg::STG_BYTES;
+    constexpr int S_INFO_BYTES = Cfg::INFO_BYTES, S_TM_A0 = Cfg::TM_A0, EWS = Cfg::EWS, STHREADS = Cfg::THREADS;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t *sB = smem;
+    float *stg = reinterpret_cast<float *>(sB + 2 * S_B_BUF_B);
+    long long *lbase = reinterpret_cast<long long *>(sB + 2 * S_B_BUF_B + S_STG_BYTES);
+    int *llen = reinterpret_cast<int *>(lbase + SNL);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sB + 2 * S_B_BUF_B + S_STG_BYTES + S_INFO_BYTES);
+    uint64_t *b_full = bars + 1 /* [2] */, *mma_done = bars + 3;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 4);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int chunk = blockIdx.x, dir = blockIdx.y;
+    const int hid = p.hid, GC = p.dirs * 4 * hid, OC = p.dirs * hid;
+
+    if (threadIdx.x == 0) {
+        mbar_init(&b_full[0], 4 * EWS); mbar_init(&b_full[1], 4 * EWS); mbar_init(mma_done, 1);      // one arrival per epilogue warp
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int i = threadIdx.x; i < 2 * S_B_BUF_B / 16; i += STHREADS) reinterpret_cast<uint4 *>(sB)[i] = make_uint4(0, 0, 0, 0);   // h_{-1} = 0, k >= 32 stays 0
+    if ((int)threadIdx.x < SNL) {
+        const int ql = chunk * SNL + threadIdx.x;
+        const int qq = ql < p.nseq ? ql : 0;
+        lbase[threadIdx.x] = (long long)(qq / p.q2) * p.s_outer + (long long)(qq % p.q2) * p.s_inner;
+        llen[threadIdx.x] = ql < p.nseq ? min(max(p.lens ? p.lens[ql] : p.T, 0), p.T) : 0;
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(Cfg::TM_ALLOC) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+    if (warp >= 1 && warp <= 4) {
+        const int m = 32 * (warp & 3) + lane;
+        const uint32_t *src = reinterpret_cast<const uint32_t *>(p.wpk) + ((size_t)dir * 2 * S_A_PLANE_ELEMS) / 2 + (size_t)m * 16;
+#pragma unroll 1
+        for (int pl = 0; pl < 2; ++pl) {
+            uint32_t r[16];
+#pragma unroll
+            for (int i = 0; i < 16; i += 4) {
+                const uint4 v = __ldg(reinterpret_cast<const uint4 *>(src + (size_t)pl * (S_A_PLANE_ELEMS / 2) + i));
+                r[i] = v.x; r[i + 1] = v.y; r[i + 2] = v.z; r[i + 3] = v.w;
+            }
+            tmem_st16(tmem_base + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)(S_TM_A0 + pl * 16), r);
+        }
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+
+    int maxlen = 0;
+    for (int lb = 0; lb < SNL; ++lb) maxlen = max(maxlen, llen[lb]);
+
+    if (warp == 0) {
+        // ===================== MMA issuer =====================
+        const uint32_t id1 = idesc_f16(0, 0, 128, 2 * SNL), id2 = idesc_f16(0, 0, 128, SNL);
+        for (int s = 0; s < maxlen; ++s) {
+            const int cur = s & 1;
+            if (s > 0) mbar_wait(&b_full[cur], (uint32_t)(((s - 1) >> 1) & 1));
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (elect_one()) {
+                const uint32_t b0 = smem_u32(sB + cur * S_B_BUF_B);
+#pragma unroll
+                for (int k = 0; k < 2; ++k) {
+                    const uint64_t bd = umma_desc_sw128(b0) + (uint64_t)(2 * k);
+                    const uint32_t a1 = tmem_base + (uint32_t)(S_TM_A0 + k * 8);
+                    umma_f16_ts(tmem_base, a1, bd, id1, (uint32_t)k);                       // [W1 h1 | W1 h2s]
+                    umma_f16_ts(tmem_base + (uint32_t)(2 * SNL), a1 + 16u, bd, id2, (uint32_t)k);   // W2s h1 (first 64 rows of B)
+                }
+                umma_commit(mma_done);
+            }
+            __syncwarp();
+        }
+    } else {
+        // ===================== epilogue warps 1..16: quarter q = warp & 3, sub-warp sw = (warp-1) >> 2 =====================
+        const int q = warp & 3;
+        const int sw = (warp - 1) >> 2;
+        const int jq = lane >> 2, g = lane & 3;
+        const int u = 8 * q + jq;
+        const bool uvalid = u < hid;
+        float *sg = stg + q * (S_SG + S_SH), *sh = sg + S_SG;
+        const int tq = sw * 32 + lane;
+        // the four cells this thread updates: line cl, units cu0 .. cu0+3
+        const int cl = tq >> 1, cj0 = (tq & 1) * 4, cu0 = 8 * q + cj0;
+        const int cql = chunk * SNL + cl;
+        const int clen = llen[cl];
+        const long long cbase = lbase[cl];
+        float cst[4] = {0.f, 0.f, 0.f, 0.f};
+        if (cql < p.nseq)
+            for (int tt = clen; tt < p.T; ++tt)
+                for (int e = 0; e < 4; ++e)
+                    if (cu0 + e < hid) p.out[(size_t)(cbase + (long long)tt * p.step) * OC + dir * hid + cu0 + e] = 0.f;
+        float *optr = p.out + (size_t)(cbase + (long long)(dir ? max(clen - 1, 0) : 0) * p.step) * OC + dir * hid + cu0;
+        const long long ostride = (long long)(dir ? -1 : 1) * p.step * OC;
+        const bool ovec = (hid & 3) == 0 && cu0 + 3 < hid;
+        const float *gx0 = p.gx + (size_t)dir * 4 * hid + (size_t)(uvalid ? u : 0) * 4 + g;
+        const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(S_LPW * sw);
+        const float act_k = g == 2 ? 2.f : 1.f;
+
+        for (int s = 0; s < maxlen; ++s) {
+            const int nxt = (s + 1) & 1;
+            float gxv[S_LPW];
+#pragma unroll
+            for (int i = 0; i < S_LPW; ++i) {
+                const int l = S_LPW * sw + i, len = llen[l];
+                const int t = dir ? len - 1 - s : s;
+                gxv[i] = (uvalid && s < len) ? __ldg(gx0 + (size_t)(lbase[l] + (long long)t * p.step) * GC) : 0.f;
+            }
+            mbar_wait(mma_done, (uint32_t)(s & 1));
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            uint32_t m0[S_LPW], c0[S_LPW], c1[S_LPW];
+            tmem_ld16_nowait(lane_base, m0);
+            tmem_ld16_nowait(lane_base + SNL, c0);
+            tmem_ld16_nowait(lane_base + 2 * SNL, c1);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+#pragma unroll
+            for (int i = 0; i < S_LPW; ++i) {
+                const float corr = __uint_as_float(c0[i]) + __uint_as_float(c1[i]);
+                const float pre = (__uint_as_float(m0[i]) + corr * (1.f / X2_SCALE)) + gxv[i];
+                sg[((S_LPW * sw + i) * 8 + jq) * 4 + g] = fmaf(sigmoid_fast(pre * act_k), act_k, 1.f - act_k);
+            }
+            named_bar(1 + q, 32 * EWS);
+            {
+                float hv[4];
+                const bool live = cql < p.nseq && s < clen;
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const float4 gt = *reinterpret_cast<const float4 *>(&sg[(cl * 8 + cj0 + e) * 4]);      // i, f, g, o
+                    hv[e] = 0.f;
+                    if (live && cu0 + e < hid) {
+                        cst[e] = gt.y * cst[e] + gt.x * gt.z;
+                        hv[e] = gt.w * tanh_fast(cst[e]);
+                    }
+                }
+                if (live) {
+                    if (ovec) *reinterpret_cast<float4 *>(optr) = make_float4(hv[0], hv[1], hv[2], hv[3]);
+                    else
+                        for (int e = 0; e < 4; ++e) if (cu0 + e < hid) optr[e] = hv[e];
+                    optr += ostride;
+                }
+                *reinterpret_cast<float4 *>(&sh[cl * 8 + cj0]) = make_float4(hv[0], hv[1], hv[2], hv[3]);
+            }
+            named_bar(1 + q, 32 * EWS);
+            if (s + 1 < maxlen) {
+                // chunk = 8 units of one line in one fp16 plane: tile row = plane*64 + line, 16-byte k-chunk q
+                const int plane = tq / SNL, line = tq % SNL;
+                const float4 x0 = *reinterpret_cast<const float4 *>(&sh[line * 8]), x1 = *reinterpret_cast<const float4 *>(&sh[line * 8 + 4]);
+                const float xs[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+                uint32_t pk[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    uint32_t two[2];
+#pragma unroll
+                    for (int f = 0; f < 2; ++f) {
+                        const float x = xs[2 * e + f];
+                        const __half h1 = __float2half_rn(x);
+                        const __half h2 = __float2half_rn((x - __half2float(h1)) * X2_SCALE);
+                        two[f] = (uint32_t)__half_as_ushort(plane == 0 ? h1 : h2);
+                    }
+                    pk[e] = two[0] | (two[1] << 16);
+                }
+                const int row = plane * SNL + line;
+                const uint32_t off = (uint32_t)(nxt * S_B_BUF_B + row * 128 + ((q ^ (row & 7)) << 4));
+                // plain shared store + proxy fence + one mbarrier arrival per warp (st.async faults with "illegal instruction"
+                // in a launch without a cluster dimension, measured)
+                *reinterpret_cast<uint4 *>(sB + off) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&b_full[nxt]);
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(Cfg::TM_ALLOC) : "memory");
+    }
+}
+
 }  // namespace ltc
 }  // namespace kb

@@ -337,3 +337,34 @@ def test_tensor_core_recurrence(hid):
         assert rel_err(out, ref) <= TIGHT, (tc, rel_err(out, ref))
         assert ol.tolist() == rl.tolist()
         assert triples(dec) == triples(ref_dec), tc
+
+
+@pytest.mark.parametrize('spec,n,h,w,ragged', [
+    ('[1,16,0,1 Cr3,3,32 Mp2,2 S1(1x0)1,3 Lbx32 O1c30]', 70, 16, 120, True),     # packed lines, 2 CTAs per direction
+    ('[1,16,0,1 Cr3,3,32 Mp2,2 S1(1x0)1,3 Lfx27 O1c30]', 9, 16, 90, True),       # hid % 4 != 0, forward only
+    ('[1,0,0,3 Cr3,3,16 Lbx32 Lby32 Cr1,1,8 Lby20 Lrx32 O2l4]', 2, 37, 45, False),   # blla-style 2-D sweeps, both axes
+])
+def test_tensor_core_recurrence_small_hidden(spec, n, h, w, ragged):
+    """Single-CTA tcgen05 recurrence (k_lstm_rec_tc_small, hidden <= 32, the blla BiLSTM sweeps) against the oracle and against
+    the CUDA-core kernel (KB_LSTM_TC=0)."""
+    om = vo.OracleModel(spec)
+    wts = om.init_like_reference(77)
+    g = torch.Generator().manual_seed(77)
+    cin = om.input[1]
+    x = torch.rand(n, cin, h, w, generator=g)
+    lens = None
+    if ragged:
+        lens = torch.randint(10, w + 1, (n,), generator=g)
+        lens[0] = w
+        for i, l in enumerate(lens.tolist()):
+            x[i, ..., l:] = 0
+    ref, rl = om.forward(x, lens)
+    m = kb.TorchVGSLModel(vgsl=spec)
+    m.load_state_dict(wts)
+    m.to('cuda:0')
+    for tc in (1, 0):
+        with env(KB_LSTM_TC=tc):
+            out, ol = m.nn(x.cuda(), lens)
+        assert rel_err(out, ref) <= TIGHT, (tc, rel_err(out, ref))
+        if ragged:
+            assert ol.tolist() == rl.tolist()
