@@ -51,7 +51,7 @@ __global__ void __launch_bounds__(CTHREADS, 1)
 k_conv_tc(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ CUtensorMap tm_x_lo,
           const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant__ CUtensorMap tm_w_lo, ConvTcParams p) {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t *smem = smem_align1024(smem_raw);
     const int R = p.kh + 1;
     const int a_plane = p.a_row_bytes, a_row = 2 * a_plane;              // hi | lo
     const int CT = p.CT, NSTB = p.nstb;

@@ -293,6 +293,7 @@ static void finalize_weights(kb_model *m) {
 struct Exec {
     kb_model *m; cudaStream_t st; bool dry;
     int leaf_counter = 0;
+    bool planes_hint = false;        // set by run() for a GroupNorm whose consumer reads TF32 planes
 
     int *dev_lens(const Lens &l) {
         if (!l.has) return nullptr;
@@ -412,11 +413,27 @@ struct Exec {
             bool ragged = false;
             if (lens.has) for (int32_t l : lens.v) if (l < W) ragged = true;
             int *dl = ragged ? dev_lens(lens) : nullptr;
+            const bool vec4 = (C % 4) == 0 && C <= 1024 && !(getenv("KB_GN") && strcmp(getenv("KB_GN"), "scalar") == 0);
+            float2 *ab = vec4 ? (float2 *)m->arena.alloc((size_t)N * C * sizeof(float2)) : nullptr;
+            const bool planes = vec4 && planes_hint;
+            planes_hint = false;
+            if (planes) { y.hi = (float *)m->arena.alloc((size_t)y.numel() * 4); y.lo = (float *)m->arena.alloc((size_t)y.numel() * 4); }
             if (!dry && y.numel()) {
-                const int bt = rows * cthreads;
-                LAUNCH(m, k_gn_partial, dim3(chunks, N), bt, (size_t)bt * cpt * 2 * sizeof(double), st, x.p, partial, H, W, C, G, dl, chunks, rows, cthreads, cpt);
-                LAUNCH(m, k_gn_finalize, (unsigned)((N * G + 127) / 128), 128, 0, st, partial, stats, N, G, chunks, H, W, C, dl, 1e-5f);
-                LAUNCH(m, k_gn_apply, grid1d(y.numel(), 256, sm), 256, 0, st, x.p, y.p, stats, w.aux, w.bias, (long long)y.numel(), H, W, C, G, dl);
+                if (vec4) {
+                    // float4 streaming passes (kernels.cuh k_gn_stats4 / k_gn_apply4); the apply pass also emits the TF32 planes a
+                    // tensor-core consumer wants, which saves the separate split pass (and the fp32 copy unless KB_KEEP_FP32)
+                    const int rows4 = 256 / (C / 4);
+                    LAUNCH(m, k_gn_stats4, dim3(chunks, N), 256, 0, st, x.p, partial, H, W, C, G, dl, chunks);
+                    LAUNCH(m, k_gn_finalize, (unsigned)((N * G + 127) / 128), 128, 0, st, partial, stats, N, G, chunks, H, W, C, dl, 1e-5f);
+                    LAUNCH(m, k_gn_coeffs, (unsigned)((N * C + 255) / 256), 256, 0, st, stats, w.aux, w.bias, ab, N, C, G);
+                    const long long nb = std::min<long long>((npix + rows4 - 1) / rows4, std::max(1, 16 * sm / std::max(N, 1)));
+                    LAUNCH(m, k_gn_apply4, dim3((unsigned)nb, N), 256, 0, st, x.p, (planes && !m->keep_fp32) ? nullptr : y.p, y.hi, y.lo, ab, H, W, C, dl);
+                } else {
+                    const int bt = rows * cthreads;
+                    LAUNCH(m, k_gn_partial, dim3(chunks, N), bt, (size_t)bt * cpt * 2 * sizeof(double), st, x.p, partial, H, W, C, G, dl, chunks, rows, cthreads, cpt);
+                    LAUNCH(m, k_gn_finalize, (unsigned)((N * G + 127) / 128), 128, 0, st, partial, stats, N, G, chunks, H, W, C, dl, 1e-5f);
+                    LAUNCH(m, k_gn_apply, grid1d(y.numel(), 256, sm), 256, 0, st, x.p, y.p, stats, w.aux, w.bias, (long long)y.numel(), H, W, C, G, dl);
+                }
             }
             break;
         }
@@ -553,6 +570,20 @@ struct Exec {
         if (lens.has) for (auto &l : lens.v) l = leaf_len(c, l, din, dout);
     }
 
+    // does the layer at/after position j of `series` read TF32 split planes of a tensor with dims d?  (tensor-core conv, or an
+    // LSTM / Linear whose projection runs on k_gemm_tc)
+    bool wants_planes(const Node &series, size_t j, const Dims &d) const {
+        const Node *nx = next_real(series, j);
+        if (!nx || !m->use_tc) return false;
+        if (nx->kind == K_CONV) return (m->fuse_mask & 2) && tc_conv_eligible(*nx, d);
+        if ((nx->kind == K_LSTM && !nx->legacy) || nx->kind == K_LINEAR) {
+            const LeafWeights &nw = m->lw[nx->leaf_index];
+            const long long M = (long long)d.n * d.h * d.w;
+            return nw.b_hi && (d.c % 4) == 0 && d.c >= 32 && nw.ncols >= 64 && M >= 128 && !(nx->kind == K_LINEAR && nx->aug);
+        }
+        return false;
+    }
+
     // Fused layer groups.  Returns the number of children of `series` consumed (0 = no pattern applies); on success `cur`
     // and `lens` are advanced past the group.  Layers inside a group do not materialise (no kb_debug_layer_output tap).
     size_t try_fuse(const Node &series, size_t i, Tensor &cur, Lens &lens) {
@@ -621,18 +652,7 @@ struct Exec {
         (void)jpool; (void)jfold;
         Tensor y = mk(dout);
         // consumer wants TF32 planes?  (another tensor-core conv, or an LSTM / Linear whose projection runs on k_gemm_tc)
-        bool planes = false;
-        {
-            const Node *nx = next_real(series, j);
-            if (nx && m->use_tc) {
-                if (nx->kind == K_CONV) planes = tc_conv_eligible(*nx, dout);
-                else if ((nx->kind == K_LSTM && !nx->legacy) || nx->kind == K_LINEAR) {
-                    const LeafWeights &nw = m->lw[nx->leaf_index];
-                    const long long M = (long long)dout.n * dout.h * dout.w;
-                    planes = nw.b_hi && (dout.c % 4) == 0 && dout.c >= 32 && nw.ncols >= 64 && M >= 128 && !(nx->kind == K_LINEAR && nx->aug);
-                }
-            }
-        }
+        const bool planes = wants_planes(series, j, dout);
         if (planes) { y.hi = (float *)m->arena.alloc((size_t)y.numel() * 4); y.lo = (float *)m->arena.alloc((size_t)y.numel() * 4); }
         float *x_hi = cur.hi, *x_lo = cur.lo;
         if (!x_hi) { x_hi = (float *)m->arena.alloc((size_t)cur.numel() * 4); x_lo = (float *)m->arena.alloc((size_t)cur.numel() * 4); }
@@ -680,7 +700,9 @@ struct Exec {
                 size_t used = 0;
                 if (m->fuse) used = try_fuse(n, i, cur, lens);
                 if (used) { i += used; continue; }
+                if (n.children[i]->kind == K_GN && m->fuse) planes_hint = wants_planes(n, i + 1, dims_of(cur));
                 cur = run(*n.children[i], cur, lens);
+                planes_hint = false;
                 ++i;
             }
             return cur;

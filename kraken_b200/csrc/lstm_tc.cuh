@@ -128,13 +128,14 @@ __device__ __forceinline__ void mbar_wait_cluster(uint64_t *bar, uint32_t parity
         "CD_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
 // gate non-linearities on the SFU: ex2.approx + rcp, absolute error ~1e-7 (the CUDA-core kernel keeps expf/tanhf)
-__device__ __forceinline__ float sigmoid_fast(float x) { return __frcp_rn(1.f + __expf(-x)); }
+__device__ __forceinline__ float rcp_fast(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }   // MUFU.RCP, no IEEE fix-up path
+__device__ __forceinline__ float sigmoid_fast(float x) { return rcp_fast(1.f + __expf(-x)); }
 __device__ __forceinline__ float tanh_fast(float x) { return fmaf(2.f, sigmoid_fast(2.f * x), -1.f); }
 __device__ __forceinline__ void named_bar(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 
 __global__ void __launch_bounds__(LTHREADS, 1) k_lstm_rec_tc(LstmTcParams p) {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t *smem = smem_align1024(smem_raw);
     uint8_t *sB = smem;
     float *stg = reinterpret_cast<float *>(sB + 2 * B_BUF_B);
     uint64_t *bars = reinterpret_cast<uint64_t *>(sB + 2 * B_BUF_B + STG_BYTES);
@@ -360,7 +361,7 @@ template <int NLS> struct SmallCfg {                    // NLS lines per CTA, EW
     static constexpr int B_BUF_B = 2 * NLS * 128;        // [h1 | h2s] rows x 128 B
     static constexpr int SG = NLS * 8 * 4, SH = NLS * 8;
     static constexpr int STG_BYTES = 4 * (SG + SH) * 4;
-    static constexpr int INFO_BYTES = NLS * 8 + NLS * 4; // per line: base pixel (long long), length (int)
+    static constexpr int INFO_BYTES = NLS * 8 + NLS * 8 + NLS * 4;   // per line: base pixel, first gx element (long long), length (int)
     static constexpr int SMEM_BYTES = 2 * B_BUF_B + STG_BYTES + INFO_BYTES + 128 + 1024;
     static constexpr int TM_A0 = 3 * NLS;                // D1 @0 (2 NLS cols), D2 @2 NLS (NLS cols); A: W1 @3 NLS (16 cols), W2s @3 NLS + 16
     static constexpr int TM_ALLOC = NLS == 64 ? 256 : NLS == 32 ? 128 : 128;
@@ -386,11 +387,12 @@ __global__ void __launch_bounds__(SmallCfg<NLS>::THREADS, SmallCfg<NLS>::MINB) k
     constexpr int SNL = NLS, S_B_BUF_B = Cfg::B_BUF_B, S_SG = Cfg::SG, S_SH = Cfg::SH, S_STG_BYTES = Cfg::STG_BYTES;
     constexpr int S_INFO_BYTES = Cfg::INFO_BYTES, S_TM_A0 = Cfg::TM_A0, EWS = Cfg::EWS, STHREADS = Cfg::THREADS;
     extern __shared__ uint8_t smem_raw[];
-    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t *smem = smem_align1024(smem_raw);
     uint8_t *sB = smem;
     float *stg = reinterpret_cast<float *>(sB + 2 * S_B_BUF_B);
     long long *lbase = reinterpret_cast<long long *>(sB + 2 * S_B_BUF_B + S_STG_BYTES);
-    int *llen = reinterpret_cast<int *>(lbase + SNL);
+    long long *lgoff = lbase + SNL;
+    int *llen = reinterpret_cast<int *>(lgoff + SNL);
     uint64_t *bars = reinterpret_cast<uint64_t *>(sB + 2 * S_B_BUF_B + S_STG_BYTES + S_INFO_BYTES);
     uint64_t *b_full = bars + 1 /* [2] */, *mma_done = bars + 3;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 4);
@@ -407,8 +409,11 @@ __global__ void __launch_bounds__(SmallCfg<NLS>::THREADS, SmallCfg<NLS>::MINB) k
     if ((int)threadIdx.x < SNL) {
         const int ql = chunk * SNL + threadIdx.x;
         const int qq = ql < p.nseq ? ql : 0;
-        lbase[threadIdx.x] = (long long)(qq / p.q2) * p.s_outer + (long long)(qq % p.q2) * p.s_inner;
-        llen[threadIdx.x] = ql < p.nseq ? min(max(p.lens ? p.lens[ql] : p.T, 0), p.T) : 0;
+        const long long lb = (long long)(qq / p.q2) * p.s_outer + (long long)(qq % p.q2) * p.s_inner;
+        const int ln = ql < p.nseq ? min(max(p.lens ? p.lens[ql] : p.T, 0), p.T) : 0;
+        lbase[threadIdx.x] = lb;
+        llen[threadIdx.x] = ln;
+        lgoff[threadIdx.x] = (lb + (long long)(dir ? max(ln - 1, 0) : 0) * p.step) * GC;      // gx element of the line's first time step
     }
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(Cfg::TM_ALLOC) : "memory");
@@ -488,14 +493,25 @@ __global__ void __launch_bounds__(SmallCfg<NLS>::THREADS, SmallCfg<NLS>::MINB) k
         const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(S_LPW * sw);
         const float act_k = g == 2 ? 2.f : 1.f;
 
+        // gx of this thread's gate row for its 16 lines, fetched one time step ahead (the loads have a whole step to land)
+        const long long gstride = (long long)(dir ? -1 : 1) * p.step * GC;
+        float gxn[S_LPW];
+#pragma unroll
+        for (int i = 0; i < S_LPW; ++i) {
+            const int l = S_LPW * sw + i;
+            gxn[i] = (uvalid && 0 < llen[l]) ? __ldg(gx0 + lgoff[l]) : 0.f;
+        }
         for (int s = 0; s < maxlen; ++s) {
             const int nxt = (s + 1) & 1;
             float gxv[S_LPW];
+            {
+                const float *gs = gx0 + (long long)(s + 1) * gstride;
 #pragma unroll
-            for (int i = 0; i < S_LPW; ++i) {
-                const int l = S_LPW * sw + i, len = llen[l];
-                const int t = dir ? len - 1 - s : s;
-                gxv[i] = (uvalid && s < len) ? __ldg(gx0 + (size_t)(lbase[l] + (long long)t * p.step) * GC) : 0.f;
+                for (int i = 0; i < S_LPW; ++i) {
+                    const int l = S_LPW * sw + i;
+                    gxv[i] = gxn[i];
+                    gxn[i] = (uvalid && s + 1 < llen[l]) ? __ldg(gs + lgoff[l]) : 0.f;
+                }
             }
             mbar_wait(mma_done, (uint32_t)(s & 1));
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");

@@ -283,6 +283,9 @@ FUSE_SPECS = [
     ('[1,16,0,1 Cr3,3,8 Mp2,2 Cr3,3,32 Cr3,9,32 Mp2,2 S1(1x0)1,3 Lfx24 O1c7]', 16, (513,)),         # Cin 8 -> FFMA, then conv_tc chain
     ('[1,16,0,1 Cr3,3,64 Mp2,2 Cr3,3,64 Cr3,5,128 Mp2,2 S1(1x0)1,3 O1c9]', 16, (300, 131)),          # conv_tc with 2 input chunks, Cout 128
     ('[1,12,0,1 Cr3,3,32 Mp2,2 Cr3,3,256 Cr3,3,256 Ct1,1,64 S1(1x0)1,3 O1c5]', 12, (260,)),           # 8 input chunks, 2 output-channel tiles
+    ('[1,16,0,1 Cr3,3,32 Gn8 Cr3,3,32 Gn4 Mp2,2 S1(1x0)1,3 Lbx40 O1c11]', 16, (301, 77)),            # GN -> conv_tc planes, GN ragged
+    ('[1,8,0,1 Cr3,3,48 Gn3 S1(1x0)1,3 Lbx40 O1c11]', 8, (150,)),                                    # GN with 12 channel quads -> GEMM planes
+    ('[1,8,0,1 Cr3,3,6 Gn2 Cr3,3,32 Gn32 Mp2,2 S1(1x0)1,3 O1c11]', 8, (90,)),                         # scalar GN fallback (C % 4 != 0), G == C
 ]
 
 
