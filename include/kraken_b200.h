@@ -141,13 +141,17 @@ int  kb_segment(kb_model *m, const float *pages, int pages_on_device, int32_t n,
 /* output of leaf layer `name` from the most recent forward on this handle, as NCHW host fp32.
  * dims_only != 0: only fills dims.  Valid until the next call on the handle.                        */
 int  kb_debug_layer_output(kb_model *m, const char *name, int32_t dims[4], float *out_host, int dims_only);
-/* C[M][N] = A[M][K] * B[N][K]^T + bias through the engine's GEMM kernels (use_tc: 1 = tcgen05 3xTF32 kernel,
+/* C[M][N] = A[M][K] * B[N][K]^T + bias through the engine's GEMM kernels (use_tc: 1 = tcgen05 split-fp16 kernel,
  * 0 = CUDA-core fp32 kernel); host pointers.  Unit-test hook for the kernels behind Linear / LSTM projection.   */
 int  kb_debug_gemm(const float *a, const float *b, const float *bias, float *c, int32_t M, int32_t N, int32_t K,
                    int use_tc, int device);
 /* number of kernels this handle launched since creation / last reset (bench `gpu_launches`) */
 int64_t kb_launch_count(const kb_model *m);
 void    kb_reset_launch_count(kb_model *m);
+/* The tensor-core layers read activations as two fp16 operand planes (22 significand bits, |x| <= 65504).  A call in
+ * which an activation left that range is transparently repeated on the fp32 CUDA-core kernels; this counts those
+ * repeats since creation (0 for every sane model; a persistent non-zero rate means KB_GEMM=ffma is the better mode). */
+int64_t kb_range_fallback_count(const kb_model *m);
 /* device-side stage timing of the most recent compute call on this handle.  With kb_set_timing(m, 1) every
  * stage (one per leaf layer; LSTMs as "<name>.xproj" + "<name>.rec"; "stage_in", "decode", "emit",
  * "upsample_sigmoid") is bracketed by CUDA events on the launching stream.  kb_timing_count() returns the number

@@ -65,6 +65,7 @@ _SIGS = {
     'kb_debug_layer_output': (C.c_int, [_vp, C.c_char_p, _pi32, _vp, C.c_int]),
     'kb_debug_gemm': (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, C.c_int, C.c_int]),
     'kb_launch_count': (_i64, [_vp]),
+    'kb_range_fallback_count': (_i64, [_vp]),
     'kb_reset_launch_count': (None, [_vp]),
     'kb_set_timing': (C.c_int, [_vp, C.c_int]),
     'kb_timing_count': (C.c_int, [_vp]),

@@ -1,23 +1,23 @@
 // conv_tc.cuh - tcgen05 implicit-GEMM convolution (Cin a multiple of 32, stride 1, no dilation) with fused epilogue for sm_100a.
 //
-//   ActConv2D -> [Dropout] -> [MaxPool 2x2/2] -> [Dropout] -> [Reshape S1(1x0)1,3] -> (TF32 planes for the LSTM projection)
+//   ActConv2D -> [Dropout] -> [MaxPool 2x2/2] -> [Dropout] -> [Reshape S1(1x0)1,3] -> (fp16 planes for the next tensor-core layer)
 //   kraken/lib/vgsl/layers.py:842-852, 381-388, 313-335
 //
 // Work item = one image n, one PAIR of output rows (h0, h0+1), 128 output columns, one tile of <= 128 output channels.  In
-// NHWC a 32-channel chunk of one pixel is exactly one 128-byte swizzle row, so the im2col matrix never exists (for Cin > 32
-// the item loops over the 32-channel chunks, re-using the row buffers and accumulating into the same TMEM columns):
-//   * TMA (4-D tensor map C,W,H,N; box 32 x (128+kw-1) x 1 x 1, 128B swizzle) brings the kh+1 input rows a row pair
+// NHWC fp16 planes a 32-channel chunk of one pixel is exactly one 64-byte swizzle row, so the im2col matrix never exists (for
+// Cin > 32 the item loops over the 32-channel chunks, re-using the row buffers and accumulating into the same TMEM columns):
+//   * TMA (4-D tensor map C,W,H,N; box 32 x (128+kw-1) x 1 x 1, 64B swizzle) brings the kh+1 input rows a row pair
 //     needs into shared memory ONCE; out-of-bounds coordinates are zero-filled by the TMA unit = the conv's zero padding
 //   * the A operand of tap (ky, kx) for output row r is the row buffer (ky + r) with its UMMA descriptor start address
-//     advanced by kx pixel rows (128 B each).  Measured on B200: the 128B-swizzle XOR is taken from the ABSOLUTE shared-
-//     memory address bits [7:9], exactly as TMA wrote it, so a descriptor may start at any 128-byte row of a 1024-byte
-//     aligned buffer with base_offset = 0 (setting base_offset = kx gives garbage - tests/gpu_fuse_debug.py)
-//   * B operand = the tap's [Cout][32] weight slice, streamed through a 3-stage TMA ring
-//   * 3xTF32 split as in gemm_tc.cuh: per tap and K=8 step  corr += a_lo*b_hi + a_hi*b_lo ; main += a_hi*b_hi, for both
+//     advanced by kx pixel rows (64 B each).  Measured on B200 (with 128-byte rows in round 1a, tests/gpu_fuse_debug.py): the
+//     swizzle XOR is taken from the ABSOLUTE shared-memory address bits, exactly as TMA wrote it, so a descriptor may start
+//     at any pixel row of an aligned buffer with base_offset = 0 (setting base_offset = kx gives garbage)
+//   * B operand = the tap's [Cout][32] weight slice, streamed through a 4-stage TMA ring
+//   * split fp16 operands as in gemm_tc.cuh: per tap and K=16 step  corr += a2s*b1 + a1*b2s ; main += a1*b1, for both
 //     output rows -> 4 TMEM accumulators of Cout columns (two sets when 8*Cout <= 512, so the epilogue overlaps the MMAs)
 //   * epilogue: one thread = one output column of the tile and holds BOTH rows -> the vertical half of the 2x2 max-pool is
 //     a register max, the horizontal half one shuffle; bias/activation; the store is strided so that the `S` fold
-//     (h into the feature axis) costs nothing; optional TF32 hi/lo planes for the consumer GEMM.
+//     (h into the feature axis) costs nothing; optional fp16 planes for the consumer.
 #pragma once
 #include "gemm_tc.cuh"
 
@@ -27,12 +27,13 @@ namespace ctc {
 using namespace kb::tc;
 
 constexpr int TW = 128;                  // output columns per work item
-constexpr int MAX_STB = 3;               // weight-tile ring stages (3 for channel tiles <= 64, 2 for 128)
+constexpr int MAX_STB = 4;               // weight-tile ring stages
+constexpr int PIX_B = 64;                // bytes of one pixel row of a plane: 32 channels x fp16
 constexpr int CTHREADS = 192;
 constexpr int MAX_ROWS = 8;              // kh + 1 <= 8
 
 struct ConvTcParams {
-    const float *bias; float *y; float *y_hi; float *y_lo;
+    const float *bias; float *y; __half *y_hi; __half *y_lo; int *flag;
     int N, Ho, Wo, Cout, kh, kw, py, px, act, pool;
     int items_h, items_w, items_c;       // row pairs, column segments, output-channel tiles
     int NC, CT, nstb;                    // 32-channel input chunks, output channels per tile, weight ring stages
@@ -55,7 +56,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ C
     const int R = p.kh + 1;
     const int a_plane = p.a_row_bytes, a_row = 2 * a_plane;              // hi | lo
     const int CT = p.CT, NSTB = p.nstb;
-    const int b_plane = CT * 128, b_stage = 2 * b_plane;
+    const int b_plane = CT * PIX_B, b_stage = 2 * b_plane;
     uint8_t *a_base = smem, *b_base = smem + R * a_row;
     uint64_t *bars = reinterpret_cast<uint64_t *>(b_base + NSTB * b_stage);
     uint64_t *full_a = bars, *empty_a = bars + MAX_ROWS, *full_b = bars + 2 * MAX_ROWS, *empty_b = full_b + MAX_STB;
@@ -64,7 +65,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ C
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nitems = p.N * p.items_h * p.items_w * p.items_c;
-    const uint32_t a_tx = (uint32_t)(2 * (TW + p.kw - 1) * 128), b_tx = (uint32_t)b_stage;
+    const uint32_t a_tx = (uint32_t)(2 * (TW + p.kw - 1) * PIX_B), b_tx = (uint32_t)b_stage;
 
     if (threadIdx.x == 0) {
         for (int r = 0; r < R; ++r) { mbar_init(&full_a[r], 1); mbar_init(&empty_a[r], 1); }
@@ -114,7 +115,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ C
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
-        const uint32_t idesc = idesc_tf32(128, CT);
+        const uint32_t idesc = idesc_f16(0, 0, 128, CT);
         uint32_t a_phase = 0; int bs = 0; uint32_t b_phase = 0; int acc = 0; uint32_t acc_phase = 0;
         for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
             mbar_wait(&tempty[acc], acc_phase ^ 1);
@@ -129,19 +130,19 @@ k_conv_tc(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ C
                         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                         if (elect_one()) {
                             const uint32_t sb = smem_u32(b_base + bs * b_stage);
-                            const uint64_t b_hi = umma_desc_sw128(sb), b_lo = umma_desc_sw128(sb + b_plane);
+                            const uint64_t b_hi = umma_desc_sw64(sb), b_lo = umma_desc_sw64(sb + b_plane);
                             const bool first = (cc | ky | kx) == 0;
 #pragma unroll
                             for (int r = 0; r < 2; ++r) {
-                                const uint32_t sa = smem_u32(a_base + (ky + r) * a_row) + (uint32_t)kx * 128u;
-                                const uint64_t a_hi = umma_desc_sw128(sa), a_lo = umma_desc_sw128(sa + a_plane);
+                                const uint32_t sa = smem_u32(a_base + (ky + r) * a_row) + (uint32_t)(kx * PIX_B);
+                                const uint64_t a_hi = umma_desc_sw64(sa), a_lo = umma_desc_sw64(sa + a_plane);
                                 const uint32_t d_main = d0 + (uint32_t)(2 * r * CT), d_corr = d_main + (uint32_t)CT;
 #pragma unroll
-                                for (int k = 0; k < 4; ++k) {
+                                for (int k = 0; k < 2; ++k) {                     // 32 channels = 2 x K16
                                     const uint64_t adv = (uint64_t)((k * 32) >> 4);
-                                    umma_tf32(d_corr, a_lo + adv, b_hi + adv, idesc, (first && k == 0) ? 0u : 1u);
-                                    umma_tf32(d_corr, a_hi + adv, b_lo + adv, idesc, 1u);
-                                    umma_tf32(d_main, a_hi + adv, b_hi + adv, idesc, (first && k == 0) ? 0u : 1u);
+                                    umma_f16(d_corr, a_lo + adv, b_hi + adv, idesc, (first && k == 0) ? 0u : 1u);
+                                    umma_f16(d_corr, a_hi + adv, b_lo + adv, idesc, 1u);
+                                    umma_f16(d_main, a_hi + adv, b_hi + adv, idesc, (first && k == 0) ? 0u : 1u);
                                 }
                             }
                             umma_commit(&empty_b[bs]);
@@ -164,6 +165,8 @@ k_conv_tc(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ C
         // ===================== epilogue (warps 2..5): thread = output column of the tile, both rows =====================
         const int q = warp & 3;
         int acc = 0; uint32_t acc_phase = 0;
+        bool bad = false;
+        constexpr float RS = 1.f / X2_SCALE;
         for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
             const int ct = item % p.items_c; const int rest = item / p.items_c;
             const int ws = rest % p.items_w, hp = (rest / p.items_w) % p.items_h, n = rest / (p.items_w * p.items_h);
@@ -180,11 +183,11 @@ k_conv_tc(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ C
                     tmem_ld32(lane_base + (uint32_t)c0, v0);
                     tmem_ld32(lane_base + (uint32_t)(CT + c0), t);
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) v0[j] += t[j];
+                    for (int j = 0; j < 32; ++j) v0[j] = fmaf(t[j], RS, v0[j]);
                     tmem_ld32(lane_base + (uint32_t)(2 * CT + c0), v1);
                     tmem_ld32(lane_base + (uint32_t)(3 * CT + c0), t);
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) v1[j] += t[j];
+                    for (int j = 0; j < 32; ++j) v1[j] = fmaf(t[j], RS, v1[j]);
                 }
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
@@ -202,15 +205,12 @@ k_conv_tc(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ C
                     if ((lane & 1) == 0 && hp < p.out_h && wp < p.out_w) {
                         const size_t off = (size_t)((long long)n * p.sN + (long long)hp * p.sH + (long long)wp * p.sW) + cbase + c0;
 #pragma unroll
-                        for (int j = 0; j < 32; j += 4) {
-                            if (p.y) *reinterpret_cast<float4 *>(p.y + off + j) = make_float4(v0[j], v0[j + 1], v0[j + 2], v0[j + 3]);
-                            if (p.y_hi) {
-                                float h[4], l[4];
-#pragma unroll
-                                for (int e = 0; e < 4; ++e) { uint32_t tt; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(tt) : "f"(v0[j + e])); h[e] = __uint_as_float(tt); l[e] = v0[j + e] - h[e]; }
-                                *reinterpret_cast<float4 *>(p.y_hi + off + j) = make_float4(h[0], h[1], h[2], h[3]);
-                                *reinterpret_cast<float4 *>(p.y_lo + off + j) = make_float4(l[0], l[1], l[2], l[3]);
+                        for (int j = 0; j < 32; j += 8) {
+                            if (p.y) {
+                                *reinterpret_cast<float4 *>(p.y + off + j) = make_float4(v0[j], v0[j + 1], v0[j + 2], v0[j + 3]);
+                                *reinterpret_cast<float4 *>(p.y + off + j + 4) = make_float4(v0[j + 4], v0[j + 5], v0[j + 6], v0[j + 7]);
                             }
+                            if (p.y_hi) store_planes8(p.y_hi + off + j, p.y_lo + off + j, v0 + j, bad);
                         }
                     }
                 } else {
@@ -221,15 +221,12 @@ k_conv_tc(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ C
                             const size_t off = (size_t)((long long)n * p.sN + (long long)ho * p.sH + (long long)wcol * p.sW) + cbase + c0;
                             const float *v = r ? v1 : v0;
 #pragma unroll
-                            for (int j = 0; j < 32; j += 4) {
-                                if (p.y) *reinterpret_cast<float4 *>(p.y + off + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-                                if (p.y_hi) {
-                                    float h[4], l[4];
-#pragma unroll
-                                    for (int e = 0; e < 4; ++e) { uint32_t tt; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(tt) : "f"(v[j + e])); h[e] = __uint_as_float(tt); l[e] = v[j + e] - h[e]; }
-                                    *reinterpret_cast<float4 *>(p.y_hi + off + j) = make_float4(h[0], h[1], h[2], h[3]);
-                                    *reinterpret_cast<float4 *>(p.y_lo + off + j) = make_float4(l[0], l[1], l[2], l[3]);
+                            for (int j = 0; j < 32; j += 8) {
+                                if (p.y) {
+                                    *reinterpret_cast<float4 *>(p.y + off + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                                    *reinterpret_cast<float4 *>(p.y + off + j + 4) = make_float4(v[j + 4], v[j + 5], v[j + 6], v[j + 7]);
                                 }
+                                if (p.y_hi) store_planes8(p.y_hi + off + j, p.y_lo + off + j, v + j, bad);
                             }
                         }
                     }
@@ -241,6 +238,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ C
             if (p.acc_sets == 2) { if (++acc == 2) { acc = 0; acc_phase ^= 1; } }
             else acc_phase ^= 1;
         }
+        if (bad && p.flag) atomicOr(p.flag, 1);
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -250,27 +248,27 @@ k_conv_tc(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ C
     }
 }
 
-// NHWC fp32 activation [N][H][W][C] (C a multiple of 32) as a 4-D tensor map (C, W, H, N); box = 32 x box_w x 1 x 1, 128B swizzle, OOB -> 0
-inline bool make_map_nhwc(CUtensorMap *map, const float *base, uint64_t N, uint64_t H, uint64_t W, uint64_t C, uint32_t box_w) {
+// NHWC fp16 plane [N][H][W][C] (C a multiple of 32) as a 4-D tensor map (C, W, H, N); box = 32 x box_w x 1 x 1, 64B swizzle, OOB -> 0
+inline bool make_map_nhwc(CUtensorMap *map, const __half *base, uint64_t N, uint64_t H, uint64_t W, uint64_t C, uint32_t box_w) {
     PFN_encodeTiled enc = get_encode();
     if (!enc) return false;
     cuuint64_t dims[4] = {C, W, H, N};
-    cuuint64_t strides[3] = {C * sizeof(float), W * C * sizeof(float), H * W * C * sizeof(float)};
+    cuuint64_t strides[3] = {C * sizeof(__half), W * C * sizeof(__half), H * W * C * sizeof(__half)};
     cuuint32_t box[4] = {32, box_w, 1, 1};
     cuuint32_t estr[4] = {1, 1, 1, 1};
-    return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+    return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<__half *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 // output-channel tile and weight-ring depth for a layer; returns the dynamic shared memory the kernel needs
 inline size_t conv_tc_plan(int kh, int kw, int cout, int *ct_out, int *nstb_out, int *a_row_bytes) {
     const int ct = cout <= 128 ? cout : (cout % 128 == 0 ? 128 : (cout % 64 == 0 ? 64 : 32));
-    const int nstb = ct > 64 ? 2 : 3;
-    const int plane = ((TW + kw - 1) * 128 + 1023) & ~1023;
+    const int nstb = MAX_STB;
+    const int plane = ((TW + kw - 1) * PIX_B + 1023) & ~1023;
     if (ct_out) *ct_out = ct;
     if (nstb_out) *nstb_out = nstb;
     if (a_row_bytes) *a_row_bytes = plane;
-    return (size_t)(kh + 1) * 2 * plane + (size_t)nstb * 2 * ct * 128 + 512 + 1024;
+    return (size_t)(kh + 1) * 2 * plane + (size_t)nstb * 2 * ct * PIX_B + 512 + 1024;
 }
 
 }  // namespace ctc

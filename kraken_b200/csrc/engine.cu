@@ -32,7 +32,7 @@ struct CudaError : std::runtime_error { using std::runtime_error::runtime_error;
 
 struct Tensor {
     float *p = nullptr; int64_t n = 0, h = 0, w = 0, c = 0;
-    float *hi = nullptr, *lo = nullptr;      // optional TF32 split planes written by a fused producer (same layout as p)
+    __half *hi = nullptr, *lo = nullptr;     // optional fp16 operand planes (x1, x2s) written by a fused producer (same layout as p)
     int64_t numel() const { return n * h * w * c; }
 };
 
@@ -43,8 +43,8 @@ struct LeafWeights {
     float *wt = nullptr;    // [K][Ncp]  conv/linear/lstm-x projection
     float *bias = nullptr;  // [Cout] / folded LSTM bias / GN beta
     float *aux = nullptr;   // W_hh [dirs][4h][h] / GN gamma
-    float *b_hi = nullptr, *b_lo = nullptr;   // [ncols][K] TF32 split planes for the tcgen05 GEMM (K-major)
-    float *c_hi = nullptr, *c_lo = nullptr;   // [tap][Cout][32] TF32 split planes for the tcgen05 convolution
+    __half *b_hi = nullptr, *b_lo = nullptr;  // [ncols][K] fp16 operand planes for the tcgen05 GEMM (K-major)
+    __half *c_hi = nullptr, *c_lo = nullptr;  // [tap][chunk][Cout][32] fp16 operand planes for the tcgen05 convolution
     void *wpk = nullptr;                      // W_hh as pre-swizzled bf16x3 UMMA tiles [dir][rank][split][k-atom][128][64] (tcgen05 recurrence)
     int ncp = 0, K = 0, ncols = 0;
 };
@@ -84,7 +84,11 @@ struct kb_model {
     int sm_count = 148;
     int max_clusters8 = -1;          // co-resident 8-CTA clusters of the recurrence kernel (queried once)
     int fuse_mask = 3;               // bit 0: stencil+pool group, bit 1: tcgen05 conv group
-    bool keep_fp32 = false;          // KB_KEEP_FP32=1: fused producers also write the fp32 tensor their TF32-plane consumer ignores (taps)
+    bool keep_fp32 = false;          // KB_KEEP_FP32=1: fused producers also write the fp32 tensor their plane-only consumer ignores (taps)
+    int *d_flag = nullptr;           // device: set by plane producers when an activation leaves the fp16 range
+    int *h_flag = nullptr;           // pinned copy, valid after the stream is synchronised
+    bool force_ffma = false;         // second attempt of a call whose first attempt raised the flag: fp32 CUDA-core kernels only
+    int64_t overflow_reruns = 0;
     bool fuse = true;                // fused layer groups (KB_FUSE=0 runs every layer on its own, e.g. for layer taps)
     bool use_tc = true;              // tcgen05 GEMM path (KB_GEMM=ffma forces the CUDA-core kernel)
     ~kb_model() {
@@ -93,6 +97,7 @@ struct kb_model {
             for (void *p : dev_allocs) cudaFree(p);
             if (arena.base) cudaFree(arena.base);
             if (pinned) cudaFreeHost(pinned);
+            if (h_flag) cudaFreeHost(h_flag);
             for (auto &e : stages) { if (e.a) cudaEventDestroy(e.a); if (e.b) cudaEventDestroy(e.b); }
         }
     }
@@ -140,16 +145,28 @@ static float *upload(kb_model *m, const std::vector<float> &h) {
     return d;
 }
 
-static inline float tf32_rna(float x) {
-    uint32_t u; memcpy(&u, &x, 4);
-    u = (u + 0x00001000u) & 0xFFFFE000u;         // round-to-nearest (ties away) on the magnitude bits == cvt.rna.tf32.f32
-    float r; memcpy(&r, &u, 4); return r;
+// host-side split of weights into the two fp16 operand planes (kernels.cuh split_f16); false if a value leaves the fp16 range
+static bool split_planes_host(const std::vector<float> &v, std::vector<__half> &hi, std::vector<__half> &lo) {
+    hi.resize(v.size()); lo.resize(v.size());
+    for (size_t i = 0; i < v.size(); ++i) {
+        if (!(std::fabs(v[i]) <= 65504.f)) return false;
+        const __half h1 = __float2half_rn(v[i]);
+        hi[i] = h1; lo[i] = __float2half_rn((v[i] - __half2float(h1)) * X2_SCALE);
+    }
+    return true;
 }
-// rows[N][K] (K contiguous) -> device hi / lo planes
+static __half *upload_half(kb_model *m, const std::vector<__half> &h) {
+    __half *d = nullptr;
+    CK(cudaMalloc(&d, std::max<size_t>(h.size(), 1) * sizeof(__half)));
+    m->dev_allocs.push_back(d);
+    if (!h.empty()) CK(cudaMemcpy(d, h.data(), h.size() * sizeof(__half), cudaMemcpyHostToDevice));
+    return d;
+}
+// rows[N][K] (K contiguous) -> device operand planes; a layer whose weights do not fit fp16 keeps the CUDA-core kernel
 static void upload_split(kb_model *m, const std::vector<float> &rows, LeafWeights &w) {
-    std::vector<float> hi(rows.size()), lo(rows.size());
-    for (size_t i = 0; i < rows.size(); ++i) { hi[i] = tf32_rna(rows[i]); lo[i] = rows[i] - hi[i]; }
-    w.b_hi = upload(m, hi); w.b_lo = upload(m, lo);
+    std::vector<__half> hi, lo;
+    if (!split_planes_host(rows, hi, lo)) { w.b_hi = w.b_lo = nullptr; return; }
+    w.b_hi = upload_half(m, hi); w.b_lo = upload_half(m, lo);
 }
 
 static void finalize_weights(kb_model *m) {
@@ -158,7 +175,7 @@ static void finalize_weights(kb_model *m) {
     for (size_t li = 0; li < m->plan->leaf_nodes.size(); ++li) {
         const Node &n = *m->plan->leaf_nodes[li];
         LeafWeights &w = m->lw[li];
-        w.wt = w.bias = w.aux = w.b_hi = w.b_lo = w.c_hi = w.c_lo = nullptr; w.wpk = nullptr;
+        w.wt = w.bias = w.aux = nullptr; w.b_hi = w.b_lo = w.c_hi = w.c_lo = nullptr; w.wpk = nullptr;
         auto need = [&](int slots) {
             for (int s = 0; s < slots; ++s)
                 if ((int)w.loaded.size() <= s || !w.loaded[s]) throw SpecError("weights of layer " + n.name + " not loaded (missing tensor for nn." + n.path + ")");
@@ -177,9 +194,9 @@ static void finalize_weights(kb_model *m) {
             if (n.kh == 1 && n.kw == 1) upload_split(m, src, w);          // [Cout][Cin] is already K-major
             if (n.cin % 32 == 0 && n.sy == 1 && n.sx == 1 && n.dy == 1 && n.dx == 1 && n.cout % 32 == 0 && n.kh + 1 <= ctc::MAX_ROWS &&
                 n.kh * n.kw > 1) {
-                // tcgen05 convolution operand: [tap][32-channel chunk][Cout][32] TF32 hi/lo planes
+                // tcgen05 convolution operand: [tap][32-channel chunk][Cout][32] fp16 planes
                 const int nc = n.cin / 32;
-                std::vector<float> taps((size_t)n.kh * n.kw * nc * n.cout * 32), hi(taps.size()), lo(taps.size());
+                std::vector<float> taps((size_t)n.kh * n.kw * nc * n.cout * 32);
                 for (int ky = 0; ky < n.kh; ++ky)
                     for (int kx = 0; kx < n.kw; ++kx)
                         for (int cc = 0; cc < nc; ++cc)
@@ -187,8 +204,8 @@ static void finalize_weights(kb_model *m) {
                                 for (int ci = 0; ci < 32; ++ci)
                                     taps[((((size_t)(ky * n.kw + kx) * nc + cc) * n.cout) + co) * 32 + ci] =
                                         src[(((size_t)co * n.cin + cc * 32 + ci) * n.kh + ky) * n.kw + kx];
-                for (size_t i = 0; i < taps.size(); ++i) { hi[i] = tf32_rna(taps[i]); lo[i] = taps[i] - hi[i]; }
-                w.c_hi = upload(m, hi); w.c_lo = upload(m, lo);
+                std::vector<__half> hi, lo;
+                if (split_planes_host(taps, hi, lo)) { w.c_hi = upload_half(m, hi); w.c_lo = upload_half(m, lo); }
             }
         } else if (n.kind == K_LINEAR) {
             need(2);
@@ -253,7 +270,7 @@ static void finalize_weights(kb_model *m) {
                                 const __half x1 = __float2half_rn(x);
                                 const size_t o = ((((size_t)d * 8 + r) * 2) * 128 + mrow) * 256 + kp;
                                 pk[o] = __half_as_ushort(x1);
-                                pk[o + (size_t)128 * 256] = __half_as_ushort(__float2half_rn((x - __half2float(x1)) * ltc::X2_SCALE));
+                                pk[o + (size_t)128 * 256] = __half_as_ushort(__float2half_rn((x - __half2float(x1)) * X2_SCALE));
                             }
                         }
                 }
@@ -274,7 +291,7 @@ static void finalize_weights(kb_model *m) {
                                 const __half x1 = __float2half_rn(x);
                                 const size_t o = (((size_t)d * 2) * 128 + (size_t)(4 * u + gate)) * 32 + u2;
                                 pk[o] = __half_as_ushort(x1);
-                                pk[o + (size_t)128 * 32] = __half_as_ushort(__float2half_rn((x - __half2float(x1)) * ltc::X2_SCALE));
+                                pk[o + (size_t)128 * 32] = __half_as_ushort(__float2half_rn((x - __half2float(x1)) * X2_SCALE));
                             }
                 }
                 void *dp = nullptr;
@@ -313,27 +330,48 @@ struct Exec {
         if (!m->use_tc || !w.b_hi) return false;
         if (conv && (conv->kh != 1 || conv->kw != 1 || conv->sy != 1 || conv->sx != 1)) return false;
         const long long M = (long long)x.n * x.h * x.w;
-        return (w.K % 4) == 0 && w.K >= 32 && w.ncols >= 64 && M >= 128;
+        return (w.K % 8) == 0 && w.K >= 32 && w.ncols >= 64 && M >= 128;        // K % 8: 16-byte row pitch of the fp16 planes (TMA)
     }
     void gemm_tc(const Tensor &x, const LeafWeights &w, int act, float *y) {
         const long long M = (long long)x.n * x.h * x.w;
         const int K = w.K, N = w.ncols;
-        float *a_hi = x.hi, *a_lo = x.lo;
+        __half *a_hi = x.hi, *a_lo = x.lo;
         if (!a_hi) {
-            a_hi = (float *)m->arena.alloc((size_t)M * K * sizeof(float));
-            a_lo = (float *)m->arena.alloc((size_t)M * K * sizeof(float));
+            a_hi = (__half *)m->arena.alloc((size_t)M * K * sizeof(__half));
+            a_lo = (__half *)m->arena.alloc((size_t)M * K * sizeof(__half));
         }
         if (dry) return;
-        if (!x.hi) LAUNCH(m, tc::k_split_tf32, grid1d(M * K / 4, 256, m->sm_count), 256, 0, st, x.p, a_hi, a_lo, M * K / 4);
+        if (!x.hi) LAUNCH(m, tc::k_split_f16, grid1d(M * K / 4, 256, m->sm_count), 256, 0, st, x.p, a_hi, a_lo, M * K / 4, m->d_flag);
         CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
-        if (!tc::make_map_2d(&ta_hi, a_hi, (uint64_t)M, (uint64_t)K, tc::BM) || !tc::make_map_2d(&ta_lo, a_lo, (uint64_t)M, (uint64_t)K, tc::BM) ||
-            !tc::make_map_2d(&tb_hi, w.b_hi, (uint64_t)N, (uint64_t)K, tc::BN) || !tc::make_map_2d(&tb_lo, w.b_lo, (uint64_t)N, (uint64_t)K, tc::BN))
+        if (!tc::make_map_2d(&ta_hi, a_hi, (uint64_t)M, (uint64_t)K, tc::BM, tc::BK) || !tc::make_map_2d(&ta_lo, a_lo, (uint64_t)M, (uint64_t)K, tc::BM, tc::BK) ||
+            !tc::make_map_2d(&tb_hi, w.b_hi, (uint64_t)N, (uint64_t)K, tc::BN / 2, tc::BK) || !tc::make_map_2d(&tb_lo, w.b_lo, (uint64_t)N, (uint64_t)K, tc::BN / 2, tc::BK))
             throw CudaError("cuTensorMapEncodeTiled failed");
         static bool attr_set = false;
-        if (!attr_set) { CK(cudaFuncSetAttribute(tc::k_gemm_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES)); attr_set = true; }
+        if (!attr_set) {
+            CK(cudaFuncSetAttribute(tc::k_gemm_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
+            CK(cudaFuncSetAttribute(tc::k_gemm_tc<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
+            attr_set = true;
+        }
         tc::GemmTcParams gp; gp.c = y; gp.bias = w.bias; gp.M = (int)M; gp.N = N; gp.K = K; gp.ldc = N; gp.act = act;
-        const int ntiles = (int)((M + tc::BM - 1) / tc::BM) * ((N + tc::BN - 1) / tc::BN);
-        LAUNCH(m, tc::k_gemm_tc, (unsigned)std::min(ntiles, m->sm_count), tc::THREADS, tc::SMEM_BYTES, st, ta_hi, ta_lo, tb_hi, tb_lo, gp);
+        const int tiles_m = (int)((M + tc::BM - 1) / tc::BM), tiles_n = (N + tc::BN - 1) / tc::BN;
+        // KB_GEMM_MC=1: pairs of vertically adjacent tiles on 2-CTA clusters with the weight tile multicast (no gain measured)
+        const bool mc = tiles_m >= 2 && getenv("KB_GEMM_MC") && atoi(getenv("KB_GEMM_MC")) == 1;
+        if (mc) {
+            const int npairs = ((tiles_m + 1) / 2) * tiles_n;
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3((unsigned)(2 * std::min(npairs, std::max(1, m->sm_count / 2))), 1, 1);
+            cfg.blockDim = dim3(tc::THREADS, 1, 1);
+            cfg.dynamicSmemBytes = tc::SMEM_BYTES; cfg.stream = st;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+            cfg.attrs = at; cfg.numAttrs = 1;
+            CK(cudaLaunchKernelEx(&cfg, tc::k_gemm_tc<2>, ta_hi, ta_lo, tb_hi, tb_lo, gp));
+            ++m->launches;
+            CK(cudaPeekAtLastError());
+        } else {
+            LAUNCH(m, tc::k_gemm_tc<1>, (unsigned)std::min(tiles_m * tiles_n, m->sm_count), tc::THREADS, tc::SMEM_BYTES, st, ta_hi, ta_lo, tb_hi, tb_lo, gp);
+        }
     }
 
     void gemm(const Tensor &x, const LeafWeights &w, const Node *conv, int act, float *y, int64_t Ho, int64_t Wo) {
@@ -417,7 +455,7 @@ struct Exec {
             float2 *ab = vec4 ? (float2 *)m->arena.alloc((size_t)N * C * sizeof(float2)) : nullptr;
             const bool planes = vec4 && planes_hint;
             planes_hint = false;
-            if (planes) { y.hi = (float *)m->arena.alloc((size_t)y.numel() * 4); y.lo = (float *)m->arena.alloc((size_t)y.numel() * 4); }
+            if (planes) { y.hi = (__half *)m->arena.alloc((size_t)y.numel() * 2); y.lo = (__half *)m->arena.alloc((size_t)y.numel() * 2); }
             if (!dry && y.numel()) {
                 if (vec4) {
                     // float4 streaming passes (kernels.cuh k_gn_stats4 / k_gn_apply4); the apply pass also emits the TF32 planes a
@@ -427,7 +465,7 @@ struct Exec {
                     LAUNCH(m, k_gn_finalize, (unsigned)((N * G + 127) / 128), 128, 0, st, partial, stats, N, G, chunks, H, W, C, dl, 1e-5f);
                     LAUNCH(m, k_gn_coeffs, (unsigned)((N * C + 255) / 256), 256, 0, st, stats, w.aux, w.bias, ab, N, C, G);
                     const long long nb = std::min<long long>((npix + rows4 - 1) / rows4, std::max(1, 16 * sm / std::max(N, 1)));
-                    LAUNCH(m, k_gn_apply4, dim3((unsigned)nb, N), 256, 0, st, x.p, (planes && !m->keep_fp32) ? nullptr : y.p, y.hi, y.lo, ab, H, W, C, dl);
+                    LAUNCH(m, k_gn_apply4, dim3((unsigned)nb, N), 256, 0, st, x.p, (planes && !m->keep_fp32) ? nullptr : y.p, y.hi, y.lo, ab, H, W, C, dl, m->d_flag);
                 } else {
                     const int bt = rows * cthreads;
                     LAUNCH(m, k_gn_partial, dim3(chunks, N), bt, (size_t)bt * cpt * 2 * sizeof(double), st, x.p, partial, H, W, C, G, dl, chunks, rows, cthreads, cpt);
@@ -579,7 +617,7 @@ struct Exec {
         if ((nx->kind == K_LSTM && !nx->legacy) || nx->kind == K_LINEAR) {
             const LeafWeights &nw = m->lw[nx->leaf_index];
             const long long M = (long long)d.n * d.h * d.w;
-            return nw.b_hi && (d.c % 4) == 0 && d.c >= 32 && nw.ncols >= 64 && M >= 128 && !(nx->kind == K_LINEAR && nx->aug);
+            return nw.b_hi && (d.c % 8) == 0 && d.c >= 32 && nw.ncols >= 64 && M >= 128 && !(nx->kind == K_LINEAR && nx->aug);
         }
         return false;
     }
@@ -603,11 +641,11 @@ struct Exec {
             // a tensor-core conv right behind wants the TF32 planes
             const Node *nx = next_real(series, j + 1);
             const bool planes = m->use_tc && nx && nx->kind == K_CONV && tc_conv_eligible(*nx, dpool);
-            if (planes) { y.hi = (float *)m->arena.alloc((size_t)y.numel() * 4); y.lo = (float *)m->arena.alloc((size_t)y.numel() * 4); }
+            if (planes) { y.hi = (__half *)m->arena.alloc((size_t)y.numel() * 2); y.lo = (__half *)m->arena.alloc((size_t)y.numel() * 2); }
             if (!dry && y.numel()) {
                 StageTimer tt(m, st, c0.name + "+" + pl->name, true);
                 Conv1PoolParams cp;
-                cp.x = cur.p; cp.wt = w.wt; cp.bias = w.bias; cp.y = (planes && !m->keep_fp32) ? nullptr : y.p; cp.y_hi = y.hi; cp.y_lo = y.lo;
+                cp.x = cur.p; cp.wt = w.wt; cp.bias = w.bias; cp.y = (planes && !m->keep_fp32) ? nullptr : y.p; cp.y_hi = y.hi; cp.y_lo = y.lo; cp.flag = m->d_flag;
                 cp.N = (int)cur.n; cp.H = (int)cur.h; cp.W = (int)cur.w; cp.Cout = c0.cout; cp.Ncp = w.ncp; cp.kh = c0.kh; cp.kw = c0.kw;
                 cp.py = c0.py; cp.px = c0.px; cp.Hp = (int)dpool.h; cp.Wp = (int)dpool.w; cp.act = c0.act;
                 const int cgroups = c0.cout / 8, ppb = 256 / cgroups;
@@ -653,16 +691,16 @@ struct Exec {
         Tensor y = mk(dout);
         // consumer wants TF32 planes?  (another tensor-core conv, or an LSTM / Linear whose projection runs on k_gemm_tc)
         const bool planes = wants_planes(series, j, dout);
-        if (planes) { y.hi = (float *)m->arena.alloc((size_t)y.numel() * 4); y.lo = (float *)m->arena.alloc((size_t)y.numel() * 4); }
-        float *x_hi = cur.hi, *x_lo = cur.lo;
-        if (!x_hi) { x_hi = (float *)m->arena.alloc((size_t)cur.numel() * 4); x_lo = (float *)m->arena.alloc((size_t)cur.numel() * 4); }
+        if (planes) { y.hi = (__half *)m->arena.alloc((size_t)y.numel() * 2); y.lo = (__half *)m->arena.alloc((size_t)y.numel() * 2); }
+        __half *x_hi = cur.hi, *x_lo = cur.lo;
+        if (!x_hi) { x_hi = (__half *)m->arena.alloc((size_t)cur.numel() * 2); x_lo = (__half *)m->arena.alloc((size_t)cur.numel() * 2); }
         if (!dry && y.numel()) {
             std::string nm = c0.name; if (pl) nm += "+" + pl->name; if (fd) nm += "+" + fd->name;
             StageTimer tt(m, st, nm, true);
-            if (!cur.hi) LAUNCH(m, tc::k_split_tf32, grid1d(cur.numel() / 4, 256, m->sm_count), 256, 0, st, cur.p, x_hi, x_lo, (long long)(cur.numel() / 4));
+            if (!cur.hi) LAUNCH(m, tc::k_split_f16, grid1d(cur.numel() / 4, 256, m->sm_count), 256, 0, st, cur.p, x_hi, x_lo, (long long)(cur.numel() / 4), m->d_flag);
             const LeafWeights &w = m->lw[c0.leaf_index];
             ctc::ConvTcParams cp;
-            cp.bias = w.bias; cp.y = (planes && !m->keep_fp32) ? nullptr : y.p; cp.y_hi = y.hi; cp.y_lo = y.lo;
+            cp.bias = w.bias; cp.y = (planes && !m->keep_fp32) ? nullptr : y.p; cp.y_hi = y.hi; cp.y_lo = y.lo; cp.flag = m->d_flag;
             cp.N = (int)cur.n; cp.Ho = (int)dconv.h; cp.Wo = (int)dconv.w; cp.Cout = c0.cout; cp.kh = c0.kh; cp.kw = c0.kw; cp.py = c0.py; cp.px = c0.px;
             cp.act = c0.act; cp.pool = pl ? 1 : 0;
             cp.out_h = (int)dpost.h; cp.out_w = (int)dpost.w;
@@ -758,7 +796,7 @@ static ForwardResult forward_impl(kb_model *m, const float *x, int x_on_device, 
                                   cudaStream_t st, size_t extra_bytes) {
     const Plan &pl = *m->plan;
     const int C = pl.input[1];
-    { const char *e = getenv("KB_GEMM"); m->use_tc = !(e && strcmp(e, "ffma") == 0); }
+    { const char *e = getenv("KB_GEMM"); m->use_tc = !(e && strcmp(e, "ffma") == 0) && !m->force_ffma; }
     { const char *e = getenv("KB_KEEP_FP32"); m->keep_fp32 = e && strcmp(e, "0") != 0; }
     { const char *e = getenv("KB_FUSE"); m->fuse_mask = e ? atoi(e) : 3; m->fuse = m->fuse_mask != 0; }
     if (n <= 0 || h <= 0 || w <= 0) throw ShapeError("empty input batch");
@@ -808,10 +846,29 @@ static ForwardResult forward_impl(kb_model *m, const float *x, int x_on_device, 
         t.p = nhwc;
     } else t.p = const_cast<float *>(src);
     t_in.reset();
+    CK(cudaMemsetAsync(m->d_flag, 0, sizeof(int), st));
     Exec ex{m, st, false};
     ForwardResult r; r.lens = lens0;
     r.y = ex.run(*pl.root, t, r.lens);
+    CK(cudaMemcpyAsync(m->h_flag, m->d_flag, sizeof(int), cudaMemcpyDeviceToHost, st));
     return r;
+}
+
+// Runs `body` (forward + post-processing of one ABI call).  The tensor-core layers read fp16 operand planes; if any producer saw
+// an activation beyond the fp16 range it raised the device flag, and the whole call is repeated on the fp32 CUDA-core kernels
+// (still on the GPU: there is no CPU path).  The check needs the stream to be idle, which host-output calls are anyway.
+template <class F>
+static void run_with_range_fallback(kb_model *m, cudaStream_t st, F body) {
+    m->force_ffma = false;
+    body();
+    CK(cudaStreamSynchronize(st));
+    if (m->h_flag && *m->h_flag) {
+        if (getenv("KB_DEBUG")) fprintf(stderr, "[kb] activation outside the fp16 operand range: repeating the call on the fp32 CUDA-core kernels\n");
+        ++m->overflow_reruns;
+        m->force_ffma = true;
+        try { body(); CK(cudaStreamSynchronize(st)); } catch (...) { m->force_ffma = false; throw; }
+        m->force_ffma = false;
+    }
 }
 
 static void collect_timing(kb_model *m) {
@@ -1038,6 +1095,8 @@ int kb_model_finalize(kb_model *m, int device) {
             m->arena = Arena();
             if (m->pinned) cudaFreeHost(m->pinned);
             m->pinned = nullptr; m->pinned_cap = 0;
+            if (m->h_flag) cudaFreeHost(m->h_flag);
+            m->h_flag = nullptr;
             for (auto &e : m->stages) { if (e.a) cudaEventDestroy(e.a); if (e.b) cudaEventDestroy(e.b); }
             m->stages.clear(); m->n_stages = 0;
         }
@@ -1048,6 +1107,11 @@ int kb_model_finalize(kb_model *m, int device) {
         m->sm_count = prop.multiProcessorCount;
         m->device = device;
         finalize_weights(m);
+        CK(cudaMalloc((void **)&m->d_flag, sizeof(int)));
+        m->dev_allocs.push_back(m->d_flag);
+        CK(cudaMemset(m->d_flag, 0, sizeof(int)));
+        if (!m->h_flag) CK(cudaHostAlloc((void **)&m->h_flag, sizeof(int), cudaHostAllocDefault));
+        *m->h_flag = 0;
         m->finalized = true;
         return KB_OK;
     });
@@ -1063,13 +1127,14 @@ int kb_forward(kb_model *m, const float *x, int x_on_device, int32_t n, int32_t 
         cudaStream_t st = (cudaStream_t)stream;
         Dims d; d.n = n; d.c = m->plan->input[1]; d.h = h; d.w = w; Lens l;
         infer(*m->plan->root, d, l);
-        ForwardResult r = forward_impl(m, x, x_on_device, n, h, w, widths, st, out_on_device ? 0 : (size_t)(d.n * d.c * d.h * d.w) * 4 + 4096);
-        { StageTimer tt(m, st, "emit", true); emit_nchw(m, r.y, out, out_on_device, st); }
-        if (out_lens) {
-            if (r.lens.has) for (int i = 0; i < n; ++i) out_lens[i] = r.lens.v[i];
-            else for (int i = 0; i < n; ++i) out_lens[i] = (int32_t)r.y.w;
-        }
-        if (!out_on_device || m->timing) CK(cudaStreamSynchronize(st));
+        run_with_range_fallback(m, st, [&]() {
+            ForwardResult r = forward_impl(m, x, x_on_device, n, h, w, widths, st, out_on_device ? 0 : (size_t)(d.n * d.c * d.h * d.w) * 4 + 4096);
+            { StageTimer tt(m, st, "emit", true); emit_nchw(m, r.y, out, out_on_device, st); }
+            if (out_lens) {
+                if (r.lens.has) for (int i = 0; i < n; ++i) out_lens[i] = r.lens.v[i];
+                else for (int i = 0; i < n; ++i) out_lens[i] = (int32_t)r.y.w;
+            }
+        });
         collect_timing(m);
         return KB_OK;
     });
@@ -1091,25 +1156,27 @@ int kb_recognize(kb_model *m, const float *lines, int lines_on_device, int32_t n
             throw ShapeError("Expected dimension 3 to be 1, actual (" + std::to_string(d.n) + ", " + std::to_string(d.c) + ", " + std::to_string(d.h) + ", " + std::to_string(d.w) + ")");
         const int T = (int)d.w, C = (int)d.c;
         size_t extra = decode_bytes(n, T, max_out) + (probs && !probs_on_device ? (size_t)n * C * T * 4 + 4096 : 0);
-        ForwardResult r = forward_impl(m, lines, lines_on_device, n, h, w, widths, st, extra);
-        std::unique_ptr<StageTimer> t_dec(new StageTimer(m, st, "decode", true));
-        const long long rows = (long long)n * T;
-        int *d_lab = (int *)m->arena.alloc((size_t)rows * 4);
-        float *d_conf = (float *)m->arena.alloc((size_t)rows * 4);
-        LAUNCH(m, k_row_argmax_softmax, (unsigned)((rows + 7) / 8), 256, 0, st, r.y.p, rows, C, temperature, d_lab, d_conf);
         std::vector<int32_t> olens(n);
-        for (int i = 0; i < n; ++i) olens[i] = r.lens.has ? r.lens.v[i] : T;
-        int *d_lens = (int *)m->arena.alloc((size_t)n * 4);
-        CK(cudaMemcpyAsync(d_lens, olens.data(), (size_t)n * 4, cudaMemcpyHostToDevice, st));
-        if (probs) {
-            float *dp = probs_on_device ? probs : (float *)m->arena.alloc((size_t)n * C * T * 4);
-            const size_t smem = (size_t)32 * (C + 1) * 4;
-            if (smem <= 48 * 1024) LAUNCH(m, k_probs_nct, dim3((unsigned)((T + 31) / 32), (unsigned)n), 256, smem, st, r.y.p, dp, T, C, temperature);
-            else LAUNCH(m, k_probs_nct_simple, (unsigned)((rows + 7) / 8), 256, 0, st, r.y.p, dp, n, T, C, temperature);
-            if (!probs_on_device) CK(cudaMemcpyAsync(probs, dp, (size_t)n * C * T * 4, cudaMemcpyDeviceToHost, st));
-        }
-        decode_and_fetch(m, m->sm_count, n, T, max_out, d_lab, d_conf, d_lens, labels, starts, ends, confs, counts, st,
-                         m->arena, &m->pinned, &m->pinned_cap, &m->launches, t_dec.get());
+        run_with_range_fallback(m, st, [&]() {
+            ForwardResult r = forward_impl(m, lines, lines_on_device, n, h, w, widths, st, extra);
+            std::unique_ptr<StageTimer> t_dec(new StageTimer(m, st, "decode", true));
+            const long long rows = (long long)n * T;
+            int *d_lab = (int *)m->arena.alloc((size_t)rows * 4);
+            float *d_conf = (float *)m->arena.alloc((size_t)rows * 4);
+            LAUNCH(m, k_row_argmax_softmax, (unsigned)((rows + 7) / 8), 256, 0, st, r.y.p, rows, C, temperature, d_lab, d_conf);
+            for (int i = 0; i < n; ++i) olens[i] = r.lens.has ? r.lens.v[i] : T;
+            int *d_lens = (int *)m->arena.alloc((size_t)n * 4);
+            CK(cudaMemcpyAsync(d_lens, olens.data(), (size_t)n * 4, cudaMemcpyHostToDevice, st));
+            if (probs) {
+                float *dp = probs_on_device ? probs : (float *)m->arena.alloc((size_t)n * C * T * 4);
+                const size_t smem = (size_t)32 * (C + 1) * 4;
+                if (smem <= 48 * 1024) LAUNCH(m, k_probs_nct, dim3((unsigned)((T + 31) / 32), (unsigned)n), 256, smem, st, r.y.p, dp, T, C, temperature);
+                else LAUNCH(m, k_probs_nct_simple, (unsigned)((rows + 7) / 8), 256, 0, st, r.y.p, dp, n, T, C, temperature);
+                if (!probs_on_device) CK(cudaMemcpyAsync(probs, dp, (size_t)n * C * T * 4, cudaMemcpyDeviceToHost, st));
+            }
+            decode_and_fetch(m, m->sm_count, n, T, max_out, d_lab, d_conf, d_lens, labels, starts, ends, confs, counts, st,
+                             m->arena, &m->pinned, &m->pinned_cap, &m->launches, t_dec.get());
+        });
         if (out_lens) for (int i = 0; i < n; ++i) out_lens[i] = olens[i];
         collect_timing(m);
         return KB_OK;
@@ -1159,14 +1226,15 @@ int kb_segment(kb_model *m, const float *pages, int pages_on_device, int32_t n, 
         Dims d; d.n = n; d.c = m->plan->input[1]; d.h = h; d.w = w; Lens l;
         infer(*m->plan->root, d, l);
         const size_t out_elems = (size_t)n * d.c * out_h * out_w;
-        ForwardResult r = forward_impl(m, pages, pages_on_device, n, h, w, nullptr, st, heatmap_on_device ? 0 : out_elems * 4 + 4096);
-        std::unique_ptr<StageTimer> t_up(new StageTimer(m, st, "upsample_sigmoid", true));
-        float *dst = heatmap_on_device ? heatmap : (float *)m->arena.alloc(out_elems * 4);
-        LAUNCH(m, k_upsample_sigmoid, grid1d((long long)n * out_h * out_w, 256, m->sm_count), 256, 0, st, r.y.p, dst, (int)r.y.n, (int)r.y.h,
-               (int)r.y.w, (int)r.y.c, out_h, out_w);
-        if (!heatmap_on_device) CK(cudaMemcpyAsync(heatmap, dst, out_elems * 4, cudaMemcpyDeviceToHost, st));
-        t_up.reset();
-        if (!heatmap_on_device || m->timing) CK(cudaStreamSynchronize(st));
+        run_with_range_fallback(m, st, [&]() {
+            ForwardResult r = forward_impl(m, pages, pages_on_device, n, h, w, nullptr, st, heatmap_on_device ? 0 : out_elems * 4 + 4096);
+            std::unique_ptr<StageTimer> t_up(new StageTimer(m, st, "upsample_sigmoid", true));
+            float *dst = heatmap_on_device ? heatmap : (float *)m->arena.alloc(out_elems * 4);
+            LAUNCH(m, k_upsample_sigmoid, grid1d((long long)n * out_h * out_w, 256, m->sm_count), 256, 0, st, r.y.p, dst, (int)r.y.n, (int)r.y.h,
+                   (int)r.y.w, (int)r.y.c, out_h, out_w);
+            if (!heatmap_on_device) CK(cudaMemcpyAsync(heatmap, dst, out_elems * 4, cudaMemcpyDeviceToHost, st));
+            t_up.reset();
+        });
         collect_timing(m);
         return KB_OK;
     });
@@ -1215,13 +1283,16 @@ int kb_debug_gemm(const float *a, const float *b, const float *bias, float *c, i
         w.wt = upload(&tmp, wt);
         if (bias) w.bias = upload(&tmp, std::vector<float>(bias, bias + N));
         upload_split(&tmp, rows, w);
+        CK(cudaMalloc((void **)&tmp.d_flag, sizeof(int)));
+        tmp.dev_allocs.push_back(tmp.d_flag);
+        CK(cudaMemset(tmp.d_flag, 0, sizeof(int)));
         const size_t abytes = (size_t)M * K * 4, cbytes = (size_t)M * N * 4;
         CK(cudaMalloc((void **)&tmp.arena.base, 3 * abytes + cbytes + 65536)); tmp.arena.cap = 3 * abytes + cbytes + 65536;
         Tensor x; x.n = 1; x.h = 1; x.w = M; x.c = K; x.p = (float *)tmp.arena.alloc(abytes);
         float *dc = (float *)tmp.arena.alloc(cbytes);
         CK(cudaMemcpy(x.p, a, abytes, cudaMemcpyHostToDevice));
         Exec ex{&tmp, nullptr, false};
-        if (use_tc && !ex.tc_eligible(x, w, nullptr)) throw Unsupported("shape not eligible for the tcgen05 GEMM (need K % 4 == 0, K >= 32, N >= 64, M >= 128)");
+        if (use_tc && !ex.tc_eligible(x, w, nullptr)) throw Unsupported("shape not eligible for the tcgen05 GEMM (need K % 8 == 0, K >= 32, N >= 64, M >= 128)");
         ex.gemm(x, w, nullptr, ACT_LINEAR, dc, 1, M);
         CK(cudaDeviceSynchronize());
         CK(cudaMemcpy(c, dc, cbytes, cudaMemcpyDeviceToHost));
@@ -1231,6 +1302,7 @@ int kb_debug_gemm(const float *a, const float *b, const float *bias, float *c, i
 
 int64_t kb_launch_count(const kb_model *m) { return m ? m->launches : 0; }
 void kb_reset_launch_count(kb_model *m) { if (m) m->launches = 0; }
+int64_t kb_range_fallback_count(const kb_model *m) { return m ? m->overflow_reruns : 0; }
 int kb_set_timing(kb_model *m, int enabled) { if (!m) return fail(KB_ERR_ARG, "model is NULL"); m->timing = enabled != 0; return KB_OK; }
 int kb_timing_count(kb_model *m) {
     if (!m) return -1;

@@ -1,28 +1,32 @@
-// gemm_tc.cuh - tcgen05 / TMEM / TMA GEMM with fp32-grade accuracy ("3xTF32") for sm_100a.
+// gemm_tc.cuh - tcgen05 / TMEM / TMA GEMM with fp32-grade accuracy from split fp16 operands, for sm_100a.
 //
 //   C[M][N] = A[M][K] * B[N][K]^T + bias[N]          (A: activations, pixel-major; B: weights, K-major)
 //
 // Used for the LSTM input projection (K = 768 -> N = 2048 on cfg2, 50% of the path's FLOPs), the output Linear and
 // 1x1 convolutions.  CTC label sequences must match the fp32 reference bit for bit, and a single TF32/BF16 pass
-// flips arg-maxes, so every fp32 operand is split once into two TF32-exact terms
-//       x = hi + lo,   hi = rna_tf32(x),   lo = x - hi   (exact; |lo| <= 2^-11 |x|)
+// flips arg-maxes, so every fp32 operand is split once into two fp16 terms with a power-of-two scale on the second,
+//       x = x1 + x2s * 2^-11,   x1 = fp16(x),   x2s = fp16((x - x1) * 2^11)        (22 significand bits, |error| <= 2^-23 |x|)
 // and three tensor-core products are accumulated in fp32 in TMEM:
-//       main = a_hi*b_hi            corr = a_lo*b_hi + a_hi*b_lo            (dropped term a_lo*b_lo ~ 2^-22)
+//       main = a1*b1            corr = a2s*b1 + a1*b2s            C = main + corr * 2^-11     (dropped a2*b2 ~ 2^-22)
+// Rounds 1a/1b used TF32 planes (hi = rna_tf32(x), lo = x - hi): same 11+11 bit split, but kind::tf32 runs at a third of the
+// kind::f16 MAC rate (measured: 265 cycles per M128xN256xK8 tf32 MMA = 507 TFLOP/s; ncu showed the producer waiting on `empty`,
+// i.e. the kernel was MMA bound at "48 % tensor pipe active") and the planes were twice the bytes.  fp16 narrows the exponent
+// range: |x| must stay below 65504 (producers raise a device flag, the engine then re-runs the call on the fp32 CUDA-core
+// kernels) and values below 2^-14 keep an ABSOLUTE error of 2^-36 instead of a relative one.
 // The tensor core adds into its accumulator with round-toward-zero, a bias that grows linearly with the number of
 // accumulations into a LARGE accumulator (measured: 4.2e-6 relative at K = 768 with one accumulator vs 7.6e-7 for
-// fp32 FFMA).  Keeping the small correction products in their own accumulator (columns 256..511) cuts the chain
-// on the big one to K/8 and makes the correction's own rounding negligible; the epilogue adds the two in fp32 (RN).
-// The split planes live in HBM (weights: once at finalize; activations: k_split_tf32 below) so the kernel's
-// shared-memory bandwidth is spent on TMA fills and UMMA operand reads only.
+// fp32 FFMA).  Keeping the small correction products in their own accumulator (columns 256..511) makes the correction's own
+// rounding negligible; the epilogue adds the two in fp32 (RN).
+// The split planes live in HBM (weights: once at finalize; activations: written by the producing kernel or k_split_f16).
 //
 // Kernel anatomy (one persistent CTA per SM, 192 threads):
-//   warp 0      TMA producer : 4 x cp.async.bulk.tensor.2d (A_hi, A_lo, B_hi, B_lo; 128B swizzle) per k-block
-//   warp 1      MMA issuer   : tcgen05.mma.cta_group::1.kind::tf32, M128 x N256 x K8, 12 per k-block of 32 floats;
+//   warp 0      TMA producer : cp.async.bulk.tensor.2d boxes of 32 halves x 128 rows (64-byte rows, SWIZZLE_64B), 4 stages x 48 KB
+//   warp 1      MMA issuer   : tcgen05.mma.cta_group::1.kind::f16, M128 x N256 x K16, 6 per k-block of 32 halves;
 //               also owns TMEM alloc/dealloc (512 columns = main + correction accumulator of 256 each)
-//   warps 2..5  epilogue     : tcgen05.ld 32x32b.x32 -> + bias -> st.global (one accumulator row per thread)
-// Pipelines: smem full/empty mbarriers (2 stages x 96 KB), TMEM full/empty mbarrier pair (one accumulator set).
+//   warps 2..5  epilogue     : tcgen05.ld 32x32b.x32 -> main + corr/2048 + bias -> st.global (one accumulator row per thread)
 #pragma once
 #include <cuda.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -31,9 +35,9 @@
 namespace kb {
 namespace tc {
 
-constexpr int BM = 128, BN = 256, BK = 32, STAGES = 2;
-constexpr int A_TILE = BM * BK * 4, B_TILE = BN * BK * 4;                 // bytes
-constexpr int STAGE_BYTES = 2 * A_TILE + 2 * B_TILE;                      // 96 KB
+constexpr int BM = 128, BN = 256, BK = 32, STAGES = 4;                 // BK in fp16 elements: 64-byte rows
+constexpr int A_TILE = BM * BK * 2, B_TILE = BN * BK * 2;                 // bytes
+constexpr int STAGE_BYTES = 2 * A_TILE + 2 * B_TILE;                      // 48 KB
 constexpr int EPI_LD = 36;                                                // padded row of the per-warp 32x32 staging tile
 constexpr int EPI_BYTES = 4 * 32 * EPI_LD * 4;                            // 4 epilogue warps
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + EPI_BYTES;
@@ -68,6 +72,11 @@ __device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, u
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
                  ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
 }
+// multicast variant: the tile (and its complete_tx bytes) lands at the same CTA-relative offsets in every CTA of `mask`
+__device__ __forceinline__ void tma_load_2d_mc(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, uint16_t mask) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+                 ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(mask) : "memory");
+}
 __device__ __forceinline__ bool elect_one() {
     uint32_t pred;
     asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
@@ -84,6 +93,28 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
     d |= (uint64_t)2 << 61;                           // SWIZZLE_128B
     return d;
 }
+// same for 64-byte rows (32 halves) written with CU_TENSOR_MAP_SWIZZLE_64B: 8-row groups 512 B apart, layout type 4
+__device__ __forceinline__ uint64_t umma_desc_sw64(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(512 >> 4) << 32;                  // SBO
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)4 << 61;                           // SWIZZLE_64B
+    return d;
+}
+// kind::f16 instruction descriptor: fp32 accumulate, K-major operands; a_fmt/b_fmt: 0 = fp16, 1 = bf16 (A and B of one MMA must
+// share a format: a mixed fp16 x bf16 MMA faults with "illegal instruction", measured)
+__host__ __device__ constexpr uint32_t idesc_f16(int a_fmt, int b_fmt, int m, int n) {
+    return (1u << 4) | ((uint32_t)a_fmt << 7) | ((uint32_t)b_fmt << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
 // kind::tf32, fp32 accumulate, both operands K-major
 __host__ __device__ constexpr uint32_t idesc_tf32(int m, int n) {
     return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
@@ -97,6 +128,11 @@ __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint6
 }
 __device__ __forceinline__ void umma_commit(uint64_t *bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// arrives on the barrier at this offset in every CTA of `mask` when the MMAs issued so far retire
+__device__ __forceinline__ void umma_commit_mc(uint64_t *bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"(mask) : "memory");
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float *v) {
     uint32_t r[32];
@@ -118,6 +154,10 @@ struct GemmTcParams {
     int M, N, K, ldc, act;
 };
 
+// CL = 1: independent CTAs.  CL = 2: clusters of two CTAs work on two vertically adjacent output tiles (same n-tile): each CTA
+// fetches only HALF of the shared weight tile and multicasts it to both.  A stage is free when the MMAs of BOTH CTAs have
+// retired, so the consumers commit with a multicast arrive and `empty` counts CL arrivals.
+template <int CL>
 __global__ void __launch_bounds__(THREADS, 1)
 k_gemm_tc(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
           const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo, GemmTcParams p) {
@@ -130,11 +170,14 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ C
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tiles_m = (p.M + BM - 1) / BM, tiles_n = (p.N + BN - 1) / BN;
-    const int ntiles = tiles_m * tiles_n;
+    const int ntiles = ((tiles_m + CL - 1) / CL) * tiles_n;        // work items of a cluster: CL vertically adjacent tiles
     const int nkb = (p.K + BK - 1) / BK;
+    uint32_t crank = 0;
+    if (CL > 1) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
+    const int first = blockIdx.x / CL, nworkers = gridDim.x / CL;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], CL); }
         mbar_init(&tfull[0], 1); mbar_init(&tempty[0], 4);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -145,32 +188,42 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ C
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    if (CL > 1) asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");   // peer barriers initialised
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
         // ===================== TMA producer =====================
         if (elect_one()) {
             int stage = 0; uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            for (int tile = first; tile < ntiles; tile += nworkers) {
                 // n-tiles innermost: consecutive CTAs share the same A rows (L2 reuse), weights stay L2 resident
-                const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
+                const int m0 = ((tile / tiles_n) * CL + (int)crank) * BM, n0 = (tile % tiles_n) * BN;
                 for (int kb = 0; kb < nkb; ++kb) {
                     mbar_wait(&empty[stage], phase ^ 1);
                     uint8_t *st = smem + stage * STAGE_BYTES;
                     mbar_expect_tx(&full[stage], STAGE_BYTES);
                     tma_load_2d(st, &tm_a_hi, &full[stage], kb * BK, m0);
                     tma_load_2d(st + A_TILE, &tm_a_lo, &full[stage], kb * BK, m0);
-                    tma_load_2d(st + 2 * A_TILE, &tm_b_hi, &full[stage], kb * BK, n0);
-                    tma_load_2d(st + 2 * A_TILE + B_TILE, &tm_b_lo, &full[stage], kb * BK, n0);
+                    // weight tile = two 128-row boxes per plane
+                    if (CL == 1) {
+                        tma_load_2d(st + 2 * A_TILE, &tm_b_hi, &full[stage], kb * BK, n0);
+                        tma_load_2d(st + 2 * A_TILE + B_TILE / 2, &tm_b_hi, &full[stage], kb * BK, n0 + BN / 2);
+                        tma_load_2d(st + 2 * A_TILE + B_TILE, &tm_b_lo, &full[stage], kb * BK, n0);
+                        tma_load_2d(st + 2 * A_TILE + B_TILE + B_TILE / 2, &tm_b_lo, &full[stage], kb * BK, n0 + BN / 2);
+                    } else {
+                        const int half = (int)crank * (BN / 2);
+                        tma_load_2d_mc(st + 2 * A_TILE + (int)crank * (B_TILE / 2), &tm_b_hi, &full[stage], kb * BK, n0 + half, (uint16_t)0x3);
+                        tma_load_2d_mc(st + 2 * A_TILE + B_TILE + (int)crank * (B_TILE / 2), &tm_b_lo, &full[stage], kb * BK, n0 + half, (uint16_t)0x3);
+                    }
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
-        constexpr uint32_t idesc = idesc_tf32(BM, BN);
+        constexpr uint32_t idesc = idesc_f16(0, 0, BM, BN);
         int stage = 0; uint32_t phase = 0; uint32_t acc_phase = 0;
-        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        for (int tile = first; tile < ntiles; tile += nworkers) {
             mbar_wait(&tempty[0], acc_phase ^ 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t d_main = tmem_base, d_corr = tmem_base + (uint32_t)BN;
@@ -179,16 +232,17 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ C
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 if (elect_one()) {
                     const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
-                    const uint64_t a_hi = umma_desc_sw128(sa), a_lo = umma_desc_sw128(sa + A_TILE);
-                    const uint64_t b_hi = umma_desc_sw128(sa + 2 * A_TILE), b_lo = umma_desc_sw128(sa + 2 * A_TILE + B_TILE);
+                    const uint64_t a_hi = umma_desc_sw64(sa), a_lo = umma_desc_sw64(sa + A_TILE);
+                    const uint64_t b_hi = umma_desc_sw64(sa + 2 * A_TILE), b_lo = umma_desc_sw64(sa + 2 * A_TILE + B_TILE);
 #pragma unroll
-                    for (int k = 0; k < BK / 8; ++k) {
-                        const uint64_t adv = (uint64_t)((k * 8 * 4) >> 4);      // 32 bytes per K=8 step inside the 128B swizzle atom
-                        umma_tf32(d_corr, a_lo + adv, b_hi + adv, idesc, (kb | k) ? 1u : 0u);
-                        umma_tf32(d_corr, a_hi + adv, b_lo + adv, idesc, 1u);
-                        umma_tf32(d_main, a_hi + adv, b_hi + adv, idesc, (kb | k) ? 1u : 0u);
+                    for (int k = 0; k < BK / 16; ++k) {
+                        const uint64_t adv = (uint64_t)((k * 16 * 2) >> 4);     // 32 bytes per K=16 step inside the 64B swizzle atom
+                        umma_f16(d_corr, a_lo + adv, b_hi + adv, idesc, (kb | k) ? 1u : 0u);
+                        umma_f16(d_corr, a_hi + adv, b_lo + adv, idesc, 1u);
+                        umma_f16(d_main, a_hi + adv, b_hi + adv, idesc, (kb | k) ? 1u : 0u);
                     }
-                    umma_commit(&empty[stage]);                               // frees the smem stage when these MMAs retire
+                    if (CL == 1) umma_commit(&empty[stage]);                  // frees the smem stage when these MMAs retire
+                    else umma_commit_mc(&empty[stage], (uint16_t)0x3);        // ... in both CTAs: the peer multicasts into this stage too
                     if (kb == nkb - 1) umma_commit(&tfull[0]);                // accumulators complete -> epilogue
                 }
                 __syncwarp();
@@ -200,8 +254,8 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ C
         // ===================== epilogue (warps 2..5) =====================
         const int q = warp & 3;                                              // TMEM lane quarter this warp may access
         uint32_t acc_phase = 0;
-        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-            const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
+        for (int tile = first; tile < ntiles; tile += nworkers) {
+            const int m0 = ((tile / tiles_n) * CL + (int)crank) * BM, n0 = (tile % tiles_n) * BN;
             mbar_wait(&tfull[0], acc_phase);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             float *stg = epi_stage + (warp - 2) * 32 * EPI_LD;
@@ -219,7 +273,8 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ C
                 for (int j = 0; j < 32; j += 4) {
                     const int n = n0 + c0 + j;
                     float4 o;
-                    o.x = v[j] + cr[j]; o.y = v[j + 1] + cr[j + 1]; o.z = v[j + 2] + cr[j + 2]; o.w = v[j + 3] + cr[j + 3];
+                    constexpr float R = 1.f / X2_SCALE;
+                    o.x = fmaf(cr[j], R, v[j]); o.y = fmaf(cr[j + 1], R, v[j + 1]); o.z = fmaf(cr[j + 2], R, v[j + 2]); o.w = fmaf(cr[j + 3], R, v[j + 3]);
                     if (p.bias) {
                         o.x += (n + 0 < p.N) ? __ldg(p.bias + n + 0) : 0.f; o.y += (n + 1 < p.N) ? __ldg(p.bias + n + 1) : 0.f;
                         o.z += (n + 2 < p.N) ? __ldg(p.bias + n + 2) : 0.f; o.w += (n + 3 < p.N) ? __ldg(p.bias + n + 3) : 0.f;
@@ -250,25 +305,24 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ C
     // ===================== teardown =====================
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    if (CL > 1) asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");   // no multicast / remote arrive may target an exited CTA
     if (warp == 1) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
     }
 }
 
-// x -> (hi, lo): hi = round-to-nearest TF32 (low 13 mantissa bits zero), lo = x - hi (exact in fp32)
-__global__ void k_split_tf32(const float *__restrict__ x, float *__restrict__ hi, float *__restrict__ lo, long long n4) {
+// x -> fp16 planes (x1, x2s); raises *flag when a value leaves the fp16 range
+__global__ void k_split_f16(const float *__restrict__ x, __half *__restrict__ hi, __half *__restrict__ lo, long long n4, int *flag) {
+    bool bad = false;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
         const float4 v = __ldg(reinterpret_cast<const float4 *>(x) + i);
-        float4 h, l;
-        uint32_t t;
-        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v.x)); h.x = __uint_as_float(t); l.x = v.x - h.x;
-        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v.y)); h.y = __uint_as_float(t); l.y = v.y - h.y;
-        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v.z)); h.z = __uint_as_float(t); l.z = v.z - h.z;
-        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v.w)); h.w = __uint_as_float(t); l.w = v.w - h.w;
-        reinterpret_cast<float4 *>(hi)[i] = h;
-        reinterpret_cast<float4 *>(lo)[i] = l;
+        __half h[4], l[4];
+        split_f16(v.x, h[0], l[0], bad); split_f16(v.y, h[1], l[1], bad); split_f16(v.z, h[2], l[2], bad); split_f16(v.w, h[3], l[3], bad);
+        reinterpret_cast<uint2 *>(hi)[i] = make_uint2(pack_h2(h[0], h[1]), pack_h2(h[2], h[3]));
+        reinterpret_cast<uint2 *>(lo)[i] = make_uint2(pack_h2(l[0], l[1]), pack_h2(l[2], l[3]));
     }
+    if (bad) atomicOr(flag, 1);
 }
 
 // ---- host side: tensor maps -------------------------------------------------------------------------
@@ -287,15 +341,18 @@ inline PFN_encodeTiled get_encode() {
 }
 
 // row-major fp32 matrix [rows][K] (K contiguous), box = [box_rows][32], 128B swizzle, OOB -> 0
-inline bool make_map_2d(CUtensorMap *map, const float *base, uint64_t rows, uint64_t K, uint32_t box_rows) {
+// 2-D map over a row-major fp16 matrix [rows][K]; box = box_k halves x box_rows rows: 32 halves -> 64-byte rows / SWIZZLE_64B,
+// 64 halves -> 128-byte rows / SWIZZLE_128B
+inline bool make_map_2d(CUtensorMap *map, const __half *base, uint64_t rows, uint64_t K, uint32_t box_rows, uint32_t box_k = 32) {
     PFN_encodeTiled enc = get_encode();
     if (!enc) return false;
     cuuint64_t dims[2] = {K, rows};
-    cuuint64_t strides[1] = {K * sizeof(float)};
-    cuuint32_t box[2] = {(cuuint32_t)BK, box_rows};
+    cuuint64_t strides[1] = {K * sizeof(__half)};
+    cuuint32_t box[2] = {(cuuint32_t)box_k, box_rows};
     cuuint32_t estr[2] = {1, 1};
-    return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+    return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<__half *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               box_k == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 }  // namespace tc

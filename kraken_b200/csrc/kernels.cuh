@@ -9,10 +9,11 @@
 //
 // Arithmetic: everything here is IEEE fp32 FMA with accurate expf/tanhf, because CTC label sequences
 // have to be bit-identical to the fp32 reference and a random-weight model has top-2 logit gaps down to
-// 1e-4 (SURVEY.md 7 "hard parts").  The tensor-core GEMM (3xTF32 split on tcgen05) lives in
+// 1e-4 (SURVEY.md 7 "hard parts").  The tensor-core GEMM (split fp16 operands on tcgen05) lives in
 // gemm_tc.cuh and replaces k_conv_gemm for the shapes it supports.
 #pragma once
 #include <cooperative_groups.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -44,6 +45,24 @@ __device__ __forceinline__ unsigned long long pack2f(float lo, float hi) {
 }
 __device__ __forceinline__ void unpack2f(unsigned long long v, float &lo, float &hi) {
     asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+
+// Tensor-core operand planes (gemm_tc.cuh): x = x1 + x2s * 2^-11 with x1 = fp16(x), x2s = fp16((x - x1) * 2^11).
+// `bad` is raised when |x| leaves the fp16 range (the engine then re-runs the call on the fp32 CUDA-core kernels).
+constexpr float X2_SCALE = 2048.f;
+__device__ __forceinline__ void split_f16(float x, __half &h1, __half &h2, bool &bad) {
+    h1 = __float2half_rn(x);
+    h2 = __float2half_rn((x - __half2float(h1)) * X2_SCALE);
+    bad |= fabsf(x) > 65504.f;
+}
+__device__ __forceinline__ uint32_t pack_h2(__half a, __half b) { return (uint32_t)__half_as_ushort(a) | ((uint32_t)__half_as_ushort(b) << 16); }
+// 8 consecutive channels of one pixel -> both planes (one 16-byte store each)
+__device__ __forceinline__ void store_planes8(__half *hi, __half *lo, const float *v, bool &bad) {
+    __half h[8], l[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) split_f16(v[e], h[e], l[e], bad);
+    *reinterpret_cast<uint4 *>(hi) = make_uint4(pack_h2(h[0], h[1]), pack_h2(h[2], h[3]), pack_h2(h[4], h[5]), pack_h2(h[6], h[7]));
+    *reinterpret_cast<uint4 *>(lo) = make_uint4(pack_h2(l[0], l[1]), pack_h2(l[2], l[3]), pack_h2(l[4], l[5]), pack_h2(l[6], l[7]));
 }
 
 // =============================================================================================
@@ -196,7 +215,7 @@ __global__ void __launch_bounds__(CG_NT, 2) k_conv_gemm(ConvParams p) {
 // planes of the result for a tensor-core consumer.  max(relu(a), relu(b)) == relu(max(a, b)): pooling first is exact.
 // =============================================================================================
 struct Conv1PoolParams {
-    const float *x; const float *wt; const float *bias; float *y; float *y_hi; float *y_lo;
+    const float *x; const float *wt; const float *bias; float *y; __half *y_hi; __half *y_lo; int *flag;
     int N, H, W, Cout, Ncp, kh, kw, py, px, Hp, Wp, act;
 };
 __global__ void __launch_bounds__(256) k_conv1_pool(Conv1PoolParams p) {
@@ -248,22 +267,14 @@ __global__ void __launch_bounds__(256) k_conv1_pool(Conv1PoolParams p) {
         o[c] = act_apply(m, p.act);
     }
     const size_t off = (((size_t)n * p.Hp + hp) * p.Wp + wp) * p.Cout + cg_i * 8;
-    if (p.y) {            // the fp32 tensor is skipped when the only consumer reads the TF32 planes
+    if (p.y) {            // the fp32 tensor is skipped when the only consumer reads the fp16 planes
         *reinterpret_cast<float4 *>(p.y + off) = make_float4(o[0], o[1], o[2], o[3]);
         *reinterpret_cast<float4 *>(p.y + off + 4) = make_float4(o[4], o[5], o[6], o[7]);
     }
     if (p.y_hi) {
-        float h[8], l[8];
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-            uint32_t t;
-            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(o[c]));
-            h[c] = __uint_as_float(t); l[c] = o[c] - h[c];
-        }
-        *reinterpret_cast<float4 *>(p.y_hi + off) = make_float4(h[0], h[1], h[2], h[3]);
-        *reinterpret_cast<float4 *>(p.y_hi + off + 4) = make_float4(h[4], h[5], h[6], h[7]);
-        *reinterpret_cast<float4 *>(p.y_lo + off) = make_float4(l[0], l[1], l[2], l[3]);
-        *reinterpret_cast<float4 *>(p.y_lo + off + 4) = make_float4(l[4], l[5], l[6], l[7]);
+        bool bad = false;
+        store_planes8(p.y_hi + off, p.y_lo + off, o, bad);
+        if (bad) atomicOr(p.flag, 1);
     }
 }
 
@@ -464,8 +475,6 @@ __global__ void k_gn_apply(const float *__restrict__ x, float *__restrict__ y, c
     }
 }
 
-__device__ __forceinline__ float tf32_rna_dev(float v) { uint32_t t; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v)); return __uint_as_float(t); }
-
 // ---- vectorised GroupNorm (C % 4 == 0, C <= 1024): the kernels above spend their time in scalar loads and 64-bit div/mod
 //      (2.97 ms for 1.24 GB on cfg3's Gn_1 = 1.25 TB/s); these stream float4 quads with the channel quad fixed per thread.
 // block = 256 threads: thread -> (pixel row r = tid / C4, channel quad q = tid % C4), rows = 256 / C4 pixel rows per sweep
@@ -525,10 +534,10 @@ __global__ void k_gn_coeffs(const float2 *__restrict__ stats, const float *__res
     const double a = (double)st.y * (double)gamma[c];
     ab[idx] = make_float2((float)a, (float)((double)beta[c] - (double)st.x * a));
 }
-// y (optional), y_hi / y_lo (optional TF32 split planes for a tensor-core consumer)
-__global__ void __launch_bounds__(256) k_gn_apply4(const float *__restrict__ x, float *__restrict__ y, float *__restrict__ y_hi,
-                                                   float *__restrict__ y_lo, const float2 *__restrict__ ab, int H, int W, int C,
-                                                   const int *__restrict__ lens) {
+// y (optional), y_hi / y_lo (optional fp16 planes for a tensor-core consumer)
+__global__ void __launch_bounds__(256) k_gn_apply4(const float *__restrict__ x, float *__restrict__ y, __half *__restrict__ y_hi,
+                                                   __half *__restrict__ y_lo, const float2 *__restrict__ ab, int H, int W, int C,
+                                                   const int *__restrict__ lens, int *flag) {
     const int n = blockIdx.y;
     const int C4 = C >> 2, rows = 256 / C4;
     const int r = threadIdx.x / C4, q = threadIdx.x - r * C4;
@@ -539,8 +548,9 @@ __global__ void __launch_bounds__(256) k_gn_apply4(const float *__restrict__ x, 
     const size_t base = (size_t)n * npix * C4 + q;
     const float4 *px = reinterpret_cast<const float4 *>(x) + base;
     float4 *py = y ? reinterpret_cast<float4 *>(y) + base : nullptr;
-    float4 *ph = y_hi ? reinterpret_cast<float4 *>(y_hi) + base : nullptr;
-    float4 *pl = y_lo ? reinterpret_cast<float4 *>(y_lo) + base : nullptr;
+    uint2 *ph = y_hi ? reinterpret_cast<uint2 *>(y_hi) + base : nullptr;
+    uint2 *pl = y_lo ? reinterpret_cast<uint2 *>(y_lo) + base : nullptr;
+    bool bad = false;
     const int len = lens ? min(max(lens[n], 1), W) : W;
     const long long stride = (long long)gridDim.x * rows;
     long long pix = (long long)blockIdx.x * rows + r;
@@ -554,13 +564,14 @@ __global__ void __launch_bounds__(256) k_gn_apply4(const float *__restrict__ x, 
         }
         if (py) py[pix * C4] = o;
         if (ph) {
-            float4 hi, lo;
-            hi.x = tf32_rna_dev(o.x); hi.y = tf32_rna_dev(o.y); hi.z = tf32_rna_dev(o.z); hi.w = tf32_rna_dev(o.w);
-            lo.x = o.x - hi.x; lo.y = o.y - hi.y; lo.z = o.z - hi.z; lo.w = o.w - hi.w;
-            ph[pix * C4] = hi; pl[pix * C4] = lo;
+            __half h[4], l[4];
+            split_f16(o.x, h[0], l[0], bad); split_f16(o.y, h[1], l[1], bad); split_f16(o.z, h[2], l[2], bad); split_f16(o.w, h[3], l[3], bad);
+            ph[pix * C4] = make_uint2(pack_h2(h[0], h[1]), pack_h2(h[2], h[3]));
+            pl[pix * C4] = make_uint2(pack_h2(l[0], l[1]), pack_h2(l[2], l[3]));
         }
         if (lens) { w += wstep; if (w >= W) w -= W; }
     }
+    if (bad) atomicOr(flag, 1);
 }
 
 // =============================================================================================

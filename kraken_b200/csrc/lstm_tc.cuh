@@ -52,7 +52,6 @@ constexpr int LPW = NL / EW;                             // lines per epilogue w
 constexpr int LTHREADS = 32 + 4 * EW * 32;               // warp 0: MMA issue / TMEM alloc; warps 1..16: epilogue
 constexpr int TM_COLS = 512;                             // D: D1a @0 (32), D1b @32, D2a @64 (16), D2b @80;  A: W1 @128 (128), W2s @256 (128)
 constexpr int TM_A0 = 128;
-constexpr float X2_SCALE = 2048.f;                       // 2^11 on the second fp16 term of W and of h
 
 struct LstmTcParams {
     const float *gx; const uint16_t *wpk; float *out; const int *lens;
@@ -61,17 +60,6 @@ struct LstmTcParams {
     int dbg;
 };
 
-// kind::f16 instruction descriptor: fp32 accumulate, K-major operands; a_fmt/b_fmt: 0 = fp16, 1 = bf16
-__device__ __forceinline__ uint32_t idesc_f16(int a_fmt, int b_fmt, int m, int n) {
-    return (1u << 4) | ((uint32_t)a_fmt << 7) | ((uint32_t)b_fmt << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
-}
-__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
-}
 __device__ __forceinline__ void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"

@@ -419,6 +419,11 @@ class TorchVGSLModel:
     def launch_count(self) -> int:
         return int(lib.kb_launch_count(self._h))
 
+    @property
+    def range_fallback_count(self) -> int:
+        """Calls that were repeated on the fp32 CUDA-core kernels because an activation left the fp16 operand range."""
+        return int(lib.kb_range_fallback_count(self._h))
+
     def reset_launch_count(self):
         lib.kb_reset_launch_count(self._h)
 

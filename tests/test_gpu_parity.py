@@ -371,3 +371,28 @@ def test_tensor_core_recurrence_small_hidden(spec, n, h, w, ragged):
         assert rel_err(out, ref) <= TIGHT, (tc, rel_err(out, ref))
         if ragged:
             assert ol.tolist() == rl.tolist()
+
+
+def test_fp16_operand_range_fallback():
+    """Activations beyond the fp16 operand range (|x| > 65504) of the tensor-core layers: the call is repeated on the fp32 CUDA-core
+    kernels and still matches the oracle; in-range inputs never take that path."""
+    spec = '[1,16,0,1 Cr3,3,32 Mp2,2 Cr3,3,64 Mp2,2 S1(1x0)1,3 Lbx40 O1c13]'
+    om = vo.OracleModel(spec)
+    wts = om.init_like_reference(5)
+    m = kb.TorchVGSLModel(vgsl=spec)
+    m.load_state_dict(wts)
+    m.to('cuda:0')
+    g = torch.Generator().manual_seed(5)
+    x = torch.rand(3, 1, 16, 300, generator=g)
+    out, _ = m.nn(x.cuda())
+    ref, _ = om.forward(x, None)
+    assert rel_err(out, ref) <= TIGHT
+    assert m.range_fallback_count == 0
+    big = x * 3e6                                          # conv outputs ~1e6: not representable in the fp16 planes
+    ref_big, _ = om.forward(big, None)
+    out_big, _ = m.nn(big.cuda())
+    assert m.range_fallback_count == 1
+    assert rel_err(out_big, ref_big) <= TIGHT
+    out2, _ = m.nn(x.cuda())                               # the next in-range call is back on the tensor cores
+    assert m.range_fallback_count == 1
+    assert rel_err(out2, ref) <= TIGHT
