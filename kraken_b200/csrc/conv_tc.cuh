@@ -29,7 +29,8 @@ using namespace kb::tc;
 constexpr int TW = 128;                  // output columns per work item
 constexpr int MAX_STB = 4;               // weight-tile ring stages
 constexpr int PIX_B = 64;                // bytes of one pixel row of a plane: 32 channels x fp16
-constexpr int CTHREADS = 192;
+constexpr int CEPI_WARPS = 8;             // two per TMEM lane quarter: even / odd 32-channel chunks
+constexpr int CTHREADS = 64 + CEPI_WARPS * 32;
 constexpr int MAX_ROWS = 8;              // kh + 1 <= 8
 
 struct ConvTcParams {
@@ -70,7 +71,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ C
     if (threadIdx.x == 0) {
         for (int r = 0; r < R; ++r) { mbar_init(&full_a[r], 1); mbar_init(&empty_a[r], 1); }
         for (int s = 0; s < NSTB; ++s) { mbar_init(&full_b[s], 1); mbar_init(&empty_b[s], 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 4); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], CEPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -162,8 +163,9 @@ k_conv_tc(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ C
             else acc_phase ^= 1;
         }
     } else {
-        // ===================== epilogue (warps 2..5): thread = output column of the tile, both rows =====================
-        const int q = warp & 3;
+        // ===================== epilogue (warps 2..9): thread = output column of the tile, both rows; the two warps of a TMEM
+        // lane quarter take the even / odd 32-channel chunks =====================
+        const int q = warp & 3, half = (warp - 2) >> 2;
         int acc = 0; uint32_t acc_phase = 0;
         bool bad = false;
         constexpr float RS = 1.f / X2_SCALE;
@@ -176,24 +178,30 @@ k_conv_tc(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ C
             const int cbase = ct * CT;                                     // first output channel of this tile
             const int wcol = ws * TW + q * 32 + lane;                       // conv output column
 #pragma unroll 1
-            for (int c0 = 0; c0 < CT; c0 += 32) {
+            for (int c0 = 32 * half; c0 < CT; c0 += 64) {
                 float v0[32], v1[32];
                 {
-                    float t[32];
-                    tmem_ld32(lane_base + (uint32_t)c0, v0);
-                    tmem_ld32(lane_base + (uint32_t)(CT + c0), t);
+                    uint32_t a[32], t[32];
+                    tmem_ld32_nowait(lane_base + (uint32_t)c0, a);
+                    tmem_ld32_nowait(lane_base + (uint32_t)(CT + c0), t);
+                    tmem_ld_wait();
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) v0[j] = fmaf(t[j], RS, v0[j]);
-                    tmem_ld32(lane_base + (uint32_t)(2 * CT + c0), v1);
-                    tmem_ld32(lane_base + (uint32_t)(3 * CT + c0), t);
+                    for (int j = 0; j < 32; ++j) v0[j] = fmaf(__uint_as_float(t[j]), RS, __uint_as_float(a[j]));
+                    tmem_ld32_nowait(lane_base + (uint32_t)(2 * CT + c0), a);
+                    tmem_ld32_nowait(lane_base + (uint32_t)(3 * CT + c0), t);
+                    tmem_ld_wait();
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) v1[j] = fmaf(t[j], RS, v1[j]);
+                    for (int j = 0; j < 32; ++j) v1[j] = fmaf(__uint_as_float(t[j]), RS, __uint_as_float(a[j]));
                 }
+                if (p.bias) {                                                 // 32 channels = 128 bytes, 16-byte aligned (Cout % 16 == 0)
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const float b = p.bias ? __ldg(p.bias + cbase + c0 + j) : 0.f;
-                    v0[j] = act_apply(v0[j] + b, p.act); v1[j] = act_apply(v1[j] + b, p.act);
+                    for (int j = 0; j < 32; j += 4) {
+                        const float4 b4 = __ldg(reinterpret_cast<const float4 *>(p.bias + cbase + c0 + j));
+                        v0[j] += b4.x; v0[j + 1] += b4.y; v0[j + 2] += b4.z; v0[j + 3] += b4.w;
+                        v1[j] += b4.x; v1[j + 1] += b4.y; v1[j + 2] += b4.z; v1[j + 3] += b4.w;
+                    }
                 }
+                act_apply_vec(v0, p.act); act_apply_vec(v1, p.act);
                 if (p.pool) {
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {

@@ -19,11 +19,12 @@
 // rounding negligible; the epilogue adds the two in fp32 (RN).
 // The split planes live in HBM (weights: once at finalize; activations: written by the producing kernel or k_split_f16).
 //
-// Kernel anatomy (one persistent CTA per SM, 192 threads):
+// Kernel anatomy (one persistent CTA per SM, 320 threads):
 //   warp 0      TMA producer : cp.async.bulk.tensor.2d boxes of 32 halves x 128 rows (64-byte rows, SWIZZLE_64B), 4 stages x 48 KB
 //   warp 1      MMA issuer   : tcgen05.mma.cta_group::1.kind::f16, M128 x N256 x K16, 6 per k-block of 32 halves;
 //               also owns TMEM alloc/dealloc (512 columns = main + correction accumulator of 256 each)
-//   warps 2..5  epilogue     : tcgen05.ld 32x32b.x32 -> main + corr/2048 + bias -> st.global (one accumulator row per thread)
+//   warps 2..9  epilogue     : tcgen05.ld 32x32b.x32 -> main + corr/2048 + bias -> st.global (one accumulator row per thread,
+//               the two warps of a TMEM lane quarter split the column chunks)
 #pragma once
 #include <cuda.h>
 #include <cuda_fp16.h>
@@ -38,10 +39,9 @@ namespace tc {
 constexpr int BM = 128, BN = 256, BK = 32, STAGES = 4;                 // BK in fp16 elements: 64-byte rows
 constexpr int A_TILE = BM * BK * 2, B_TILE = BN * BK * 2;                 // bytes
 constexpr int STAGE_BYTES = 2 * A_TILE + 2 * B_TILE;                      // 48 KB
-constexpr int EPI_LD = 36;                                                // padded row of the per-warp 32x32 staging tile
-constexpr int EPI_BYTES = 4 * 32 * EPI_LD * 4;                            // 4 epilogue warps
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + EPI_BYTES;
-constexpr int THREADS = 192;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int EPI_WARPS = 8;                                             // two per TMEM lane quarter: even / odd 32-column chunks
+constexpr int THREADS = 64 + EPI_WARPS * 32;
 constexpr int TMEM_COLS = 512;
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -134,6 +134,17 @@ __device__ __forceinline__ void umma_commit_mc(uint64_t *bar, uint16_t mask) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
                  ::"r"(smem_u32(bar)), "h"(mask) : "memory");
 }
+__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t *r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+          "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+          "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float *v) {
     uint32_t r[32];
     asm volatile(
@@ -166,7 +177,6 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ C
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + STAGES * STAGE_BYTES);
     uint64_t *full = bars, *empty = bars + STAGES, *tfull = bars + 2 * STAGES, *tempty = bars + 2 * STAGES + 2;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * STAGES + 4);
-    float *epi_stage = reinterpret_cast<float *>(smem + STAGES * STAGE_BYTES + 256);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tiles_m = (p.M + BM - 1) / BM, tiles_n = (p.N + BN - 1) / BN;
@@ -178,7 +188,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ C
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], CL); }
-        mbar_init(&tfull[0], 1); mbar_init(&tempty[0], 4);
+        mbar_init(&tfull[0], 1); mbar_init(&tempty[0], EPI_WARPS);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -251,50 +261,55 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ C
             acc_phase ^= 1;
         }
     } else {
-        // ===================== epilogue (warps 2..5) =====================
-        const int q = warp & 3;                                              // TMEM lane quarter this warp may access
+        // ===================== epilogue (warps 2..9) =====================
+        // thread = one accumulator row (TMEM lane) x 32 consecutive columns per chunk = one full 128-byte line of C per chunk;
+        // the warp pair of a lane quarter takes the even / odd chunks.  (Round 1 used 4 warps with a per-element activation
+        // switch and a shared-memory transpose: with the mainloop on fp16 MMAs the epilogue took as long as the mainloop.)
+        const int q = warp & 3, half = (warp - 2) >> 2;                       // TMEM lane quarter this warp may access
         uint32_t acc_phase = 0;
+        constexpr float R = 1.f / X2_SCALE;
         for (int tile = first; tile < ntiles; tile += nworkers) {
             const int m0 = ((tile / tiles_n) * CL + (int)crank) * BM, n0 = (tile % tiles_n) * BN;
             mbar_wait(&tfull[0], acc_phase);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            float *stg = epi_stage + (warp - 2) * 32 * EPI_LD;
             const bool vec = (p.ldc & 3) == 0 && (p.N & 3) == 0;
+            const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
+            const int m = m0 + q * 32 + lane;
 #pragma unroll 1
-            for (int c0 = 0; c0 < BN; c0 += 32) {
+            for (int c0 = 32 * half; c0 < BN; c0 += 64) {
                 if (n0 + c0 >= p.N) break;                                    // warp-uniform
-                float v[32], cr[32];
-                const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
-                tmem_ld32(lane_base + (uint32_t)c0, v);
-                tmem_ld32(lane_base + (uint32_t)(BN + c0), cr);
-                // row = lane: main + correction (+ bias, activation), staged so that the global stores below are
-                // row-contiguous (each store instruction writes 4 rows x 128 B instead of 32 rows x 16 B)
+                uint32_t vm[32], vc[32];
+                tmem_ld32_nowait(lane_base + (uint32_t)c0, vm);
+                tmem_ld32_nowait(lane_base + (uint32_t)(BN + c0), vc);
+                tmem_ld_wait();
+                float o[32];
 #pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                    const int n = n0 + c0 + j;
-                    float4 o;
-                    constexpr float R = 1.f / X2_SCALE;
-                    o.x = fmaf(cr[j], R, v[j]); o.y = fmaf(cr[j + 1], R, v[j + 1]); o.z = fmaf(cr[j + 2], R, v[j + 2]); o.w = fmaf(cr[j + 3], R, v[j + 3]);
-                    if (p.bias) {
-                        o.x += (n + 0 < p.N) ? __ldg(p.bias + n + 0) : 0.f; o.y += (n + 1 < p.N) ? __ldg(p.bias + n + 1) : 0.f;
-                        o.z += (n + 2 < p.N) ? __ldg(p.bias + n + 2) : 0.f; o.w += (n + 3 < p.N) ? __ldg(p.bias + n + 3) : 0.f;
-                    }
-                    o.x = act_apply(o.x, p.act); o.y = act_apply(o.y, p.act); o.z = act_apply(o.z, p.act); o.w = act_apply(o.w, p.act);
-                    *reinterpret_cast<float4 *>(stg + lane * EPI_LD + j) = o;
-                }
-                __syncwarp();
+                for (int j = 0; j < 32; ++j) o[j] = fmaf(__uint_as_float(vc[j]), R, __uint_as_float(vm[j]));
+                const int n = n0 + c0;
+                if (p.bias) {
+                    if (n + 32 <= p.N && (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0 && (n & 3) == 0) {
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int r = i * 4 + (lane >> 3), c4 = (lane & 7) * 4;
-                    const int m = m0 + q * 32 + r, n = n0 + c0 + c4;
-                    if (m < p.M && n < p.N) {
-                        const float4 o = *reinterpret_cast<const float4 *>(stg + r * EPI_LD + c4);
-                        float *dst = p.c + (size_t)m * p.ldc + n;
-                        if (vec) *reinterpret_cast<float4 *>(dst) = o;
-                        else { dst[0] = o.x; if (n + 1 < p.N) dst[1] = o.y; if (n + 2 < p.N) dst[2] = o.z; if (n + 3 < p.N) dst[3] = o.w; }
+                        for (int j = 0; j < 32; j += 4) {
+                            const float4 b4 = __ldg(reinterpret_cast<const float4 *>(p.bias + n + j));
+                            o[j] += b4.x; o[j + 1] += b4.y; o[j + 2] += b4.z; o[j + 3] += b4.w;
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) o[j] += (n + j < p.N) ? __ldg(p.bias + n + j) : 0.f;
                     }
                 }
-                __syncwarp();
+                act_apply_vec(o, p.act);
+                if (m < p.M) {
+                    float *dst = p.c + (size_t)m * p.ldc + n;
+                    if (vec) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4)
+                            if (n + j < p.N) *reinterpret_cast<float4 *>(dst + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) if (n + j < p.N) dst[j] = o[j];
+                    }
+                }
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();

@@ -31,6 +31,21 @@ __device__ __forceinline__ float act_apply(float v, int act) {
     }
 }
 __device__ __forceinline__ float sigmoidf_acc(float x) { return 1.f / (1.f + expf(-x)); }
+// activation over a register array with the kind test hoisted out of the element loop (one branch per call, not per element:
+// the per-element switch made the tcgen05 epilogues branch- and instruction-fetch bound, ncu r01d)
+template <int N>
+__device__ __forceinline__ void act_apply_vec(float (&v)[N], int act) {
+    if (act == DACT_RELU) {
+#pragma unroll
+        for (int i = 0; i < N; ++i) v[i] = v[i] > 0.f ? v[i] : 0.f;
+    } else if (act == DACT_TANH) {
+#pragma unroll
+        for (int i = 0; i < N; ++i) v[i] = tanhf(v[i]);
+    } else if (act == DACT_LEAKY) {
+#pragma unroll
+        for (int i = 0; i < N; ++i) v[i] = v[i] > 0.f ? v[i] : 0.01f * v[i];
+    }
+}
 // Blackwell packed fp32 FMA: (acc.lo, acc.hi) += (w.lo, w.hi) * s.  ptxas folds the {s, s} pack into FFMA2's scalar-broadcast
 // operand form (`FFMA2 Rd, Ra.F32x2.HI_LO, Rb.F32, Rc.F32x2.HI_LO`), so this is ONE issue slot for two IEEE fmas.
 __device__ __forceinline__ void ffma2_bcast(unsigned long long &acc, unsigned long long w, float s) {
