@@ -287,7 +287,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--cpu-steps', type=int, default=6)
-    ap.add_argument('--inflight', type=int, default=2, help='engine handles driven concurrently in the e2e arm')
+    ap.add_argument('--inflight', type=int, default=4, help='engine handles driven concurrently in the e2e arm')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--workload', default='cfg2', choices=['cfg2', 'cfg3'])
     ap.add_argument('--pages', type=int, default=8)

@@ -9,6 +9,7 @@
 #include <vector>
 
 #include <cuda_runtime.h>
+#include <chrono>
 
 #include "../../include/kraken_b200.h"
 #include "kernels.cuh"
@@ -89,6 +90,7 @@ struct kb_model {
     int *h_flag = nullptr;           // pinned copy, valid after the stream is synchronised
     bool force_ffma = false;         // second attempt of a call whose first attempt raised the flag: fp32 CUDA-core kernels only
     int64_t overflow_reruns = 0;
+    double prof_us[4] = {0, 0, 0, 0}; int64_t prof_calls = 0;    // KB_HOST_PROF: host microseconds in plan / launch / wait / unpack
     bool fuse = true;                // fused layer groups (KB_FUSE=0 runs every layer on its own, e.g. for layer taps)
     bool use_tc = true;              // tcgen05 GEMM path (KB_GEMM=ffma forces the CUDA-core kernel)
     ~kb_model() {
@@ -806,6 +808,7 @@ static ForwardResult forward_impl(kb_model *m, const float *x, int x_on_device, 
     if (widths) { lens0.has = true; lens0.v.assign(widths, widths + n); }
     const size_t in_elems = (size_t)n * C * h * w;
     // ---- pass 1: plan the arena
+    const auto prof_t0 = std::chrono::steady_clock::now();
     size_t need;
     {
         Arena saved = m->arena;
@@ -830,6 +833,8 @@ static ForwardResult forward_impl(kb_model *m, const float *x, int x_on_device, 
     m->arena.dry = false; m->arena.off = 0;
     m->taps.clear();
     m->n_stages = 0;
+    const auto prof_t1 = std::chrono::steady_clock::now();
+    m->prof_us[0] += std::chrono::duration<double, std::micro>(prof_t1 - prof_t0).count();
     // ---- stage input
     Tensor t; t.n = n; t.c = C; t.h = h; t.w = w;
     const float *src = x;
@@ -851,6 +856,7 @@ static ForwardResult forward_impl(kb_model *m, const float *x, int x_on_device, 
     ForwardResult r; r.lens = lens0;
     r.y = ex.run(*pl.root, t, r.lens);
     CK(cudaMemcpyAsync(m->h_flag, m->d_flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+    m->prof_us[1] += std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - prof_t1).count();
     return r;
 }
 
@@ -915,7 +921,7 @@ static size_t decode_bytes(int n, int T, int max_out) {
 static void decode_and_fetch(kb_model *m, int dev_sm, int n, int T, int max_out, const int *d_lab, const float *d_conf, const int *d_lens,
                              int32_t *labels, int32_t *starts, int32_t *ends, float *confs, int32_t *counts, cudaStream_t st,
                              Arena &arena, void **pinned, size_t *pinned_cap, int64_t *launches, StageTimer *timer = nullptr) {
-    (void)dev_sm; (void)m;
+    (void)dev_sm;
     const size_t per = (size_t)n * max_out;
     const size_t blk = per * 16 + (size_t)n * 4;
     char *d = (char *)arena.alloc(blk);
@@ -932,7 +938,10 @@ static void decode_and_fetch(kb_model *m, int dev_sm, int n, int T, int max_out,
     }
     CK(cudaMemcpyAsync(*pinned, d, blk, cudaMemcpyDeviceToHost, st));
     if (timer && timer->idx >= 0) { cudaEventRecord(timer->m->stages[timer->idx].b, st); timer->idx = -1; }
+    const auto prof_t2 = std::chrono::steady_clock::now();
     CK(cudaStreamSynchronize(st));
+    const auto prof_t3 = std::chrono::steady_clock::now();
+    if (m) m->prof_us[2] += std::chrono::duration<double, std::micro>(prof_t3 - prof_t2).count();
     const char *hsrc = (const char *)*pinned;
     // only the valid prefix of every line is defined on the device; zero the rest for the caller
     const int32_t *h_cnt = (const int32_t *)(hsrc + per * 16);
@@ -944,6 +953,14 @@ static void decode_and_fetch(kb_model *m, int dev_sm, int n, int T, int max_out,
         memcpy(starts + o, hsrc + per * 4 + o * 4, (size_t)c * 4); memset(starts + o + c, 0, (size_t)(max_out - c) * 4);
         memcpy(ends + o, hsrc + per * 8 + o * 4, (size_t)c * 4); memset(ends + o + c, 0, (size_t)(max_out - c) * 4);
         memcpy(confs + o, hsrc + per * 12 + o * 4, (size_t)c * 4); memset(confs + o + c, 0, (size_t)(max_out - c) * 4);
+    }
+    if (m) {
+        m->prof_us[3] += std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - prof_t3).count();
+        if (++m->prof_calls % 50 == 0 && getenv("KB_HOST_PROF")) {
+            fprintf(stderr, "[kb] host us per call: plan %.1f  launch %.1f  wait %.1f  unpack %.1f\n", m->prof_us[0] / 50, m->prof_us[1] / 50,
+                    m->prof_us[2] / 50, m->prof_us[3] / 50);
+            m->prof_us[0] = m->prof_us[1] = m->prof_us[2] = m->prof_us[3] = 0;
+        }
     }
 }
 

@@ -38,19 +38,21 @@ namespace ltc {
 using namespace kb::tc;
 
 constexpr int NL = 16;                                   // lines per cluster
+constexpr int NG = 2;                                    // independent line groups per cluster, processed in ping-pong (version 5)
+constexpr int GL = NL / NG;                              // 8 lines per group
 constexpr int LCS = 8;                                   // cluster size
 constexpr int A_PLANE_ELEMS = 128 * 256;                 // fp16 elements of one W plane of a CTA: [128 gate rows][K = 256], row-major
-constexpr int B_ROWS = 2 * NL;                           // 32 rows: h1 | h2s
-constexpr int B_TILE_B = B_ROWS * 128;                   // 4096 bytes per k-atom
-constexpr int B_BUF_B = 4 * B_TILE_B;                    // 16384 bytes per buffer
-constexpr int SG_FLOATS = NL * 8 * 4;                    // per warp (TMEM lane quarter): [line][unit][gate]
-constexpr int SH_FLOATS = NL * 8;                        // per warp: [line][unit]
-constexpr int STG_BYTES = 4 * (SG_FLOATS + SH_FLOATS) * 4;
-constexpr int LSMEM_BYTES = 2 * B_BUF_B + STG_BYTES + 128 + 1024;
-constexpr int EW = 4;                                    // epilogue warps per TMEM lane quarter (latency hiding: v3 with 1 was 2x slower)
-constexpr int LPW = NL / EW;                             // lines per epilogue warp in the activation phase
+constexpr int B_ROWS = 2 * GL;                           // 16 rows per group: h1 | h2s
+constexpr int B_TILE_B = B_ROWS * 128;                   // 2048 bytes per k-atom
+constexpr int B_BUF_B = 4 * B_TILE_B;                    // 8192 bytes per (group, buffer)
+constexpr int SG_FLOATS = GL * 8 * 4;                    // per (TMEM lane quarter, group): [line][unit][gate]
+constexpr int SH_FLOATS = GL * 8;                        // per (quarter, group): [line][unit]
+constexpr int STG_BYTES = 4 * NG * (SG_FLOATS + SH_FLOATS) * 4;
+constexpr int LSMEM_BYTES = NG * 2 * B_BUF_B + STG_BYTES + 128 + 1024;
+constexpr int EW = 4;                                    // epilogue warps per TMEM lane quarter: 2 per group (latency hiding: v3 with 1 was 2x slower)
+constexpr int LPW = 4;                                   // lines per epilogue warp in the activation phase
 constexpr int LTHREADS = 32 + 4 * EW * 32;               // warp 0: MMA issue / TMEM alloc; warps 1..16: epilogue
-constexpr int TM_COLS = 512;                             // D: D1a @0 (32), D1b @32, D2a @64 (16), D2b @80;  A: W1 @128 (128), W2s @256 (128)
+constexpr int TM_COLS = 512;                             // D of group g @64g: D1a (16), D1b @16, D2a @32, D2b @48;  A: W1 @128 (128), W2s @256 (128)
 constexpr int TM_A0 = 128;
 
 struct LstmTcParams {
@@ -114,11 +116,11 @@ __device__ __forceinline__ void named_bar(int id, int nthreads) { asm volatile("
 __global__ void __launch_bounds__(LTHREADS, 1) k_lstm_rec_tc(LstmTcParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = smem_align1024(smem_raw);
-    uint8_t *sB = smem;
-    float *stg = reinterpret_cast<float *>(sB + 2 * B_BUF_B);
-    uint64_t *bars = reinterpret_cast<uint64_t *>(sB + 2 * B_BUF_B + STG_BYTES);
-    uint64_t *b_full = bars + 1 /* [2] */, *mma_done = bars + 3;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 4);
+    uint8_t *sB = smem;                                   // [group][buffer][k-atom][16 rows x 128 B]
+    float *stg = reinterpret_cast<float *>(sB + NG * 2 * B_BUF_B);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sB + NG * 2 * B_BUF_B + STG_BYTES);
+    uint64_t *b_full = bars /* [group][2] */, *mma_done = bars + 4 /* [group] */;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 6);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint32_t rank;
@@ -127,11 +129,13 @@ __global__ void __launch_bounds__(LTHREADS, 1) k_lstm_rec_tc(LstmTcParams p) {
     const int hid = p.hid, GC = p.dirs * 4 * hid, OC = p.dirs * hid;
 
     if (threadIdx.x == 0) {
-        mbar_init(&b_full[0], 1); mbar_init(&b_full[1], 1); mbar_init(mma_done, 1);
+        for (int i = 0; i < 4; ++i) mbar_init(&b_full[i], 1);
+        mbar_init(&mma_done[0], 1); mbar_init(&mma_done[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        mbar_expect_tx(&b_full[1], B_BUF_B);             // buffer 1 receives h_0 at the end of step 0
+        mbar_expect_tx(&b_full[1], B_BUF_B);             // buffer 1 of each group receives h_0 at the end of step 0
+        mbar_expect_tx(&b_full[3], B_BUF_B);
     }
-    for (int i = threadIdx.x; i < 2 * B_BUF_B / 16; i += LTHREADS) reinterpret_cast<uint4 *>(sB)[i] = make_uint4(0, 0, 0, 0);   // h_{-1} = 0
+    for (int i = threadIdx.x; i < NG * 2 * B_BUF_B / 16; i += LTHREADS) reinterpret_cast<uint4 *>(sB)[i] = make_uint4(0, 0, 0, 0);   // h_{-1} = 0
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -164,58 +168,60 @@ __global__ void __launch_bounds__(LTHREADS, 1) k_lstm_rec_tc(LstmTcParams p) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 
-    int maxlen = 0;                                       // uniform across the cluster
+    int maxlen = 0;                                       // uniform across the cluster (both groups run the same number of steps)
     for (int lb = 0; lb < NL; ++lb) {
         const int q = chunk * NL + lb;
         if (q < p.nseq) maxlen = max(maxlen, p.lens ? min(max(p.lens[q], 0), p.T) : p.T);
     }
 
     if (warp == 0) {
-        // ===================== MMA issuer =====================
-        const uint32_t id1 = idesc_f16(0, 0, 128, 32), id2 = idesc_f16(0, 0, 128, 16);
+        // ===================== MMA issuer: alternates between the two line groups =====================
+        const uint32_t id = idesc_f16(0, 0, 128, 2 * GL);
         for (int s = 0; s < maxlen; ++s) {
             const int cur = s & 1;
-            if (s > 0) mbar_wait(&b_full[cur], (uint32_t)(((s - 1) >> 1) & 1));   // default acquire.cta: an acquire.cluster wait costs a CCTL.IVALL per step
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // st.async writes -> UMMA (async proxy) reads
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const long long dbg_c0 = p.dbg ? clock64() : 0;
-            if (elect_one()) {
-                // this buffer is refilled during step s+1 (nobody can send that before receiving our h_s)
-                if (s + 2 < maxlen) mbar_expect_tx(&b_full[cur], B_BUF_B);
-                const uint32_t b0 = smem_u32(sB + cur * B_BUF_B);
+#pragma unroll 1
+            for (int g = 0; g < NG; ++g) {
+                uint64_t *bf = &b_full[g * 2 + cur];
+                if (s > 0) mbar_wait(bf, (uint32_t)(((s - 1) >> 1) & 1));       // default acquire.cta: an acquire.cluster wait costs a CCTL.IVALL per step
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // st.async writes -> UMMA (async proxy) reads
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                if (elect_one()) {
+                    // this buffer is refilled during step s+1 (nobody can send that before receiving our h_s)
+                    if (s + 2 < maxlen) mbar_expect_tx(bf, B_BUF_B);
+                    const uint32_t b0 = smem_u32(sB + (g * 2 + cur) * B_BUF_B);
+                    const uint32_t dg = tmem_base + (uint32_t)(g * 64);
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
+                    for (int k = 0; k < 4; ++k) {
 #pragma unroll
-                    for (int kk = 0; kk < 4; ++kk) {
-                        const int ka = kk == 0 ? 0 : kk == 1 ? 2 : kk == 2 ? 1 : 3;      // 0,2,1,3: same-chain MMAs 4 issues apart
-                        const int half = ka >> 1;
-                        const uint64_t bd = umma_desc_sw128(b0 + (uint32_t)(ka * B_TILE_B)) + (uint64_t)(2 * k);
-                        const uint32_t a1 = tmem_base + (uint32_t)(TM_A0 + ka * 32 + k * 8);      // K = 16 -> 8 columns of fp16 pairs
-                        const uint32_t a2 = a1 + 128u;
-                        const uint32_t first = ((ka & 1) == 0 && k == 0) ? 0u : 1u;
-                        umma_f16_ts(tmem_base + (uint32_t)(half * 32), a1, bd, id1, first);          // [W1 h1 | W1 h2s]
-                        umma_f16_ts(tmem_base + (uint32_t)(64 + half * 16), a2, bd, id2, first);     // W2s h1 (first 16 rows of B)
+                        for (int kk = 0; kk < 4; ++kk) {
+                            const int ka = kk == 0 ? 0 : kk == 1 ? 2 : kk == 2 ? 1 : 3;      // 0,2,1,3: same-chain MMAs 4 issues apart
+                            const int half = ka >> 1;
+                            const uint64_t bd = umma_desc_sw128(b0 + (uint32_t)(ka * B_TILE_B)) + (uint64_t)(2 * k);
+                            const uint32_t a1 = tmem_base + (uint32_t)(TM_A0 + ka * 32 + k * 8);      // K = 16 -> 8 columns of fp16 pairs
+                            const uint32_t a2 = a1 + 128u;
+                            const uint32_t first = ((ka & 1) == 0 && k == 0) ? 0u : 1u;
+                            umma_f16_ts(dg + (uint32_t)(half * 16), a1, bd, id, first);          // [W1 h1 | W1 h2s]
+                            umma_f16_ts(dg + (uint32_t)(32 + half * 16), a2, bd, id, first);     // [W2s h1 | (W2s h2s: unused, N must be >= 16)]
+                        }
                     }
+                    umma_commit(&mma_done[g]);
                 }
-                umma_commit(mma_done);
-                if (p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && (s == 100 || s == 101))
-                    printf("[tcrec] s=%d MMA  bfull_ready=%lld issued=%lld (issue %lld)\n", s, dbg_c0, clock64(), clock64() - dbg_c0);
+                __syncwarp();
             }
-            __syncwarp();
         }
     } else {
-        // ===================== epilogue warps 1..16: quarter q = warp & 3, sub-warp sw = (warp-1) >> 2 =====================
+        // ===================== epilogue warps 1..16: quarter q = warp & 3; sub-warp sw = (warp-1) >> 2: group g = sw >> 1 =====================
         const int q = warp & 3;                            // TMEM lane quarter: unit slots 8q .. 8q+7
-        const int sw = (warp - 1) >> 2;                    // activation phase: lines LPW*sw .. LPW*sw + LPW-1 of this thread's TMEM row
-        const int jq = lane >> 2, g = lane & 3;            // unit slot within the quarter, gate of this thread's TMEM row
+        const int sw = (warp - 1) >> 2, g = sw >> 1, sw2 = sw & 1;
+        const int jq = lane >> 2, gate = lane & 3;         // unit slot within the quarter, gate of this thread's TMEM row
         const int slot = 8 * q + jq, u = (int)rank * p.U + slot;
         const bool uvalid = slot < p.U && u < hid;
-        float *sg = stg + q * (SG_FLOATS + SH_FLOATS), *sh = sg + SG_FLOATS;
-        const int tq = sw * 32 + lane;                     // thread index within the quarter's 128 threads
-        // the one cell this thread updates: line cl, unit slot cj of the quarter
+        float *sg = stg + (q * NG + g) * (SG_FLOATS + SH_FLOATS), *sh = sg + SG_FLOATS;
+        const int tq = sw2 * 32 + lane;                    // thread index within the (quarter, group)'s 64 threads
+        // the one cell this thread updates: line cl of the group, unit slot cj of the quarter
         const int cl = tq >> 3, cj = tq & 7;
         const int cu = (int)rank * p.U + 8 * q + cj;
-        const int cql = chunk * NL + cl;
+        const int cql = chunk * NL + g * GL + cl;
         const bool cv = cql < p.nseq && (8 * q + cj) < p.U && cu < hid;
         const int clen = cql < p.nseq ? min(max(p.lens ? p.lens[cql] : p.T, 0), p.T) : 0;
         const int cqq = cql < p.nseq ? cql : 0;
@@ -224,43 +230,49 @@ __global__ void __launch_bounds__(LTHREADS, 1) k_lstm_rec_tc(LstmTcParams p) {
         if (cv) for (int tt = clen; tt < p.T; ++tt) p.out[(size_t)(cbase + (long long)tt * p.step) * OC + dir * hid + cu] = 0.f;
         float *optr = p.out + (size_t)(cbase + (long long)(dir ? max(clen - 1, 0) : 0) * p.step) * OC + dir * hid + cu;
         const long long ostride = (long long)(dir ? -1 : 1) * p.step * OC;
-        // gx of this thread's TMEM row (gate g of unit u) for its LPW lines: running pointers, +-one time step per iteration
-        int glen[LPW]; const float *gptr[LPW];
+        // gx of this thread's TMEM row (gate of unit u) for its LPW lines: running pointers, fetched one time step ahead
+        int glen[LPW]; const float *gptr[LPW]; float gxn[LPW];
         const long long gstride = (long long)(dir ? -1 : 1) * p.step * GC;
 #pragma unroll
         for (int i = 0; i < LPW; ++i) {
-            const int ql = chunk * NL + LPW * sw + i;
+            const int ql = chunk * NL + g * GL + LPW * sw2 + i;
             const bool v = ql < p.nseq && uvalid;
             glen[i] = v ? min(max(p.lens ? p.lens[ql] : p.T, 0), p.T) : 0;
             const int qq = ql < p.nseq ? ql : 0;
             const long long gb = (long long)(qq / p.q2) * p.s_outer + (long long)(qq % p.q2) * p.s_inner;
             const int t0 = dir ? max(glen[i] - 1, 0) : 0;
-            gptr[i] = p.gx + (size_t)(gb + (long long)t0 * p.step) * GC + (size_t)dir * 4 * hid + (size_t)(uvalid ? u : 0) * 4 + g;
+            gptr[i] = p.gx + (size_t)(gb + (long long)t0 * p.step) * GC + (size_t)dir * 4 * hid + (size_t)(uvalid ? u : 0) * 4 + gate;
+            gxn[i] = 0 < glen[i] ? __ldg(gptr[i]) : 0.f;
+            gptr[i] += gstride;
         }
-        uint32_t rB[LCS], rFull[LCS];
+        // destinations of this lane's share of the hand-off: lanes 0..15 send to CTAs 0..3, lanes 16..31 to CTAs 4..7
+        uint32_t rB[LCS / 2], rFull[LCS / 2];
 #pragma unroll
-        for (int r = 0; r < LCS; ++r) { rB[r] = mapa32(smem_u32(sB), (uint32_t)r); rFull[r] = mapa32(smem_u32(b_full), (uint32_t)r); }
-        const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(LPW * sw);
+        for (int r = 0; r < LCS / 2; ++r) {
+            const uint32_t dst = (uint32_t)((lane >> 4) * (LCS / 2) + r);
+            rB[r] = mapa32(smem_u32(sB), dst); rFull[r] = mapa32(smem_u32(b_full), dst);
+        }
+        const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * 64 + LPW * sw2);
         // gate non-linearity without divergence: sigmoid(x) for i, f, o; tanh(x) = 2*sigmoid(2x) - 1 for the candidate gate
-        const float act_k = g == 2 ? 2.f : 1.f;
+        const float act_k = gate == 2 ? 2.f : 1.f;
+        const int bar_id = 1 + q + 4 * g;
 
         for (int s = 0; s < maxlen; ++s) {
             const int nxt = (s + 1) & 1;
             float gxv[LPW];
 #pragma unroll
             for (int i = 0; i < LPW; ++i) {
-                gxv[i] = s < glen[i] ? __ldg(gptr[i]) : 0.f;
+                gxv[i] = gxn[i];
+                gxn[i] = s + 1 < glen[i] ? __ldg(gptr[i]) : 0.f;
                 gptr[i] += gstride;
             }
-            const long long e_pre = p.dbg ? clock64() : 0;
-            mbar_wait(mma_done, (uint32_t)(s & 1));
+            mbar_wait(&mma_done[g], (uint32_t)(s & 1));
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const long long e0 = p.dbg ? clock64() : 0;
-            // D1a = cols 0..31 [W1 h1 | W1 h2s], D1b = 32..63 (k-atoms 2,3), D2a = 64..79, D2b = 80..95 [W2s h1]
+            // group columns: D1a = [W1 h1 (8) | W1 h2s (8)] k-atoms 0,1; D1b @16 k-atoms 2,3; D2a @32 = [W2s h1 | -]; D2b @48
             uint32_t m0[LPW], m1[LPW], c0[LPW], c1[LPW], c2[LPW], c3[LPW];
-            tmem_ld4_nowait(lane_base + 0, m0);  tmem_ld4_nowait(lane_base + 32, m1);
-            tmem_ld4_nowait(lane_base + 16, c0); tmem_ld4_nowait(lane_base + 48, c1);
-            tmem_ld4_nowait(lane_base + 64, c2); tmem_ld4_nowait(lane_base + 80, c3);
+            tmem_ld4_nowait(lane_base + 0, m0);  tmem_ld4_nowait(lane_base + 16, m1);
+            tmem_ld4_nowait(lane_base + 8, c0);  tmem_ld4_nowait(lane_base + 24, c1);
+            tmem_ld4_nowait(lane_base + 32, c2); tmem_ld4_nowait(lane_base + 48, c3);
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
 #pragma unroll
@@ -268,11 +280,9 @@ __global__ void __launch_bounds__(LTHREADS, 1) k_lstm_rec_tc(LstmTcParams p) {
                 const float main_ = __uint_as_float(m0[i]) + __uint_as_float(m1[i]);
                 const float corr = (__uint_as_float(c0[i]) + __uint_as_float(c1[i])) + (__uint_as_float(c2[i]) + __uint_as_float(c3[i]));
                 const float pre = (main_ + corr * (1.f / X2_SCALE)) + gxv[i];
-                sg[((LPW * sw + i) * 8 + jq) * 4 + g] = fmaf(sigmoid_fast(pre * act_k), act_k, 1.f - act_k);
+                sg[((LPW * sw2 + i) * 8 + jq) * 4 + gate] = fmaf(sigmoid_fast(pre * act_k), act_k, 1.f - act_k);
             }
-            const long long e1 = p.dbg ? clock64() : 0;
-            named_bar(1 + q, 32 * EW);
-            const long long e2 = p.dbg ? clock64() : 0;
+            named_bar(bar_id, 64);
             {
                 const float4 gt = *reinterpret_cast<const float4 *>(&sg[(cl * 8 + cj) * 4]);      // i, f, g, o
                 float h = 0.f;                             // finished / padding cells feed zeros (never used again)
@@ -284,11 +294,10 @@ __global__ void __launch_bounds__(LTHREADS, 1) k_lstm_rec_tc(LstmTcParams p) {
                 }
                 sh[cl * 8 + cj] = h;
             }
-            const long long e3 = p.dbg ? clock64() : 0;
-            named_bar(1 + q, 32 * EW);
-            if (s + 1 < maxlen && sw == 0) {
-                // chunk = 8 unit slots of one line in one fp16 plane: row = plane*16 + line of the k-atom tile
-                const int plane = lane >> 4, line = lane & 15;
+            named_bar(bar_id, 64);
+            if (s + 1 < maxlen && sw2 == 0) {
+                // chunk = 8 unit slots of one line in one fp16 plane: row = plane*8 + line of the group's k-atom tile
+                const int ci = lane & 15, plane = ci >> 3, line = ci & 7;
                 const float4 x0 = *reinterpret_cast<const float4 *>(&sh[line * 8]), x1 = *reinterpret_cast<const float4 *>(&sh[line * 8 + 4]);
                 const float xs[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
                 uint32_t pk[4];
@@ -304,15 +313,12 @@ __global__ void __launch_bounds__(LTHREADS, 1) k_lstm_rec_tc(LstmTcParams p) {
                     }
                     pk[e] = two[0] | (two[1] << 16);
                 }
-                const int k0 = (int)rank * 32 + 8 * q, ka = k0 >> 6, c = (k0 & 63) >> 3, row = plane * NL + line;
-                const uint32_t off = (uint32_t)(nxt * B_BUF_B + ka * B_TILE_B + row * 128 + ((c ^ (row & 7)) << 4));
+                const int k0 = (int)rank * 32 + 8 * q, ka = k0 >> 6, c = (k0 & 63) >> 3, row = plane * GL + line;
+                const uint32_t off = (uint32_t)((g * 2 + nxt) * B_BUF_B + ka * B_TILE_B + row * 128 + ((c ^ (row & 7)) << 4));
                 const uint4 v = make_uint4(pk[0], pk[1], pk[2], pk[3]);
 #pragma unroll
-                for (int r = 0; r < LCS; ++r) st_async_v4(rB[r] + off, v, rFull[r] + (uint32_t)nxt * 8u);
+                for (int r = 0; r < LCS / 2; ++r) st_async_v4(rB[r] + off, v, rFull[r] + (uint32_t)(g * 2 + nxt) * 8u);
             }
-            if (p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && warp == 1 && lane == 0 && (s == 100 || s == 101))
-                printf("[tcrec] s=%d EPI  loop_top=%lld mma_done=%lld | wait %lld tmem+act %lld bar %lld cell %lld bar+pack+send %lld\n",
-                       s, e_pre, e0, e0 - e_pre, e1 - e0, e2 - e1, e3 - e2, clock64() - e3);
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -323,7 +329,6 @@ __global__ void __launch_bounds__(LTHREADS, 1) k_lstm_rec_tc(LstmTcParams p) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TM_COLS) : "memory");
     }
 }
-
 
 // ------------------------------------------------------------------------------------------------------------------------
 // Small-hidden variant (hid <= 32: the blla 2-D BiLSTM sweeps Lbx32 / Lby32): one CTA, no cluster.
