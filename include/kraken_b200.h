@@ -124,6 +124,21 @@ int  kb_recognize(kb_model *m, const float *lines, int lines_on_device, int32_t 
                   int32_t *labels, int32_t *starts, int32_t *ends, float *confs, int32_t *counts,
                   int32_t max_out, int32_t *out_lens, float *probs, int probs_on_device, void *stream);
 
+/* ---- fused recognition on uint8 line images --------------------------------
+ * Same as kb_recognize, but the lines arrive as the uint8 tensors `v2.PILToTensor()` produces and the rest of
+ * ImageInputTransforms runs on the device, bit-identical to the reference:
+ *   v2.ToDtype(float32, scale=True)  x.to(float32).mul_(1.0/255)   kraken/lib/dataset/utils.py:148-149
+ *   tensor_invert                    im.max() - im                 kraken/lib/functional_im_transforms.py:58-59
+ *   zero right-padding to the batch width                           kraken/lib/vgsl/rpred.py:129-131
+ * lines: n x C x h x w uint8 (host or device).  widths (n, or NULL): columns >= widths[i] are fed as 0 whatever the
+ * buffer holds.  invert_max (n, or NULL = no inversion): per line the maximum pixel value of the un-padded crop
+ * (im.max() * 255; 255 for anything that contains white), or a negative value to skip the inversion of that line.
+ * A quarter of the host-to-device bytes of the float call.                                                       */
+int  kb_recognize_u8(kb_model *m, const uint8_t *lines, int lines_on_device, int32_t n, int32_t h, int32_t w,
+                     const int32_t *widths, const int16_t *invert_max, float temperature, int32_t *labels, int32_t *starts,
+                     int32_t *ends, float *confs, int32_t *counts, int32_t max_out, int32_t *out_lens, float *probs,
+                     int probs_on_device, void *stream);
+
 /* ---- decoder hook -------------------------------------------------------------------------------
  * replaces kraken.lib.ctc_decoder.greedy_decoder (ctc_decoder.py:35-72) for a (N, C, W) probability
  * tensor; lens: n int32 (NULL => all W, as the reference allows for N == 1).                        */

@@ -60,6 +60,7 @@ _SIGS = {
     'kb_model_device': (C.c_int, [_vp]),
     'kb_forward': (C.c_int, [_vp, _vp, C.c_int, _i32, _i32, _i32, _vp, _vp, C.c_int, _vp, _vp]),
     'kb_recognize': (C.c_int, [_vp, _vp, C.c_int, _i32, _i32, _i32, _vp, _f, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, C.c_int, _vp]),
+    'kb_recognize_u8': (C.c_int, [_vp, _vp, C.c_int, _i32, _i32, _i32, _vp, _vp, _f, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, C.c_int, _vp]),
     'kb_ctc_greedy_decode': (C.c_int, [_vp, C.c_int, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _i32, C.c_int, _vp]),
     'kb_segment': (C.c_int, [_vp, _vp, C.c_int, _i32, _i32, _i32, _i32, _i32, _vp, C.c_int, _vp]),
     'kb_debug_layer_output': (C.c_int, [_vp, C.c_char_p, _pi32, _vp, C.c_int]),

@@ -90,6 +90,8 @@ struct kb_model {
     int *h_flag = nullptr;           // pinned copy, valid after the stream is synchronised
     bool force_ffma = false;         // second attempt of a call whose first attempt raised the flag: fp32 CUDA-core kernels only
     int64_t overflow_reruns = 0;
+    uint8_t *u8_raw = nullptr; size_t u8_raw_cap = 0;       // kb_recognize_u8: device copy of host uint8 lines
+    float *u8_f32 = nullptr; size_t u8_f32_cap = 0;         // ... and their float form (the network input)
     double prof_us[4] = {0, 0, 0, 0}; int64_t prof_calls = 0;    // KB_HOST_PROF: host microseconds in plan / launch / wait / unpack
     bool fuse = true;                // fused layer groups (KB_FUSE=0 runs every layer on its own, e.g. for layer taps)
     bool use_tc = true;              // tcgen05 GEMM path (KB_GEMM=ffma forces the CUDA-core kernel)
@@ -100,6 +102,8 @@ struct kb_model {
             if (arena.base) cudaFree(arena.base);
             if (pinned) cudaFreeHost(pinned);
             if (h_flag) cudaFreeHost(h_flag);
+            if (u8_raw) cudaFree(u8_raw);
+            if (u8_f32) cudaFree(u8_f32);
             for (auto &e : stages) { if (e.a) cudaEventDestroy(e.a); if (e.b) cudaEventDestroy(e.b); }
         }
     }
@@ -654,8 +658,21 @@ struct Exec {
                 const int tw = 2 * ppb + c0.kw - 1, th = c0.kh + 1;
                 const size_t smem = ((size_t)((th * tw + 3) & ~3) + (size_t)c0.kh * c0.kw * c0.cout) * sizeof(float);
                 if (smem > 48 * 1024) throw Unsupported(c0.name + ": filter bank too large for the fused stencil kernel");
-                dim3 grid((unsigned)((dpool.w + ppb - 1) / ppb), (unsigned)dpool.h, (unsigned)dpool.n);
-                LAUNCH(m, k_conv1_pool, grid, 256, smem, st, cp);
+                if (c0.kh == 3 && c0.kw == 3 && (w.ncp % 4) == 0 && !(getenv("KB_CONV1") && strcmp(getenv("KB_CONV1"), "generic") == 0)) {
+                    // register-resident 3x3 filter bank, strips of 8 pooled rows per block
+                    constexpr int RP = 8;
+                    dim3 grid3((unsigned)((dpool.w + ppb - 1) / ppb), (unsigned)((dpool.h + RP - 1) / RP), (unsigned)dpool.n);
+                    const size_t sm3 = (size_t)2 * 4 * (2 * ppb + 2) * sizeof(float);
+                    switch (c0.cout) {                                         // patch elements per thread = ceil(4 * (2 * ppb + 2) / 256)
+                    case 64: LAUNCH(m, (k_conv1_pool33<RP, 2>), grid3, 256, sm3, st, cp); break;
+                    case 32: LAUNCH(m, (k_conv1_pool33<RP, 3>), grid3, 256, sm3, st, cp); break;
+                    case 16: LAUNCH(m, (k_conv1_pool33<RP, 5>), grid3, 256, sm3, st, cp); break;
+                    default: LAUNCH(m, (k_conv1_pool33<RP, 9>), grid3, 256, sm3, st, cp); break;
+                    }
+                } else {
+                    dim3 grid((unsigned)((dpool.w + ppb - 1) / ppb), (unsigned)dpool.h, (unsigned)dpool.n);
+                    LAUNCH(m, k_conv1_pool, grid, 256, smem, st, cp);
+                }
             }
             advance_lens(c0, lens, din, dconv);
             advance_lens(*pl, lens, dconv, dpool);
@@ -1114,6 +1131,9 @@ int kb_model_finalize(kb_model *m, int device) {
             m->pinned = nullptr; m->pinned_cap = 0;
             if (m->h_flag) cudaFreeHost(m->h_flag);
             m->h_flag = nullptr;
+            if (m->u8_raw) cudaFree(m->u8_raw);
+            if (m->u8_f32) cudaFree(m->u8_f32);
+            m->u8_raw = nullptr; m->u8_f32 = nullptr; m->u8_raw_cap = m->u8_f32_cap = 0;
             for (auto &e : m->stages) { if (e.a) cudaEventDestroy(e.a); if (e.b) cudaEventDestroy(e.b); }
             m->stages.clear(); m->n_stages = 0;
         }
@@ -1157,15 +1177,12 @@ int kb_forward(kb_model *m, const float *x, int x_on_device, int32_t n, int32_t 
     });
 }
 
-int kb_recognize(kb_model *m, const float *lines, int lines_on_device, int32_t n, int32_t h, int32_t w, const int32_t *widths,
+}  // extern "C" (reopened below)
+
+static int recognize_locked(kb_model *m, const float *lines, int lines_on_device, int32_t n, int32_t h, int32_t w, const int32_t *widths,
                  float temperature, int32_t *labels, int32_t *starts, int32_t *ends, float *confs, int32_t *counts,
                  int32_t max_out, int32_t *out_lens, float *probs, int probs_on_device, void *stream) {
-    if (!m || !lines || !labels || !starts || !ends || !confs || !counts) return fail(KB_ERR_ARG, "NULL argument");
-    if (max_out <= 0) return fail(KB_ERR_ARG, "max_out must be positive");
-    if (!(temperature > 0.f)) return fail(KB_ERR_ARG, "temperature must be positive");
-    std::lock_guard<std::mutex> lk(m->mu);
-    return guarded([&]() {
-        ensure_ready(m);
+    {
         cudaStream_t st = (cudaStream_t)stream;
         Dims d; d.n = n; d.c = m->plan->input[1]; d.h = h; d.w = w; Lens l;
         infer(*m->plan->root, d, l);
@@ -1197,6 +1214,63 @@ int kb_recognize(kb_model *m, const float *lines, int lines_on_device, int32_t n
         if (out_lens) for (int i = 0; i < n; ++i) out_lens[i] = olens[i];
         collect_timing(m);
         return KB_OK;
+    }
+}
+
+
+extern "C" {
+
+int kb_recognize(kb_model *m, const float *lines, int lines_on_device, int32_t n, int32_t h, int32_t w, const int32_t *widths,
+                 float temperature, int32_t *labels, int32_t *starts, int32_t *ends, float *confs, int32_t *counts,
+                 int32_t max_out, int32_t *out_lens, float *probs, int probs_on_device, void *stream) {
+    if (!m || !lines || !labels || !starts || !ends || !confs || !counts) return fail(KB_ERR_ARG, "NULL argument");
+    if (max_out <= 0) return fail(KB_ERR_ARG, "max_out must be positive");
+    if (!(temperature > 0.f)) return fail(KB_ERR_ARG, "temperature must be positive");
+    std::lock_guard<std::mutex> lk(m->mu);
+    return guarded([&]() {
+        ensure_ready(m);
+        return recognize_locked(m, lines, lines_on_device, n, h, w, widths, temperature, labels, starts, ends, confs, counts, max_out,
+                                out_lens, probs, probs_on_device, stream);
+    });
+}
+
+int kb_recognize_u8(kb_model *m, const uint8_t *lines, int lines_on_device, int32_t n, int32_t h, int32_t w, const int32_t *widths,
+                    const int16_t *invert_max, float temperature, int32_t *labels, int32_t *starts, int32_t *ends, float *confs,
+                    int32_t *counts, int32_t max_out, int32_t *out_lens, float *probs, int probs_on_device, void *stream) {
+    if (!m || !lines || !labels || !starts || !ends || !confs || !counts) return fail(KB_ERR_ARG, "NULL argument");
+    if (max_out <= 0) return fail(KB_ERR_ARG, "max_out must be positive");
+    if (!(temperature > 0.f)) return fail(KB_ERR_ARG, "temperature must be positive");
+    if (n <= 0 || h <= 0 || w <= 0) return fail(KB_ERR_SHAPE, "empty input batch");
+    std::lock_guard<std::mutex> lk(m->mu);
+    return guarded([&]() {
+        ensure_ready(m);
+        cudaStream_t st = (cudaStream_t)stream;
+        const int C = m->plan->input[1];
+        const size_t elems = (size_t)n * C * h * w;
+        const size_t meta = ((size_t)n * 6 + 15) & ~(size_t)15;                   // widths (int32) + invert_max (int16) behind the pixels
+        if (elems + meta + 16 > m->u8_raw_cap) {
+            CK(cudaStreamSynchronize(st));
+            if (m->u8_raw) cudaFree(m->u8_raw);
+            m->u8_raw = nullptr; m->u8_raw_cap = 0;
+            CK(cudaMalloc((void **)&m->u8_raw, elems + meta + 16));
+            m->u8_raw_cap = elems + meta + 16;
+        }
+        if (elems * sizeof(float) > m->u8_f32_cap) {
+            CK(cudaStreamSynchronize(st));
+            if (m->u8_f32) cudaFree(m->u8_f32);
+            m->u8_f32 = nullptr; m->u8_f32_cap = 0;
+            CK(cudaMalloc((void **)&m->u8_f32, elems * sizeof(float)));
+            m->u8_f32_cap = elems * sizeof(float);
+        }
+        const uint8_t *src = lines;
+        if (!lines_on_device) { CK(cudaMemcpyAsync(m->u8_raw, lines, elems, cudaMemcpyHostToDevice, st)); src = m->u8_raw; }
+        uint8_t *mp = m->u8_raw + ((elems + 15) & ~(size_t)15);
+        int *d_w = nullptr; short *d_inv = nullptr;
+        if (widths) { d_w = (int *)mp; CK(cudaMemcpyAsync(d_w, widths, (size_t)n * 4, cudaMemcpyHostToDevice, st)); }
+        if (invert_max) { d_inv = (short *)(mp + (size_t)n * 4); CK(cudaMemcpyAsync(d_inv, invert_max, (size_t)n * 2, cudaMemcpyHostToDevice, st)); }
+        LAUNCH(m, k_u8_lines_to_f32, grid1d((long long)elems, 256, m->sm_count), 256, 0, st, src, m->u8_f32, (int)n, C, (int)h, (int)w, d_w, d_inv);
+        return recognize_locked(m, m->u8_f32, 1, n, h, w, widths, temperature, labels, starts, ends, confs, counts, max_out, out_lens,
+                                probs, probs_on_device, stream);
     });
 }
 

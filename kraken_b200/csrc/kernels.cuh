@@ -81,6 +81,28 @@ __device__ __forceinline__ void store_planes8(__half *hi, __half *lo, const floa
 }
 
 // =============================================================================================
+// uint8 line images -> the network's float input, on the device.  Reproduces, bit for bit,
+//   v2.ToDtype(float32, scale=True)   = x.to(float32).mul_(1.0 / 255)          (torchvision to_dtype_image)
+//   tensor_invert                     = im.max() - im                            (kraken/lib/functional_im_transforms.py:58-59)
+//   zero right-padding to the batch width                                         (kraken/lib/vgsl/rpred.py:129-131)
+// of ImageInputTransforms (kraken/lib/dataset/utils.py:148-151).  inv_max[n] >= 0: the line's maximum pixel value (the caller
+// knows it from the crop; 255 for a white-padded page), < 0: no inversion.  Columns >= widths[n] become 0.
+// =============================================================================================
+__global__ void k_u8_lines_to_f32(const uint8_t *__restrict__ src, float *__restrict__ dst, int n_lines, int C, int H, int W,
+                                  const int *__restrict__ widths, const short *__restrict__ inv_max) {
+    const float s = (float)(1.0 / 255);
+    const long long per = (long long)C * H * W, total = per * n_lines;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int n = (int)(i / per), w = (int)(i % W);
+        float x = __fmul_rn((float)src[i], s);
+        const int im = inv_max ? inv_max[n] : -1;
+        if (im >= 0) x = __fsub_rn(__fmul_rn((float)im, s), x);
+        if (widths && w >= widths[n]) x = 0.f;
+        dst[i] = x;
+    }
+}
+
+// =============================================================================================
 // batched transpose  in[B][R][C] -> out[B][C][R]   (NCHW <-> NHWC at the ABI edge)
 // =============================================================================================
 __global__ void k_transpose(const float *__restrict__ in, float *__restrict__ out, int R, int C) {
@@ -291,6 +313,93 @@ __global__ void __launch_bounds__(256) k_conv1_pool(Conv1PoolParams p) {
         store_planes8(p.y_hi + off, p.y_lo + off, o, bad);
         if (bad) atomicOr(p.flag, 1);
     }
+}
+
+// 3x3 specialisation of the fused stencil (cfg2's first layer): the filter bank lives in REGISTERS (9 taps x 8 channels = 36
+// packed pairs per thread) and a block walks a strip of RP pooled rows, so per pooled pixel a thread issues 8 LDS.64 for its
+// 4x4 input patch, 144 FFMA2 and the epilogue; the generic kernel above reloads the bank per block and reads 2 LDS.128 of
+// weights per tap (measured 0.107 ms on cfg2 = 5x its FMA bound).
+template <int RP, int NE>                     // NE = ceil(4 * tw / 256): patch elements per thread
+__global__ void __launch_bounds__(256) k_conv1_pool33(Conv1PoolParams p) {
+    extern __shared__ float c1_sm[];                                   // [2][4][tw]
+    const int cgroups = p.Cout >> 3, ppb = 256 / cgroups;
+    const int tw = 2 * ppb + 2;
+    const int n = blockIdx.z, wp0 = blockIdx.x * ppb;
+    const int tid = threadIdx.x, cg_i = tid % cgroups, px = tid / cgroups, wp = wp0 + px;
+    unsigned long long wr[9][4];
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+        const float4 a = __ldg(reinterpret_cast<const float4 *>(p.wt + (size_t)t * p.Ncp + cg_i * 8));
+        const float4 b = __ldg(reinterpret_cast<const float4 *>(p.wt + (size_t)t * p.Ncp + cg_i * 8 + 4));
+        wr[t][0] = pack2f(a.x, a.y); wr[t][1] = pack2f(a.z, a.w); wr[t][2] = pack2f(b.x, b.y); wr[t][3] = pack2f(b.z, b.w);
+    }
+    float bias[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) bias[c] = p.bias ? __ldg(p.bias + cg_i * 8 + c) : 0.f;
+    const float *img = p.x + (size_t)n * p.H * p.W;
+    const int w0 = 2 * wp0 - p.px;
+    const int hp_end = min(p.Hp, ((int)blockIdx.y + 1) * RP);
+    bool bad = false;
+    int buf = 0;
+    // the 4 x tw input patch of a pooled row: NE elements per thread, fetched one row AHEAD into registers so that the global
+    // latency hides under the previous row's FMAs
+    float pre[NE];
+    auto fetch = [&](int hp) {
+        const int h0 = 2 * hp - p.py;
+#pragma unroll
+        for (int e = 0; e < NE; ++e) {
+            const int i = tid + e * 256;
+            const int r = (i >= tw) + (i >= 2 * tw) + (i >= 3 * tw), c = i - r * tw, hi = h0 + r, wi = w0 + c;
+            pre[e] = (i < 4 * tw && hi >= 0 && hi < p.H && wi >= 0 && wi < p.W) ? __ldg(img + (size_t)hi * p.W + wi) : 0.f;
+        }
+    };
+    fetch(blockIdx.y * RP);
+    for (int hp = blockIdx.y * RP; hp < hp_end; ++hp, buf ^= 1) {
+        float *s_in = c1_sm + buf * 4 * tw;
+#pragma unroll
+        for (int e = 0; e < NE; ++e) { const int i = tid + e * 256; if (i < 4 * tw) s_in[i] = pre[e]; }
+        __syncthreads();
+        if (hp + 1 < hp_end) fetch(hp + 1);
+        if (wp < p.Wp) {
+            float v[4][4];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const float2 a = *reinterpret_cast<const float2 *>(s_in + r * tw + 2 * px), b = *reinterpret_cast<const float2 *>(s_in + r * tw + 2 * px + 2);
+                v[r][0] = a.x; v[r][1] = a.y; v[r][2] = b.x; v[r][3] = b.y;
+            }
+            unsigned long long acc2[4][4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) acc2[q][c] = 0ull;
+#pragma unroll
+            for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+                for (int kx = 0; kx < 3; ++kx) {
+                    const float in4[4] = {v[ky][kx], v[ky][kx + 1], v[ky + 1][kx], v[ky + 1][kx + 1]};
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) ffma2_bcast(acc2[q][c], wr[ky * 3 + kx][c], in4[q]);
+                }
+            float o[8];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                float a0, a1, b0, b1, c0, c1, d0, d1;
+                unpack2f(acc2[0][c], a0, a1); unpack2f(acc2[1][c], b0, b1); unpack2f(acc2[2][c], c0, c1); unpack2f(acc2[3][c], d0, d1);
+                o[2 * c] = fmaxf(fmaxf(a0, b0), fmaxf(c0, d0)) + bias[2 * c];            // + b commutes with max
+                o[2 * c + 1] = fmaxf(fmaxf(a1, b1), fmaxf(c1, d1)) + bias[2 * c + 1];
+            }
+            act_apply_vec(o, p.act);
+            const size_t off = (((size_t)n * p.Hp + hp) * p.Wp + wp) * p.Cout + cg_i * 8;
+            if (p.y) {
+                *reinterpret_cast<float4 *>(p.y + off) = make_float4(o[0], o[1], o[2], o[3]);
+                *reinterpret_cast<float4 *>(p.y + off + 4) = make_float4(o[4], o[5], o[6], o[7]);
+            }
+            if (p.y_hi) store_planes8(p.y_hi + off, p.y_lo + off, o, bad);
+        }
+    }
+    if (bad) atomicOr(p.flag, 1);
 }
 
 // softmax over the feature axis of NHWC rows, in place ('m' convs, layers.py:817-818). One warp per pixel.

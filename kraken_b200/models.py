@@ -90,6 +90,35 @@ class TorchSeqRecognizer:
         return {'labels': labels, 'starts': starts, 'ends': ends, 'confs': confs, 'counts': counts,
                 'olens': olens if lens is not None else None}
 
+    def recognize_u8(self, lines_u8, widths=None, invert_max=None) -> dict:
+        """One `kb_recognize_u8` call on uint8 line images (N, C, H, W) as `v2.PILToTensor()` yields them; scaling to
+        [0, 1], `tensor_invert` and the zero right-padding of `ImageInputTransforms` / `_recognize_*_lines`
+        (kraken/lib/dataset/utils.py:148-151, kraken/lib/vgsl/rpred.py:129-131) run on the device, bit-identical to the
+        reference.  `invert_max`: per line `int(im.max())` of the un-padded crop (None: no inversion).  Returns the same
+        blocks as `_recognize_raw`."""
+        net = self.nn
+        x = lines_u8 if isinstance(lines_u8, torch.Tensor) else torch.as_tensor(np.ascontiguousarray(lines_u8))
+        if x.dtype != torch.uint8 or x.ndim != 4:
+            raise ValueError('expected a uint8 NCHW tensor')
+        x = x.contiguous()
+        net._ensure_finalized(x)
+        n, c, h, w = (int(v) for v in x.shape)
+        wd = np.ascontiguousarray(torch.as_tensor(widths).cpu().numpy(), dtype=np.int32) if widths is not None else None
+        inv = np.ascontiguousarray(np.asarray(invert_max), dtype=np.int16) if invert_max is not None else None
+        dims = net.infer_dims(n, h, w)
+        if dims[2] != 1:
+            raise KrakenInputException('Expected dimension 3 to be 1, actual {}'.format(tuple(dims)))
+        T = dims[3]
+        stride = max(T, 1)
+        labels = np.zeros((n, stride), np.int32); starts = np.zeros((n, stride), np.int32); ends = np.zeros((n, stride), np.int32)
+        confs = np.zeros((n, stride), np.float32); counts = np.zeros(n, np.int32); olens = np.zeros(n, np.int32)
+        check(lib.kb_recognize_u8(net._h, x.data_ptr(), int(x.is_cuda), n, h, w, wd.ctypes.data if wd is not None else None,
+                                  inv.ctypes.data if inv is not None else None, float(self.temperature), labels.ctypes.data,
+                                  starts.ctypes.data, ends.ctypes.data, confs.ctypes.data, counts.ctypes.data, stride, olens.ctypes.data,
+                                  None, 0, _stream_for(x, net._device)))
+        return {'labels': labels, 'starts': starts, 'ends': ends, 'confs': confs, 'counts': counts,
+                'olens': olens if widths is not None else None}
+
     # -- reference surface ------------------------------------------------------------------------
     def forward(self, line: torch.Tensor, lens: Optional[torch.Tensor] = None):
         """(N, C, H, W) lines -> ((N, C, W) softmax numpy array, output lengths) - models.py:93-119."""

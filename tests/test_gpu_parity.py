@@ -396,3 +396,40 @@ def test_fp16_operand_range_fallback():
     out2, _ = m.nn(x.cuda())                               # the next in-range call is back on the tensor cores
     assert m.range_fallback_count == 1
     assert rel_err(out2, ref) <= TIGHT
+
+
+def test_recognize_u8_matches_reference_transforms():
+    """kb_recognize_u8: uint8 lines in, ToDtype(scale) + tensor_invert + zero right-padding on the device
+    (kraken/lib/dataset/utils.py:148-151, functional_im_transforms.py:58-59, rpred.py:129-131).  The device arithmetic is
+    bit-identical to torch's, so the result must EQUAL the float call fed with the CPU-transformed batch, and match the oracle."""
+    spec = '[1,16,0,1 Cr3,3,32 Mp2,2 Cr3,3,64 Mp2,2 S1(1x0)1,3 Lbx40 O1c13]'
+    om = vo.OracleModel(spec)
+    wts = om.init_like_reference(9)
+    m = kb.TorchVGSLModel(vgsl=spec)
+    m.load_state_dict(wts)
+    m.to('cuda:0')
+    rec = kb.TorchSeqRecognizer(m, device='cuda:0')
+    g = torch.Generator().manual_seed(9)
+    n, h, wmax = 5, 16, 200
+    widths = torch.tensor([200, 150, 33, 8, 199])
+    raw = torch.randint(0, 256, (n, 1, h, wmax), generator=g, dtype=torch.uint8)
+    raw[1] = raw[1].clamp(max=201)                       # a line whose maximum is not 255
+    inv_max, batch = [], torch.zeros(n, 1, h, wmax)
+    for i, wd in enumerate(widths.tolist()):
+        im = raw[i, :, :, :wd].to(torch.float32).mul_(1.0 / 255)      # v2.ToDtype(float32, scale=True)
+        inv_max.append(int(raw[i, :, :, :wd].max()))
+        batch[i, :, :, :wd] = im.max() - im                            # tensor_invert; the rest stays 0 (rpred.py:130)
+    ref_out, ref_l, _, ref_dec = vo.rec_predict(om, batch, widths)
+    a = rec.recognize_u8(raw, widths, inv_max)
+    b = rec._recognize_raw(batch.cuda(), widths, want_probs=False)
+    c = rec.recognize_u8(raw.cuda(), widths, inv_max)
+    for k in ('labels', 'starts', 'ends', 'counts', 'olens'):
+        assert np.array_equal(a[k], b[k]) and np.array_equal(c[k], b[k]), k
+    assert np.array_equal(a['confs'], b['confs'])         # same bits: the conversion is exact
+    for i in range(n):
+        got = [(int(a['labels'][i, j]), int(a['starts'][i, j]), int(a['ends'][i, j])) for j in range(int(a['counts'][i]))]
+        assert got == [(l, s, e) for l, s, e, _ in ref_dec[i]]
+    # no inversion, no widths
+    d = rec.recognize_u8(raw[:2])
+    e = rec._recognize_raw(raw[:2].to(torch.float32).mul_(1.0 / 255).cuda(), None, want_probs=False)
+    assert np.array_equal(d['labels'], e['labels']) and np.array_equal(d['confs'], e['confs'])
