@@ -340,6 +340,9 @@ def main():
     NB = 4                                               # distinct input batches rotated through the steps
     host = [b.pin_memory() for b in make_batches(NB, 1000 + rank)]
     devb = [b.to(dev) for b in host]
+    # the same kind of lines as uint8 crops: scale / invert / pad run on the device inside kb_recognize_u8
+    host_u8 = [(b * 255).to(torch.uint8).pin_memory() for b in host]
+    inv255 = np.full(BATCH, 255, np.int16)
     T = WIDTH // 4
 
     def step(x):
@@ -359,7 +362,7 @@ def main():
         dist.gather(tdev, out, dst=0)
         return out
 
-    def run_pipelined(batches, steps, sink):
+    def run_pipelined(batches, steps, sink, u8=False):
         import threading
         res = [None] * steps
         errs = []
@@ -369,7 +372,10 @@ def main():
                 torch.cuda.set_device(local)
                 with torch.cuda.stream(streams[k]):
                     for i in range(k, steps, len(recs)):
-                        res[i] = recs[k]._recognize_raw(batches[i % NB], lens, want_probs=False)
+                        if u8:
+                            res[i] = recs[k].recognize_u8(batches[i % NB], lens, inv255)
+                        else:
+                            res[i] = recs[k]._recognize_raw(batches[i % NB], lens, want_probs=False)
             except Exception as e:       # surface worker failures in the main thread
                 errs.append(e)
         cur = torch.cuda.current_stream()
@@ -386,12 +392,12 @@ def main():
             raise errs[0]
         sink.extend(res)
 
-    def timed(batches, steps, sink, on_step=None, pipelined=False):
+    def timed(batches, steps, sink, on_step=None, pipelined=False, u8=False):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         if pipelined and len(recs) > 1:
-            run_pipelined(batches, steps, sink)
+            run_pipelined(batches, steps, sink, u8)
         else:
             for i in range(steps):
                 sink.append(step(batches[i % NB]))
@@ -412,6 +418,7 @@ def main():
         step(devb[i % NB]); step(host[i % NB])
     if len(recs) > 1:
         run_pipelined(host, 2 * len(recs), [])
+        run_pipelined(host_u8, 2 * len(recs), [], u8=True)
     if world > 1:
         gather_all([step(devb[0])])          # warm the NCCL gather up (lazy communicator / channel setup) before timing
         ms_warm = torch.zeros(1, device=dev); dist.all_reduce(ms_warm, op=dist.ReduceOp.MAX)
@@ -438,6 +445,7 @@ def main():
     results_buf2 = []
     ms_e2e_serial = timed(host, args.steps, [])
     ms_e2e = timed(host, args.steps, results_buf2, pipelined=True)
+    ms_e2e_u8 = timed(host_u8, args.steps, [], pipelined=True, u8=True) if len(recs) > 1 else None
 
     if rank != 0:
         if world > 1:
@@ -480,11 +488,15 @@ def main():
             'data': 'synthetic',
             'config': {'workload': 'cfg2', 'spec': CFG2, 'batch_per_gpu': BATCH, 'global_batch': BATCH * world, 'line': f'{HEIGHT}x{WIDTH}',
                        'parallelism': f'replicas x{world} (independent line shards, 1 weight broadcast + 1 result gather)',
-                       'l2': f'{NB} rotating input batches; ~0.77 GB of activations per step > 126 MB L2'},
+                       'l2': f'{NB} rotating input batches; ~0.3 GB of activations per step > 126 MB L2'},
             'e2e': {'value': e2e, 'unit': UNIT, 'ms_per_step': ms_e2e / args.steps, 'in_flight': len(recs),
                     'serial_value': world * BATCH * args.steps / (ms_e2e_serial / 1e3),
                     'h2d_bytes_per_step': BATCH * HEIGHT * WIDTH * 4, 'd2h_bytes_per_step': d2h,
                     'api': 'TorchSeqRecognizer._recognize_raw -> kb_recognize, pinned host lines in, label blocks out'},
+            'e2e_u8': None if ms_e2e_u8 is None else {
+                'value': world * BATCH * args.steps / (ms_e2e_u8 / 1e3), 'unit': UNIT, 'ms_per_step': ms_e2e_u8 / args.steps,
+                'in_flight': len(recs), 'h2d_bytes_per_step': BATCH * HEIGHT * WIDTH + BATCH * 6, 'd2h_bytes_per_step': d2h,
+                'api': 'TorchSeqRecognizer.recognize_u8 -> kb_recognize_u8: pinned uint8 lines in; ToDtype(scale) + tensor_invert + padding on the device'},
             'gpu_launches': int(launches), 'clocks': clocks, 'roofline': roof, 'cpu_baseline': cpu,
             'decoded_labels_last_step': int(results_buf[-1]['counts'].sum()) if results_buf else 0}
     print(json.dumps(line), flush=True)
