@@ -512,7 +512,7 @@ struct Exec {
                     // hid <= 32 (blla's Lbx32 / Lby32): 64 sequences per CTA, W_hh in tensor memory, no cluster
                     ltc::LstmTcParams tp;
                     tp.gx = lp.gx; tp.wpk = (const uint16_t *)w.wpk; tp.out = lp.out; tp.lens = lp.lens; tp.nseq = lp.nseq; tp.T = lp.T;
-                    tp.dbg = 0; tp.hid = hid; tp.dirs = dirs; tp.U = hid; tp.q2 = lp.q2; tp.s_outer = lp.s_outer; tp.s_inner = lp.s_inner; tp.step = lp.step;
+                    tp.dbg = 0; tp.dbgbuf = nullptr; tp.hid = hid; tp.dirs = dirs; tp.U = hid; tp.q2 = lp.q2; tp.s_outer = lp.s_outer; tp.s_inner = lp.s_inner; tp.step = lp.step;
                     int snl = lp.nseq * dirs >= 64 * 2 * sm ? 64 : lp.nseq * dirs >= 16 * 4 * sm ? 32 : 16;      // fill the SMs first, then grow the CTAs
                     if (getenv("KB_LSTM_SNL")) snl = atoi(getenv("KB_LSTM_SNL"));
                     if (snl != 64 && snl != 32) snl = 16;
@@ -533,19 +533,42 @@ struct Exec {
                 } else if (rec_tc) {
                     ltc::LstmTcParams tp;
                     tp.gx = lp.gx; tp.wpk = (const uint16_t *)w.wpk; tp.out = lp.out; tp.lens = lp.lens; tp.nseq = lp.nseq; tp.T = lp.T;
-                    tp.dbg = getenv("KB_LSTM_DBG") ? 1 : 0; tp.hid = hid; tp.dirs = dirs; tp.U = lp.U; tp.q2 = lp.q2; tp.s_outer = lp.s_outer; tp.s_inner = lp.s_inner; tp.step = lp.step;
+                    tp.dbg = getenv("KB_LSTM_DBG") ? atoi(getenv("KB_LSTM_DBG")) : 0; tp.hid = hid; tp.dirs = dirs; tp.U = lp.U; tp.q2 = lp.q2; tp.s_outer = lp.s_outer; tp.s_inner = lp.s_inner; tp.step = lp.step;
                     static bool attr_set = false;
-                    if (!attr_set) { CK(cudaFuncSetAttribute(ltc::k_lstm_rec_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, ltc::LSMEM_BYTES)); attr_set = true; }
+                    if (!attr_set) {
+                        CK(cudaFuncSetAttribute(ltc::k_lstm_rec_tc<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, ltc::ClusterCfg<8>::SMEM_BYTES));
+                        CK(cudaFuncSetAttribute(ltc::k_lstm_rec_tc<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, ltc::ClusterCfg<16>::SMEM_BYTES));
+                        attr_set = true;
+                    }
+                    // lines per cluster: 16 (two groups of 8); KB_LSTM_GL=16 selects 32 (two groups of 16: half the SMs per batch, but
+                    // the longer epilogue stretches the per-step latency chain by 1.7x)
+                    int gl = 8;                                  // measured on cfg2: 32 lines per cluster = 0.54 ms vs 0.31 ms, and no e2e gain
+                    if (getenv("KB_LSTM_GL")) gl = atoi(getenv("KB_LSTM_GL")) == 16 ? 16 : 8;
+                    const int nl = 2 * gl;
                     cudaLaunchConfig_t tcfg = {};
-                    tcfg.gridDim = dim3((unsigned)(ltc::LCS * ((lp.nseq + ltc::NL - 1) / ltc::NL)), (unsigned)dirs, 1);
+                    tcfg.gridDim = dim3((unsigned)(ltc::LCS * ((lp.nseq + nl - 1) / nl)), (unsigned)dirs, 1);
                     tcfg.blockDim = dim3(ltc::LTHREADS, 1, 1);
-                    tcfg.dynamicSmemBytes = ltc::LSMEM_BYTES; tcfg.stream = st;
+                    tcfg.dynamicSmemBytes = gl == 16 ? ltc::ClusterCfg<16>::SMEM_BYTES : ltc::ClusterCfg<8>::SMEM_BYTES; tcfg.stream = st;
                     cudaLaunchAttribute tat[1];
                     tat[0].id = cudaLaunchAttributeClusterDimension;
                     tat[0].val.clusterDim.x = ltc::LCS; tat[0].val.clusterDim.y = 1; tat[0].val.clusterDim.z = 1;
                     tcfg.attrs = tat; tcfg.numAttrs = 1;
-                    if (getenv("KB_DEBUG")) fprintf(stderr, "[kb] %s: tcgen05 recurrence, %u clusters of 8, T=%d\n", n.name.c_str(), tcfg.gridDim.x / 8 * dirs, lp.T);
-                    CK(cudaLaunchKernelEx(&tcfg, ltc::k_lstm_rec_tc, tp));
+                    if (getenv("KB_DEBUG")) fprintf(stderr, "[kb] %s: tcgen05 recurrence, %u clusters of 8 CTAs x %d lines, T=%d\n", n.name.c_str(), tcfg.gridDim.x / 8 * dirs, nl, lp.T);
+                    tp.dbgbuf = nullptr;
+                    if (tp.dbg & 1) { CK(cudaMalloc((void **)&tp.dbgbuf, 64 * sizeof(long long))); CK(cudaMemset(tp.dbgbuf, 0, 64 * sizeof(long long))); }
+                    if (gl == 16) CK(cudaLaunchKernelEx(&tcfg, ltc::k_lstm_rec_tc<16>, tp));
+                    else CK(cudaLaunchKernelEx(&tcfg, ltc::k_lstm_rec_tc<8>, tp));
+                    if (tp.dbg & 1) {
+                        long long hb[64];
+                        CK(cudaMemcpy(hb, tp.dbgbuf, sizeof(hb), cudaMemcpyDeviceToHost));
+                        cudaFree(tp.dbgbuf);
+                        const long long t0 = hb[1];
+                        for (int i = 0; i < 8; ++i) {
+                            const long long *d = hb + i * 8;
+                            fprintf(stderr, "[tcrec] step %d group %d: mma_wait_from %lld  h_ready %lld  mma_issued %lld | epi_loop_top %lld  mma_done %lld  act_end %lld  cell_end %lld  sent %lld\n",
+                                    100 + i / 2, i & 1, d[0] - t0, d[1] - t0, d[2] - t0, d[7] - t0, d[3] - t0, d[4] - t0, d[5] - t0, d[6] - t0);
+                        }
+                    }
                     ++m->launches;
                     CK(cudaPeekAtLastError());
                 } else {

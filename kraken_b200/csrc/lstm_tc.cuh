@@ -37,29 +37,33 @@ namespace ltc {
 
 using namespace kb::tc;
 
-constexpr int NL = 16;                                   // lines per cluster
 constexpr int NG = 2;                                    // independent line groups per cluster, processed in ping-pong (version 5)
-constexpr int GL = NL / NG;                              // 8 lines per group
 constexpr int LCS = 8;                                   // cluster size
 constexpr int A_PLANE_ELEMS = 128 * 256;                 // fp16 elements of one W plane of a CTA: [128 gate rows][K = 256], row-major
-constexpr int B_ROWS = 2 * GL;                           // 16 rows per group: h1 | h2s
-constexpr int B_TILE_B = B_ROWS * 128;                   // 2048 bytes per k-atom
-constexpr int B_BUF_B = 4 * B_TILE_B;                    // 8192 bytes per (group, buffer)
-constexpr int SG_FLOATS = GL * 8 * 4;                    // per (TMEM lane quarter, group): [line][unit][gate]
-constexpr int SH_FLOATS = GL * 8;                        // per (quarter, group): [line][unit]
-constexpr int STG_BYTES = 4 * NG * (SG_FLOATS + SH_FLOATS) * 4;
-constexpr int LSMEM_BYTES = NG * 2 * B_BUF_B + STG_BYTES + 128 + 1024;
 constexpr int EW = 4;                                    // epilogue warps per TMEM lane quarter: 2 per group (latency hiding: v3 with 1 was 2x slower)
-constexpr int LPW = 4;                                   // lines per epilogue warp in the activation phase
 constexpr int LTHREADS = 32 + 4 * EW * 32;               // warp 0: MMA issue / TMEM alloc; warps 1..16: epilogue
-constexpr int TM_COLS = 512;                             // D of group g @64g: D1a (16), D1b @16, D2a @32, D2b @48;  A: W1 @128 (128), W2s @256 (128)
-constexpr int TM_A0 = 128;
+constexpr int TM_COLS = 512;
+template <int GL> struct ClusterCfg {                    // GL = lines per group: 8 (16 lines per cluster) or 16 (32 lines per cluster)
+    static constexpr int NL = NG * GL;                   // lines per cluster
+    static constexpr int CH_B = 2 * GL * 16;             // bytes of one k-chunk (8 unit slots) of a group: [h1 lines | h2s lines] x 16 B
+    static constexpr int B_BUF_B = 32 * CH_B;            // bytes per (group, buffer): K = 256 = 32 chunks
+    static constexpr int SX_BYTES = 4 * NG * 2 * CH_B;   // outgoing chunk staging per (quarter, group), double buffered
+    static constexpr int SG_FLOATS = GL * 8 * 4;         // per (TMEM lane quarter, group): [line][unit][gate]
+    static constexpr int SH_FLOATS = GL * 8;             // per (quarter, group): [line][unit]
+    static constexpr int STG_BYTES = 4 * NG * (SG_FLOATS + SH_FLOATS) * 4;
+    static constexpr int SMEM_BYTES = NG * 2 * B_BUF_B + STG_BYTES + SX_BYTES + 128 + 1024;
+    static constexpr int LPW = GL / 2;                   // lines per epilogue warp in the activation phase
+    static constexpr int N2 = 16;                        // N of the W2s x h1 product (UMMA minimum; only the first GL columns are read)
+    static constexpr int GSTRIDE = GL == 8 ? 64 : 128;   // TMEM columns per group: D1a @0 (2 GL), D1b @2 GL, D2a @4 GL (16), D2b @4 GL + 16
+    static constexpr int TM_A0 = NG * GSTRIDE;           // A: W1 @TM_A0 (128 columns), W2s @TM_A0 + 128
+    static constexpr int CPT = GL / 8;                   // cells per thread in the update phase
+};
 
 struct LstmTcParams {
     const float *gx; const uint16_t *wpk; float *out; const int *lens;
     int nseq, T, hid, dirs, U;
     int q2; long long s_outer, s_inner, step;
-    int dbg;
+    int dbg; long long *dbgbuf;      // KB_LSTM_DBG: bit 0 = clock64 stamps of steps 100..103 of cluster 0 into dbgbuf[step][group][8]
 };
 
 __device__ __forceinline__ void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
@@ -107,18 +111,51 @@ __device__ __forceinline__ void mbar_wait_cluster(uint64_t *bar, uint32_t parity
         "bra CW_%=;\n\t"
         "CD_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
+// K-major operand WITHOUT swizzle: core matrices (8 rows x 16 bytes, 128 contiguous bytes) `lbo` bytes apart along K and `sbo`
+// bytes apart along M/N.  The h operand uses it because one (CTA, lane quarter) produces exactly whole core matrices (8 lines x
+// 8 unit slots per plane), so its share of the hand-off is ONE contiguous block per destination.
+__device__ __forceinline__ uint64_t umma_desc_nosw(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+    d |= (uint64_t)(lbo >> 4) << 16;
+    d |= (uint64_t)(sbo >> 4) << 32;
+    d |= (uint64_t)1 << 46;                           // descriptor version (sm_100); layout type 0 = no swizzle
+    return d;
+}
+// shared::cta -> (remote) shared::cluster bulk copy, byte-counted by the destination's mbarrier: one transaction per block
+// instead of one per 16 bytes (512 st.async.v4 per buffer and step made the hand-off ~1100 cycles, KB_LSTM_DBG=1)
+__device__ __forceinline__ void bulk_s2s(uint32_t dst_cluster, uint32_t src_cta, uint32_t bytes, uint32_t mbar_cluster) {
+    asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst_cluster), "r"(src_cta), "r"(bytes), "r"(mbar_cluster) : "memory");
+}
+// non-suspending poll (mbarrier.test_wait): try_wait may park the warp for an implementation-defined time, and on the critical
+// path of the recurrence (h hand-off -> MMA issue -> epilogue) the wake-up latency is paid twice per time step
+__device__ __forceinline__ void mbar_wait_poll(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "PW_%=:\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra PD_%=;\n\t"
+        "bra PW_%=;\n\t"
+        "PD_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
 // gate non-linearities on the SFU: ex2.approx + rcp, absolute error ~1e-7 (the CUDA-core kernel keeps expf/tanhf)
 __device__ __forceinline__ float rcp_fast(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }   // MUFU.RCP, no IEEE fix-up path
 __device__ __forceinline__ float sigmoid_fast(float x) { return rcp_fast(1.f + __expf(-x)); }
 __device__ __forceinline__ float tanh_fast(float x) { return fmaf(2.f, sigmoid_fast(2.f * x), -1.f); }
 __device__ __forceinline__ void named_bar(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 
+template <int GL>
 __global__ void __launch_bounds__(LTHREADS, 1) k_lstm_rec_tc(LstmTcParams p) {
+    using Cfg = ClusterCfg<GL>;
+    constexpr int NL = Cfg::NL, CH_B = Cfg::CH_B, B_BUF_B = Cfg::B_BUF_B, SG_FLOATS = Cfg::SG_FLOATS, SH_FLOATS = Cfg::SH_FLOATS;
+    constexpr int STG_BYTES = Cfg::STG_BYTES, LPW = Cfg::LPW, TM_A0 = Cfg::TM_A0, GSTRIDE = Cfg::GSTRIDE, CPT = Cfg::CPT;
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = smem_align1024(smem_raw);
-    uint8_t *sB = smem;                                   // [group][buffer][k-atom][16 rows x 128 B]
+    uint8_t *sB = smem;                                   // [group][buffer][k-chunk][plane][line][8 unit slots] fp16 = core matrices, no swizzle
     float *stg = reinterpret_cast<float *>(sB + NG * 2 * B_BUF_B);
-    uint64_t *bars = reinterpret_cast<uint64_t *>(sB + NG * 2 * B_BUF_B + STG_BYTES);
+    uint8_t *sx = sB + NG * 2 * B_BUF_B + STG_BYTES;      // [quarter][group][2][CH_B]
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sB + NG * 2 * B_BUF_B + STG_BYTES + Cfg::SX_BYTES);
     uint64_t *b_full = bars /* [group][2] */, *mma_done = bars + 4 /* [group] */;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 6);
 
@@ -176,35 +213,44 @@ __global__ void __launch_bounds__(LTHREADS, 1) k_lstm_rec_tc(LstmTcParams p) {
 
     if (warp == 0) {
         // ===================== MMA issuer: alternates between the two line groups =====================
-        const uint32_t id = idesc_f16(0, 0, 128, 2 * GL);
+        const uint32_t id1 = idesc_f16(0, 0, 128, 2 * GL), id2 = idesc_f16(0, 0, 128, Cfg::N2);
         for (int s = 0; s < maxlen; ++s) {
             const int cur = s & 1;
 #pragma unroll 1
             for (int g = 0; g < NG; ++g) {
                 uint64_t *bf = &b_full[g * 2 + cur];
-                if (s > 0) mbar_wait(bf, (uint32_t)(((s - 1) >> 1) & 1));       // default acquire.cta: an acquire.cluster wait costs a CCTL.IVALL per step
+                const long long d_w0 = (p.dbg & 1) ? clock64() : 0;
+                if (s > 0) {                                                     // default acquire.cta: an acquire.cluster wait costs a CCTL.IVALL per step
+                    if (p.dbg & 2) mbar_wait(bf, (uint32_t)(((s - 1) >> 1) & 1));
+                    else mbar_wait_poll(bf, (uint32_t)(((s - 1) >> 1) & 1));
+                }
+                const long long d_w1 = (p.dbg & 1) ? clock64() : 0;
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // st.async writes -> UMMA (async proxy) reads
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 if (elect_one()) {
                     // this buffer is refilled during step s+1 (nobody can send that before receiving our h_s)
                     if (s + 2 < maxlen) mbar_expect_tx(bf, B_BUF_B);
                     const uint32_t b0 = smem_u32(sB + (g * 2 + cur) * B_BUF_B);
-                    const uint32_t dg = tmem_base + (uint32_t)(g * 64);
+                    const uint32_t dg = tmem_base + (uint32_t)(g * GSTRIDE);
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
 #pragma unroll
                         for (int kk = 0; kk < 4; ++kk) {
                             const int ka = kk == 0 ? 0 : kk == 1 ? 2 : kk == 2 ? 1 : 3;      // 0,2,1,3: same-chain MMAs 4 issues apart
                             const int half = ka >> 1;
-                            const uint64_t bd = umma_desc_sw128(b0 + (uint32_t)(ka * B_TILE_B)) + (uint64_t)(2 * k);
+                            const uint64_t bd = umma_desc_nosw(b0 + (uint32_t)((ka * 4 + k) * 2 * CH_B), (uint32_t)CH_B, 128u);   // K16 = chunks 2j, 2j+1
                             const uint32_t a1 = tmem_base + (uint32_t)(TM_A0 + ka * 32 + k * 8);      // K = 16 -> 8 columns of fp16 pairs
                             const uint32_t a2 = a1 + 128u;
                             const uint32_t first = ((ka & 1) == 0 && k == 0) ? 0u : 1u;
-                            umma_f16_ts(dg + (uint32_t)(half * 16), a1, bd, id, first);          // [W1 h1 | W1 h2s]
-                            umma_f16_ts(dg + (uint32_t)(32 + half * 16), a2, bd, id, first);     // [W2s h1 | (W2s h2s: unused, N must be >= 16)]
+                            umma_f16_ts(dg + (uint32_t)(half * 2 * GL), a1, bd, id1, first);                 // [W1 h1 | W1 h2s]
+                            umma_f16_ts(dg + (uint32_t)(4 * GL + half * Cfg::N2), a2, bd, id2, first);     // W2s x first 16 rows of B (h1; N >= 16)
                         }
                     }
                     umma_commit(&mma_done[g]);
+                    if ((p.dbg & 1) && blockIdx.x == 0 && blockIdx.y == 0 && s >= 100 && s < 104) {
+                        long long *d = p.dbgbuf + ((s - 100) * 2 + g) * 8;
+                        d[0] = d_w0; d[1] = d_w1; d[2] = clock64();
+                    }
                 }
                 __syncwarp();
             }
@@ -216,18 +262,24 @@ __global__ void __launch_bounds__(LTHREADS, 1) k_lstm_rec_tc(LstmTcParams p) {
         const int jq = lane >> 2, gate = lane & 3;         // unit slot within the quarter, gate of this thread's TMEM row
         const int slot = 8 * q + jq, u = (int)rank * p.U + slot;
         const bool uvalid = slot < p.U && u < hid;
-        float *sg = stg + (q * NG + g) * (SG_FLOATS + SH_FLOATS), *sh = sg + SG_FLOATS;
+        float *sg = stg + (q * NG + g) * (SG_FLOATS + SH_FLOATS);
         const int tq = sw2 * 32 + lane;                    // thread index within the (quarter, group)'s 64 threads
-        // the one cell this thread updates: line cl of the group, unit slot cj of the quarter
-        const int cl = tq >> 3, cj = tq & 7;
+        // the CPT cells this thread updates: line cl of the group, unit slots cj .. cj + CPT - 1 of the quarter
+        const int cl = (tq * CPT) >> 3, cj = (tq * CPT) & 7;
         const int cu = (int)rank * p.U + 8 * q + cj;
         const int cql = chunk * NL + g * GL + cl;
-        const bool cv = cql < p.nseq && (8 * q + cj) < p.U && cu < hid;
+        bool cv[CPT];
+#pragma unroll
+        for (int e = 0; e < CPT; ++e) cv[e] = cql < p.nseq && (8 * q + cj + e) < p.U && cu + e < hid;
         const int clen = cql < p.nseq ? min(max(p.lens ? p.lens[cql] : p.T, 0), p.T) : 0;
         const int cqq = cql < p.nseq ? cql : 0;
         const long long cbase = (long long)(cqq / p.q2) * p.s_outer + (long long)(cqq % p.q2) * p.s_inner;
-        float cst = 0.f;
-        if (cv) for (int tt = clen; tt < p.T; ++tt) p.out[(size_t)(cbase + (long long)tt * p.step) * OC + dir * hid + cu] = 0.f;
+        float cst[CPT];
+#pragma unroll
+        for (int e = 0; e < CPT; ++e) {
+            cst[e] = 0.f;
+            if (cv[e]) for (int tt = clen; tt < p.T; ++tt) p.out[(size_t)(cbase + (long long)tt * p.step) * OC + dir * hid + cu + e] = 0.f;
+        }
         float *optr = p.out + (size_t)(cbase + (long long)(dir ? max(clen - 1, 0) : 0) * p.step) * OC + dir * hid + cu;
         const long long ostride = (long long)(dir ? -1 : 1) * p.step * OC;
         // gx of this thread's TMEM row (gate of unit u) for its LPW lines: running pointers, fetched one time step ahead
@@ -245,14 +297,10 @@ __global__ void __launch_bounds__(LTHREADS, 1) k_lstm_rec_tc(LstmTcParams p) {
             gxn[i] = 0 < glen[i] ? __ldg(gptr[i]) : 0.f;
             gptr[i] += gstride;
         }
-        // destinations of this lane's share of the hand-off: lanes 0..15 send to CTAs 0..3, lanes 16..31 to CTAs 4..7
-        uint32_t rB[LCS / 2], rFull[LCS / 2];
-#pragma unroll
-        for (int r = 0; r < LCS / 2; ++r) {
-            const uint32_t dst = (uint32_t)((lane >> 4) * (LCS / 2) + r);
-            rB[r] = mapa32(smem_u32(sB), dst); rFull[r] = mapa32(smem_u32(b_full), dst);
-        }
-        const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * 64 + LPW * sw2);
+        // hand-off: lane r < 8 of the group's first warp copies this (quarter, group)'s chunk to CTA r
+        const uint32_t dstB = mapa32(smem_u32(sB), (uint32_t)(lane & 7)), dstFull = mapa32(smem_u32(b_full), (uint32_t)(lane & 7));
+        uint8_t *sxq = sx + (q * NG + g) * 2 * CH_B;
+        const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * GSTRIDE + LPW * sw2);
         // gate non-linearity without divergence: sigmoid(x) for i, f, o; tanh(x) = 2*sigmoid(2x) - 1 for the candidate gate
         const float act_k = gate == 2 ? 2.f : 1.f;
         const int bar_id = 1 + q + 4 * g;
@@ -266,13 +314,22 @@ __global__ void __launch_bounds__(LTHREADS, 1) k_lstm_rec_tc(LstmTcParams p) {
                 gxn[i] = s + 1 < glen[i] ? __ldg(gptr[i]) : 0.f;
                 gptr[i] += gstride;
             }
-            mbar_wait(&mma_done[g], (uint32_t)(s & 1));
+            const long long e_top = (p.dbg & 1) ? clock64() : 0;
+            if (p.dbg & 4) mbar_wait_poll(&mma_done[g], (uint32_t)(s & 1));
+            else mbar_wait(&mma_done[g], (uint32_t)(s & 1));
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            // group columns: D1a = [W1 h1 (8) | W1 h2s (8)] k-atoms 0,1; D1b @16 k-atoms 2,3; D2a @32 = [W2s h1 | -]; D2b @48
+            const long long e_done = (p.dbg & 1) ? clock64() : 0;
+            // group columns: D1a = [W1 h1 (GL) | W1 h2s (GL)] k-atoms 0,1; D1b @2 GL k-atoms 2,3; D2a @4 GL = W2s h1; D2b @4 GL + 16
             uint32_t m0[LPW], m1[LPW], c0[LPW], c1[LPW], c2[LPW], c3[LPW];
-            tmem_ld4_nowait(lane_base + 0, m0);  tmem_ld4_nowait(lane_base + 16, m1);
-            tmem_ld4_nowait(lane_base + 8, c0);  tmem_ld4_nowait(lane_base + 24, c1);
-            tmem_ld4_nowait(lane_base + 32, c2); tmem_ld4_nowait(lane_base + 48, c3);
+            if (LPW == 4) {
+                tmem_ld4_nowait(lane_base + 0, m0);      tmem_ld4_nowait(lane_base + 2 * GL, m1);
+                tmem_ld4_nowait(lane_base + GL, c0);     tmem_ld4_nowait(lane_base + 3 * GL, c1);
+                tmem_ld4_nowait(lane_base + 4 * GL, c2); tmem_ld4_nowait(lane_base + 4 * GL + Cfg::N2, c3);
+            } else {
+                tmem_ld8_nowait(lane_base + 0, m0);      tmem_ld8_nowait(lane_base + 2 * GL, m1);
+                tmem_ld8_nowait(lane_base + GL, c0);     tmem_ld8_nowait(lane_base + 3 * GL, c1);
+                tmem_ld8_nowait(lane_base + 4 * GL, c2); tmem_ld8_nowait(lane_base + 4 * GL + Cfg::N2, c3);
+            }
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
 #pragma unroll
@@ -282,42 +339,39 @@ __global__ void __launch_bounds__(LTHREADS, 1) k_lstm_rec_tc(LstmTcParams p) {
                 const float pre = (main_ + corr * (1.f / X2_SCALE)) + gxv[i];
                 sg[((LPW * sw2 + i) * 8 + jq) * 4 + gate] = fmaf(sigmoid_fast(pre * act_k), act_k, 1.f - act_k);
             }
+            const long long e_act = (p.dbg & 1) ? clock64() : 0;
             named_bar(bar_id, 64);
             {
-                const float4 gt = *reinterpret_cast<const float4 *>(&sg[(cl * 8 + cj) * 4]);      // i, f, g, o
-                float h = 0.f;                             // finished / padding cells feed zeros (never used again)
-                if (cv && s < clen) {
-                    cst = gt.y * cst + gt.x * gt.z;
-                    h = gt.w * tanh_fast(cst);
-                    *optr = h;
-                    optr += ostride;
-                }
-                sh[cl * 8 + cj] = h;
-            }
-            named_bar(bar_id, 64);
-            if (s + 1 < maxlen && sw2 == 0) {
-                // chunk = 8 unit slots of one line in one fp16 plane: row = plane*8 + line of the group's k-atom tile
-                const int ci = lane & 15, plane = ci >> 3, line = ci & 7;
-                const float4 x0 = *reinterpret_cast<const float4 *>(&sh[line * 8]), x1 = *reinterpret_cast<const float4 *>(&sh[line * 8 + 4]);
-                const float xs[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
-                uint32_t pk[4];
+                const bool live = s < clen;
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    uint32_t two[2];
-#pragma unroll
-                    for (int f = 0; f < 2; ++f) {
-                        const float x = xs[2 * e + f];
-                        const __half h1 = __float2half_rn(x);
-                        const __half h2 = __float2half_rn((x - __half2float(h1)) * X2_SCALE);
-                        two[f] = (uint32_t)__half_as_ushort(plane == 0 ? h1 : h2);
+                for (int e = 0; e < CPT; ++e) {
+                    const float4 gt = *reinterpret_cast<const float4 *>(&sg[(cl * 8 + cj + e) * 4]);      // i, f, g, o
+                    float h = 0.f;                         // finished / padding cells feed zeros (never used again)
+                    if (cv[e] && live) {
+                        cst[e] = gt.y * cst[e] + gt.x * gt.z;
+                        h = gt.w * tanh_fast(cst[e]);
+                        optr[e] = h;
                     }
-                    pk[e] = two[0] | (two[1] << 16);
+                    // both fp16 planes of h straight into the outgoing chunk: [plane][line][unit slot]
+                    const __half h1 = __float2half_rn(h);
+                    const __half h2 = __float2half_rn((h - __half2float(h1)) * X2_SCALE);
+                    __half *cx = reinterpret_cast<__half *>(sxq + (s & 1) * CH_B);
+                    cx[cl * 8 + cj + e] = h1;
+                    cx[(GL + cl) * 8 + cj + e] = h2;
                 }
-                const int k0 = (int)rank * 32 + 8 * q, ka = k0 >> 6, c = (k0 & 63) >> 3, row = plane * GL + line;
-                const uint32_t off = (uint32_t)((g * 2 + nxt) * B_BUF_B + ka * B_TILE_B + row * 128 + ((c ^ (row & 7)) << 4));
-                const uint4 v = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-#pragma unroll
-                for (int r = 0; r < LCS / 2; ++r) st_async_v4(rB[r] + off, v, rFull[r] + (uint32_t)(g * 2 + nxt) * 8u);
+                if (live) optr += ostride;
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic writes -> the bulk copy engine (async proxy)
+            }
+            const long long e_cell = (p.dbg & 1) ? clock64() : 0;
+            named_bar(bar_id, 64);
+            if (s + 1 < maxlen && sw2 == 0 && lane < LCS) {
+                const uint32_t kc = (uint32_t)rank * 4u + (uint32_t)q;                 // this quarter's k-chunk: unit slots 8 kc .. 8 kc + 7
+                bulk_s2s(dstB + (uint32_t)((g * 2 + nxt) * B_BUF_B) + kc * (uint32_t)CH_B, smem_u32(sxq + (s & 1) * CH_B), (uint32_t)CH_B,
+                         dstFull + (uint32_t)(g * 2 + nxt) * 8u);
+            }
+            if ((p.dbg & 1) && blockIdx.x == 0 && blockIdx.y == 0 && (warp == 1 || warp == 9) && lane == 0 && s >= 100 && s < 104) {
+                long long *d = p.dbgbuf + ((s - 100) * 2 + g) * 8;
+                d[3] = e_done; d[4] = e_act; d[5] = e_cell; d[6] = clock64(); d[7] = e_top;
             }
         }
     }

@@ -333,13 +333,13 @@ def test_tensor_core_recurrence(hid):
     m = kb.TorchVGSLModel(vgsl=spec)
     m.load_state_dict(wts)
     m.to('cuda:0')
-    for tc in (1, 0):
-        with env(KB_LSTM_TC=tc):
+    for tc, gl in ((1, 8), (1, 16), (0, 8)):             # tensor-core kernel with 16 / 32 lines per cluster, CUDA-core kernel
+        with env(KB_LSTM_TC=tc, KB_LSTM_GL=gl):
             out, ol = m.nn(x.cuda(), lens)
             dec = kb.TorchSeqRecognizer(m, device='cuda:0').predict_labels(x.cuda(), lens)
-        assert rel_err(out, ref) <= TIGHT, (tc, rel_err(out, ref))
+        assert rel_err(out, ref) <= TIGHT, (tc, gl, rel_err(out, ref))
         assert ol.tolist() == rl.tolist()
-        assert triples(dec) == triples(ref_dec), tc
+        assert triples(dec) == triples(ref_dec), (tc, gl)
 
 
 @pytest.mark.parametrize('spec,n,h,w,ragged', [
