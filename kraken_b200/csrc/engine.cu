@@ -494,6 +494,12 @@ struct Exec {
             Tensor gx = mk(dg);
             Dims dfull = din; dfull.c = dirs * hid;
             Tensor full = mk(dfull);
+            // the tensor-core recurrences can emit the consumer's fp16 operand planes themselves (no k_split_f16 pass)
+            const int ks_p = hid <= 32 ? 1 : hid <= 64 ? 2 : hid <= 128 ? 4 : 8;
+            const bool tc_rec = (ks_p == 8 || ks_p == 1) && w.wpk && m->use_tc && !(getenv("KB_LSTM_TC") && atoi(getenv("KB_LSTM_TC")) == 0);
+            const bool lplanes = planes_hint && tc_rec && !n.summarize;
+            planes_hint = false;
+            if (lplanes) { full.hi = (__half *)m->arena.alloc((size_t)full.numel() * 2); full.lo = (__half *)m->arena.alloc((size_t)full.numel() * 2); }
             int *dl = packed ? dev_lens(lens) : nullptr;
             if (full.numel()) { StageTimer tt(m, st, n.name + ".xproj", !dry); gemm(x, w, nullptr, ACT_LINEAR, gx.p, x.h, x.w); }
             if (!dry && full.numel()) {
@@ -511,7 +517,8 @@ struct Exec {
                 if (ks == 1 && tc_on) {
                     // hid <= 32 (blla's Lbx32 / Lby32): 64 sequences per CTA, W_hh in tensor memory, no cluster
                     ltc::LstmTcParams tp;
-                    tp.gx = lp.gx; tp.wpk = (const uint16_t *)w.wpk; tp.out = lp.out; tp.lens = lp.lens; tp.nseq = lp.nseq; tp.T = lp.T;
+                    tp.gx = lp.gx; tp.wpk = (const uint16_t *)w.wpk; tp.out = (lplanes && !m->keep_fp32) ? nullptr : lp.out; tp.lens = lp.lens; tp.nseq = lp.nseq; tp.T = lp.T;
+                    tp.out_hi = full.hi; tp.out_lo = full.lo;
                     tp.dbg = 0; tp.dbgbuf = nullptr; tp.hid = hid; tp.dirs = dirs; tp.U = hid; tp.q2 = lp.q2; tp.s_outer = lp.s_outer; tp.s_inner = lp.s_inner; tp.step = lp.step;
                     int snl = lp.nseq * dirs >= 64 * 2 * sm ? 64 : lp.nseq * dirs >= 16 * 4 * sm ? 32 : 16;      // fill the SMs first, then grow the CTAs
                     if (getenv("KB_LSTM_SNL")) snl = atoi(getenv("KB_LSTM_SNL"));
@@ -532,7 +539,8 @@ struct Exec {
                     CK(cudaPeekAtLastError());
                 } else if (rec_tc) {
                     ltc::LstmTcParams tp;
-                    tp.gx = lp.gx; tp.wpk = (const uint16_t *)w.wpk; tp.out = lp.out; tp.lens = lp.lens; tp.nseq = lp.nseq; tp.T = lp.T;
+                    tp.gx = lp.gx; tp.wpk = (const uint16_t *)w.wpk; tp.out = (lplanes && !m->keep_fp32) ? nullptr : lp.out; tp.lens = lp.lens; tp.nseq = lp.nseq; tp.T = lp.T;
+                    tp.out_hi = full.hi; tp.out_lo = full.lo;
                     tp.dbg = getenv("KB_LSTM_DBG") ? atoi(getenv("KB_LSTM_DBG")) : 0; tp.hid = hid; tp.dirs = dirs; tp.U = lp.U; tp.q2 = lp.q2; tp.s_outer = lp.s_outer; tp.s_inner = lp.s_inner; tp.step = lp.step;
                     static bool attr_set = false;
                     if (!attr_set) {
@@ -780,7 +788,11 @@ struct Exec {
                 size_t used = 0;
                 if (m->fuse) used = try_fuse(n, i, cur, lens);
                 if (used) { i += used; continue; }
-                if (n.children[i]->kind == K_GN && m->fuse) planes_hint = wants_planes(n, i + 1, dims_of(cur));
+                if (m->fuse && (n.children[i]->kind == K_GN || n.children[i]->kind == K_LSTM)) {
+                    Dims dn = dims_of(cur);
+                    if (n.children[i]->kind == K_LSTM) { Lens ltmp; dn = leaf_dims(*n.children[i], dn); (void)ltmp; }
+                    planes_hint = wants_planes(n, i + 1, dn);
+                }
                 cur = run(*n.children[i], cur, lens);
                 planes_hint = false;
                 ++i;
@@ -967,7 +979,7 @@ static void decode_and_fetch(kb_model *m, int dev_sm, int n, int T, int max_out,
     char *d = (char *)arena.alloc(blk);
     int *o_lab = (int *)d, *o_start = (int *)(d + per * 4), *o_end = (int *)(d + per * 8);
     float *o_conf = (float *)(d + per * 12); int *o_cnt = (int *)(d + per * 16);
-    k_ctc_collapse<<<(unsigned)((n + 3) / 4), 128, 0, st>>>(d_lab, d_conf, d_lens, n, T, max_out, o_lab, o_start, o_end, o_conf, o_cnt);
+    k_ctc_collapse<<<(unsigned)n, 256, (size_t)((T + 31) / 32 + 1) * sizeof(int), st>>>(d_lab, d_conf, d_lens, n, T, max_out, o_lab, o_start, o_end, o_conf, o_cnt);
     ++*launches;
     CK(cudaPeekAtLastError());
     if (blk > *pinned_cap) {

@@ -969,23 +969,48 @@ __global__ void k_col_argmax(const float *__restrict__ probs, int N, int C, int 
     lab[idx] = bi; conf[idx] = be;
 }
 
-// One warp per line: runs of equal labels; blank (0) runs dropped; (label, first t, last t, max conf of run).
-__global__ void k_ctc_collapse(const int *__restrict__ lab, const float *__restrict__ conf, const int *__restrict__ lens,
+// CTC collapse (ctc_decoder.py:55-72): runs of equal labels; blank (0) runs dropped; (label, first t, last t, max conf of run).
+// One block (8 warps) per line: pass 1 counts the run starts of every 32-step chunk, warp 0 scans the counts, pass 2 writes the
+// runs at their final positions.  (The first version walked the chunks of a line serially in one warp: 7 dependent global
+// round trips = 28 us for cfg2's T = 200, a third of the decode stage.)
+__global__ void __launch_bounds__(256) k_ctc_collapse(const int *__restrict__ lab, const float *__restrict__ conf, const int *__restrict__ lens,
                                int N, int T, int max_out, int *__restrict__ o_lab, int *__restrict__ o_start,
                                int *__restrict__ o_end, float *__restrict__ o_conf, int *__restrict__ o_cnt) {
-    const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (n >= N) return;
-    const int lane = threadIdx.x & 31;
+    extern __shared__ int cc_sm[];                    // [chunks]: run starts per chunk, then their exclusive prefix sums
+    const int n = blockIdx.x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
     const int L = lens ? min(max(lens[n], 0), T) : T;
+    const int nch = (L + 31) >> 5;
     const int *l = lab + (size_t)n * T; const float *cf = conf + (size_t)n * T;
-    int count = 0;
-    for (int t0 = 0; t0 < L; t0 += 32) {
-        const int t = t0 + lane;
+    for (int c = warp; c < nch; c += nw) {
+        const int t = 32 * c + lane;
+        bool emit = false;
+        if (t < L) { const int cur = l[t]; emit = cur != 0 && (t == 0 || l[t - 1] != cur); }
+        const unsigned bal = __ballot_sync(0xffffffffu, emit);
+        if (lane == 0) cc_sm[c] = __popc(bal);
+    }
+    __syncthreads();
+    if (warp == 0) {
+        int carry = 0;
+        for (int c0 = 0; c0 < nch; c0 += 32) {
+            const int c = c0 + lane;
+            const int v = c < nch ? cc_sm[c] : 0;
+            int incl = v;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += u; }
+            if (c < nch) cc_sm[c] = carry + incl - v;
+            carry += __shfl_sync(0xffffffffu, incl, 31);
+        }
+        if (lane == 0) o_cnt[n] = carry;
+    }
+    __syncthreads();
+    for (int c = warp; c < nch; c += nw) {
+        const int t = 32 * c + lane;
         int cur = -1; bool emit = false;
         if (t < L) { cur = l[t]; emit = cur != 0 && (t == 0 || l[t - 1] != cur); }
         const unsigned bal = __ballot_sync(0xffffffffu, emit);
         if (emit) {
-            const int pos = count + __popc(bal & ((1u << lane) - 1));
+            const int pos = cc_sm[c] + __popc(bal & ((1u << lane) - 1));
             int e = t; float mx = cf[t];
             while (e + 1 < L && l[e + 1] == cur) { ++e; mx = fmaxf(mx, cf[e]); }
             if (pos < max_out) {
@@ -993,9 +1018,7 @@ __global__ void k_ctc_collapse(const int *__restrict__ lab, const float *__restr
                 o_end[(size_t)n * max_out + pos] = e; o_conf[(size_t)n * max_out + pos] = mx;
             }
         }
-        count += __popc(bal);
     }
-    if (lane == 0) o_cnt[n] = count;
 }
 
 // probabilities in the reference's (N, C, T) layout (`self.outputs`, rpred.py:227) from NHWC logits rows.

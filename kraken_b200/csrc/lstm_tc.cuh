@@ -61,6 +61,7 @@ template <int GL> struct ClusterCfg {                    // GL = lines per group
 
 struct LstmTcParams {
     const float *gx; const uint16_t *wpk; float *out; const int *lens;
+    __half *out_hi, *out_lo;         // optional fp16 operand planes of the output for a tensor-core consumer (out may then be NULL)
     int nseq, T, hid, dirs, U;
     int q2; long long s_outer, s_inner, step;
     int dbg; long long *dbgbuf;      // KB_LSTM_DBG: bit 0 = clock64 stamps of steps 100..103 of cluster 0 into dbgbuf[step][group][8]
@@ -278,9 +279,13 @@ __global__ void __launch_bounds__(LTHREADS, 1) k_lstm_rec_tc(LstmTcParams p) {
 #pragma unroll
         for (int e = 0; e < CPT; ++e) {
             cst[e] = 0.f;
-            if (cv[e]) for (int tt = clen; tt < p.T; ++tt) p.out[(size_t)(cbase + (long long)tt * p.step) * OC + dir * hid + cu + e] = 0.f;
+            if (cv[e]) for (int tt = clen; tt < p.T; ++tt) {
+                const size_t o = (size_t)(cbase + (long long)tt * p.step) * OC + dir * hid + cu + e;
+                if (p.out) p.out[o] = 0.f;
+                if (p.out_hi) { p.out_hi[o] = __float2half_rn(0.f); p.out_lo[o] = __float2half_rn(0.f); }
+            }
         }
-        float *optr = p.out + (size_t)(cbase + (long long)(dir ? max(clen - 1, 0) : 0) * p.step) * OC + dir * hid + cu;
+        long long ooff = (cbase + (long long)(dir ? max(clen - 1, 0) : 0) * p.step) * OC + dir * hid + cu;
         const long long ostride = (long long)(dir ? -1 : 1) * p.step * OC;
         // gx of this thread's TMEM row (gate of unit u) for its LPW lines: running pointers, fetched one time step ahead
         int glen[LPW]; const float *gptr[LPW]; float gxn[LPW];
@@ -350,16 +355,19 @@ __global__ void __launch_bounds__(LTHREADS, 1) k_lstm_rec_tc(LstmTcParams p) {
                     if (cv[e] && live) {
                         cst[e] = gt.y * cst[e] + gt.x * gt.z;
                         h = gt.w * tanh_fast(cst[e]);
-                        optr[e] = h;
                     }
                     // both fp16 planes of h straight into the outgoing chunk: [plane][line][unit slot]
                     const __half h1 = __float2half_rn(h);
                     const __half h2 = __float2half_rn((h - __half2float(h1)) * X2_SCALE);
+                    if (cv[e] && live) {
+                        if (p.out) p.out[ooff + e] = h;
+                        if (p.out_hi) { p.out_hi[ooff + e] = h1; p.out_lo[ooff + e] = h2; }
+                    }
                     __half *cx = reinterpret_cast<__half *>(sxq + (s & 1) * CH_B);
                     cx[cl * 8 + cj + e] = h1;
                     cx[(GL + cl) * 8 + cj + e] = h2;
                 }
-                if (live) optr += ostride;
+                if (live) ooff += ostride;
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic writes -> the bulk copy engine (async proxy)
             }
             const long long e_cell = (p.dbg & 1) ? clock64() : 0;
@@ -522,8 +530,12 @@ __global__ void __launch_bounds__(SmallCfg<NLS>::THREADS, SmallCfg<NLS>::MINB) k
         if (cql < p.nseq)
             for (int tt = clen; tt < p.T; ++tt)
                 for (int e = 0; e < 4; ++e)
-                    if (cu0 + e < hid) p.out[(size_t)(cbase + (long long)tt * p.step) * OC + dir * hid + cu0 + e] = 0.f;
-        float *optr = p.out + (size_t)(cbase + (long long)(dir ? max(clen - 1, 0) : 0) * p.step) * OC + dir * hid + cu0;
+                    if (cu0 + e < hid) {
+                        const size_t o = (size_t)(cbase + (long long)tt * p.step) * OC + dir * hid + cu0 + e;
+                        if (p.out) p.out[o] = 0.f;
+                        if (p.out_hi) { p.out_hi[o] = __float2half_rn(0.f); p.out_lo[o] = __float2half_rn(0.f); }
+                    }
+        long long ooff = (cbase + (long long)(dir ? max(clen - 1, 0) : 0) * p.step) * OC + dir * hid + cu0;
         const long long ostride = (long long)(dir ? -1 : 1) * p.step * OC;
         const bool ovec = (hid & 3) == 0 && cu0 + 3 < hid;
         const float *gx0 = p.gx + (size_t)dir * 4 * hid + (size_t)(uvalid ? u : 0) * 4 + g;
@@ -578,10 +590,23 @@ __global__ void __launch_bounds__(SmallCfg<NLS>::THREADS, SmallCfg<NLS>::MINB) k
                     }
                 }
                 if (live) {
-                    if (ovec) *reinterpret_cast<float4 *>(optr) = make_float4(hv[0], hv[1], hv[2], hv[3]);
-                    else
-                        for (int e = 0; e < 4; ++e) if (cu0 + e < hid) optr[e] = hv[e];
-                    optr += ostride;
+                    if (p.out) {
+                        if (ovec) *reinterpret_cast<float4 *>(p.out + ooff) = make_float4(hv[0], hv[1], hv[2], hv[3]);
+                        else
+                            for (int e = 0; e < 4; ++e) if (cu0 + e < hid) p.out[ooff + e] = hv[e];
+                    }
+                    if (p.out_hi) {
+                        __half a[4], b[4];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) { a[e] = __float2half_rn(hv[e]); b[e] = __float2half_rn((hv[e] - __half2float(a[e])) * X2_SCALE); }
+                        if (ovec) {
+                            *reinterpret_cast<uint2 *>(p.out_hi + ooff) = make_uint2(pack_h2(a[0], a[1]), pack_h2(a[2], a[3]));
+                            *reinterpret_cast<uint2 *>(p.out_lo + ooff) = make_uint2(pack_h2(b[0], b[1]), pack_h2(b[2], b[3]));
+                        } else {
+                            for (int e = 0; e < 4; ++e) if (cu0 + e < hid) { p.out_hi[ooff + e] = a[e]; p.out_lo[ooff + e] = b[e]; }
+                        }
+                    }
+                    ooff += ostride;
                 }
                 *reinterpret_cast<float4 *>(&sh[cl * 8 + cj0]) = make_float4(hv[0], hv[1], hv[2], hv[3]);
             }
