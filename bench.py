@@ -466,7 +466,19 @@ def main():
         roof = {'bound': 'tensor', 'achieved': flops / dur / 1e12, 'peak': pk['tf_sustained'], 'unit': 'TFLOP/s'}
     else:
         roof = {'bound': 'hbm', 'achieved': byts / dur / 1e9, 'peak': pk['hbm_gbs'], 'unit': 'GB/s'}
-    roof.update({'frac': roof['achieved'] / roof['peak'], 'traffic': None, 'kernel': dom, 'kernel_ms': per_stage[dom],
+    # measured DRAM bytes per launch of that kernel from the committed `ncu --set full` capture of this same command
+    # (profiles/r01d_ncu_full_summary.csv -> r01d_ncu_dram_bytes_per_launch.json); null if the capture is missing
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, 'profiles', 'r01d_ncu_dram_bytes_per_launch.json')) as fh:
+            tj = json.load(fh)
+        kmap = {'L_5.rec': ('void ltc::k_lstm_rec_tc<8>', 0), 'L_5.xproj': ('void tc::k_gemm_tc<1>', 0), 'O_6': ('void tc::k_gemm_tc<1>', 1),
+                'C_2+Mp_3+S_4': ('ctc::k_conv_tc', 0), 'C_0+Mp_1': ('void k_conv1_pool33<8, 3>', 0)}
+        if dom in kmap and kmap[dom][0] in tj:
+            traffic = float(tj[kmap[dom][0]][kmap[dom][1]])
+    except (OSError, ValueError, IndexError, KeyError):
+        traffic = None
+    roof.update({'frac': roof['achieved'] / roof['peak'], 'traffic': traffic, 'kernel': dom, 'kernel_ms': per_stage[dom],
                  'share_of_step': per_stage[dom] / ms_step, 'peak_source': pk['src'] + (' (sustained bf16 GEMM)' if roof['bound'] == 'tensor' else ' (copy bandwidth)'),
                  'algorithmic_per_launch': {'flops': flops, 'bytes': byts},
                  'stages_ms': {k: round(v, 4) for k, v in per_stage.items()}})
