@@ -34,6 +34,10 @@ struct CudaError : std::runtime_error { using std::runtime_error::runtime_error;
 struct Tensor {
     float *p = nullptr; int64_t n = 0, h = 0, w = 0, c = 0;
     __half *hi = nullptr, *lo = nullptr;     // optional fp16 operand planes (x1, x2s) written by a fused producer (same layout as p)
+    // space-to-depth operand planes [N][ceil(H/2)][ceil(W/2)][s2d_c] (channel = (h&1, w&1, c), zero padded to s2d_c) for a stride-2
+    // convolution that runs as a stride-1 convolution on k_conv_tc
+    __half *s_hi = nullptr, *s_lo = nullptr; int s2d_c = 0;
+    const float *nchw = nullptr;             // network input still in the caller's NCHW layout (first layer consumes it directly)
     int64_t numel() const { return n * h * w * c; }
 };
 
@@ -46,6 +50,7 @@ struct LeafWeights {
     float *aux = nullptr;   // W_hh [dirs][4h][h] / GN gamma
     __half *b_hi = nullptr, *b_lo = nullptr;  // [ncols][K] fp16 operand planes for the tcgen05 GEMM (K-major)
     __half *c_hi = nullptr, *c_lo = nullptr;  // [tap][chunk][Cout][32] fp16 operand planes for the tcgen05 convolution
+    int s2d = 0, s_th = 0, s_tw = 0, s_py = 0, s_px = 0, s_cs = 0;   // stride-2 conv as space-to-depth stride-1 conv: block taps, block padding, channels
     void *wpk = nullptr;                      // W_hh as pre-swizzled bf16x3 UMMA tiles [dir][rank][split][k-atom][128][64] (tcgen05 recurrence)
     int ncp = 0, K = 0, ncols = 0;
 };
@@ -84,7 +89,7 @@ struct kb_model {
     size_t n_stages = 0;             // entries used by the most recent call
     int sm_count = 148;
     int max_clusters8 = -1;          // co-resident 8-CTA clusters of the recurrence kernel (queried once)
-    int fuse_mask = 3;               // bit 0: stencil+pool group, bit 1: tcgen05 conv group
+    int fuse_mask = 7;               // bit 0: stencil+pool group, bit 1: tcgen05 conv group, bit 2: stride-2 conv via space-to-depth
     bool keep_fp32 = false;          // KB_KEEP_FP32=1: fused producers also write the fp32 tensor their plane-only consumer ignores (taps)
     int *d_flag = nullptr;           // device: set by plane producers when an activation leaves the fp16 range
     int *h_flag = nullptr;           // pinned copy, valid after the stream is synchronised
@@ -213,6 +218,36 @@ static void finalize_weights(kb_model *m) {
                 std::vector<__half> hi, lo;
                 if (split_planes_host(taps, hi, lo)) { w.c_hi = upload_half(m, hi); w.c_lo = upload_half(m, lo); }
             }
+            w.s2d = 0;
+            if (n.sy == 2 && n.sx == 2 && n.dy == 1 && n.dx == 1 && n.cout % 32 == 0 && n.kh * n.kw > 1) {
+                // stride 2 = stride 1 over the space-to-depth input: in(2(y+by)+py, 2(x+bx)+px) with ky = 2 by + py + pad.
+                // Block taps by in [by0, by1]; weights [tap][32-channel chunk][Cout][32] over channels (py, px, c), zero where
+                // (ky, kx) falls outside the filter or the channel is padding.
+                auto range = [](int k, int pad, int *b0, int *b1) {
+                    *b0 = 99; *b1 = -99;
+                    for (int b = -8; b <= 8; ++b) for (int ph = 0; ph < 2; ++ph) { const int kk = 2 * b + ph + pad; if (kk >= 0 && kk < k) { *b0 = std::min(*b0, b); *b1 = std::max(*b1, b); } }
+                };
+                int by0, by1, bx0, bx1;
+                range(n.kh, n.py, &by0, &by1); range(n.kw, n.px, &bx0, &bx1);
+                const int th = by1 - by0 + 1, tw = bx1 - bx0 + 1, cs = (4 * n.cin + 31) / 32 * 32, nc = cs / 32;
+                if (th + 1 <= ctc::MAX_ROWS && by0 <= 0 && bx0 <= 0 && ctc::conv_tc_plan(th, tw, n.cout, nullptr, nullptr, nullptr) <= 227 * 1024) {
+                    std::vector<float> taps((size_t)th * tw * nc * n.cout * 32, 0.f);
+                    for (int tby = 0; tby < th; ++tby)
+                        for (int tbx = 0; tbx < tw; ++tbx)
+                            for (int sc = 0; sc < 4 * n.cin; ++sc) {
+                                const int ph = sc / n.cin, ci = sc % n.cin, ky = 2 * (tby + by0) + (ph >> 1) + n.py, kx = 2 * (tbx + bx0) + (ph & 1) + n.px;
+                                if (ky < 0 || ky >= n.kh || kx < 0 || kx >= n.kw) continue;
+                                for (int co = 0; co < n.cout; ++co)
+                                    taps[((((size_t)(tby * tw + tbx) * nc + sc / 32) * n.cout) + co) * 32 + (sc % 32)] =
+                                        src[(((size_t)co * n.cin + ci) * n.kh + ky) * n.kw + kx];
+                            }
+                    std::vector<__half> hi, lo;
+                    if (split_planes_host(taps, hi, lo)) {
+                        w.c_hi = upload_half(m, hi); w.c_lo = upload_half(m, lo);
+                        w.s2d = 1; w.s_th = th; w.s_tw = tw; w.s_py = -by0; w.s_px = -bx0; w.s_cs = cs;
+                    }
+                }
+            }
         } else if (n.kind == K_LINEAR) {
             need(2);
             const int K = n.cin, ncp = (n.cout + 63) / 64 * 64, ld = n.cin + (n.aug ? 1 : 0);
@@ -316,7 +351,8 @@ static void finalize_weights(kb_model *m) {
 struct Exec {
     kb_model *m; cudaStream_t st; bool dry;
     int leaf_counter = 0;
-    bool planes_hint = false;        // set by run() for a GroupNorm whose consumer reads TF32 planes
+    bool planes_hint = false;        // set by run() for a GroupNorm / LSTM whose consumer reads fp16 operand planes
+    bool s2d_hint = false;           // ... for a GroupNorm whose consumer is a stride-2 convolution on the tensor cores
 
     int *dev_lens(const Lens &l) {
         if (!l.has) return nullptr;
@@ -459,9 +495,14 @@ struct Exec {
             int *dl = ragged ? dev_lens(lens) : nullptr;
             const bool vec4 = (C % 4) == 0 && C <= 1024 && !(getenv("KB_GN") && strcmp(getenv("KB_GN"), "scalar") == 0);
             float2 *ab = vec4 ? (float2 *)m->arena.alloc((size_t)N * C * sizeof(float2)) : nullptr;
-            const bool planes = vec4 && planes_hint;
-            planes_hint = false;
+            const bool s2d = vec4 && s2d_hint && (C % 8) == 0;
+            const bool planes = vec4 && planes_hint && !s2d;
+            planes_hint = false; s2d_hint = false;
             if (planes) { y.hi = (__half *)m->arena.alloc((size_t)y.numel() * 2); y.lo = (__half *)m->arena.alloc((size_t)y.numel() * 2); }
+            if (s2d) {
+                const size_t se = (size_t)N * ((H + 1) / 2) * ((W + 1) / 2) * 4 * C;
+                y.s_hi = (__half *)m->arena.alloc(se * 2); y.s_lo = (__half *)m->arena.alloc(se * 2); y.s2d_c = 4 * C;
+            }
             if (!dry && y.numel()) {
                 if (vec4) {
                     // float4 streaming passes (kernels.cuh k_gn_stats4 / k_gn_apply4); the apply pass also emits the TF32 planes a
@@ -471,7 +512,8 @@ struct Exec {
                     LAUNCH(m, k_gn_finalize, (unsigned)((N * G + 127) / 128), 128, 0, st, partial, stats, N, G, chunks, H, W, C, dl, 1e-5f);
                     LAUNCH(m, k_gn_coeffs, (unsigned)((N * C + 255) / 256), 256, 0, st, stats, w.aux, w.bias, ab, N, C, G);
                     const long long nb = std::min<long long>((npix + rows4 - 1) / rows4, std::max(1, 16 * sm / std::max(N, 1)));
-                    LAUNCH(m, k_gn_apply4, dim3((unsigned)nb, N), 256, 0, st, x.p, (planes && !m->keep_fp32) ? nullptr : y.p, y.hi, y.lo, ab, H, W, C, dl, m->d_flag);
+                    LAUNCH(m, k_gn_apply4, dim3((unsigned)nb, N), 256, 0, st, x.p, ((planes || s2d) && !m->keep_fp32) ? nullptr : y.p,
+                           s2d ? y.s_hi : y.hi, s2d ? y.s_lo : y.lo, ab, H, W, C, dl, m->d_flag, s2d ? 1 : 0);
                 } else {
                     const int bt = rows * cthreads;
                     LAUNCH(m, k_gn_partial, dim3(chunks, N), bt, (size_t)bt * cpt * 2 * sizeof(double), st, x.p, partial, H, W, C, G, dl, chunks, rows, cthreads, cpt);
@@ -711,6 +753,7 @@ struct Exec {
             if (!dry) m->taps[pl->name] = y;
             return j + 1 - i;
         }
+        if ((m->fuse_mask & 4) && c0.kind == K_CONV && m->lw[c0.leaf_index].s2d) { const size_t u = fuse_conv_s2d(series, i, cur, lens); if (u) return u; }
         if ((m->fuse_mask & 2) && c0.kind == K_CONV) return fuse_conv_tc(series, i, cur, lens);
         return 0;
     }
@@ -718,12 +761,78 @@ struct Exec {
     bool tc_conv_eligible(const Node &c, const Dims &in) const {
         if (!m->use_tc || c.kind != K_CONV || in.c != c.cin || (in.c % 32) != 0) return false;
         const LeafWeights &w = m->lw[c.leaf_index];
-        if (!w.c_hi) return false;
+        if (!w.c_hi || w.s2d || c.sy != 1 || c.sx != 1) return false;
         if (!(c.act == ACT_RELU || c.act == ACT_LINEAR || c.act == ACT_SIGMOID_LOGITS || c.act == ACT_TANH || c.act == ACT_LEAKY)) return false;
         if (in.h < 1 || in.w < 1) return false;
         return ctc::conv_tc_plan(c.kh, c.kw, c.cout, nullptr, nullptr, nullptr) <= 227 * 1024;
     }
+    // stride-2 convolution as a stride-1 convolution over the space-to-depth planes (weights repacked at finalize)
+    bool s2d_conv_eligible(const Node &c, const Dims &in) const {
+        if (!m->use_tc || !m->fuse || !(m->fuse_mask & 4) || c.kind != K_CONV || in.c != c.cin) return false;
+        const LeafWeights &w = m->lw[c.leaf_index];
+        if (!w.c_hi || !w.s2d) return false;
+        if (!(c.act == ACT_RELU || c.act == ACT_LINEAR || c.act == ACT_SIGMOID_LOGITS || c.act == ACT_TANH || c.act == ACT_LEAKY)) return false;
+        return in.h >= 1 && in.w >= 1;
+    }
+    bool first_is_s2d(const Node &root, const Dims &in) const {
+        return root.kind == K_SERIES && !root.children.empty() && s2d_conv_eligible(*root.children[0], in);
+    }
     static bool fold_h(const Node &c) { return c.kind == K_RESHAPE && c.rs_src == 2 && c.rs_a == 1 && c.rs_b == -1 && c.rs_high == 2 && c.rs_low == 1; }
+
+    // ---- P3: conv(stride 2) on tcgen05 via space-to-depth: the planes come from the GroupNorm in front (k_gn_apply4), from the
+    // NCHW network input, or from k_s2d_planes over an NHWC activation
+    size_t fuse_conv_s2d(const Node &series, size_t i, Tensor &cur, Lens &lens) {
+        const Node &c0 = *series.children[i];
+        const Dims din = dims_of(cur);
+        if (!s2d_conv_eligible(c0, din)) return 0;
+        const LeafWeights &w = m->lw[c0.leaf_index];
+        const Dims dconv = leaf_dims(c0, din);
+        const int64_t Hb = (din.h + 1) / 2, Wb = (din.w + 1) / 2;
+        const int cs = w.s_cs;
+        Tensor y = mk(dconv);
+        const bool planes = wants_planes(series, i + 1, dconv);
+        if (planes) { y.hi = (__half *)m->arena.alloc((size_t)y.numel() * 2); y.lo = (__half *)m->arena.alloc((size_t)y.numel() * 2); }
+        __half *x_hi = cur.s_hi, *x_lo = cur.s_lo;
+        const bool have = x_hi && cur.s2d_c == cs;
+        if (!have) {
+            const size_t se = (size_t)din.n * Hb * Wb * cs;
+            x_hi = (__half *)m->arena.alloc(se * 2); x_lo = (__half *)m->arena.alloc(se * 2);
+        }
+        if (!dry && y.numel()) {
+            StageTimer tt(m, st, c0.name, true);
+            if (!have) {
+                const float *src = cur.nchw ? cur.nchw : cur.p;
+                LAUNCH(m, k_s2d_planes, grid1d((long long)din.n * Hb * Wb * (cs / 8), 256, m->sm_count), 256, 0, st, src, cur.nchw ? 1 : 0, x_hi, x_lo,
+                       (int)din.n, (int)din.c, (int)din.h, (int)din.w, (int)Hb, (int)Wb, cs, m->d_flag);
+            }
+            ctc::ConvTcParams cp;
+            cp.bias = w.bias; cp.y = (planes && !m->keep_fp32) ? nullptr : y.p; cp.y_hi = y.hi; cp.y_lo = y.lo; cp.flag = m->d_flag;
+            cp.N = (int)din.n; cp.Ho = (int)dconv.h; cp.Wo = (int)dconv.w; cp.Cout = c0.cout; cp.kh = w.s_th; cp.kw = w.s_tw; cp.py = w.s_py; cp.px = w.s_px;
+            cp.act = c0.act; cp.pool = 0;
+            cp.out_h = (int)dconv.h; cp.out_w = (int)dconv.w;
+            cp.items_h = (int)((dconv.h + 1) / 2);
+            cp.items_w = (int)((dconv.w + ctc::TW - 1) / ctc::TW);
+            cp.sN = dconv.h * dconv.w * dconv.c; cp.sH = dconv.w * dconv.c; cp.sW = dconv.c;
+            const size_t smem = ctc::conv_tc_plan(w.s_th, w.s_tw, c0.cout, &cp.CT, &cp.nstb, &cp.a_row_bytes);
+            cp.NC = cs / 32; cp.items_c = c0.cout / cp.CT;
+            cp.acc_sets = 8 * cp.CT <= 512 ? 2 : 1;
+            CUtensorMap tx_hi, tx_lo, tw_hi, tw_lo;
+            const uint32_t box_w = (uint32_t)(ctc::TW + w.s_tw - 1);
+            if (!ctc::make_map_nhwc(&tx_hi, x_hi, (uint64_t)din.n, (uint64_t)Hb, (uint64_t)Wb, (uint64_t)cs, box_w) ||
+                !ctc::make_map_nhwc(&tx_lo, x_lo, (uint64_t)din.n, (uint64_t)Hb, (uint64_t)Wb, (uint64_t)cs, box_w) ||
+                !tc::make_map_2d(&tw_hi, w.c_hi, (uint64_t)w.s_th * w.s_tw * cp.NC * c0.cout, 32, (uint32_t)cp.CT) ||
+                !tc::make_map_2d(&tw_lo, w.c_lo, (uint64_t)w.s_th * w.s_tw * cp.NC * c0.cout, 32, (uint32_t)cp.CT))
+                throw CudaError("cuTensorMapEncodeTiled failed (strided conv)");
+            static bool attr_set3 = false;
+            if (!attr_set3) { CK(cudaFuncSetAttribute(ctc::k_conv_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); attr_set3 = true; }
+            const int nitems = cp.N * cp.items_h * cp.items_w * cp.items_c;
+            if (nitems > 0) LAUNCH(m, ctc::k_conv_tc, (unsigned)std::min(nitems, m->sm_count), ctc::CTHREADS, smem, st, tx_hi, tx_lo, tw_hi, tw_lo, cp);
+        }
+        advance_lens(c0, lens, din, dconv);
+        cur = y;
+        if (!dry) m->taps[c0.name] = y;
+        return 1;
+    }
 
     // ---- P2: conv(Cin = 32, stride 1) -> [Do]* -> [MaxPool 2x2/2] -> [Do]* -> [S fold of H into features] on tcgen05
     size_t fuse_conv_tc(const Node &series, size_t i, Tensor &cur, Lens &lens) {
@@ -792,9 +901,10 @@ struct Exec {
                     Dims dn = dims_of(cur);
                     if (n.children[i]->kind == K_LSTM) { Lens ltmp; dn = leaf_dims(*n.children[i], dn); (void)ltmp; }
                     planes_hint = wants_planes(n, i + 1, dn);
+                    if (n.children[i]->kind == K_GN) { const Node *nx = next_real(n, i + 1); s2d_hint = nx && s2d_conv_eligible(*nx, dn) && m->lw[nx->leaf_index].s_cs == 4 * dn.c; }
                 }
                 cur = run(*n.children[i], cur, lens);
-                planes_hint = false;
+                planes_hint = false; s2d_hint = false;
                 ++i;
             }
             return cur;
@@ -852,7 +962,7 @@ static ForwardResult forward_impl(kb_model *m, const float *x, int x_on_device, 
     const int C = pl.input[1];
     { const char *e = getenv("KB_GEMM"); m->use_tc = !(e && strcmp(e, "ffma") == 0) && !m->force_ffma; }
     { const char *e = getenv("KB_KEEP_FP32"); m->keep_fp32 = e && strcmp(e, "0") != 0; }
-    { const char *e = getenv("KB_FUSE"); m->fuse_mask = e ? atoi(e) : 3; m->fuse = m->fuse_mask != 0; }
+    { const char *e = getenv("KB_FUSE"); m->fuse_mask = e ? atoi(e) : 7; m->fuse = m->fuse_mask != 0; }
     if (n <= 0 || h <= 0 || w <= 0) throw ShapeError("empty input batch");
     if (pl.input[2] > 0 && h != pl.input[2] && pl.input[2] != 1)
         ;   // the reference does not check the declared height either; convs accept any H
@@ -862,12 +972,15 @@ static ForwardResult forward_impl(kb_model *m, const float *x, int x_on_device, 
     // ---- pass 1: plan the arena
     const auto prof_t0 = std::chrono::steady_clock::now();
     size_t need;
+    bool first_s2d = false;
     {
         Arena saved = m->arena;
         m->arena.dry = true; m->arena.off = 0;
         Exec ex{m, st, true};
+        Dims d0; d0.n = n; d0.c = C; d0.h = h; d0.w = w;
+        first_s2d = C > 1 && ex.first_is_s2d(*pl.root, d0);     // the first layer reads the NCHW input itself (space-to-depth planes)
         if (!x_on_device || C > 1) m->arena.alloc(in_elems * sizeof(float));      // staging of the raw input
-        if (C > 1) m->arena.alloc(in_elems * sizeof(float));
+        if (C > 1 && !first_s2d) m->arena.alloc(in_elems * sizeof(float));
         Tensor t; t.p = nullptr; t.n = n; t.c = C; t.h = h; t.w = w;
         Lens l = lens0;
         try { ex.run(*pl.root, t, l); } catch (...) { m->arena = saved; throw; }
@@ -896,7 +1009,8 @@ static ForwardResult forward_impl(kb_model *m, const float *x, int x_on_device, 
         CK(cudaMemcpyAsync(stg, x, in_elems * sizeof(float), cudaMemcpyHostToDevice, st));
         src = stg;
     } else if (C > 1) m->arena.alloc(in_elems * sizeof(float));   // keep offsets identical to the dry pass
-    if (C > 1) {
+    if (C > 1 && first_s2d) { t.p = nullptr; t.nchw = src; }
+    else if (C > 1) {
         float *nhwc = (float *)m->arena.alloc(in_elems * sizeof(float));
         dim3 grid((unsigned)((h * (long long)w + 31) / 32), (unsigned)((C + 31) / 32), (unsigned)n);
         LAUNCH(m, k_transpose, grid, dim3(32, 8), 0, st, src, nhwc, C, h * w);

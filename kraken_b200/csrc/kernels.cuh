@@ -103,6 +103,36 @@ __global__ void k_u8_lines_to_f32(const uint8_t *__restrict__ src, float *__rest
 }
 
 // =============================================================================================
+// space-to-depth operand planes for a stride-2 convolution on the tensor cores (conv_tc.cuh): out[n][hb][wb][cs] fp16 planes with
+// channel s = (h & 1, w & 1, c) for s < 4 C and zeros above / outside the image.  src is the NCHW network input (nchw = 1) or an
+// NHWC activation.  One thread = 8 consecutive s2d channels of one block pixel (one 16-byte store per plane).
+// =============================================================================================
+__global__ void k_s2d_planes(const float *__restrict__ src, int nchw, __half *__restrict__ hi, __half *__restrict__ lo, int N, int C, int H,
+                             int W, int Hb, int Wb, int cs, int *flag) {
+    const int groups = cs >> 3;
+    const long long total = (long long)N * Hb * Wb * groups;
+    bool bad = false;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int g = (int)(i % groups); long long t = i / groups;
+        const int wb = (int)(t % Wb); t /= Wb;
+        const int hb = (int)(t % Hb); const int n = (int)(t / Hb);
+        float v[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const int sc = g * 8 + e;
+            float x = 0.f;
+            if (sc < 4 * C) {
+                const int phs = sc / C, c = sc - phs * C, h = 2 * hb + (phs >> 1), w = 2 * wb + (phs & 1);
+                if (h < H && w < W) x = nchw ? __ldg(src + (((size_t)n * C + c) * H + h) * W + w) : __ldg(src + (((size_t)n * H + h) * W + w) * C + c);
+            }
+            v[e] = x;
+        }
+        store_planes8(hi + (size_t)i * 8, lo + (size_t)i * 8, v, bad);
+    }
+    if (bad) atomicOr(flag, 1);
+}
+
+// =============================================================================================
 // batched transpose  in[B][R][C] -> out[B][C][R]   (NCHW <-> NHWC at the ABI edge)
 // =============================================================================================
 __global__ void k_transpose(const float *__restrict__ in, float *__restrict__ out, int R, int C) {
@@ -661,7 +691,9 @@ __global__ void k_gn_coeffs(const float2 *__restrict__ stats, const float *__res
 // y (optional), y_hi / y_lo (optional fp16 planes for a tensor-core consumer)
 __global__ void __launch_bounds__(256) k_gn_apply4(const float *__restrict__ x, float *__restrict__ y, __half *__restrict__ y_hi,
                                                    __half *__restrict__ y_lo, const float2 *__restrict__ ab, int H, int W, int C,
-                                                   const int *__restrict__ lens, int *flag) {
+                                                   const int *__restrict__ lens, int *flag, int s2d) {
+    // s2d != 0: the planes are written in space-to-depth order [n][h/2][w/2][(h&1, w&1, c)] for a stride-2 tensor-core convolution
+    // (odd H / W: the missing phase of the last block row / column is written as zeros here)
     const int n = blockIdx.y;
     const int C4 = C >> 2, rows = 256 / C4;
     const int r = threadIdx.x / C4, q = threadIdx.x - r * C4;
@@ -672,8 +704,9 @@ __global__ void __launch_bounds__(256) k_gn_apply4(const float *__restrict__ x, 
     const size_t base = (size_t)n * npix * C4 + q;
     const float4 *px = reinterpret_cast<const float4 *>(x) + base;
     float4 *py = y ? reinterpret_cast<float4 *>(y) + base : nullptr;
-    uint2 *ph = y_hi ? reinterpret_cast<uint2 *>(y_hi) + base : nullptr;
-    uint2 *pl = y_lo ? reinterpret_cast<uint2 *>(y_lo) + base : nullptr;
+    uint2 *ph = y_hi ? reinterpret_cast<uint2 *>(y_hi) + (s2d ? 0 : base) : nullptr;
+    uint2 *pl = y_lo ? reinterpret_cast<uint2 *>(y_lo) + (s2d ? 0 : base) : nullptr;
+    const int Hb = (H + 1) >> 1, Wb = (W + 1) >> 1;
     bool bad = false;
     const int len = lens ? min(max(lens[n], 1), W) : W;
     const long long stride = (long long)gridDim.x * rows;
@@ -690,8 +723,19 @@ __global__ void __launch_bounds__(256) k_gn_apply4(const float *__restrict__ x, 
         if (ph) {
             __half h[4], l[4];
             split_f16(o.x, h[0], l[0], bad); split_f16(o.y, h[1], l[1], bad); split_f16(o.z, h[2], l[2], bad); split_f16(o.w, h[3], l[3], bad);
-            ph[pix * C4] = make_uint2(pack_h2(h[0], h[1]), pack_h2(h[2], h[3]));
-            pl[pix * C4] = make_uint2(pack_h2(l[0], l[1]), pack_h2(l[2], l[3]));
+            const uint2 vh = make_uint2(pack_h2(h[0], h[1]), pack_h2(h[2], h[3])), vl = make_uint2(pack_h2(l[0], l[1]), pack_h2(l[2], l[3]));
+            if (!s2d) { ph[pix * C4] = vh; pl[pix * C4] = vl; }
+            else {
+                const int hh = (int)(pix / W), ww = (int)(pix - (long long)hh * W);
+                const size_t blk = (((size_t)n * Hb + (hh >> 1)) * Wb + (ww >> 1)) * 4;          // 4 phases of C channels each
+                const size_t d = (blk + (hh & 1) * 2 + (ww & 1)) * C4 + q;
+                ph[d] = vh; pl[d] = vl;
+                const uint2 z = make_uint2(0u, 0u);
+                const bool last_w = (W & 1) && ww == W - 1, last_h = (H & 1) && hh == H - 1;
+                if (last_w) { ph[d + C4] = z; pl[d + C4] = z; }
+                if (last_h) { ph[d + 2 * C4] = z; pl[d + 2 * C4] = z; }
+                if (last_w && last_h) { ph[d + 3 * C4] = z; pl[d + 3 * C4] = z; }
+            }
         }
         if (lens) { w += wstep; if (w >= W) w -= W; }
     }

@@ -286,6 +286,8 @@ FUSE_SPECS = [
     ('[1,16,0,1 Cr3,3,32 Gn8 Cr3,3,32 Gn4 Mp2,2 S1(1x0)1,3 Lbx40 O1c11]', 16, (301, 77)),            # GN -> conv_tc planes, GN ragged
     ('[1,8,0,1 Cr3,3,48 Gn3 S1(1x0)1,3 Lbx40 O1c11]', 8, (150,)),                                    # GN with 12 channel quads -> GEMM planes
     ('[1,8,0,1 Cr3,3,6 Gn2 Cr3,3,32 Gn32 Mp2,2 S1(1x0)1,3 O1c11]', 8, (90,)),                         # scalar GN fallback (C % 4 != 0), G == C
+    ('[1,16,0,1 Cr3,3,32 Gn8 Cr3,3,64,2,2 Gn8 S1(1x0)1,3 Lbx40 O1c11]', 16, (301, 78)),                # stride-2 conv on tcgen05: planes from GroupNorm (s2d store)
+    ('[1,15,0,1 Cr3,3,32 Cr5,3,64,2,2 Cr3,3,32,2,2 S1(1x0)1,3 O1c9]', 15, (131, 64)),                  # ... planes from k_s2d_planes, odd H, 5x3 filter, chained
 ]
 
 
@@ -433,3 +435,27 @@ def test_recognize_u8_matches_reference_transforms():
     d = rec.recognize_u8(raw[:2])
     e = rec._recognize_raw(raw[:2].to(torch.float32).mul_(1.0 / 255).cuda(), None, want_probs=False)
     assert np.array_equal(d['labels'], e['labels']) and np.array_equal(d['confs'], e['confs'])
+
+
+@pytest.mark.parametrize('h,w', [(37, 45), (64, 50), (33, 32)])
+def test_strided_convs_on_tensor_cores_3channel(h, w):
+    """blla-style front end (Cin = 3 7x7/2, GroupNorm, 3x3/2): both strided convolutions run as stride-1 convolutions over
+    space-to-depth operand planes (first layer straight from the NCHW input), odd and even sizes; KB_FUSE=3 keeps them on the
+    CUDA-core kernel."""
+    spec = '[1,0,0,3 Cr7,7,32,2,2 Gn8 Cr3,3,64,2,2 Gn8 Cr3,3,32 O2l4]'
+    om = vo.OracleModel(spec)
+    wts = om.init_like_reference(21)
+    m = kb.TorchVGSLModel(vgsl=spec)
+    m.load_state_dict(wts)
+    m.to('cuda:0')
+    g = torch.Generator().manual_seed(h * 100 + w)
+    x = torch.rand(2, 3, h, w, generator=g)
+    ref, _ = om.forward(x, None)
+    out, _ = m.nn(x.cuda())
+    assert tuple(out.shape) == tuple(ref.shape)
+    assert rel_err(out, ref) <= TIGHT, rel_err(out, ref)
+    out_h, _ = m.nn(x)                                      # host input takes the same first-layer path
+    assert torch.equal(out_h.cpu(), out.cpu())
+    with env(KB_FUSE=3):
+        out2, _ = m.nn(x.cuda())
+    assert rel_err(out2, ref) <= TIGHT
