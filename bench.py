@@ -56,9 +56,10 @@ def stage_work(W=WIDTH):
         'L_5.rec': (2 * T * 2 * 1024 * 256, f * (2048 * T + 512 * T)),
         'O_6': (2 * T * 512 * 200, f * (512 * T + 200 * T)),
         'decode': (0, f * (200 * T) + 16 * T),
-        # fused groups (same FLOPs, only the group's external input/output touch HBM; hi+lo TF32 planes count as output)
-        'C_0+Mp_1': (2 * 48 * W * 32 * 9, f * (48 * W + 3 * 24 * w2 * 32)),
-        'C_2+Mp_3+S_4': (2 * 24 * w2 * 64 * 288, f * (2 * 24 * w2 * 32 + 3 * 768 * T)),
+        # fused groups: same FLOPs, only the group's external input and output touch HBM (4 bytes per element: one fp32 tensor or,
+        # equivalently, the two fp16 operand planes the tensor-core consumer reads)
+        'C_0+Mp_1': (2 * 48 * W * 32 * 9, f * (48 * W + 24 * w2 * 32)),
+        'C_2+Mp_3+S_4': (2 * 24 * w2 * 64 * 288, f * (24 * w2 * 32 + 768 * T)),
     }
 
 
@@ -252,6 +253,18 @@ def run_cfg3(args):
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / args.steps
     launches = int(m.launch_count)
+    # end to end through the public call with HOST tensors (pinned pages in, heat maps out to host memory), strictly serial
+    hpages = [p_.cpu().pin_memory() for p_ in pages]
+    segmentation_heatmap(m, hpages[0], (H, W))
+    sampler = ClockSampler(0)
+    sampler.start()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        hm_host = segmentation_heatmap(m, hpages[i % 2], (H, W))
+    torch.cuda.synchronize()
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / args.steps
+    clocks = sampler.stop()
     # per-stage times from a separate pass (the stage timers put event pairs around every layer)
     stage = {}
     m.set_timing(True)
@@ -274,6 +287,9 @@ def run_cfg3(args):
     line = {'metric': 'pages/sec (blla forward, 2400x3200 pages)', 'value': N / (ms / 1e3), 'unit': 'pages/s', 'n_gpus': 1, 'steps': args.steps,
             'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
             'data': 'synthetic', 'config': {'workload': 'cfg3', 'spec': BLLA, 'batch': N, 'page': f'3x{H}x{W}', 'heatmap': f'4x{H}x{W}'},
+            'e2e': {'value': N / (e2e_ms / 1e3), 'unit': 'pages/s', 'ms_per_step': e2e_ms, 'h2d_bytes_per_step': N * 3 * H * W * 4,
+                    'd2h_bytes_per_step': int(hm_host.numel()) * 4, 'api': 'kraken_b200.blla.segmentation_heatmap -> kb_segment, host pages in, host heat maps out'},
+            'clocks': clocks,
             'gpu_launches': launches, 'stages_ms': {k: round(v / args.steps, 3) for k, v in stage.items()},
             'whole_step_tflops_fp32_equiv': flops / (ms / 1e3) / 1e12, 'cpu_baseline': cpu,
             'heatmap_range': [float(hm.min()), float(hm.max())]}

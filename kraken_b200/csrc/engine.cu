@@ -505,7 +505,7 @@ struct Exec {
             }
             if (!dry && y.numel()) {
                 if (vec4) {
-                    // float4 streaming passes (kernels.cuh k_gn_stats4 / k_gn_apply4); the apply pass also emits the TF32 planes a
+                    // float4 streaming passes (kernels.cuh k_gn_stats4 / k_gn_apply4); the apply pass also emits the fp16 operand planes a
                     // tensor-core consumer wants, which saves the separate split pass (and the fp32 copy unless KB_KEEP_FP32)
                     const int rows4 = 256 / (C / 4);
                     LAUNCH(m, k_gn_stats4, dim3(chunks, N), 256, 0, st, x.p, partial, H, W, C, G, dl, chunks);
@@ -687,7 +687,7 @@ struct Exec {
         if (lens.has) for (auto &l : lens.v) l = leaf_len(c, l, din, dout);
     }
 
-    // does the layer at/after position j of `series` read TF32 split planes of a tensor with dims d?  (tensor-core conv, or an
+    // does the layer at/after position j of `series` read fp16 operand planes of a tensor with dims d?  (tensor-core conv, or an
     // LSTM / Linear whose projection runs on k_gemm_tc)
     bool wants_planes(const Node &series, size_t j, const Dims &d) const {
         const Node *nx = next_real(series, j);
@@ -717,7 +717,7 @@ struct Exec {
             const Dims dpool = leaf_dims(*pl, dconv);
             const LeafWeights &w = m->lw[c0.leaf_index];
             Tensor y = mk(dpool);
-            // a tensor-core conv right behind wants the TF32 planes
+            // a tensor-core conv right behind wants the operand planes
             const Node *nx = next_real(series, j + 1);
             const bool planes = m->use_tc && nx && nx->kind == K_CONV && tc_conv_eligible(*nx, dpool);
             if (planes) { y.hi = (__half *)m->arena.alloc((size_t)y.numel() * 2); y.lo = (__half *)m->arena.alloc((size_t)y.numel() * 2); }
@@ -848,7 +848,7 @@ struct Exec {
         Dims dout = fd ? leaf_dims(*fd, dpost) : dpost;
         (void)jpool; (void)jfold;
         Tensor y = mk(dout);
-        // consumer wants TF32 planes?  (another tensor-core conv, or an LSTM / Linear whose projection runs on k_gemm_tc)
+        // consumer wants operand planes?  (another tensor-core conv, or an LSTM / Linear whose projection runs on k_gemm_tc)
         const bool planes = wants_planes(series, j, dout);
         if (planes) { y.hi = (__half *)m->arena.alloc((size_t)y.numel() * 2); y.lo = (__half *)m->arena.alloc((size_t)y.numel() * 2); }
         __half *x_hi = cur.hi, *x_lo = cur.lo;

@@ -278,7 +278,7 @@ __global__ void __launch_bounds__(CG_NT, 2) k_conv_gemm(ConvParams p) {
 // The first layer of every kraken recogniser reads a 1-channel line image: it is a stencil, not a GEMM, and its
 // full-resolution output (cfg2: 315 MB per batch) is only ever consumed by the pool that follows.  One block = 64 pooled
 // pixels of one pooled row x all output channels; the (kh+1) x (128+kw-1) input patch and the filter bank sit in shared
-// memory; each thread produces 8 channels of one pooled pixel (4 conv positions).  Optionally also writes the TF32 hi/lo
+// memory; each thread produces 8 channels of one pooled pixel (4 conv positions).  Optionally also writes the fp16 operand
 // planes of the result for a tensor-core consumer.  max(relu(a), relu(b)) == relu(max(a, b)): pooling first is exact.
 // =============================================================================================
 struct Conv1PoolParams {

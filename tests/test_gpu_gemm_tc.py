@@ -1,4 +1,4 @@
-"""tcgen05 3xTF32 GEMM kernel (kraken_b200/csrc/gemm_tc.cuh) against float64 numpy and against the CUDA-core kernel."""
+"""tcgen05 split-fp16 GEMM kernel (kraken_b200/csrc/gemm_tc.cuh) against float64 numpy and against the CUDA-core kernel."""
 import ctypes as C
 
 import numpy as np
@@ -31,7 +31,7 @@ def test_gemm_tc_matches_fp64(M, N, K):
     c_ff = gemm(a, b, bias, False)
     e_tc = np.abs(c_tc - ref).max() / scale
     e_ff = np.abs(c_ff - ref).max() / scale
-    print(f'M={M} N={N} K={K}: rel err tcgen05-3xTF32 {e_tc:.2e}, fp32 FFMA {e_ff:.2e}')
+    print(f'M={M} N={N} K={K}: rel err tcgen05 split-fp16 {e_tc:.2e}, fp32 FFMA {e_ff:.2e}')
     assert e_ff < 2e-6
     assert e_tc < 3e-6, 'the split-precision tensor-core GEMM must stay fp32-grade'
 
@@ -42,7 +42,7 @@ def test_gemm_tc_special_values_and_no_bias():
     a[5, :] = np.linspace(-3, 3, 64, dtype=np.float32)
     b = np.eye(64, dtype=np.float32)[np.arange(128) % 64]
     c = gemm(a, b, None, True)
-    ref = a @ b.T                                  # single-term sums: only the TF32 truncation of the `lo` plane (2^-22) remains
+    ref = a @ b.T                                  # single-term sums: only the rounding of the second fp16 plane (2^-22) remains
     assert np.abs(c - ref).max() <= 1e-6 * np.abs(ref).max()
     assert np.array_equal(c[:5], ref[:5])          # 0/1 data is exact
 
