@@ -180,6 +180,19 @@ static void upload_split(kb_model *m, const std::vector<float> &rows, LeafWeight
     w.b_hi = upload_half(m, hi); w.b_lo = upload_half(m, lo);
 }
 
+// opt-in dynamic shared memory sizes of the tensor-core kernels; function attributes are per device, so this runs at every
+// kb_model_finalize (after cudaSetDevice) instead of behind process-wide "already done" flags
+static void set_kernel_attributes() {
+    CK(cudaFuncSetAttribute(tc::k_gemm_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
+    CK(cudaFuncSetAttribute(tc::k_gemm_tc<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
+    CK(cudaFuncSetAttribute(ctc::k_conv_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CK(cudaFuncSetAttribute(ltc::k_lstm_rec_tc<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, ltc::ClusterCfg<8>::SMEM_BYTES));
+    CK(cudaFuncSetAttribute(ltc::k_lstm_rec_tc<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, ltc::ClusterCfg<16>::SMEM_BYTES));
+    CK(cudaFuncSetAttribute(ltc::k_lstm_rec_tc_small<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, ltc::SmallCfg<64>::SMEM_BYTES));
+    CK(cudaFuncSetAttribute(ltc::k_lstm_rec_tc_small<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, ltc::SmallCfg<32>::SMEM_BYTES));
+    CK(cudaFuncSetAttribute(ltc::k_lstm_rec_tc_small<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, ltc::SmallCfg<16>::SMEM_BYTES));
+}
+
 static void finalize_weights(kb_model *m) {
     for (void *p : m->dev_allocs) cudaFree(p);
     m->dev_allocs.clear();
@@ -388,12 +401,6 @@ struct Exec {
         if (!tc::make_map_2d(&ta_hi, a_hi, (uint64_t)M, (uint64_t)K, tc::BM, tc::BK) || !tc::make_map_2d(&ta_lo, a_lo, (uint64_t)M, (uint64_t)K, tc::BM, tc::BK) ||
             !tc::make_map_2d(&tb_hi, w.b_hi, (uint64_t)N, (uint64_t)K, tc::BN / 2, tc::BK) || !tc::make_map_2d(&tb_lo, w.b_lo, (uint64_t)N, (uint64_t)K, tc::BN / 2, tc::BK))
             throw CudaError("cuTensorMapEncodeTiled failed");
-        static bool attr_set = false;
-        if (!attr_set) {
-            CK(cudaFuncSetAttribute(tc::k_gemm_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
-            CK(cudaFuncSetAttribute(tc::k_gemm_tc<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
-            attr_set = true;
-        }
         tc::GemmTcParams gp; gp.c = y; gp.bias = w.bias; gp.M = (int)M; gp.N = N; gp.K = K; gp.ldc = N; gp.act = act;
         const int tiles_m = (int)((M + tc::BM - 1) / tc::BM), tiles_n = (N + tc::BN - 1) / tc::BN;
         // KB_GEMM_MC=1: pairs of vertically adjacent tiles on 2-CTA clusters with the weight tile multicast (no gain measured)
@@ -567,13 +574,6 @@ struct Exec {
                     if (snl != 64 && snl != 32) snl = 16;
                     const dim3 grid((unsigned)((lp.nseq + snl - 1) / snl), (unsigned)dirs, 1);
                     if (getenv("KB_DEBUG")) fprintf(stderr, "[kb] %s: tcgen05 recurrence (single CTA, %d lines), %u CTAs, T=%d\n", n.name.c_str(), snl, grid.x * grid.y, lp.T);
-                    static bool attr_set_s = false;
-                    if (!attr_set_s) {
-                        CK(cudaFuncSetAttribute(ltc::k_lstm_rec_tc_small<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, ltc::SmallCfg<64>::SMEM_BYTES));
-                        CK(cudaFuncSetAttribute(ltc::k_lstm_rec_tc_small<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, ltc::SmallCfg<32>::SMEM_BYTES));
-                        CK(cudaFuncSetAttribute(ltc::k_lstm_rec_tc_small<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, ltc::SmallCfg<16>::SMEM_BYTES));
-                        attr_set_s = true;
-                    }
                     if (snl == 64) ltc::k_lstm_rec_tc_small<64><<<grid, ltc::SmallCfg<64>::THREADS, ltc::SmallCfg<64>::SMEM_BYTES, st>>>(tp);
                     else if (snl == 32) ltc::k_lstm_rec_tc_small<32><<<grid, ltc::SmallCfg<32>::THREADS, ltc::SmallCfg<32>::SMEM_BYTES, st>>>(tp);
                     else ltc::k_lstm_rec_tc_small<16><<<grid, ltc::SmallCfg<16>::THREADS, ltc::SmallCfg<16>::SMEM_BYTES, st>>>(tp);
@@ -584,12 +584,6 @@ struct Exec {
                     tp.gx = lp.gx; tp.wpk = (const uint16_t *)w.wpk; tp.out = (lplanes && !m->keep_fp32) ? nullptr : lp.out; tp.lens = lp.lens; tp.nseq = lp.nseq; tp.T = lp.T;
                     tp.out_hi = full.hi; tp.out_lo = full.lo;
                     tp.dbg = getenv("KB_LSTM_DBG") ? atoi(getenv("KB_LSTM_DBG")) : 0; tp.hid = hid; tp.dirs = dirs; tp.U = lp.U; tp.q2 = lp.q2; tp.s_outer = lp.s_outer; tp.s_inner = lp.s_inner; tp.step = lp.step;
-                    static bool attr_set = false;
-                    if (!attr_set) {
-                        CK(cudaFuncSetAttribute(ltc::k_lstm_rec_tc<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, ltc::ClusterCfg<8>::SMEM_BYTES));
-                        CK(cudaFuncSetAttribute(ltc::k_lstm_rec_tc<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, ltc::ClusterCfg<16>::SMEM_BYTES));
-                        attr_set = true;
-                    }
                     // lines per cluster: 16 (two groups of 8); KB_LSTM_GL=16 selects 32 (two groups of 16: half the SMs per batch, but
                     // the longer epilogue stretches the per-step latency chain by 1.7x)
                     int gl = 8;                                  // measured on cfg2: 32 lines per cluster = 0.54 ms vs 0.31 ms, and no e2e gain
@@ -823,8 +817,6 @@ struct Exec {
                 !tc::make_map_2d(&tw_hi, w.c_hi, (uint64_t)w.s_th * w.s_tw * cp.NC * c0.cout, 32, (uint32_t)cp.CT) ||
                 !tc::make_map_2d(&tw_lo, w.c_lo, (uint64_t)w.s_th * w.s_tw * cp.NC * c0.cout, 32, (uint32_t)cp.CT))
                 throw CudaError("cuTensorMapEncodeTiled failed (strided conv)");
-            static bool attr_set3 = false;
-            if (!attr_set3) { CK(cudaFuncSetAttribute(ctc::k_conv_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); attr_set3 = true; }
             const int nitems = cp.N * cp.items_h * cp.items_w * cp.items_c;
             if (nitems > 0) LAUNCH(m, ctc::k_conv_tc, (unsigned)std::min(nitems, m->sm_count), ctc::CTHREADS, smem, st, tx_hi, tx_lo, tw_hi, tw_lo, cp);
         }
@@ -877,8 +869,6 @@ struct Exec {
                 !tc::make_map_2d(&tw_hi, w.c_hi, (uint64_t)c0.kh * c0.kw * cp.NC * c0.cout, 32, (uint32_t)cp.CT) ||
                 !tc::make_map_2d(&tw_lo, w.c_lo, (uint64_t)c0.kh * c0.kw * cp.NC * c0.cout, 32, (uint32_t)cp.CT))
                 throw CudaError("cuTensorMapEncodeTiled failed (conv)");
-            static bool attr_set = false;
-            if (!attr_set) { CK(cudaFuncSetAttribute(ctc::k_conv_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); attr_set = true; }
             const int nitems = cp.N * cp.items_h * cp.items_w * cp.items_c;
             if (nitems > 0) LAUNCH(m, ctc::k_conv_tc, (unsigned)std::min(nitems, m->sm_count), ctc::CTHREADS, smem, st, tx_hi, tx_lo, tw_hi, tw_lo, cp);
         }
@@ -1292,6 +1282,7 @@ int kb_model_finalize(kb_model *m, int device) {
         if (prop.major < 10) throw CudaError(std::string("device ") + prop.name + " is not a Blackwell (sm_100) GPU; this library only carries sm_100a code");
         m->sm_count = prop.multiProcessorCount;
         m->device = device;
+        set_kernel_attributes();
         finalize_weights(m);
         CK(cudaMalloc((void **)&m->d_flag, sizeof(int)));
         m->dev_allocs.push_back(m->d_flag);
@@ -1523,6 +1514,7 @@ int kb_debug_gemm(const float *a, const float *b, const float *bias, float *c, i
         w.wt = upload(&tmp, wt);
         if (bias) w.bias = upload(&tmp, std::vector<float>(bias, bias + N));
         upload_split(&tmp, rows, w);
+        set_kernel_attributes();
         CK(cudaMalloc((void **)&tmp.d_flag, sizeof(int)));
         tmp.dev_allocs.push_back(tmp.d_flag);
         CK(cudaMemset(tmp.d_flag, 0, sizeof(int)));
