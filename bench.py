@@ -369,11 +369,28 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    # fixed-stride int32 result blocks [step][line][count | labels | starts | ends | confs], filled step by step into pinned memory
+    # so that the run's single gather to rank 0 needs no host-side repacking
+    pack_buf = {}
+
+    def pack_into(buf, i, r):
+        b = buf[i]
+        b[:, 0] = r['counts']; b[:, 1:1 + T] = r['labels']; b[:, 1 + T:1 + 2 * T] = r['starts']; b[:, 1 + 2 * T:1 + 3 * T] = r['ends']
+        b[:, 1 + 3 * T:] = r['confs'].view(np.int32)
+
+    def packed(steps):
+        if steps not in pack_buf:
+            pack_buf[steps] = torch.empty((steps, BATCH, 1 + 4 * T), dtype=torch.int32).pin_memory()
+        return pack_buf[steps]
+
     def gather_all(sink):
-        # the single gather of the run's decoded label sequences to rank 0: fixed-stride int32 blocks over NCCL
-        blk = np.stack([np.concatenate([r['counts'][:, None], r['labels'], r['starts'], r['ends'], r['confs'].view(np.int32)], axis=1)
-                        for r in sink]) if sink else np.zeros((0, BATCH, 1 + 4 * T), np.int32)
-        tdev = torch.from_numpy(blk).to(dev)
+        # the single gather of the run's decoded label sequences to rank 0 over NCCL
+        t = packed(len(sink))
+        buf = t.numpy()
+        for i, r in enumerate(sink):
+            if r is not None and not r.get('_packed'):
+                pack_into(buf, i, r)
+        tdev = t.to(dev, non_blocking=True)
         out = [torch.empty_like(tdev) for _ in range(world)] if rank == 0 else None
         dist.gather(tdev, out, dst=0)
         return out
@@ -382,6 +399,7 @@ def main():
         import threading
         res = [None] * steps
         errs = []
+        pbuf = packed(steps).numpy() if world > 1 else None
 
         def worker(k):
             try:
@@ -392,6 +410,8 @@ def main():
                             res[i] = recs[k].recognize_u8(batches[i % NB], lens, inv255)
                         else:
                             res[i] = recs[k]._recognize_raw(batches[i % NB], lens, want_probs=False)
+                        if pbuf is not None:
+                            pack_into(pbuf, i, res[i]); res[i]['_packed'] = True
             except Exception as e:       # surface worker failures in the main thread
                 errs.append(e)
         cur = torch.cuda.current_stream()
@@ -415,8 +435,12 @@ def main():
         if pipelined and len(recs) > 1:
             run_pipelined(batches, steps, sink, u8)
         else:
+            buf = packed(steps).numpy() if world > 1 else None
             for i in range(steps):
-                sink.append(step(batches[i % NB]))
+                r = step(batches[i % NB])
+                if buf is not None:
+                    pack_into(buf, i, r); r['_packed'] = True
+                sink.append(r)
                 if on_step is not None:
                     on_step()
         if world > 1:
