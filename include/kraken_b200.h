@@ -17,7 +17,11 @@
  * ctypes stub a kraken maintainer would add.
  *
  * Conventions
- *   - plain pointers and sizes only; no torch types.  All tensors are fp32, NCHW, dense, as in the reference.
+ *   - plain pointers and sizes only; no torch types.  All tensors are fp32, NCHW, dense, as in the reference
+ *     (kb_recognize_u8 additionally takes the uint8 images the reference's transforms start from).
+ *   - arithmetic: fp32 on CUDA cores for stencil / scan / gate math; the tensor-core layers (convolutions, LSTM
+ *     projections and recurrences, linear) read every fp32 operand as two fp16 planes (22 significand bits) and
+ *     accumulate in fp32: logits agree with the fp32 reference to ~2e-6 relative, CTC label sequences bit for bit.
  *   - `*_on_device` flags say whether a data pointer is a CUDA device pointer (of the model's device) or
  *     a host pointer (pinned or pageable).  Host pointers are copied inside the call.
  *   - every function returns KB_OK or an error code; kb_last_error() returns a thread-local message.
@@ -30,8 +34,9 @@
  *   - a model handle is internally serialised (one call at a time per handle); different handles are
  *     independent and may be driven from different threads/streams.  The engine owns weights and
  *     workspaces; the caller owns every buffer it passes in.
- *   - `stream` is a cudaStream_t passed as void* (NULL = the legacy default stream).  Calls that return
- *     host results synchronise that stream before returning; device-output calls do not.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = the legacy default stream).  Every compute call
+ *     synchronises that stream before returning (results are complete; the operand-range check of the
+ *     tensor-core layers, see kb_range_fallback_count, needs the stream idle).
  */
 #ifndef KRAKEN_B200_H
 #define KRAKEN_B200_H

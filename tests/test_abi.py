@@ -59,3 +59,4 @@ def test_product_never_imports_oracle():
             if f.endswith(('.py', '.cu', '.cuh', '.hpp', '.h')):
                 txt = open(os.path.join(dirpath, f), errors='ignore').read()
                 assert 'vgsl_oracle' not in txt and 'refshim' not in txt and 'np_kernels' not in txt, f
+

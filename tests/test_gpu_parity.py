@@ -431,6 +431,10 @@ def test_recognize_u8_matches_reference_transforms():
     for i in range(n):
         got = [(int(a['labels'][i, j]), int(a['starts'][i, j]), int(a['ends'][i, j])) for j in range(int(a['counts'][i]))]
         assert got == [(l, s, e) for l, s, e, _ in ref_dec[i]]
+    with pytest.raises(ValueError):
+        rec.recognize_u8(torch.zeros(2, 1, 16, 40))                     # float input
+    with pytest.raises(ValueError):
+        rec.recognize_u8(np.zeros((16, 40), np.uint8))                  # not NCHW
     # no inversion, no widths
     d = rec.recognize_u8(raw[:2])
     e = rec._recognize_raw(raw[:2].to(torch.float32).mul_(1.0 / 255).cuda(), None, want_probs=False)
