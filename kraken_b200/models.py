@@ -44,6 +44,7 @@ class TorchSeqRecognizer:
         self.one_channel_mode = nn.one_channel_mode
         self.seg_type = nn.seg_type
         self.outputs = None
+        self._dims_cache = {}          # (engine handle, n, h, w) -> output dims of nn
         if self.device:
             self.nn.to(device)
 
@@ -68,16 +69,20 @@ class TorchSeqRecognizer:
         widths = None
         if lens is not None:
             widths = np.ascontiguousarray(torch.as_tensor(lens).cpu().numpy(), dtype=np.int32)
-        dims = net.infer_dims(n, h, w)
+        key = (getattr(net._h, 'value', None), getattr(net, 'spec', None), n, h, w)
+        dims = self._dims_cache.get(key)
+        if dims is None:
+            dims = self._dims_cache[key] = net.infer_dims(n, h, w)
         if dims[2] != 1:
             raise KrakenInputException('Expected dimension 3 to be 1, actual {}'.format(tuple(dims)))
         T, ncls = dims[3], dims[1]
         stride = max(T, 1)
-        labels = np.zeros((n, stride), np.int32)
-        starts = np.zeros((n, stride), np.int32)
-        ends = np.zeros((n, stride), np.int32)
-        confs = np.zeros((n, stride), np.float32)
-        counts = np.zeros(n, np.int32)
+        # the engine writes every element of these blocks (valid prefix + zero fill), so they need no initialisation
+        labels = np.empty((n, stride), np.int32)
+        starts = np.empty((n, stride), np.int32)
+        ends = np.empty((n, stride), np.int32)
+        confs = np.empty((n, stride), np.float32)
+        counts = np.empty(n, np.int32)
         olens = np.zeros(n, np.int32)
         probs = np.empty((n, ncls, T), np.float32) if want_probs else None
         on_dev = _on_device(x)
