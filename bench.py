@@ -72,14 +72,36 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    """SM clock / throttle reasons DURING the timed region (B200_PROFILING.md).  In-process NVML polling every 10 ms (nvidia_ml_py):
+    an `nvidia-smi -lms` child, as used first, kept the driver busy enough to stretch the serial multi-GPU steps by ~0.15 ms;
+    nvidia-smi stays as the fallback when NVML cannot be loaded."""
     Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
          'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+    BITS = {'sw_power_cap': 0x4, 'hw_slowdown': 0x8, 'sw_thermal_slowdown': 0x20, 'hw_thermal_slowdown': 0x40}
 
     def __init__(self, index):
         self.index, self.proc, self.lines = index, None, []
+        self.nvml, self.h, self.samples, self.stop_flag = None, None, [], False
+
+    def _nvml_index(self):
+        cvd = os.environ.get('CUDA_VISIBLE_DEVICES', '')
+        try:
+            ids = [int(x) for x in cvd.split(',') if x.strip() != '']
+            return ids[self.index] if ids else self.index
+        except (ValueError, IndexError):
+            return self.index
 
     def start(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(self._nvml_index())
+            self.nvml = pynvml
+            self.th = threading.Thread(target=self._poll, daemon=True)
+            self.th.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits', '-lms', '100',
                                           '-i', str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
@@ -88,11 +110,30 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
+    def _poll(self):
+        n = self.nvml
+        while not self.stop_flag:
+            try:
+                sm = n.nvmlDeviceGetClockInfo(self.h, n.NVML_CLOCK_SM)
+                mx = n.nvmlDeviceGetMaxClockInfo(self.h, n.NVML_CLOCK_SM)
+                rs = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                self.samples.append((float(sm), float(mx), int(rs)))
+            except Exception:
+                pass
+            time.sleep(0.01)
+
     def _read(self):
         for ln in self.proc.stdout:
             self.lines.append(ln.strip())
 
     def stop(self):
+        if self.nvml is not None:
+            self.stop_flag = True
+            self.th.join(timeout=1)
+            sm = [s_[0] for s_ in self.samples]; mx = [s_[1] for s_ in self.samples]
+            reasons = sorted(k for k, bit in self.BITS.items() if any(s_[2] & bit for s_ in self.samples))
+            return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(mx) if mx else None, 'reasons': reasons,
+                    'samples': len(sm), 'source': 'nvml'}
         if not self.proc:
             return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
         self.proc.terminate()
@@ -113,7 +154,7 @@ class ClockSampler:
                 if v.lower().startswith('active'):
                     reasons.add(name)
         return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
-                'reasons': sorted(reasons), 'samples': len(sm)}
+                'reasons': sorted(reasons), 'samples': len(sm), 'source': 'nvidia-smi'}
 
 
 def make_batches(count, seed):
@@ -361,27 +402,35 @@ def main():
     inv255 = np.full(BATCH, 255, np.int16)
     T = WIDTH // 4
 
-    def step(x):
-        return rec._recognize_raw(x, lens, want_probs=False)     # the ABI's own output blocks (labels, starts, ends, confs, counts)
+    def step(x, out=None):
+        return rec._recognize_raw(x, lens, want_probs=False, out=out)     # the ABI's own output blocks (labels, starts, ends, confs, counts)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # fixed-stride int32 result blocks [step][line][count | labels | starts | ends | confs], filled step by step into pinned memory
-    # so that the run's single gather to rank 0 needs no host-side repacking
+    # result blocks of a run in ONE pinned int32 buffer [step][counts (B) | labels (B x T) | starts | ends | confs]: every
+    # kb_recognize call writes its output blocks straight into its slice, so the run's single gather to rank 0 ships the buffer
+    # as it is (no host-side repacking)
     pack_buf = {}
-
-    def pack_into(buf, i, r):
-        b = buf[i]
-        b[:, 0] = r['counts']; b[:, 1:1 + T] = r['labels']; b[:, 1 + T:1 + 2 * T] = r['starts']; b[:, 1 + 2 * T:1 + 3 * T] = r['ends']
-        b[:, 1 + 3 * T:] = r['confs'].view(np.int32)
+    STEP_WORDS = BATCH * (1 + 4 * T)
 
     def packed(steps):
         if steps not in pack_buf:
-            pack_buf[steps] = torch.empty((steps, BATCH, 1 + 4 * T), dtype=torch.int32).pin_memory()
+            pack_buf[steps] = torch.empty((steps, STEP_WORDS), dtype=torch.int32).pin_memory()
         return pack_buf[steps]
+
+    def out_views(buf, i):
+        b = buf[i]
+        o, bt = BATCH, BATCH * T
+        return {'counts': b[:o], 'labels': b[o:o + bt].reshape(BATCH, T), 'starts': b[o + bt:o + 2 * bt].reshape(BATCH, T),
+                'ends': b[o + 2 * bt:o + 3 * bt].reshape(BATCH, T), 'confs': b[o + 3 * bt:o + 4 * bt].view(np.float32).reshape(BATCH, T)}
+
+    def pack_into(buf, i, r):                # for calls that could not write in place (uint8 arm)
+        v = out_views(buf, i)
+        for k in ('counts', 'labels', 'starts', 'ends', 'confs'):
+            v[k][...] = r[k]
 
     def gather_all(sink):
         # the single gather of the run's decoded label sequences to rank 0 over NCCL
@@ -408,10 +457,13 @@ def main():
                     for i in range(k, steps, len(recs)):
                         if u8:
                             res[i] = recs[k].recognize_u8(batches[i % NB], lens, inv255)
+                            if pbuf is not None:
+                                pack_into(pbuf, i, res[i]); res[i]['_packed'] = True
                         else:
-                            res[i] = recs[k]._recognize_raw(batches[i % NB], lens, want_probs=False)
-                        if pbuf is not None:
-                            pack_into(pbuf, i, res[i]); res[i]['_packed'] = True
+                            res[i] = recs[k]._recognize_raw(batches[i % NB], lens, want_probs=False,
+                                                            out=out_views(pbuf, i) if pbuf is not None else None)
+                            if pbuf is not None:
+                                res[i]['_packed'] = True
             except Exception as e:       # surface worker failures in the main thread
                 errs.append(e)
         cur = torch.cuda.current_stream()
@@ -437,9 +489,9 @@ def main():
         else:
             buf = packed(steps).numpy() if world > 1 else None
             for i in range(steps):
-                r = step(batches[i % NB])
+                r = step(batches[i % NB], out_views(buf, i) if buf is not None else None)
                 if buf is not None:
-                    pack_into(buf, i, r); r['_packed'] = True
+                    r['_packed'] = True
                 sink.append(r)
                 if on_step is not None:
                     on_step()

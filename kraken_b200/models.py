@@ -57,9 +57,10 @@ class TorchSeqRecognizer:
         r = self._recognize_raw(line, lens, want_probs)
         return ctc_decoder.unpack_decoded(r['labels'], r['starts'], r['ends'], r['confs'], r['counts']), r['olens']
 
-    def _recognize_raw(self, line, lens, want_probs: bool) -> dict:
+    def _recognize_raw(self, line, lens, want_probs: bool, out: Optional[dict] = None) -> dict:
         """One `kb_recognize` call; returns the ABI's fixed-stride output blocks as numpy arrays
-        (labels/starts/ends/confs [N, T], counts [N], olens [N] or None)."""
+        (labels/starts/ends/confs [N, T], counts [N], olens [N] or None).  `out` may supply preallocated C-contiguous
+        blocks (e.g. views into one pinned buffer that is shipped elsewhere afterwards) for labels/starts/ends/confs/counts."""
         net = self.nn
         net._ensure_finalized(line)
         x = _as_f32(line)
@@ -78,11 +79,18 @@ class TorchSeqRecognizer:
         T, ncls = dims[3], dims[1]
         stride = max(T, 1)
         # the engine writes every element of these blocks (valid prefix + zero fill), so they need no initialisation
-        labels = np.empty((n, stride), np.int32)
-        starts = np.empty((n, stride), np.int32)
-        ends = np.empty((n, stride), np.int32)
-        confs = np.empty((n, stride), np.float32)
-        counts = np.empty(n, np.int32)
+        if out is not None:
+            labels, starts, ends, confs, counts = out['labels'], out['starts'], out['ends'], out['confs'], out['counts']
+            for a, dt, shp in ((labels, np.int32, (n, stride)), (starts, np.int32, (n, stride)), (ends, np.int32, (n, stride)),
+                               (confs, np.float32, (n, stride)), (counts, np.int32, (n,))):
+                if a.dtype != dt or a.shape != shp or not a.flags['C_CONTIGUOUS']:
+                    raise ValueError('preallocated output block has the wrong dtype, shape or layout')
+        else:
+            labels = np.empty((n, stride), np.int32)
+            starts = np.empty((n, stride), np.int32)
+            ends = np.empty((n, stride), np.int32)
+            confs = np.empty((n, stride), np.float32)
+            counts = np.empty(n, np.int32)
         olens = np.zeros(n, np.int32)
         probs = np.empty((n, ncls, T), np.float32) if want_probs else None
         on_dev = _on_device(x)
