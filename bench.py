@@ -512,7 +512,8 @@ def main():
         run_pipelined(host, 2 * len(recs), [])
         run_pipelined(host_u8, 2 * len(recs), [], u8=True)
     if world > 1:
-        gather_all([step(devb[0])])          # warm the NCCL gather up (lazy communicator / channel setup) before timing
+        gather_all([step(devb[0])])          # warm the NCCL gather up (lazy communicator / channel setup) before timing ...
+        gather_all([None] * args.steps)      # ... at the payload size of the timed runs (buffers grow with the first large collective)
         ms_warm = torch.zeros(1, device=dev); dist.all_reduce(ms_warm, op=dist.ReduceOp.MAX)
 
     # ---- timed region 1: inputs resident in HBM; per-stage CUDA-event timing on the launching stream
