@@ -63,6 +63,20 @@ def stage_work(W=WIDTH):
     }
 
 
+def per_stage_roofline(per_stage_ms, work, pk, batch):
+    """stage -> achieved TFLOP/s and GB/s on the algorithmic work of `stage_work`, and both as fractions of the measured peaks
+    (report both fractions per kernel; the binding one is the larger)."""
+    out = {}
+    for k, ms in per_stage_ms.items():
+        if k not in work or ms <= 0:
+            continue
+        fl, by = work[k][0] * batch, work[k][1] * batch
+        tf, gbs = fl / (ms * 1e-3) / 1e12, by / (ms * 1e-3) / 1e9
+        out[k] = {'ms': round(ms, 4), 'tflops': round(tf, 2), 'gbs': round(gbs, 1), 'tensor_frac': round(tf / pk['tf_sustained'], 4),
+                  'hbm_frac': round(gbs / pk['hbm_gbs'], 4)}
+    return out
+
+
 def peaks():
     p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
     if os.path.exists(p):
@@ -574,7 +588,8 @@ def main():
     roof.update({'frac': roof['achieved'] / roof['peak'], 'traffic': traffic, 'kernel': dom, 'kernel_ms': per_stage[dom],
                  'share_of_step': per_stage[dom] / ms_step, 'peak_source': pk['src'] + (' (sustained bf16 GEMM)' if roof['bound'] == 'tensor' else ' (copy bandwidth)'),
                  'algorithmic_per_launch': {'flops': flops, 'bytes': byts},
-                 'stages_ms': {k: round(v, 4) for k, v in per_stage.items()}})
+                 'stages_ms': {k: round(v, 4) for k, v in per_stage.items()},
+                 'per_stage': per_stage_roofline(per_stage, work, pk, BATCH)})
     tot_f = sum(v[0] for v in work.values()) * BATCH
     tot_b = (4 * 48 * WIDTH + 2 * 4 * 768 * T + 2 * 4 * 2048 * T + 2 * 4 * 512 * T + 8 * T) * BATCH
     roof['whole_step'] = {'tensor_frac': tot_f / (ms_step / 1e3) / (pk['tf_sustained'] * 1e12),

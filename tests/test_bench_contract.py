@@ -29,3 +29,15 @@ def test_reference_arm_other_ranks_exit_quietly():
                        capture_output=True, text=True, timeout=120, cwd=ROOT, env=env)
     assert p.returncode == 0, p.stderr[-2000:]
     assert p.stdout.strip() == ''
+
+
+def test_per_stage_roofline_arithmetic():
+    sys.path.insert(0, ROOT)
+    import bench
+    work = bench.stage_work()
+    pk = {'tf_sustained': 1000.0, 'hbm_gbs': 5000.0}
+    r = bench.per_stage_roofline({'L_5.xproj': 0.1, 'decode': 0.05, 'unknown': 1.0, 'O_6': 0.0}, work, pk, 64)
+    assert set(r) == {'L_5.xproj', 'decode'}
+    fl = 2 * 200 * 768 * 2048 * 64
+    assert abs(r['L_5.xproj']['tflops'] - fl / 1e-4 / 1e12) < 0.01 and abs(r['L_5.xproj']['tensor_frac'] - r['L_5.xproj']['tflops'] / 1000.0) < 1e-3
+    assert r['decode']['tflops'] == 0 and r['decode']['gbs'] > 0
