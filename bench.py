@@ -400,7 +400,9 @@ def main():
     lens = torch.full((BATCH,), WIDTH, dtype=torch.long)
     # end-to-end arm: IN_FLIGHT engine handles (own stream + workspace each, same weights) driven by host threads, so that the
     # H2D copy / D2H read-back / host work of one batch overlap the kernels of the other - how a serving job would run it
-    IN_FLIGHT = max(1, args.inflight)
+    # every in-flight batch is a host thread that spin-waits on its stream: do not oversubscribe the cores this job may use
+    # (all ranks of a node share them), but keep at least two batches in flight
+    IN_FLIGHT = max(1, min(args.inflight, max(2, usable_cpus() // max(world, 1))))
     recs = [rec]
     for _ in range(IN_FLIGHT - 1):
         m2 = kb.TorchVGSLModel(vgsl=CFG2, model_type=['recognition'])
