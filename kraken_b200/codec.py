@@ -102,3 +102,44 @@ class PytorchCodec:
                     raise KrakenEncodeException(f'Non-decodable sequence {labs[i:i + 5]}... encountered.')
                 i += 1
         return out
+
+    # -- record assembly fast path ------------------------------------------------------------------
+    def decode_blocks(self, labels, starts, ends, confs, counts):
+        """Vectorised `decode` over the engine's fixed-stride output blocks (labels/starts/ends/confs [N, T], counts [N]) as
+        `kb_recognize` fills them: per line (text, starts, ends, confs) with numpy arrays for the positions / confidences.
+        For 1:1 codecs (every code one label, one code point - the common case, kraken/lib/codec.py:164-195 `l2c_single`)
+        this is one table lookup per line; anything else goes through `decode`.  Identical results to `decode` either way."""
+        labels = np.asarray(labels); starts = np.asarray(starts); ends = np.asarray(ends); confs = np.asarray(confs)
+        counts = np.asarray(counts)
+        lut = self._single_lut()
+        out = []
+        for i in range(labels.shape[0]):
+            c = int(min(counts[i], labels.shape[1]))
+            if lut is None:
+                dec = self.decode([(int(labels[i, j]), int(starts[i, j]), int(ends[i, j]), float(confs[i, j])) for j in range(c)])
+                out.append((''.join(d[0] for d in dec), np.array([d[1] for d in dec], np.int32), np.array([d[2] for d in dec], np.int32),
+                            np.array([d[3] for d in dec], np.float32)))
+                continue
+            lab = labels[i, :c]
+            known = (lab >= 0) & (lab < lut.shape[0])
+            chars = np.where(known, lut[np.where(known, lab, 0)], '')
+            keep = chars != ''
+            if self.strict and not keep.all():
+                bad = lab[~keep]
+                raise KrakenEncodeException(f'Non-decodable sequence {tuple(int(b) for b in bad[:5])}... encountered.')
+            out.append((''.join(chars[keep].tolist()), starts[i, :c][keep].astype(np.int32), ends[i, :c][keep].astype(np.int32),
+                        confs[i, :c][keep].astype(np.float32)))
+        return out
+
+    def _single_lut(self):
+        """label -> code point table for 1:1 codecs, else None (cached)."""
+        if not hasattr(self, '_lut'):
+            if all(len(k) == 1 and len(v) == 1 for k, v in self.l2c.items()):
+                lut = np.full(self.max_label + 1, '', dtype='<U1')
+                for (lab,), ch in self.l2c.items():
+                    lut[lab] = ch
+                self._lut = lut
+            else:
+                self._lut = None
+        return self._lut
+

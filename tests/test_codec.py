@@ -62,3 +62,35 @@ def test_identical_to_reference_codec_on_random_streams():
             a, b = ours.decode(labs), ref.decode(labs)
             assert [x[:3] for x in a] == [tuple(y[:3]) for y in b]
             assert all(abs(x[3] - float(y[3])) < 1e-9 for x, y in zip(a, b))
+
+
+@pytest.mark.parametrize('charset', [{'a': [1], 'b': [2], 'c': [4]},                      # 1:1 -> table lookup
+                                     {'a': [1], 'xy': [2, 3], 'b': [4]},                  # multi-label code -> generic path
+                                     {chr(0x710 + i): [i + 1] for i in range(15)}])
+def test_decode_blocks_equals_decode(charset):
+    import numpy as np
+    rnd = np.random.default_rng(3)
+    c = PytorchCodec(charset)
+    n, t = 9, 40
+    labels = rnd.integers(0, c.max_label + 3, (n, t)).astype(np.int32)       # includes undecodable labels
+    starts = np.cumsum(rnd.integers(1, 4, (n, t)), axis=1).astype(np.int32)
+    ends = (starts + rnd.integers(0, 3, (n, t))).astype(np.int32)
+    confs = rnd.random((n, t)).astype(np.float32)
+    counts = rnd.integers(0, t + 1, n).astype(np.int32)
+    counts[0] = 0
+    got = c.decode_blocks(labels, starts, ends, confs, counts)
+    for i in range(n):
+        ref = c.decode([(int(labels[i, j]), int(starts[i, j]), int(ends[i, j]), float(confs[i, j])) for j in range(counts[i])])
+        text, s_, e_, cf = got[i]
+        assert text == ''.join(r[0] for r in ref)
+        assert s_.tolist() == [r[1] for r in ref] and e_.tolist() == [r[2] for r in ref]
+        assert np.allclose(cf, [r[3] for r in ref], atol=1e-7)
+
+
+def test_decode_blocks_strict():
+    import numpy as np
+    c = PytorchCodec({'a': [1], 'b': [2]}, strict=True)
+    ok = c.decode_blocks(np.array([[1, 2, 1]]), np.zeros((1, 3), np.int32), np.zeros((1, 3), np.int32), np.ones((1, 3), np.float32), np.array([3]))
+    assert ok[0][0] == 'aba'
+    with pytest.raises(KrakenEncodeException):
+        c.decode_blocks(np.array([[1, 7, 1]]), np.zeros((1, 3), np.int32), np.zeros((1, 3), np.int32), np.ones((1, 3), np.float32), np.array([3]))

@@ -107,6 +107,10 @@ def test_cfg1_exact_strings():
         pred = rec.predict(x)[0]
         assert ''.join(c for c, *_ in pred) == str(g['raw_prediction'])
         assert rec.outputs.shape == g['probs'].shape
+        text, st_, en_, cf_ = rec.predict_records(x)[0]                       # vectorised record assembly
+        assert text == str(g['raw_prediction'])
+        assert st_.tolist() == [p[1] for p in pred] and en_.tolist() == [p[2] for p in pred]
+        assert np.allclose(cf_, [p[3] for p in pred], atol=1e-6)
 
 
 @pytest.mark.parametrize('seed,n,w', [(11, 8, 320), (12, 3, 97), (13, 1, 64), (14, 16, 802)])
