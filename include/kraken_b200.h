@@ -79,6 +79,9 @@ typedef struct kb_layer_info {
 /* ---- library ------------------------------------------------------------------------------------ */
 int         kb_abi_version(void);
 const char *kb_last_error(void);
+/* hash of the sources + compiler flags this library was built from (see __graft_entry__.py::source_hash); lets the tests and
+ * build() notice a stale binary next to newer sources */
+const char *kb_source_hash(void);
 /* number of visible CUDA devices (0 when there is no driver/GPU; never fails) */
 int         kb_device_count(void);
 

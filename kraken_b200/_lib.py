@@ -43,6 +43,7 @@ _pi32, _pf = C.POINTER(C.c_int32), C.POINTER(C.c_float)
 _SIGS = {
     'kb_abi_version': (C.c_int, []),
     'kb_last_error': (C.c_char_p, []),
+    'kb_source_hash': (C.c_char_p, []),
     'kb_device_count': (C.c_int, []),
     'kb_model_create': (C.c_int, [C.c_char_p, C.POINTER(_vp)]),
     'kb_model_destroy': (None, [_vp]),

@@ -25,6 +25,10 @@ def segmentation_heatmap(model: TorchVGSLModel, pages, size: Optional[Sequence[i
     if x.ndim == 3:
         x = x[None]
     n, c, h, w = (int(v) for v in x.shape)
+    if c != model.input[1]:
+        raise ValueError(f'expected {model.input[1]} input channels, got {c}')
+    if _on_device(x) and x.device.index != model._device:
+        x = x.to(f'cuda:{model._device}')
     if size is None:
         size = (h, w)
     oc = model.infer_dims(n, h, w)[1]

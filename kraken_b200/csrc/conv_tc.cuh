@@ -9,7 +9,7 @@
 //   * TMA (4-D tensor map C,W,H,N; box 32 x (128+kw-1) x 1 x 1, 64B swizzle) brings the kh+1 input rows a row pair
 //     needs into shared memory ONCE; out-of-bounds coordinates are zero-filled by the TMA unit = the conv's zero padding
 //   * the A operand of tap (ky, kx) for output row r is the row buffer (ky + r) with its UMMA descriptor start address
-//     advanced by kx pixel rows (64 B each).  Measured on B200 (with 128-byte rows in round 1a, tests/gpu_fuse_debug.py): the
+//     advanced by kx pixel rows (64 B each).  Measured on B200 (with 128-byte rows in round 1a, tools/gpu_fuse_debug.py): the
 //     swizzle XOR is taken from the ABSOLUTE shared-memory address bits, exactly as TMA wrote it, so a descriptor may start
 //     at any pixel row of an aligned buffer with base_offset = 0 (setting base_offset = kx gives garbage)
 //   * B operand = the tap's [Cout][32] weight slice, streamed through a 4-stage TMA ring

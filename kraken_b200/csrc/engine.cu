@@ -102,6 +102,8 @@ struct kb_model {
     bool use_tc = true;              // tcgen05 GEMM path (KB_GEMM=ffma forces the CUDA-core kernel)
     ~kb_model() {
         if (device >= 0) {
+            int prev = -1;
+            if (cudaGetDevice(&prev) != cudaSuccess) { cudaGetLastError(); prev = -1; }
             cudaSetDevice(device);
             for (void *p : dev_allocs) cudaFree(p);
             if (arena.base) cudaFree(arena.base);
@@ -110,6 +112,7 @@ struct kb_model {
             if (u8_raw) cudaFree(u8_raw);
             if (u8_f32) cudaFree(u8_f32);
             for (auto &e : stages) { if (e.a) cudaEventDestroy(e.a); if (e.b) cudaEventDestroy(e.b); }
+            if (prev >= 0) cudaSetDevice(prev);
         }
     }
 };
@@ -929,6 +932,14 @@ struct Exec {
     }
 };
 
+// Every ABI entry point that selects the model's device restores the caller's current device on the way out: torch (and any
+// other runtime-API user in the process) reads the current device of the calling thread.
+struct DeviceGuard {
+    int prev = -1;
+    DeviceGuard() { if (cudaGetDevice(&prev) != cudaSuccess) { cudaGetLastError(); prev = -1; } }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
 static void ensure_ready(kb_model *m) {
     if (!m->finalized) throw SpecError("model not finalized: call kb_model_finalize() after loading weights");
     CK(cudaSetDevice(m->device));
@@ -1127,8 +1138,12 @@ static void decode_and_fetch(kb_model *m, int dev_sm, int n, int T, int max_out,
 // =================================================================================================
 extern "C" {
 
+#ifndef KB_SOURCE_HASH
+#define KB_SOURCE_HASH "unknown"
+#endif
 int kb_abi_version(void) { return KB_ABI_VERSION; }
 const char *kb_last_error(void) { return g_err.c_str(); }
+const char *kb_source_hash(void) { return KB_SOURCE_HASH; }
 int kb_device_count(void) {
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
@@ -1259,6 +1274,7 @@ int kb_model_finalize(kb_model *m, int device) {
             cudaGetLastError();
             throw CudaError("no CUDA device available: kraken_b200 has no CPU fallback");
         }
+        DeviceGuard dguard0;
         if (device < 0 || device >= cnt) throw CudaError("invalid device ordinal " + std::to_string(device));
         if (m->device >= 0 && m->device != device) {
             CK(cudaSetDevice(m->device));
@@ -1300,6 +1316,7 @@ int kb_forward(kb_model *m, const float *x, int x_on_device, int32_t n, int32_t 
     if (!m || !x || !out) return fail(KB_ERR_ARG, "NULL argument");
     std::lock_guard<std::mutex> lk(m->mu);
     return guarded([&]() {
+        DeviceGuard dguard;
         ensure_ready(m);
         cudaStream_t st = (cudaStream_t)stream;
         Dims d; d.n = n; d.c = m->plan->input[1]; d.h = h; d.w = w; Lens l;
@@ -1368,6 +1385,7 @@ int kb_recognize(kb_model *m, const float *lines, int lines_on_device, int32_t n
     if (!(temperature > 0.f)) return fail(KB_ERR_ARG, "temperature must be positive");
     std::lock_guard<std::mutex> lk(m->mu);
     return guarded([&]() {
+        DeviceGuard dguard;
         ensure_ready(m);
         return recognize_locked(m, lines, lines_on_device, n, h, w, widths, temperature, labels, starts, ends, confs, counts, max_out,
                                 out_lens, probs, probs_on_device, stream);
@@ -1383,6 +1401,7 @@ int kb_recognize_u8(kb_model *m, const uint8_t *lines, int lines_on_device, int3
     if (n <= 0 || h <= 0 || w <= 0) return fail(KB_ERR_SHAPE, "empty input batch");
     std::lock_guard<std::mutex> lk(m->mu);
     return guarded([&]() {
+        DeviceGuard dguard;
         ensure_ready(m);
         cudaStream_t st = (cudaStream_t)stream;
         const int C = m->plan->input[1];
@@ -1423,6 +1442,7 @@ int kb_ctc_greedy_decode(const float *probs, int probs_on_device, int32_t n, int
     return guarded([&]() {
         int cnt = 0;
         if (cudaGetDeviceCount(&cnt) != cudaSuccess || cnt == 0) { cudaGetLastError(); throw CudaError("no CUDA device available: kraken_b200 has no CPU fallback"); }
+        DeviceGuard dguard;
         CK(cudaSetDevice(device));
         cudaStream_t st = (cudaStream_t)stream;
         if (w == 0) { for (int i = 0; i < n; ++i) counts[i] = 0; return (int)KB_OK; }
@@ -1452,6 +1472,7 @@ int kb_segment(kb_model *m, const float *pages, int pages_on_device, int32_t n, 
     if (out_h <= 0 || out_w <= 0) return fail(KB_ERR_ARG, "invalid output size");
     std::lock_guard<std::mutex> lk(m->mu);
     return guarded([&]() {
+        DeviceGuard dguard;
         ensure_ready(m);
         cudaStream_t st = (cudaStream_t)stream;
         Dims d; d.n = n; d.c = m->plan->input[1]; d.h = h; d.w = w; Lens l;
@@ -1475,6 +1496,7 @@ int kb_debug_layer_output(kb_model *m, const char *name, int32_t dims[4], float 
     if (!m || !name || !dims) return fail(KB_ERR_ARG, "NULL argument");
     std::lock_guard<std::mutex> lk(m->mu);
     return guarded([&]() {
+        DeviceGuard dguard;
         ensure_ready(m);
         auto it = m->taps.find(name);
         if (it == m->taps.end()) throw SpecError(std::string("no output recorded for layer ") + name);
@@ -1505,6 +1527,7 @@ int kb_debug_gemm(const float *a, const float *b, const float *bias, float *c, i
     return guarded([&]() {
         int cnt = 0;
         if (cudaGetDeviceCount(&cnt) != cudaSuccess || cnt == 0) { cudaGetLastError(); throw CudaError("no CUDA device available: kraken_b200 has no CPU fallback"); }
+        DeviceGuard dguard;
         CK(cudaSetDevice(device));
         kb_model tmp; tmp.device = device; tmp.use_tc = use_tc != 0;
         cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, device)); tmp.sm_count = prop.multiProcessorCount;

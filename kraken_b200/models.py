@@ -67,9 +67,15 @@ class TorchSeqRecognizer:
         if x.ndim != 4:
             raise ValueError(f'expected a 4D NCHW input, got shape {tuple(x.shape)}')
         n, c, h, w = (int(v) for v in x.shape)
+        if c != net.input[1]:
+            raise ValueError(f'expected {net.input[1]} input channels, got {c}')
+        if _on_device(x) and x.device.index != net._device:
+            x = x.to(f'cuda:{net._device}')
         widths = None
         if lens is not None:
             widths = np.ascontiguousarray(torch.as_tensor(lens).cpu().numpy(), dtype=np.int32)
+            if widths.shape != (n,):
+                raise ValueError('seq_lens must have one entry per batch element')
         key = (getattr(net._h, 'value', None), getattr(net, 'spec', None), n, h, w)
         dims = self._dims_cache.get(key)
         if dims is None:
@@ -116,6 +122,10 @@ class TorchSeqRecognizer:
         x = x.contiguous()
         net._ensure_finalized(x)
         n, c, h, w = (int(v) for v in x.shape)
+        if c != net.input[1]:
+            raise ValueError(f'expected {net.input[1]} input channels, got {c}')
+        if x.is_cuda and x.device.index != net._device:
+            x = x.to(f'cuda:{net._device}')
         wd = np.ascontiguousarray(torch.as_tensor(widths).cpu().numpy(), dtype=np.int32) if widths is not None else None
         inv = np.ascontiguousarray(np.asarray(invert_max), dtype=np.int16) if invert_max is not None else None
         dims = net.infer_dims(n, h, w)
@@ -139,6 +149,8 @@ class TorchSeqRecognizer:
         return self.outputs, olens
 
     def _decode(self, line, lens):
+        if lens is None and getattr(line, 'ndim', 0) == 4 and int(line.shape[0]) > 1:
+            raise ValueError('seq_lens need to be set for batch decoding.')          # ctc_decoder.py:60-61
         if self.decoder is ctc_decoder.greedy_decoder:
             dec, _ = self._recognize(line, lens, want_probs=True)      # `outputs` stays populated (mm_rpred reads its shape)
             return dec

@@ -31,6 +31,13 @@ def test_library_exports_every_declared_symbol():
     assert sorted(_lib.EXPORTS) == declared_symbols()
 
 
+def test_library_was_built_from_the_sources_in_the_tree():
+    """The .so is git-ignored but travels to the GPU box with the snapshot: a stale binary must not pass for the current kernels."""
+    import __graft_entry__ as ge
+    import kraken_b200
+    assert kraken_b200.lib.kb_source_hash().decode() == ge.source_hash()
+
+
 def test_abi_version_and_device_count():
     import kraken_b200
     assert kraken_b200.lib.kb_abi_version() == 1

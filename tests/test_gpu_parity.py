@@ -74,7 +74,12 @@ def test_golden_logits_and_labels(name):
     if 'dec_count' in g:
         temp = float(g['temperature']) if 'temperature' in g else 1.0
         rec = kb.TorchSeqRecognizer(m, temperature=temp, device='cuda:0')
-        dec = rec.predict_labels(x, lens)
+        if lens is None and x.shape[0] > 1:
+            with pytest.raises(ValueError):               # like the reference's decoder (ctc_decoder.py:60-61)
+                rec.predict_labels(x, lens)
+            dec = rec._recognize(x, None, want_probs=False)[0]      # the engine itself decodes the full width
+        else:
+            dec = rec.predict_labels(x, lens)
         exp = dec_from_golden(g)
         assert triples(dec) == triples(exp)
         for d, ex in zip(dec, exp):

@@ -28,7 +28,7 @@ SPECS = [
 @pytest.mark.parametrize('spec', SPECS)
 def test_named_spec_shapes_and_keys_match_oracle_grammar(spec):
     m = kb.TorchVGSLModel(vgsl=spec)
-    om = vo.OracleModel(spec)                     # pinned bit-identically to the reference (test_oracle_pinned.py)
+    om = vo.OracleModel(spec)                     # pinned bit-identically to the reference (tests/test_oracle.py)
     assert '[' + ' '.join(m.named_spec) + ']' == om.named_spec
     assert m.user_metadata['vgsl'] == om.named_spec
     assert tuple(m.input) == tuple(om.input)

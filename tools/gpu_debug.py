@@ -1,5 +1,5 @@
 """Stand-alone GPU diagnostic (not a pytest module): per-layer error of the engine vs the oracle for every golden
-case, printed as a table.  Usage under gpurun:  python tests/gpu_debug.py > gpurun_out/debug.log 2>&1"""
+case, printed as a table.  Usage under gpurun:  python tools/gpu_debug.py > gpurun_out/debug.log 2>&1"""
 import os
 import sys
 import time
