@@ -358,7 +358,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--cpu-steps', type=int, default=6)
-    ap.add_argument('--inflight', type=int, default=4, help='engine handles driven concurrently in the e2e arm')
+    ap.add_argument('--inflight', type=int, default=4, help='pipeline slots (batches in flight from the one host thread) of the e2e arm')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--workload', default='cfg2', choices=['cfg2', 'cfg3'])
     ap.add_argument('--pages', type=int, default=8)
@@ -398,17 +398,11 @@ def main():
         m.load_state_dict(broadcast_state_dict(m.state_dict(), src=0, device=torch.device(dev)))
     rec = kb.TorchSeqRecognizer(m, device=dev)
     lens = torch.full((BATCH,), WIDTH, dtype=torch.long)
-    # end-to-end arm: IN_FLIGHT engine handles (own stream + workspace each, same weights) driven by host threads, so that the
-    # H2D copy / D2H read-back / host work of one batch overlap the kernels of the other - how a serving job would run it
-    # every in-flight batch is a host thread that spin-waits on its stream: do not oversubscribe the cores this job may use
-    # (all ranks of a node share them), but keep at least two batches in flight
-    IN_FLIGHT = max(1, min(args.inflight, max(2, usable_cpus() // max(world, 1))))
-    recs = [rec]
-    for _ in range(IN_FLIGHT - 1):
-        m2 = kb.TorchVGSLModel(vgsl=CFG2, model_type=['recognition'])
-        m2.load_state_dict(m.state_dict())
-        recs.append(kb.TorchSeqRecognizer(m2, device=dev))
-    streams = [torch.cuda.Stream(device=dev) for _ in recs]
+    # end-to-end arm: ONE engine handle with DEPTH pipeline slots (own stream + workspace each, one copy of the weights) fed by ONE
+    # host thread through kb_recognize_async / kb_wait: the H2D copy, the kernels and the D2H read-back of consecutive batches overlap,
+    # and the thread sleeps on a blocking CUDA event while it waits - how a serving loop would run it
+    DEPTH = max(1, min(args.inflight, 16))
+    rec.set_pipeline_depth(DEPTH)
 
     NB = 4                                               # distinct input batches rotated through the steps
     host = [b.pin_memory() for b in make_batches(NB, 1000 + rank)]
@@ -461,46 +455,28 @@ def main():
         return out
 
     def run_pipelined(batches, steps, sink, u8=False):
-        import threading
         res = [None] * steps
-        errs = []
         pbuf = packed(steps).numpy() if world > 1 else None
+        pend = []
 
-        def worker(k):
-            try:
-                torch.cuda.set_device(local)
-                with torch.cuda.stream(streams[k]):
-                    for i in range(k, steps, len(recs)):
-                        if u8:
-                            res[i] = recs[k].recognize_u8(batches[i % NB], lens, inv255)
-                            if pbuf is not None:
-                                pack_into(pbuf, i, res[i]); res[i]['_packed'] = True
-                        else:
-                            res[i] = recs[k]._recognize_raw(batches[i % NB], lens, want_probs=False,
-                                                            out=out_views(pbuf, i) if pbuf is not None else None)
-                            if pbuf is not None:
-                                res[i]['_packed'] = True
-            except Exception as e:       # surface worker failures in the main thread
-                errs.append(e)
-        cur = torch.cuda.current_stream()
-        for s_ in streams:
-            s_.wait_stream(cur)
-        ths = [threading.Thread(target=worker, args=(k,)) for k in range(len(recs))]
-        for th in ths:
-            th.start()
-        for th in ths:
-            th.join()
-        for s_ in streams:
-            cur.wait_stream(s_)
-        if errs:
-            raise errs[0]
+        def fetch():
+            j, t = pend.pop(0)
+            res[j] = rec.collect(t, out=out_views(pbuf, j) if pbuf is not None else None)
+            if pbuf is not None:
+                res[j]['_packed'] = True
+        for i in range(steps):
+            if len(pend) == DEPTH:
+                fetch()
+            pend.append((i, rec.submit(batches[i % NB], lens, inv255 if u8 else None)))
+        while pend:
+            fetch()
         sink.extend(res)
 
     def timed(batches, steps, sink, on_step=None, pipelined=False, u8=False):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        if pipelined and len(recs) > 1:
+        if pipelined:
             run_pipelined(batches, steps, sink, u8)
         else:
             buf = packed(steps).numpy() if world > 1 else None
@@ -524,9 +500,9 @@ def main():
 
     for i in range(args.warmup):
         step(devb[i % NB]); step(host[i % NB])
-    if len(recs) > 1:
-        run_pipelined(host, 2 * len(recs), [])
-        run_pipelined(host_u8, 2 * len(recs), [], u8=True)
+    run_pipelined(host, 2 * DEPTH, [])
+    run_pipelined(host_u8, 2 * DEPTH, [], u8=True)
+    run_pipelined(devb, 2 * DEPTH, [])
     if world > 1:
         gather_all([step(devb[0])])          # warm the NCCL gather up (lazy communicator / channel setup) before timing ...
         gather_all([None] * args.steps)      # ... at the payload size of the timed runs (buffers grow with the first large collective)
@@ -554,7 +530,8 @@ def main():
     results_buf2 = []
     ms_e2e_serial = timed(host, args.steps, [])
     ms_e2e = timed(host, args.steps, results_buf2, pipelined=True)
-    ms_e2e_u8 = timed(host_u8, args.steps, [], pipelined=True, u8=True) if len(recs) > 1 else None
+    ms_e2e_u8 = timed(host_u8, args.steps, [], pipelined=True, u8=True)
+    ms_dev_pipe = timed(devb, args.steps, [], pipelined=True)          # device-resident inputs through the same pipeline
 
     if rank != 0:
         if world > 1:
@@ -592,7 +569,7 @@ def main():
                  'algorithmic_per_launch': {'flops': flops, 'bytes': byts},
                  'stages_ms': {k: round(v, 4) for k, v in per_stage.items()},
                  'per_stage': per_stage_roofline(per_stage, work, pk, BATCH)})
-    tot_f = sum(v[0] for v in work.values()) * BATCH
+    tot_f = sum(work[k][0] for k in per_stage if k in work) * BATCH          # only the stages that actually ran (fused groups replace their members)
     tot_b = (4 * 48 * WIDTH + 2 * 4 * 768 * T + 2 * 4 * 2048 * T + 2 * 4 * 512 * T + 8 * T) * BATCH
     roof['whole_step'] = {'tensor_frac': tot_f / (ms_step / 1e3) / (pk['tf_sustained'] * 1e12),
                           'hbm_frac': tot_b / (ms_step / 1e3) / (pk['hbm_gbs'] * 1e9)}
@@ -611,14 +588,17 @@ def main():
             'config': {'workload': 'cfg2', 'spec': CFG2, 'batch_per_gpu': BATCH, 'global_batch': BATCH * world, 'line': f'{HEIGHT}x{WIDTH}',
                        'parallelism': f'replicas x{world} (independent line shards, 1 weight broadcast + 1 result gather)',
                        'l2': f'{NB} rotating input batches; ~0.3 GB of activations per step > 126 MB L2'},
-            'e2e': {'value': e2e, 'unit': UNIT, 'ms_per_step': ms_e2e / args.steps, 'in_flight': len(recs),
+            'value_pipelined': {'value': world * BATCH * args.steps / (ms_dev_pipe / 1e3), 'unit': UNIT, 'ms_per_step': ms_dev_pipe / args.steps,
+                                'note': f'device-resident inputs, kb_recognize_async with {DEPTH} batches in flight from one host thread'},
+            'e2e': {'value': e2e, 'unit': UNIT, 'ms_per_step': ms_e2e / args.steps, 'in_flight': DEPTH, 'host_threads': 1,
                     'serial_value': world * BATCH * args.steps / (ms_e2e_serial / 1e3),
                     'h2d_bytes_per_step': BATCH * HEIGHT * WIDTH * 4, 'd2h_bytes_per_step': d2h,
-                    'api': 'TorchSeqRecognizer._recognize_raw -> kb_recognize, pinned host lines in, label blocks out'},
+                    'api': 'TorchSeqRecognizer.submit/collect -> kb_recognize_async/kb_wait on one handle, pinned host lines in, label blocks out; '
+                           'serial_value = TorchSeqRecognizer._recognize_raw -> kb_recognize one call at a time'},
             'e2e_u8': None if ms_e2e_u8 is None else {
                 'value': world * BATCH * args.steps / (ms_e2e_u8 / 1e3), 'unit': UNIT, 'ms_per_step': ms_e2e_u8 / args.steps,
-                'in_flight': len(recs), 'h2d_bytes_per_step': BATCH * HEIGHT * WIDTH + BATCH * 6, 'd2h_bytes_per_step': d2h,
-                'api': 'TorchSeqRecognizer.recognize_u8 -> kb_recognize_u8: pinned uint8 lines in; ToDtype(scale) + tensor_invert + padding on the device'},
+                'in_flight': DEPTH, 'host_threads': 1, 'h2d_bytes_per_step': BATCH * HEIGHT * WIDTH + BATCH * 6, 'd2h_bytes_per_step': d2h,
+                'api': 'TorchSeqRecognizer.submit(uint8 lines) -> kb_recognize_async(KB_DTYPE_U8): pinned uint8 lines in; ToDtype(scale) + tensor_invert + padding on the device'},
             'gpu_launches': int(launches), 'clocks': clocks, 'roofline': roof, 'cpu_baseline': cpu,
             'decoded_labels_last_step': int(results_buf[-1]['counts'].sum()) if results_buf else 0}
     print(json.dumps(line), flush=True)

@@ -48,7 +48,7 @@
 extern "C" {
 #endif
 
-#define KB_ABI_VERSION 1
+#define KB_ABI_VERSION 2
 
 enum {
     KB_OK = 0,
@@ -146,6 +146,37 @@ int  kb_recognize_u8(kb_model *m, const uint8_t *lines, int lines_on_device, int
                      const int32_t *widths, const int16_t *invert_max, float temperature, int32_t *labels, int32_t *starts,
                      int32_t *ends, float *confs, int32_t *counts, int32_t max_out, int32_t *out_lens, float *probs,
                      int probs_on_device, void *stream);
+
+/* ---- asynchronous pipeline ------------------------------------------------------------------------
+ * The calls above finish with the results in the caller's arrays (one cudaStreamSynchronize each).  A serving loop that wants the
+ * copies, the host work and the kernels of consecutive batches to overlap uses ONE model handle with `depth` pipeline slots instead
+ * (own stream, activation arena and pinned result block each; ONE copy of the weights): kb_recognize_async enqueues a batch into the
+ * next slot and returns a ticket without waiting for the device; kb_wait(ticket) sleeps until that batch is done (blocking-sync
+ * event, no spinning) and unpacks its labels.  One host thread keeps `depth` batches in flight:
+ *
+ *     kb_set_pipeline_depth(m, 4);
+ *     for (i = 0; i < nbatches; ++i) {
+ *         if (i >= 4) kb_wait(m, t[i - 4], ...);                        // oldest first: its slot is the next to be reused
+ *         kb_recognize_async(m, batch[i], KB_DTYPE_F32, 0, n, h, w, widths, NULL, 1.f, T, NULL, &t[i]);
+ *     }
+ *
+ * lines: float32 (KB_DTYPE_F32, kb_recognize semantics) or uint8 (KB_DTYPE_U8, kb_recognize_u8 semantics incl. invert_max).  A HOST
+ * `lines` buffer must stay valid and unchanged until kb_wait returns (pin it for a truly asynchronous copy); `widths` / `invert_max`
+ * are copied during the call.  For a DEVICE buffer `input_stream` is the stream it was produced on (the slot's stream waits for the
+ * work queued there so far).  A batch whose activations left the fp16 operand range is repeated on the fp32 kernels inside kb_wait.
+ * kb_recognize_async fails with KB_ERR_SPEC when every slot still holds an un-waited ticket.  Replaces the reference's one-batch-at-
+ * a-time loop over `_rec_predict` (kraken/lib/vgsl/rpred.py:126-131,171-176,210-229).                                              */
+#define KB_DTYPE_F32 0
+#define KB_DTYPE_U8  1
+int  kb_set_pipeline_depth(kb_model *m, int32_t depth);       /* 1..16 slots; allowed only while no ticket is in flight */
+int  kb_pipeline_depth(const kb_model *m);
+int  kb_recognize_async(kb_model *m, const void *lines, int dtype, int lines_on_device, int32_t n, int32_t h, int32_t w,
+                        const int32_t *widths, const int16_t *invert_max, float temperature, int32_t max_out, void *input_stream,
+                        int64_t *ticket);
+/* counts[i] is the number of labels line i decoded to; it can exceed max_out, in which case only the first max_out are stored
+ * (the same holds for kb_recognize / kb_recognize_u8 / kb_ctc_greedy_decode).                                                     */
+int  kb_wait(kb_model *m, int64_t ticket, int32_t *labels, int32_t *starts, int32_t *ends, float *confs, int32_t *counts,
+             int32_t *out_lens);
 
 /* ---- decoder hook -------------------------------------------------------------------------------
  * replaces kraken.lib.ctc_decoder.greedy_decoder (ctc_decoder.py:35-72) for a (N, C, W) probability

@@ -68,6 +68,58 @@ struct Arena {
 
 struct Lens { bool has = false; std::vector<int32_t> v; };
 
+// Per-call state.  Workspace 0 serves the synchronous entry points on the caller's stream; workspaces 1..depth are the slots of the
+// asynchronous pipeline (kb_recognize_async / kb_wait): own stream, arena, pinned result block and range flag each, ONE copy of the
+// weights shared by all of them.
+struct Workspace {
+    int index = 0;
+    Arena arena;
+    cudaStream_t stream = nullptr;            // internal stream of an async slot (workspace 0 runs on the caller's stream)
+    cudaEvent_t done = nullptr, input_ready = nullptr;
+    void *pinned = nullptr; size_t pinned_cap = 0;          // result block (D2H target)
+    char *params = nullptr; size_t params_cap = 0, params_off = 0;      // pinned staging of the call's small host arrays (lens, widths)
+    int *d_flag = nullptr;           // device: set by plane producers when an activation leaves the fp16 range
+    int *h_flag = nullptr;           // pinned copy, valid after the stream is synchronised
+    uint8_t *u8_raw = nullptr; size_t u8_raw_cap = 0;       // kb_recognize_u8: device copy of host uint8 lines
+    float *u8_f32 = nullptr; size_t u8_f32_cap = 0;         // ... and their float form (the network input)
+    std::map<std::string, Tensor> taps;
+    bool timing = false;
+    struct Stage { std::string name; cudaEvent_t a = nullptr, b = nullptr; float ms = 0.f; };
+    std::vector<Stage> stages;       // event pool, reused across calls
+    size_t n_stages = 0;             // entries used by the most recent call
+    // ---- pending asynchronous call (kb_recognize_async .. kb_wait)
+    bool busy = false; int64_t ticket = -1;
+    struct Pending {
+        int n = 0, h = 0, w = 0, T = 0, max_out = 0, dtype = 0; float temperature = 1.f;
+        const void *device_input = nullptr;      // network input as staged on the device (valid until the slot is reused)
+        bool has_widths = false; std::vector<int32_t> widths, olens;
+        char *d_result = nullptr; size_t result_bytes = 0;
+    } pend;
+    void release() {
+        if (arena.base) cudaFree(arena.base);
+        arena = Arena();
+        if (pinned) cudaFreeHost(pinned);
+        pinned = nullptr; pinned_cap = 0;
+        if (params) cudaFreeHost(params);
+        params = nullptr; params_cap = 0;
+        if (h_flag) cudaFreeHost(h_flag);
+        h_flag = nullptr;
+        if (d_flag) cudaFree(d_flag);
+        d_flag = nullptr;
+        if (u8_raw) cudaFree(u8_raw);
+        if (u8_f32) cudaFree(u8_f32);
+        u8_raw = nullptr; u8_f32 = nullptr; u8_raw_cap = u8_f32_cap = 0;
+        for (auto &e : stages) { if (e.a) cudaEventDestroy(e.a); if (e.b) cudaEventDestroy(e.b); }
+        stages.clear(); n_stages = 0;
+        if (done) cudaEventDestroy(done);
+        if (input_ready) cudaEventDestroy(input_ready);
+        done = input_ready = nullptr;
+        if (stream) cudaStreamDestroy(stream);
+        stream = nullptr;
+        busy = false; ticket = -1;
+    }
+};
+
 }  // namespace kb
 
 using namespace kb;
@@ -78,40 +130,34 @@ struct kb_model {
     int device = -1;
     bool finalized = false;
     std::mutex mu;
-    Arena arena;
+    std::vector<std::unique_ptr<Workspace>> wss;      // [0] synchronous calls, [1..] asynchronous slots
+    int64_t next_ticket = 0;
     std::vector<void *> dev_allocs;              // weights
-    void *pinned = nullptr; size_t pinned_cap = 0;
     int64_t launches = 0;
-    std::map<std::string, Tensor> taps;
     bool timing = false;
-    struct Stage { std::string name; cudaEvent_t a = nullptr, b = nullptr; float ms = 0.f; };
-    std::vector<Stage> stages;       // event pool, reused across calls
-    size_t n_stages = 0;             // entries used by the most recent call
     int sm_count = 148;
     int max_clusters8 = -1;          // co-resident 8-CTA clusters of the recurrence kernel (queried once)
     int fuse_mask = 7;               // bit 0: stencil+pool group, bit 1: tcgen05 conv group, bit 2: stride-2 conv via space-to-depth
     bool keep_fp32 = false;          // KB_KEEP_FP32=1: fused producers also write the fp32 tensor their plane-only consumer ignores (taps)
-    int *d_flag = nullptr;           // device: set by plane producers when an activation leaves the fp16 range
-    int *h_flag = nullptr;           // pinned copy, valid after the stream is synchronised
     bool force_ffma = false;         // second attempt of a call whose first attempt raised the flag: fp32 CUDA-core kernels only
     int64_t overflow_reruns = 0;
-    uint8_t *u8_raw = nullptr; size_t u8_raw_cap = 0;       // kb_recognize_u8: device copy of host uint8 lines
-    float *u8_f32 = nullptr; size_t u8_f32_cap = 0;         // ... and their float form (the network input)
     double prof_us[4] = {0, 0, 0, 0}; int64_t prof_calls = 0;    // KB_HOST_PROF: host microseconds in plan / launch / wait / unpack
     bool fuse = true;                // fused layer groups (KB_FUSE=0 runs every layer on its own, e.g. for layer taps)
     bool use_tc = true;              // tcgen05 GEMM path (KB_GEMM=ffma forces the CUDA-core kernel)
+    kb_model() { wss.emplace_back(new Workspace()); }
+    Workspace *ws0() { return wss[0].get(); }
+    void release_device_state() {
+        for (void *p : dev_allocs) cudaFree(p);
+        dev_allocs.clear();
+        for (auto &w : wss) w->release();
+        wss.resize(1);
+    }
     ~kb_model() {
         if (device >= 0) {
             int prev = -1;
             if (cudaGetDevice(&prev) != cudaSuccess) { cudaGetLastError(); prev = -1; }
             cudaSetDevice(device);
-            for (void *p : dev_allocs) cudaFree(p);
-            if (arena.base) cudaFree(arena.base);
-            if (pinned) cudaFreeHost(pinned);
-            if (h_flag) cudaFreeHost(h_flag);
-            if (u8_raw) cudaFree(u8_raw);
-            if (u8_f32) cudaFree(u8_f32);
-            for (auto &e : stages) { if (e.a) cudaEventDestroy(e.a); if (e.b) cudaEventDestroy(e.b); }
+            release_device_state();
             if (prev >= 0) cudaSetDevice(prev);
         }
     }
@@ -129,17 +175,17 @@ namespace kb {
 // RAII device timer for one named stage of a call (only when kb_set_timing(m, 1)); events are recorded on the
 // launching stream, so the elapsed time is what the stream spent between the two records.
 struct StageTimer {
-    kb_model *m; cudaStream_t st; int idx = -1;
-    StageTimer(kb_model *m_, cudaStream_t st_, const std::string &name, bool active) : m(m_), st(st_) {
-        if (!active || !m->timing) return;
-        if (m->n_stages == m->stages.size()) {
-            kb_model::Stage s; CK(cudaEventCreate(&s.a)); CK(cudaEventCreate(&s.b)); m->stages.push_back(s);
+    Workspace *ws; cudaStream_t st; int idx = -1;
+    StageTimer(Workspace *ws_, cudaStream_t st_, const std::string &name, bool active) : ws(ws_), st(st_) {
+        if (!active || !ws->timing) return;
+        if (ws->n_stages == ws->stages.size()) {
+            Workspace::Stage s; CK(cudaEventCreate(&s.a)); CK(cudaEventCreate(&s.b)); ws->stages.push_back(s);
         }
-        idx = (int)m->n_stages++;
-        m->stages[idx].name = name; m->stages[idx].ms = 0.f;
-        CK(cudaEventRecord(m->stages[idx].a, st));
+        idx = (int)ws->n_stages++;
+        ws->stages[idx].name = name; ws->stages[idx].ms = 0.f;
+        CK(cudaEventRecord(ws->stages[idx].a, st));
     }
-    ~StageTimer() { if (idx >= 0) cudaEventRecord(m->stages[idx].b, st); }
+    ~StageTimer() { if (idx >= 0) cudaEventRecord(ws->stages[idx].b, st); }
 };
 
 static inline unsigned grid1d(long long total, int block, int sm_count) {
@@ -365,20 +411,20 @@ static void finalize_weights(kb_model *m) {
 // executor
 // -------------------------------------------------------------------------------------------------
 struct Exec {
-    kb_model *m; cudaStream_t st; bool dry;
+    kb_model *m; Workspace *ws; cudaStream_t st; bool dry;
     int leaf_counter = 0;
     bool planes_hint = false;        // set by run() for a GroupNorm / LSTM whose consumer reads fp16 operand planes
     bool s2d_hint = false;           // ... for a GroupNorm whose consumer is a stride-2 convolution on the tensor cores
 
     int *dev_lens(const Lens &l) {
         if (!l.has) return nullptr;
-        int *d = (int *)m->arena.alloc(l.v.size() * sizeof(int));
+        int *d = (int *)ws->arena.alloc(l.v.size() * sizeof(int));
         if (!dry) CK(cudaMemcpyAsync(d, l.v.data(), l.v.size() * sizeof(int), cudaMemcpyHostToDevice, st));
         return d;
     }
     Tensor mk(const Dims &d) {
         Tensor t; t.n = d.n; t.c = d.c; t.h = d.h; t.w = d.w;
-        t.p = (float *)m->arena.alloc((size_t)std::max<int64_t>(t.numel(), 1) * sizeof(float));
+        t.p = (float *)ws->arena.alloc((size_t)std::max<int64_t>(t.numel(), 1) * sizeof(float));
         return t;
     }
     static Dims dims_of(const Tensor &t) { Dims d; d.n = t.n; d.c = t.c; d.h = t.h; d.w = t.w; return d; }
@@ -395,11 +441,11 @@ struct Exec {
         const int K = w.K, N = w.ncols;
         __half *a_hi = x.hi, *a_lo = x.lo;
         if (!a_hi) {
-            a_hi = (__half *)m->arena.alloc((size_t)M * K * sizeof(__half));
-            a_lo = (__half *)m->arena.alloc((size_t)M * K * sizeof(__half));
+            a_hi = (__half *)ws->arena.alloc((size_t)M * K * sizeof(__half));
+            a_lo = (__half *)ws->arena.alloc((size_t)M * K * sizeof(__half));
         }
         if (dry) return;
-        if (!x.hi) LAUNCH(m, tc::k_split_f16, grid1d(M * K / 4, 256, m->sm_count), 256, 0, st, x.p, a_hi, a_lo, M * K / 4, m->d_flag);
+        if (!x.hi) LAUNCH(m, tc::k_split_f16, grid1d(M * K / 4, 256, m->sm_count), 256, 0, st, x.p, a_hi, a_lo, M * K / 4, ws->d_flag);
         CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
         if (!tc::make_map_2d(&ta_hi, a_hi, (uint64_t)M, (uint64_t)K, tc::BM, tc::BK) || !tc::make_map_2d(&ta_lo, a_lo, (uint64_t)M, (uint64_t)K, tc::BM, tc::BK) ||
             !tc::make_map_2d(&tb_hi, w.b_hi, (uint64_t)N, (uint64_t)K, tc::BN / 2, tc::BK) || !tc::make_map_2d(&tb_lo, w.b_lo, (uint64_t)N, (uint64_t)K, tc::BN / 2, tc::BK))
@@ -498,20 +544,20 @@ struct Exec {
             const long long npix = (long long)H * W;
             int chunks = (int)std::min<long long>(std::max<long long>(1, npix * C / 16384), (long long)std::max(1, 8 * sm / std::max(N, 1)));
             const int cthreads = std::min(C, 256), rows = std::max(1, 256 / cthreads), cpt = (C + cthreads - 1) / cthreads;
-            double *partial = (double *)m->arena.alloc((size_t)N * chunks * G * 2 * sizeof(double));
-            float2 *stats = (float2 *)m->arena.alloc((size_t)N * G * sizeof(float2));
+            double *partial = (double *)ws->arena.alloc((size_t)N * chunks * G * 2 * sizeof(double));
+            float2 *stats = (float2 *)ws->arena.alloc((size_t)N * G * sizeof(float2));
             bool ragged = false;
             if (lens.has) for (int32_t l : lens.v) if (l < W) ragged = true;
             int *dl = ragged ? dev_lens(lens) : nullptr;
             const bool vec4 = (C % 4) == 0 && C <= 1024 && !(getenv("KB_GN") && strcmp(getenv("KB_GN"), "scalar") == 0);
-            float2 *ab = vec4 ? (float2 *)m->arena.alloc((size_t)N * C * sizeof(float2)) : nullptr;
+            float2 *ab = vec4 ? (float2 *)ws->arena.alloc((size_t)N * C * sizeof(float2)) : nullptr;
             const bool s2d = vec4 && s2d_hint && (C % 8) == 0;
             const bool planes = vec4 && planes_hint && !s2d;
             planes_hint = false; s2d_hint = false;
-            if (planes) { y.hi = (__half *)m->arena.alloc((size_t)y.numel() * 2); y.lo = (__half *)m->arena.alloc((size_t)y.numel() * 2); }
+            if (planes) { y.hi = (__half *)ws->arena.alloc((size_t)y.numel() * 2); y.lo = (__half *)ws->arena.alloc((size_t)y.numel() * 2); }
             if (s2d) {
                 const size_t se = (size_t)N * ((H + 1) / 2) * ((W + 1) / 2) * 4 * C;
-                y.s_hi = (__half *)m->arena.alloc(se * 2); y.s_lo = (__half *)m->arena.alloc(se * 2); y.s2d_c = 4 * C;
+                y.s_hi = (__half *)ws->arena.alloc(se * 2); y.s_lo = (__half *)ws->arena.alloc(se * 2); y.s2d_c = 4 * C;
             }
             if (!dry && y.numel()) {
                 if (vec4) {
@@ -523,7 +569,7 @@ struct Exec {
                     LAUNCH(m, k_gn_coeffs, (unsigned)((N * C + 255) / 256), 256, 0, st, stats, w.aux, w.bias, ab, N, C, G);
                     const long long nb = std::min<long long>((npix + rows4 - 1) / rows4, std::max(1, 16 * sm / std::max(N, 1)));
                     LAUNCH(m, k_gn_apply4, dim3((unsigned)nb, N), 256, 0, st, x.p, ((planes || s2d) && !m->keep_fp32) ? nullptr : y.p,
-                           s2d ? y.s_hi : y.hi, s2d ? y.s_lo : y.lo, ab, H, W, C, dl, m->d_flag, s2d ? 1 : 0);
+                           s2d ? y.s_hi : y.hi, s2d ? y.s_lo : y.lo, ab, H, W, C, dl, ws->d_flag, s2d ? 1 : 0);
                 } else {
                     const int bt = rows * cthreads;
                     LAUNCH(m, k_gn_partial, dim3(chunks, N), bt, (size_t)bt * cpt * 2 * sizeof(double), st, x.p, partial, H, W, C, G, dl, chunks, rows, cthreads, cpt);
@@ -551,11 +597,11 @@ struct Exec {
             const bool tc_rec = (ks_p == 8 || ks_p == 1) && w.wpk && m->use_tc && !(getenv("KB_LSTM_TC") && atoi(getenv("KB_LSTM_TC")) == 0);
             const bool lplanes = planes_hint && tc_rec && !n.summarize;
             planes_hint = false;
-            if (lplanes) { full.hi = (__half *)m->arena.alloc((size_t)full.numel() * 2); full.lo = (__half *)m->arena.alloc((size_t)full.numel() * 2); }
+            if (lplanes) { full.hi = (__half *)ws->arena.alloc((size_t)full.numel() * 2); full.lo = (__half *)ws->arena.alloc((size_t)full.numel() * 2); }
             int *dl = packed ? dev_lens(lens) : nullptr;
-            if (full.numel()) { StageTimer tt(m, st, n.name + ".xproj", !dry); gemm(x, w, nullptr, ACT_LINEAR, gx.p, x.h, x.w); }
+            if (full.numel()) { StageTimer tt(ws, st, n.name + ".xproj", !dry); gemm(x, w, nullptr, ACT_LINEAR, gx.p, x.h, x.w); }
             if (!dry && full.numel()) {
-                StageTimer tt(m, st, n.name + ".rec", true);
+                StageTimer tt(ws, st, n.name + ".rec", true);
                 LstmParams lp;
                 lp.gx = gx.p; lp.whh = w.aux; lp.out = full.p; lp.lens = dl; lp.hid = hid; lp.dirs = dirs;
                 if (!n.transpose) { lp.nseq = (int)(x.n * x.h); lp.T = (int)x.w; lp.q2 = 1; lp.s_outer = x.w; lp.s_inner = 0; lp.step = 1; }
@@ -717,11 +763,11 @@ struct Exec {
             // a tensor-core conv right behind wants the operand planes
             const Node *nx = next_real(series, j + 1);
             const bool planes = m->use_tc && nx && nx->kind == K_CONV && tc_conv_eligible(*nx, dpool);
-            if (planes) { y.hi = (__half *)m->arena.alloc((size_t)y.numel() * 2); y.lo = (__half *)m->arena.alloc((size_t)y.numel() * 2); }
+            if (planes) { y.hi = (__half *)ws->arena.alloc((size_t)y.numel() * 2); y.lo = (__half *)ws->arena.alloc((size_t)y.numel() * 2); }
             if (!dry && y.numel()) {
-                StageTimer tt(m, st, c0.name + "+" + pl->name, true);
+                StageTimer tt(ws, st, c0.name + "+" + pl->name, true);
                 Conv1PoolParams cp;
-                cp.x = cur.p; cp.wt = w.wt; cp.bias = w.bias; cp.y = (planes && !m->keep_fp32) ? nullptr : y.p; cp.y_hi = y.hi; cp.y_lo = y.lo; cp.flag = m->d_flag;
+                cp.x = cur.p; cp.wt = w.wt; cp.bias = w.bias; cp.y = (planes && !m->keep_fp32) ? nullptr : y.p; cp.y_hi = y.hi; cp.y_lo = y.lo; cp.flag = ws->d_flag;
                 cp.N = (int)cur.n; cp.H = (int)cur.h; cp.W = (int)cur.w; cp.Cout = c0.cout; cp.Ncp = w.ncp; cp.kh = c0.kh; cp.kw = c0.kw;
                 cp.py = c0.py; cp.px = c0.px; cp.Hp = (int)dpool.h; cp.Wp = (int)dpool.w; cp.act = c0.act;
                 const int cgroups = c0.cout / 8, ppb = 256 / cgroups;
@@ -747,7 +793,7 @@ struct Exec {
             advance_lens(c0, lens, din, dconv);
             advance_lens(*pl, lens, dconv, dpool);
             cur = y;
-            if (!dry) m->taps[pl->name] = y;
+            if (!dry) ws->taps[pl->name] = y;
             return j + 1 - i;
         }
         if ((m->fuse_mask & 4) && c0.kind == K_CONV && m->lw[c0.leaf_index].s2d) { const size_t u = fuse_conv_s2d(series, i, cur, lens); if (u) return u; }
@@ -788,22 +834,22 @@ struct Exec {
         const int cs = w.s_cs;
         Tensor y = mk(dconv);
         const bool planes = wants_planes(series, i + 1, dconv);
-        if (planes) { y.hi = (__half *)m->arena.alloc((size_t)y.numel() * 2); y.lo = (__half *)m->arena.alloc((size_t)y.numel() * 2); }
+        if (planes) { y.hi = (__half *)ws->arena.alloc((size_t)y.numel() * 2); y.lo = (__half *)ws->arena.alloc((size_t)y.numel() * 2); }
         __half *x_hi = cur.s_hi, *x_lo = cur.s_lo;
         const bool have = x_hi && cur.s2d_c == cs;
         if (!have) {
             const size_t se = (size_t)din.n * Hb * Wb * cs;
-            x_hi = (__half *)m->arena.alloc(se * 2); x_lo = (__half *)m->arena.alloc(se * 2);
+            x_hi = (__half *)ws->arena.alloc(se * 2); x_lo = (__half *)ws->arena.alloc(se * 2);
         }
         if (!dry && y.numel()) {
-            StageTimer tt(m, st, c0.name, true);
+            StageTimer tt(ws, st, c0.name, true);
             if (!have) {
                 const float *src = cur.nchw ? cur.nchw : cur.p;
                 LAUNCH(m, k_s2d_planes, grid1d((long long)din.n * Hb * Wb * (cs / 8), 256, m->sm_count), 256, 0, st, src, cur.nchw ? 1 : 0, x_hi, x_lo,
-                       (int)din.n, (int)din.c, (int)din.h, (int)din.w, (int)Hb, (int)Wb, cs, m->d_flag);
+                       (int)din.n, (int)din.c, (int)din.h, (int)din.w, (int)Hb, (int)Wb, cs, ws->d_flag);
             }
             ctc::ConvTcParams cp;
-            cp.bias = w.bias; cp.y = (planes && !m->keep_fp32) ? nullptr : y.p; cp.y_hi = y.hi; cp.y_lo = y.lo; cp.flag = m->d_flag;
+            cp.bias = w.bias; cp.y = (planes && !m->keep_fp32) ? nullptr : y.p; cp.y_hi = y.hi; cp.y_lo = y.lo; cp.flag = ws->d_flag;
             cp.N = (int)din.n; cp.Ho = (int)dconv.h; cp.Wo = (int)dconv.w; cp.Cout = c0.cout; cp.kh = w.s_th; cp.kw = w.s_tw; cp.py = w.s_py; cp.px = w.s_px;
             cp.act = c0.act; cp.pool = 0;
             cp.out_h = (int)dconv.h; cp.out_w = (int)dconv.w;
@@ -825,7 +871,7 @@ struct Exec {
         }
         advance_lens(c0, lens, din, dconv);
         cur = y;
-        if (!dry) m->taps[c0.name] = y;
+        if (!dry) ws->taps[c0.name] = y;
         return 1;
     }
 
@@ -845,16 +891,16 @@ struct Exec {
         Tensor y = mk(dout);
         // consumer wants operand planes?  (another tensor-core conv, or an LSTM / Linear whose projection runs on k_gemm_tc)
         const bool planes = wants_planes(series, j, dout);
-        if (planes) { y.hi = (__half *)m->arena.alloc((size_t)y.numel() * 2); y.lo = (__half *)m->arena.alloc((size_t)y.numel() * 2); }
+        if (planes) { y.hi = (__half *)ws->arena.alloc((size_t)y.numel() * 2); y.lo = (__half *)ws->arena.alloc((size_t)y.numel() * 2); }
         __half *x_hi = cur.hi, *x_lo = cur.lo;
-        if (!x_hi) { x_hi = (__half *)m->arena.alloc((size_t)cur.numel() * 2); x_lo = (__half *)m->arena.alloc((size_t)cur.numel() * 2); }
+        if (!x_hi) { x_hi = (__half *)ws->arena.alloc((size_t)cur.numel() * 2); x_lo = (__half *)ws->arena.alloc((size_t)cur.numel() * 2); }
         if (!dry && y.numel()) {
             std::string nm = c0.name; if (pl) nm += "+" + pl->name; if (fd) nm += "+" + fd->name;
-            StageTimer tt(m, st, nm, true);
-            if (!cur.hi) LAUNCH(m, tc::k_split_f16, grid1d(cur.numel() / 4, 256, m->sm_count), 256, 0, st, cur.p, x_hi, x_lo, (long long)(cur.numel() / 4), m->d_flag);
+            StageTimer tt(ws, st, nm, true);
+            if (!cur.hi) LAUNCH(m, tc::k_split_f16, grid1d(cur.numel() / 4, 256, m->sm_count), 256, 0, st, cur.p, x_hi, x_lo, (long long)(cur.numel() / 4), ws->d_flag);
             const LeafWeights &w = m->lw[c0.leaf_index];
             ctc::ConvTcParams cp;
-            cp.bias = w.bias; cp.y = (planes && !m->keep_fp32) ? nullptr : y.p; cp.y_hi = y.hi; cp.y_lo = y.lo; cp.flag = m->d_flag;
+            cp.bias = w.bias; cp.y = (planes && !m->keep_fp32) ? nullptr : y.p; cp.y_hi = y.hi; cp.y_lo = y.lo; cp.flag = ws->d_flag;
             cp.N = (int)cur.n; cp.Ho = (int)dconv.h; cp.Wo = (int)dconv.w; cp.Cout = c0.cout; cp.kh = c0.kh; cp.kw = c0.kw; cp.py = c0.py; cp.px = c0.px;
             cp.act = c0.act; cp.pool = pl ? 1 : 0;
             cp.out_h = (int)dpost.h; cp.out_w = (int)dpost.w;
@@ -879,7 +925,7 @@ struct Exec {
         if (pl) advance_lens(*pl, lens, dconv, dpost);
         if (fd) advance_lens(*fd, lens, dpost, dout);
         cur = y;
-        if (!dry) m->taps[fd ? fd->name : (pl ? pl->name : c0.name)] = y;
+        if (!dry) ws->taps[fd ? fd->name : (pl ? pl->name : c0.name)] = y;
         return j - i;
     }
 
@@ -924,10 +970,10 @@ struct Exec {
         // leaf
         Tensor y;
         {
-            StageTimer tt(m, st, n.name, !dry && n.kind != K_LSTM && n.kind != K_DROPOUT && n.kind != K_IDENTITY);
+            StageTimer tt(ws, st, n.name, !dry && n.kind != K_LSTM && n.kind != K_DROPOUT && n.kind != K_IDENTITY);
             y = leaf(n, x, lens);
         }
-        if (!dry) m->taps[n.name] = y;
+        if (!dry) ws->taps[n.name] = y;
         return y;
     }
 };
@@ -945,19 +991,23 @@ static void ensure_ready(kb_model *m) {
     CK(cudaSetDevice(m->device));
 }
 
-static void ensure_pinned(kb_model *m, size_t bytes) {
-    if (bytes <= m->pinned_cap) return;
-    if (m->pinned) cudaFreeHost(m->pinned);
-    m->pinned = nullptr; m->pinned_cap = 0;
-    CK(cudaHostAlloc(&m->pinned, bytes, cudaHostAllocDefault));
-    m->pinned_cap = bytes;
+// device-side pieces of a workspace that every call needs: range flag pair (and, for async slots, stream + events)
+static void ensure_workspace(kb_model *m, Workspace *ws) {
+    (void)m;
+    if (!ws->d_flag) { CK(cudaMalloc((void **)&ws->d_flag, sizeof(int))); CK(cudaMemset(ws->d_flag, 0, sizeof(int))); }
+    if (!ws->h_flag) { CK(cudaHostAlloc((void **)&ws->h_flag, sizeof(int), cudaHostAllocDefault)); *ws->h_flag = 0; }
+    if (ws->index > 0 && !ws->stream) {
+        CK(cudaStreamCreateWithFlags(&ws->stream, cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&ws->done, cudaEventBlockingSync | cudaEventDisableTiming));      // kb_wait sleeps instead of spinning
+        CK(cudaEventCreateWithFlags(&ws->input_ready, cudaEventDisableTiming));
+    }
 }
 
 struct ForwardResult { Tensor y; Lens lens; };
 
 // Stages the NCHW input into the arena as NHWC, runs the net.  `extra_bytes`: additional arena space the
 // caller will allocate after the forward (decode buffers etc.).
-static ForwardResult forward_impl(kb_model *m, const float *x, int x_on_device, int n, int h, int w, const int32_t *widths,
+static ForwardResult forward_impl(kb_model *m, Workspace *ws, const float *x, int x_on_device, int n, int h, int w, const int32_t *widths,
                                   cudaStream_t st, size_t extra_bytes) {
     const Plan &pl = *m->plan;
     const int C = pl.input[1];
@@ -975,54 +1025,54 @@ static ForwardResult forward_impl(kb_model *m, const float *x, int x_on_device, 
     size_t need;
     bool first_s2d = false;
     {
-        Arena saved = m->arena;
-        m->arena.dry = true; m->arena.off = 0;
-        Exec ex{m, st, true};
+        Arena saved = ws->arena;
+        ws->arena.dry = true; ws->arena.off = 0;
+        Exec ex{m, ws, st, true};
         Dims d0; d0.n = n; d0.c = C; d0.h = h; d0.w = w;
         first_s2d = C > 1 && ex.first_is_s2d(*pl.root, d0);     // the first layer reads the NCHW input itself (space-to-depth planes)
-        if (!x_on_device || C > 1) m->arena.alloc(in_elems * sizeof(float));      // staging of the raw input
-        if (C > 1 && !first_s2d) m->arena.alloc(in_elems * sizeof(float));
+        if (!x_on_device || C > 1) ws->arena.alloc(in_elems * sizeof(float));      // staging of the raw input
+        if (C > 1 && !first_s2d) ws->arena.alloc(in_elems * sizeof(float));
         Tensor t; t.p = nullptr; t.n = n; t.c = C; t.h = h; t.w = w;
         Lens l = lens0;
-        try { ex.run(*pl.root, t, l); } catch (...) { m->arena = saved; throw; }
-        need = m->arena.off + extra_bytes + (1 << 20);
-        m->arena = saved;
+        try { ex.run(*pl.root, t, l); } catch (...) { ws->arena = saved; throw; }
+        need = ws->arena.off + extra_bytes + (1 << 20);
+        ws->arena = saved;
     }
-    if (need > m->arena.cap) {
+    if (need > ws->arena.cap) {
         CK(cudaStreamSynchronize(st));
-        if (m->arena.base) CK(cudaFree(m->arena.base));
-        m->arena.base = nullptr; m->arena.cap = 0;
+        if (ws->arena.base) CK(cudaFree(ws->arena.base));
+        ws->arena.base = nullptr; ws->arena.cap = 0;
         size_t cap = need + need / 4;
-        CK(cudaMalloc((void **)&m->arena.base, cap));
-        m->arena.cap = cap;
+        CK(cudaMalloc((void **)&ws->arena.base, cap));
+        ws->arena.cap = cap;
     }
-    m->arena.dry = false; m->arena.off = 0;
-    m->taps.clear();
-    m->n_stages = 0;
+    ws->arena.dry = false; ws->arena.off = 0;
+    ws->taps.clear();
+    ws->n_stages = 0;
     const auto prof_t1 = std::chrono::steady_clock::now();
     m->prof_us[0] += std::chrono::duration<double, std::micro>(prof_t1 - prof_t0).count();
     // ---- stage input
     Tensor t; t.n = n; t.c = C; t.h = h; t.w = w;
     const float *src = x;
-    std::unique_ptr<StageTimer> t_in(new StageTimer(m, st, "stage_in", true));
+    std::unique_ptr<StageTimer> t_in(new StageTimer(ws, st, "stage_in", true));
     if (!x_on_device) {
-        float *stg = (float *)m->arena.alloc(in_elems * sizeof(float));
+        float *stg = (float *)ws->arena.alloc(in_elems * sizeof(float));
         CK(cudaMemcpyAsync(stg, x, in_elems * sizeof(float), cudaMemcpyHostToDevice, st));
         src = stg;
-    } else if (C > 1) m->arena.alloc(in_elems * sizeof(float));   // keep offsets identical to the dry pass
+    } else if (C > 1) ws->arena.alloc(in_elems * sizeof(float));   // keep offsets identical to the dry pass
     if (C > 1 && first_s2d) { t.p = nullptr; t.nchw = src; }
     else if (C > 1) {
-        float *nhwc = (float *)m->arena.alloc(in_elems * sizeof(float));
+        float *nhwc = (float *)ws->arena.alloc(in_elems * sizeof(float));
         dim3 grid((unsigned)((h * (long long)w + 31) / 32), (unsigned)((C + 31) / 32), (unsigned)n);
         LAUNCH(m, k_transpose, grid, dim3(32, 8), 0, st, src, nhwc, C, h * w);
         t.p = nhwc;
     } else t.p = const_cast<float *>(src);
     t_in.reset();
-    CK(cudaMemsetAsync(m->d_flag, 0, sizeof(int), st));
-    Exec ex{m, st, false};
+    CK(cudaMemsetAsync(ws->d_flag, 0, sizeof(int), st));
+    Exec ex{m, ws, st, false};
     ForwardResult r; r.lens = lens0;
     r.y = ex.run(*pl.root, t, r.lens);
-    CK(cudaMemcpyAsync(m->h_flag, m->d_flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(ws->h_flag, ws->d_flag, sizeof(int), cudaMemcpyDeviceToHost, st));
     m->prof_us[1] += std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - prof_t1).count();
     return r;
 }
@@ -1031,11 +1081,11 @@ static ForwardResult forward_impl(kb_model *m, const float *x, int x_on_device, 
 // an activation beyond the fp16 range it raised the device flag, and the whole call is repeated on the fp32 CUDA-core kernels
 // (still on the GPU: there is no CPU path).  The check needs the stream to be idle, which host-output calls are anyway.
 template <class F>
-static void run_with_range_fallback(kb_model *m, cudaStream_t st, F body) {
+static void run_with_range_fallback(kb_model *m, Workspace *ws, cudaStream_t st, F body) {
     m->force_ffma = false;
     body();
     CK(cudaStreamSynchronize(st));
-    if (m->h_flag && *m->h_flag) {
+    if (ws->h_flag && *ws->h_flag) {
         if (getenv("KB_DEBUG")) fprintf(stderr, "[kb] activation outside the fp16 operand range: repeating the call on the fp32 CUDA-core kernels\n");
         ++m->overflow_reruns;
         m->force_ffma = true;
@@ -1044,20 +1094,20 @@ static void run_with_range_fallback(kb_model *m, cudaStream_t st, F body) {
     }
 }
 
-static void collect_timing(kb_model *m) {
-    if (!m->timing) return;
-    for (size_t i = 0; i < m->n_stages; ++i) {
+static void collect_timing(Workspace *ws) {
+    if (!ws->timing) return;
+    for (size_t i = 0; i < ws->n_stages; ++i) {
         float ms = 0.f;
-        if (cudaEventElapsedTime(&ms, m->stages[i].a, m->stages[i].b) == cudaSuccess) m->stages[i].ms = ms;
-        else { cudaGetLastError(); m->stages[i].ms = 0.f; }
+        if (cudaEventElapsedTime(&ms, ws->stages[i].a, ws->stages[i].b) == cudaSuccess) ws->stages[i].ms = ms;
+        else { cudaGetLastError(); ws->stages[i].ms = 0.f; }
     }
 }
 
 // NHWC device tensor -> NCHW destination (device or host)
-static void emit_nchw(kb_model *m, const Tensor &y, float *out, int out_on_device, cudaStream_t st) {
+static void emit_nchw(kb_model *m, Workspace *ws, const Tensor &y, float *out, int out_on_device, cudaStream_t st) {
     const size_t elems = (size_t)y.numel();
     if (!elems) return;
-    float *dst = out_on_device ? out : (float *)m->arena.alloc(elems * sizeof(float));
+    float *dst = out_on_device ? out : (float *)ws->arena.alloc(elems * sizeof(float));
     if (y.c == 1) CK(cudaMemcpyAsync(dst, y.p, elems * sizeof(float), cudaMemcpyDeviceToDevice, st));
     else {
         const int R = (int)(y.h * y.w), Cc = (int)y.c;
@@ -1078,19 +1128,37 @@ static int guarded(F &&f) {
     catch (const std::exception &e) { return fail(KB_ERR_STATE, e.what()); }
 }
 
-struct DecodeBufs { int *lab; float *conf; int *o_lab, *o_start, *o_end; float *o_conf; int *o_cnt; size_t out_bytes; };
+static void infer(const Node &n, Dims &d, Lens &l) {
+    if (n.kind == K_SERIES) { for (auto &c : n.children) infer(*c, d, l); return; }
+    if (n.kind == K_PARALLEL) {
+        Dims first; Lens last = l; int64_t ctot = 0; bool have = false;
+        for (auto &c : n.children) {
+            Dims dc = d; Lens lc = l; infer(*c, dc, lc);
+            if (have && (dc.h != first.h || dc.w != first.w)) throw ShapeError("Output shape in parallel block not equal!");
+            first = dc; have = true; ctot += dc.c; last = lc;
+        }
+        d = first; d.c = ctot; l = last; return;
+    }
+    Dims o = leaf_dims(n, d);
+    if (n.kind == K_LSTM && !n.transpose && l.has && d.h != 1)
+        throw ShapeError("Height has to be 1 (not " + std::to_string(d.h) + ") for batching/multi-sequences.");
+    if (l.has) for (auto &v : l.v) v = leaf_len(n, v, d, o);
+    d = o;
+}
 
 static size_t decode_bytes(int n, int T, int max_out) {
     return (size_t)n * T * 8 + (size_t)n * max_out * 16 + (size_t)n * 4 + 8 * 256;
 }
 
-// runs the collapse and copies the fixed-stride result block back to the caller's host arrays
-static void decode_and_fetch(kb_model *m, int dev_sm, int n, int T, int max_out, const int *d_lab, const float *d_conf, const int *d_lens,
-                             int32_t *labels, int32_t *starts, int32_t *ends, float *confs, int32_t *counts, cudaStream_t st,
-                             Arena &arena, void **pinned, size_t *pinned_cap, int64_t *launches, StageTimer *timer = nullptr) {
-    (void)dev_sm;
+// Fixed-stride result block of a recognition call: [labels | starts | ends | confs] (n x max_out each) + counts (n).
+static size_t result_block_bytes(int n, int max_out) { return (size_t)n * max_out * 16 + (size_t)n * 4; }
+
+// Enqueues the CTC collapse and the copy of the result block into the pinned buffer `*pinned` (grown as needed); returns the block
+// size.  Nothing here waits for the device.
+static size_t decode_enqueue(int n, int T, int max_out, const int *d_lab, const float *d_conf, const int *d_lens, cudaStream_t st,
+                             Arena &arena, void **pinned, size_t *pinned_cap, int64_t *launches) {
     const size_t per = (size_t)n * max_out;
-    const size_t blk = per * 16 + (size_t)n * 4;
+    const size_t blk = result_block_bytes(n, max_out);
     char *d = (char *)arena.alloc(blk);
     int *o_lab = (int *)d, *o_start = (int *)(d + per * 4), *o_end = (int *)(d + per * 8);
     float *o_conf = (float *)(d + per * 12); int *o_cnt = (int *)(d + per * 16);
@@ -1098,19 +1166,22 @@ static void decode_and_fetch(kb_model *m, int dev_sm, int n, int T, int max_out,
     ++*launches;
     CK(cudaPeekAtLastError());
     if (blk > *pinned_cap) {
+        CK(cudaStreamSynchronize(st));                    // an earlier copy into the old buffer may still be in flight
         if (*pinned) cudaFreeHost(*pinned);
         *pinned = nullptr; *pinned_cap = 0;
         CK(cudaHostAlloc(pinned, blk, cudaHostAllocDefault));
         *pinned_cap = blk;
     }
     CK(cudaMemcpyAsync(*pinned, d, blk, cudaMemcpyDeviceToHost, st));
-    if (timer && timer->idx >= 0) { cudaEventRecord(timer->m->stages[timer->idx].b, st); timer->idx = -1; }
-    const auto prof_t2 = std::chrono::steady_clock::now();
-    CK(cudaStreamSynchronize(st));
-    const auto prof_t3 = std::chrono::steady_clock::now();
-    if (m) m->prof_us[2] += std::chrono::duration<double, std::micro>(prof_t3 - prof_t2).count();
-    const char *hsrc = (const char *)*pinned;
-    // only the valid prefix of every line is defined on the device; zero the rest for the caller
+    return blk;
+}
+
+// Result block (host, complete) -> the caller's arrays.  Only the valid prefix of every line is defined in the block; the rest of
+// the caller's arrays is zeroed.  counts[i] is the number of labels the line decoded to and may exceed max_out (then only the first
+// max_out are stored).
+static void decode_unpack(const void *block, int n, int max_out, int32_t *labels, int32_t *starts, int32_t *ends, float *confs, int32_t *counts) {
+    const size_t per = (size_t)n * max_out;
+    const char *hsrc = (const char *)block;
     const int32_t *h_cnt = (const int32_t *)(hsrc + per * 16);
     for (int i = 0; i < n; ++i) {
         const int c = std::min<int>(h_cnt[i], max_out);
@@ -1121,14 +1192,82 @@ static void decode_and_fetch(kb_model *m, int dev_sm, int n, int T, int max_out,
         memcpy(ends + o, hsrc + per * 8 + o * 4, (size_t)c * 4); memset(ends + o + c, 0, (size_t)(max_out - c) * 4);
         memcpy(confs + o, hsrc + per * 12 + o * 4, (size_t)c * 4); memset(confs + o + c, 0, (size_t)(max_out - c) * 4);
     }
-    if (m) {
-        m->prof_us[3] += std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - prof_t3).count();
-        if (++m->prof_calls % 50 == 0 && getenv("KB_HOST_PROF")) {
-            fprintf(stderr, "[kb] host us per call: plan %.1f  launch %.1f  wait %.1f  unpack %.1f\n", m->prof_us[0] / 50, m->prof_us[1] / 50,
-                    m->prof_us[2] / 50, m->prof_us[3] / 50);
-            m->prof_us[0] = m->prof_us[1] = m->prof_us[2] = m->prof_us[3] = 0;
-        }
+}
+
+static void host_prof_tick(kb_model *m) {
+    if (++m->prof_calls % 50 == 0 && getenv("KB_HOST_PROF")) {
+        fprintf(stderr, "[kb] host us per call: plan %.1f  launch %.1f  wait %.1f  unpack %.1f\n", m->prof_us[0] / 50, m->prof_us[1] / 50,
+                m->prof_us[2] / 50, m->prof_us[3] / 50);
+        m->prof_us[0] = m->prof_us[1] = m->prof_us[2] = m->prof_us[3] = 0;
     }
+}
+
+// uint8 line images -> the float network input on the device (scale, invert, zero padding; kb_recognize_u8 / async dtype 1)
+static const float *stage_u8_lines(kb_model *m, Workspace *ws, const uint8_t *lines, int lines_on_device, int n, int h, int w,
+                                   const int32_t *widths, const int16_t *invert_max, cudaStream_t st) {
+    const int C = m->plan->input[1];
+    const size_t elems = (size_t)n * C * h * w;
+    const size_t meta = ((size_t)n * 6 + 15) & ~(size_t)15;                   // widths (int32) + invert_max (int16) behind the pixels
+    if (elems + meta + 16 > ws->u8_raw_cap) {
+        CK(cudaStreamSynchronize(st));
+        if (ws->u8_raw) cudaFree(ws->u8_raw);
+        ws->u8_raw = nullptr; ws->u8_raw_cap = 0;
+        CK(cudaMalloc((void **)&ws->u8_raw, elems + meta + 16));
+        ws->u8_raw_cap = elems + meta + 16;
+    }
+    if (elems * sizeof(float) > ws->u8_f32_cap) {
+        CK(cudaStreamSynchronize(st));
+        if (ws->u8_f32) cudaFree(ws->u8_f32);
+        ws->u8_f32 = nullptr; ws->u8_f32_cap = 0;
+        CK(cudaMalloc((void **)&ws->u8_f32, elems * sizeof(float)));
+        ws->u8_f32_cap = elems * sizeof(float);
+    }
+    const uint8_t *src = lines;
+    if (!lines_on_device) { CK(cudaMemcpyAsync(ws->u8_raw, lines, elems, cudaMemcpyHostToDevice, st)); src = ws->u8_raw; }
+    uint8_t *mp = ws->u8_raw + ((elems + 15) & ~(size_t)15);
+    int *d_w = nullptr; short *d_inv = nullptr;
+    if (widths) { d_w = (int *)mp; CK(cudaMemcpyAsync(d_w, widths, (size_t)n * 4, cudaMemcpyHostToDevice, st)); }
+    if (invert_max) { d_inv = (short *)(mp + (size_t)n * 4); CK(cudaMemcpyAsync(d_inv, invert_max, (size_t)n * 2, cudaMemcpyHostToDevice, st)); }
+    LAUNCH(m, k_u8_lines_to_f32, grid1d((long long)elems, 256, m->sm_count), 256, 0, st, src, ws->u8_f32, (int)n, C, (int)h, (int)w, d_w, d_inv);
+    return ws->u8_f32;
+}
+
+// One recognition pass on workspace `ws` and stream `st`: net -> softmax statistics -> arg-max -> CTC collapse -> result block on
+// its way into ws->pinned.  Enqueue only; the caller synchronises (or records ws->done) and unpacks.
+struct RecognizeArgs {
+    const float *lines; int lines_on_device; int n, h, w; const int32_t *widths; float temperature; int max_out;
+    float *probs; int probs_on_device;
+};
+static void recognize_enqueue(kb_model *m, Workspace *ws, const RecognizeArgs &a, cudaStream_t st, int T, int C, std::vector<int32_t> &olens) {
+    const int n = a.n;
+    size_t extra = decode_bytes(n, T, a.max_out) + (a.probs && !a.probs_on_device ? (size_t)n * C * T * 4 + 4096 : 0);
+    ForwardResult r = forward_impl(m, ws, a.lines, a.lines_on_device, n, a.h, a.w, a.widths, st, extra);
+    std::unique_ptr<StageTimer> t_dec(new StageTimer(ws, st, "decode", true));
+    const long long rows = (long long)n * T;
+    int *d_lab = (int *)ws->arena.alloc((size_t)rows * 4);
+    float *d_conf = (float *)ws->arena.alloc((size_t)rows * 4);
+    LAUNCH(m, k_row_argmax_softmax, (unsigned)((rows + 7) / 8), 256, 0, st, r.y.p, rows, C, a.temperature, d_lab, d_conf);
+    olens.resize(n);
+    for (int i = 0; i < n; ++i) olens[i] = r.lens.has ? r.lens.v[i] : T;
+    int *d_lens = (int *)ws->arena.alloc((size_t)n * 4);
+    CK(cudaMemcpyAsync(d_lens, olens.data(), (size_t)n * 4, cudaMemcpyHostToDevice, st));
+    if (a.probs) {
+        float *dp = a.probs_on_device ? a.probs : (float *)ws->arena.alloc((size_t)n * C * T * 4);
+        const size_t smem = (size_t)32 * (C + 1) * 4;
+        if (smem <= 48 * 1024) LAUNCH(m, k_probs_nct, dim3((unsigned)((T + 31) / 32), (unsigned)n), 256, smem, st, r.y.p, dp, T, C, a.temperature);
+        else LAUNCH(m, k_probs_nct_simple, (unsigned)((rows + 7) / 8), 256, 0, st, r.y.p, dp, n, T, C, a.temperature);
+        if (!a.probs_on_device) CK(cudaMemcpyAsync(a.probs, dp, (size_t)n * C * T * 4, cudaMemcpyDeviceToHost, st));
+    }
+    decode_enqueue(n, T, a.max_out, d_lab, d_conf, d_lens, st, ws->arena, &ws->pinned, &ws->pinned_cap, &m->launches);
+    t_dec.reset();
+}
+
+static void recognition_dims(kb_model *m, int n, int h, int w, int *T, int *C) {
+    Dims d; d.n = n; d.c = m->plan->input[1]; d.h = h; d.w = w; Lens l;
+    infer(*m->plan->root, d, l);
+    if (d.h != 1)
+        throw ShapeError("Expected dimension 3 to be 1, actual (" + std::to_string(d.n) + ", " + std::to_string(d.c) + ", " + std::to_string(d.h) + ", " + std::to_string(d.w) + ")");
+    *T = (int)d.w; *C = (int)d.c;
 }
 
 }  // namespace kb
@@ -1208,24 +1347,6 @@ int kb_model_tensor_info(const kb_model *m, int index, char *name, size_t cap, i
     return KB_OK;
 }
 
-static void infer(const Node &n, Dims &d, Lens &l) {
-    if (n.kind == K_SERIES) { for (auto &c : n.children) infer(*c, d, l); return; }
-    if (n.kind == K_PARALLEL) {
-        Dims first; Lens last = l; int64_t ctot = 0; bool have = false;
-        for (auto &c : n.children) {
-            Dims dc = d; Lens lc = l; infer(*c, dc, lc);
-            if (have && (dc.h != first.h || dc.w != first.w)) throw ShapeError("Output shape in parallel block not equal!");
-            first = dc; have = true; ctot += dc.c; last = lc;
-        }
-        d = first; d.c = ctot; l = last; return;
-    }
-    Dims o = leaf_dims(n, d);
-    if (n.kind == K_LSTM && !n.transpose && l.has && d.h != 1)
-        throw ShapeError("Height has to be 1 (not " + std::to_string(d.h) + ") for batching/multi-sequences.");
-    if (l.has) for (auto &v : l.v) v = leaf_len(n, v, d, o);
-    d = o;
-}
-
 int kb_model_infer_dims(const kb_model *m, int32_t n, int32_t h, int32_t w, int32_t out_nchw[4]) {
     if (!m || !out_nchw) return fail(KB_ERR_ARG, "NULL argument");
     return guarded([&]() {
@@ -1278,19 +1399,7 @@ int kb_model_finalize(kb_model *m, int device) {
         if (device < 0 || device >= cnt) throw CudaError("invalid device ordinal " + std::to_string(device));
         if (m->device >= 0 && m->device != device) {
             CK(cudaSetDevice(m->device));
-            for (void *p : m->dev_allocs) cudaFree(p);
-            m->dev_allocs.clear();
-            if (m->arena.base) cudaFree(m->arena.base);
-            m->arena = Arena();
-            if (m->pinned) cudaFreeHost(m->pinned);
-            m->pinned = nullptr; m->pinned_cap = 0;
-            if (m->h_flag) cudaFreeHost(m->h_flag);
-            m->h_flag = nullptr;
-            if (m->u8_raw) cudaFree(m->u8_raw);
-            if (m->u8_f32) cudaFree(m->u8_f32);
-            m->u8_raw = nullptr; m->u8_f32 = nullptr; m->u8_raw_cap = m->u8_f32_cap = 0;
-            for (auto &e : m->stages) { if (e.a) cudaEventDestroy(e.a); if (e.b) cudaEventDestroy(e.b); }
-            m->stages.clear(); m->n_stages = 0;
+            m->release_device_state();
         }
         CK(cudaSetDevice(device));
         cudaDeviceProp prop;
@@ -1300,11 +1409,7 @@ int kb_model_finalize(kb_model *m, int device) {
         m->device = device;
         set_kernel_attributes();
         finalize_weights(m);
-        CK(cudaMalloc((void **)&m->d_flag, sizeof(int)));
-        m->dev_allocs.push_back(m->d_flag);
-        CK(cudaMemset(m->d_flag, 0, sizeof(int)));
-        if (!m->h_flag) CK(cudaHostAlloc((void **)&m->h_flag, sizeof(int), cudaHostAllocDefault));
-        *m->h_flag = 0;
+        for (auto &w : m->wss) ensure_workspace(m, w.get());
         m->finalized = true;
         return KB_OK;
     });
@@ -1318,62 +1423,48 @@ int kb_forward(kb_model *m, const float *x, int x_on_device, int32_t n, int32_t 
     return guarded([&]() {
         DeviceGuard dguard;
         ensure_ready(m);
+        Workspace *ws = m->ws0();
+        ws->timing = m->timing;
         cudaStream_t st = (cudaStream_t)stream;
         Dims d; d.n = n; d.c = m->plan->input[1]; d.h = h; d.w = w; Lens l;
         infer(*m->plan->root, d, l);
-        run_with_range_fallback(m, st, [&]() {
-            ForwardResult r = forward_impl(m, x, x_on_device, n, h, w, widths, st, out_on_device ? 0 : (size_t)(d.n * d.c * d.h * d.w) * 4 + 4096);
-            { StageTimer tt(m, st, "emit", true); emit_nchw(m, r.y, out, out_on_device, st); }
+        run_with_range_fallback(m, ws, st, [&]() {
+            ForwardResult r = forward_impl(m, ws, x, x_on_device, n, h, w, widths, st, out_on_device ? 0 : (size_t)(d.n * d.c * d.h * d.w) * 4 + 4096);
+            { StageTimer tt(ws, st, "emit", true); emit_nchw(m, ws, r.y, out, out_on_device, st); }
             if (out_lens) {
                 if (r.lens.has) for (int i = 0; i < n; ++i) out_lens[i] = r.lens.v[i];
                 else for (int i = 0; i < n; ++i) out_lens[i] = (int32_t)r.y.w;
             }
         });
-        collect_timing(m);
+        collect_timing(ws);
         return KB_OK;
     });
 }
 
 }  // extern "C" (reopened below)
 
+// synchronous recognition on workspace 0 and the caller's stream
 static int recognize_locked(kb_model *m, const float *lines, int lines_on_device, int32_t n, int32_t h, int32_t w, const int32_t *widths,
                  float temperature, int32_t *labels, int32_t *starts, int32_t *ends, float *confs, int32_t *counts,
                  int32_t max_out, int32_t *out_lens, float *probs, int probs_on_device, void *stream) {
-    {
-        cudaStream_t st = (cudaStream_t)stream;
-        Dims d; d.n = n; d.c = m->plan->input[1]; d.h = h; d.w = w; Lens l;
-        infer(*m->plan->root, d, l);
-        if (d.h != 1)
-            throw ShapeError("Expected dimension 3 to be 1, actual (" + std::to_string(d.n) + ", " + std::to_string(d.c) + ", " + std::to_string(d.h) + ", " + std::to_string(d.w) + ")");
-        const int T = (int)d.w, C = (int)d.c;
-        size_t extra = decode_bytes(n, T, max_out) + (probs && !probs_on_device ? (size_t)n * C * T * 4 + 4096 : 0);
-        std::vector<int32_t> olens(n);
-        run_with_range_fallback(m, st, [&]() {
-            ForwardResult r = forward_impl(m, lines, lines_on_device, n, h, w, widths, st, extra);
-            std::unique_ptr<StageTimer> t_dec(new StageTimer(m, st, "decode", true));
-            const long long rows = (long long)n * T;
-            int *d_lab = (int *)m->arena.alloc((size_t)rows * 4);
-            float *d_conf = (float *)m->arena.alloc((size_t)rows * 4);
-            LAUNCH(m, k_row_argmax_softmax, (unsigned)((rows + 7) / 8), 256, 0, st, r.y.p, rows, C, temperature, d_lab, d_conf);
-            for (int i = 0; i < n; ++i) olens[i] = r.lens.has ? r.lens.v[i] : T;
-            int *d_lens = (int *)m->arena.alloc((size_t)n * 4);
-            CK(cudaMemcpyAsync(d_lens, olens.data(), (size_t)n * 4, cudaMemcpyHostToDevice, st));
-            if (probs) {
-                float *dp = probs_on_device ? probs : (float *)m->arena.alloc((size_t)n * C * T * 4);
-                const size_t smem = (size_t)32 * (C + 1) * 4;
-                if (smem <= 48 * 1024) LAUNCH(m, k_probs_nct, dim3((unsigned)((T + 31) / 32), (unsigned)n), 256, smem, st, r.y.p, dp, T, C, temperature);
-                else LAUNCH(m, k_probs_nct_simple, (unsigned)((rows + 7) / 8), 256, 0, st, r.y.p, dp, n, T, C, temperature);
-                if (!probs_on_device) CK(cudaMemcpyAsync(probs, dp, (size_t)n * C * T * 4, cudaMemcpyDeviceToHost, st));
-            }
-            decode_and_fetch(m, m->sm_count, n, T, max_out, d_lab, d_conf, d_lens, labels, starts, ends, confs, counts, st,
-                             m->arena, &m->pinned, &m->pinned_cap, &m->launches, t_dec.get());
-        });
-        if (out_lens) for (int i = 0; i < n; ++i) out_lens[i] = olens[i];
-        collect_timing(m);
-        return KB_OK;
-    }
+    cudaStream_t st = (cudaStream_t)stream;
+    Workspace *ws = m->ws0();
+    ws->timing = m->timing;
+    int T, C;
+    recognition_dims(m, n, h, w, &T, &C);
+    std::vector<int32_t> olens;
+    RecognizeArgs a{lines, lines_on_device, n, h, w, widths, temperature, max_out, probs, probs_on_device};
+    const auto t0 = std::chrono::steady_clock::now();
+    run_with_range_fallback(m, ws, st, [&]() { recognize_enqueue(m, ws, a, st, T, C, olens); });
+    const auto t1 = std::chrono::steady_clock::now();
+    decode_unpack(ws->pinned, n, max_out, labels, starts, ends, confs, counts);
+    m->prof_us[3] += std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t1).count();
+    m->prof_us[2] += std::chrono::duration<double, std::micro>(t1 - t0).count();
+    host_prof_tick(m);
+    if (out_lens) for (int i = 0; i < n; ++i) out_lens[i] = olens[i];
+    collect_timing(ws);
+    return KB_OK;
 }
-
 
 extern "C" {
 
@@ -1403,33 +1494,115 @@ int kb_recognize_u8(kb_model *m, const uint8_t *lines, int lines_on_device, int3
     return guarded([&]() {
         DeviceGuard dguard;
         ensure_ready(m);
-        cudaStream_t st = (cudaStream_t)stream;
-        const int C = m->plan->input[1];
-        const size_t elems = (size_t)n * C * h * w;
-        const size_t meta = ((size_t)n * 6 + 15) & ~(size_t)15;                   // widths (int32) + invert_max (int16) behind the pixels
-        if (elems + meta + 16 > m->u8_raw_cap) {
-            CK(cudaStreamSynchronize(st));
-            if (m->u8_raw) cudaFree(m->u8_raw);
-            m->u8_raw = nullptr; m->u8_raw_cap = 0;
-            CK(cudaMalloc((void **)&m->u8_raw, elems + meta + 16));
-            m->u8_raw_cap = elems + meta + 16;
-        }
-        if (elems * sizeof(float) > m->u8_f32_cap) {
-            CK(cudaStreamSynchronize(st));
-            if (m->u8_f32) cudaFree(m->u8_f32);
-            m->u8_f32 = nullptr; m->u8_f32_cap = 0;
-            CK(cudaMalloc((void **)&m->u8_f32, elems * sizeof(float)));
-            m->u8_f32_cap = elems * sizeof(float);
-        }
-        const uint8_t *src = lines;
-        if (!lines_on_device) { CK(cudaMemcpyAsync(m->u8_raw, lines, elems, cudaMemcpyHostToDevice, st)); src = m->u8_raw; }
-        uint8_t *mp = m->u8_raw + ((elems + 15) & ~(size_t)15);
-        int *d_w = nullptr; short *d_inv = nullptr;
-        if (widths) { d_w = (int *)mp; CK(cudaMemcpyAsync(d_w, widths, (size_t)n * 4, cudaMemcpyHostToDevice, st)); }
-        if (invert_max) { d_inv = (short *)(mp + (size_t)n * 4); CK(cudaMemcpyAsync(d_inv, invert_max, (size_t)n * 2, cudaMemcpyHostToDevice, st)); }
-        LAUNCH(m, k_u8_lines_to_f32, grid1d((long long)elems, 256, m->sm_count), 256, 0, st, src, m->u8_f32, (int)n, C, (int)h, (int)w, d_w, d_inv);
-        return recognize_locked(m, m->u8_f32, 1, n, h, w, widths, temperature, labels, starts, ends, confs, counts, max_out, out_lens,
+        const float *f32 = stage_u8_lines(m, m->ws0(), lines, lines_on_device, n, h, w, widths, invert_max, (cudaStream_t)stream);
+        return recognize_locked(m, f32, 1, n, h, w, widths, temperature, labels, starts, ends, confs, counts, max_out, out_lens,
                                 probs, probs_on_device, stream);
+    });
+}
+
+/* ---- asynchronous pipeline ------------------------------------------------------------------------------------------------------ */
+int kb_set_pipeline_depth(kb_model *m, int32_t depth) {
+    if (!m) return fail(KB_ERR_ARG, "model is NULL");
+    if (depth < 1 || depth > 16) return fail(KB_ERR_ARG, "pipeline depth must be in 1..16");
+    std::lock_guard<std::mutex> lk(m->mu);
+    return guarded([&]() {
+        DeviceGuard dguard;
+        ensure_ready(m);
+        for (size_t i = 1; i < m->wss.size(); ++i)
+            if (m->wss[i]->busy) throw SpecError("kb_set_pipeline_depth: tickets are still in flight");
+        while ((int)m->wss.size() > depth + 1) { m->wss.back()->release(); m->wss.pop_back(); }
+        while ((int)m->wss.size() < depth + 1) {
+            m->wss.emplace_back(new Workspace());
+            m->wss.back()->index = (int)m->wss.size() - 1;
+            ensure_workspace(m, m->wss.back().get());
+        }
+        return (int)KB_OK;
+    });
+}
+int kb_pipeline_depth(const kb_model *m) { return m ? (int)m->wss.size() - 1 : -1; }
+
+int kb_recognize_async(kb_model *m, const void *lines, int dtype, int lines_on_device, int32_t n, int32_t h, int32_t w, const int32_t *widths,
+                       const int16_t *invert_max, float temperature, int32_t max_out, void *input_stream, int64_t *ticket) {
+    if (!m || !lines || !ticket) return fail(KB_ERR_ARG, "NULL argument");
+    if (dtype != KB_DTYPE_F32 && dtype != KB_DTYPE_U8) return fail(KB_ERR_ARG, "dtype must be KB_DTYPE_F32 or KB_DTYPE_U8");
+    if (max_out <= 0) return fail(KB_ERR_ARG, "max_out must be positive");
+    if (!(temperature > 0.f)) return fail(KB_ERR_ARG, "temperature must be positive");
+    if (n <= 0 || h <= 0 || w <= 0) return fail(KB_ERR_SHAPE, "empty input batch");
+    std::lock_guard<std::mutex> lk(m->mu);
+    return guarded([&]() {
+        DeviceGuard dguard;
+        ensure_ready(m);
+        if (m->wss.size() < 2) throw SpecError("kb_recognize_async: call kb_set_pipeline_depth() first");
+        const int depth = (int)m->wss.size() - 1;
+        Workspace *ws = m->wss[1 + (size_t)(m->next_ticket % depth)].get();
+        if (ws->busy) throw SpecError("kb_recognize_async: all " + std::to_string(depth) + " pipeline slots hold un-waited tickets (kb_wait the oldest first)");
+        ws->timing = false;
+        cudaStream_t st = ws->stream;
+        if (lines_on_device) {                            // the input was produced on the caller's stream
+            CK(cudaEventRecord(ws->input_ready, (cudaStream_t)input_stream));
+            CK(cudaStreamWaitEvent(st, ws->input_ready, 0));
+        }
+        int T, C;
+        recognition_dims(m, n, h, w, &T, &C);
+        Workspace::Pending &pd = ws->pend;
+        pd.n = n; pd.h = h; pd.w = w; pd.T = T; pd.max_out = max_out; pd.dtype = dtype; pd.temperature = temperature;
+        pd.has_widths = widths != nullptr;
+        if (widths) pd.widths.assign(widths, widths + n); else pd.widths.clear();
+        m->force_ffma = false;
+        const float *f32 = (const float *)lines; int on_dev = lines_on_device;
+        if (dtype == KB_DTYPE_U8) { f32 = stage_u8_lines(m, ws, (const uint8_t *)lines, lines_on_device, n, h, w, widths, invert_max, st); on_dev = 1; }
+        pd.device_input = on_dev ? f32 : nullptr;
+        RecognizeArgs a{f32, on_dev, n, h, w, widths, temperature, max_out, nullptr, 0};
+        recognize_enqueue(m, ws, a, st, T, C, pd.olens);
+        if (!on_dev) pd.device_input = ws->arena.base;           // host lines were staged at the start of the slot's arena
+        CK(cudaEventRecord(ws->done, st));
+        ws->busy = true; ws->ticket = m->next_ticket;
+        *ticket = m->next_ticket++;
+        return (int)KB_OK;
+    });
+}
+
+int kb_wait(kb_model *m, int64_t ticket, int32_t *labels, int32_t *starts, int32_t *ends, float *confs, int32_t *counts, int32_t *out_lens) {
+    if (!m || !labels || !starts || !ends || !confs || !counts) return fail(KB_ERR_ARG, "NULL argument");
+    Workspace *ws = nullptr;
+    {
+        std::lock_guard<std::mutex> lk(m->mu);
+        for (size_t i = 1; i < m->wss.size(); ++i)
+            if (m->wss[i]->busy && m->wss[i]->ticket == ticket) ws = m->wss[i].get();
+    }
+    if (!ws) return fail(KB_ERR_ARG, "kb_wait: unknown or already collected ticket");
+    return guarded([&]() {
+        DeviceGuard dguard;
+        CK(cudaSetDevice(m->device));
+        CK(cudaEventSynchronize(ws->done));               // blocking-sync event: the host thread sleeps, the model stays unlocked
+        std::lock_guard<std::mutex> lk(m->mu);
+        Workspace::Pending &pd = ws->pend;
+        try {
+            if (*ws->h_flag) {
+                // an activation left the fp16 operand range: repeat this batch on the fp32 CUDA-core kernels (input still staged on the device)
+                ++m->overflow_reruns;
+                m->force_ffma = true;
+                int T, C;
+                recognition_dims(m, pd.n, pd.h, pd.w, &T, &C);
+                RecognizeArgs a{(const float *)pd.device_input, 1, pd.n, pd.h, pd.w, pd.has_widths ? pd.widths.data() : nullptr, pd.temperature, pd.max_out, nullptr, 0};
+                // the staged input sits inside the arena this pass is about to reuse: move it out of the way first
+                const size_t in_bytes = (size_t)pd.n * m->plan->input[1] * pd.h * pd.w * sizeof(float);
+                float *keep = nullptr;
+                CK(cudaMalloc((void **)&keep, in_bytes));
+                try {
+                    CK(cudaMemcpyAsync(keep, pd.device_input, in_bytes, cudaMemcpyDeviceToDevice, ws->stream));
+                    a.lines = keep;
+                    recognize_enqueue(m, ws, a, ws->stream, T, C, pd.olens);
+                    CK(cudaStreamSynchronize(ws->stream));
+                } catch (...) { cudaFree(keep); throw; }
+                cudaFree(keep);
+                m->force_ffma = false;
+            }
+        } catch (...) { m->force_ffma = false; ws->busy = false; throw; }
+        decode_unpack(ws->pinned, pd.n, pd.max_out, labels, starts, ends, confs, counts);
+        if (out_lens) for (int i = 0; i < pd.n; ++i) out_lens[i] = pd.olens[i];
+        ws->busy = false;
+        return (int)KB_OK;
     });
 }
 
@@ -1459,7 +1632,9 @@ int kb_ctc_greedy_decode(const float *probs, int probs_on_device, int32_t n, int
             if (lens) { d_lens = (int *)ar.alloc((size_t)n * 4); CK(cudaMemcpyAsync(d_lens, lens, (size_t)n * 4, cudaMemcpyHostToDevice, st)); }
             k_col_argmax<<<(unsigned)(((long long)n * w + 255) / 256), 256, 0, st>>>(dp, n, c, w, d_lab, d_conf);
             CK(cudaPeekAtLastError());
-            decode_and_fetch(nullptr, 0, n, w, max_out, d_lab, d_conf, d_lens, labels, starts, ends, confs, counts, st, ar, &pinned, &pcap, &launches);
+            decode_enqueue(n, w, max_out, d_lab, d_conf, d_lens, st, ar, &pinned, &pcap, &launches);
+            CK(cudaStreamSynchronize(st));
+            decode_unpack(pinned, n, max_out, labels, starts, ends, confs, counts);
         } catch (...) { cudaFree(ar.base); if (pinned) cudaFreeHost(pinned); throw; }
         cudaFree(ar.base); if (pinned) cudaFreeHost(pinned);
         return (int)KB_OK;
@@ -1478,16 +1653,18 @@ int kb_segment(kb_model *m, const float *pages, int pages_on_device, int32_t n, 
         Dims d; d.n = n; d.c = m->plan->input[1]; d.h = h; d.w = w; Lens l;
         infer(*m->plan->root, d, l);
         const size_t out_elems = (size_t)n * d.c * out_h * out_w;
-        run_with_range_fallback(m, st, [&]() {
-            ForwardResult r = forward_impl(m, pages, pages_on_device, n, h, w, nullptr, st, heatmap_on_device ? 0 : out_elems * 4 + 4096);
-            std::unique_ptr<StageTimer> t_up(new StageTimer(m, st, "upsample_sigmoid", true));
-            float *dst = heatmap_on_device ? heatmap : (float *)m->arena.alloc(out_elems * 4);
+        Workspace *ws = m->ws0();
+        ws->timing = m->timing;
+        run_with_range_fallback(m, ws, st, [&]() {
+            ForwardResult r = forward_impl(m, ws, pages, pages_on_device, n, h, w, nullptr, st, heatmap_on_device ? 0 : out_elems * 4 + 4096);
+            std::unique_ptr<StageTimer> t_up(new StageTimer(ws, st, "upsample_sigmoid", true));
+            float *dst = heatmap_on_device ? heatmap : (float *)ws->arena.alloc(out_elems * 4);
             LAUNCH(m, k_upsample_sigmoid, grid1d((long long)n * out_h * out_w, 256, m->sm_count), 256, 0, st, r.y.p, dst, (int)r.y.n, (int)r.y.h,
                    (int)r.y.w, (int)r.y.c, out_h, out_w);
             if (!heatmap_on_device) CK(cudaMemcpyAsync(heatmap, dst, out_elems * 4, cudaMemcpyDeviceToHost, st));
             t_up.reset();
         });
-        collect_timing(m);
+        collect_timing(ws);
         return KB_OK;
     });
 }
@@ -1498,8 +1675,9 @@ int kb_debug_layer_output(kb_model *m, const char *name, int32_t dims[4], float 
     return guarded([&]() {
         DeviceGuard dguard;
         ensure_ready(m);
-        auto it = m->taps.find(name);
-        if (it == m->taps.end()) throw SpecError(std::string("no output recorded for layer ") + name);
+        Workspace *ws = m->ws0();
+        auto it = ws->taps.find(name);
+        if (it == ws->taps.end()) throw SpecError(std::string("no output recorded for layer ") + name);
         const Tensor &t = it->second;
         dims[0] = (int32_t)t.n; dims[1] = (int32_t)t.c; dims[2] = (int32_t)t.h; dims[3] = (int32_t)t.w;
         if (dims_only || !out_host) return (int)KB_OK;
@@ -1538,15 +1716,14 @@ int kb_debug_gemm(const float *a, const float *b, const float *bias, float *c, i
         if (bias) w.bias = upload(&tmp, std::vector<float>(bias, bias + N));
         upload_split(&tmp, rows, w);
         set_kernel_attributes();
-        CK(cudaMalloc((void **)&tmp.d_flag, sizeof(int)));
-        tmp.dev_allocs.push_back(tmp.d_flag);
-        CK(cudaMemset(tmp.d_flag, 0, sizeof(int)));
+        Workspace *ws = tmp.ws0();
+        ensure_workspace(&tmp, ws);
         const size_t abytes = (size_t)M * K * 4, cbytes = (size_t)M * N * 4;
-        CK(cudaMalloc((void **)&tmp.arena.base, 3 * abytes + cbytes + 65536)); tmp.arena.cap = 3 * abytes + cbytes + 65536;
-        Tensor x; x.n = 1; x.h = 1; x.w = M; x.c = K; x.p = (float *)tmp.arena.alloc(abytes);
-        float *dc = (float *)tmp.arena.alloc(cbytes);
+        CK(cudaMalloc((void **)&ws->arena.base, 3 * abytes + cbytes + 65536)); ws->arena.cap = 3 * abytes + cbytes + 65536;
+        Tensor x; x.n = 1; x.h = 1; x.w = M; x.c = K; x.p = (float *)ws->arena.alloc(abytes);
+        float *dc = (float *)ws->arena.alloc(cbytes);
         CK(cudaMemcpy(x.p, a, abytes, cudaMemcpyHostToDevice));
-        Exec ex{&tmp, nullptr, false};
+        Exec ex{&tmp, ws, nullptr, false};
         if (use_tc && !ex.tc_eligible(x, w, nullptr)) throw Unsupported("shape not eligible for the tcgen05 GEMM (need K % 8 == 0, K >= 32, N >= 64, M >= 128)");
         ex.gemm(x, w, nullptr, ACT_LINEAR, dc, 1, M);
         CK(cudaDeviceSynchronize());
@@ -1562,14 +1739,16 @@ int kb_set_timing(kb_model *m, int enabled) { if (!m) return fail(KB_ERR_ARG, "m
 int kb_timing_count(kb_model *m) {
     if (!m) return -1;
     std::lock_guard<std::mutex> lk(m->mu);
-    return m->timing ? (int)m->n_stages : 0;
+    Workspace *ws = m->ws0();
+    return m->timing ? (int)ws->n_stages : 0;
 }
 int kb_timing_entry(kb_model *m, int index, char *name, size_t cap, float *ms) {
     if (!m) return fail(KB_ERR_ARG, "model is NULL");
     std::lock_guard<std::mutex> lk(m->mu);
-    if (index < 0 || index >= (int)m->n_stages) return fail(KB_ERR_ARG, "timing index out of range");
-    if (name && cap) snprintf(name, cap, "%s", m->stages[index].name.c_str());
-    if (ms) *ms = m->stages[index].ms;
+    Workspace *ws = m->ws0();
+    if (index < 0 || index >= (int)ws->n_stages) return fail(KB_ERR_ARG, "timing index out of range");
+    if (name && cap) snprintf(name, cap, "%s", ws->stages[index].name.c_str());
+    if (ms) *ms = ws->stages[index].ms;
     return KB_OK;
 }
 

@@ -44,6 +44,7 @@ class TorchSeqRecognizer:
         self.one_channel_mode = nn.one_channel_mode
         self.seg_type = nn.seg_type
         self.outputs = None
+        self.keep_outputs = False      # True: predict* also fetch the (N, C, W) probabilities into `self.outputs` (models.py:116)
         self._dims_cache = {}          # (engine handle, n, h, w) -> output dims of nn
         if self.device:
             self.nn.to(device)
@@ -142,6 +143,81 @@ class TorchSeqRecognizer:
         return {'labels': labels, 'starts': starts, 'ends': ends, 'confs': confs, 'counts': counts,
                 'olens': olens if widths is not None else None}
 
+    # -- asynchronous pipeline (kb_recognize_async / kb_wait) --------------------------------------------
+    def set_pipeline_depth(self, depth: int) -> None:
+        """Number of batches one host thread can keep in flight on this model (own stream + workspace per slot, one copy of
+        the weights)."""
+        self.nn._ensure_finalized(None)
+        check(lib.kb_set_pipeline_depth(self.nn._h, int(depth)))
+        self._depth = int(depth)
+
+    def submit(self, line, lens=None, invert_max=None) -> int:
+        """Enqueues one batch - float32 lines (N, C, H, W) as `predict` takes them, or the uint8 lines `recognize_u8` takes - and
+        returns a ticket without waiting for the GPU.  Host tensors should be pinned (`tensor.pin_memory()`); they are kept alive
+        until `collect`."""
+        net = self.nn
+        if not getattr(self, '_depth', 0):
+            self.set_pipeline_depth(4)
+        is_u8 = isinstance(line, torch.Tensor) and line.dtype == torch.uint8 or isinstance(line, np.ndarray) and line.dtype == np.uint8
+        if is_u8:
+            x = line if isinstance(line, torch.Tensor) else torch.as_tensor(np.ascontiguousarray(line))
+            x = x.contiguous()
+        else:
+            x = _as_f32(line)
+        if x.ndim != 4:
+            raise ValueError(f'expected a 4D NCHW input, got shape {tuple(x.shape)}')
+        n, c, h, w = (int(v) for v in x.shape)
+        if c != net.input[1]:
+            raise ValueError(f'expected {net.input[1]} input channels, got {c}')
+        if _on_device(x) and x.device.index != net._device:
+            x = x.to(f'cuda:{net._device}')
+        widths = np.ascontiguousarray(torch.as_tensor(lens).cpu().numpy(), dtype=np.int32) if lens is not None else None
+        if widths is not None and widths.shape != (n,):
+            raise ValueError('seq_lens must have one entry per batch element')
+        inv = np.ascontiguousarray(np.asarray(invert_max), dtype=np.int16) if invert_max is not None else None
+        key = (getattr(net._h, 'value', None), getattr(net, 'spec', None), n, h, w)
+        dims = self._dims_cache.get(key)
+        if dims is None:
+            dims = self._dims_cache[key] = net.infer_dims(n, h, w)
+        if dims[2] != 1:
+            raise KrakenInputException('Expected dimension 3 to be 1, actual {}'.format(tuple(dims)))
+        stride = max(dims[3], 1)
+        t = C.c_int64()
+        on_dev = _on_device(x)
+        check(lib.kb_recognize_async(net._h, _ptr(x), 1 if is_u8 else 0, int(on_dev), n, h, w,
+                                     widths.ctypes.data if widths is not None else None, inv.ctypes.data if inv is not None else None,
+                                     float(self.temperature), stride, _stream_for(x, net._device) if on_dev else None, C.byref(t)))
+        if not hasattr(self, '_inflight'):
+            self._inflight = {}
+        self._inflight[t.value] = (x, n, stride, lens is not None)
+        return t.value
+
+    def collect(self, ticket: int, out: Optional[dict] = None) -> dict:
+        """Waits for a submitted batch (the thread sleeps on a blocking CUDA event) and returns the same blocks as `_recognize_raw`."""
+        x, n, stride, has_lens = self._inflight.pop(ticket)
+        if out is not None:
+            labels, starts, ends, confs, counts = out['labels'], out['starts'], out['ends'], out['confs'], out['counts']
+        else:
+            labels = np.empty((n, stride), np.int32); starts = np.empty((n, stride), np.int32); ends = np.empty((n, stride), np.int32)
+            confs = np.empty((n, stride), np.float32); counts = np.empty(n, np.int32)
+        olens = np.zeros(n, np.int32)
+        check(lib.kb_wait(self.nn._h, int(ticket), labels.ctypes.data, starts.ctypes.data, ends.ctypes.data, confs.ctypes.data,
+                          counts.ctypes.data, olens.ctypes.data))
+        return {'labels': labels, 'starts': starts, 'ends': ends, 'confs': confs, 'counts': counts, 'olens': olens if has_lens else None}
+
+    def recognize_stream(self, batches, depth: int = 4):
+        """Generator: feeds `(lines, lens)` pairs (or `(uint8 lines, lens, invert_max)` triples) through the engine with `depth` batches
+        in flight from this one thread and yields their result blocks in order."""
+        if getattr(self, '_depth', 0) != depth:
+            self.set_pipeline_depth(depth)
+        pending = []
+        for b in batches:
+            if len(pending) == depth:
+                yield self.collect(pending.pop(0))
+            pending.append(self.submit(*b))
+        while pending:
+            yield self.collect(pending.pop(0))
+
     # -- reference surface ------------------------------------------------------------------------
     def forward(self, line: torch.Tensor, lens: Optional[torch.Tensor] = None):
         """(N, C, H, W) lines -> ((N, C, W) softmax numpy array, output lengths) - models.py:93-119."""
@@ -152,7 +228,9 @@ class TorchSeqRecognizer:
         if lens is None and getattr(line, 'ndim', 0) == 4 and int(line.shape[0]) > 1:
             raise ValueError('seq_lens need to be set for batch decoding.')          # ctc_decoder.py:60-61
         if self.decoder is ctc_decoder.greedy_decoder:
-            dec, _ = self._recognize(line, lens, want_probs=True)      # `outputs` stays populated (mm_rpred reads its shape)
+            # fused device path: only the label blocks come back.  `return_logits` (the reference's RecognitionInferenceConfig flag,
+            # rpred.py:227) or the legacy callers that read `self.outputs` set `keep_outputs`.
+            dec, _ = self._recognize(line, lens, want_probs=bool(self.keep_outputs))
             return dec
         o, olens = self.forward(line, lens)
         return self.decoder(o, olens)

@@ -176,8 +176,12 @@ def test_cfg5_batch_of_1200_wide_lines():
 
 @pytest.mark.parametrize('w', [800, 1200, 2000])
 def test_cfg2_label_exactness_over_seeds(w):
-    """8 seeds x 64 lines at T = 200 / 300 / 500: the approximate SFU gates and the split-fp16 operands never flip an arg-max."""
-    flips = 0
+    """8 seeds x 64 lines at T = 200 / 300 / 500: the approximate SFU gates and the split-fp16 operands never flip an arg-max that the
+    reference decides by more than its own rounding noise.  Random-init models produce near-uniform logits; over 1536 lines the
+    smallest top-2 gap of the fp32 reference is ONE ulp (1.2e-7), where the reference's own arg-max depends on the summation order of
+    its BLAS.  Such time steps (gap <= 1e-5 relative, 5x the engine's measured logit error and 100x below the 1e-3 contract) may go
+    either way; every other time step, and every line without such a step, must match bit for bit."""
+    real_flips, tie_steps, tie_lines, lines_cmp = 0, 0, 0, 0
     min_gap = 1e9
     for seed in range(100, 108):
         om = vo.OracleModel(CFG2)
@@ -186,12 +190,31 @@ def test_cfg2_label_exactness_over_seeds(w):
         x = torch.rand(64, 1, 48, w, generator=g)
         lens = torch.full((64,), w, dtype=torch.long)
         ref_logits, _, _, ref_dec = vo.rec_predict(om, x, lens)
-        top2 = ref_logits.squeeze(2).topk(2, dim=1).values
-        min_gap = min(min_gap, float((top2[:, 0] - top2[:, 1]).min()))
+        rl = ref_logits.squeeze(2)                                   # (N, C, T)
+        top2 = rl.topk(2, dim=1).values
+        gap = top2[:, 0] - top2[:, 1]                                # (N, T)
+        min_gap = min(min_gap, float(gap.min()))
+        tol = 1e-5 * float(rl.abs().max())
         m = kb.TorchVGSLModel(vgsl=CFG2)
         m.load_state_dict(wts)
         rec = kb.TorchSeqRecognizer(m, device='cuda:0')
-        dec = rec.predict_labels(x.cuda(), lens)
-        flips += sum(a != b for a, b in zip(triples(dec), triples(ref_dec)))
-    print(f'[seeds] W={w}: smallest top-2 logit gap {min_gap:.3e}; lines with a differing label sequence: {flips}/512')
-    assert flips == 0
+        logits, _ = m.nn(x.cuda(), lens)
+        gl = logits.squeeze(2).cpu()
+        assert rel_err(gl, rl) <= REL_TOL
+        differ = gl.argmax(1) != rl.argmax(1)                        # (N, T)
+        real_flips += int((differ & (gap > tol)).sum())
+        tie_steps += int((differ & (gap <= tol)).sum())
+        dec = triples(rec.predict_labels(x.cuda(), lens))
+        ref = triples(ref_dec)
+        own = triples(vo.greedy_decode(gl.softmax(1), torch.full((64,), gl.shape[-1])))
+        for i in range(64):
+            if bool(differ[i].any()):
+                tie_lines += 1
+                assert dec[i] == own[i]                               # the decoder is consistent with the engine's own logits
+            else:
+                lines_cmp += 1
+                assert dec[i] == ref[i], (seed, i)
+    print(f'[seeds] W={w}: smallest top-2 logit gap of the reference {min_gap:.3e}; lines identical to the reference {lines_cmp}/512; '
+          f'time steps decided differently at a near-tie {tie_steps} (in {tie_lines} lines); beyond the tie tolerance {real_flips}')
+    assert real_flips == 0
+    assert tie_lines <= 2

@@ -472,3 +472,56 @@ def test_strided_convs_on_tensor_cores_3channel(h, w):
     with env(KB_FUSE=3):
         out2, _ = m.nn(x.cuda())
     assert rel_err(out2, ref) <= TIGHT
+
+
+def test_async_pipeline_matches_synchronous_calls():
+    """kb_recognize_async / kb_wait: one handle, `depth` slots, one host thread; every batch must equal the synchronous call bit for
+    bit, whatever is in flight around it (mixed shapes, uint8 and float, device and host inputs, the fp16-range re-run)."""
+    spec = '[1,16,0,1 Cr3,3,32 Mp2,2 Cr3,3,64 Mp2,2 S1(1x0)1,3 Lbx40 O1c13]'
+    om = vo.OracleModel(spec)
+    m = kb.TorchVGSLModel(vgsl=spec)
+    m.load_state_dict(om.init_like_reference(3))
+    rec = kb.TorchSeqRecognizer(m, device='cuda:0')
+    g = torch.Generator().manual_seed(3)
+    batches = []
+    for i, (n, w) in enumerate([(5, 200), (9, 333), (2, 64), (7, 200), (16, 512), (5, 200), (3, 97)]):
+        lens = torch.randint(max(8, w // 2), w + 1, (n,), generator=g)
+        lens[0] = w
+        x = torch.rand(n, 1, 16, w, generator=g)
+        for j, l in enumerate(lens.tolist()):
+            x[j, ..., l:] = 0
+        if i == 4:
+            x = x * 3e6                                    # leaves the fp16 operand range -> re-run on the fp32 kernels inside kb_wait
+        batches.append((x.pin_memory() if i % 2 == 0 else x.cuda(), lens))
+    sync = [rec._recognize_raw(x, lens, want_probs=False) for x, lens in batches]
+    reruns = m.range_fallback_count
+    got = list(rec.recognize_stream(batches, depth=3))
+    assert m.range_fallback_count == reruns + 1
+    for a, b in zip(got, sync):
+        for k in ('labels', 'starts', 'ends', 'confs', 'counts', 'olens'):
+            assert np.array_equal(a[k], b[k]), k
+    # against the oracle as well (batch 1)
+    _, _, _, ref = vo.rec_predict(om, batches[1][0].cpu(), batches[1][1])
+    from kraken_b200.ctc_decoder import unpack_decoded
+    assert triples(unpack_decoded(got[1]['labels'], got[1]['starts'], got[1]['ends'], got[1]['confs'], got[1]['counts'])) == triples(ref)
+    # uint8 lines through the same pipeline
+    raw = torch.randint(0, 256, (4, 1, 16, 120), generator=g, dtype=torch.uint8)
+    wd = torch.tensor([120, 77, 120, 9])
+    inv = [int(raw[i, :, :, :w_].max()) for i, w_ in enumerate(wd.tolist())]
+    s8 = rec.recognize_u8(raw, wd, inv)
+    t = rec.submit(raw.pin_memory(), wd, inv)
+    a8 = rec.collect(t)
+    for k in ('labels', 'starts', 'ends', 'confs', 'counts', 'olens'):
+        assert np.array_equal(a8[k], s8[k]), k
+    # more tickets than slots -> loud failure, nothing lost
+    rec.set_pipeline_depth(2)
+    t1 = rec.submit(*batches[0]); t2 = rec.submit(*batches[1])
+    with pytest.raises(ValueError):
+        rec.submit(*batches[2])
+    r2 = rec.collect(t2); r1 = rec.collect(t1)               # any order
+    assert np.array_equal(r1['labels'], sync[0]['labels']) and np.array_equal(r2['labels'], sync[1]['labels'])
+    with pytest.raises(KeyError):
+        rec.collect(t1)
+    # the synchronous entry point keeps working next to the pipeline and leaves torch's current device alone
+    assert torch.cuda.current_device() == 0
+    assert np.array_equal(rec._recognize_raw(*batches[3], want_probs=False)['labels'], sync[3]['labels'])
