@@ -232,8 +232,9 @@ static void upload_split(kb_model *m, const std::vector<float> &rows, LeafWeight
 // opt-in dynamic shared memory sizes of the tensor-core kernels; function attributes are per device, so this runs at every
 // kb_model_finalize (after cudaSetDevice) instead of behind process-wide "already done" flags
 static void set_kernel_attributes() {
-    CK(cudaFuncSetAttribute(tc::k_gemm_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
-    CK(cudaFuncSetAttribute(tc::k_gemm_tc<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
+    CK(cudaFuncSetAttribute(tc::k_gemm_tc<128, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::GemmCfg<128>::SMEM_BYTES));
+    CK(cudaFuncSetAttribute(tc::k_gemm_tc<256, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::GemmCfg<256>::SMEM_BYTES));
+    CK(cudaFuncSetAttribute(tc::k_gemm_tc<256, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::GemmCfg<256>::SMEM_BYTES));
     CK(cudaFuncSetAttribute(ctc::k_conv_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     CK(cudaFuncSetAttribute(ltc::k_lstm_rec_tc<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, ltc::ClusterCfg<8>::SMEM_BYTES));
     CK(cudaFuncSetAttribute(ltc::k_lstm_rec_tc<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, ltc::ClusterCfg<16>::SMEM_BYTES));
@@ -436,7 +437,13 @@ struct Exec {
         const long long M = (long long)x.n * x.h * x.w;
         return (w.K % 8) == 0 && w.K >= 32 && w.ncols >= 64 && M >= 128;        // K % 8: 16-byte row pitch of the fp16 planes (TMA)
     }
-    void gemm_tc(const Tensor &x, const LeafWeights &w, int act, float *y) {
+    // recognition head: when set (kb_recognize without a probability request), the network's final Linear runs with the arg-max
+    // epilogue of k_gemm_tc<256, 1> and emits per-row labels / confidences instead of logits
+    struct ArgmaxOut { float temperature = 1.f; int *lab = nullptr; float *conf = nullptr; bool done = false; };
+    ArgmaxOut *amx = nullptr;
+    const Node *final_leaf = nullptr;
+
+    void gemm_tc(const Tensor &x, const LeafWeights &w, int act, float *y, ArgmaxOut *am = nullptr) {
         const long long M = (long long)x.n * x.h * x.w;
         const int K = w.K, N = w.ncols;
         __half *a_hi = x.hi, *a_lo = x.lo;
@@ -448,28 +455,17 @@ struct Exec {
         if (!x.hi) LAUNCH(m, tc::k_split_f16, grid1d(M * K / 4, 256, m->sm_count), 256, 0, st, x.p, a_hi, a_lo, M * K / 4, ws->d_flag);
         CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
         if (!tc::make_map_2d(&ta_hi, a_hi, (uint64_t)M, (uint64_t)K, tc::BM, tc::BK) || !tc::make_map_2d(&ta_lo, a_lo, (uint64_t)M, (uint64_t)K, tc::BM, tc::BK) ||
-            !tc::make_map_2d(&tb_hi, w.b_hi, (uint64_t)N, (uint64_t)K, tc::BN / 2, tc::BK) || !tc::make_map_2d(&tb_lo, w.b_lo, (uint64_t)N, (uint64_t)K, tc::BN / 2, tc::BK))
+            !tc::make_map_2d(&tb_hi, w.b_hi, (uint64_t)N, (uint64_t)K, 128, tc::BK) || !tc::make_map_2d(&tb_lo, w.b_lo, (uint64_t)N, (uint64_t)K, 128, tc::BK))
             throw CudaError("cuTensorMapEncodeTiled failed");
         tc::GemmTcParams gp; gp.c = y; gp.bias = w.bias; gp.M = (int)M; gp.N = N; gp.K = K; gp.ldc = N; gp.act = act;
-        const int tiles_m = (int)((M + tc::BM - 1) / tc::BM), tiles_n = (N + tc::BN - 1) / tc::BN;
-        // KB_GEMM_MC=1: pairs of vertically adjacent tiles on 2-CTA clusters with the weight tile multicast (no gain measured)
-        const bool mc = tiles_m >= 2 && getenv("KB_GEMM_MC") && atoi(getenv("KB_GEMM_MC")) == 1;
-        if (mc) {
-            const int npairs = ((tiles_m + 1) / 2) * tiles_n;
-            cudaLaunchConfig_t cfg = {};
-            cfg.gridDim = dim3((unsigned)(2 * std::min(npairs, std::max(1, m->sm_count / 2))), 1, 1);
-            cfg.blockDim = dim3(tc::THREADS, 1, 1);
-            cfg.dynamicSmemBytes = tc::SMEM_BYTES; cfg.stream = st;
-            cudaLaunchAttribute at[1];
-            at[0].id = cudaLaunchAttributeClusterDimension;
-            at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-            cfg.attrs = at; cfg.numAttrs = 1;
-            CK(cudaLaunchKernelEx(&cfg, tc::k_gemm_tc<2>, ta_hi, ta_lo, tb_hi, tb_lo, gp));
-            ++m->launches;
-            CK(cudaPeekAtLastError());
-        } else {
-            LAUNCH(m, tc::k_gemm_tc<1>, (unsigned)std::min(tiles_m * tiles_n, m->sm_count), tc::THREADS, tc::SMEM_BYTES, st, ta_hi, ta_lo, tb_hi, tb_lo, gp);
-        }
+        gp.lab = am ? am->lab : nullptr; gp.conf = am ? am->conf : nullptr; gp.temperature = am ? am->temperature : 1.f;
+        const int tiles_m = (int)((M + tc::BM - 1) / tc::BM);
+        // 128 < N <= 256: one 256-wide tile per row block (whole rows in one tile); everything else on 128-wide tiles with two
+        // accumulator sets (epilogue under the next tile's MMAs)
+        const bool wide = am || (N > 128 && N <= 256);
+        if (am) LAUNCH(m, (tc::k_gemm_tc<256, 1>), (unsigned)std::min(tiles_m, m->sm_count), tc::THREADS, tc::GemmCfg<256>::SMEM_BYTES, st, ta_hi, ta_lo, tb_hi, tb_lo, gp);
+        else if (wide) LAUNCH(m, (tc::k_gemm_tc<256, 0>), (unsigned)std::min(tiles_m, m->sm_count), tc::THREADS, tc::GemmCfg<256>::SMEM_BYTES, st, ta_hi, ta_lo, tb_hi, tb_lo, gp);
+        else LAUNCH(m, (tc::k_gemm_tc<128, 0>), (unsigned)std::min(tiles_m * ((N + 127) / 128), m->sm_count), tc::THREADS, tc::GemmCfg<128>::SMEM_BYTES, st, ta_hi, ta_lo, tb_hi, tb_lo, gp);
     }
 
     void gemm(const Tensor &x, const LeafWeights &w, const Node *conv, int act, float *y, int64_t Ho, int64_t Wo) {
@@ -507,6 +503,15 @@ struct Exec {
             break;
         }
         case K_LINEAR: {
+            if (amx && &n == final_leaf && x.h == 1 && w.ncols <= 256 && tc_eligible(x, w, nullptr)) {
+                // recognition head: labels + confidences straight from the accumulators, the logits tensor never exists
+                y.n = dout.n; y.c = dout.c; y.h = dout.h; y.w = dout.w; y.p = nullptr;
+                const size_t rows = (size_t)x.n * x.w;
+                amx->lab = (int *)ws->arena.alloc(rows * 4); amx->conf = (float *)ws->arena.alloc(rows * 4);
+                amx->done = true;
+                gemm_tc(x, w, ACT_LINEAR, nullptr, amx);
+                break;
+            }
             y = mk(dout);
             gemm(x, w, nullptr, ACT_LINEAR, y.p, x.h, x.w);
             break;
@@ -1005,10 +1010,17 @@ static void ensure_workspace(kb_model *m, Workspace *ws) {
 
 struct ForwardResult { Tensor y; Lens lens; };
 
+// the network's last layer if it is a Linear sitting directly at the end of the top-level series (the recognition head)
+static const Node *final_linear(const Node &root) {
+    if (root.kind != K_SERIES || root.children.empty()) return nullptr;
+    const Node *last = root.children.back().get();
+    return last->kind == K_LINEAR ? last : nullptr;
+}
+
 // Stages the NCHW input into the arena as NHWC, runs the net.  `extra_bytes`: additional arena space the
 // caller will allocate after the forward (decode buffers etc.).
 static ForwardResult forward_impl(kb_model *m, Workspace *ws, const float *x, int x_on_device, int n, int h, int w, const int32_t *widths,
-                                  cudaStream_t st, size_t extra_bytes) {
+                                  cudaStream_t st, size_t extra_bytes, Exec::ArgmaxOut *amx = nullptr) {
     const Plan &pl = *m->plan;
     const int C = pl.input[1];
     { const char *e = getenv("KB_GEMM"); m->use_tc = !(e && strcmp(e, "ffma") == 0) && !m->force_ffma; }
@@ -1028,6 +1040,7 @@ static ForwardResult forward_impl(kb_model *m, Workspace *ws, const float *x, in
         Arena saved = ws->arena;
         ws->arena.dry = true; ws->arena.off = 0;
         Exec ex{m, ws, st, true};
+        ex.amx = amx; ex.final_leaf = final_linear(*pl.root);
         Dims d0; d0.n = n; d0.c = C; d0.h = h; d0.w = w;
         first_s2d = C > 1 && ex.first_is_s2d(*pl.root, d0);     // the first layer reads the NCHW input itself (space-to-depth planes)
         if (!x_on_device || C > 1) ws->arena.alloc(in_elems * sizeof(float));      // staging of the raw input
@@ -1070,6 +1083,8 @@ static ForwardResult forward_impl(kb_model *m, Workspace *ws, const float *x, in
     t_in.reset();
     CK(cudaMemsetAsync(ws->d_flag, 0, sizeof(int), st));
     Exec ex{m, ws, st, false};
+    ex.amx = amx; ex.final_leaf = final_linear(*pl.root);
+    if (amx) amx->done = false;
     ForwardResult r; r.lens = lens0;
     r.y = ex.run(*pl.root, t, r.lens);
     CK(cudaMemcpyAsync(ws->h_flag, ws->d_flag, sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -1241,12 +1256,16 @@ struct RecognizeArgs {
 static void recognize_enqueue(kb_model *m, Workspace *ws, const RecognizeArgs &a, cudaStream_t st, int T, int C, std::vector<int32_t> &olens) {
     const int n = a.n;
     size_t extra = decode_bytes(n, T, a.max_out) + (a.probs && !a.probs_on_device ? (size_t)n * C * T * 4 + 4096 : 0);
-    ForwardResult r = forward_impl(m, ws, a.lines, a.lines_on_device, n, a.h, a.w, a.widths, st, extra);
+    // without a probability request the head's arg-max / softmax statistics come out of the final Linear's epilogue (KB_ARGMAX=0:
+    // separate kernel over the logits, as with probabilities)
+    Exec::ArgmaxOut am; am.temperature = a.temperature;
+    const bool fuse_am = !a.probs && !(getenv("KB_ARGMAX") && atoi(getenv("KB_ARGMAX")) == 0);
+    ForwardResult r = forward_impl(m, ws, a.lines, a.lines_on_device, n, a.h, a.w, a.widths, st, extra, fuse_am ? &am : nullptr);
     std::unique_ptr<StageTimer> t_dec(new StageTimer(ws, st, "decode", true));
     const long long rows = (long long)n * T;
-    int *d_lab = (int *)ws->arena.alloc((size_t)rows * 4);
-    float *d_conf = (float *)ws->arena.alloc((size_t)rows * 4);
-    LAUNCH(m, k_row_argmax_softmax, (unsigned)((rows + 7) / 8), 256, 0, st, r.y.p, rows, C, a.temperature, d_lab, d_conf);
+    int *d_lab = am.done ? am.lab : (int *)ws->arena.alloc((size_t)rows * 4);
+    float *d_conf = am.done ? am.conf : (float *)ws->arena.alloc((size_t)rows * 4);
+    if (!am.done) LAUNCH(m, k_row_argmax_softmax, (unsigned)((rows + 7) / 8), 256, 0, st, r.y.p, rows, C, a.temperature, d_lab, d_conf);
     olens.resize(n);
     for (int i = 0; i < n; ++i) olens[i] = r.lens.has ? r.lens.v[i] : T;
     int *d_lens = (int *)ws->arena.alloc((size_t)n * 4);
@@ -1679,6 +1698,7 @@ int kb_debug_layer_output(kb_model *m, const char *name, int32_t dims[4], float 
         auto it = ws->taps.find(name);
         if (it == ws->taps.end()) throw SpecError(std::string("no output recorded for layer ") + name);
         const Tensor &t = it->second;
+        if (!t.p && !dims_only) throw SpecError(std::string("layer ") + name + " did not materialise in the last call (fused into its consumer); set KB_FUSE=0 / KB_KEEP_FP32=1, or use kb_forward");
         dims[0] = (int32_t)t.n; dims[1] = (int32_t)t.c; dims[2] = (int32_t)t.h; dims[3] = (int32_t)t.w;
         if (dims_only || !out_host) return (int)KB_OK;
         const size_t elems = (size_t)t.numel();

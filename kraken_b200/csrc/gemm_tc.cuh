@@ -20,9 +20,9 @@
 // The split planes live in HBM (weights: once at finalize; activations: written by the producing kernel or k_split_f16).
 //
 // Kernel anatomy (one persistent CTA per SM, 320 threads):
-//   warp 0      TMA producer : cp.async.bulk.tensor.2d boxes of 32 halves x 128 rows (64-byte rows, SWIZZLE_64B), 4 stages x 48 KB
-//   warp 1      MMA issuer   : tcgen05.mma.cta_group::1.kind::f16, M128 x N256 x K16, 6 per k-block of 32 halves;
-//               also owns TMEM alloc/dealloc (512 columns = main + correction accumulator of 256 each)
+//   warp 0      TMA producer : cp.async.bulk.tensor.2d boxes of 32 halves x 128 rows (64-byte rows, SWIZZLE_64B), 192 KB of stages
+//   warp 1      MMA issuer   : tcgen05.mma.cta_group::1.kind::f16, M128 x N{128,256} x K16, 6 per k-block of 32 halves;
+//               also owns TMEM alloc/dealloc (512 columns: main + correction accumulators, two sets of them for N128 tiles)
 //   warps 2..9  epilogue     : tcgen05.ld 32x32b.x32 -> main + corr/2048 + bias -> st.global (one accumulator row per thread,
 //               the two warps of a TMEM lane quarter split the column chunks)
 #pragma once
@@ -36,10 +36,22 @@
 namespace kb {
 namespace tc {
 
-constexpr int BM = 128, BN = 256, BK = 32, STAGES = 4;                 // BK in fp16 elements: 64-byte rows
-constexpr int A_TILE = BM * BK * 2, B_TILE = BN * BK * 2;                 // bytes
-constexpr int STAGE_BYTES = 2 * A_TILE + 2 * B_TILE;                      // 48 KB
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int BM = 128, BK = 32;                                          // BK in fp16 elements: 64-byte rows
+constexpr int A_TILE = BM * BK * 2;                                       // bytes of one plane of the activation tile
+// Two tile shapes.  BNT = 256: one accumulator set (main 256 + correction 256 columns = all of TMEM), 4 stages x 48 KB; the MMA
+// warp waits while the epilogue drains (used for 128 < N <= 256, where one tile holds whole rows: the arg-max epilogue needs that).
+// BNT = 128: TWO accumulator sets (2 x (128 + 128) columns), 6 stages x 32 KB: the epilogue of tile i runs under the MMAs of tile
+// i + 1.  Round 1 ran everything on the first shape: ncu showed the tensor pipe 49.8 % active with the MMA warp parked on `tempty`
+// for the whole epilogue of each of the 800 tiles of cfg2's projection.
+template <int BNT> struct GemmCfg {
+    static constexpr int ACC_SETS = BNT == 128 ? 2 : 1;
+    static constexpr int B_TILE = BNT * BK * 2;
+    static constexpr int STAGE_BYTES = 2 * A_TILE + 2 * B_TILE;
+    static constexpr int STAGES = BNT == 128 ? 6 : 4;
+    static constexpr int RED_BYTES = 4 * 2 * 32 * 4 * 4;                    // arg-max epilogue: per (lane quarter, half, lane) 4 words
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + RED_BYTES;
+};
+constexpr int BN = 256;                                                  // (largest tile; host-side helpers)
 constexpr int EPI_WARPS = 8;                                             // two per TMEM lane quarter: even / odd 32-column chunks
 constexpr int THREADS = 64 + EPI_WARPS * 32;
 constexpr int TMEM_COLS = 512;
@@ -152,32 +164,35 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float *v) {
 struct GemmTcParams {
     float *c; const float *bias;
     int M, N, K, ldc, act;
+    // arg-max epilogue (MODE 1): per row the first-maximum class of softmax(row / temperature) and its probability, instead of C
+    int *lab; float *conf; float temperature;
 };
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 
-// CL = 1: independent CTAs.  CL = 2: clusters of two CTAs work on two vertically adjacent output tiles (same n-tile): each CTA
-// fetches only HALF of the shared weight tile and multicasts it to both.  A stage is free when the MMAs of BOTH CTAs have
-// retired, so the consumers commit with a multicast arrive and `empty` counts CL arrivals.
-template <int CL>
+// MODE 0: C = A B^T + bias (+ activation).  MODE 1 (BNT = 256, N <= 256, one n-tile): the recognition head - logits are never
+// written; each row's arg-max label and softmax confidence are (rpred.py:226 softmax, ctc_decoder.py:65 max over classes).
+template <int BNT, int MODE>
 __global__ void __launch_bounds__(THREADS, 1)
 k_gemm_tc(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
           const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo, GemmTcParams p) {
+    using Cfg = GemmCfg<BNT>;
+    constexpr int STAGES = Cfg::STAGES, STAGE_BYTES = Cfg::STAGE_BYTES, B_TILE = Cfg::B_TILE, ACC_SETS = Cfg::ACC_SETS;
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = smem_align1024(smem_raw);
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + STAGES * STAGE_BYTES);
     uint64_t *full = bars, *empty = bars + STAGES, *tfull = bars + 2 * STAGES, *tempty = bars + 2 * STAGES + 2;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * STAGES + 4);
+    float *red = reinterpret_cast<float *>(smem + STAGES * STAGE_BYTES + 256);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int tiles_m = (p.M + BM - 1) / BM, tiles_n = (p.N + BN - 1) / BN;
-    const int ntiles = ((tiles_m + CL - 1) / CL) * tiles_n;        // work items of a cluster: CL vertically adjacent tiles
+    const int tiles_m = (p.M + BM - 1) / BM, tiles_n = (p.N + BNT - 1) / BNT;
+    const int ntiles = tiles_m * tiles_n;
     const int nkb = (p.K + BK - 1) / BK;
-    uint32_t crank = 0;
-    if (CL > 1) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
-    const int first = blockIdx.x / CL, nworkers = gridDim.x / CL;
+    const int first = blockIdx.x, nworkers = gridDim.x;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], CL); }
-        mbar_init(&tfull[0], 1); mbar_init(&tempty[0], EPI_WARPS);
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -187,7 +202,6 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ C
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    if (CL > 1) asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");   // peer barriers initialised
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
@@ -196,23 +210,17 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ C
             int stage = 0; uint32_t phase = 0;
             for (int tile = first; tile < ntiles; tile += nworkers) {
                 // n-tiles innermost: consecutive CTAs share the same A rows (L2 reuse), weights stay L2 resident
-                const int m0 = ((tile / tiles_n) * CL + (int)crank) * BM, n0 = (tile % tiles_n) * BN;
+                const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BNT;
                 for (int kb = 0; kb < nkb; ++kb) {
                     mbar_wait(&empty[stage], phase ^ 1);
                     uint8_t *st = smem + stage * STAGE_BYTES;
                     mbar_expect_tx(&full[stage], STAGE_BYTES);
                     tma_load_2d(st, &tm_a_hi, &full[stage], kb * BK, m0);
                     tma_load_2d(st + A_TILE, &tm_a_lo, &full[stage], kb * BK, m0);
-                    // weight tile = two 128-row boxes per plane
-                    if (CL == 1) {
-                        tma_load_2d(st + 2 * A_TILE, &tm_b_hi, &full[stage], kb * BK, n0);
-                        tma_load_2d(st + 2 * A_TILE + B_TILE / 2, &tm_b_hi, &full[stage], kb * BK, n0 + BN / 2);
-                        tma_load_2d(st + 2 * A_TILE + B_TILE, &tm_b_lo, &full[stage], kb * BK, n0);
-                        tma_load_2d(st + 2 * A_TILE + B_TILE + B_TILE / 2, &tm_b_lo, &full[stage], kb * BK, n0 + BN / 2);
-                    } else {
-                        const int half = (int)crank * (BN / 2);
-                        tma_load_2d_mc(st + 2 * A_TILE + (int)crank * (B_TILE / 2), &tm_b_hi, &full[stage], kb * BK, n0 + half, (uint16_t)0x3);
-                        tma_load_2d_mc(st + 2 * A_TILE + B_TILE + (int)crank * (B_TILE / 2), &tm_b_lo, &full[stage], kb * BK, n0 + half, (uint16_t)0x3);
+#pragma unroll
+                    for (int h = 0; h < BNT / 128; ++h) {                       // weight tile = 128-row boxes per plane
+                        tma_load_2d(st + 2 * A_TILE + h * (128 * BK * 2), &tm_b_hi, &full[stage], kb * BK, n0 + 128 * h);
+                        tma_load_2d(st + 2 * A_TILE + B_TILE + h * (128 * BK * 2), &tm_b_lo, &full[stage], kb * BK, n0 + 128 * h);
                     }
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
@@ -220,12 +228,12 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ C
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
-        constexpr uint32_t idesc = idesc_f16(0, 0, BM, BN);
-        int stage = 0; uint32_t phase = 0; uint32_t acc_phase = 0;
+        constexpr uint32_t idesc = idesc_f16(0, 0, BM, BNT);
+        int stage = 0; uint32_t phase = 0; uint32_t acc_phase[2] = {0, 0}; int acc = 0;
         for (int tile = first; tile < ntiles; tile += nworkers) {
-            mbar_wait(&tempty[0], acc_phase ^ 1);
+            mbar_wait(&tempty[acc], acc_phase[acc] ^ 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t d_main = tmem_base, d_corr = tmem_base + (uint32_t)BN;
+            const uint32_t d_main = tmem_base + (uint32_t)(acc * 256), d_corr = d_main + (uint32_t)BNT;
             for (int kb = 0; kb < nkb; ++kb) {
                 mbar_wait(&full[stage], phase);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -240,14 +248,14 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ C
                         umma_f16(d_corr, a_hi + adv, b_lo + adv, idesc, 1u);
                         umma_f16(d_main, a_hi + adv, b_hi + adv, idesc, (kb | k) ? 1u : 0u);
                     }
-                    if (CL == 1) umma_commit(&empty[stage]);                  // frees the smem stage when these MMAs retire
-                    else umma_commit_mc(&empty[stage], (uint16_t)0x3);        // ... in both CTAs: the peer multicasts into this stage too
-                    if (kb == nkb - 1) umma_commit(&tfull[0]);                // accumulators complete -> epilogue
+                    umma_commit(&empty[stage]);                               // frees the smem stage when these MMAs retire
+                    if (kb == nkb - 1) umma_commit(&tfull[acc]);              // accumulators complete -> epilogue
                 }
                 __syncwarp();
                 if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
-            acc_phase ^= 1;
+            acc_phase[acc] ^= 1;
+            if (ACC_SETS == 2) acc ^= 1;
         }
     } else {
         // ===================== epilogue (warps 2..9) =====================
@@ -255,61 +263,111 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ C
         // the warp pair of a lane quarter takes the even / odd chunks.  (Round 1 used 4 warps with a per-element activation
         // switch and a shared-memory transpose: with the mainloop on fp16 MMAs the epilogue took as long as the mainloop.)
         const int q = warp & 3, half = (warp - 2) >> 2;                       // TMEM lane quarter this warp may access
-        uint32_t acc_phase = 0;
+        uint32_t acc_phase[2] = {0, 0}; int acc = 0;
         constexpr float R = 1.f / X2_SCALE;
         for (int tile = first; tile < ntiles; tile += nworkers) {
-            const int m0 = ((tile / tiles_n) * CL + (int)crank) * BM, n0 = (tile % tiles_n) * BN;
-            mbar_wait(&tfull[0], acc_phase);
+            const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BNT;
+            mbar_wait(&tfull[acc], acc_phase[acc]);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const bool vec = (p.ldc & 3) == 0 && (p.N & 3) == 0;
-            const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
+            const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 256);
             const int m = m0 + q * 32 + lane;
+            if (MODE == 0) {
+                const bool vec = (p.ldc & 3) == 0 && (p.N & 3) == 0;
 #pragma unroll 1
-            for (int c0 = 32 * half; c0 < BN; c0 += 64) {
-                if (n0 + c0 >= p.N) break;                                    // warp-uniform
-                uint32_t vm[32], vc[32];
-                tmem_ld32_nowait(lane_base + (uint32_t)c0, vm);
-                tmem_ld32_nowait(lane_base + (uint32_t)(BN + c0), vc);
-                tmem_ld_wait();
-                float o[32];
+                for (int c0 = 32 * half; c0 < BNT; c0 += 64) {
+                    if (n0 + c0 >= p.N) break;                                // warp-uniform
+                    uint32_t vm[32], vc[32];
+                    tmem_ld32_nowait(lane_base + (uint32_t)c0, vm);
+                    tmem_ld32_nowait(lane_base + (uint32_t)(BNT + c0), vc);
+                    tmem_ld_wait();
+                    float o[32];
 #pragma unroll
-                for (int j = 0; j < 32; ++j) o[j] = fmaf(__uint_as_float(vc[j]), R, __uint_as_float(vm[j]));
-                const int n = n0 + c0;
-                if (p.bias) {
-                    if (n + 32 <= p.N && (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0 && (n & 3) == 0) {
+                    for (int j = 0; j < 32; ++j) o[j] = fmaf(__uint_as_float(vc[j]), R, __uint_as_float(vm[j]));
+                    const int n = n0 + c0;
+                    if (p.bias) {
+                        if (n + 32 <= p.N && (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0 && (n & 3) == 0) {
 #pragma unroll
-                        for (int j = 0; j < 32; j += 4) {
-                            const float4 b4 = __ldg(reinterpret_cast<const float4 *>(p.bias + n + j));
-                            o[j] += b4.x; o[j + 1] += b4.y; o[j + 2] += b4.z; o[j + 3] += b4.w;
+                            for (int j = 0; j < 32; j += 4) {
+                                const float4 b4 = __ldg(reinterpret_cast<const float4 *>(p.bias + n + j));
+                                o[j] += b4.x; o[j + 1] += b4.y; o[j + 2] += b4.z; o[j + 3] += b4.w;
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) o[j] += (n + j < p.N) ? __ldg(p.bias + n + j) : 0.f;
                         }
-                    } else {
+                    }
+                    act_apply_vec(o, p.act);
+                    if (m < p.M) {
+                        float *dst = p.c + (size_t)m * p.ldc + n;
+                        if (vec) {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) o[j] += (n + j < p.N) ? __ldg(p.bias + n + j) : 0.f;
+                            for (int j = 0; j < 32; j += 4)
+                                if (n + j < p.N) *reinterpret_cast<float4 *>(dst + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) if (n + j < p.N) dst[j] = o[j];
+                        }
                     }
                 }
-                act_apply_vec(o, p.act);
-                if (m < p.M) {
-                    float *dst = p.c + (size_t)m * p.ldc + n;
-                    if (vec) {
+            } else {
+                // ---- arg-max epilogue: two passes over this row's accumulator columns (TMEM reads are cheap), the two warps of a
+                // lane quarter combine through shared memory.  Same arithmetic as k_row_argmax_softmax: v = x / T (IEEE division),
+                // e = expf(v - max), label = FIRST maximum of e, confidence = e_max / sum(e).
+                float *rq = red + (q * 2) * 32 * 4;
+                float mx = -INFINITY;
+#pragma unroll 1
+                for (int c0 = 32 * half; c0 < BNT; c0 += 64) {
+                    if (c0 >= p.N) break;
+                    uint32_t vm[32], vc[32];
+                    tmem_ld32_nowait(lane_base + (uint32_t)c0, vm);
+                    tmem_ld32_nowait(lane_base + (uint32_t)(BNT + c0), vc);
+                    tmem_ld_wait();
 #pragma unroll
-                        for (int j = 0; j < 32; j += 4)
-                            if (n + j < p.N) *reinterpret_cast<float4 *>(dst + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) if (n + j < p.N) dst[j] = o[j];
-                    }
+                    for (int j = 0; j < 32; ++j)
+                        if (c0 + j < p.N) {
+                            const float o = fmaf(__uint_as_float(vc[j]), R, __uint_as_float(vm[j])) + (p.bias ? __ldg(p.bias + c0 + j) : 0.f);
+                            mx = fmaxf(mx, __fdiv_rn(o, p.temperature));
+                        }
                 }
+                rq[half * 128 + lane * 4] = mx;
+                named_bar_sync(1 + q, 64);
+                mx = fmaxf(mx, rq[(half ^ 1) * 128 + lane * 4]);
+                float s = 0.f, be = -1.f; int bi = 0x7fffffff;
+#pragma unroll 1
+                for (int c0 = 32 * half; c0 < BNT; c0 += 64) {
+                    if (c0 >= p.N) break;
+                    uint32_t vm[32], vc[32];
+                    tmem_ld32_nowait(lane_base + (uint32_t)c0, vm);
+                    tmem_ld32_nowait(lane_base + (uint32_t)(BNT + c0), vc);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (c0 + j < p.N) {
+                            const float o = fmaf(__uint_as_float(vc[j]), R, __uint_as_float(vm[j])) + (p.bias ? __ldg(p.bias + c0 + j) : 0.f);
+                            const float e = expf(__fdiv_rn(o, p.temperature) - mx);
+                            s += e;
+                            if (e > be) { be = e; bi = c0 + j; }               // strict >: first maximum in ascending column order
+                        }
+                }
+                rq[half * 128 + lane * 4 + 1] = s; rq[half * 128 + lane * 4 + 2] = be; reinterpret_cast<int *>(rq)[half * 128 + lane * 4 + 3] = bi;
+                named_bar_sync(1 + q, 64);
+                if (half == 0 && m < p.M) {
+                    const float s2 = rq[128 + lane * 4 + 1], be2 = rq[128 + lane * 4 + 2]; const int bi2 = reinterpret_cast<int *>(rq)[128 + lane * 4 + 3];
+                    if (be2 > be || (be2 == be && bi2 < bi)) { be = be2; bi = bi2; }     // first index on ties, as torch.max
+                    p.lab[m] = bi; p.conf[m] = be / (s + s2);
+                }
+                named_bar_sync(1 + q, 64);                                    // `red` is reused by the next tile
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty[0]);
-            acc_phase ^= 1;
+            if (lane == 0) mbar_arrive(&tempty[acc]);
+            acc_phase[acc] ^= 1;
+            if (ACC_SETS == 2) acc ^= 1;
         }
     }
     // ===================== teardown =====================
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (CL > 1) asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");   // no multicast / remote arrive may target an exited CTA
     if (warp == 1) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");

@@ -41,22 +41,20 @@ constexpr int NG = 2;                                    // independent line gro
 constexpr int LCS = 8;                                   // cluster size
 constexpr int A_PLANE_ELEMS = 128 * 256;                 // fp16 elements of one W plane of a CTA: [128 gate rows][K = 256], row-major
 constexpr int EW = 4;                                    // epilogue warps per TMEM lane quarter: 2 per group (latency hiding: v3 with 1 was 2x slower)
-constexpr int LTHREADS = 32 + 4 * EW * 32;               // warp 0: MMA issue / TMEM alloc; warps 1..16: epilogue
+constexpr int LTHREADS = 64 + 4 * EW * 32;               // warp 0: MMA issue of the W1 chains / TMEM alloc; warps 1..16: epilogue; warp 17: W2s chains
 constexpr int TM_COLS = 512;
 template <int GL> struct ClusterCfg {                    // GL = lines per group: 8 (16 lines per cluster) or 16 (32 lines per cluster)
     static constexpr int NL = NG * GL;                   // lines per cluster
-    static constexpr int CH_B = 2 * GL * 16;             // bytes of one k-chunk (8 unit slots) of a group: [h1 lines | h2s lines] x 16 B
+    static constexpr int LPW = GL / 2;                   // lines per epilogue warp (two warps per TMEM lane quarter and group)
+    static constexpr int NT = LPW / 4;                   // 4x4 gate transposes (= cells) per thread and step
+    static constexpr int WB_B = 2 * LPW * 16;            // bytes an epilogue warp contributes to a k-chunk: [h1 of its lines | h2s of its lines] x 16 B
+    static constexpr int CH_B = 2 * GL * 16;             // bytes of one k-chunk (8 unit slots) of a group = the two warps' blocks
     static constexpr int B_BUF_B = 32 * CH_B;            // bytes per (group, buffer): K = 256 = 32 chunks
-    static constexpr int SX_BYTES = 4 * NG * 2 * CH_B;   // outgoing chunk staging per (quarter, group), double buffered
-    static constexpr int SG_FLOATS = GL * 8 * 4;         // per (TMEM lane quarter, group): [line][unit][gate]
-    static constexpr int SH_FLOATS = GL * 8;             // per (quarter, group): [line][unit]
-    static constexpr int STG_BYTES = 4 * NG * (SG_FLOATS + SH_FLOATS) * 4;
-    static constexpr int SMEM_BYTES = NG * 2 * B_BUF_B + STG_BYTES + SX_BYTES + 128 + 1024;
-    static constexpr int LPW = GL / 2;                   // lines per epilogue warp in the activation phase
-    static constexpr int N2 = 16;                        // N of the W2s x h1 product (UMMA minimum; only the first GL columns are read)
-    static constexpr int GSTRIDE = GL == 8 ? 64 : 128;   // TMEM columns per group: D1a @0 (2 GL), D1b @2 GL, D2a @4 GL (16), D2b @4 GL + 16
+    static constexpr int SX_BYTES = 4 * NG * 2 * 2 * WB_B;   // outgoing block staging per epilogue warp, double buffered
+    static constexpr int SMEM_BYTES = NG * 2 * B_BUF_B + SX_BYTES + 128 + 1024;
+    static constexpr int N1 = 2 * GL;                    // N of both products (W2s x the same operand rows; only its h1 columns are read)
+    static constexpr int GSTRIDE = 4 * N1;               // TMEM columns per group: D1a @0, D1b @N1, D2a @2 N1, D2b @3 N1
     static constexpr int TM_A0 = NG * GSTRIDE;           // A: W1 @TM_A0 (128 columns), W2s @TM_A0 + 128
-    static constexpr int CPT = GL / 8;                   // cells per thread in the update phase
 };
 
 struct LstmTcParams {
@@ -146,19 +144,30 @@ __device__ __forceinline__ float sigmoid_fast(float x) { return rcp_fast(1.f + _
 __device__ __forceinline__ float tanh_fast(float x) { return fmaf(2.f, sigmoid_fast(2.f * x), -1.f); }
 __device__ __forceinline__ void named_bar(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 
+// 4x4 transpose across the four lanes of a quad: in: v[i] = this lane's value for item i; out: v[j] = lane (quad base + j)'s value
+// for item (lane & 3).  Three shuffles; the selects keep the register indices static.
+__device__ __forceinline__ void quad_transpose4(float (&v)[4], int gq) {
+#pragma unroll
+    for (int k = 1; k < 4; ++k) {
+        const int pr = gq ^ k;                                         // partner's index in the quad
+        const float send = pr == 0 ? v[0] : pr == 1 ? v[1] : pr == 2 ? v[2] : v[3];
+        const float got = __shfl_xor_sync(0xffffffffu, send, k);
+        if (pr == 0) v[0] = got; else if (pr == 1) v[1] = got; else if (pr == 2) v[2] = got; else v[3] = got;
+    }
+}
+
 template <int GL>
 __global__ void __launch_bounds__(LTHREADS, 1) k_lstm_rec_tc(LstmTcParams p) {
     using Cfg = ClusterCfg<GL>;
-    constexpr int NL = Cfg::NL, CH_B = Cfg::CH_B, B_BUF_B = Cfg::B_BUF_B, SG_FLOATS = Cfg::SG_FLOATS, SH_FLOATS = Cfg::SH_FLOATS;
-    constexpr int STG_BYTES = Cfg::STG_BYTES, LPW = Cfg::LPW, TM_A0 = Cfg::TM_A0, GSTRIDE = Cfg::GSTRIDE, CPT = Cfg::CPT;
+    constexpr int NL = Cfg::NL, CH_B = Cfg::CH_B, B_BUF_B = Cfg::B_BUF_B, WB_B = Cfg::WB_B, LPW = Cfg::LPW, NT = Cfg::NT;
+    constexpr int TM_A0 = Cfg::TM_A0, GSTRIDE = Cfg::GSTRIDE, N1 = Cfg::N1;
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = smem_align1024(smem_raw);
-    uint8_t *sB = smem;                                   // [group][buffer][k-chunk][plane][line][8 unit slots] fp16 = core matrices, no swizzle
-    float *stg = reinterpret_cast<float *>(sB + NG * 2 * B_BUF_B);
-    uint8_t *sx = sB + NG * 2 * B_BUF_B + STG_BYTES;      // [quarter][group][2][CH_B]
-    uint64_t *bars = reinterpret_cast<uint64_t *>(sB + NG * 2 * B_BUF_B + STG_BYTES + Cfg::SX_BYTES);
-    uint64_t *b_full = bars /* [group][2] */, *mma_done = bars + 4 /* [group] */;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 6);
+    uint8_t *sB = smem;                                   // [group][buffer][k-chunk][row = (warp half, plane, line)][8 unit slots] fp16, no swizzle
+    uint8_t *sx = sB + NG * 2 * B_BUF_B;                  // [quarter][group][warp half][2][WB_B]
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sB + NG * 2 * B_BUF_B + Cfg::SX_BYTES);
+    uint64_t *b_full = bars /* [group][2] */, *mma_done = bars + 4 /* [group][chain owner: W1 / W2s] */;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 8);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint32_t rank;
@@ -167,8 +176,7 @@ __global__ void __launch_bounds__(LTHREADS, 1) k_lstm_rec_tc(LstmTcParams p) {
     const int hid = p.hid, GC = p.dirs * 4 * hid, OC = p.dirs * hid;
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < 4; ++i) mbar_init(&b_full[i], 1);
-        mbar_init(&mma_done[0], 1); mbar_init(&mma_done[1], 1);
+        for (int i = 0; i < 4; ++i) { mbar_init(&b_full[i], 1); mbar_init(&mma_done[i], 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         mbar_expect_tx(&b_full[1], B_BUF_B);             // buffer 1 of each group receives h_0 at the end of step 0
         mbar_expect_tx(&b_full[3], B_BUF_B);
@@ -212,9 +220,12 @@ __global__ void __launch_bounds__(LTHREADS, 1) k_lstm_rec_tc(LstmTcParams p) {
         if (q < p.nseq) maxlen = max(maxlen, p.lens ? min(max(p.lens[q], 0), p.T) : p.T);
     }
 
-    if (warp == 0) {
-        // ===================== MMA issuer: alternates between the two line groups =====================
-        const uint32_t id1 = idesc_f16(0, 0, 128, 2 * GL), id2 = idesc_f16(0, 0, 128, Cfg::N2);
+    if (warp == 0 || warp == 17) {
+        // ===================== two MMA issuers (round 1 had one: 32 tiny MMAs per group and step took 650-1000 cycles to ISSUE, the
+        // products finished 50 cycles later).  Warp 0 issues the W1 x [h1|h2s] chains, warp 17 the W2s x [h1|..] chains; both alternate
+        // between the two line groups and commit to their own mbarrier.
+        const int own = warp == 0 ? 0 : 1;
+        const uint32_t id1 = idesc_f16(0, 0, 128, N1);
         for (int s = 0; s < maxlen; ++s) {
             const int cur = s & 1;
 #pragma unroll 1
@@ -226,73 +237,70 @@ __global__ void __launch_bounds__(LTHREADS, 1) k_lstm_rec_tc(LstmTcParams p) {
                     else mbar_wait_poll(bf, (uint32_t)(((s - 1) >> 1) & 1));
                 }
                 const long long d_w1 = (p.dbg & 1) ? clock64() : 0;
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // st.async writes -> UMMA (async proxy) reads
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // bulk-copy writes -> UMMA (async proxy) reads
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 if (elect_one()) {
-                    // this buffer is refilled during step s+1 (nobody can send that before receiving our h_s)
-                    if (s + 2 < maxlen) mbar_expect_tx(bf, B_BUF_B);
                     const uint32_t b0 = smem_u32(sB + (g * 2 + cur) * B_BUF_B);
-                    const uint32_t dg = tmem_base + (uint32_t)(g * GSTRIDE);
+                    const uint32_t dg = tmem_base + (uint32_t)(g * GSTRIDE + own * 2 * N1);
+                    const uint32_t abase = tmem_base + (uint32_t)(TM_A0 + own * 128);
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
 #pragma unroll
                         for (int kk = 0; kk < 4; ++kk) {
-                            const int ka = kk == 0 ? 0 : kk == 1 ? 2 : kk == 2 ? 1 : 3;      // 0,2,1,3: same-chain MMAs 4 issues apart
+                            const int ka = kk == 0 ? 0 : kk == 1 ? 2 : kk == 2 ? 1 : 3;      // 0,2,1,3: alternate between the two chains
                             const int half = ka >> 1;
                             const uint64_t bd = umma_desc_nosw(b0 + (uint32_t)((ka * 4 + k) * 2 * CH_B), (uint32_t)CH_B, 128u);   // K16 = chunks 2j, 2j+1
-                            const uint32_t a1 = tmem_base + (uint32_t)(TM_A0 + ka * 32 + k * 8);      // K = 16 -> 8 columns of fp16 pairs
-                            const uint32_t a2 = a1 + 128u;
                             const uint32_t first = ((ka & 1) == 0 && k == 0) ? 0u : 1u;
-                            umma_f16_ts(dg + (uint32_t)(half * 2 * GL), a1, bd, id1, first);                 // [W1 h1 | W1 h2s]
-                            umma_f16_ts(dg + (uint32_t)(4 * GL + half * Cfg::N2), a2, bd, id2, first);     // W2s x first 16 rows of B (h1; N >= 16)
+                            umma_f16_ts(dg + (uint32_t)(half * N1), abase + (uint32_t)(ka * 32 + k * 8), bd, id1, first);   // K = 16 -> 8 columns of fp16 pairs
                         }
                     }
-                    umma_commit(&mma_done[g]);
+                    umma_commit(&mma_done[g * 2 + own]);
+                    // this buffer is refilled during step s+1 (nobody can send that before receiving our h_s); the W1 issuer re-arms it.
+                    // Both issuers have passed their wait on this phase by the time the next one can complete (the epilogue needs both
+                    // chains before any CTA can send h_s).
+                    if (own == 0 && s + 2 < maxlen) mbar_expect_tx(bf, B_BUF_B);
                     if ((p.dbg & 1) && blockIdx.x == 0 && blockIdx.y == 0 && s >= 100 && s < 104) {
                         long long *d = p.dbgbuf + ((s - 100) * 2 + g) * 8;
-                        d[0] = d_w0; d[1] = d_w1; d[2] = clock64();
+                        if (own == 0) { d[0] = d_w0; d[1] = d_w1; d[2] = clock64(); }
                     }
                 }
                 __syncwarp();
             }
         }
     } else {
-        // ===================== epilogue warps 1..16: quarter q = warp & 3; sub-warp sw = (warp-1) >> 2: group g = sw >> 1 =====================
+        // ===================== epilogue warps 1..16: quarter q = warp & 3; sub-warp sw = (warp-1) >> 2: group g = sw >> 1, half sw2 = sw & 1.
+        // A warp owns LPW lines of its group x the 8 unit slots of its TMEM lane quarter and never synchronises with another warp:
+        // gate values are regrouped by quad shuffles (round 1: shared memory + two named barriers per step).
         const int q = warp & 3;                            // TMEM lane quarter: unit slots 8q .. 8q+7
         const int sw = (warp - 1) >> 2, g = sw >> 1, sw2 = sw & 1;
         const int jq = lane >> 2, gate = lane & 3;         // unit slot within the quarter, gate of this thread's TMEM row
         const int slot = 8 * q + jq, u = (int)rank * p.U + slot;
         const bool uvalid = slot < p.U && u < hid;
-        float *sg = stg + (q * NG + g) * (SG_FLOATS + SH_FLOATS);
-        const int tq = sw2 * 32 + lane;                    // thread index within the (quarter, group)'s 64 threads
-        // the CPT cells this thread updates: line cl of the group, unit slots cj .. cj + CPT - 1 of the quarter
-        const int cl = (tq * CPT) >> 3, cj = (tq * CPT) & 7;
-        const int cu = (int)rank * p.U + 8 * q + cj;
-        const int cql = chunk * NL + g * GL + cl;
-        bool cv[CPT];
+        // after the transposes this thread updates unit `u` of lines (first line of the warp) + 4 t + gate
+        const int line0 = chunk * NL + g * GL + LPW * sw2;
+        int clen[NT]; long long ooff[NT]; bool cval[NT]; float cst[NT];
+        const long long ostride = (long long)(dir ? -1 : 1) * p.step * OC;
 #pragma unroll
-        for (int e = 0; e < CPT; ++e) cv[e] = cql < p.nseq && (8 * q + cj + e) < p.U && cu + e < hid;
-        const int clen = cql < p.nseq ? min(max(p.lens ? p.lens[cql] : p.T, 0), p.T) : 0;
-        const int cqq = cql < p.nseq ? cql : 0;
-        const long long cbase = (long long)(cqq / p.q2) * p.s_outer + (long long)(cqq % p.q2) * p.s_inner;
-        float cst[CPT];
-#pragma unroll
-        for (int e = 0; e < CPT; ++e) {
-            cst[e] = 0.f;
-            if (cv[e]) for (int tt = clen; tt < p.T; ++tt) {
-                const size_t o = (size_t)(cbase + (long long)tt * p.step) * OC + dir * hid + cu + e;
+        for (int t = 0; t < NT; ++t) {
+            const int ql = line0 + 4 * t + gate;
+            cval[t] = ql < p.nseq && uvalid;
+            clen[t] = ql < p.nseq ? min(max(p.lens ? p.lens[ql] : p.T, 0), p.T) : 0;
+            const int qq = ql < p.nseq ? ql : 0;
+            const long long cbase = (long long)(qq / p.q2) * p.s_outer + (long long)(qq % p.q2) * p.s_inner;
+            cst[t] = 0.f;
+            if (cval[t]) for (int tt = clen[t]; tt < p.T; ++tt) {
+                const size_t o = (size_t)(cbase + (long long)tt * p.step) * OC + dir * hid + u;
                 if (p.out) p.out[o] = 0.f;
                 if (p.out_hi) { p.out_hi[o] = __float2half_rn(0.f); p.out_lo[o] = __float2half_rn(0.f); }
             }
+            ooff[t] = (cbase + (long long)(dir ? max(clen[t] - 1, 0) : 0) * p.step) * OC + dir * hid + u;
         }
-        long long ooff = (cbase + (long long)(dir ? max(clen - 1, 0) : 0) * p.step) * OC + dir * hid + cu;
-        const long long ostride = (long long)(dir ? -1 : 1) * p.step * OC;
         // gx of this thread's TMEM row (gate of unit u) for its LPW lines: running pointers, fetched one time step ahead
         int glen[LPW]; const float *gptr[LPW]; float gxn[LPW];
         const long long gstride = (long long)(dir ? -1 : 1) * p.step * GC;
 #pragma unroll
         for (int i = 0; i < LPW; ++i) {
-            const int ql = chunk * NL + g * GL + LPW * sw2 + i;
+            const int ql = line0 + i;
             const bool v = ql < p.nseq && uvalid;
             glen[i] = v ? min(max(p.lens ? p.lens[ql] : p.T, 0), p.T) : 0;
             const int qq = ql < p.nseq ? ql : 0;
@@ -302,13 +310,14 @@ __global__ void __launch_bounds__(LTHREADS, 1) k_lstm_rec_tc(LstmTcParams p) {
             gxn[i] = 0 < glen[i] ? __ldg(gptr[i]) : 0.f;
             gptr[i] += gstride;
         }
-        // hand-off: lane r < 8 of the group's first warp copies this (quarter, group)'s chunk to CTA r
+        // hand-off: lane r < 8 copies this warp's block of the k-chunk to CTA r
         const uint32_t dstB = mapa32(smem_u32(sB), (uint32_t)(lane & 7)), dstFull = mapa32(smem_u32(b_full), (uint32_t)(lane & 7));
-        uint8_t *sxq = sx + (q * NG + g) * 2 * CH_B;
-        const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * GSTRIDE + LPW * sw2);
+        uint8_t *sxw = sx + ((q * NG + g) * 2 + sw2) * 2 * WB_B;
+        // this warp's accumulator columns: rows of the operand = [warp half][plane][line]
+        const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * GSTRIDE + 2 * LPW * sw2);
         // gate non-linearity without divergence: sigmoid(x) for i, f, o; tanh(x) = 2*sigmoid(2x) - 1 for the candidate gate
         const float act_k = gate == 2 ? 2.f : 1.f;
-        const int bar_id = 1 + q + 4 * g;
+        const uint32_t kc_off = ((uint32_t)rank * 4u + (uint32_t)q) * (uint32_t)CH_B + (uint32_t)(sw2 * WB_B);   // this quarter's k-chunk, this warp's rows
 
         for (int s = 0; s < maxlen; ++s) {
             const int nxt = (s + 1) & 1;
@@ -320,63 +329,61 @@ __global__ void __launch_bounds__(LTHREADS, 1) k_lstm_rec_tc(LstmTcParams p) {
                 gptr[i] += gstride;
             }
             const long long e_top = (p.dbg & 1) ? clock64() : 0;
-            if (p.dbg & 4) mbar_wait_poll(&mma_done[g], (uint32_t)(s & 1));
-            else mbar_wait(&mma_done[g], (uint32_t)(s & 1));
+            if (p.dbg & 4) { mbar_wait_poll(&mma_done[g * 2], (uint32_t)(s & 1)); mbar_wait_poll(&mma_done[g * 2 + 1], (uint32_t)(s & 1)); }
+            else { mbar_wait(&mma_done[g * 2], (uint32_t)(s & 1)); mbar_wait(&mma_done[g * 2 + 1], (uint32_t)(s & 1)); }
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const long long e_done = (p.dbg & 1) ? clock64() : 0;
-            // group columns: D1a = [W1 h1 (GL) | W1 h2s (GL)] k-atoms 0,1; D1b @2 GL k-atoms 2,3; D2a @4 GL = W2s h1; D2b @4 GL + 16
+            // group columns: D1a = W1 x rows (k-atoms 0,1) @0, D1b (k-atoms 2,3) @N1, D2a = W2s x rows @2 N1, D2b @3 N1; within the warp's
+            // 2 LPW rows: [h1 lines | h2s lines]
             uint32_t m0[LPW], m1[LPW], c0[LPW], c1[LPW], c2[LPW], c3[LPW];
             if (LPW == 4) {
-                tmem_ld4_nowait(lane_base + 0, m0);      tmem_ld4_nowait(lane_base + 2 * GL, m1);
-                tmem_ld4_nowait(lane_base + GL, c0);     tmem_ld4_nowait(lane_base + 3 * GL, c1);
-                tmem_ld4_nowait(lane_base + 4 * GL, c2); tmem_ld4_nowait(lane_base + 4 * GL + Cfg::N2, c3);
+                tmem_ld4_nowait(lane_base + 0, m0);        tmem_ld4_nowait(lane_base + N1, m1);
+                tmem_ld4_nowait(lane_base + LPW, c0);      tmem_ld4_nowait(lane_base + N1 + LPW, c1);
+                tmem_ld4_nowait(lane_base + 2 * N1, c2);   tmem_ld4_nowait(lane_base + 3 * N1, c3);
             } else {
-                tmem_ld8_nowait(lane_base + 0, m0);      tmem_ld8_nowait(lane_base + 2 * GL, m1);
-                tmem_ld8_nowait(lane_base + GL, c0);     tmem_ld8_nowait(lane_base + 3 * GL, c1);
-                tmem_ld8_nowait(lane_base + 4 * GL, c2); tmem_ld8_nowait(lane_base + 4 * GL + Cfg::N2, c3);
+                tmem_ld8_nowait(lane_base + 0, m0);        tmem_ld8_nowait(lane_base + N1, m1);
+                tmem_ld8_nowait(lane_base + LPW, c0);      tmem_ld8_nowait(lane_base + N1 + LPW, c1);
+                tmem_ld8_nowait(lane_base + 2 * N1, c2);   tmem_ld8_nowait(lane_base + 3 * N1, c3);
             }
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            float av[LPW];
 #pragma unroll
             for (int i = 0; i < LPW; ++i) {
                 const float main_ = __uint_as_float(m0[i]) + __uint_as_float(m1[i]);
                 const float corr = (__uint_as_float(c0[i]) + __uint_as_float(c1[i])) + (__uint_as_float(c2[i]) + __uint_as_float(c3[i]));
                 const float pre = (main_ + corr * (1.f / X2_SCALE)) + gxv[i];
-                sg[((LPW * sw2 + i) * 8 + jq) * 4 + gate] = fmaf(sigmoid_fast(pre * act_k), act_k, 1.f - act_k);
+                av[i] = fmaf(sigmoid_fast(pre * act_k), act_k, 1.f - act_k);
             }
             const long long e_act = (p.dbg & 1) ? clock64() : 0;
-            named_bar(bar_id, 64);
-            {
-                const bool live = s < clen;
+            __half *cx = reinterpret_cast<__half *>(sxw + (s & 1) * WB_B);
 #pragma unroll
-                for (int e = 0; e < CPT; ++e) {
-                    const float4 gt = *reinterpret_cast<const float4 *>(&sg[(cl * 8 + cj + e) * 4]);      // i, f, g, o
-                    float h = 0.f;                         // finished / padding cells feed zeros (never used again)
-                    if (cv[e] && live) {
-                        cst[e] = gt.y * cst[e] + gt.x * gt.z;
-                        h = gt.w * tanh_fast(cst[e]);
-                    }
-                    // both fp16 planes of h straight into the outgoing chunk: [plane][line][unit slot]
-                    const __half h1 = __float2half_rn(h);
-                    const __half h2 = __float2half_rn((h - __half2float(h1)) * X2_SCALE);
-                    if (cv[e] && live) {
-                        if (p.out) p.out[ooff + e] = h;
-                        if (p.out_hi) { p.out_hi[ooff + e] = h1; p.out_lo[ooff + e] = h2; }
-                    }
-                    __half *cx = reinterpret_cast<__half *>(sxq + (s & 1) * CH_B);
-                    cx[cl * 8 + cj + e] = h1;
-                    cx[(GL + cl) * 8 + cj + e] = h2;
+            for (int t = 0; t < NT; ++t) {
+                float gt[4] = {av[4 * t], av[4 * t + 1], av[4 * t + 2], av[4 * t + 3]};
+                quad_transpose4(gt, gate);                 // now: i, f, g, o of unit u for line 4 t + gate
+                const bool live = s < clen[t];
+                float h = 0.f;                             // finished / padding cells feed zeros (never used again)
+                if (cval[t] && live) {
+                    cst[t] = gt[1] * cst[t] + gt[0] * gt[2];
+                    h = gt[3] * tanh_fast(cst[t]);
                 }
-                if (live) ooff += ostride;
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic writes -> the bulk copy engine (async proxy)
+                // both fp16 planes of h straight into the outgoing block: [plane][line][unit slot]
+                const __half h1 = __float2half_rn(h);
+                const __half h2 = __float2half_rn((h - __half2float(h1)) * X2_SCALE);
+                if (cval[t] && live) {
+                    if (p.out) p.out[ooff[t]] = h;
+                    if (p.out_hi) { p.out_hi[ooff[t]] = h1; p.out_lo[ooff[t]] = h2; }
+                    ooff[t] += ostride;
+                }
+                cx[(4 * t + gate) * 8 + jq] = h1;
+                cx[(LPW + 4 * t + gate) * 8 + jq] = h2;
             }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic writes -> the bulk copy engine (async proxy)
+            __syncwarp();
             const long long e_cell = (p.dbg & 1) ? clock64() : 0;
-            named_bar(bar_id, 64);
-            if (s + 1 < maxlen && sw2 == 0 && lane < LCS) {
-                const uint32_t kc = (uint32_t)rank * 4u + (uint32_t)q;                 // this quarter's k-chunk: unit slots 8 kc .. 8 kc + 7
-                bulk_s2s(dstB + (uint32_t)((g * 2 + nxt) * B_BUF_B) + kc * (uint32_t)CH_B, smem_u32(sxq + (s & 1) * CH_B), (uint32_t)CH_B,
+            if (s + 1 < maxlen && lane < LCS)
+                bulk_s2s(dstB + (uint32_t)((g * 2 + nxt) * B_BUF_B) + kc_off, smem_u32(sxw + (s & 1) * WB_B), (uint32_t)WB_B,
                          dstFull + (uint32_t)(g * 2 + nxt) * 8u);
-            }
             if ((p.dbg & 1) && blockIdx.x == 0 && blockIdx.y == 0 && (warp == 1 || warp == 9) && lane == 0 && s >= 100 && s < 104) {
                 long long *d = p.dbgbuf + ((s - 100) * 2 + g) * 8;
                 d[3] = e_done; d[4] = e_act; d[5] = e_cell; d[6] = clock64(); d[7] = e_top;

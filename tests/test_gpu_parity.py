@@ -109,6 +109,8 @@ def test_cfg1_exact_strings():
         rec = kb.TorchSeqRecognizer(m, device='cuda:0')
         x = torch.from_numpy(g['x'])
         assert rec.predict_string(x) == [str(g['raw_prediction'])]
+        assert rec.outputs is None                       # fused path: only label blocks cross PCIe ...
+        rec.keep_outputs = True                           # ... unless the caller wants `outputs` like the legacy API (models.py:116)
         pred = rec.predict(x)[0]
         assert ''.join(c for c, *_ in pred) == str(g['raw_prediction'])
         assert rec.outputs.shape == g['probs'].shape
