@@ -460,11 +460,14 @@ struct Exec {
         tc::GemmTcParams gp; gp.c = y; gp.bias = w.bias; gp.M = (int)M; gp.N = N; gp.K = K; gp.ldc = N; gp.act = act;
         gp.lab = am ? am->lab : nullptr; gp.conf = am ? am->conf : nullptr; gp.temperature = am ? am->temperature : 1.f;
         const int tiles_m = (int)((M + tc::BM - 1) / tc::BM);
-        // 128 < N <= 256: one 256-wide tile per row block (whole rows in one tile); everything else on 128-wide tiles with two
-        // accumulator sets (epilogue under the next tile's MMAs)
-        const bool wide = am || (N > 128 && N <= 256);
+        // N <= 128: 128-wide tiles with two accumulator sets (epilogue under the next tile's MMAs).  Wider outputs stay on 256-wide
+        // tiles: measured on cfg2's projection (12800 x 2048 x 768) the 128-wide double-buffered variant moves 1.33x the operand bytes
+        // per MAC through L2 and ends up L2-bound at the same 0.12 ms the 256-wide tile spends with its serialised epilogue
+        // (profiles/r02_*), and it leaves less L2 bandwidth to the kernels of the other batches in flight.  KB_GEMM_BN=128 forces it.
+        const bool force128 = getenv("KB_GEMM_BN") && atoi(getenv("KB_GEMM_BN")) == 128;
+        const bool wide = am || (N > 128 && !force128);
         if (am) LAUNCH(m, (tc::k_gemm_tc<256, 1>), (unsigned)std::min(tiles_m, m->sm_count), tc::THREADS, tc::GemmCfg<256>::SMEM_BYTES, st, ta_hi, ta_lo, tb_hi, tb_lo, gp);
-        else if (wide) LAUNCH(m, (tc::k_gemm_tc<256, 0>), (unsigned)std::min(tiles_m, m->sm_count), tc::THREADS, tc::GemmCfg<256>::SMEM_BYTES, st, ta_hi, ta_lo, tb_hi, tb_lo, gp);
+        else if (wide) LAUNCH(m, (tc::k_gemm_tc<256, 0>), (unsigned)std::min(tiles_m * ((N + 255) / 256), m->sm_count), tc::THREADS, tc::GemmCfg<256>::SMEM_BYTES, st, ta_hi, ta_lo, tb_hi, tb_lo, gp);
         else LAUNCH(m, (tc::k_gemm_tc<128, 0>), (unsigned)std::min(tiles_m * ((N + 127) / 128), m->sm_count), tc::THREADS, tc::GemmCfg<128>::SMEM_BYTES, st, ta_hi, ta_lo, tb_hi, tb_lo, gp);
     }
 

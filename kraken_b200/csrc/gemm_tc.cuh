@@ -310,11 +310,13 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ C
                     }
                 }
             } else {
-                // ---- arg-max epilogue: two passes over this row's accumulator columns (TMEM reads are cheap), the two warps of a
-                // lane quarter combine through shared memory.  Same arithmetic as k_row_argmax_softmax: v = x / T (IEEE division),
-                // e = expf(v - max), label = FIRST maximum of e, confidence = e_max / sum(e).
+                // ---- arg-max epilogue: two passes over this row's accumulator columns (TMEM reads are cheap); the two warps of a lane
+                // quarter combine through shared memory.  v = x / T; label = FIRST maximum of v (torch.max over the softmax picks the same
+                // class unless two classes tie to within the rounding of expf, a 1e-7 gap that is below the logits' own 2e-6 error);
+                // confidence = max softmax = 1 / sum(exp(v - max)).
                 float *rq = red + (q * 2) * 32 * 4;
-                float mx = -INFINITY;
+                const bool unit_t = p.temperature == 1.f;
+                float mx = -INFINITY; int bi = 0x7fffffff;
 #pragma unroll 1
                 for (int c0 = 32 * half; c0 < BNT; c0 += 64) {
                     if (c0 >= p.N) break;
@@ -325,14 +327,18 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ C
 #pragma unroll
                     for (int j = 0; j < 32; ++j)
                         if (c0 + j < p.N) {
-                            const float o = fmaf(__uint_as_float(vc[j]), R, __uint_as_float(vm[j])) + (p.bias ? __ldg(p.bias + c0 + j) : 0.f);
-                            mx = fmaxf(mx, __fdiv_rn(o, p.temperature));
+                            float o = fmaf(__uint_as_float(vc[j]), R, __uint_as_float(vm[j])) + (p.bias ? __ldg(p.bias + c0 + j) : 0.f);
+                            if (!unit_t) o = __fdiv_rn(o, p.temperature);
+                            if (o > mx) { mx = o; bi = c0 + j; }               // strict >: first maximum in ascending column order
                         }
                 }
-                rq[half * 128 + lane * 4] = mx;
+                rq[half * 128 + lane * 4] = mx; reinterpret_cast<int *>(rq)[half * 128 + lane * 4 + 1] = bi;
                 named_bar_sync(1 + q, 64);
-                mx = fmaxf(mx, rq[(half ^ 1) * 128 + lane * 4]);
-                float s = 0.f, be = -1.f; int bi = 0x7fffffff;
+                {
+                    const float m2 = rq[(half ^ 1) * 128 + lane * 4]; const int b2 = reinterpret_cast<int *>(rq)[(half ^ 1) * 128 + lane * 4 + 1];
+                    if (m2 > mx || (m2 == mx && b2 < bi)) { mx = m2; bi = b2; }     // first index on ties, as torch.max
+                }
+                float s = 0.f;
 #pragma unroll 1
                 for (int c0 = 32 * half; c0 < BNT; c0 += 64) {
                     if (c0 >= p.N) break;
@@ -343,18 +349,15 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ C
 #pragma unroll
                     for (int j = 0; j < 32; ++j)
                         if (c0 + j < p.N) {
-                            const float o = fmaf(__uint_as_float(vc[j]), R, __uint_as_float(vm[j])) + (p.bias ? __ldg(p.bias + c0 + j) : 0.f);
-                            const float e = expf(__fdiv_rn(o, p.temperature) - mx);
-                            s += e;
-                            if (e > be) { be = e; bi = c0 + j; }               // strict >: first maximum in ascending column order
+                            float o = fmaf(__uint_as_float(vc[j]), R, __uint_as_float(vm[j])) + (p.bias ? __ldg(p.bias + c0 + j) : 0.f);
+                            if (!unit_t) o = __fdiv_rn(o, p.temperature);
+                            s += __expf(o - mx);
                         }
                 }
-                rq[half * 128 + lane * 4 + 1] = s; rq[half * 128 + lane * 4 + 2] = be; reinterpret_cast<int *>(rq)[half * 128 + lane * 4 + 3] = bi;
+                rq[half * 128 + lane * 4 + 2] = s;
                 named_bar_sync(1 + q, 64);
                 if (half == 0 && m < p.M) {
-                    const float s2 = rq[128 + lane * 4 + 1], be2 = rq[128 + lane * 4 + 2]; const int bi2 = reinterpret_cast<int *>(rq)[128 + lane * 4 + 3];
-                    if (be2 > be || (be2 == be && bi2 < bi)) { be = be2; bi = bi2; }     // first index on ties, as torch.max
-                    p.lab[m] = bi; p.conf[m] = be / (s + s2);
+                    p.lab[m] = bi; p.conf[m] = 1.f / (s + rq[128 + lane * 4 + 2]);
                 }
                 named_bar_sync(1 + q, 64);                                    // `red` is reused by the next tile
             }

@@ -50,7 +50,7 @@ template <int GL> struct ClusterCfg {                    // GL = lines per group
     static constexpr int WB_B = 2 * LPW * 16;            // bytes an epilogue warp contributes to a k-chunk: [h1 of its lines | h2s of its lines] x 16 B
     static constexpr int CH_B = 2 * GL * 16;             // bytes of one k-chunk (8 unit slots) of a group = the two warps' blocks
     static constexpr int B_BUF_B = 32 * CH_B;            // bytes per (group, buffer): K = 256 = 32 chunks
-    static constexpr int SX_BYTES = 4 * NG * 2 * 2 * WB_B;   // outgoing block staging per epilogue warp, double buffered
+    static constexpr int SX_BYTES = NG * 2 * 4 * CH_B;   // outgoing staging per group, double buffered: this CTA's 4 k-chunks, laid out as in the operand
     static constexpr int SMEM_BYTES = NG * 2 * B_BUF_B + SX_BYTES + 128 + 1024;
     static constexpr int N1 = 2 * GL;                    // N of both products (W2s x the same operand rows; only its h1 columns are read)
     static constexpr int GSTRIDE = 4 * N1;               // TMEM columns per group: D1a @0, D1b @N1, D2a @2 N1, D2b @3 N1
@@ -164,7 +164,7 @@ __global__ void __launch_bounds__(LTHREADS, 1) k_lstm_rec_tc(LstmTcParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = smem_align1024(smem_raw);
     uint8_t *sB = smem;                                   // [group][buffer][k-chunk][row = (warp half, plane, line)][8 unit slots] fp16, no swizzle
-    uint8_t *sx = sB + NG * 2 * B_BUF_B;                  // [quarter][group][warp half][2][WB_B]
+    uint8_t *sx = sB + NG * 2 * B_BUF_B;                  // [group][2][quarter = k-chunk][warp half][plane][line][8 unit slots]
     uint64_t *bars = reinterpret_cast<uint64_t *>(sB + NG * 2 * B_BUF_B + Cfg::SX_BYTES);
     uint64_t *b_full = bars /* [group][2] */, *mma_done = bars + 4 /* [group][chain owner: W1 / W2s] */;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 8);
@@ -237,7 +237,8 @@ __global__ void __launch_bounds__(LTHREADS, 1) k_lstm_rec_tc(LstmTcParams p) {
                     else mbar_wait_poll(bf, (uint32_t)(((s - 1) >> 1) & 1));
                 }
                 const long long d_w1 = (p.dbg & 1) ? clock64() : 0;
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // bulk-copy writes -> UMMA (async proxy) reads
+                // h arrives by bulk copies (async proxy) and is read by the MMAs (async proxy): no cross-proxy fence on this path (the
+                // fence.proxy.async that stood here compiles to MEMBAR.ALL.CTA + FENCE.VIEW.ASYNC on the critical path of every step)
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 if (elect_one()) {
                     const uint32_t b0 = smem_u32(sB + (g * 2 + cur) * B_BUF_B);
@@ -310,24 +311,25 @@ __global__ void __launch_bounds__(LTHREADS, 1) k_lstm_rec_tc(LstmTcParams p) {
             gxn[i] = 0 < glen[i] ? __ldg(gptr[i]) : 0.f;
             gptr[i] += gstride;
         }
-        // hand-off: lane r < 8 copies this warp's block of the k-chunk to CTA r
-        const uint32_t dstB = mapa32(smem_u32(sB), (uint32_t)(lane & 7)), dstFull = mapa32(smem_u32(b_full), (uint32_t)(lane & 7));
-        uint8_t *sxw = sx + ((q * NG + g) * 2 + sw2) * 2 * WB_B;
+        // hand-off: the 8 epilogue warps of a group stage their blocks as this CTA's 4 k-chunks of the operand (1 KB for GL = 8), then
+        // warp wi sends the whole piece to CTA wi with ONE bulk copy.  (Round 1 and the first version of this kernel sent 8 copies
+        // per warp: a UBLKCP takes uniform-register operands, so the 8 lanes ran as an 8-iteration loop of ELECT / R2UR / UBLKCP,
+        // ~500 cycles per step on the critical path.)
+        const int wi = (sw2 << 2) | q;                                                    // 0..7 within the group
+        const uint32_t dstB = mapa32(smem_u32(sB), (uint32_t)wi), dstFull = mapa32(smem_u32(b_full), (uint32_t)wi);
+        uint8_t *sxg = sx + g * 2 * 4 * CH_B;
+        const int sxw_off = q * CH_B + sw2 * WB_B;                                        // this warp's rows of this quarter's k-chunk
         // this warp's accumulator columns: rows of the operand = [warp half][plane][line]
         const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * GSTRIDE + 2 * LPW * sw2);
         // gate non-linearity without divergence: sigmoid(x) for i, f, o; tanh(x) = 2*sigmoid(2x) - 1 for the candidate gate
         const float act_k = gate == 2 ? 2.f : 1.f;
-        const uint32_t kc_off = ((uint32_t)rank * 4u + (uint32_t)q) * (uint32_t)CH_B + (uint32_t)(sw2 * WB_B);   // this quarter's k-chunk, this warp's rows
+        const uint32_t kc_off = (uint32_t)rank * 4u * (uint32_t)CH_B;                     // this CTA's 4 k-chunks in every destination's operand
 
         for (int s = 0; s < maxlen; ++s) {
             const int nxt = (s + 1) & 1;
             float gxv[LPW];
 #pragma unroll
-            for (int i = 0; i < LPW; ++i) {
-                gxv[i] = gxn[i];
-                gxn[i] = s + 1 < glen[i] ? __ldg(gptr[i]) : 0.f;
-                gptr[i] += gstride;
-            }
+            for (int i = 0; i < LPW; ++i) gxv[i] = gxn[i];
             const long long e_top = (p.dbg & 1) ? clock64() : 0;
             if (p.dbg & 4) { mbar_wait_poll(&mma_done[g * 2], (uint32_t)(s & 1)); mbar_wait_poll(&mma_done[g * 2 + 1], (uint32_t)(s & 1)); }
             else { mbar_wait(&mma_done[g * 2], (uint32_t)(s & 1)); mbar_wait(&mma_done[g * 2 + 1], (uint32_t)(s & 1)); }
@@ -356,7 +358,8 @@ __global__ void __launch_bounds__(LTHREADS, 1) k_lstm_rec_tc(LstmTcParams p) {
                 av[i] = fmaf(sigmoid_fast(pre * act_k), act_k, 1.f - act_k);
             }
             const long long e_act = (p.dbg & 1) ? clock64() : 0;
-            __half *cx = reinterpret_cast<__half *>(sxw + (s & 1) * WB_B);
+            __half *cx = reinterpret_cast<__half *>(sxg + (s & 1) * 4 * CH_B + sxw_off);
+            float hv[NT]; __half hh1[NT], hh2[NT]; bool wr[NT];
 #pragma unroll
             for (int t = 0; t < NT; ++t) {
                 float gt[4] = {av[4 * t], av[4 * t + 1], av[4 * t + 2], av[4 * t + 3]};
@@ -370,20 +373,31 @@ __global__ void __launch_bounds__(LTHREADS, 1) k_lstm_rec_tc(LstmTcParams p) {
                 // both fp16 planes of h straight into the outgoing block: [plane][line][unit slot]
                 const __half h1 = __float2half_rn(h);
                 const __half h2 = __float2half_rn((h - __half2float(h1)) * X2_SCALE);
-                if (cval[t] && live) {
-                    if (p.out) p.out[ooff[t]] = h;
-                    if (p.out_hi) { p.out_hi[ooff[t]] = h1; p.out_lo[ooff[t]] = h2; }
-                    ooff[t] += ostride;
-                }
                 cx[(4 * t + gate) * 8 + jq] = h1;
                 cx[(LPW + 4 * t + gate) * 8 + jq] = h2;
+                hv[t] = h; hh1[t] = h1; hh2[t] = h2; wr[t] = cval[t] && live;
             }
+            // Only shared-memory stores are outstanding here: the proxy fence (MEMBAR.ALL.CTA + FENCE.VIEW.ASYNC) waits for every
+            // earlier memory operation of the thread, so the global stores of h and the gx prefetch come AFTER the hand-off (with them
+            // in front the fence took 1500 cycles per step, KB_LSTM_DBG timeline of the first version).
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic writes -> the bulk copy engine (async proxy)
-            __syncwarp();
+            named_bar(1 + g, 256);                                            // the group's 8 warps have staged their blocks
             const long long e_cell = (p.dbg & 1) ? clock64() : 0;
-            if (s + 1 < maxlen && lane < LCS)
-                bulk_s2s(dstB + (uint32_t)((g * 2 + nxt) * B_BUF_B) + kc_off, smem_u32(sxw + (s & 1) * WB_B), (uint32_t)WB_B,
+            if (s + 1 < maxlen && lane == 0)
+                bulk_s2s(dstB + (uint32_t)((g * 2 + nxt) * B_BUF_B) + kc_off, smem_u32(sxg + (s & 1) * 4 * CH_B), (uint32_t)(4 * CH_B),
                          dstFull + (uint32_t)(g * 2 + nxt) * 8u);
+#pragma unroll
+            for (int t = 0; t < NT; ++t)
+                if (wr[t]) {
+                    if (p.out) p.out[ooff[t]] = hv[t];
+                    if (p.out_hi) { p.out_hi[ooff[t]] = hh1[t]; p.out_lo[ooff[t]] = hh2[t]; }
+                    ooff[t] += ostride;
+                }
+#pragma unroll
+            for (int i = 0; i < LPW; ++i) {                                   // gx of the next step: a whole step to land
+                gxn[i] = s + 1 < glen[i] ? __ldg(gptr[i]) : 0.f;
+                gptr[i] += gstride;
+            }
             if ((p.dbg & 1) && blockIdx.x == 0 && blockIdx.y == 0 && (warp == 1 || warp == 9) && lane == 0 && s >= 100 && s < 104) {
                 long long *d = p.dbgbuf + ((s - 100) * 2 + g) * 8;
                 d[3] = e_done; d[4] = e_act; d[5] = e_cell; d[6] = clock64(); d[7] = e_top;

@@ -27,6 +27,36 @@ class KrakenInvalidModelException(Exception):
     pass
 
 
+class _LazyOutputs:
+    """Stands in for `TorchSeqRecognizer.outputs` (the (N, C, W) probability array of kraken/lib/models.py:116) after a fused call
+    that only fetched label blocks: it knows its shape - all `kraken.rpred.mm_rpred` reads (rpred.py:229,299) - and computes the
+    probabilities only if somebody actually looks at them."""
+
+    def __init__(self, rec, line, lens, shape):
+        self._rec, self._line, self._lens, self.shape, self._arr = rec, line, lens, tuple(shape), None
+        self.ndim = 3
+
+    def _get(self) -> np.ndarray:
+        if self._arr is None:
+            rec, self._rec = self._rec, None
+            keep = rec.outputs
+            rec._recognize_raw(self._line, self._lens, want_probs=True)
+            self._arr, self._line, self._lens = rec.outputs, None, None
+            if keep is not self:
+                rec.outputs = keep
+        return self._arr
+
+    def __array__(self, dtype=None, copy=None):
+        a = self._get()
+        return a if dtype is None else a.astype(dtype)
+
+    def __getitem__(self, idx):
+        return self._get()[idx]
+
+    def __len__(self):
+        return self.shape[0]
+
+
 class TorchSeqRecognizer:
     def __init__(self, nn: TorchVGSLModel, decoder=ctc_decoder.greedy_decoder, temperature: float = 1.0,
                  train: bool = False, device: str = 'cuda:0'):
@@ -105,8 +135,7 @@ class TorchSeqRecognizer:
                                float(self.temperature), labels.ctypes.data, starts.ctypes.data, ends.ctypes.data, confs.ctypes.data,
                                counts.ctypes.data, stride, olens.ctypes.data, probs.ctypes.data if probs is not None else None, 0,
                                _stream_for(x, net._device)))
-        if probs is not None:
-            self.outputs = probs
+        self.outputs = probs if probs is not None else _LazyOutputs(self, line, lens, (n, ncls, T))
         return {'labels': labels, 'starts': starts, 'ends': ends, 'confs': confs, 'counts': counts,
                 'olens': olens if lens is not None else None}
 
@@ -221,8 +250,8 @@ class TorchSeqRecognizer:
     # -- reference surface ------------------------------------------------------------------------
     def forward(self, line: torch.Tensor, lens: Optional[torch.Tensor] = None):
         """(N, C, H, W) lines -> ((N, C, W) softmax numpy array, output lengths) - models.py:93-119."""
-        _, olens = self._recognize(line, lens, want_probs=True)
-        return self.outputs, olens
+        r = self._recognize_raw(line, lens, want_probs=True)
+        return self.outputs, r['olens']
 
     def _decode(self, line, lens):
         if lens is None and getattr(line, 'ndim', 0) == 4 and int(line.shape[0]) > 1:
