@@ -27,7 +27,7 @@ namespace ctc {
 using namespace kb::tc;
 
 constexpr int TW = 128;                  // output columns per work item
-constexpr int MAX_STB = 4;               // weight-tile ring stages
+constexpr int MAX_STB = 8;               // weight-tile ring stages (as many as fit next to the row buffers, at least 4)
 constexpr int PIX_B = 64;                // bytes of one pixel row of a plane: 32 channels x fp16
 constexpr int CEPI_WARPS = 8;             // two per TMEM lane quarter: even / odd 32-channel chunks
 constexpr int CTHREADS = 64 + CEPI_WARPS * 32;
@@ -42,6 +42,7 @@ struct ConvTcParams {
     int out_h, out_w;                    // valid output extent (pooled when pool)
     int a_row_bytes;                     // bytes of one plane of one input-row buffer (multiple of 1024)
     int acc_sets;
+    int a_sets;                          // 2: the input rows of the NEXT (item, chunk) load while the current one is multiplied
 };
 
 __device__ __forceinline__ void tma_load_4d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2, int c3) {
@@ -58,9 +59,10 @@ k_conv_tc(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ C
     const int a_plane = p.a_row_bytes, a_row = 2 * a_plane;              // hi | lo
     const int CT = p.CT, NSTB = p.nstb;
     const int b_plane = CT * PIX_B, b_stage = 2 * b_plane;
-    uint8_t *a_base = smem, *b_base = smem + R * a_row;
+    const int ASETS = p.a_sets;
+    uint8_t *a_base = smem, *b_base = smem + ASETS * R * a_row;
     uint64_t *bars = reinterpret_cast<uint64_t *>(b_base + NSTB * b_stage);
-    uint64_t *full_a = bars, *empty_a = bars + MAX_ROWS, *full_b = bars + 2 * MAX_ROWS, *empty_b = full_b + MAX_STB;
+    uint64_t *full_a = bars /* [2][MAX_ROWS] */, *empty_a = bars + 2 * MAX_ROWS, *full_b = bars + 4 * MAX_ROWS, *empty_b = full_b + MAX_STB;
     uint64_t *tfull = empty_b + MAX_STB, *tempty = tfull + 2;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty + 2);
 
@@ -69,7 +71,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ C
     const uint32_t a_tx = (uint32_t)(2 * (TW + p.kw - 1) * PIX_B), b_tx = (uint32_t)b_stage;
 
     if (threadIdx.x == 0) {
-        for (int r = 0; r < R; ++r) { mbar_init(&full_a[r], 1); mbar_init(&empty_a[r], 1); }
+        for (int r = 0; r < 2 * MAX_ROWS; ++r) { mbar_init(&full_a[r], 1); mbar_init(&empty_a[r], 1); }
         for (int s = 0; s < NSTB; ++s) { mbar_init(&full_b[s], 1); mbar_init(&empty_b[s], 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], CEPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -86,20 +88,22 @@ k_conv_tc(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ C
     if (warp == 0) {
         // ===================== TMA producer =====================
         if (elect_one()) {
-            uint32_t a_phase = 0; int bs = 0; uint32_t b_phase = 0;
+            uint32_t a_phase = 0; int aset = 0; int bs = 0; uint32_t b_phase = 0;
             for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
                 const int ct = item % p.items_c; int rest = item / p.items_c;
                 const int ws = rest % p.items_w, hp = (rest / p.items_w) % p.items_h, n = rest / (p.items_w * p.items_h);
                 const int h0 = 2 * hp - p.py, w0 = ws * TW - p.px;
                 for (int cc = 0; cc < p.NC; ++cc) {
                     int r_loaded = 0;
+                    uint8_t *aset_base = a_base + aset * R * a_row;
+                    uint64_t *fa = full_a + aset * MAX_ROWS, *ea = empty_a + aset * MAX_ROWS;
                     // interleave: input row r is needed from tap row ky = r - 1 on; weight tiles in (ky, kx) order
                     for (int ky = 0; ky < p.kh; ++ky) {
                         for (; r_loaded <= ky + 1; ++r_loaded) {
-                            mbar_wait(&empty_a[r_loaded], a_phase ^ 1);
-                            mbar_expect_tx(&full_a[r_loaded], a_tx);
-                            tma_load_4d(a_base + r_loaded * a_row, &tm_x_hi, &full_a[r_loaded], cc * 32, w0, h0 + r_loaded, n);
-                            tma_load_4d(a_base + r_loaded * a_row + a_plane, &tm_x_lo, &full_a[r_loaded], cc * 32, w0, h0 + r_loaded, n);
+                            mbar_wait(&ea[r_loaded], a_phase ^ 1);
+                            mbar_expect_tx(&fa[r_loaded], a_tx);
+                            tma_load_4d(aset_base + r_loaded * a_row, &tm_x_hi, &fa[r_loaded], cc * 32, w0, h0 + r_loaded, n);
+                            tma_load_4d(aset_base + r_loaded * a_row + a_plane, &tm_x_lo, &fa[r_loaded], cc * 32, w0, h0 + r_loaded, n);
                         }
                         for (int kx = 0; kx < p.kw; ++kx) {
                             mbar_wait(&empty_b[bs], b_phase ^ 1);
@@ -110,22 +114,29 @@ k_conv_tc(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ C
                             if (++bs == NSTB) { bs = 0; b_phase ^= 1; }
                         }
                     }
-                    a_phase ^= 1;
+                    if (ASETS == 2) { if (++aset == 2) { aset = 0; a_phase ^= 1; } }
+                    else a_phase ^= 1;
                 }
             }
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
-        const uint32_t idesc = idesc_f16(0, 0, 128, CT);
-        uint32_t a_phase = 0; int bs = 0; uint32_t b_phase = 0; int acc = 0; uint32_t acc_phase = 0;
+        // per (tap, K16 step) and output row TWO MMAs: a1 x [b1 | b2s] (N = 2 CT: the hi and lo weight planes of a ring stage are
+        // contiguous rows of one K-major tile) -> [main | corr], then a2s x b1 (N = CT) -> corr.  Round 1 issued three N = CT MMAs;
+        // at CT = 64 each of those reads 6 KB of operands for 32 cycles of tensor work, 1.5x the shared-memory bandwidth.
+        const uint32_t idesc = idesc_f16(0, 0, 128, CT), idesc2 = idesc_f16(0, 0, 128, 2 * CT);
+        const bool merged = 2 * CT <= 256;
+        uint32_t a_phase = 0; int aset = 0; int bs = 0; uint32_t b_phase = 0; int acc = 0; uint32_t acc_phase = 0;
         for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
             mbar_wait(&tempty[acc], acc_phase ^ 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t d0 = tmem_base + (uint32_t)(acc * 4 * CT);
             for (int cc = 0; cc < p.NC; ++cc) {
+                uint8_t *aset_base = a_base + aset * R * a_row;
+                uint64_t *fa = full_a + aset * MAX_ROWS, *ea = empty_a + aset * MAX_ROWS;
                 for (int ky = 0; ky < p.kh; ++ky) {
-                    if (ky == 0) mbar_wait(&full_a[0], a_phase);
-                    mbar_wait(&full_a[ky + 1], a_phase);
+                    if (ky == 0) mbar_wait(&fa[0], a_phase);
+                    mbar_wait(&fa[ky + 1], a_phase);
                     for (int kx = 0; kx < p.kw; ++kx) {
                         mbar_wait(&full_b[bs], b_phase);
                         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -135,29 +146,35 @@ k_conv_tc(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ C
                             const bool first = (cc | ky | kx) == 0;
 #pragma unroll
                             for (int r = 0; r < 2; ++r) {
-                                const uint32_t sa = smem_u32(a_base + (ky + r) * a_row) + (uint32_t)(kx * PIX_B);
+                                const uint32_t sa = smem_u32(aset_base + (ky + r) * a_row) + (uint32_t)(kx * PIX_B);
                                 const uint64_t a_hi = umma_desc_sw64(sa), a_lo = umma_desc_sw64(sa + a_plane);
                                 const uint32_t d_main = d0 + (uint32_t)(2 * r * CT), d_corr = d_main + (uint32_t)CT;
 #pragma unroll
                                 for (int k = 0; k < 2; ++k) {                     // 32 channels = 2 x K16
                                     const uint64_t adv = (uint64_t)((k * 32) >> 4);
-                                    umma_f16(d_corr, a_lo + adv, b_hi + adv, idesc, (first && k == 0) ? 0u : 1u);
-                                    umma_f16(d_corr, a_hi + adv, b_lo + adv, idesc, 1u);
-                                    umma_f16(d_main, a_hi + adv, b_hi + adv, idesc, (first && k == 0) ? 0u : 1u);
+                                    if (merged) {
+                                        umma_f16(d_main, a_hi + adv, b_hi + adv, idesc2, (first && k == 0) ? 0u : 1u);     // [main | corr]
+                                        umma_f16(d_corr, a_lo + adv, b_hi + adv, idesc, 1u);
+                                    } else {
+                                        umma_f16(d_corr, a_lo + adv, b_hi + adv, idesc, (first && k == 0) ? 0u : 1u);
+                                        umma_f16(d_corr, a_hi + adv, b_lo + adv, idesc, 1u);
+                                        umma_f16(d_main, a_hi + adv, b_hi + adv, idesc, (first && k == 0) ? 0u : 1u);
+                                    }
                                 }
                             }
                             umma_commit(&empty_b[bs]);
                             if (kx == p.kw - 1) {
                                 // input row buffers whose last reader (for this chunk) was this tap row: row ky (and kh when ky == kh-1)
-                                umma_commit(&empty_a[ky]);
-                                if (ky == p.kh - 1) { umma_commit(&empty_a[p.kh]); if (cc == p.NC - 1) umma_commit(&tfull[acc]); }
+                                umma_commit(&ea[ky]);
+                                if (ky == p.kh - 1) { umma_commit(&ea[p.kh]); if (cc == p.NC - 1) umma_commit(&tfull[acc]); }
                             }
                         }
                         __syncwarp();
                         if (++bs == NSTB) { bs = 0; b_phase ^= 1; }
                     }
                 }
-                a_phase ^= 1;
+                if (ASETS == 2) { if (++aset == 2) { aset = 0; a_phase ^= 1; } }
+                else a_phase ^= 1;
             }
             if (p.acc_sets == 2) { if (++acc == 2) { acc = 0; acc_phase ^= 1; } }
             else acc_phase ^= 1;
@@ -268,15 +285,21 @@ inline bool make_map_nhwc(CUtensorMap *map, const __half *base, uint64_t N, uint
                CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-// output-channel tile and weight-ring depth for a layer; returns the dynamic shared memory the kernel needs
-inline size_t conv_tc_plan(int kh, int kw, int cout, int *ct_out, int *nstb_out, int *a_row_bytes) {
+// output-channel tile, weight-ring depth and input-row buffering for a layer; returns the dynamic shared memory the kernel needs.
+// Preference: two sets of input rows (the next item's rows load under the current item's MMAs: with one set the issuer stalled for a
+// TMA round trip at every item boundary), then as deep a weight ring as still fits (a tap's tile feeds only 12 MMAs).
+inline size_t conv_tc_plan(int kh, int kw, int cout, int *ct_out, int *nstb_out, int *a_row_bytes, int *a_sets_out = nullptr) {
     const int ct = cout <= 128 ? cout : (cout % 128 == 0 ? 128 : (cout % 64 == 0 ? 64 : 32));
-    const int nstb = MAX_STB;
     const int plane = ((TW + kw - 1) * PIX_B + 1023) & ~1023;
+    const size_t rows = (size_t)(kh + 1) * 2 * plane, stage = (size_t)2 * ct * PIX_B, fixed = 512 + 1024, cap = 227 * 1024;
+    int a_sets = 2, nstb = MAX_STB;
+    if (2 * rows + 4 * stage + fixed > cap) a_sets = 1;
+    while (nstb > 4 && a_sets * rows + nstb * stage + fixed > cap) --nstb;
     if (ct_out) *ct_out = ct;
     if (nstb_out) *nstb_out = nstb;
     if (a_row_bytes) *a_row_bytes = plane;
-    return (size_t)(kh + 1) * 2 * plane + (size_t)nstb * 2 * ct * PIX_B + 512 + 1024;
+    if (a_sets_out) *a_sets_out = a_sets;
+    return a_sets * rows + nstb * stage + fixed;
 }
 
 }  // namespace ctc

@@ -656,18 +656,18 @@ struct Exec {
                     tcfg.attrs = tat; tcfg.numAttrs = 1;
                     if (getenv("KB_DEBUG")) fprintf(stderr, "[kb] %s: tcgen05 recurrence, %u clusters of 8 CTAs x %d lines, T=%d\n", n.name.c_str(), tcfg.gridDim.x / 8 * dirs, nl, lp.T);
                     tp.dbgbuf = nullptr;
-                    if (tp.dbg & 1) { CK(cudaMalloc((void **)&tp.dbgbuf, 64 * sizeof(long long))); CK(cudaMemset(tp.dbgbuf, 0, 64 * sizeof(long long))); }
+                    if (tp.dbg & 1) { CK(cudaMalloc((void **)&tp.dbgbuf, 96 * sizeof(long long))); CK(cudaMemset(tp.dbgbuf, 0, 96 * sizeof(long long))); }
                     if (gl == 16) CK(cudaLaunchKernelEx(&tcfg, ltc::k_lstm_rec_tc<16>, tp));
                     else CK(cudaLaunchKernelEx(&tcfg, ltc::k_lstm_rec_tc<8>, tp));
                     if (tp.dbg & 1) {
-                        long long hb[64];
+                        long long hb[96];
                         CK(cudaMemcpy(hb, tp.dbgbuf, sizeof(hb), cudaMemcpyDeviceToHost));
                         cudaFree(tp.dbgbuf);
                         const long long t0 = hb[1];
                         for (int i = 0; i < 8; ++i) {
                             const long long *d = hb + i * 8;
-                            fprintf(stderr, "[tcrec] step %d group %d: mma_wait_from %lld  h_ready %lld  mma_issued %lld | epi_loop_top %lld  mma_done %lld  act_end %lld  cell_end %lld  sent %lld\n",
-                                    100 + i / 2, i & 1, d[0] - t0, d[1] - t0, d[2] - t0, d[7] - t0, d[3] - t0, d[4] - t0, d[5] - t0, d[6] - t0);
+                            fprintf(stderr, "[tcrec] step %d group %d: mma_wait_from %lld  h_ready %lld  mma_issued %lld | epi_loop_top %lld  mma_done %lld  act_end %lld  staged %lld  fenced %lld  barrier(cell_end) %lld  sent %lld\n",
+                                    100 + i / 2, i & 1, d[0] - t0, d[1] - t0, d[2] - t0, d[7] - t0, d[3] - t0, d[4] - t0, hb[64 + 2 * i] - t0, hb[65 + 2 * i] - t0, d[5] - t0, d[6] - t0);
                         }
                     }
                     ++m->launches;
@@ -864,7 +864,7 @@ struct Exec {
             cp.items_h = (int)((dconv.h + 1) / 2);
             cp.items_w = (int)((dconv.w + ctc::TW - 1) / ctc::TW);
             cp.sN = dconv.h * dconv.w * dconv.c; cp.sH = dconv.w * dconv.c; cp.sW = dconv.c;
-            const size_t smem = ctc::conv_tc_plan(w.s_th, w.s_tw, c0.cout, &cp.CT, &cp.nstb, &cp.a_row_bytes);
+            const size_t smem = ctc::conv_tc_plan(w.s_th, w.s_tw, c0.cout, &cp.CT, &cp.nstb, &cp.a_row_bytes, &cp.a_sets);
             cp.NC = cs / 32; cp.items_c = c0.cout / cp.CT;
             cp.acc_sets = 8 * cp.CT <= 512 ? 2 : 1;
             CUtensorMap tx_hi, tx_lo, tw_hi, tw_lo;
@@ -916,7 +916,7 @@ struct Exec {
             cp.items_w = (int)((dconv.w + ctc::TW - 1) / ctc::TW);
             if (fd) { cp.sN = dpost.w * dpost.h * dpost.c; cp.sW = dpost.h * dpost.c; cp.sH = dpost.c; }
             else { cp.sN = dpost.h * dpost.w * dpost.c; cp.sH = dpost.w * dpost.c; cp.sW = dpost.c; }
-            const size_t smem = ctc::conv_tc_plan(c0.kh, c0.kw, c0.cout, &cp.CT, &cp.nstb, &cp.a_row_bytes);
+            const size_t smem = ctc::conv_tc_plan(c0.kh, c0.kw, c0.cout, &cp.CT, &cp.nstb, &cp.a_row_bytes, &cp.a_sets);
             cp.NC = c0.cin / 32; cp.items_c = c0.cout / cp.CT;
             cp.acc_sets = 8 * cp.CT <= 512 ? 2 : 1;
             CUtensorMap tx_hi, tx_lo, tw_hi, tw_lo;

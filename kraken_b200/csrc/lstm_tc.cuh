@@ -377,10 +377,12 @@ __global__ void __launch_bounds__(LTHREADS, 1) k_lstm_rec_tc(LstmTcParams p) {
                 cx[(LPW + 4 * t + gate) * 8 + jq] = h2;
                 hv[t] = h; hh1[t] = h1; hh2[t] = h2; wr[t] = cval[t] && live;
             }
+            const long long e_sts = (p.dbg & 1) ? clock64() : 0;
             // Only shared-memory stores are outstanding here: the proxy fence (MEMBAR.ALL.CTA + FENCE.VIEW.ASYNC) waits for every
             // earlier memory operation of the thread, so the global stores of h and the gx prefetch come AFTER the hand-off (with them
             // in front the fence took 1500 cycles per step, KB_LSTM_DBG timeline of the first version).
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic writes -> the bulk copy engine (async proxy)
+            const long long e_fence = (p.dbg & 1) ? clock64() : 0;
             named_bar(1 + g, 256);                                            // the group's 8 warps have staged their blocks
             const long long e_cell = (p.dbg & 1) ? clock64() : 0;
             if (s + 1 < maxlen && lane == 0)
@@ -401,6 +403,7 @@ __global__ void __launch_bounds__(LTHREADS, 1) k_lstm_rec_tc(LstmTcParams p) {
             if ((p.dbg & 1) && blockIdx.x == 0 && blockIdx.y == 0 && (warp == 1 || warp == 9) && lane == 0 && s >= 100 && s < 104) {
                 long long *d = p.dbgbuf + ((s - 100) * 2 + g) * 8;
                 d[3] = e_done; d[4] = e_act; d[5] = e_cell; d[6] = clock64(); d[7] = e_top;
+                p.dbgbuf[64 + ((s - 100) * 2 + g) * 2] = e_sts; p.dbgbuf[64 + ((s - 100) * 2 + g) * 2 + 1] = e_fence;
             }
         }
     }

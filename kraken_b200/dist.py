@@ -18,7 +18,8 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
-__all__ = ['shard_batches', 'broadcast_state_dict', 'gather_decoded', 'recognize_sharded']
+__all__ = ['shard_batches', 'broadcast_state_dict', 'gather_decoded', 'recognize_sharded', 'bind_to_gpu_numa', 'ResultBlocks',
+           'recognize_sharded_blocks']
 
 
 def shard_batches(widths: Sequence[int], world_size: int, batch_size: int, mode: str = 'arrival') -> list[list[list[int]]]:
@@ -133,3 +134,82 @@ def recognize_sharded(recognize_batch: Callable, lines: Sequence[torch.Tensor], 
     if stride is None:
         stride = max(1, max(widths) if widths else 1)
     return gather_decoded(idxs, decs, len(lines), stride, dst=dst, device=device)
+
+
+# ---- throughput path: result blocks instead of Python tuples ---------------------------------------------------------------------
+def bind_to_gpu_numa(device_index: int) -> Optional[list]:
+    """Restricts this process to the CPU cores that are local to GPU `device_index` (NVML's ideal CPU affinity, intersected with
+    the cores the process may use) - call it before pinned buffers are allocated and before worker threads start, so that the
+    staging memory is first-touched on the GPU's NUMA node and the H2D copies do not cross the socket interconnect.  Returns the
+    core list, or None when NVML / affinity control is unavailable (nothing is changed then)."""
+    import os
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        cvd = [x for x in os.environ.get('CUDA_VISIBLE_DEVICES', '').split(',') if x.strip() != '']
+        idx = int(cvd[device_index]) if cvd and cvd[device_index].isdigit() else device_index
+        h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        ideal = {64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1}
+        allowed = os.sched_getaffinity(0)
+        cores = sorted(ideal & allowed)
+        if not cores:
+            return None
+        os.sched_setaffinity(0, cores)
+        return cores
+    except Exception:
+        return None
+
+
+class ResultBlocks:
+    """The decoded label blocks of a run of `nbatches` batches of `batch` lines in ONE pinned int32 buffer
+    [batch index][counts (B) | labels (B x stride) | starts | ends | confs (float32 bits)]: the engine writes every batch straight
+    into its slice (`views(i)` are the arrays `TorchSeqRecognizer.collect(out=...)` / `_recognize_raw(out=...)` take) and the run's
+    single gather ships the buffer as it is."""
+
+    def __init__(self, nbatches: int, batch: int, stride: int, pin: bool = True):
+        self.nbatches, self.batch, self.stride = nbatches, batch, stride
+        self.words = batch * (1 + 4 * stride)
+        self.t = torch.empty((max(nbatches, 1), self.words), dtype=torch.int32)
+        if pin and torch.cuda.is_available():
+            self.t = self.t.pin_memory()
+        self.a = self.t.numpy()
+
+    def views(self, i: int) -> dict:
+        b, o, bt = self.a[i], self.batch, self.batch * self.stride
+        shp = (self.batch, self.stride)
+        return {'counts': b[:o], 'labels': b[o:o + bt].reshape(shp), 'starts': b[o + bt:o + 2 * bt].reshape(shp),
+                'ends': b[o + 2 * bt:o + 3 * bt].reshape(shp), 'confs': b[o + 3 * bt:o + 4 * bt].view(np.float32).reshape(shp)}
+
+    def gather(self, dst: int = 0, device: Optional[torch.device] = None):
+        """ONE collective for the whole run (NCCL gather over NVLink when `device` is a CUDA device; gloo on CPU tensors).  Returns the
+        list of all ranks' buffers on `dst`, None elsewhere.  Every rank must hold the same number of batches."""
+        world, rank = dist.get_world_size(), dist.get_rank()
+        t = self.t.to(device, non_blocking=True) if device is not None else self.t
+        out = [torch.empty_like(t) for _ in range(world)] if rank == dst else None
+        dist.gather(t, out, dst=dst)
+        return out
+
+
+def recognize_sharded_blocks(rec, my_batches: Sequence, stride: int, depth: int = 4, device: Optional[torch.device] = None, dst: int = 0,
+                             blocks: Optional[ResultBlocks] = None):
+    """This rank's share of a job: `my_batches` = [(lines[B,C,H,W], lens)] (host pinned or device tensors, all with the same B) go
+    through the engine's asynchronous pipeline (`depth` batches in flight from this one thread), results land in a `ResultBlocks`
+    buffer, and ONE gather delivers every rank's buffer to `dst`.  No collective on the data path.  Returns (blocks, gathered)."""
+    nb = len(my_batches)
+    if blocks is None:
+        blocks = ResultBlocks(nb, int(my_batches[0][0].shape[0]) if nb else 1, stride)
+    if getattr(rec, '_depth', 0) != depth:
+        rec.set_pipeline_depth(depth)
+    pend = []
+    for i, b in enumerate(my_batches):
+        if len(pend) == depth:
+            j, t = pend.pop(0)
+            rec.collect(t, out=blocks.views(j))
+        pend.append((i, rec.submit(*b)))
+    while pend:
+        j, t = pend.pop(0)
+        rec.collect(t, out=blocks.views(j))
+    gathered = blocks.gather(dst, device) if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1 else [blocks.t]
+    return blocks, gathered

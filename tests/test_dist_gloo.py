@@ -101,3 +101,86 @@ def test_two_rank_gloo_recognition_matches_single_process():
         assert [t[:3] for t in a] == [t[:3] for t in b]
         assert np.allclose([t[3] for t in a], [t[3] for t in b], atol=1e-6)
     assert res == [[], [], [], [], [], [(3, 0, 1, 0.5)]]
+
+
+class _OracleRec:
+    """Stands in for TorchSeqRecognizer.submit / collect on a box without a GPU: same block contract, oracle arithmetic."""
+
+    def __init__(self, vo, om):
+        self.vo, self.om, self._depth, self.q, self.n = vo, om, 0, {}, 0
+
+    def set_pipeline_depth(self, d):
+        self._depth = d
+
+    def submit(self, line, lens=None, invert_max=None):
+        self.n += 1
+        t = self.n
+        self.q[t] = self.vo.rec_predict(self.om, line, lens)[3]
+        return t
+
+    def collect(self, ticket, out=None):
+        dec = self.q.pop(ticket)
+        for k in ('labels', 'starts', 'ends', 'confs'):
+            out[k][...] = 0
+        for i, d in enumerate(dec):
+            out['counts'][i] = len(d)
+            for j, (l, s, e, c) in enumerate(d):
+                out['labels'][i, j], out['starts'][i, j], out['ends'][i, j], out['confs'][i, j] = l, s, e, c
+        return out
+
+
+def _worker_blocks(rank, world, port, q):
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, os.path.join(root, 'oracle'))
+    import vgsl_oracle as vo
+    from kraken_b200.dist import recognize_sharded_blocks
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        torch.set_num_threads(1)
+        om = vo.OracleModel(SPEC)
+        om.init_like_reference(seed=0)
+        g = torch.Generator().manual_seed(11 + rank)                       # every rank owns DIFFERENT lines (its shard)
+        mine = [(torch.rand(4, 1, 16, 60, generator=g), torch.tensor([60, 33, 60, 17])) for _ in range(3)]
+        blocks, gathered = recognize_sharded_blocks(_OracleRec(vo, om), mine, stride=15, depth=2, device=None, dst=0)
+        if rank == 0:
+            q.put([t.numpy().copy() for t in gathered])
+        else:
+            assert gathered is None
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_gloo_result_blocks_single_gather():
+    """The throughput path of the multi-GPU job: result blocks written in place, ONE gather of the whole run (dist.ResultBlocks)."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'oracle'))
+    import vgsl_oracle as vo
+    from kraken_b200.dist import ResultBlocks
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_blocks, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = q.get(timeout=180)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert len(got) == 2 and got[0].shape == (3, 4 * (1 + 4 * 15))
+    om = vo.OracleModel(SPEC)
+    om.init_like_reference(seed=0)
+    for rank in range(2):
+        g = torch.Generator().manual_seed(11 + rank)
+        rb = ResultBlocks(3, 4, 15, pin=False)
+        rb.a[...] = got[rank]
+        for i in range(3):
+            x, lens = torch.rand(4, 1, 16, 60, generator=g), torch.tensor([60, 33, 60, 17])
+            exp = vo.rec_predict(om, x, lens)[3]
+            v = rb.views(i)
+            for j, d in enumerate(exp):
+                assert int(v['counts'][j]) == len(d)
+                assert [(int(v['labels'][j, k]), int(v['starts'][j, k]), int(v['ends'][j, k])) for k in range(len(d))] == [t[:3] for t in d]
+                assert np.allclose(v['confs'][j, :len(d)], [t[3] for t in d], atol=1e-6)
