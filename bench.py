@@ -267,7 +267,8 @@ def run_reference_arm(args, rank):
     line = {'impl': 'reference', 'metric': METRIC, 'value': lps, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
             'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
             'dtype': 'f32', 'data': 'synthetic',
-            'config': {'workload': 'cfg2', 'spec': CFG2, 'batch': BATCH, 'line': f'{HEIGHT}x{WIDTH}', 'device': 'host CPU'},
+            'config': {'workload': 'cfg2', 'spec': CFG2, 'batch_per_gpu': BATCH, 'global_batch': BATCH * args.gpus, 'line': f'{HEIGHT}x{WIDTH}'},
+            'notes': {'device': 'host CPU (rank 0 only)'},
             'cpu_baseline': {'value': lps, 'unit': UNIT, 'cores': threads, 'kind': 'port', 'cpu': cpu_model_name(),
                              'sample': f'{args.steps} batches of {BATCH} lines {HEIGHT}x{WIDTH} after {args.warmup} warm-up; '
                                        'torch-CPU restatement of the reference path (oracle/vgsl_oracle.py), fp32; ' + CPU_NOTE},
@@ -360,8 +361,11 @@ def main():
     ap.add_argument('--cpu-steps', type=int, default=6)
     ap.add_argument('--inflight', type=int, default=4, help='pipeline slots (batches in flight from the one host thread) of the e2e arm')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-numa-bind', action='store_true')
+    ap.add_argument('--no-extra', action='store_true', help='skip the cfg3 / cfg5 side measurements')
     ap.add_argument('--workload', default='cfg2', choices=['cfg2', 'cfg3'])
     ap.add_argument('--pages', type=int, default=8)
+    ap.add_argument('--cfg5-lines', type=int, default=100000)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'b200' else args.warmup
 
@@ -385,7 +389,11 @@ def main():
         dist.init_process_group('nccl', device_id=torch.device(f'cuda:{local}'))
         dist.barrier()
     import kraken_b200 as kb
+    from kraken_b200.dist import ResultBlocks, bind_to_gpu_numa, recognize_sharded_blocks
     dev = f'cuda:{local}'
+    # bind this rank (its threads and the pinned staging buffers it is about to first-touch) to the cores of its GPU's NUMA node:
+    # round 1 lost 40 % of the 8-GPU end-to-end rate to ranks feeding their GPU across the socket interconnect
+    numa_cores = bind_to_gpu_numa(local) if not args.no_numa_bind else None
     torch.cuda.set_device(local)
 
     # ---- weights: rank 0 initialises, one NCCL broadcast of the packed blob, every rank loads its replica
@@ -420,75 +428,42 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    # result blocks of a run in ONE pinned int32 buffer [step][counts (B) | labels (B x T) | starts | ends | confs]: every
-    # kb_recognize call writes its output blocks straight into its slice, so the run's single gather to rank 0 ships the buffer
-    # as it is (no host-side repacking)
-    pack_buf = {}
-    STEP_WORDS = BATCH * (1 + 4 * T)
+    # result blocks of a run in ONE pinned int32 buffer (kraken_b200.dist.ResultBlocks): every engine call writes its output blocks
+    # straight into its slice, the run's single gather to rank 0 ships the buffer as it is (no host-side repacking)
+    blocks = {}
 
-    def packed(steps):
-        if steps not in pack_buf:
-            pack_buf[steps] = torch.empty((steps, STEP_WORDS), dtype=torch.int32).pin_memory()
-        return pack_buf[steps]
+    def run_blocks(steps):
+        if steps not in blocks:
+            blocks[steps] = ResultBlocks(steps, BATCH, T)
+        return blocks[steps]
 
-    def out_views(buf, i):
-        b = buf[i]
-        o, bt = BATCH, BATCH * T
-        return {'counts': b[:o], 'labels': b[o:o + bt].reshape(BATCH, T), 'starts': b[o + bt:o + 2 * bt].reshape(BATCH, T),
-                'ends': b[o + 2 * bt:o + 3 * bt].reshape(BATCH, T), 'confs': b[o + 3 * bt:o + 4 * bt].view(np.float32).reshape(BATCH, T)}
-
-    def pack_into(buf, i, r):                # for calls that could not write in place (uint8 arm)
-        v = out_views(buf, i)
-        for k in ('counts', 'labels', 'starts', 'ends', 'confs'):
-            v[k][...] = r[k]
-
-    def gather_all(sink):
-        # the single gather of the run's decoded label sequences to rank 0 over NCCL
-        t = packed(len(sink))
-        buf = t.numpy()
-        for i, r in enumerate(sink):
-            if r is not None and not r.get('_packed'):
-                pack_into(buf, i, r)
-        tdev = t.to(dev, non_blocking=True)
-        out = [torch.empty_like(tdev) for _ in range(world)] if rank == 0 else None
-        dist.gather(tdev, out, dst=0)
-        return out
-
-    def run_pipelined(batches, steps, sink, u8=False):
-        res = [None] * steps
-        pbuf = packed(steps).numpy() if world > 1 else None
+    def run_pipelined(batches, steps, u8=False):
+        rb = run_blocks(steps)
         pend = []
-
-        def fetch():
-            j, t = pend.pop(0)
-            res[j] = rec.collect(t, out=out_views(pbuf, j) if pbuf is not None else None)
-            if pbuf is not None:
-                res[j]['_packed'] = True
         for i in range(steps):
             if len(pend) == DEPTH:
-                fetch()
+                j, t = pend.pop(0)
+                rec.collect(t, out=rb.views(j))
             pend.append((i, rec.submit(batches[i % NB], lens, inv255 if u8 else None)))
         while pend:
-            fetch()
-        sink.extend(res)
+            j, t = pend.pop(0)
+            rec.collect(t, out=rb.views(j))
+        return rb
 
-    def timed(batches, steps, sink, on_step=None, pipelined=False, u8=False):
+    def timed(batches, steps, on_step=None, pipelined=False, u8=False):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         if pipelined:
-            run_pipelined(batches, steps, sink, u8)
+            rb = run_pipelined(batches, steps, u8)
         else:
-            buf = packed(steps).numpy() if world > 1 else None
+            rb = run_blocks(steps)
             for i in range(steps):
-                r = step(batches[i % NB], out_views(buf, i) if buf is not None else None)
-                if buf is not None:
-                    r['_packed'] = True
-                sink.append(r)
+                step(batches[i % NB], rb.views(i))
                 if on_step is not None:
                     on_step()
         if world > 1:
-            got = gather_all(sink)
+            got = rb.gather(0, torch.device(dev))          # the single gather of the run's decoded label sequences to rank 0 over NCCL
             if rank == 0:
                 assert len(got) == world and got[0].shape[0] == steps
         e1.record()
@@ -496,23 +471,20 @@ def main():
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return float(ms.item())
+        return float(ms.item()), rb
 
     for i in range(args.warmup):
         step(devb[i % NB]); step(host[i % NB])
-    run_pipelined(host, 2 * DEPTH, [])
-    run_pipelined(host_u8, 2 * DEPTH, [], u8=True)
-    run_pipelined(devb, 2 * DEPTH, [])
+    run_pipelined(host, 2 * DEPTH)
+    run_pipelined(host_u8, 2 * DEPTH, u8=True)
+    run_pipelined(devb, 2 * DEPTH)
     if world > 1:
-        gather_all([step(devb[0])])          # warm the NCCL gather up (lazy communicator / channel setup) before timing ...
-        gather_all([None] * args.steps)      # ... at the payload size of the timed runs (buffers grow with the first large collective)
+        run_blocks(args.steps).gather(0, torch.device(dev))      # warm the NCCL gather up at the payload size of the timed runs
         ms_warm = torch.zeros(1, device=dev); dist.all_reduce(ms_warm, op=dist.ReduceOp.MAX)
 
-    # ---- timed region 1: inputs resident in HBM; per-stage CUDA-event timing on the launching stream
+    # ---- timed region 1 (strictly serial, one synchronous kb_recognize per step): per-stage CUDA-event timing on the launching stream
     m.set_timing(True)
     stage_ms = {}
-
-    results_buf = []
 
     def on_step():
         for name, ms in m.last_timing():
@@ -522,27 +494,60 @@ def main():
     if rank == 0:
         sampler.start()
     m.reset_launch_count()
-    ms_total = timed(devb, args.steps, results_buf, on_step)
-    launches = m.launch_count
-    clocks = sampler.stop() if rank == 0 else None
+    ms_serial, _ = timed(devb, args.steps, on_step)
+    launches_serial = m.launch_count
     m.set_timing(False)
-    # ---- timed region 2: end to end through the public API with pinned host buffers
-    results_buf2 = []
-    ms_e2e_serial = timed(host, args.steps, [])
-    ms_e2e = timed(host, args.steps, results_buf2, pipelined=True)
-    ms_e2e_u8 = timed(host_u8, args.steps, [], pipelined=True, u8=True)
-    ms_dev_pipe = timed(devb, args.steps, [], pipelined=True)          # device-resident inputs through the same pipeline
+    # ---- timed region 2: `value` - the same K steps, inputs resident in HBM, through the asynchronous pipeline (one host thread)
+    m.reset_launch_count()
+    ms_total, rb_value = timed(devb, args.steps, pipelined=True)
+    launches = m.launch_count
+    # ---- timed region 3: end to end through the public API with pinned host buffers
+    ms_e2e_serial, _ = timed(host, args.steps)
+    ms_e2e, _ = timed(host, args.steps, pipelined=True)
+    ms_e2e_u8, _ = timed(host_u8, args.steps, pipelined=True, u8=True)
+    clocks = sampler.stop() if rank == 0 else None
+    decoded_last = int(rb_value.views(args.steps - 1)['counts'].sum())
+
+    # ---- cfg5 (BASELINE configs[4]): 100 000 synthetic 48 x 1200 lines sharded over the ranks (strong scaling), lines generated on the
+    # device per shard, through kraken_b200.dist.recognize_sharded_blocks: asynchronous pipeline per rank + ONE gather at the end
+    cfg5 = None
+    if not args.no_extra:
+        W5, T5, TOTAL5 = 1200, 300, args.cfg5_lines
+        nb_total = (TOTAL5 + BATCH - 1) // BATCH
+        nb_mine = (nb_total + world - 1) // world            # every rank runs the same number of batches (the last ones may be surplus)
+        g5 = torch.Generator(device=dev).manual_seed(2 + rank)
+        dev5 = [torch.rand(BATCH, 1, HEIGHT, W5, generator=g5, device=dev) for _ in range(NB)]
+        lens5 = torch.full((BATCH,), W5, dtype=torch.long)
+        my5 = [(dev5[i % NB], lens5) for i in range(nb_mine)]
+        rb5 = ResultBlocks(nb_mine, BATCH, T5)
+        recognize_sharded_blocks(rec, my5[:2 * DEPTH], T5, depth=DEPTH, device=torch.device(dev) if world > 1 else None, blocks=ResultBlocks(2 * DEPTH, BATCH, T5))
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        recognize_sharded_blocks(rec, my5, T5, depth=DEPTH, device=torch.device(dev) if world > 1 else None, blocks=rb5)
+        e1.record()
+        barrier()
+        ms5 = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms5, op=dist.ReduceOp.MAX)
+        ms5 = float(ms5.item())
+        lines5 = nb_mine * world * BATCH
+        cfg5 = {'workload': 'cfg5', 'lines': lines5, 'line': f'{HEIGHT}x{W5}', 'scaling': 'strong', 'ms_total': ms5, 'value': lines5 / (ms5 / 1e3), 'unit': UNIT,
+                'batches_per_rank': nb_mine, 'in_flight': DEPTH, 'decoded_labels_last_batch': int(rb5.views(nb_mine - 1)['counts'].sum()),
+                'api': 'kraken_b200.dist.recognize_sharded_blocks: device-resident shard -> kb_recognize_async/kb_wait -> one NCCL gather of the label blocks'}
+        del dev5, my5, rb5
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
+    pk = peaks()
+    work = stage_work()
+    T_ = T
     ms_step = ms_total / args.steps
     value = world * BATCH * args.steps / (ms_total / 1e3)
     e2e = world * BATCH * args.steps / (ms_e2e / 1e3)
-    pk = peaks()
-    work = stage_work()
     per_stage = {k: v / args.steps for k, v in stage_ms.items()}
     dom = max((k for k in per_stage if k in work), key=lambda k: per_stage[k])
     flops, byts = work[dom][0] * BATCH, work[dom][1] * BATCH
@@ -552,27 +557,42 @@ def main():
         roof = {'bound': 'tensor', 'achieved': flops / dur / 1e12, 'peak': pk['tf_sustained'], 'unit': 'TFLOP/s'}
     else:
         roof = {'bound': 'hbm', 'achieved': byts / dur / 1e9, 'peak': pk['hbm_gbs'], 'unit': 'GB/s'}
-    # measured DRAM bytes per launch of that kernel from the committed `ncu --set full` capture of this same command
-    # (profiles/r01d_ncu_full_summary.csv -> r01d_ncu_dram_bytes_per_launch.json); null if the capture is missing
+    # measured DRAM bytes per launch of that kernel from the committed `ncu --set full` capture of this same command (profiles/); null if
+    # the capture is missing
     traffic = None
-    try:
-        with open(os.path.join(ROOT, 'profiles', 'r01d_ncu_dram_bytes_per_launch.json')) as fh:
-            tj = json.load(fh)
-        kmap = {'L_5.rec': ('void ltc::k_lstm_rec_tc<8>', 0), 'L_5.xproj': ('void tc::k_gemm_tc<1>', 0), 'O_6': ('void tc::k_gemm_tc<1>', 1),
-                'C_2+Mp_3+S_4': ('ctc::k_conv_tc', 0), 'C_0+Mp_1': ('void k_conv1_pool33<8, 3>', 0)}
-        if dom in kmap and kmap[dom][0] in tj:
-            traffic = float(tj[kmap[dom][0]][kmap[dom][1]])
-    except (OSError, ValueError, IndexError, KeyError):
-        traffic = None
+    for tf_name in ('r02_ncu_dram_bytes_per_launch.json', 'r01d_ncu_dram_bytes_per_launch.json'):
+        try:
+            with open(os.path.join(ROOT, 'profiles', tf_name)) as fh:
+                tj = json.load(fh)
+            kmap = {'L_5.rec': ('k_lstm_rec_tc<8>', 0), 'L_5.xproj': ('k_gemm_tc<', 0), 'O_6': ('k_gemm_tc<', 1),
+                    'C_2+Mp_3+S_4': ('k_conv_tc', 0), 'C_0+Mp_1': ('k_conv1_pool33', 0)}
+            if dom in kmap:
+                hits = [v for k_, v in tj.items() if kmap[dom][0] in k_]
+                if hits:
+                    traffic = float(hits[0][min(kmap[dom][1], len(hits[0]) - 1)])
+                    break
+        except (OSError, ValueError, IndexError, KeyError, TypeError):
+            continue
     roof.update({'frac': roof['achieved'] / roof['peak'], 'traffic': traffic, 'kernel': dom, 'kernel_ms': per_stage[dom],
-                 'share_of_step': per_stage[dom] / ms_step, 'peak_source': pk['src'] + (' (sustained bf16 GEMM)' if roof['bound'] == 'tensor' else ' (copy bandwidth)'),
+                 'share_of_serial_step': per_stage[dom] / (ms_serial / args.steps),
+                 'peak_source': pk['src'] + (' (sustained bf16 GEMM)' if roof['bound'] == 'tensor' else ' (copy bandwidth)'),
                  'algorithmic_per_launch': {'flops': flops, 'bytes': byts},
+                 'timed': 'per-stage CUDA events on the launching stream inside the strictly serial timed region (kb_set_timing)',
                  'stages_ms': {k: round(v, 4) for k, v in per_stage.items()},
                  'per_stage': per_stage_roofline(per_stage, work, pk, BATCH)})
     tot_f = sum(work[k][0] for k in per_stage if k in work) * BATCH          # only the stages that actually ran (fused groups replace their members)
-    tot_b = (4 * 48 * WIDTH + 2 * 4 * 768 * T + 2 * 4 * 2048 * T + 2 * 4 * 512 * T + 8 * T) * BATCH
-    roof['whole_step'] = {'tensor_frac': tot_f / (ms_step / 1e3) / (pk['tf_sustained'] * 1e12),
-                          'hbm_frac': tot_b / (ms_step / 1e3) / (pk['hbm_gbs'] * 1e9)}
+    tot_b = (4 * 48 * WIDTH + 2 * 4 * 768 * T_ + 2 * 4 * 2048 * T_ + 2 * 4 * 512 * T_ + 8 * T_) * BATCH
+
+    def whole(ms):
+        return {'tensor_frac': tot_f / (ms / 1e3) / (pk['tf_sustained'] * 1e12), 'hbm_frac': tot_b / (ms / 1e3) / (pk['hbm_gbs'] * 1e9)}
+    roof['whole_step'] = {'serial': whole(ms_serial / args.steps), 'pipelined_value': whole(ms_step * world), 'pipelined_e2e': whole(ms_e2e / args.steps * world),
+                          'algorithmic_per_step': {'flops': tot_f, 'bytes': tot_b}}
+    if cfg5 is not None:
+        f5 = (2 * 48 * 1200 * 32 * 9 + 2 * 24 * 600 * 64 * 288 + 300 * (2 * 2 * 1024 * 768 + 2 * 2 * 1024 * 256 + 2 * 200 * 512))
+        b5 = 4 * 48 * 1200 + 2 * 4 * 768 * 300 + 2 * 4 * 2048 * 300 + 2 * 4 * 512 * 300 + 8 * 300
+        lps_gpu = cfg5['value'] / world
+        cfg5['roofline'] = {'tensor_frac': lps_gpu * f5 / (pk['tf_sustained'] * 1e12), 'hbm_frac': lps_gpu * b5 / (pk['hbm_gbs'] * 1e9),
+                            'algorithmic_per_line': {'flops': f5, 'bytes': b5}, 'note': 'whole path per GPU against the measured peaks (SURVEY 8d)'}
 
     cpu = None
     if not args.no_cpu_baseline and world == 1:
@@ -580,30 +600,79 @@ def main():
         cpu = {'value': lps, 'unit': UNIT, 'cores': threads, 'kind': 'port', 'cpu': cpu_model_name(),
                'sample': f'{args.cpu_steps} batches of {BATCH} lines {HEIGHT}x{WIDTH} after 2 warm-up ({cms:.0f} ms/batch); '
                          'oracle/vgsl_oracle.py = torch-CPU restatement of rpred.py:225-228 + ctc_decoder.py, fp32; ' + CPU_NOTE}
+    cfg3 = None
+    if world == 1 and not args.no_extra:
+        cfg3 = cfg3_brief(args)
 
-    d2h = BATCH * T * 16 + BATCH * 4
+    d2h = BATCH * T_ * 16 + BATCH * 4
     line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
             'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
             'data': 'synthetic',
-            'config': {'workload': 'cfg2', 'spec': CFG2, 'batch_per_gpu': BATCH, 'global_batch': BATCH * world, 'line': f'{HEIGHT}x{WIDTH}',
-                       'parallelism': f'replicas x{world} (independent line shards, 1 weight broadcast + 1 result gather)',
-                       'l2': f'{NB} rotating input batches; ~0.3 GB of activations per step > 126 MB L2'},
-            'value_pipelined': {'value': world * BATCH * args.steps / (ms_dev_pipe / 1e3), 'unit': UNIT, 'ms_per_step': ms_dev_pipe / args.steps,
-                                'note': f'device-resident inputs, kb_recognize_async with {DEPTH} batches in flight from one host thread'},
+            'config': {'workload': 'cfg2', 'spec': CFG2, 'batch_per_gpu': BATCH, 'global_batch': BATCH * world, 'line': f'{HEIGHT}x{WIDTH}'},
+            'notes': {'parallelism': f'replicas x{world} (independent line shards, 1 weight broadcast + 1 result gather)',
+                       'value_is': f'{args.steps} steps per GPU, line batches resident in HBM, submitted through kb_recognize_async / kb_wait with {DEPTH} batches '
+                                   'in flight from one host thread per GPU (serial.* = one synchronous kb_recognize per step)',
+                       'l2': f'{NB} rotating input batches; ~0.3 GB of activations per step > 126 MB L2',
+                       'numa_cores': None if numa_cores is None else f'{numa_cores[0]}..{numa_cores[-1]} ({len(numa_cores)} cores)'},
+            'serial': {'value': world * BATCH * args.steps / (ms_serial / 1e3), 'ms_per_step': ms_serial / args.steps, 'gpu_launches': int(launches_serial),
+                       'sum_of_stages_ms': round(sum(per_stage.values()), 4),
+                       'note': 'one synchronous kb_recognize per step with per-stage event timing on; the gap to the sum of the stages is the host turn-around between calls'},
             'e2e': {'value': e2e, 'unit': UNIT, 'ms_per_step': ms_e2e / args.steps, 'in_flight': DEPTH, 'host_threads': 1,
                     'serial_value': world * BATCH * args.steps / (ms_e2e_serial / 1e3),
                     'h2d_bytes_per_step': BATCH * HEIGHT * WIDTH * 4, 'd2h_bytes_per_step': d2h,
+                    'h2d_gbs_per_rank': BATCH * HEIGHT * WIDTH * 4 / (ms_e2e / args.steps / 1e3) / 1e9,
                     'api': 'TorchSeqRecognizer.submit/collect -> kb_recognize_async/kb_wait on one handle, pinned host lines in, label blocks out; '
                            'serial_value = TorchSeqRecognizer._recognize_raw -> kb_recognize one call at a time'},
-            'e2e_u8': None if ms_e2e_u8 is None else {
-                'value': world * BATCH * args.steps / (ms_e2e_u8 / 1e3), 'unit': UNIT, 'ms_per_step': ms_e2e_u8 / args.steps,
-                'in_flight': DEPTH, 'host_threads': 1, 'h2d_bytes_per_step': BATCH * HEIGHT * WIDTH + BATCH * 6, 'd2h_bytes_per_step': d2h,
-                'api': 'TorchSeqRecognizer.submit(uint8 lines) -> kb_recognize_async(KB_DTYPE_U8): pinned uint8 lines in; ToDtype(scale) + tensor_invert + padding on the device'},
-            'gpu_launches': int(launches), 'clocks': clocks, 'roofline': roof, 'cpu_baseline': cpu,
-            'decoded_labels_last_step': int(results_buf[-1]['counts'].sum()) if results_buf else 0}
+            'e2e_u8': {'value': world * BATCH * args.steps / (ms_e2e_u8 / 1e3), 'unit': UNIT, 'ms_per_step': ms_e2e_u8 / args.steps,
+                       'in_flight': DEPTH, 'host_threads': 1, 'h2d_bytes_per_step': BATCH * HEIGHT * WIDTH + BATCH * 6, 'd2h_bytes_per_step': d2h,
+                       'api': 'TorchSeqRecognizer.submit(uint8 lines) -> kb_recognize_async(KB_DTYPE_U8): pinned uint8 lines in; ToDtype(scale) + tensor_invert + padding on the device'},
+            'gpu_launches': int(launches), 'clocks': clocks, 'roofline': roof, 'cpu_baseline': cpu, 'cfg5': cfg5, 'cfg3': cfg3,
+            'decoded_labels_last_step': decoded_last}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def cfg3_brief(args):
+    """BASELINE configs[2] next to the headline: blla architecture on 8 pages 3x1800x1350 -> 4x1800x1350 heat maps (kb_segment), device-timed
+    and end to end with pinned host pages in / pinned host heat maps out.  `python bench.py --workload cfg3` has the long form."""
+    import kraken_b200 as kb
+    from kraken_b200.blla import segmentation_heatmap
+    sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+    import vgsl_oracle as vo
+    N, H, W = 8, 1800, 1350
+    om = vo.OracleModel(BLLA)
+    m3 = kb.TorchVGSLModel(vgsl=BLLA, model_type=['segmentation'])
+    m3.load_state_dict(om.init_like_reference(3))
+    m3.to('cuda:0')
+    g = torch.Generator().manual_seed(3)
+    hpages = [torch.rand(N, 3, H, W, generator=g).pin_memory() for _ in range(2)]
+    pages = [p_.cuda() for p_ in hpages]
+    for i in range(3):
+        segmentation_heatmap(m3, pages[i % 2], (H, W))
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    steps = 5
+    e0.record()
+    for i in range(steps):
+        segmentation_heatmap(m3, pages[i % 2], (H, W))
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    segmentation_heatmap(m3, hpages[0], (H, W))
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for i in range(steps):
+        hm = segmentation_heatmap(m3, hpages[i % 2], (H, W))
+    torch.cuda.synchronize()
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / steps
+    pk = peaks()
+    return {'workload': 'cfg3', 'metric': 'pages/sec (blla forward, 2400x3200 pages -> 3x1800x1350)', 'batch': N, 'value': N / (ms / 1e3), 'unit': 'pages/s',
+            'ms_per_step': ms, 'e2e': {'value': N / (e2e_ms / 1e3), 'ms_per_step': e2e_ms, 'h2d_bytes_per_step': N * 3 * H * W * 4,
+                                       'd2h_bytes_per_step': int(hm.numel()) * 4, 'pinned_output': bool(hm.is_pinned())},
+            'roofline': {'tensor_frac': N / (ms / 1e3) * 390.9e9 / (pk['tf_sustained'] * 1e12), 'hbm_frac': N / (ms / 1e3) * 1.628e9 / (pk['hbm_gbs'] * 1e9),
+                         'note': 'whole forward: 390.9 GFLOP and 1.628 GB algorithmic per page (SURVEY 8d)'},
+            'weights': 'seeded (reference init); parity of this size with the real blla.mlmodel weights: tests/test_gpu_configs.py'}
 
 
 if __name__ == '__main__':

@@ -19,7 +19,8 @@ __all__ = ['compute_segmentation_map', 'segmentation_heatmap']
 
 def segmentation_heatmap(model: TorchVGSLModel, pages, size: Optional[Sequence[int]] = None):
     """pages: (N, C, H, W) tensor already transformed to network input.  Returns sigmoid heat maps
-    (N, C', size[0], size[1]) - on the GPU if `pages` is a CUDA tensor, else a CPU tensor."""
+    (N, C', size[0], size[1]) - on the GPU if `pages` is a CUDA tensor, else a CPU tensor (a pinned buffer owned by the model and
+    reused by the next call with the same shape: copy it if you keep it)."""
     model._ensure_finalized(pages)
     x = _as_f32(pages)
     if x.ndim == 3:
@@ -33,7 +34,20 @@ def segmentation_heatmap(model: TorchVGSLModel, pages, size: Optional[Sequence[i
         size = (h, w)
     oc = model.infer_dims(n, h, w)[1]
     on_dev = _on_device(x)
-    out = torch.empty((n, oc, int(size[0]), int(size[1])), dtype=torch.float32, device=x.device if on_dev else 'cpu')
+    shape = (n, oc, int(size[0]), int(size[1]))
+    if on_dev:
+        out = torch.empty(shape, dtype=torch.float32, device=x.device)
+    else:
+        # host result: a PINNED buffer (cached per shape on the model) - a pageable destination made the 544 MB heat-map read-back of
+        # a cfg3 batch crawl at ~4.7 GB/s, 6.5x longer than the forward itself (round-1 measurement)
+        cache = model.__dict__.setdefault('_pinned_out', {})
+        out = cache.get(shape)
+        if out is None:
+            out = torch.empty(shape, dtype=torch.float32)
+            if torch.cuda.is_available():
+                out = out.pin_memory()
+            cache.clear()
+            cache[shape] = out
     check(lib.kb_segment(model._h, _ptr(x), int(on_dev), n, h, w, int(size[0]), int(size[1]), out.data_ptr(), int(on_dev), _stream_for(x, model._device)))
     return out
 
@@ -54,6 +68,8 @@ def compute_segmentation_map(model: TorchVGSLModel, tensor_im, scal_shape: Optio
     pad[3] = -pad[3] if pad[3] else None
     o = o[:, :, pad[2]:pad[3], pad[0]:pad[1]]
     hm = o.squeeze().cpu().float().numpy()
+    if not o.is_cuda:
+        hm = hm.copy()                 # the host result is a view of the model's reusable pinned buffer
     return {'heatmap': hm,
             'cls_map': model.user_metadata.get('class_mapping'),
             'bounding_regions': model.user_metadata.get('bounding_regions', None)}

@@ -51,7 +51,8 @@ struct LeafWeights {
     __half *b_hi = nullptr, *b_lo = nullptr;  // [ncols][K] fp16 operand planes for the tcgen05 GEMM (K-major)
     __half *c_hi = nullptr, *c_lo = nullptr;  // [tap][chunk][Cout][32] fp16 operand planes for the tcgen05 convolution
     int s2d = 0, s_th = 0, s_tw = 0, s_py = 0, s_px = 0, s_cs = 0;   // stride-2 conv as space-to-depth stride-1 conv: block taps, block padding, channels
-    void *wpk = nullptr;                      // W_hh as pre-swizzled bf16x3 UMMA tiles [dir][rank][split][k-atom][128][64] (tcgen05 recurrence)
+    void *wpk = nullptr;                      // W_hh as fp16 operand planes of the tcgen05 recurrences
+    float *whh_t = nullptr; int whh_ncp = 0;  // hidden > 256: W_hh^T [dir][k = h][gate column (unit, gate) padded to 64] for the per-step GEMM
     int ncp = 0, K = 0, ncols = 0;
 };
 
@@ -249,7 +250,7 @@ static void finalize_weights(kb_model *m) {
     for (size_t li = 0; li < m->plan->leaf_nodes.size(); ++li) {
         const Node &n = *m->plan->leaf_nodes[li];
         LeafWeights &w = m->lw[li];
-        w.wt = w.bias = w.aux = nullptr; w.b_hi = w.b_lo = w.c_hi = w.c_lo = nullptr; w.wpk = nullptr;
+        w.wt = w.bias = w.aux = nullptr; w.b_hi = w.b_lo = w.c_hi = w.c_lo = nullptr; w.wpk = nullptr; w.whh_t = nullptr;
         auto need = [&](int slots) {
             for (int s = 0; s < slots; ++s)
                 if ((int)w.loaded.size() <= s || !w.loaded[s]) throw SpecError("weights of layer " + n.name + " not loaded (missing tensor for nn." + n.path + ")");
@@ -333,7 +334,6 @@ static void finalize_weights(kb_model *m) {
             if (n.legacy) throw Unsupported(n.name + ": legacy clstm/ocropy LSTM variants are not implemented by the engine");
             const int dirs = n.bidi ? 2 : 1, h = n.hidden, gc = dirs * 4 * h;
             need(4 * dirs);
-            if (h > 256) throw Unsupported(n.name + ": hidden sizes above 256 are not supported by the register-resident recurrence kernel yet");
             const int K = n.cin, ncp = (gc + 63) / 64 * 64;
             std::vector<float> wt((size_t)K * ncp, 0.f), b((size_t)gc, 0.f), whh((size_t)dirs * 4 * h * h);
             for (int d = 0; d < dirs; ++d) {
@@ -347,6 +347,19 @@ static void finalize_weights(kb_model *m) {
                 std::copy(wh.begin(), wh.end(), whh.begin() + (size_t)d * 4 * h * h);
             }
             w.wt = upload(m, wt); w.bias = upload(m, b); w.aux = upload(m, whh); w.ncp = ncp; w.K = K; w.ncols = gc;
+            w.whh_t = nullptr;
+            if (h > 256 || getenv("KB_LSTM_GENERIC")) {
+                // generic per-step path: W_hh^T [dir][k][col = 4 u + gate], columns padded to the GEMM's tile
+                const int hncp = (4 * h + 63) / 64 * 64;
+                std::vector<float> t((size_t)dirs * h * hncp, 0.f);
+                for (int d = 0; d < dirs; ++d) {
+                    const std::vector<float> &wh = w.host[d * 4 + 1];          // [4h][h], torch gate order i,f,g,o
+                    for (int g = 0; g < 4; ++g)
+                        for (int u = 0; u < h; ++u)
+                            for (int k = 0; k < h; ++k) t[((size_t)d * h + k) * hncp + u * 4 + g] = wh[(size_t)(g * h + u) * h + k];
+                }
+                w.whh_t = upload(m, t); w.whh_ncp = hncp;
+            }
             {
                 std::vector<float> rows((size_t)gc * K);
                 for (int d = 0; d < dirs; ++d)
@@ -487,6 +500,32 @@ struct Exec {
         else LAUNCH(m, k_conv_gemm<false>, grid, CG_NT, 0, st, p);
     }
 
+    // Recurrence for hidden sizes above 256 (no resident-weight kernel): per time step one fp32 GEMM launch + one pointwise launch
+    // (kernels.cuh k_lstm_generic_*).  Slow (2 T launches) but complete: any nn.LSTM the reference builds (layers.py:507-511) runs.
+    void run_lstm_generic(const Node &n, const LeafWeights &w, const LstmParams &lp, float *G, float *H, float *C, const Lens &lens) {
+        const int hid = lp.hid, nseq = lp.nseq;
+        int maxlen = lp.T;
+        if (lp.lens && lens.has) { maxlen = 0; for (int32_t l : lens.v) maxlen = std::max(maxlen, std::min(std::max((int)l, 0), lp.T)); }
+        if (getenv("KB_DEBUG")) fprintf(stderr, "[kb] %s: generic per-step recurrence (hidden %d), %d steps x %d directions\n", n.name.c_str(), hid, maxlen, lp.dirs);
+        LAUNCH(m, k_lstm_generic_init, grid1d((long long)nseq * lp.T * lp.dirs * hid, 256, m->sm_count), 256, 0, st, lp.out, H, C, lp.lens, nseq, lp.T, hid, lp.dirs, lp.q2,
+               lp.s_outer, lp.s_inner, lp.step);
+        for (int t = 0; t < maxlen; ++t)
+            for (int d = 0; d < lp.dirs; ++d) {
+                float *Hd = H + (size_t)d * nseq * hid, *Cd = C + (size_t)d * nseq * hid;
+                ConvParams p;
+                p.x = Hd; p.wt = w.whh_t + (size_t)d * hid * w.whh_ncp; p.bias = nullptr; p.y = G;
+                p.N = 1; p.H = 1; p.W = nseq; p.Cin = hid; p.Ho = 1; p.Wo = nseq; p.Cout = 4 * hid; p.Ncp = w.whh_ncp;
+                p.kh = p.kw = p.sy = p.sx = p.dy = p.dx = 1; p.py = p.px = 0; p.K = hid; p.M = nseq; p.act = ACT_LINEAR;
+                dim3 grid((unsigned)((p.M + CG_BM - 1) / CG_BM), (unsigned)(w.whh_ncp / CG_BN));
+                if ((hid & 3) == 0) LAUNCH(m, k_conv_gemm<true>, grid, CG_NT, 0, st, p);
+                else LAUNCH(m, k_conv_gemm<false>, grid, CG_NT, 0, st, p);
+                LstmStepParams sp;
+                sp.G = G; sp.gx = lp.gx; sp.hstate = Hd; sp.cstate = Cd; sp.out = lp.out; sp.lens = lp.lens; sp.nseq = nseq; sp.T = lp.T; sp.hid = hid;
+                sp.dirs = lp.dirs; sp.dir = d; sp.t = t; sp.q2 = lp.q2; sp.s_outer = lp.s_outer; sp.s_inner = lp.s_inner; sp.step = lp.step;
+                LAUNCH(m, k_lstm_generic_step, (unsigned)(((long long)nseq * hid + 255) / 256), 256, 0, st, sp);
+            }
+    }
+
     Tensor leaf(const Node &n, const Tensor &x, Lens &lens) {
         const Dims din = dims_of(x);
         const Dims dout = leaf_dims(n, din);
@@ -607,6 +646,14 @@ struct Exec {
             planes_hint = false;
             if (lplanes) { full.hi = (__half *)ws->arena.alloc((size_t)full.numel() * 2); full.lo = (__half *)ws->arena.alloc((size_t)full.numel() * 2); }
             int *dl = packed ? dev_lens(lens) : nullptr;
+            // per-step GEMM path (hidden > 256): gate pre-activations of one step, h and c state for both directions
+            float *gen_g = nullptr, *gen_h = nullptr, *gen_c = nullptr;
+            if (w.whh_t) {
+                const size_t nsq = (size_t)(n.transpose ? x.n * x.w : x.n * x.h);
+                gen_g = (float *)ws->arena.alloc(nsq * 4 * hid * sizeof(float));
+                gen_h = (float *)ws->arena.alloc((size_t)dirs * nsq * hid * sizeof(float));
+                gen_c = (float *)ws->arena.alloc((size_t)dirs * nsq * hid * sizeof(float));
+            }
             if (full.numel()) { StageTimer tt(ws, st, n.name + ".xproj", !dry); gemm(x, w, nullptr, ACT_LINEAR, gx.p, x.h, x.w); }
             if (!dry && full.numel()) {
                 StageTimer tt(ws, st, n.name + ".rec", true);
@@ -616,11 +663,14 @@ struct Exec {
                 else { lp.nseq = (int)(x.n * x.w); lp.T = (int)x.h; lp.q2 = (int)x.w; lp.s_outer = x.h * x.w; lp.s_inner = 1; lp.step = x.w; }
                 const int ks = hid <= 32 ? 1 : hid <= 64 ? 2 : hid <= 128 ? 4 : 8;
                 lp.U = (hid + ks - 1) / ks;
+                const bool generic = w.whh_t && (hid > 256 || (getenv("KB_LSTM_GENERIC") && atoi(getenv("KB_LSTM_GENERIC")) != 0));
                 // tcgen05 recurrence (lstm_tc.cuh) for hidden sizes 129..256: 0.44 ms vs 0.69 ms for the CUDA-core kernel on cfg2 and
                 // only 64 instead of 112 SMs; KB_LSTM_TC=0 selects the CUDA-core kernel (accurate expf/tanhf, fp32 FMA)
                 const bool tc_on = w.wpk && m->use_tc && !(getenv("KB_LSTM_TC") && atoi(getenv("KB_LSTM_TC")) == 0);
                 const bool rec_tc = ks == 8 && tc_on;
-                if (ks == 1 && tc_on) {
+                if (generic) {
+                    run_lstm_generic(n, w, lp, gen_g, gen_h, gen_c, lens);
+                } else if (ks == 1 && tc_on) {
                     // hid <= 32 (blla's Lbx32 / Lby32): 64 sequences per CTA, W_hh in tensor memory, no cluster
                     ltc::LstmTcParams tp;
                     tp.gx = lp.gx; tp.wpk = (const uint16_t *)w.wpk; tp.out = (lplanes && !m->keep_fp32) ? nullptr : lp.out; tp.lens = lp.lens; tp.nseq = lp.nseq; tp.T = lp.T;

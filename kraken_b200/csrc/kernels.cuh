@@ -755,6 +755,50 @@ __global__ void __launch_bounds__(256) k_gn_apply4(const float *__restrict__ x, 
 // Packed-sequence semantics (pack_padded_sequence, layers.py:528-536): line q runs len[q] steps, the
 // reverse direction starts at its own last valid column, outputs beyond len are zero.
 // =============================================================================================
+// Generic recurrence for hidden sizes no resident-weight kernel takes (> 256): one step = one fp32 GEMM launch
+// (G[seq][4h] = H[seq][h] . W_hh^T, k_conv_gemm) + this pointwise kernel.  2 T launches per layer, any size, same arithmetic as
+// k_lstm_rec (expf / tanhf, fp32 cell state, packed-sequence semantics: a line stops at its own length, the reverse direction starts
+// at each line's own end, padded steps are zero).  Layout as everywhere: gate columns [unit][i, f, g, o] (per direction).
+struct LstmStepParams {
+    const float *G; const float *gx; float *hstate; float *cstate; float *out; const int *lens;
+    int nseq, T, hid, dirs, dir, t;                // t = step counter (0 .. maxlen-1)
+    int q2; long long s_outer, s_inner, step;
+};
+__global__ void k_lstm_generic_step(LstmStepParams p) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)p.nseq * p.hid) return;
+    const int u = (int)(idx % p.hid), q = (int)(idx / p.hid);
+    const int len = p.lens ? min(max(p.lens[q], 0), p.T) : p.T;
+    if (p.t >= len) return;                        // finished line: its state is never read again, its padded outputs were zeroed up front
+    const int tt = p.dir ? len - 1 - p.t : p.t;
+    const long long pix = (long long)(q / p.q2) * p.s_outer + (long long)(q % p.q2) * p.s_inner + (long long)tt * p.step;
+    const float4 g4 = *reinterpret_cast<const float4 *>(p.G + ((size_t)q * p.hid + u) * 4);
+    const float4 x4 = *reinterpret_cast<const float4 *>(p.gx + (size_t)pix * (p.dirs * 4 * p.hid) + (size_t)p.dir * 4 * p.hid + (size_t)u * 4);
+    const float gi = 1.f / (1.f + expf(-(g4.x + x4.x))), gf = 1.f / (1.f + expf(-(g4.y + x4.y)));
+    const float gg = tanhf(g4.z + x4.z), go = 1.f / (1.f + expf(-(g4.w + x4.w)));
+    const float c = gf * p.cstate[idx] + gi * gg;
+    const float h = go * tanhf(c);
+    p.cstate[idx] = c; p.hstate[idx] = h;
+    p.out[(size_t)pix * (p.dirs * p.hid) + (size_t)p.dir * p.hid + u] = h;
+}
+// zero the output pixels beyond each line's length (both directions) and the initial h / c state
+__global__ void k_lstm_generic_init(float *out, float *hstate, float *cstate, const int *lens, int nseq, int T, int hid, int dirs, int q2,
+                                    long long s_outer, long long s_inner, long long step) {
+    const long long total = (long long)nseq * T * dirs * hid;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % (dirs * hid)); const long long r = i / (dirs * hid);
+        const int t = (int)(r % T), q = (int)(r / T);
+        const int len = lens ? min(max(lens[q], 0), T) : T;
+        if (t >= len) {
+            const long long pix = (long long)(q / q2) * s_outer + (long long)(q % q2) * s_inner + (long long)t * step;
+            out[(size_t)pix * (dirs * hid) + c] = 0.f;
+        }
+    }
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < (long long)dirs * nseq * hid; i += (long long)gridDim.x * blockDim.x) {
+        hstate[i] = 0.f; cstate[i] = 0.f;
+    }
+}
+
 struct LstmParams {
     const float *gx; const float *whh; float *out; const int *lens;
     int nseq, T, hid, dirs, U;

@@ -145,14 +145,20 @@ __device__ __forceinline__ float tanh_fast(float x) { return fmaf(2.f, sigmoid_f
 __device__ __forceinline__ void named_bar(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 
 // 4x4 transpose across the four lanes of a quad: in: v[i] = this lane's value for item i; out: v[j] = lane (quad base + j)'s value
-// for item (lane & 3).  Three shuffles; the selects keep the register indices static.
+// for item (lane & 3).  Two butterfly rounds (swap within 2x2 blocks, then swap the blocks), four shuffles, everything a SELECT on
+// a lane-bit predicate with static register indices.  (A first version selected v[lane ^ k] with nested ternaries: ptxas turned
+// them into 4-way divergent branches with BSSY/BSYNC - 1300 cycles per step in the KB_LSTM_DBG timeline.)
 __device__ __forceinline__ void quad_transpose4(float (&v)[4], int gq) {
-#pragma unroll
-    for (int k = 1; k < 4; ++k) {
-        const int pr = gq ^ k;                                         // partner's index in the quad
-        const float send = pr == 0 ? v[0] : pr == 1 ? v[1] : pr == 2 ? v[2] : v[3];
-        const float got = __shfl_xor_sync(0xffffffffu, send, k);
-        if (pr == 0) v[0] = got; else if (pr == 1) v[1] = got; else if (pr == 2) v[2] = got; else v[3] = got;
+    const bool b0 = gq & 1, b1 = gq & 2;
+    {
+        const float sa = b0 ? v[0] : v[1], sb = b0 ? v[2] : v[3];
+        const float ra = __shfl_xor_sync(0xffffffffu, sa, 1), rb = __shfl_xor_sync(0xffffffffu, sb, 1);
+        v[0] = b0 ? ra : v[0]; v[1] = b0 ? v[1] : ra; v[2] = b0 ? rb : v[2]; v[3] = b0 ? v[3] : rb;
+    }
+    {
+        const float sa = b1 ? v[0] : v[2], sb = b1 ? v[1] : v[3];
+        const float ra = __shfl_xor_sync(0xffffffffu, sa, 2), rb = __shfl_xor_sync(0xffffffffu, sb, 2);
+        v[0] = b1 ? ra : v[0]; v[2] = b1 ? v[2] : ra; v[1] = b1 ? rb : v[1]; v[3] = b1 ? v[3] : rb;
     }
 }
 

@@ -528,3 +528,55 @@ def test_async_pipeline_matches_synchronous_calls():
     # the synchronous entry point keeps working next to the pipeline and leaves torch's current device alone
     assert torch.cuda.current_device() == 0
     assert np.array_equal(rec._recognize_raw(*batches[3], want_probs=False)['labels'], sync[3]['labels'])
+
+
+@pytest.mark.parametrize('spec,n,h,w', [
+    ('[1,16,0,1 Cr3,3,32 Mp2,2 S1(1x0)1,3 Lbx300 O1c30]', 5, 16, 90),            # hidden 300 > 256: no resident-weight kernel
+    ('[1,16,0,1 Cr3,3,16 Mp2,2 S1(1x0)1,3 Lfx513 Lrx260 O1c11]', 3, 16, 50),      # odd size, forward / reverse only, stacked
+    ('[1,0,0,3 Cr3,3,16 Lby264 O2l4]', 2, 21, 30),                               # y-axis sweep over a 2-D map
+])
+def test_lstm_hidden_sizes_above_256(spec, n, h, w):
+    """Any nn.LSTM size the reference builds (layers.py:507-511) runs: hidden sizes above 256 take the per-step path
+    (one fp32 GEMM + one pointwise launch per time step)."""
+    om = vo.OracleModel(spec)
+    wts = om.init_like_reference(61)
+    g = torch.Generator().manual_seed(61)
+    cin = om.input[1]
+    x = torch.rand(n, cin, h, w, generator=g)
+    lens = None
+    if cin == 1:
+        lens = torch.randint(12, w + 1, (n,), generator=g)
+        lens[0] = w
+        for i, l in enumerate(lens.tolist()):
+            x[i, ..., l:] = 0
+    ref, rl = om.forward(x, lens)
+    m = kb.TorchVGSLModel(vgsl=spec)
+    m.load_state_dict(wts)
+    m.to('cuda:0')
+    out, ol = m.nn(x.cuda(), lens)
+    assert rel_err(out, ref) <= TIGHT, rel_err(out, ref)
+    if lens is not None:
+        assert ol.tolist() == rl.tolist()
+        _, _, _, ref_dec = vo.rec_predict(om, x, lens)
+        assert triples(kb.TorchSeqRecognizer(m, device='cuda:0').predict_labels(x, lens)) == triples(ref_dec)
+
+
+def test_generic_recurrence_matches_resident_kernels():
+    """KB_LSTM_GENERIC=1 forces the per-step path for sizes the resident-weight kernels take: same results."""
+    spec = '[1,16,0,1 Cr3,3,32 Mp2,2 S1(1x0)1,3 Lbx200 O1c30]'
+    om = vo.OracleModel(spec)
+    wts = om.init_like_reference(62)
+    g = torch.Generator().manual_seed(62)
+    x = torch.rand(6, 1, 16, 120, generator=g)
+    lens = torch.tensor([120, 64, 120, 33, 90, 7])
+    for i, l in enumerate(lens.tolist()):
+        x[i, ..., l:] = 0
+    ref, _ = om.forward(x, lens)
+    with env(KB_LSTM_GENERIC=1):
+        m = kb.TorchVGSLModel(vgsl=spec)
+        m.load_state_dict(wts)
+        m.to('cuda:0')                                   # the transposed W_hh is built at finalize
+        out, _ = m.nn(x.cuda(), lens)
+    assert rel_err(out, ref) <= TIGHT
+    out2, _ = m.nn(x.cuda(), lens)                       # default kernels on the same handle
+    assert rel_err(out2, ref) <= TIGHT
