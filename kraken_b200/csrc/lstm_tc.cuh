@@ -41,7 +41,7 @@ constexpr int NG = 2;                                    // independent line gro
 constexpr int LCS = 8;                                   // cluster size
 constexpr int A_PLANE_ELEMS = 128 * 256;                 // fp16 elements of one W plane of a CTA: [128 gate rows][K = 256], row-major
 constexpr int EW = 4;                                    // epilogue warps per TMEM lane quarter: 2 per group (latency hiding: v3 with 1 was 2x slower)
-constexpr int LTHREADS = 64 + 4 * EW * 32;               // warp 0: MMA issue of the W1 chains / TMEM alloc; warps 1..16: epilogue; warp 17: W2s chains
+constexpr int LTHREADS = 128 + 4 * EW * 32;              // warp 0: MMA issuer + TMEM alloc; warps 1..16: epilogue; warps 17..19: the other three MMA issuers
 constexpr int TM_COLS = 512;
 template <int GL> struct ClusterCfg {                    // GL = lines per group: 8 (16 lines per cluster) or 16 (32 lines per cluster)
     static constexpr int NL = NG * GL;                   // lines per cluster
@@ -51,7 +51,8 @@ template <int GL> struct ClusterCfg {                    // GL = lines per group
     static constexpr int CH_B = 2 * GL * 16;             // bytes of one k-chunk (8 unit slots) of a group = the two warps' blocks
     static constexpr int B_BUF_B = 32 * CH_B;            // bytes per (group, buffer): K = 256 = 32 chunks
     static constexpr int SX_BYTES = NG * 2 * 4 * CH_B;   // outgoing staging per group, double buffered: this CTA's 4 k-chunks, laid out as in the operand
-    static constexpr int SMEM_BYTES = NG * 2 * B_BUF_B + SX_BYTES + 128 + 1024;
+    static constexpr int SRC_B = 4 * CH_B;               // bytes one source CTA contributes to a buffer (its 4 k-chunks)
+    static constexpr int SMEM_BYTES = NG * 2 * B_BUF_B + SX_BYTES + 512 + 1024;
     static constexpr int N1 = 2 * GL;                    // N of both products (W2s x the same operand rows; only its h1 columns are read)
     static constexpr int GSTRIDE = 4 * N1;               // TMEM columns per group: D1a @0, D1b @N1, D2a @2 N1, D2b @3 N1
     static constexpr int TM_A0 = NG * GSTRIDE;           // A: W1 @TM_A0 (128 columns), W2s @TM_A0 + 128
@@ -172,8 +173,8 @@ __global__ void __launch_bounds__(LTHREADS, 1) k_lstm_rec_tc(LstmTcParams p) {
     uint8_t *sB = smem;                                   // [group][buffer][k-chunk][row = (warp half, plane, line)][8 unit slots] fp16, no swizzle
     uint8_t *sx = sB + NG * 2 * B_BUF_B;                  // [group][2][quarter = k-chunk][warp half][plane][line][8 unit slots]
     uint64_t *bars = reinterpret_cast<uint64_t *>(sB + NG * 2 * B_BUF_B + Cfg::SX_BYTES);
-    uint64_t *b_full = bars /* [group][2] */, *mma_done = bars + 4 /* [group][chain owner: W1 / W2s] */;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 8);
+    uint64_t *b_full = bars /* [group][buffer][source CTA] */, *mma_done = bars + 32 /* [group][chain = product * 2 + K half] */;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 40);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint32_t rank;
@@ -182,10 +183,11 @@ __global__ void __launch_bounds__(LTHREADS, 1) k_lstm_rec_tc(LstmTcParams p) {
     const int hid = p.hid, GC = p.dirs * 4 * hid, OC = p.dirs * hid;
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < 4; ++i) { mbar_init(&b_full[i], 1); mbar_init(&mma_done[i], 1); }
+        for (int i = 0; i < 32; ++i) mbar_init(&b_full[i], 1);
+        for (int i = 0; i < 8; ++i) mbar_init(&mma_done[i], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        mbar_expect_tx(&b_full[1], B_BUF_B);             // buffer 1 of each group receives h_0 at the end of step 0
-        mbar_expect_tx(&b_full[3], B_BUF_B);
+        for (int g = 0; g < NG; ++g)
+            for (int src = 0; src < LCS; ++src) mbar_expect_tx(&b_full[(g * 2 + 1) * 8 + src], Cfg::SRC_B);   // buffer 1 of each group receives h_0 at the end of step 0
     }
     for (int i = threadIdx.x; i < NG * 2 * B_BUF_B / 16; i += LTHREADS) reinterpret_cast<uint4 *>(sB)[i] = make_uint4(0, 0, 0, 0);   // h_{-1} = 0
     if (warp == 0) {
@@ -226,49 +228,56 @@ __global__ void __launch_bounds__(LTHREADS, 1) k_lstm_rec_tc(LstmTcParams p) {
         if (q < p.nseq) maxlen = max(maxlen, p.lens ? min(max(p.lens[q], 0), p.T) : p.T);
     }
 
-    if (warp == 0 || warp == 17) {
-        // ===================== two MMA issuers (round 1 had one: 32 tiny MMAs per group and step took 650-1000 cycles to ISSUE, the
-        // products finished 50 cycles later).  Warp 0 issues the W1 x [h1|h2s] chains, warp 17 the W2s x [h1|..] chains; both alternate
-        // between the two line groups and commit to their own mbarrier.
-        const int own = warp == 0 ? 0 : 1;
+    if (warp == 0 || warp >= 17) {
+        // ===================== four MMA issuers, one per accumulator chain: product (W1 x [h1|h2s] / W2s x [h1|..]) x K half (the unit
+        // slots of source CTAs 0..3 / 4..7).  Every source CTA's piece of h_{t-1} (its 4 k-chunks = two K16 steps) has its own mbarrier,
+        // so an issuer multiplies a piece as soon as it has landed - its own CTA's first - instead of waiting for the slowest sender
+        // and then issuing everything: round 1 had ONE issuer and one barrier (32 MMAs = 650-1000 cycles of issue on the critical path
+        // of every step), the first version of this round two issuers (16 MMAs each, ~500 cycles).
+        const int chain = warp == 0 ? 0 : warp - 16;          // 0..3
+        const int prod = chain & 1, half = chain >> 1;
         const uint32_t id1 = idesc_f16(0, 0, 128, N1);
+        const int start = ((int)rank >> 2) == half ? ((int)rank & 3) : 0;      // begin with the local piece when it belongs to this half
         for (int s = 0; s < maxlen; ++s) {
             const int cur = s & 1;
 #pragma unroll 1
             for (int g = 0; g < NG; ++g) {
-                uint64_t *bf = &b_full[g * 2 + cur];
-                const long long d_w0 = (p.dbg & 1) ? clock64() : 0;
-                if (s > 0) {                                                     // default acquire.cta: an acquire.cluster wait costs a CCTL.IVALL per step
-                    if (p.dbg & 2) mbar_wait(bf, (uint32_t)(((s - 1) >> 1) & 1));
-                    else mbar_wait_poll(bf, (uint32_t)(((s - 1) >> 1) & 1));
-                }
-                const long long d_w1 = (p.dbg & 1) ? clock64() : 0;
-                // h arrives by bulk copies (async proxy) and is read by the MMAs (async proxy): no cross-proxy fence on this path (the
-                // fence.proxy.async that stood here compiles to MEMBAR.ALL.CTA + FENCE.VIEW.ASYNC on the critical path of every step)
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                if (elect_one()) {
-                    const uint32_t b0 = smem_u32(sB + (g * 2 + cur) * B_BUF_B);
-                    const uint32_t dg = tmem_base + (uint32_t)(g * GSTRIDE + own * 2 * N1);
-                    const uint32_t abase = tmem_base + (uint32_t)(TM_A0 + own * 128);
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-#pragma unroll
-                        for (int kk = 0; kk < 4; ++kk) {
-                            const int ka = kk == 0 ? 0 : kk == 1 ? 2 : kk == 2 ? 1 : 3;      // 0,2,1,3: alternate between the two chains
-                            const int half = ka >> 1;
-                            const uint64_t bd = umma_desc_nosw(b0 + (uint32_t)((ka * 4 + k) * 2 * CH_B), (uint32_t)CH_B, 128u);   // K16 = chunks 2j, 2j+1
-                            const uint32_t first = ((ka & 1) == 0 && k == 0) ? 0u : 1u;
-                            umma_f16_ts(dg + (uint32_t)(half * N1), abase + (uint32_t)(ka * 32 + k * 8), bd, id1, first);   // K = 16 -> 8 columns of fp16 pairs
-                        }
+                const uint32_t b0 = smem_u32(sB + (g * 2 + cur) * B_BUF_B);
+                const uint32_t dacc = tmem_base + (uint32_t)(g * GSTRIDE + prod * 2 * N1 + half * N1);
+                const uint32_t abase = tmem_base + (uint32_t)(TM_A0 + prod * 128);
+                long long d_w0 = 0, d_w1 = 0;
+#pragma unroll 1
+                for (int i = 0; i < 4; ++i) {
+                    const int src = half * 4 + ((start + i) & 3);
+                    uint64_t *bf = &b_full[(g * 2 + cur) * 8 + src];
+                    if (i == 3) d_w0 = (p.dbg & 1) ? clock64() : 0;
+                    if (s > 0) {                                                 // default acquire.cta: an acquire.cluster wait costs a CCTL.IVALL per step
+                        if (p.dbg & 2) mbar_wait(bf, (uint32_t)(((s - 1) >> 1) & 1));
+                        else mbar_wait_poll(bf, (uint32_t)(((s - 1) >> 1) & 1));
                     }
-                    umma_commit(&mma_done[g * 2 + own]);
-                    // this buffer is refilled during step s+1 (nobody can send that before receiving our h_s); the W1 issuer re-arms it.
-                    // Both issuers have passed their wait on this phase by the time the next one can complete (the epilogue needs both
-                    // chains before any CTA can send h_s).
-                    if (own == 0 && s + 2 < maxlen) mbar_expect_tx(bf, B_BUF_B);
-                    if ((p.dbg & 1) && blockIdx.x == 0 && blockIdx.y == 0 && s >= 100 && s < 104) {
+                    if (i == 3) d_w1 = (p.dbg & 1) ? clock64() : 0;
+                    // h arrives by bulk copies (async proxy) and is read by the MMAs (async proxy): no cross-proxy fence on this path (a
+                    // fence.proxy.async here compiles to MEMBAR.ALL.CTA + FENCE.VIEW.ASYNC on the critical path of every step)
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    if (elect_one()) {
+#pragma unroll
+                        for (int jj = 0; jj < 2; ++jj) {
+                            const int j = 2 * src + jj;                                  // K16 step = k-chunks 2j, 2j+1
+                            const uint64_t bd = umma_desc_nosw(b0 + (uint32_t)(j * 2 * CH_B), (uint32_t)CH_B, 128u);
+                            umma_f16_ts(dacc, abase + (uint32_t)(j * 8), bd, id1, (i | jj) ? 1u : 0u);    // K = 16 -> 8 columns of fp16 pairs
+                        }
+                        // this piece is refilled during step s+1 (nobody can send that before receiving our h_s); the W1 issuer of the half
+                        // re-arms its barrier.  The W2s issuer has passed (or will see as completed) this phase: the next one cannot
+                        // complete before every chain of this step is done.
+                        if (prod == 0 && s + 2 < maxlen) mbar_expect_tx(bf, Cfg::SRC_B);
+                    }
+                    __syncwarp();
+                }
+                if (elect_one()) {
+                    umma_commit(&mma_done[g * 4 + chain]);
+                    if ((p.dbg & 1) && chain == 0 && blockIdx.x == 0 && blockIdx.y == 0 && s >= 100 && s < 104) {
                         long long *d = p.dbgbuf + ((s - 100) * 2 + g) * 8;
-                        if (own == 0) { d[0] = d_w0; d[1] = d_w1; d[2] = clock64(); }
+                        d[0] = d_w0; d[1] = d_w1; d[2] = clock64();
                     }
                 }
                 __syncwarp();
@@ -322,7 +331,7 @@ __global__ void __launch_bounds__(LTHREADS, 1) k_lstm_rec_tc(LstmTcParams p) {
         // per warp: a UBLKCP takes uniform-register operands, so the 8 lanes ran as an 8-iteration loop of ELECT / R2UR / UBLKCP,
         // ~500 cycles per step on the critical path.)
         const int wi = (sw2 << 2) | q;                                                    // 0..7 within the group
-        const uint32_t dstB = mapa32(smem_u32(sB), (uint32_t)wi), dstFull = mapa32(smem_u32(b_full), (uint32_t)wi);
+        const uint32_t dstB = mapa32(smem_u32(sB), (uint32_t)wi), dstFull = mapa32(smem_u32(b_full), (uint32_t)wi) + (uint32_t)rank * 8u;   // our piece's barrier at CTA wi
         uint8_t *sxg = sx + g * 2 * 4 * CH_B;
         const int sxw_off = q * CH_B + sw2 * WB_B;                                        // this warp's rows of this quarter's k-chunk
         // this warp's accumulator columns: rows of the operand = [warp half][plane][line]
@@ -337,8 +346,11 @@ __global__ void __launch_bounds__(LTHREADS, 1) k_lstm_rec_tc(LstmTcParams p) {
 #pragma unroll
             for (int i = 0; i < LPW; ++i) gxv[i] = gxn[i];
             const long long e_top = (p.dbg & 1) ? clock64() : 0;
-            if (p.dbg & 4) { mbar_wait_poll(&mma_done[g * 2], (uint32_t)(s & 1)); mbar_wait_poll(&mma_done[g * 2 + 1], (uint32_t)(s & 1)); }
-            else { mbar_wait(&mma_done[g * 2], (uint32_t)(s & 1)); mbar_wait(&mma_done[g * 2 + 1], (uint32_t)(s & 1)); }
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                if (p.dbg & 4) mbar_wait_poll(&mma_done[g * 4 + c], (uint32_t)(s & 1));
+                else mbar_wait(&mma_done[g * 4 + c], (uint32_t)(s & 1));
+            }
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const long long e_done = (p.dbg & 1) ? clock64() : 0;
             // group columns: D1a = W1 x rows (k-atoms 0,1) @0, D1b (k-atoms 2,3) @N1, D2a = W2s x rows @2 N1, D2b @3 N1; within the warp's
@@ -393,7 +405,7 @@ __global__ void __launch_bounds__(LTHREADS, 1) k_lstm_rec_tc(LstmTcParams p) {
             const long long e_cell = (p.dbg & 1) ? clock64() : 0;
             if (s + 1 < maxlen && lane == 0)
                 bulk_s2s(dstB + (uint32_t)((g * 2 + nxt) * B_BUF_B) + kc_off, smem_u32(sxg + (s & 1) * 4 * CH_B), (uint32_t)(4 * CH_B),
-                         dstFull + (uint32_t)(g * 2 + nxt) * 8u);
+                         dstFull + (uint32_t)((g * 2 + nxt) * 8) * 8u);
 #pragma unroll
             for (int t = 0; t < NT; ++t)
                 if (wr[t]) {
