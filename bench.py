@@ -368,6 +368,9 @@ def main():
     ap.add_argument('--cfg5-lines', type=int, default=100000)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'b200' else args.warmup
+    # a hung kernel or a lost pipeline ticket must not sit on the GPU box until its time limit: dump every thread's stack and exit
+    import faulthandler
+    faulthandler.dump_traceback_later(int(os.environ.get('KB_BENCH_WATCHDOG', '1200')), exit=True)
 
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))

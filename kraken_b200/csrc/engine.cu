@@ -715,9 +715,9 @@ struct Exec {
                         cudaFree(tp.dbgbuf);
                         const long long t0 = hb[1];
                         for (int i = 0; i < 8; ++i) {
-                            const long long *d = hb + i * 8;
-                            fprintf(stderr, "[tcrec] step %d group %d: mma_wait_from %lld  h_ready %lld  mma_issued %lld | epi_loop_top %lld  mma_done %lld  act_end %lld  staged %lld  fenced %lld  barrier(cell_end) %lld  sent %lld\n",
-                                    100 + i / 2, i & 1, d[0] - t0, d[1] - t0, d[2] - t0, d[7] - t0, d[3] - t0, d[4] - t0, hb[64 + 2 * i] - t0, hb[65 + 2 * i] - t0, d[5] - t0, d[6] - t0);
+                            const long long *d = hb + i * 12;
+                            fprintf(stderr, "[tcrec] step %d group %d: issuer: wait_from %lld  h_ready %lld  issued %lld | epilogue: loop_top %lld  mma_done %lld  tmem_read %lld  act_end %lld  cell+gather %lld  sent %lld  loop_end %lld\n",
+                                    100 + i / 2, i & 1, d[0] - t0, d[1] - t0, d[2] - t0, d[3] - t0, d[4] - t0, d[5] - t0, d[6] - t0, d[7] - t0, d[8] - t0, d[9] - t0);
                         }
                     }
                     ++m->launches;
@@ -1230,7 +1230,8 @@ static size_t decode_enqueue(int n, int T, int max_out, const int *d_lab, const 
     char *d = (char *)arena.alloc(blk);
     int *o_lab = (int *)d, *o_start = (int *)(d + per * 4), *o_end = (int *)(d + per * 8);
     float *o_conf = (float *)(d + per * 12); int *o_cnt = (int *)(d + per * 16);
-    k_ctc_collapse<<<(unsigned)n, 256, (size_t)((T + 31) / 32 + 1) * sizeof(int), st>>>(d_lab, d_conf, d_lens, n, T, max_out, o_lab, o_start, o_end, o_conf, o_cnt);
+    const int staged = (size_t)T * 8 <= 40 * 1024;           // labels + confidences of one line in shared memory
+    k_ctc_collapse<<<(unsigned)n, 256, (size_t)((T + 31) / 32 + 1 + (staged ? 2 * T : 0)) * sizeof(int), st>>>(d_lab, d_conf, d_lens, n, T, max_out, o_lab, o_start, o_end, o_conf, o_cnt, staged);
     ++*launches;
     CK(cudaPeekAtLastError());
     if (blk > *pinned_cap) {

@@ -37,22 +37,22 @@ namespace ltc {
 
 using namespace kb::tc;
 
-constexpr int NG = 2;                                    // independent line groups per cluster, processed in ping-pong (version 5)
+constexpr int NG = 2;                                    // independent line groups per cluster (own issuers, barriers, accumulators, epilogue warps)
 constexpr int LCS = 8;                                   // cluster size
 constexpr int A_PLANE_ELEMS = 128 * 256;                 // fp16 elements of one W plane of a CTA: [128 gate rows][K = 256], row-major
 constexpr int EW = 4;                                    // epilogue warps per TMEM lane quarter: 2 per group (latency hiding: v3 with 1 was 2x slower)
-constexpr int LTHREADS = 128 + 4 * EW * 32;              // warp 0: MMA issuer + TMEM alloc; warps 1..16: epilogue; warps 17..19: the other three MMA issuers
+constexpr int N_ISSUE = 8;                               // MMA issuer warps: [group][K half][product]
+constexpr int LTHREADS = (N_ISSUE + 4 * EW) * 32;        // warps 0..7: MMA issuers (warp 0 also owns the TMEM allocation); warps 8..23: epilogue
 constexpr int TM_COLS = 512;
 template <int GL> struct ClusterCfg {                    // GL = lines per group: 8 (16 lines per cluster) or 16 (32 lines per cluster)
     static constexpr int NL = NG * GL;                   // lines per cluster
     static constexpr int LPW = GL / 2;                   // lines per epilogue warp (two warps per TMEM lane quarter and group)
     static constexpr int NT = LPW / 4;                   // 4x4 gate transposes (= cells) per thread and step
-    static constexpr int WB_B = 2 * LPW * 16;            // bytes an epilogue warp contributes to a k-chunk: [h1 of its lines | h2s of its lines] x 16 B
-    static constexpr int CH_B = 2 * GL * 16;             // bytes of one k-chunk (8 unit slots) of a group = the two warps' blocks
+    static constexpr int CH_B = 2 * GL * 16;             // bytes of one k-chunk (8 unit slots) of a group: rows [warp half][plane][line] x 16 B
     static constexpr int B_BUF_B = 32 * CH_B;            // bytes per (group, buffer): K = 256 = 32 chunks
-    static constexpr int SX_BYTES = NG * 2 * 4 * CH_B;   // outgoing staging per group, double buffered: this CTA's 4 k-chunks, laid out as in the operand
     static constexpr int SRC_B = 4 * CH_B;               // bytes one source CTA contributes to a buffer (its 4 k-chunks)
-    static constexpr int SMEM_BYTES = NG * 2 * B_BUF_B + SX_BYTES + 512 + 1024;
+    static constexpr int HALF_B = 4 * SRC_B;             // bytes the four source CTAs of a K half deliver
+    static constexpr int SMEM_BYTES = NG * 2 * B_BUF_B + 512 + 1024;
     static constexpr int N1 = 2 * GL;                    // N of both products (W2s x the same operand rows; only its h1 columns are read)
     static constexpr int GSTRIDE = 4 * N1;               // TMEM columns per group: D1a @0, D1b @N1, D2a @2 N1, D2b @3 N1
     static constexpr int TM_A0 = NG * GSTRIDE;           // A: W1 @TM_A0 (128 columns), W2s @TM_A0 + 128
@@ -63,7 +63,7 @@ struct LstmTcParams {
     __half *out_hi, *out_lo;         // optional fp16 operand planes of the output for a tensor-core consumer (out may then be NULL)
     int nseq, T, hid, dirs, U;
     int q2; long long s_outer, s_inner, step;
-    int dbg; long long *dbgbuf;      // KB_LSTM_DBG: bit 0 = clock64 stamps of steps 100..103 of cluster 0 into dbgbuf[step][group][8]
+    int dbg; long long *dbgbuf;      // KB_LSTM_DBG: bit 0 = clock64 stamps of steps 100..103 of cluster 0 into dbgbuf[step][group][12]
 };
 
 __device__ __forceinline__ void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
@@ -89,31 +89,18 @@ __device__ __forceinline__ void tmem_ld8_nowait(uint32_t taddr, uint32_t *r) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                  : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "r"(taddr));
 }
-__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
 __device__ __forceinline__ uint32_t mapa32(uint32_t saddr, uint32_t rank) {
     uint32_t r;
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
     return r;
 }
+// 16 bytes from registers into the shared memory of a CTA of the cluster, byte-counted by an mbarrier in that CTA
 __device__ __forceinline__ void st_async_v4(uint32_t raddr, uint4 v, uint32_t rmbar) {
     asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];"
                  ::"r"(raddr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "r"(rmbar) : "memory");
 }
-__device__ __forceinline__ void mbar_wait_cluster(uint64_t *bar, uint32_t parity) {      // acquire at cluster scope (remote st.async)
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "CW_%=:\n\t"
-        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra CD_%=;\n\t"
-        "bra CW_%=;\n\t"
-        "CD_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
 // K-major operand WITHOUT swizzle: core matrices (8 rows x 16 bytes, 128 contiguous bytes) `lbo` bytes apart along K and `sbo`
-// bytes apart along M/N.  The h operand uses it because one (CTA, lane quarter) produces exactly whole core matrices (8 lines x
-// 8 unit slots per plane), so its share of the hand-off is ONE contiguous block per destination.
+// bytes apart along M/N.  The h operand uses it because one 16-byte store = 8 unit slots of one line = one row of a core matrix.
 __device__ __forceinline__ uint64_t umma_desc_nosw(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
     uint64_t d = 0;
     d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
@@ -121,23 +108,6 @@ __device__ __forceinline__ uint64_t umma_desc_nosw(uint32_t saddr, uint32_t lbo,
     d |= (uint64_t)(sbo >> 4) << 32;
     d |= (uint64_t)1 << 46;                           // descriptor version (sm_100); layout type 0 = no swizzle
     return d;
-}
-// shared::cta -> (remote) shared::cluster bulk copy, byte-counted by the destination's mbarrier: one transaction per block
-// instead of one per 16 bytes (512 st.async.v4 per buffer and step made the hand-off ~1100 cycles, KB_LSTM_DBG=1)
-__device__ __forceinline__ void bulk_s2s(uint32_t dst_cluster, uint32_t src_cta, uint32_t bytes, uint32_t mbar_cluster) {
-    asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(dst_cluster), "r"(src_cta), "r"(bytes), "r"(mbar_cluster) : "memory");
-}
-// non-suspending poll (mbarrier.test_wait): try_wait may park the warp for an implementation-defined time, and on the critical
-// path of the recurrence (h hand-off -> MMA issue -> epilogue) the wake-up latency is paid twice per time step
-__device__ __forceinline__ void mbar_wait_poll(uint64_t *bar, uint32_t parity) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "PW_%=:\n\t"
-        "mbarrier.test_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra PD_%=;\n\t"
-        "bra PW_%=;\n\t"
-        "PD_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
 // gate non-linearities on the SFU: ex2.approx + rcp, absolute error ~1e-7 (the CUDA-core kernel keeps expf/tanhf)
 __device__ __forceinline__ float rcp_fast(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }   // MUFU.RCP, no IEEE fix-up path
@@ -162,19 +132,42 @@ __device__ __forceinline__ void quad_transpose4(float (&v)[4], int gq) {
         v[0] = b1 ? ra : v[0]; v[2] = b1 ? v[2] : ra; v[1] = b1 ? rb : v[1]; v[3] = b1 ? v[3] : rb;
     }
 }
+// The eight lanes that share (lane & 3) hold one line's h for unit slots jq = lane >> 2 = 0..7 as (h1, h2s) halves.  After three
+// butterfly rounds (7 shuffles) EVERY one of them holds the line's two complete 16-byte operand rows [8 unit slots] of the h1 and
+// the h2s plane - so lane jq can hand them to CTA jq of the cluster.
+__device__ __forceinline__ void gather_rows8(__half h1, __half h2, int lane, uint4 &row1, uint4 &row2) {
+    const uint32_t my = (uint32_t)__half_as_ushort(h1) | ((uint32_t)__half_as_ushort(h2) << 16);
+    const uint32_t ot = __shfl_xor_sync(0xffffffffu, my, 4);
+    const bool b0 = lane & 4, b1 = lane & 8, b2 = lane & 16;
+    const uint32_t lo = b0 ? ot : my, hi = b0 ? my : ot;                     // unit slots (jq & ~1), (jq | 1)
+    const uint32_t p1 = (lo & 0xffffu) | (hi << 16), p2 = (lo >> 16) | (hi & 0xffff0000u);
+    const uint32_t o1 = __shfl_xor_sync(0xffffffffu, p1, 8), o2 = __shfl_xor_sync(0xffffffffu, p2, 8);
+    const uint32_t a0 = b1 ? o1 : p1, a1 = b1 ? p1 : o1, c0 = b1 ? o2 : p2, c1 = b1 ? p2 : o2;
+    const uint32_t ra0 = __shfl_xor_sync(0xffffffffu, a0, 16), ra1 = __shfl_xor_sync(0xffffffffu, a1, 16);
+    const uint32_t rc0 = __shfl_xor_sync(0xffffffffu, c0, 16), rc1 = __shfl_xor_sync(0xffffffffu, c1, 16);
+    row1 = b2 ? make_uint4(ra0, ra1, a0, a1) : make_uint4(a0, a1, ra0, ra1);
+    row2 = b2 ? make_uint4(rc0, rc1, c0, c1) : make_uint4(c0, c1, rc0, rc1);
+}
 
+// Synchronisation of one (group, time step), all through mbarriers, no CTA- or cluster-wide barrier in the loop:
+//   b_half[g][buffer][K half]  tx-count barrier: the 4 KB of h_{s-1} planes the four source CTAs of a K half store (st.async from
+//                              registers, 16 bytes per store) into this CTA's operand buffer.  Waited on by the half's two issuers;
+//                              re-armed for the refill two steps later by the W1 issuer once it has passed it (nobody can send that
+//                              refill before receiving this CTA's h_s, which needs all four chains of this step).
+//   acc_free[g]                8 arrivals: the group's epilogue warps have read the accumulators of the previous step (an issuer
+//                              whose K half does not contain this CTA's own piece could otherwise overwrite them too early).
+//   mma_done[g]                4 arrivals (tcgen05.commit of the four chains): accumulators complete.
 template <int GL>
 __global__ void __launch_bounds__(LTHREADS, 1) k_lstm_rec_tc(LstmTcParams p) {
     using Cfg = ClusterCfg<GL>;
-    constexpr int NL = Cfg::NL, CH_B = Cfg::CH_B, B_BUF_B = Cfg::B_BUF_B, WB_B = Cfg::WB_B, LPW = Cfg::LPW, NT = Cfg::NT;
+    constexpr int NL = Cfg::NL, CH_B = Cfg::CH_B, B_BUF_B = Cfg::B_BUF_B, LPW = Cfg::LPW, NT = Cfg::NT;
     constexpr int TM_A0 = Cfg::TM_A0, GSTRIDE = Cfg::GSTRIDE, N1 = Cfg::N1;
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = smem_align1024(smem_raw);
     uint8_t *sB = smem;                                   // [group][buffer][k-chunk][row = (warp half, plane, line)][8 unit slots] fp16, no swizzle
-    uint8_t *sx = sB + NG * 2 * B_BUF_B;                  // [group][2][quarter = k-chunk][warp half][plane][line][8 unit slots]
-    uint64_t *bars = reinterpret_cast<uint64_t *>(sB + NG * 2 * B_BUF_B + Cfg::SX_BYTES);
-    uint64_t *b_full = bars /* [group][buffer][source CTA] */, *mma_done = bars + 32 /* [group][chain = product * 2 + K half] */;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 40);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sB + NG * 2 * B_BUF_B);
+    uint64_t *b_half = bars /* [group][buffer][K half] */, *mma_done = bars + 8 /* [group] */, *acc_free = bars + 10 /* [group] */;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 12);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint32_t rank;
@@ -183,11 +176,11 @@ __global__ void __launch_bounds__(LTHREADS, 1) k_lstm_rec_tc(LstmTcParams p) {
     const int hid = p.hid, GC = p.dirs * 4 * hid, OC = p.dirs * hid;
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < 32; ++i) mbar_init(&b_full[i], 1);
-        for (int i = 0; i < 8; ++i) mbar_init(&mma_done[i], 1);
+        for (int i = 0; i < 8; ++i) mbar_init(&b_half[i], 1);
+        for (int g = 0; g < NG; ++g) { mbar_init(&mma_done[g], 4); mbar_init(&acc_free[g], 2 * 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         for (int g = 0; g < NG; ++g)
-            for (int src = 0; src < LCS; ++src) mbar_expect_tx(&b_full[(g * 2 + 1) * 8 + src], Cfg::SRC_B);   // buffer 1 of each group receives h_0 at the end of step 0
+            for (int hf = 0; hf < 2; ++hf) mbar_expect_tx(&b_half[(g * 2 + 1) * 2 + hf], Cfg::HALF_B);   // buffer 1 of each group receives h_0 at the end of step 0
     }
     for (int i = threadIdx.x; i < NG * 2 * B_BUF_B / 16; i += LTHREADS) reinterpret_cast<uint4 *>(sB)[i] = make_uint4(0, 0, 0, 0);   // h_{-1} = 0
     if (warp == 0) {
@@ -199,7 +192,7 @@ __global__ void __launch_bounds__(LTHREADS, 1) k_lstm_rec_tc(LstmTcParams p) {
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
-    if (warp >= 1 && warp <= 4) {
+    if (warp >= N_ISSUE && warp < N_ISSUE + 4) {
         // W_hh planes -> tensor memory: this thread's gate row (TMEM lane 32q + lane), K pairs packed low|high per column
         const int m = 32 * (warp & 3) + lane;
         const uint32_t *src = reinterpret_cast<const uint32_t *>(p.wpk) + (((size_t)dir * LCS + rank) * 2 * A_PLANE_ELEMS) / 2 + (size_t)m * 128;
@@ -227,68 +220,49 @@ __global__ void __launch_bounds__(LTHREADS, 1) k_lstm_rec_tc(LstmTcParams p) {
         const int q = chunk * NL + lb;
         if (q < p.nseq) maxlen = max(maxlen, p.lens ? min(max(p.lens[q], 0), p.T) : p.T);
     }
+    const bool dbg_cta = (p.dbg & 1) && blockIdx.x == 0 && blockIdx.y == 0;
 
-    if (warp == 0 || warp >= 17) {
-        // ===================== four MMA issuers, one per accumulator chain: product (W1 x [h1|h2s] / W2s x [h1|..]) x K half (the unit
-        // slots of source CTAs 0..3 / 4..7).  Every source CTA's piece of h_{t-1} (its 4 k-chunks = two K16 steps) has its own mbarrier,
-        // so an issuer multiplies a piece as soon as it has landed - its own CTA's first - instead of waiting for the slowest sender
-        // and then issuing everything: round 1 had ONE issuer and one barrier (32 MMAs = 650-1000 cycles of issue on the critical path
-        // of every step), the first version of this round two issuers (16 MMAs each, ~500 cycles).
-        const int chain = warp == 0 ? 0 : warp - 16;          // 0..3
-        const int prod = chain & 1, half = chain >> 1;
+    if (warp < N_ISSUE) {
+        // ===================== eight MMA issuers, one per (group, K half, product) = one per accumulator chain: W1 x [h1|h2s] and
+        // W2s x [h1|..] over the unit slots of source CTAs 0..3 / 4..7, 8 dependent M128 x N(2 GL) x K16 MMAs each.  Round 1 had ONE
+        // issuer for everything (64 MMAs per step = 650-1000 cycles of issue on the critical path of every step).
+        const int g = warp >> 2, chain = warp & 3, half = chain >> 1, prod = chain & 1;
         const uint32_t id1 = idesc_f16(0, 0, 128, N1);
-        const int start = ((int)rank >> 2) == half ? ((int)rank & 3) : 0;      // begin with the local piece when it belongs to this half
+        const uint32_t dacc = tmem_base + (uint32_t)(g * GSTRIDE + prod * 2 * N1 + half * N1);
+        const uint32_t abase = tmem_base + (uint32_t)(TM_A0 + prod * 128 + half * 64);    // K16 step = 8 columns of fp16 pairs
         for (int s = 0; s < maxlen; ++s) {
             const int cur = s & 1;
-#pragma unroll 1
-            for (int g = 0; g < NG; ++g) {
-                const uint32_t b0 = smem_u32(sB + (g * 2 + cur) * B_BUF_B);
-                const uint32_t dacc = tmem_base + (uint32_t)(g * GSTRIDE + prod * 2 * N1 + half * N1);
-                const uint32_t abase = tmem_base + (uint32_t)(TM_A0 + prod * 128);
-                long long d_w0 = 0, d_w1 = 0;
-#pragma unroll 1
-                for (int i = 0; i < 4; ++i) {
-                    const int src = half * 4 + ((start + i) & 3);
-                    uint64_t *bf = &b_full[(g * 2 + cur) * 8 + src];
-                    if (i == 3) d_w0 = (p.dbg & 1) ? clock64() : 0;
-                    if (s > 0) {                                                 // default acquire.cta: an acquire.cluster wait costs a CCTL.IVALL per step
-                        if (p.dbg & 2) mbar_wait(bf, (uint32_t)(((s - 1) >> 1) & 1));
-                        else mbar_wait_poll(bf, (uint32_t)(((s - 1) >> 1) & 1));
-                    }
-                    if (i == 3) d_w1 = (p.dbg & 1) ? clock64() : 0;
-                    // h arrives by bulk copies (async proxy) and is read by the MMAs (async proxy): no cross-proxy fence on this path (a
-                    // fence.proxy.async here compiles to MEMBAR.ALL.CTA + FENCE.VIEW.ASYNC on the critical path of every step)
-                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    if (elect_one()) {
-#pragma unroll
-                        for (int jj = 0; jj < 2; ++jj) {
-                            const int j = 2 * src + jj;                                  // K16 step = k-chunks 2j, 2j+1
-                            const uint64_t bd = umma_desc_nosw(b0 + (uint32_t)(j * 2 * CH_B), (uint32_t)CH_B, 128u);
-                            umma_f16_ts(dacc, abase + (uint32_t)(j * 8), bd, id1, (i | jj) ? 1u : 0u);    // K = 16 -> 8 columns of fp16 pairs
-                        }
-                        // this piece is refilled during step s+1 (nobody can send that before receiving our h_s); the W1 issuer of the half
-                        // re-arms its barrier.  The W2s issuer has passed (or will see as completed) this phase: the next one cannot
-                        // complete before every chain of this step is done.
-                        if (prod == 0 && s + 2 < maxlen) mbar_expect_tx(bf, Cfg::SRC_B);
-                    }
-                    __syncwarp();
-                }
-                if (elect_one()) {
-                    umma_commit(&mma_done[g * 4 + chain]);
-                    if ((p.dbg & 1) && chain == 0 && blockIdx.x == 0 && blockIdx.y == 0 && s >= 100 && s < 104) {
-                        long long *d = p.dbgbuf + ((s - 100) * 2 + g) * 8;
-                        d[0] = d_w0; d[1] = d_w1; d[2] = clock64();
-                    }
-                }
-                __syncwarp();
+            uint64_t *bh = &b_half[(g * 2 + cur) * 2 + half];
+            const long long d_w0 = dbg_cta ? clock64() : 0;
+            if (s > 0) {
+                mbar_wait(&acc_free[g], (uint32_t)((s - 1) & 1));            // complete long before h_{s-1} can arrive
+                mbar_wait(bh, (uint32_t)(((s - 1) >> 1) & 1));               // default acquire.cta: an acquire.cluster wait costs a CCTL.IVALL per step
             }
+            const long long d_w1 = dbg_cta ? clock64() : 0;
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // st.async writes (generic proxy) -> UMMA reads (async proxy)
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (elect_one()) {
+                const uint32_t b0 = smem_u32(sB + (g * 2 + cur) * B_BUF_B) + (uint32_t)(half * 16 * CH_B);
+#pragma unroll
+                for (int jj = 0; jj < 8; ++jj) {                              // K16 step = k-chunks 2j, 2j+1
+                    const uint64_t bd = umma_desc_nosw(b0 + (uint32_t)(jj * 2 * CH_B), (uint32_t)CH_B, 128u);
+                    umma_f16_ts(dacc, abase + (uint32_t)(jj * 8), bd, id1, jj ? 1u : 0u);
+                }
+                umma_commit(&mma_done[g]);
+                if (prod == 0 && s + 2 < maxlen) mbar_expect_tx(bh, Cfg::HALF_B);     // refilled during step s+1
+                if (dbg_cta && chain == 0 && s >= 100 && s < 104) {
+                    long long *d = p.dbgbuf + ((s - 100) * 2 + g) * 12;
+                    d[0] = d_w0; d[1] = d_w1; d[2] = clock64();
+                }
+            }
+            __syncwarp();
         }
     } else {
-        // ===================== epilogue warps 1..16: quarter q = warp & 3; sub-warp sw = (warp-1) >> 2: group g = sw >> 1, half sw2 = sw & 1.
+        // ===================== epilogue warps 8..23: quarter q = warp & 3; sub-warp sw = (warp-8) >> 2: group g = sw >> 1, half sw2 = sw & 1.
         // A warp owns LPW lines of its group x the 8 unit slots of its TMEM lane quarter and never synchronises with another warp:
-        // gate values are regrouped by quad shuffles (round 1: shared memory + two named barriers per step).
+        // gate values are regrouped by quad shuffles, h leaves as st.async straight from registers.
         const int q = warp & 3;                            // TMEM lane quarter: unit slots 8q .. 8q+7
-        const int sw = (warp - 1) >> 2, g = sw >> 1, sw2 = sw & 1;
+        const int sw = (warp - N_ISSUE) >> 2, g = sw >> 1, sw2 = sw & 1;
         const int jq = lane >> 2, gate = lane & 3;         // unit slot within the quarter, gate of this thread's TMEM row
         const int slot = 8 * q + jq, u = (int)rank * p.U + slot;
         const bool uvalid = slot < p.U && u < hid;
@@ -326,34 +300,27 @@ __global__ void __launch_bounds__(LTHREADS, 1) k_lstm_rec_tc(LstmTcParams p) {
             gxn[i] = 0 < glen[i] ? __ldg(gptr[i]) : 0.f;
             gptr[i] += gstride;
         }
-        // hand-off: the 8 epilogue warps of a group stage their blocks as this CTA's 4 k-chunks of the operand (1 KB for GL = 8), then
-        // warp wi sends the whole piece to CTA wi with ONE bulk copy.  (Round 1 and the first version of this kernel sent 8 copies
-        // per warp: a UBLKCP takes uniform-register operands, so the 8 lanes ran as an 8-iteration loop of ELECT / R2UR / UBLKCP,
-        // ~500 cycles per step on the critical path.)
-        const int wi = (sw2 << 2) | q;                                                    // 0..7 within the group
-        const uint32_t dstB = mapa32(smem_u32(sB), (uint32_t)wi), dstFull = mapa32(smem_u32(b_full), (uint32_t)wi) + (uint32_t)rank * 8u;   // our piece's barrier at CTA wi
-        uint8_t *sxg = sx + g * 2 * 4 * CH_B;
-        const int sxw_off = q * CH_B + sw2 * WB_B;                                        // this warp's rows of this quarter's k-chunk
+        // hand-off: after the 8-lane gather every lane holds the complete operand rows of its line; lane jq stores them into CTA jq.
+        // This CTA's rows of the operand of every destination: k-chunk (4 rank + q), row (warp half, plane, line)
+        const uint32_t row_off = ((uint32_t)rank * 4u + (uint32_t)q) * (uint32_t)CH_B + (uint32_t)((sw2 * 2 * LPW + gate) * 16);
+        const uint32_t dstB = mapa32(smem_u32(sB), (uint32_t)jq) + row_off;
+        const uint32_t dstBar = mapa32(smem_u32(b_half), (uint32_t)jq) + (uint32_t)(rank >> 2) * 8u;     // our K half's barrier at CTA jq
         // this warp's accumulator columns: rows of the operand = [warp half][plane][line]
         const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * GSTRIDE + 2 * LPW * sw2);
         // gate non-linearity without divergence: sigmoid(x) for i, f, o; tanh(x) = 2*sigmoid(2x) - 1 for the candidate gate
         const float act_k = gate == 2 ? 2.f : 1.f;
-        const uint32_t kc_off = (uint32_t)rank * 4u * (uint32_t)CH_B;                     // this CTA's 4 k-chunks in every destination's operand
+        const bool dbg_w = dbg_cta && q == 0 && sw2 == 0 && lane == 0;
 
         for (int s = 0; s < maxlen; ++s) {
             const int nxt = (s + 1) & 1;
             float gxv[LPW];
 #pragma unroll
             for (int i = 0; i < LPW; ++i) gxv[i] = gxn[i];
-            const long long e_top = (p.dbg & 1) ? clock64() : 0;
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                if (p.dbg & 4) mbar_wait_poll(&mma_done[g * 4 + c], (uint32_t)(s & 1));
-                else mbar_wait(&mma_done[g * 4 + c], (uint32_t)(s & 1));
-            }
+            const long long e_top = dbg_w ? clock64() : 0;
+            mbar_wait(&mma_done[g], (uint32_t)(s & 1));
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const long long e_done = (p.dbg & 1) ? clock64() : 0;
-            // group columns: D1a = W1 x rows (k-atoms 0,1) @0, D1b (k-atoms 2,3) @N1, D2a = W2s x rows @2 N1, D2b @3 N1; within the warp's
+            const long long e_done = dbg_w ? clock64() : 0;
+            // group columns: D1a = W1 x rows (K half 0) @0, D1b (K half 1) @N1, D2a = W2s x rows @2 N1, D2b @3 N1; within the warp's
             // 2 LPW rows: [h1 lines | h2s lines]
             uint32_t m0[LPW], m1[LPW], c0[LPW], c1[LPW], c2[LPW], c3[LPW];
             if (LPW == 4) {
@@ -367,6 +334,9 @@ __global__ void __launch_bounds__(LTHREADS, 1) k_lstm_rec_tc(LstmTcParams p) {
             }
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_free[g]);       // the issuers may overwrite the accumulators
+            const long long e_ld = dbg_w ? clock64() : 0;
             float av[LPW];
 #pragma unroll
             for (int i = 0; i < LPW; ++i) {
@@ -375,9 +345,9 @@ __global__ void __launch_bounds__(LTHREADS, 1) k_lstm_rec_tc(LstmTcParams p) {
                 const float pre = (main_ + corr * (1.f / X2_SCALE)) + gxv[i];
                 av[i] = fmaf(sigmoid_fast(pre * act_k), act_k, 1.f - act_k);
             }
-            const long long e_act = (p.dbg & 1) ? clock64() : 0;
-            __half *cx = reinterpret_cast<__half *>(sxg + (s & 1) * 4 * CH_B + sxw_off);
+            const long long e_act = dbg_w ? clock64() : 0;
             float hv[NT]; __half hh1[NT], hh2[NT]; bool wr[NT];
+            uint4 row1[NT], row2[NT];
 #pragma unroll
             for (int t = 0; t < NT; ++t) {
                 float gt[4] = {av[4 * t], av[4 * t + 1], av[4 * t + 2], av[4 * t + 3]};
@@ -388,24 +358,22 @@ __global__ void __launch_bounds__(LTHREADS, 1) k_lstm_rec_tc(LstmTcParams p) {
                     cst[t] = gt[1] * cst[t] + gt[0] * gt[2];
                     h = gt[3] * tanh_fast(cst[t]);
                 }
-                // both fp16 planes of h straight into the outgoing block: [plane][line][unit slot]
                 const __half h1 = __float2half_rn(h);
                 const __half h2 = __float2half_rn((h - __half2float(h1)) * X2_SCALE);
-                cx[(4 * t + gate) * 8 + jq] = h1;
-                cx[(LPW + 4 * t + gate) * 8 + jq] = h2;
                 hv[t] = h; hh1[t] = h1; hh2[t] = h2; wr[t] = cval[t] && live;
+                gather_rows8(h1, h2, lane, row1[t], row2[t]);
             }
-            const long long e_sts = (p.dbg & 1) ? clock64() : 0;
-            // Only shared-memory stores are outstanding here: the proxy fence (MEMBAR.ALL.CTA + FENCE.VIEW.ASYNC) waits for every
-            // earlier memory operation of the thread, so the global stores of h and the gx prefetch come AFTER the hand-off (with them
-            // in front the fence took 1500 cycles per step, KB_LSTM_DBG timeline of the first version).
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic writes -> the bulk copy engine (async proxy)
-            const long long e_fence = (p.dbg & 1) ? clock64() : 0;
-            named_bar(1 + g, 256);                                            // the group's 8 warps have staged their blocks
-            const long long e_cell = (p.dbg & 1) ? clock64() : 0;
-            if (s + 1 < maxlen && lane == 0)
-                bulk_s2s(dstB + (uint32_t)((g * 2 + nxt) * B_BUF_B) + kc_off, smem_u32(sxg + (s & 1) * 4 * CH_B), (uint32_t)(4 * CH_B),
-                         dstFull + (uint32_t)((g * 2 + nxt) * 8) * 8u);
+            const long long e_cell = dbg_w ? clock64() : 0;
+            if (s + 1 < maxlen) {
+                const uint32_t boff = (uint32_t)((g * 2 + nxt) * B_BUF_B), bar = dstBar + (uint32_t)((g * 2 + nxt) * 2) * 8u;
+#pragma unroll
+                for (int t = 0; t < NT; ++t) {
+                    st_async_v4(dstB + boff + (uint32_t)(4 * t * 16), row1[t], bar);
+                    st_async_v4(dstB + boff + (uint32_t)((LPW + 4 * t) * 16), row2[t], bar);
+                }
+            }
+            const long long e_sent = dbg_w ? clock64() : 0;
+            // h to HBM and the gx prefetch come AFTER the hand-off: nothing on the critical path waits for them
 #pragma unroll
             for (int t = 0; t < NT; ++t)
                 if (wr[t]) {
@@ -418,10 +386,9 @@ __global__ void __launch_bounds__(LTHREADS, 1) k_lstm_rec_tc(LstmTcParams p) {
                 gxn[i] = s + 1 < glen[i] ? __ldg(gptr[i]) : 0.f;
                 gptr[i] += gstride;
             }
-            if ((p.dbg & 1) && blockIdx.x == 0 && blockIdx.y == 0 && (warp == 1 || warp == 9) && lane == 0 && s >= 100 && s < 104) {
-                long long *d = p.dbgbuf + ((s - 100) * 2 + g) * 8;
-                d[3] = e_done; d[4] = e_act; d[5] = e_cell; d[6] = clock64(); d[7] = e_top;
-                p.dbgbuf[64 + ((s - 100) * 2 + g) * 2] = e_sts; p.dbgbuf[64 + ((s - 100) * 2 + g) * 2 + 1] = e_fence;
+            if (dbg_w && s >= 100 && s < 104) {
+                long long *d = p.dbgbuf + ((s - 100) * 2 + g) * 12;
+                d[3] = e_top; d[4] = e_done; d[5] = e_ld; d[6] = e_act; d[7] = e_cell; d[8] = e_sent; d[9] = clock64();
             }
         }
     }

@@ -31,3 +31,20 @@ for _ in range(10):
     for k, v in m.last_timing():
         acc[k] = acc.get(k, 0.0) + v / 10
 print('stages ms:', {k: round(v, 4) for k, v in acc.items()}, 'sum', round(sum(acc.values()), 4), file=sys.stderr)
+# wall clock of strictly serial calls without the stage timers (host turn-around included)
+import time
+m.set_timing(False)
+torch.cuda.synchronize()
+t0 = time.perf_counter()
+for _ in range(50):
+    rec._recognize_raw(x, lens, want_probs=False)
+torch.cuda.synchronize()
+print('serial wall ms/call (timing off):', round((time.perf_counter() - t0) * 20, 4), file=sys.stderr)
+m.set_timing(True)
+torch.cuda.synchronize()
+t0 = time.perf_counter()
+for _ in range(50):
+    rec._recognize_raw(x, lens, want_probs=False)
+    m.last_timing()
+torch.cuda.synchronize()
+print('serial wall ms/call (timing on):', round((time.perf_counter() - t0) * 20, 4), file=sys.stderr)
