@@ -355,7 +355,7 @@ def run_cfg3(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=30)
+    ap.add_argument('--steps', type=int, default=None, help='timed steps (default: 200 on the GPU arm, 20 CPU batches on the reference arm)')
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--cpu-steps', type=int, default=6)
@@ -368,6 +368,8 @@ def main():
     ap.add_argument('--cfg5-lines', type=int, default=100000)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'b200' else args.warmup
+    if args.steps is None:
+        args.steps = 200 if (args.impl == 'b200' and args.workload == 'cfg2') else 20
     # a hung kernel or a lost pipeline ticket must not sit on the GPU box until its time limit: dump every thread's stack and exit
     import faulthandler
     faulthandler.dump_traceback_later(int(os.environ.get('KB_BENCH_WATCHDOG', '1200')), exit=True)
@@ -454,6 +456,7 @@ def main():
         return rb
 
     def timed(batches, steps, on_step=None, pipelined=False, u8=False):
+        run_blocks(steps)                                  # the pinned result buffer of a run is allocated outside its timed region
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()

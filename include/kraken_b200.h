@@ -48,7 +48,7 @@
 extern "C" {
 #endif
 
-#define KB_ABI_VERSION 2
+#define KB_ABI_VERSION 3
 
 enum {
     KB_OK = 0,
@@ -147,6 +147,24 @@ int  kb_recognize_u8(kb_model *m, const uint8_t *lines, int lines_on_device, int
                      int32_t *ends, float *confs, int32_t *counts, int32_t max_out, int32_t *out_lens, float *probs,
                      int probs_on_device, void *stream);
 
+/* ---- bbox line extraction + the PIL half of the input transforms on the device ----------------------------
+ * Replaces, for bbox lines of horizontal text, `im.crop(box)` (kraken/lib/segmentation.py:1631-1643) and the image half of
+ * ImageInputTransforms (kraken/lib/dataset/utils.py:123-147): Grayscale, `pil_fixed_resize` = img.resize((int(w * oh / h), oh), LANCZOS)
+ * (kraken/lib/functional_im_transforms.py:58-82) and v2.Pad(pad, fill=255) - bit-identical to Pillow's 8-bit resampler (the fixed-point
+ * coefficient windows are computed on the host through the same libm calls Pillow makes; the integer convolutions run on the GPU).
+ * page:  page_h x page_w x channels uint8, channels = 1 ('L') or 3 ('RGB', interleaved as PIL / numpy hold it), host or device.
+ * boxes: n x (x0, y0, x1, y1), inside the page.  out_h: the model's input height.  pad: white columns on both ends.
+ * lines: n x 1 x out_h x wmax uint8 on the DEVICE (caller allocated); line i occupies columns [0, widths[i]), the rest of its rows is
+ *        left untouched.  widths (host, n): int(w * out_h / h) + 2 * pad.  invert_max (host, n, may be NULL): `im.max()` of
+ *        tensor_invert as 0..255 (255 whenever pad > 0).  Hand lines / widths / invert_max to kb_recognize_u8 or
+ *        kb_recognize_async(KB_DTYPE_U8, lines_on_device = 1) on the same stream.
+ * kb_line_width: the padded width one box will have (to size wmax); 0 = the reference's resize raises for such a box.
+ * Not covered (stay in kraken): baseline / polygon line extraction, the centre normaliser of legacy bbox models (valid_norm), vertical text. */
+int32_t kb_line_width(int32_t box_w, int32_t box_h, int32_t out_h, int32_t pad);
+int  kb_prepare_lines_u8(kb_model *m, const uint8_t *page, int page_on_device, int32_t page_h, int32_t page_w, int32_t channels,
+                         int32_t n, const int32_t *boxes, int32_t out_h, int32_t pad, uint8_t *lines, int32_t wmax,
+                         int32_t *widths, int16_t *invert_max, void *stream);
+
 /* ---- asynchronous pipeline ------------------------------------------------------------------------
  * The calls above finish with the results in the caller's arrays (one cudaStreamSynchronize each).  A serving loop that wants the
  * copies, the host work and the kernels of consecutive batches to overlap uses ONE model handle with `depth` pipeline slots instead
@@ -199,6 +217,10 @@ int  kb_debug_layer_output(kb_model *m, const char *name, int32_t dims[4], float
  * 0 = CUDA-core fp32 kernel); host pointers.  Unit-test hook for the kernels behind Linear / LSTM projection.   */
 int  kb_debug_gemm(const float *a, const float *b, const float *bias, float *c, int32_t M, int32_t N, int32_t K,
                    int use_tc, int device);
+/* the host half of kb_prepare_lines_u8: Pillow's fixed-point LANCZOS windows of one axis (Resample.c precompute_coeffs +
+ * normalize_coeffs_8bpc).  *ksize = window capacity; bounds [out_size][2] = (first source index, count); kk [out_size][*ksize].
+ * bounds / kk may be NULL to query ksize only.  Host only (usable without a GPU): lets the CPU tests pin the tables against Pillow. */
+int  kb_debug_axis_coeffs(int32_t in_size, int32_t out_size, int32_t *ksize, int32_t *bounds, int32_t *kk, int32_t kk_cap);
 /* number of kernels this handle launched since creation / last reset (bench `gpu_launches`) */
 int64_t kb_launch_count(const kb_model *m);
 void    kb_reset_launch_count(kb_model *m);

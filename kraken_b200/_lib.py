@@ -62,6 +62,8 @@ _SIGS = {
     'kb_forward': (C.c_int, [_vp, _vp, C.c_int, _i32, _i32, _i32, _vp, _vp, C.c_int, _vp, _vp]),
     'kb_recognize': (C.c_int, [_vp, _vp, C.c_int, _i32, _i32, _i32, _vp, _f, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, C.c_int, _vp]),
     'kb_recognize_u8': (C.c_int, [_vp, _vp, C.c_int, _i32, _i32, _i32, _vp, _vp, _f, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, C.c_int, _vp]),
+    'kb_line_width': (_i32, [_i32, _i32, _i32, _i32]),
+    'kb_prepare_lines_u8': (C.c_int, [_vp, _vp, C.c_int, _i32, _i32, _i32, _i32, _vp, _i32, _i32, _vp, _i32, _vp, _vp, _vp]),
     'kb_set_pipeline_depth': (C.c_int, [_vp, _i32]),
     'kb_pipeline_depth': (C.c_int, [_vp]),
     'kb_recognize_async': (C.c_int, [_vp, _vp, C.c_int, C.c_int, _i32, _i32, _i32, _vp, _vp, _f, _i32, _vp, C.POINTER(_i64)]),
@@ -70,6 +72,7 @@ _SIGS = {
     'kb_segment': (C.c_int, [_vp, _vp, C.c_int, _i32, _i32, _i32, _i32, _i32, _vp, C.c_int, _vp]),
     'kb_debug_layer_output': (C.c_int, [_vp, C.c_char_p, _pi32, _vp, C.c_int]),
     'kb_debug_gemm': (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, C.c_int, C.c_int]),
+    'kb_debug_axis_coeffs': (C.c_int, [_i32, _i32, _pi32, _vp, _vp, _i32]),
     'kb_launch_count': (_i64, [_vp]),
     'kb_range_fallback_count': (_i64, [_vp]),
     'kb_reset_launch_count': (None, [_vp]),

@@ -16,6 +16,7 @@
 #include "gemm_tc.cuh"
 #include "conv_tc.cuh"
 #include "lstm_tc.cuh"
+#include "line_prep.cuh"
 #include "vgsl_plan.hpp"
 
 namespace kb {
@@ -145,11 +146,16 @@ struct kb_model {
     double prof_us[4] = {0, 0, 0, 0}; int64_t prof_calls = 0;    // KB_HOST_PROF: host microseconds in plan / launch / wait / unpack
     bool fuse = true;                // fused layer groups (KB_FUSE=0 runs every layer on its own, e.g. for layer taps)
     bool use_tc = true;              // tcgen05 GEMM path (KB_GEMM=ffma forces the CUDA-core kernel)
+    // kb_prepare_lines_u8 scratch: device [page copy | line table | coefficient tables | horizontal-pass rows | line maxima], pinned host mirror of the tables
+    char *prep_dev = nullptr; size_t prep_dev_cap = 0; char *prep_host = nullptr; size_t prep_host_cap = 0;
     kb_model() { wss.emplace_back(new Workspace()); }
     Workspace *ws0() { return wss[0].get(); }
     void release_device_state() {
         for (void *p : dev_allocs) cudaFree(p);
         dev_allocs.clear();
+        if (prep_dev) cudaFree(prep_dev);
+        if (prep_host) cudaFreeHost(prep_host);
+        prep_dev = prep_host = nullptr; prep_dev_cap = prep_host_cap = 0;
         for (auto &w : wss) w->release();
         wss.resize(1);
     }
@@ -641,7 +647,8 @@ struct Exec {
             Tensor full = mk(dfull);
             // the tensor-core recurrences can emit the consumer's fp16 operand planes themselves (no k_split_f16 pass)
             const int ks_p = hid <= 32 ? 1 : hid <= 64 ? 2 : hid <= 128 ? 4 : 8;
-            const bool tc_rec = (ks_p == 8 || ks_p == 1) && w.wpk && m->use_tc && !(getenv("KB_LSTM_TC") && atoi(getenv("KB_LSTM_TC")) == 0);
+            const bool generic_rec = w.whh_t && (hid > 256 || (getenv("KB_LSTM_GENERIC") && atoi(getenv("KB_LSTM_GENERIC")) != 0));   // writes fp32 only
+            const bool tc_rec = (ks_p == 8 || ks_p == 1) && w.wpk && m->use_tc && !generic_rec && !(getenv("KB_LSTM_TC") && atoi(getenv("KB_LSTM_TC")) == 0);
             const bool lplanes = planes_hint && tc_rec && !n.summarize;
             planes_hint = false;
             if (lplanes) { full.hi = (__half *)ws->arena.alloc((size_t)full.numel() * 2); full.lo = (__half *)ws->arena.alloc((size_t)full.numel() * 2); }
@@ -675,7 +682,7 @@ struct Exec {
                     ltc::LstmTcParams tp;
                     tp.gx = lp.gx; tp.wpk = (const uint16_t *)w.wpk; tp.out = (lplanes && !m->keep_fp32) ? nullptr : lp.out; tp.lens = lp.lens; tp.nseq = lp.nseq; tp.T = lp.T;
                     tp.out_hi = full.hi; tp.out_lo = full.lo;
-                    tp.dbg = 0; tp.dbgbuf = nullptr; tp.hid = hid; tp.dirs = dirs; tp.U = hid; tp.q2 = lp.q2; tp.s_outer = lp.s_outer; tp.s_inner = lp.s_inner; tp.step = lp.step;
+                    tp.dbg = 0; tp.handoff = 0; tp.dbgbuf = nullptr; tp.hid = hid; tp.dirs = dirs; tp.U = hid; tp.q2 = lp.q2; tp.s_outer = lp.s_outer; tp.s_inner = lp.s_inner; tp.step = lp.step;
                     int snl = lp.nseq * dirs >= 64 * 2 * sm ? 64 : lp.nseq * dirs >= 16 * 4 * sm ? 32 : 16;      // fill the SMs first, then grow the CTAs
                     if (getenv("KB_LSTM_SNL")) snl = atoi(getenv("KB_LSTM_SNL"));
                     if (snl != 64 && snl != 32) snl = 16;
@@ -690,7 +697,7 @@ struct Exec {
                     ltc::LstmTcParams tp;
                     tp.gx = lp.gx; tp.wpk = (const uint16_t *)w.wpk; tp.out = (lplanes && !m->keep_fp32) ? nullptr : lp.out; tp.lens = lp.lens; tp.nseq = lp.nseq; tp.T = lp.T;
                     tp.out_hi = full.hi; tp.out_lo = full.lo;
-                    tp.dbg = getenv("KB_LSTM_DBG") ? atoi(getenv("KB_LSTM_DBG")) : 0; tp.hid = hid; tp.dirs = dirs; tp.U = lp.U; tp.q2 = lp.q2; tp.s_outer = lp.s_outer; tp.s_inner = lp.s_inner; tp.step = lp.step;
+                    tp.dbg = getenv("KB_LSTM_DBG") ? atoi(getenv("KB_LSTM_DBG")) : 0; tp.handoff = getenv("KB_LSTM_HANDOFF") ? atoi(getenv("KB_LSTM_HANDOFF")) : 0; tp.hid = hid; tp.dirs = dirs; tp.U = lp.U; tp.q2 = lp.q2; tp.s_outer = lp.s_outer; tp.s_inner = lp.s_inner; tp.step = lp.step;
                     // lines per cluster: 16 (two groups of 8); KB_LSTM_GL=16 selects 32 (two groups of 16: half the SMs per batch, but
                     // the longer epilogue stretches the per-step latency chain by 1.7x)
                     int gl = 8;                                  // measured on cfg2: 32 lines per cluster = 0.54 ms vs 0.31 ms, and no e2e gain
@@ -820,7 +827,7 @@ struct Exec {
             Tensor y = mk(dpool);
             // a tensor-core conv right behind wants the operand planes
             const Node *nx = next_real(series, j + 1);
-            const bool planes = m->use_tc && nx && nx->kind == K_CONV && tc_conv_eligible(*nx, dpool);
+            const bool planes = m->use_tc && (m->fuse_mask & 2) && nx && nx->kind == K_CONV && tc_conv_eligible(*nx, dpool);
             if (planes) { y.hi = (__half *)ws->arena.alloc((size_t)y.numel() * 2); y.lo = (__half *)ws->arena.alloc((size_t)y.numel() * 2); }
             if (!dry && y.numel()) {
                 StageTimer tt(ws, st, c0.name + "+" + pl->name, true);
@@ -1710,6 +1717,82 @@ int kb_ctc_greedy_decode(const float *probs, int probs_on_device, int32_t n, int
             decode_unpack(pinned, n, max_out, labels, starts, ends, confs, counts);
         } catch (...) { cudaFree(ar.base); if (pinned) cudaFreeHost(pinned); throw; }
         cudaFree(ar.base); if (pinned) cudaFreeHost(pinned);
+        return (int)KB_OK;
+    });
+}
+
+int32_t kb_line_width(int32_t box_w, int32_t box_h, int32_t out_h, int32_t pad) {
+    const int ow = lp::resized_width(box_w, box_h, out_h);
+    return ow < 1 ? 0 : ow + 2 * std::max(pad, 0);
+}
+
+int kb_debug_axis_coeffs(int32_t in_size, int32_t out_size, int32_t *ksize, int32_t *bounds, int32_t *kk, int32_t kk_cap) {
+    if (in_size <= 0 || out_size <= 0 || !ksize) return fail(KB_ERR_ARG, "invalid sizes");
+    const int ks = in_size == out_size ? lp::identity_ksize() : lp::axis_ksize(in_size, out_size);
+    *ksize = ks;
+    if (!bounds || !kk) return KB_OK;
+    if ((long long)kk_cap < (long long)out_size * ks) return fail(KB_ERR_ARG, "kk_cap too small");
+    lp::axis_coeffs(in_size, out_size, ks, bounds, kk);
+    return KB_OK;
+}
+
+int kb_prepare_lines_u8(kb_model *m, const uint8_t *page, int page_on_device, int32_t page_h, int32_t page_w, int32_t channels,
+                        int32_t n, const int32_t *boxes, int32_t out_h, int32_t pad, uint8_t *lines, int32_t wmax,
+                        int32_t *widths, int16_t *invert_max, void *stream) {
+    if (!m || !page || !boxes || !lines || !widths) return fail(KB_ERR_ARG, "NULL argument");
+    if (channels != 1 && channels != 3) return fail(KB_ERR_ARG, "page must have 1 ('L') or 3 ('RGB', interleaved) channels");
+    if (n <= 0 || page_h <= 0 || page_w <= 0 || out_h <= 0 || pad < 0 || wmax <= 0) return fail(KB_ERR_ARG, "invalid sizes");
+    for (int i = 0; i < n; ++i) {
+        const int32_t *b = boxes + 4 * i;
+        if (b[0] < 0 || b[1] < 0 || b[2] > page_w || b[3] > page_h || b[2] <= b[0] || b[3] <= b[1])
+            return fail(KB_ERR_ARG, "Line outside of image bounds");                                   // segmentation.py:1639-1642
+        const int wd = kb_line_width(b[2] - b[0], b[3] - b[1], out_h, pad);
+        if (wd - 2 * pad < 1) return fail(KB_ERR_SHAPE, "height and width must be > 0");               // what Image.resize raises for such a line
+        if (wd > wmax) return fail(KB_ERR_ARG, "wmax is smaller than a prepared line (size it with kb_line_width)");
+        widths[i] = wd;
+    }
+    std::lock_guard<std::mutex> lk(m->mu);
+    return guarded([&]() {
+        DeviceGuard dguard;
+        ensure_ready(m);
+        cudaStream_t st = (cudaStream_t)stream;
+        lp::Plan pl;
+        lp::build_plan(pl, n, boxes, out_h, pad);
+        const size_t page_bytes = page_on_device ? 0 : (size_t)page_h * page_w * channels;
+        const size_t meta_bytes = (size_t)n * sizeof(lp::LineMeta), tab_bytes = pl.tab.size() * sizeof(int32_t);
+        auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
+        const size_t host_need = up(meta_bytes) + up(tab_bytes);
+        const size_t dev_need = up(page_bytes) + host_need + up(pl.tmp_bytes) + up((size_t)n * sizeof(int));
+        if (host_need > m->prep_host_cap || dev_need > m->prep_dev_cap) CK(cudaStreamSynchronize(st));   // an earlier call may still read the old buffers
+        if (host_need > m->prep_host_cap) {
+            if (m->prep_host) cudaFreeHost(m->prep_host);
+            m->prep_host = nullptr; m->prep_host_cap = 0;
+            CK(cudaHostAlloc((void **)&m->prep_host, host_need + host_need / 2, cudaHostAllocDefault));
+            m->prep_host_cap = host_need + host_need / 2;
+        }
+        if (dev_need > m->prep_dev_cap) {
+            if (m->prep_dev) cudaFree(m->prep_dev);
+            m->prep_dev = nullptr; m->prep_dev_cap = 0;
+            CK(cudaMalloc((void **)&m->prep_dev, dev_need + dev_need / 2));
+            m->prep_dev_cap = dev_need + dev_need / 2;
+        }
+        char *d_page = m->prep_dev, *d_tabs = d_page + up(page_bytes), *d_tmp = d_tabs + host_need, *d_max = d_tmp + up(pl.tmp_bytes);
+        memcpy(m->prep_host, pl.meta.data(), meta_bytes);
+        memcpy(m->prep_host + up(meta_bytes), pl.tab.data(), tab_bytes);
+        if (!page_on_device) CK(cudaMemcpyAsync(d_page, page, page_bytes, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(d_tabs, m->prep_host, host_need, cudaMemcpyHostToDevice, st));
+        const bool want_max = invert_max && pad == 0;         // with white padding the maximum is 255 by construction
+        if (want_max) CK(cudaMemsetAsync(d_max, 0, (size_t)n * sizeof(int), st));
+        const uint8_t *pg = page_on_device ? page : (const uint8_t *)d_page;
+        const lp::LineMeta *d_meta = (const lp::LineMeta *)d_tabs; const int32_t *d_tab = (const int32_t *)(d_tabs + up(meta_bytes));
+        LAUNCH(m, lp::k_prep_horizontal, dim3((unsigned)((pl.max_ow + 127) / 128), (unsigned)pl.max_rows, (unsigned)n), 128, 0, st, pg, (int)page_w,
+               (int)channels, d_meta, d_tab, (uint8_t *)d_tmp);
+        LAUNCH(m, lp::k_prep_vertical, dim3((unsigned)((pl.max_width + 127) / 128), (unsigned)out_h, (unsigned)n), 128, 0, st, (const uint8_t *)d_tmp,
+               d_meta, d_tab, lines, (int)out_h, (int)wmax, (int)pad, want_max ? (int *)d_max : (int *)nullptr);
+        std::vector<int> mx((size_t)(want_max ? n : 0));
+        if (want_max) CK(cudaMemcpyAsync(mx.data(), d_max, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));                        // lines complete; the pinned tables may be overwritten by the next call
+        if (invert_max) for (int i = 0; i < n; ++i) invert_max[i] = want_max ? (int16_t)mx[(size_t)i] : (int16_t)255;
         return (int)KB_OK;
     });
 }

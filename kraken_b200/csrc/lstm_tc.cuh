@@ -41,8 +41,8 @@ constexpr int NG = 2;                                    // independent line gro
 constexpr int LCS = 8;                                   // cluster size
 constexpr int A_PLANE_ELEMS = 128 * 256;                 // fp16 elements of one W plane of a CTA: [128 gate rows][K = 256], row-major
 constexpr int EW = 4;                                    // epilogue warps per TMEM lane quarter: 2 per group (latency hiding: v3 with 1 was 2x slower)
-constexpr int N_ISSUE = 8;                               // MMA issuer warps: [group][K half][product]
-constexpr int LTHREADS = (N_ISSUE + 4 * EW) * 32;        // warps 0..7: MMA issuers (warp 0 also owns the TMEM allocation); warps 8..23: epilogue
+constexpr int N_ISSUE = 2;                               // MMA issuer warps: one per group
+constexpr int LTHREADS = (N_ISSUE + 4 * EW) * 32;        // warps 0..1: MMA issuers (warp 0 also owns the TMEM allocation); warps 2..17: epilogue
 constexpr int TM_COLS = 512;
 template <int GL> struct ClusterCfg {                    // GL = lines per group: 8 (16 lines per cluster) or 16 (32 lines per cluster)
     static constexpr int NL = NG * GL;                   // lines per cluster
@@ -52,7 +52,9 @@ template <int GL> struct ClusterCfg {                    // GL = lines per group
     static constexpr int B_BUF_B = 32 * CH_B;            // bytes per (group, buffer): K = 256 = 32 chunks
     static constexpr int SRC_B = 4 * CH_B;               // bytes one source CTA contributes to a buffer (its 4 k-chunks)
     static constexpr int HALF_B = 4 * SRC_B;             // bytes the four source CTAs of a K half deliver
-    static constexpr int SMEM_BYTES = NG * 2 * B_BUF_B + 512 + 1024;
+    static constexpr int SX_BYTES = NG * 2 * SRC_B;     // bulk hand-off: this CTA's outgoing piece per group, double buffered, laid out as in the operand
+    static constexpr int WB_B = 2 * LPW * 16;            // bytes an epilogue warp contributes to a k-chunk: [h1 of its lines | h2s of its lines] x 16 B
+    static constexpr int SMEM_BYTES = NG * 2 * B_BUF_B + SX_BYTES + 512 + 1024;
     static constexpr int N1 = 2 * GL;                    // N of both products (W2s x the same operand rows; only its h1 columns are read)
     static constexpr int GSTRIDE = 4 * N1;               // TMEM columns per group: D1a @0, D1b @N1, D2a @2 N1, D2b @3 N1
     static constexpr int TM_A0 = NG * GSTRIDE;           // A: W1 @TM_A0 (128 columns), W2s @TM_A0 + 128
@@ -63,6 +65,7 @@ struct LstmTcParams {
     __half *out_hi, *out_lo;         // optional fp16 operand planes of the output for a tensor-core consumer (out may then be NULL)
     int nseq, T, hid, dirs, U;
     int q2; long long s_outer, s_inner, step;
+    int handoff;                     // 0: st.async from registers (16-byte packets), 1: staged in shared memory + one 1 KB bulk copy per destination
     int dbg; long long *dbgbuf;      // KB_LSTM_DBG: bit 0 = clock64 stamps of steps 100..103 of cluster 0 into dbgbuf[step][group][12]
 };
 
@@ -98,6 +101,12 @@ __device__ __forceinline__ uint32_t mapa32(uint32_t saddr, uint32_t rank) {
 __device__ __forceinline__ void st_async_v4(uint32_t raddr, uint4 v, uint32_t rmbar) {
     asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];"
                  ::"r"(raddr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "r"(rmbar) : "memory");
+}
+// shared::cta -> (remote) shared::cluster bulk copy, byte-counted by the destination's mbarrier: one packet stream and ONE transaction
+// count update per block instead of one per 16 bytes
+__device__ __forceinline__ void bulk_s2s(uint32_t dst_cluster, uint32_t src_cta, uint32_t bytes, uint32_t mbar_cluster) {
+    asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst_cluster), "r"(src_cta), "r"(bytes), "r"(mbar_cluster) : "memory");
 }
 // K-major operand WITHOUT swizzle: core matrices (8 rows x 16 bytes, 128 contiguous bytes) `lbo` bytes apart along K and `sbo`
 // bytes apart along M/N.  The h operand uses it because one 16-byte store = 8 unit slots of one line = one row of a core matrix.
@@ -151,12 +160,12 @@ __device__ __forceinline__ void gather_rows8(__half h1, __half h2, int lane, uin
 
 // Synchronisation of one (group, time step), all through mbarriers, no CTA- or cluster-wide barrier in the loop:
 //   b_half[g][buffer][K half]  tx-count barrier: the 4 KB of h_{s-1} planes the four source CTAs of a K half store (st.async from
-//                              registers, 16 bytes per store) into this CTA's operand buffer.  Waited on by the half's two issuers;
-//                              re-armed for the refill two steps later by the W1 issuer once it has passed it (nobody can send that
-//                              refill before receiving this CTA's h_s, which needs all four chains of this step).
-//   acc_free[g]                8 arrivals: the group's epilogue warps have read the accumulators of the previous step (an issuer
-//                              whose K half does not contain this CTA's own piece could otherwise overwrite them too early).
-//   mma_done[g]                4 arrivals (tcgen05.commit of the four chains): accumulators complete.
+//                              registers, 16 bytes per store) into this CTA's operand buffer.  Waited on by the group's issuer, which
+//                              re-arms it for the refill two steps later once it has passed it (nobody can send that refill before
+//                              receiving this CTA's h_s, which needs this step's MMAs).
+//   acc_free[g]                8 arrivals: the group's epilogue warps have read the accumulators of the previous step.
+//   mma_done[g]                tcgen05.commit of the group's issuer: accumulators complete.  Also read (not consumed) by the OTHER
+//                              group's issuer: the groups alternate on the tensor pipe.
 template <int GL>
 __global__ void __launch_bounds__(LTHREADS, 1) k_lstm_rec_tc(LstmTcParams p) {
     using Cfg = ClusterCfg<GL>;
@@ -165,7 +174,8 @@ __global__ void __launch_bounds__(LTHREADS, 1) k_lstm_rec_tc(LstmTcParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = smem_align1024(smem_raw);
     uint8_t *sB = smem;                                   // [group][buffer][k-chunk][row = (warp half, plane, line)][8 unit slots] fp16, no swizzle
-    uint64_t *bars = reinterpret_cast<uint64_t *>(sB + NG * 2 * B_BUF_B);
+    uint8_t *sx = sB + NG * 2 * B_BUF_B;                  // [group][2][k-chunk of this CTA][row][8 unit slots]: outgoing piece (bulk hand-off)
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sx + Cfg::SX_BYTES);
     uint64_t *b_half = bars /* [group][buffer][K half] */, *mma_done = bars + 8 /* [group] */, *acc_free = bars + 10 /* [group] */;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 12);
 
@@ -177,7 +187,7 @@ __global__ void __launch_bounds__(LTHREADS, 1) k_lstm_rec_tc(LstmTcParams p) {
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < 8; ++i) mbar_init(&b_half[i], 1);
-        for (int g = 0; g < NG; ++g) { mbar_init(&mma_done[g], 4); mbar_init(&acc_free[g], 2 * 4); }
+        for (int g = 0; g < NG; ++g) { mbar_init(&mma_done[g], 1); mbar_init(&acc_free[g], 2 * 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         for (int g = 0; g < NG; ++g)
             for (int hf = 0; hf < 2; ++hf) mbar_expect_tx(&b_half[(g * 2 + 1) * 2 + hf], Cfg::HALF_B);   // buffer 1 of each group receives h_0 at the end of step 0
@@ -223,34 +233,48 @@ __global__ void __launch_bounds__(LTHREADS, 1) k_lstm_rec_tc(LstmTcParams p) {
     const bool dbg_cta = (p.dbg & 1) && blockIdx.x == 0 && blockIdx.y == 0;
 
     if (warp < N_ISSUE) {
-        // ===================== eight MMA issuers, one per (group, K half, product) = one per accumulator chain: W1 x [h1|h2s] and
-        // W2s x [h1|..] over the unit slots of source CTAs 0..3 / 4..7, 8 dependent M128 x N(2 GL) x K16 MMAs each.  Round 1 had ONE
-        // issuer for everything (64 MMAs per step = 650-1000 cycles of issue on the critical path of every step).
-        const int g = warp >> 2, chain = warp & 3, half = chain >> 1, prod = chain & 1;
+        // ===================== one MMA issuer per group.  Per step 32 MMAs M128 x N(2 GL) x K16 in four accumulator chains (product W1 /
+        // W2s x K half), interleaved so that dependent MMAs are two issues apart.  Measured (KB_LSTM_DBG): a tiny MMA costs ~17 cycles
+        // of tensor pipe whatever its N (the 128 x N fp32 accumulator read-modify-write, not the math), so the 32 MMAs of a group and
+        // step take ~550 cycles however many threads issue them - eight issuer warps (one per chain and group) bought nothing and their
+        // mbarrier polling competed with the epilogue warps' shuffles for the MIO pipe.
+        const int g = warp;
         const uint32_t id1 = idesc_f16(0, 0, 128, N1);
-        const uint32_t dacc = tmem_base + (uint32_t)(g * GSTRIDE + prod * 2 * N1 + half * N1);
-        const uint32_t abase = tmem_base + (uint32_t)(TM_A0 + prod * 128 + half * 64);    // K16 step = 8 columns of fp16 pairs
         for (int s = 0; s < maxlen; ++s) {
             const int cur = s & 1;
-            uint64_t *bh = &b_half[(g * 2 + cur) * 2 + half];
             const long long d_w0 = dbg_cta ? clock64() : 0;
-            if (s > 0) {
-                mbar_wait(&acc_free[g], (uint32_t)((s - 1) & 1));            // complete long before h_{s-1} can arrive
-                mbar_wait(bh, (uint32_t)(((s - 1) >> 1) & 1));               // default acquire.cta: an acquire.cluster wait costs a CCTL.IVALL per step
-            }
-            const long long d_w1 = dbg_cta ? clock64() : 0;
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // st.async writes (generic proxy) -> UMMA reads (async proxy)
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            if (elect_one()) {
-                const uint32_t b0 = smem_u32(sB + (g * 2 + cur) * B_BUF_B) + (uint32_t)(half * 16 * CH_B);
+            if (s > 0) mbar_wait(&acc_free[g], (uint32_t)((s - 1) & 1));    // complete long before h_{s-1} can arrive
+            // The two groups take turns on the tensor pipe: g0(s), g1(s), g0(s+1), ...  Left alone they fall into lock-step (both
+            // start at step 0, and whoever is behind catches up while the other queues on the shared pipe / DSMEM port), and then
+            // both wait for the same resource at the same time and idle together.  The other group's mma_done barrier is only READ
+            // here (parity wait, no arrival).
+            if (g == 0) { if (s > 0) mbar_wait(&mma_done[1], (uint32_t)((s - 1) & 1)); }
+            else mbar_wait(&mma_done[0], (uint32_t)(s & 1));
+            long long d_w1 = 0;
+#pragma unroll 1
+            for (int half = 0; half < 2; ++half) {
+                uint64_t *bh = &b_half[(g * 2 + cur) * 2 + half];
+                if (s > 0) mbar_wait(bh, (uint32_t)(((s - 1) >> 1) & 1));     // default acquire.cta: an acquire.cluster wait costs a CCTL.IVALL per step
+                if (half == 1) d_w1 = dbg_cta ? clock64() : 0;
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // st.async writes (generic proxy) -> UMMA reads (async proxy)
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                if (elect_one()) {
+                    const uint32_t b0 = smem_u32(sB + (g * 2 + cur) * B_BUF_B) + (uint32_t)(half * 16 * CH_B);
+                    const uint32_t dacc = tmem_base + (uint32_t)(g * GSTRIDE + half * N1);
+                    const uint32_t abase = tmem_base + (uint32_t)(TM_A0 + half * 64);      // K16 step = 8 columns of fp16 pairs
 #pragma unroll
-                for (int jj = 0; jj < 8; ++jj) {                              // K16 step = k-chunks 2j, 2j+1
-                    const uint64_t bd = umma_desc_nosw(b0 + (uint32_t)(jj * 2 * CH_B), (uint32_t)CH_B, 128u);
-                    umma_f16_ts(dacc, abase + (uint32_t)(jj * 8), bd, id1, jj ? 1u : 0u);
+                    for (int jj = 0; jj < 8; ++jj) {                          // K16 step = k-chunks 2j, 2j+1
+                        const uint64_t bd = umma_desc_nosw(b0 + (uint32_t)(jj * 2 * CH_B), (uint32_t)CH_B, 128u);
+                        umma_f16_ts(dacc, abase + (uint32_t)(jj * 8), bd, id1, jj ? 1u : 0u);                               // W1  x [h1 | h2s]
+                        umma_f16_ts(dacc + (uint32_t)(2 * N1), abase + 128u + (uint32_t)(jj * 8), bd, id1, jj ? 1u : 0u);   // W2s x [h1 | ..]
+                    }
+                    if (s + 2 < maxlen) mbar_expect_tx(bh, Cfg::HALF_B);      // refilled during step s+1 (nobody can send that before receiving our h_s)
                 }
+                __syncwarp();
+            }
+            if (elect_one()) {
                 umma_commit(&mma_done[g]);
-                if (prod == 0 && s + 2 < maxlen) mbar_expect_tx(bh, Cfg::HALF_B);     // refilled during step s+1
-                if (dbg_cta && chain == 0 && s >= 100 && s < 104) {
+                if (dbg_cta && s >= 100 && s < 104) {
                     long long *d = p.dbgbuf + ((s - 100) * 2 + g) * 12;
                     d[0] = d_w0; d[1] = d_w1; d[2] = clock64();
                 }
@@ -258,7 +282,7 @@ __global__ void __launch_bounds__(LTHREADS, 1) k_lstm_rec_tc(LstmTcParams p) {
             __syncwarp();
         }
     } else {
-        // ===================== epilogue warps 8..23: quarter q = warp & 3; sub-warp sw = (warp-8) >> 2: group g = sw >> 1, half sw2 = sw & 1.
+        // ===================== epilogue warps 2..17: quarter q = warp & 3; sub-warp sw = (warp-2) >> 2: group g = sw >> 1, half sw2 = sw & 1.
         // A warp owns LPW lines of its group x the 8 unit slots of its TMEM lane quarter and never synchronises with another warp:
         // gate values are regrouped by quad shuffles, h leaves as st.async straight from registers.
         const int q = warp & 3;                            // TMEM lane quarter: unit slots 8q .. 8q+7
@@ -310,6 +334,11 @@ __global__ void __launch_bounds__(LTHREADS, 1) k_lstm_rec_tc(LstmTcParams p) {
         // gate non-linearity without divergence: sigmoid(x) for i, f, o; tanh(x) = 2*sigmoid(2x) - 1 for the candidate gate
         const float act_k = gate == 2 ? 2.f : 1.f;
         const bool dbg_w = dbg_cta && q == 0 && sw2 == 0 && lane == 0;
+        const bool bulk = p.handoff == 1;
+        // whole 8-slot rows of this quarter are real units and 16-byte aligned in the output planes (hid 256: always)
+        const bool vec_planes = p.out_hi && 8 * q + 7 < p.U && (int)rank * p.U + 8 * q + 7 < hid && (OC & 7) == 0 &&
+                                ((dir * hid + (int)rank * p.U + 8 * q) & 7) == 0 &&
+                                (reinterpret_cast<uintptr_t>(p.out_hi) & 15) == 0 && (reinterpret_cast<uintptr_t>(p.out_lo) & 15) == 0;
 
         for (int s = 0; s < maxlen; ++s) {
             const int nxt = (s + 1) & 1;
@@ -361,10 +390,27 @@ __global__ void __launch_bounds__(LTHREADS, 1) k_lstm_rec_tc(LstmTcParams p) {
                 const __half h1 = __float2half_rn(h);
                 const __half h2 = __float2half_rn((h - __half2float(h1)) * X2_SCALE);
                 hv[t] = h; hh1[t] = h1; hh2[t] = h2; wr[t] = cval[t] && live;
-                gather_rows8(h1, h2, lane, row1[t], row2[t]);
+                if (bulk) {                                 // both fp16 planes of h straight into the staged piece: [k-chunk q][row][unit slot]
+                    __half *cx = reinterpret_cast<__half *>(sx + (size_t)((g * 2 + (s & 1)) * Cfg::SRC_B + q * CH_B + sw2 * Cfg::WB_B));
+                    cx[(4 * t + gate) * 8 + jq] = h1;
+                    cx[(LPW + 4 * t + gate) * 8 + jq] = h2;
+                }
+                if (!bulk) gather_rows8(h1, h2, lane, row1[t], row2[t]);
             }
             const long long e_cell = dbg_w ? clock64() : 0;
-            if (s + 1 < maxlen) {
+            if (bulk) {
+                // generic writes -> the bulk copy engine (async proxy); then the group's 8 warps have staged the piece and warp wi sends
+                // all of it to CTA wi: 8 packets streams of 1 KB and 8 transaction-count updates per destination buffer instead of 512
+                // 16-byte packets (measured: the st.async hand-off is packet-rate bound, ~1300 cycles from send to the last arrival)
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                named_bar(1 + g, 256);
+                if (s + 1 < maxlen && lane == 0) {
+                    const uint32_t wi = (uint32_t)((sw2 << 2) | q);
+                    bulk_s2s(mapa32(smem_u32(sB), wi) + (uint32_t)((g * 2 + nxt) * B_BUF_B) + (uint32_t)rank * (uint32_t)Cfg::SRC_B,
+                             smem_u32(sx + (size_t)(g * 2 + (s & 1)) * Cfg::SRC_B), (uint32_t)Cfg::SRC_B,
+                             mapa32(smem_u32(b_half), wi) + (uint32_t)(((g * 2 + nxt) * 2) + (int)(rank >> 2)) * 8u);
+                }
+            } else if (s + 1 < maxlen) {
                 const uint32_t boff = (uint32_t)((g * 2 + nxt) * B_BUF_B), bar = dstBar + (uint32_t)((g * 2 + nxt) * 2) * 8u;
 #pragma unroll
                 for (int t = 0; t < NT; ++t) {
@@ -378,7 +424,20 @@ __global__ void __launch_bounds__(LTHREADS, 1) k_lstm_rec_tc(LstmTcParams p) {
             for (int t = 0; t < NT; ++t)
                 if (wr[t]) {
                     if (p.out) p.out[ooff[t]] = hv[t];
-                    if (p.out_hi) { p.out_hi[ooff[t]] = hh1[t]; p.out_lo[ooff[t]] = hh2[t]; }
+                    if (p.out_hi) {
+                        if (vec_planes) {
+                            if (bulk) {                     // the staged piece holds the complete rows (this warp wrote them before the barrier)
+                                const uint8_t *cx = sx + (size_t)((g * 2 + (s & 1)) * Cfg::SRC_B + q * CH_B + sw2 * Cfg::WB_B);
+                                if (jq == 0) row1[t] = *reinterpret_cast<const uint4 *>(cx + (4 * t + gate) * 16);
+                                else if (jq == 1) row2[t] = *reinterpret_cast<const uint4 *>(cx + (LPW + 4 * t + gate) * 16);
+                            }
+                            // every lane of the line holds the complete 16-byte rows: one lane stores the h1 row, another the h2s row
+                            // (8 sectors per warp and step instead of 64 scattered 2-byte stores that clogged the LSU queue the
+                            // st.async hand-off and the shuffles of the other group share)
+                            if (jq == 0) *reinterpret_cast<uint4 *>(p.out_hi + ooff[t]) = row1[t];
+                            else if (jq == 1) *reinterpret_cast<uint4 *>(p.out_lo + ooff[t] - 1) = row2[t];
+                        } else { p.out_hi[ooff[t]] = hh1[t]; p.out_lo[ooff[t]] = hh2[t]; }
+                    }
                     ooff[t] += ostride;
                 }
 #pragma unroll
