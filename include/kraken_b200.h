@@ -147,6 +147,25 @@ int  kb_recognize_u8(kb_model *m, const uint8_t *lines, int lines_on_device, int
                      int32_t *ends, float *confs, int32_t *counts, int32_t max_out, int32_t *out_lens, float *probs,
                      int probs_on_device, void *stream);
 
+#define KB_DTYPE_F32 0
+#define KB_DTYPE_U8  1
+
+/* ---- record assembly on the device -------------------------------------------------------------------------
+ * kb_model_set_codec: label -> Unicode code point table of a 1:1 codec (`PytorchCodec.l2c_single` with one code point per label,
+ *   kraken/lib/codec.py:164-172); l2c[label] = 0 for labels outside the codec.  n_labels = 0 clears it.
+ * kb_recognize_records: kb_recognize (dtype KB_DTYPE_F32) / kb_recognize_u8 (KB_DTYPE_U8; invert_max as there) whose CTC collapse writes
+ *   records instead of raw labels: codepoints[i][j] = l2c[label] (0: not in the codec - `decode` skips those unless strict), and
+ *   starts / ends are positions in the ORIGINAL line image exactly as `_scale_val` yields them (kraken/lib/vgsl/rpred.py:138-157,231):
+ *       net_scale = widths[i] / out_lens[i];   in_scale = orig_widths[i] / (widths[i] - 2 * padding)
+ *       pos = int(round(min(max((t * net_scale - padding) * in_scale, 0), orig_widths[i] - 1)))        (Python doubles, round-half-even)
+ *   orig_widths (n): width of each line image before ImageInputTransforms; padding: the transform's horizontal padding.
+ *   confs / counts / out_lens as kb_recognize.  What is left for the host is ''.join(map(chr, codepoints)).                        */
+int  kb_model_set_codec(kb_model *m, const uint32_t *l2c, int32_t n_labels);
+int  kb_recognize_records(kb_model *m, const void *lines, int dtype, int lines_on_device, int32_t n, int32_t h, int32_t w,
+                          const int32_t *widths, const int16_t *invert_max, float temperature, const int32_t *orig_widths, int32_t padding,
+                          uint32_t *codepoints, int32_t *starts, int32_t *ends, float *confs, int32_t *counts, int32_t max_out,
+                          int32_t *out_lens, void *stream);
+
 /* ---- bbox line extraction + the PIL half of the input transforms on the device ----------------------------
  * Replaces, for bbox lines of horizontal text, `im.crop(box)` (kraken/lib/segmentation.py:1631-1643) and the image half of
  * ImageInputTransforms (kraken/lib/dataset/utils.py:123-147): Grayscale, `pil_fixed_resize` = img.resize((int(w * oh / h), oh), LANCZOS)
@@ -184,8 +203,6 @@ int  kb_prepare_lines_u8(kb_model *m, const uint8_t *page, int page_on_device, i
  * work queued there so far).  A batch whose activations left the fp16 operand range is repeated on the fp32 kernels inside kb_wait.
  * kb_recognize_async fails with KB_ERR_SPEC when every slot still holds an un-waited ticket.  Replaces the reference's one-batch-at-
  * a-time loop over `_rec_predict` (kraken/lib/vgsl/rpred.py:126-131,171-176,210-229).                                              */
-#define KB_DTYPE_F32 0
-#define KB_DTYPE_U8  1
 int  kb_set_pipeline_depth(kb_model *m, int32_t depth);       /* 1..16 slots; allowed only while no ticket is in flight */
 int  kb_pipeline_depth(const kb_model *m);
 int  kb_recognize_async(kb_model *m, const void *lines, int dtype, int lines_on_device, int32_t n, int32_t h, int32_t w,

@@ -14,7 +14,7 @@ import torch
 from ._lib import check, lib
 from .vgsl import TorchVGSLModel, _as_f32, _on_device, _ptr, _stream_for
 
-__all__ = ['compute_segmentation_map', 'segmentation_heatmap']
+__all__ = ['compute_segmentation_map', 'segmentation_heatmap', 'apply_legacy_mask']
 
 
 def segmentation_heatmap(model: TorchVGSLModel, pages, size: Optional[Sequence[int]] = None):
@@ -52,14 +52,36 @@ def segmentation_heatmap(model: TorchVGSLModel, pages, size: Optional[Sequence[i
     return out
 
 
+def apply_legacy_mask(tensor_im: torch.Tensor, mask_tensor: torch.Tensor) -> torch.Tensor:
+    """The legacy `mask` argument of `kraken.blla.compute_segmentation_map` (kraken/blla.py:107-116): the mask image goes through the
+    same ImageInputTransforms as the page (hence arrives INVERTED, like the page) and `tensor_im[~transforms(mask).bool()] = 0` zeroes
+    the page wherever the transformed mask is 0.  `tensor_im`: (C, H, W) network input, `mask_tensor`: the transformed mask with the
+    shape the reference's boolean indexing accepts (equal to `tensor_im`'s, or (1, H, W) for one-channel models).  Stays on the device
+    the page tensor is on; returns a new tensor."""
+    if tuple(mask_tensor.shape) != tuple(tensor_im.shape):
+        # the reference's boolean index raises for a (1, H, W) mask on a 3-channel page
+        raise IndexError(f'The shape of the mask {list(mask_tensor.shape)} at index 0 does not match the shape of the indexed tensor '
+                         f'{list(tensor_im.shape)} at index 0')
+    keep = mask_tensor.to(tensor_im.device).bool()
+    return torch.where(keep, tensor_im, torch.zeros((), dtype=tensor_im.dtype, device=tensor_im.device))
+
+
 def compute_segmentation_map(model: TorchVGSLModel, tensor_im, scal_shape: Optional[Sequence[int]] = None,
-                             padding: Union[int, Sequence[int]] = 0) -> dict:
+                             padding: Union[int, Sequence[int]] = 0, mask_tensor: Optional[torch.Tensor] = None) -> dict:
     """Mirror of the dict the reference returns (minus the PIL-side `scal_im`): heat map as numpy (C', H, W),
-    class map and bounding regions from the model metadata, padding removed (spred.py:271-287)."""
+    class map and bounding regions from the model metadata, padding removed (spred.py:271-287).  `mask_tensor`: the legacy masking of
+    `kraken.blla.compute_segmentation_map` (blla.py:107-116), see `apply_legacy_mask` (single page only, as in the reference)."""
     if isinstance(padding, int):
         padding = (padding,) * 4
     elif len(padding) == 2:
         padding = (padding[0], padding[0], padding[1], padding[1])
+    if mask_tensor is not None:
+        if tensor_im.ndim == 4:
+            if tensor_im.shape[0] != 1:
+                raise ValueError('the legacy mask applies to a single page')
+            tensor_im = apply_legacy_mask(tensor_im[0], mask_tensor)[None]
+        else:
+            tensor_im = apply_legacy_mask(tensor_im, mask_tensor)
     t = tensor_im if tensor_im.ndim == 4 else tensor_im[None]
     size = tuple(scal_shape) if scal_shape is not None else tuple(t.shape[2:])
     o = segmentation_heatmap(model, t, size)

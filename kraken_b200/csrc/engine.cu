@@ -53,6 +53,8 @@ struct LeafWeights {
     __half *c_hi = nullptr, *c_lo = nullptr;  // [tap][chunk][Cout][32] fp16 operand planes for the tcgen05 convolution
     int s2d = 0, s_th = 0, s_tw = 0, s_py = 0, s_px = 0, s_cs = 0;   // stride-2 conv as space-to-depth stride-1 conv: block taps, block padding, channels
     void *wpk = nullptr;                      // W_hh as fp16 operand planes of the tcgen05 recurrences
+    float *peep = nullptr;                    // ocropy cell: peephole vectors [dir][ip, fp, op][h]
+    std::vector<std::vector<float>> legacy_host;   // legacy cells rewritten as (W_ih, W_hh, b_ih, b_hh) per direction
     float *whh_t = nullptr; int whh_ncp = 0;  // hidden > 256: W_hh^T [dir][k = h][gate column (unit, gate) padded to 64] for the per-step GEMM
     int ncp = 0, K = 0, ncols = 0;
 };
@@ -147,6 +149,8 @@ struct kb_model {
     bool fuse = true;                // fused layer groups (KB_FUSE=0 runs every layer on its own, e.g. for layer taps)
     bool use_tc = true;              // tcgen05 GEMM path (KB_GEMM=ffma forces the CUDA-core kernel)
     // kb_prepare_lines_u8 scratch: device [page copy | line table | coefficient tables | horizontal-pass rows | line maxima], pinned host mirror of the tables
+    unsigned *codec_lut = nullptr; int codec_n = 0;      // kb_model_set_codec: label -> code point of a 1:1 codec (device)
+    std::vector<unsigned> codec_host;
     char *prep_dev = nullptr; size_t prep_dev_cap = 0; char *prep_host = nullptr; size_t prep_host_cap = 0;
     kb_model() { wss.emplace_back(new Workspace()); }
     Workspace *ws0() { return wss[0].get(); }
@@ -154,6 +158,8 @@ struct kb_model {
         for (void *p : dev_allocs) cudaFree(p);
         dev_allocs.clear();
         if (prep_dev) cudaFree(prep_dev);
+        if (codec_lut) cudaFree(codec_lut);
+        codec_lut = nullptr; codec_n = 0;
         if (prep_host) cudaFreeHost(prep_host);
         prep_dev = prep_host = nullptr; prep_dev_cap = prep_host_cap = 0;
         for (auto &w : wss) w->release();
@@ -337,13 +343,34 @@ static void finalize_weights(kb_model *m) {
             need(2);
             w.aux = upload(m, w.host[0]); w.bias = upload(m, w.host[1]);
         } else if (n.kind == K_LSTM) {
-            if (n.legacy) throw Unsupported(n.name + ": legacy clstm/ocropy LSTM variants are not implemented by the engine");
             const int dirs = n.bidi ? 2 : 1, h = n.hidden, gc = dirs * 4 * h;
-            need(4 * dirs);
             const int K = n.cin, ncp = (gc + 63) / 64 * 64;
+            if (n.legacy) {
+                // legacy cells -> the standard layout: the constant-one input column of weight_ih IS the bias (layers.py:522-524), no b_hh;
+                // the ocropy cell keeps its peephole vectors for the per-step kernel
+                if (n.legacy == 2 && !n.bidi) throw SpecError(n.name + ": the ocropy cell is always bidirectional (PeepholeBidiLSTM); the reference's forward fails for a one-directional spec");
+                for (int d = 0; d < dirs; ++d)
+                    for (int sl = 0; sl < (n.legacy == 2 ? 5 : 2); ++sl)
+                        if ((int)w.loaded.size() <= d * 5 + sl || !w.loaded[d * 5 + sl]) throw SpecError("weights of layer " + n.name + " not loaded (missing tensor for nn." + n.path + ")");
+                std::vector<std::vector<float>> std4((size_t)4 * dirs);
+                std::vector<float> peep;
+                for (int d = 0; d < dirs; ++d) {
+                    const std::vector<float> &wl = w.host[d * 5 + 0];        // [4h][K + 1]
+                    std4[d * 4 + 0].resize((size_t)4 * h * K); std4[d * 4 + 2].resize((size_t)4 * h); std4[d * 4 + 3].assign((size_t)4 * h, 0.f);
+                    for (int r = 0; r < 4 * h; ++r) {
+                        std4[d * 4 + 2][r] = wl[(size_t)r * (K + 1)];
+                        memcpy(&std4[d * 4 + 0][(size_t)r * K], &wl[(size_t)r * (K + 1) + 1], (size_t)K * sizeof(float));
+                    }
+                    std4[d * 4 + 1] = w.host[d * 5 + 1];
+                    if (n.legacy == 2) for (int k = 0; k < 3; ++k) peep.insert(peep.end(), w.host[d * 5 + 2 + k].begin(), w.host[d * 5 + 2 + k].end());
+                }
+                w.legacy_host = std::move(std4);
+                w.peep = n.legacy == 2 ? upload(m, peep) : nullptr;
+            } else need(4 * dirs);
+            const std::vector<std::vector<float>> &H4 = n.legacy ? w.legacy_host : w.host;
             std::vector<float> wt((size_t)K * ncp, 0.f), b((size_t)gc, 0.f), whh((size_t)dirs * 4 * h * h);
             for (int d = 0; d < dirs; ++d) {
-                const std::vector<float> &wih = w.host[d * 4 + 0], &wh = w.host[d * 4 + 1], &bih = w.host[d * 4 + 2], &bhh = w.host[d * 4 + 3];
+                const std::vector<float> &wih = H4[d * 4 + 0], &wh = H4[d * 4 + 1], &bih = H4[d * 4 + 2], &bhh = H4[d * 4 + 3];
                 for (int g = 0; g < 4; ++g)
                     for (int u = 0; u < h; ++u) {
                         const int col = d * 4 * h + u * 4 + g, row = g * h + u;      // torch gate order i,f,g,o
@@ -354,12 +381,12 @@ static void finalize_weights(kb_model *m) {
             }
             w.wt = upload(m, wt); w.bias = upload(m, b); w.aux = upload(m, whh); w.ncp = ncp; w.K = K; w.ncols = gc;
             w.whh_t = nullptr;
-            if (h > 256 || getenv("KB_LSTM_GENERIC")) {
+            if (h > 256 || n.legacy == 2 || getenv("KB_LSTM_GENERIC")) {
                 // generic per-step path: W_hh^T [dir][k][col = 4 u + gate], columns padded to the GEMM's tile
                 const int hncp = (4 * h + 63) / 64 * 64;
                 std::vector<float> t((size_t)dirs * h * hncp, 0.f);
                 for (int d = 0; d < dirs; ++d) {
-                    const std::vector<float> &wh = w.host[d * 4 + 1];          // [4h][h], torch gate order i,f,g,o
+                    const std::vector<float> &wh = H4[d * 4 + 1];          // [4h][h], torch gate order i,f,g,o
                     for (int g = 0; g < 4; ++g)
                         for (int u = 0; u < h; ++u)
                             for (int k = 0; k < h; ++k) t[((size_t)d * h + k) * hncp + u * 4 + g] = wh[(size_t)(g * h + u) * h + k];
@@ -371,7 +398,7 @@ static void finalize_weights(kb_model *m) {
                 for (int d = 0; d < dirs; ++d)
                     for (int g = 0; g < 4; ++g)
                         for (int u = 0; u < h; ++u)
-                            memcpy(&rows[(size_t)(d * 4 * h + u * 4 + g) * K], &w.host[d * 4][(size_t)(g * h + u) * K], (size_t)K * sizeof(float));
+                            memcpy(&rows[(size_t)(d * 4 * h + u * 4 + g) * K], &H4[d * 4][(size_t)(g * h + u) * K], (size_t)K * sizeof(float));
                 upload_split(m, rows, w);
             }
             if (h > 128 && h <= 256) {
@@ -381,7 +408,7 @@ static void finalize_weights(kb_model *m) {
                 const int U = (h + 7) / 8;
                 std::vector<uint16_t> pk((size_t)dirs * 8 * 2 * 128 * 256, 0);      // [dir][rank][plane][gate row][k] fp16, plain row-major
                 for (int d = 0; d < dirs; ++d) {
-                    const std::vector<float> &wh = w.host[d * 4 + 1];      // [4h][h]
+                    const std::vector<float> &wh = H4[d * 4 + 1];      // [4h][h]
                     for (int r = 0; r < 8; ++r)
                         for (int mrow = 0; mrow < 128; ++mrow) {
                             const int slot = mrow >> 2, gate = mrow & 3, u = r * U + slot;
@@ -406,7 +433,7 @@ static void finalize_weights(kb_model *m) {
                 // single-CTA tcgen05 recurrence (k_lstm_rec_tc_small): [dir][plane][gate row = 4*unit + gate][k = 32] fp16
                 std::vector<uint16_t> pk((size_t)dirs * 2 * 128 * 32, 0);
                 for (int d = 0; d < dirs; ++d) {
-                    const std::vector<float> &wh = w.host[d * 4 + 1];      // [4h][h]
+                    const std::vector<float> &wh = H4[d * 4 + 1];      // [4h][h]
                     for (int u = 0; u < h; ++u)
                         for (int gate = 0; gate < 4; ++gate)
                             for (int u2 = 0; u2 < h; ++u2) {
@@ -528,6 +555,7 @@ struct Exec {
                 LstmStepParams sp;
                 sp.G = G; sp.gx = lp.gx; sp.hstate = Hd; sp.cstate = Cd; sp.out = lp.out; sp.lens = lp.lens; sp.nseq = nseq; sp.T = lp.T; sp.hid = hid;
                 sp.dirs = lp.dirs; sp.dir = d; sp.t = t; sp.q2 = lp.q2; sp.s_outer = lp.s_outer; sp.s_inner = lp.s_inner; sp.step = lp.step;
+                sp.peep = w.peep ? w.peep + (size_t)d * 3 * hid : nullptr;
                 LAUNCH(m, k_lstm_generic_step, (unsigned)(((long long)nseq * hid + 255) / 256), 256, 0, st, sp);
             }
     }
@@ -647,7 +675,8 @@ struct Exec {
             Tensor full = mk(dfull);
             // the tensor-core recurrences can emit the consumer's fp16 operand planes themselves (no k_split_f16 pass)
             const int ks_p = hid <= 32 ? 1 : hid <= 64 ? 2 : hid <= 128 ? 4 : 8;
-            const bool generic_rec = w.whh_t && (hid > 256 || (getenv("KB_LSTM_GENERIC") && atoi(getenv("KB_LSTM_GENERIC")) != 0));   // writes fp32 only
+            const bool generic_rec = w.whh_t && (hid > 256 || n.legacy == 2 || (getenv("KB_LSTM_GENERIC") && atoi(getenv("KB_LSTM_GENERIC")) != 0));   // writes fp32 only
+            if (n.legacy == 2 && packed) throw Unsupported(n.name + ": 'PackedSequence' object has no attribute 'transpose' (the reference's ocropy cell cannot run on batches with seq_lens)");
             const bool tc_rec = (ks_p == 8 || ks_p == 1) && w.wpk && m->use_tc && !generic_rec && !(getenv("KB_LSTM_TC") && atoi(getenv("KB_LSTM_TC")) == 0);
             const bool lplanes = planes_hint && tc_rec && !n.summarize;
             planes_hint = false;
@@ -670,7 +699,7 @@ struct Exec {
                 else { lp.nseq = (int)(x.n * x.w); lp.T = (int)x.h; lp.q2 = (int)x.w; lp.s_outer = x.h * x.w; lp.s_inner = 1; lp.step = x.w; }
                 const int ks = hid <= 32 ? 1 : hid <= 64 ? 2 : hid <= 128 ? 4 : 8;
                 lp.U = (hid + ks - 1) / ks;
-                const bool generic = w.whh_t && (hid > 256 || (getenv("KB_LSTM_GENERIC") && atoi(getenv("KB_LSTM_GENERIC")) != 0));
+                const bool generic = generic_rec;
                 // tcgen05 recurrence (lstm_tc.cuh) for hidden sizes 129..256: 0.44 ms vs 0.69 ms for the CUDA-core kernel on cfg2 and
                 // only 64 instead of 112 SMs; KB_LSTM_TC=0 selects the CUDA-core kernel (accurate expf/tanhf, fp32 FMA)
                 const bool tc_on = w.wpk && m->use_tc && !(getenv("KB_LSTM_TC") && atoi(getenv("KB_LSTM_TC")) == 0);
@@ -1222,7 +1251,7 @@ static void infer(const Node &n, Dims &d, Lens &l) {
 }
 
 static size_t decode_bytes(int n, int T, int max_out) {
-    return (size_t)n * T * 8 + (size_t)n * max_out * 16 + (size_t)n * 4 + 8 * 256;
+    return (size_t)n * T * 8 + (size_t)n * max_out * 16 + (size_t)n * 4 + (size_t)n * 24 + 12 * 256;
 }
 
 // Fixed-stride result block of a recognition call: [labels | starts | ends | confs] (n x max_out each) + counts (n).
@@ -1231,14 +1260,14 @@ static size_t result_block_bytes(int n, int max_out) { return (size_t)n * max_ou
 // Enqueues the CTC collapse and the copy of the result block into the pinned buffer `*pinned` (grown as needed); returns the block
 // size.  Nothing here waits for the device.
 static size_t decode_enqueue(int n, int T, int max_out, const int *d_lab, const float *d_conf, const int *d_lens, cudaStream_t st,
-                             Arena &arena, void **pinned, size_t *pinned_cap, int64_t *launches) {
+                             Arena &arena, void **pinned, size_t *pinned_cap, int64_t *launches, RecordXform rx = RecordXform{nullptr, 0, nullptr, nullptr, 0}) {
     const size_t per = (size_t)n * max_out;
     const size_t blk = result_block_bytes(n, max_out);
     char *d = (char *)arena.alloc(blk);
     int *o_lab = (int *)d, *o_start = (int *)(d + per * 4), *o_end = (int *)(d + per * 8);
     float *o_conf = (float *)(d + per * 12); int *o_cnt = (int *)(d + per * 16);
     const int staged = (size_t)T * 8 <= 40 * 1024;           // labels + confidences of one line in shared memory
-    k_ctc_collapse<<<(unsigned)n, 256, (size_t)((T + 31) / 32 + 1 + (staged ? 2 * T : 0)) * sizeof(int), st>>>(d_lab, d_conf, d_lens, n, T, max_out, o_lab, o_start, o_end, o_conf, o_cnt, staged);
+    k_ctc_collapse<<<(unsigned)n, 256, (size_t)((T + 31) / 32 + 1 + (staged ? 2 * T : 0)) * sizeof(int), st>>>(d_lab, d_conf, d_lens, n, T, max_out, o_lab, o_start, o_end, o_conf, o_cnt, staged, rx);
     ++*launches;
     CK(cudaPeekAtLastError());
     if (blk > *pinned_cap) {
@@ -1313,6 +1342,7 @@ static const float *stage_u8_lines(kb_model *m, Workspace *ws, const uint8_t *li
 struct RecognizeArgs {
     const float *lines; int lines_on_device; int n, h, w; const int32_t *widths; float temperature; int max_out;
     float *probs; int probs_on_device;
+    const int32_t *orig_widths = nullptr; int padding = 0;      // kb_recognize_records: code points + `_scale_val` positions instead of labels / time steps
 };
 static void recognize_enqueue(kb_model *m, Workspace *ws, const RecognizeArgs &a, cudaStream_t st, int T, int C, std::vector<int32_t> &olens) {
     const int n = a.n;
@@ -1338,7 +1368,24 @@ static void recognize_enqueue(kb_model *m, Workspace *ws, const RecognizeArgs &a
         else LAUNCH(m, k_probs_nct_simple, (unsigned)((rows + 7) / 8), 256, 0, st, r.y.p, dp, n, T, C, a.temperature);
         if (!a.probs_on_device) CK(cudaMemcpyAsync(a.probs, dp, (size_t)n * C * T * 4, cudaMemcpyDeviceToHost, st));
     }
-    decode_enqueue(n, T, a.max_out, d_lab, d_conf, d_lens, st, ws->arena, &ws->pinned, &ws->pinned_cap, &m->launches);
+    RecordXform rx{nullptr, 0, nullptr, nullptr, 0};
+    if (a.orig_widths) {
+        // per line: net_scale = line width / output length, in_scale = original width / (line width - 2 padding)   (rpred.py:143-146)
+        std::vector<double> sc((size_t)2 * n); std::vector<int> mv((size_t)n);
+        for (int i = 0; i < n; ++i) {
+            const int wi = a.widths ? a.widths[i] : a.w;
+            if (olens[i] <= 0 || wi - 2 * a.padding == 0) throw ShapeError("record assembly: empty line or line no wider than its padding");
+            sc[(size_t)2 * i] = (double)wi / (double)olens[i];
+            sc[(size_t)2 * i + 1] = (double)a.orig_widths[i] / (double)(wi - 2 * a.padding);
+            mv[(size_t)i] = a.orig_widths[i];
+        }
+        double *d_sc = (double *)ws->arena.alloc((size_t)2 * n * sizeof(double));
+        int *d_mv = (int *)ws->arena.alloc((size_t)n * sizeof(int));
+        CK(cudaMemcpyAsync(d_sc, sc.data(), (size_t)2 * n * sizeof(double), cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(d_mv, mv.data(), (size_t)n * sizeof(int), cudaMemcpyHostToDevice, st));
+        rx = RecordXform{m->codec_lut, m->codec_n, d_sc, d_mv, a.padding};
+    }
+    decode_enqueue(n, T, a.max_out, d_lab, d_conf, d_lens, st, ws->arena, &ws->pinned, &ws->pinned_cap, &m->launches, rx);
     t_dec.reset();
 }
 
@@ -1526,7 +1573,8 @@ int kb_forward(kb_model *m, const float *x, int x_on_device, int32_t n, int32_t 
 // synchronous recognition on workspace 0 and the caller's stream
 static int recognize_locked(kb_model *m, const float *lines, int lines_on_device, int32_t n, int32_t h, int32_t w, const int32_t *widths,
                  float temperature, int32_t *labels, int32_t *starts, int32_t *ends, float *confs, int32_t *counts,
-                 int32_t max_out, int32_t *out_lens, float *probs, int probs_on_device, void *stream) {
+                 int32_t max_out, int32_t *out_lens, float *probs, int probs_on_device, void *stream,
+                 const int32_t *orig_widths = nullptr, int32_t padding = 0) {
     cudaStream_t st = (cudaStream_t)stream;
     Workspace *ws = m->ws0();
     ws->timing = m->timing;
@@ -1534,6 +1582,13 @@ static int recognize_locked(kb_model *m, const float *lines, int lines_on_device
     recognition_dims(m, n, h, w, &T, &C);
     std::vector<int32_t> olens;
     RecognizeArgs a{lines, lines_on_device, n, h, w, widths, temperature, max_out, probs, probs_on_device};
+    a.orig_widths = orig_widths; a.padding = padding;
+    if (orig_widths && !m->codec_lut) {                      // the table is uploaded lazily, on the model's device
+        if (m->codec_host.empty()) throw SpecError("kb_recognize_records: call kb_model_set_codec() first");
+        CK(cudaMalloc((void **)&m->codec_lut, m->codec_host.size() * sizeof(unsigned)));
+        CK(cudaMemcpy(m->codec_lut, m->codec_host.data(), m->codec_host.size() * sizeof(unsigned), cudaMemcpyHostToDevice));
+        m->codec_n = (int)m->codec_host.size();
+    }
     const auto t0 = std::chrono::steady_clock::now();
     run_with_range_fallback(m, ws, st, [&]() { recognize_enqueue(m, ws, a, st, T, C, olens); });
     const auto t1 = std::chrono::steady_clock::now();
@@ -1577,6 +1632,42 @@ int kb_recognize_u8(kb_model *m, const uint8_t *lines, int lines_on_device, int3
         const float *f32 = stage_u8_lines(m, m->ws0(), lines, lines_on_device, n, h, w, widths, invert_max, (cudaStream_t)stream);
         return recognize_locked(m, f32, 1, n, h, w, widths, temperature, labels, starts, ends, confs, counts, max_out, out_lens,
                                 probs, probs_on_device, stream);
+    });
+}
+
+int kb_model_set_codec(kb_model *m, const uint32_t *l2c, int32_t n_labels) {
+    if (!m || (n_labels > 0 && !l2c) || n_labels < 0) return fail(KB_ERR_ARG, "invalid codec table");
+    std::lock_guard<std::mutex> lk(m->mu);
+    return guarded([&]() {
+        m->codec_host.assign(l2c, l2c + n_labels);
+        if (m->codec_lut) {
+            DeviceGuard dguard;
+            CK(cudaSetDevice(m->device));
+            CK(cudaDeviceSynchronize());
+            cudaFree(m->codec_lut);
+            m->codec_lut = nullptr; m->codec_n = 0;
+        }
+        return (int)KB_OK;
+    });
+}
+
+int kb_recognize_records(kb_model *m, const void *lines, int dtype, int lines_on_device, int32_t n, int32_t h, int32_t w,
+                         const int32_t *widths, const int16_t *invert_max, float temperature, const int32_t *orig_widths, int32_t padding,
+                         uint32_t *codepoints, int32_t *starts, int32_t *ends, float *confs, int32_t *counts, int32_t max_out,
+                         int32_t *out_lens, void *stream) {
+    if (!m || !lines || !orig_widths || !codepoints || !starts || !ends || !confs || !counts) return fail(KB_ERR_ARG, "NULL argument");
+    if (dtype != KB_DTYPE_F32 && dtype != KB_DTYPE_U8) return fail(KB_ERR_ARG, "dtype must be KB_DTYPE_F32 or KB_DTYPE_U8");
+    if (max_out <= 0 || padding < 0) return fail(KB_ERR_ARG, "max_out must be positive, padding non-negative");
+    if (!(temperature > 0.f)) return fail(KB_ERR_ARG, "temperature must be positive");
+    if (n <= 0 || h <= 0 || w <= 0) return fail(KB_ERR_SHAPE, "empty input batch");
+    std::lock_guard<std::mutex> lk(m->mu);
+    return guarded([&]() {
+        DeviceGuard dguard;
+        ensure_ready(m);
+        const float *f32 = (const float *)lines; int on_dev = lines_on_device;
+        if (dtype == KB_DTYPE_U8) { f32 = stage_u8_lines(m, m->ws0(), (const uint8_t *)lines, lines_on_device, n, h, w, widths, invert_max, (cudaStream_t)stream); on_dev = 1; }
+        return recognize_locked(m, f32, on_dev, n, h, w, widths, temperature, (int32_t *)codepoints, starts, ends, confs, counts, max_out, out_lens,
+                                nullptr, 0, stream, orig_widths, padding);
     });
 }
 

@@ -763,6 +763,7 @@ struct LstmStepParams {
     const float *G; const float *gx; float *hstate; float *cstate; float *out; const int *lens;
     int nseq, T, hid, dirs, dir, t;                // t = step counter (0 .. maxlen-1)
     int q2; long long s_outer, s_inner, step;
+    const float *peep;                             // ocropy cell (layers.py:74-103): [ip | fp | op][hid] of this direction, else NULL
 };
 __global__ void k_lstm_generic_step(LstmStepParams p) {
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -774,10 +775,21 @@ __global__ void k_lstm_generic_step(LstmStepParams p) {
     const long long pix = (long long)(q / p.q2) * p.s_outer + (long long)(q % p.q2) * p.s_inner + (long long)tt * p.step;
     const float4 g4 = *reinterpret_cast<const float4 *>(p.G + ((size_t)q * p.hid + u) * 4);
     const float4 x4 = *reinterpret_cast<const float4 *>(p.gx + (size_t)pix * (p.dirs * 4 * p.hid) + (size_t)p.dir * 4 * p.hid + (size_t)u * 4);
-    const float gi = 1.f / (1.f + expf(-(g4.x + x4.x))), gf = 1.f / (1.f + expf(-(g4.y + x4.y)));
-    const float gg = tanhf(g4.z + x4.z), go = 1.f / (1.f + expf(-(g4.w + x4.w)));
-    const float c = gf * p.cstate[idx] + gi * gg;
-    const float h = go * tanhf(c);
+    float c, h;
+    if (!p.peep) {
+        const float gi = 1.f / (1.f + expf(-(g4.x + x4.x))), gf = 1.f / (1.f + expf(-(g4.y + x4.y)));
+        const float gg = tanhf(g4.z + x4.z), go = 1.f / (1.f + expf(-(g4.w + x4.w)));
+        c = gf * p.cstate[idx] + gi * gg;
+        h = go * tanhf(c);
+    } else {
+        // PeepholeLSTMCell: peepholes from c_{t-1} into input / forget gate, from c_t into the output gate - which the reference does NOT
+        // squash (hy = (outgate + w_op * cy) * tanh(cy), layers.py:98-101)
+        const float cx = p.cstate[idx];
+        const float gi = 1.f / (1.f + expf(-((g4.x + x4.x) + p.peep[u] * cx))), gf = 1.f / (1.f + expf(-((g4.y + x4.y) + p.peep[p.hid + u] * cx)));
+        const float gg = tanhf(g4.z + x4.z);
+        c = gf * cx + gi * gg;
+        h = ((g4.w + x4.w) + p.peep[2 * p.hid + u] * c) * tanhf(c);
+    }
     p.cstate[idx] = c; p.hstate[idx] = h;
     p.out[(size_t)pix * (p.dirs * p.hid) + (size_t)p.dir * p.hid + u] = h;
 }
@@ -1063,9 +1075,26 @@ __global__ void k_col_argmax(const float *__restrict__ probs, int N, int C, int 
 // run's end reads shared memory.  (History: one warp walking the chunks serially = 7 dependent global round trips, 28 us for
 // cfg2's T = 200; then block-parallel with the run walk on global memory = one dependent L2 round trip per time step of the
 // longest run, 23 us.)  `staged` = 0 keeps everything in global memory (lines too long for shared memory).
+// Optional record assembly at the write: the label becomes its code point (1:1 codec table, kraken/lib/codec.py:164-172;
+// 0 = not in the codec) and start / end become positions in the original line image exactly as `_scale_val` computes them
+// (kraken/lib/vgsl/rpred.py:138-157,231): int(round(min(max((v * net_scale - padding) * in_scale, 0), width - 1))) with Python's double
+// arithmetic - separately rounded multiply / subtract / multiply (no FMA contraction) and round-half-to-even.
+struct RecordXform {
+    const unsigned *lut; int n_lut;        // label -> code point
+    const double *scale;                   // [N][2] = (net_scale, in_scale) per line
+    const int *maxv;                       // [N] original line width
+    int padding;
+};
+__device__ __forceinline__ int scale_val_dev(int v, double net_scale, double in_scale, int padding, int maxv) {
+    double x = __dmul_rn(__dsub_rn(__dmul_rn((double)v, net_scale), (double)padding), in_scale);
+    x = x > 0.0 ? x : 0.0;                                                 // max(x, min_val = 0)
+    const double hi = (double)(maxv - 1);
+    x = x < hi ? x : hi;                                                   // min(x, max_val - 1)
+    return (int)rint(x);
+}
 __global__ void __launch_bounds__(256) k_ctc_collapse(const int *__restrict__ lab, const float *__restrict__ conf, const int *__restrict__ lens,
                                int N, int T, int max_out, int *__restrict__ o_lab, int *__restrict__ o_start,
-                               int *__restrict__ o_end, float *__restrict__ o_conf, int *__restrict__ o_cnt, int staged) {
+                               int *__restrict__ o_end, float *__restrict__ o_conf, int *__restrict__ o_cnt, int staged, RecordXform rx) {
     extern __shared__ int cc_sm[];                    // [chunks + 1]: run starts per chunk, then their exclusive prefix sums; [T] labels; [T] confs
     const int n = blockIdx.x;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
@@ -1110,8 +1139,14 @@ __global__ void __launch_bounds__(256) k_ctc_collapse(const int *__restrict__ la
             int e = t; float mx = cf[t];
             while (e + 1 < L && l[e + 1] == cur) { ++e; mx = fmaxf(mx, cf[e]); }
             if (pos < max_out) {
-                o_lab[(size_t)n * max_out + pos] = cur; o_start[(size_t)n * max_out + pos] = t;
-                o_end[(size_t)n * max_out + pos] = e; o_conf[(size_t)n * max_out + pos] = mx;
+                int vl = cur, vs = t, ve = e;
+                if (rx.scale) {
+                    vl = (cur >= 0 && cur < rx.n_lut) ? (int)rx.lut[cur] : 0;
+                    const double ns = rx.scale[2 * n], is = rx.scale[2 * n + 1];
+                    vs = scale_val_dev(t, ns, is, rx.padding, rx.maxv[n]); ve = scale_val_dev(e, ns, is, rx.padding, rx.maxv[n]);
+                }
+                o_lab[(size_t)n * max_out + pos] = vl; o_start[(size_t)n * max_out + pos] = vs;
+                o_end[(size_t)n * max_out + pos] = ve; o_conf[(size_t)n * max_out + pos] = mx;
             }
         }
     }

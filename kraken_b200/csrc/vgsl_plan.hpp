@@ -470,6 +470,20 @@ static inline std::unique_ptr<Plan> parse_spec(const std::string &spec_in) {
         if (n->kind == K_CONV) { add(".co.weight", {n->cout, n->cin, n->kh, n->kw}, 0); add(".co.bias", {n->cout}, 1); }
         else if (n->kind == K_LINEAR) { add(".lin.weight", {n->cout, n->cin + (n->aug ? 1 : 0)}, 0); add(".lin.bias", {n->cout}, 1); }
         else if (n->kind == K_GN) { add(".layer.weight", {n->cin}, 0); add(".layer.bias", {n->cin}, 1); }
+        else if (n->kind == K_LSTM && n->legacy) {
+            // legacy cells (layers.py:498-511): a constant-one input column instead of biases; 'c' = nn.LSTM(in + 1, h, bias=False),
+            // 'o' = PeepholeBidiLSTM (always both directions; peephole vectors weight_{ip,fp,op})
+            int64_t h4 = 4 * (int64_t)n->hidden;
+            const int ndir = (n->legacy == 2 || n->bidi) ? 2 : 1;
+            for (int d = 0; d < ndir; ++d) {
+                const std::string sfx = d ? "_reverse" : "";
+                add(".layer.weight_ih_l0" + sfx, {h4, n->cin + 1}, d * 5 + 0); add(".layer.weight_hh_l0" + sfx, {h4, n->hidden}, d * 5 + 1);
+                if (n->legacy == 2) {
+                    add(".layer.weight_ip_l0" + sfx, {n->hidden}, d * 5 + 2); add(".layer.weight_fp_l0" + sfx, {n->hidden}, d * 5 + 3);
+                    add(".layer.weight_op_l0" + sfx, {n->hidden}, d * 5 + 4);
+                }
+            }
+        }
         else if (n->kind == K_LSTM && !n->legacy) {
             int64_t h4 = 4 * (int64_t)n->hidden;
             // nn.LSTM parameter order: all forward tensors, then the reverse ones

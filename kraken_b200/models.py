@@ -172,6 +172,58 @@ class TorchSeqRecognizer:
         return {'labels': labels, 'starts': starts, 'ends': ends, 'confs': confs, 'counts': counts,
                 'olens': olens if widths is not None else None}
 
+    # -- record assembly on the device -----------------------------------------------
+    def recognize_records(self, line, lens, orig_widths, padding: int = 16, invert_max=None):
+        """`_recognize_*_lines` up to the record fields (kraken/lib/vgsl/rpred.py:126-157): one engine call returns, per line,
+        (text, [[start, end]] in the coordinates of the ORIGINAL line image - `_scale_val`, rpred.py:231 - and confidences).
+        Code-point lookup and position scaling run inside the CTC collapse kernel (`kb_recognize_records`); needs a 1:1 codec
+        (one label - one code point, the common case; anything else: `predict` + the reference's own record code).
+        `line`: float32 (N, C, H, W) as `predict` takes it, or uint8 as `recognize_u8` (then `invert_max` applies)."""
+        net = self.nn
+        if self.codec is None or self.codec._single_lut() is None:
+            raise ValueError('recognize_records needs a codec in which every code is one label and one code point')
+        is_u8 = isinstance(line, torch.Tensor) and line.dtype == torch.uint8 or isinstance(line, np.ndarray) and line.dtype == np.uint8
+        x = (line if isinstance(line, torch.Tensor) else torch.as_tensor(np.ascontiguousarray(line))).contiguous() if is_u8 else _as_f32(line)
+        net._ensure_finalized(x)
+        n, c, h, w = (int(v) for v in x.shape)
+        if c != net.input[1]:
+            raise ValueError(f'expected {net.input[1]} input channels, got {c}')
+        if _on_device(x) and x.device.index != net._device:
+            x = x.to(f'cuda:{net._device}')
+        if getattr(self, '_codec_pushed', None) is not self.codec:
+            lut = self.codec._single_lut()
+            table = np.zeros(lut.shape[0], np.uint32)
+            for i, ch in enumerate(lut.tolist()):
+                table[i] = ord(ch) if ch else 0
+            check(lib.kb_model_set_codec(net._h, table.ctypes.data, int(table.shape[0])))
+            self._codec_pushed = self.codec
+        widths = np.ascontiguousarray(torch.as_tensor(lens).cpu().numpy(), dtype=np.int32) if lens is not None else np.full(n, w, np.int32)
+        ow = np.ascontiguousarray(np.asarray(orig_widths), dtype=np.int32)
+        if widths.shape != (n,) or ow.shape != (n,):
+            raise ValueError('seq_lens and orig_widths must have one entry per batch element')
+        inv = np.ascontiguousarray(np.asarray(invert_max), dtype=np.int16) if invert_max is not None else None
+        dims = net.infer_dims(n, h, w)
+        if dims[2] != 1:
+            raise KrakenInputException('Expected dimension 3 to be 1, actual {}'.format(tuple(dims)))
+        stride = max(dims[3], 1)
+        cps = np.empty((n, stride), np.uint32); starts = np.empty((n, stride), np.int32); ends = np.empty((n, stride), np.int32)
+        confs = np.empty((n, stride), np.float32); counts = np.empty(n, np.int32); olens = np.zeros(n, np.int32)
+        on_dev = _on_device(x)
+        check(lib.kb_recognize_records(net._h, _ptr(x), 1 if is_u8 else 0, int(on_dev), n, h, w, widths.ctypes.data,
+                                       inv.ctypes.data if inv is not None else None, float(self.temperature), ow.ctypes.data, int(padding),
+                                       cps.ctypes.data, starts.ctypes.data, ends.ctypes.data, confs.ctypes.data, counts.ctypes.data, stride,
+                                       olens.ctypes.data, _stream_for(x, net._device)))
+        out = []
+        for i in range(n):
+            k = int(min(counts[i], stride))
+            keep = cps[i, :k] != 0
+            if self.codec.strict and not keep.all():
+                from .codec import KrakenEncodeException
+                raise KrakenEncodeException('Non-decodable sequence encountered.')
+            text = ''.join(map(chr, cps[i, :k][keep].tolist()))
+            out.append((text, np.stack([starts[i, :k][keep], ends[i, :k][keep]], 1).tolist(), confs[i, :k][keep].tolist()))
+        return out
+
     # -- asynchronous pipeline (kb_recognize_async / kb_wait) --------------------------------------------
     def set_pipeline_depth(self, depth: int) -> None:
         """Number of batches one host thread can keep in flight on this model (own stream + workspace per slot, one copy of

@@ -188,6 +188,8 @@ class TorchVGSLModel:
                 torch.nn.init.xavier_uniform_(t)
             elif name.endswith('.lin.bias'):
                 t.zero_()
+            elif '.layer.weight_' in name and len(shape) == 1:
+                torch.nn.init.uniform_(t, -0.1, 0.1)       # peephole vectors of the ocropy cell (the reference leaves them uninitialised)
             elif '.layer.weight_' in name:
                 torch.nn.init.orthogonal_(t)
             elif '.layer.bias_' in name:

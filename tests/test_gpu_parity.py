@@ -580,3 +580,34 @@ def test_generic_recurrence_matches_resident_kernels():
     assert rel_err(out, ref) <= TIGHT
     out2, _ = m.nn(x.cuda(), lens)                       # default kernels on the same handle
     assert rel_err(out2, ref) <= TIGHT
+
+
+@pytest.mark.parametrize('spec,with_lens', [
+    ('[1,32,0,1 Cr3,3,16 Mp2,2 S1(1x0)1,3 Lbxc40 Lfxc24 O1c30]', True),       # legacy clstm cells: ones column instead of biases
+    ('[1,32,0,1 Cr3,3,16 Mp2,2 S1(1x0)1,3 Lbxo40 O1c30]', False),             # legacy ocropy cell: peepholes, un-squashed output gate
+    ('[1,16,0,1 Cr3,3,8 Lbyo8 Lbxc136 O1c12]', False),                        # ocropy along y, clstm on the tensor-core recurrence
+])
+def test_legacy_lstm_cells(spec, with_lens):
+    """`L..c` / `L..o` (kraken/lib/vgsl/layers.py:74-181,498-524) against the oracle, which is pinned bit for bit to the reference's
+    cells (tests/test_oracle.py)."""
+    om = vo.OracleModel(spec)
+    wts = om.init_like_reference(71)
+    g = torch.Generator().manual_seed(71)
+    n, w = 5, 96
+    x = torch.rand(n, 1, om.input[2], w, generator=g)
+    lens = None
+    if with_lens:
+        lens = torch.tensor([96, 40, 96, 17, 64])
+        for i, l in enumerate(lens.tolist()):
+            x[i, ..., l:] = 0
+    ref, rl = om.forward(x, lens)
+    m = kb.TorchVGSLModel(vgsl=spec)
+    m.load_state_dict(wts)
+    m.to('cuda:0')
+    out, ol = m.nn(x.cuda(), lens)
+    assert rel_err(out, ref) <= TIGHT, rel_err(out, ref)
+    if lens is not None:
+        assert ol.tolist() == rl.tolist()
+    if 'Lbxo' in spec:
+        with pytest.raises(Exception):                       # the reference's ocropy cell cannot take packed batches either
+            m.nn(x.cuda(), torch.tensor([96, 40, 96, 17, 64]))

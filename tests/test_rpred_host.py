@@ -30,3 +30,18 @@ def test_resolve_type_to_model():
         resolve_type_to_model('syriac', nets)
     dd = defaultdict(lambda: 'D', nets)
     assert resolve_type_to_model('latin', dd, dd.default_factory()) == ('latin', 'A')
+
+
+def test_legacy_segmentation_mask_is_the_references_boolean_indexing():
+    """kraken/blla.py:115 `tensor_im[~transforms(mask).bool()] = 0` on a one-channel page; shape errors as the reference's indexing raises"""
+    import pytest
+    import torch
+    from kraken_b200.blla import apply_legacy_mask
+    g = torch.Generator().manual_seed(0)
+    page = torch.rand(1, 40, 30, generator=g)
+    mask = (torch.rand(1, 40, 30, generator=g) > 0.5).float() * 0.7          # any non-zero value keeps a pixel
+    ref = page.clone()
+    ref[~mask.bool()] = 0
+    assert torch.equal(apply_legacy_mask(page, mask), ref)
+    with pytest.raises(IndexError):
+        apply_legacy_mask(torch.rand(3, 40, 30), mask)
