@@ -248,6 +248,7 @@ static void set_kernel_attributes() {
     CK(cudaFuncSetAttribute(tc::k_gemm_tc<128, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::GemmCfg<128>::SMEM_BYTES));
     CK(cudaFuncSetAttribute(tc::k_gemm_tc<256, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::GemmCfg<256>::SMEM_BYTES));
     CK(cudaFuncSetAttribute(tc::k_gemm_tc<256, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::GemmCfg<256>::SMEM_BYTES));
+    CK(cudaFuncSetAttribute((tc::k_gemm_tc<256, 0, 2>), cudaFuncAttributeMaxDynamicSharedMemorySize, tc::GemmCfg<256>::SMEM_BYTES));
     CK(cudaFuncSetAttribute(ctc::k_conv_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     CK(cudaFuncSetAttribute(ltc::k_lstm_rec_tc<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, ltc::ClusterCfg<8>::SMEM_BYTES));
     CK(cudaFuncSetAttribute(ltc::k_lstm_rec_tc<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, ltc::ClusterCfg<16>::SMEM_BYTES));
@@ -512,7 +513,23 @@ struct Exec {
         // (profiles/r02_*), and it leaves less L2 bandwidth to the kernels of the other batches in flight.  KB_GEMM_BN=128 forces it.
         const bool force128 = getenv("KB_GEMM_BN") && atoi(getenv("KB_GEMM_BN")) == 128;
         const bool wide = am || (N > 128 && !force128);
-        if (am) LAUNCH(m, (tc::k_gemm_tc<256, 1>), (unsigned)std::min(tiles_m, m->sm_count), tc::THREADS, tc::GemmCfg<256>::SMEM_BYTES, st, ta_hi, ta_lo, tb_hi, tb_lo, gp);
+        // 2-CTA clusters with the weight tile multicast for wide outputs with at least a few tiles per cluster (KB_GEMM_MC=0 turns it off)
+        const bool mc = !am && wide && tiles_m >= 4 && !(getenv("KB_GEMM_MC") && atoi(getenv("KB_GEMM_MC")) == 0);
+        if (mc) {
+            const int npairs = ((tiles_m + 1) / 2) * ((N + 255) / 256);
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3((unsigned)(2 * std::min(npairs, std::max(1, m->sm_count / 2))), 1, 1);
+            cfg.blockDim = dim3(tc::THREADS, 1, 1);
+            cfg.dynamicSmemBytes = tc::GemmCfg<256>::SMEM_BYTES; cfg.stream = st;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+            cfg.attrs = at; cfg.numAttrs = 1;
+            CK(cudaLaunchKernelEx(&cfg, tc::k_gemm_tc<256, 0, 2>, ta_hi, ta_lo, tb_hi, tb_lo, gp));
+            ++m->launches;
+            CK(cudaPeekAtLastError());
+        }
+        else if (am) LAUNCH(m, (tc::k_gemm_tc<256, 1>), (unsigned)std::min(tiles_m, m->sm_count), tc::THREADS, tc::GemmCfg<256>::SMEM_BYTES, st, ta_hi, ta_lo, tb_hi, tb_lo, gp);
         else if (wide) LAUNCH(m, (tc::k_gemm_tc<256, 0>), (unsigned)std::min(tiles_m * ((N + 255) / 256), m->sm_count), tc::THREADS, tc::GemmCfg<256>::SMEM_BYTES, st, ta_hi, ta_lo, tb_hi, tb_lo, gp);
         else LAUNCH(m, (tc::k_gemm_tc<128, 0>), (unsigned)std::min(tiles_m * ((N + 127) / 128), m->sm_count), tc::THREADS, tc::GemmCfg<128>::SMEM_BYTES, st, ta_hi, ta_lo, tb_hi, tb_lo, gp);
     }

@@ -171,7 +171,11 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volat
 
 // MODE 0: C = A B^T + bias (+ activation).  MODE 1 (BNT = 256, N <= 256, one n-tile): the recognition head - logits are never
 // written; each row's arg-max label and softmax confidence are (rpred.py:226 softmax, ctc_decoder.py:65 max over classes).
-template <int BNT, int MODE>
+// CL = 2 (BNT = 256, MODE 0): clusters of two CTAs work on vertically adjacent tiles (same weight columns) and each CTA loads only its
+// half of the weight tile, multicast into both CTAs' stage buffers: a third fewer bytes from L2 per k-block (A 16 KB + B 16 KB instead
+// of 16 + 32).  The mainloop of the one-CTA kernel is bound by the aggregate L2 -> SM feed (cfg2's projection pulls 944 MB = 7.7 TB/s
+// through L2 at 0.122 ms while the MMAs of a k-block take 786 cycles), not by the tensor pipe.
+template <int BNT, int MODE, int CL = 1>
 __global__ void __launch_bounds__(THREADS, 1)
 k_gemm_tc(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
           const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo, GemmTcParams p) {
@@ -186,12 +190,14 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ C
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tiles_m = (p.M + BM - 1) / BM, tiles_n = (p.N + BNT - 1) / BNT;
-    const int ntiles = tiles_m * tiles_n;
+    const int ntiles = ((tiles_m + CL - 1) / CL) * tiles_n;        // work items of a cluster: CL vertically adjacent tiles
     const int nkb = (p.K + BK - 1) / BK;
-    const int first = blockIdx.x, nworkers = gridDim.x;
+    uint32_t crank = 0;
+    if (CL > 1) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
+    const int first = blockIdx.x / CL, nworkers = gridDim.x / CL;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], CL); }
         for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -203,6 +209,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ C
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    if (CL > 1) asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");   // peer barriers initialised
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
@@ -211,17 +218,23 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ C
             int stage = 0; uint32_t phase = 0;
             for (int tile = first; tile < ntiles; tile += nworkers) {
                 // n-tiles innermost: consecutive CTAs share the same A rows (L2 reuse), weights stay L2 resident
-                const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BNT;
+                const int m0 = ((tile / tiles_n) * CL + (int)crank) * BM, n0 = (tile % tiles_n) * BNT;
                 for (int kb = 0; kb < nkb; ++kb) {
                     mbar_wait(&empty[stage], phase ^ 1);
                     uint8_t *st = smem + stage * STAGE_BYTES;
                     mbar_expect_tx(&full[stage], STAGE_BYTES);
                     tma_load_2d(st, &tm_a_hi, &full[stage], kb * BK, m0);
                     tma_load_2d(st + A_TILE, &tm_a_lo, &full[stage], kb * BK, m0);
+                    if (CL == 1) {
 #pragma unroll
-                    for (int h = 0; h < BNT / 128; ++h) {                       // weight tile = 128-row boxes per plane
-                        tma_load_2d(st + 2 * A_TILE + h * (128 * BK * 2), &tm_b_hi, &full[stage], kb * BK, n0 + 128 * h);
-                        tma_load_2d(st + 2 * A_TILE + B_TILE + h * (128 * BK * 2), &tm_b_lo, &full[stage], kb * BK, n0 + 128 * h);
+                        for (int h = 0; h < BNT / 128; ++h) {                   // weight tile = 128-row boxes per plane
+                            tma_load_2d(st + 2 * A_TILE + h * (128 * BK * 2), &tm_b_hi, &full[stage], kb * BK, n0 + 128 * h);
+                            tma_load_2d(st + 2 * A_TILE + B_TILE + h * (128 * BK * 2), &tm_b_lo, &full[stage], kb * BK, n0 + 128 * h);
+                        }
+                    } else {                                                    // this CTA's 128-row box of each plane, into both CTAs
+                        const int h = (int)crank;
+                        tma_load_2d_mc(st + 2 * A_TILE + h * (128 * BK * 2), &tm_b_hi, &full[stage], kb * BK, n0 + 128 * h, (uint16_t)0x3);
+                        tma_load_2d_mc(st + 2 * A_TILE + B_TILE + h * (128 * BK * 2), &tm_b_lo, &full[stage], kb * BK, n0 + 128 * h, (uint16_t)0x3);
                     }
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
@@ -249,7 +262,8 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ C
                         umma_f16(d_corr, a_hi + adv, b_lo + adv, idesc, 1u);
                         umma_f16(d_main, a_hi + adv, b_hi + adv, idesc, (kb | k) ? 1u : 0u);
                     }
-                    umma_commit(&empty[stage]);                               // frees the smem stage when these MMAs retire
+                    if (CL == 1) umma_commit(&empty[stage]);                  // frees the smem stage when these MMAs retire
+                    else umma_commit_mc(&empty[stage], (uint16_t)0x3);        // ... in both CTAs: the peer multicasts into this stage too
                     if (kb == nkb - 1) umma_commit(&tfull[acc]);              // accumulators complete -> epilogue
                 }
                 __syncwarp();
@@ -267,7 +281,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ C
         uint32_t acc_phase[2] = {0, 0}; int acc = 0;
         constexpr float R = 1.f / X2_SCALE;
         for (int tile = first; tile < ntiles; tile += nworkers) {
-            const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BNT;
+            const int m0 = ((tile / tiles_n) * CL + (int)crank) * BM, n0 = (tile % tiles_n) * BNT;
             mbar_wait(&tfull[acc], acc_phase[acc]);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 256);
@@ -388,6 +402,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ C
     // ===================== teardown =====================
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    if (CL > 1) asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");   // no multicast / remote arrive may target an exited CTA
     if (warp == 1) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
