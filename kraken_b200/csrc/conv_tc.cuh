@@ -43,6 +43,7 @@ struct ConvTcParams {
     int a_row_bytes;                     // bytes of one plane of one input-row buffer (multiple of 1024)
     int acc_sets;
     int a_sets;                          // 2: the input rows of the NEXT (item, chunk) load while the current one is multiplied
+    int w_res;                           // 1: all kh*kw*NC weight tiles stay resident in shared memory (loaded once per CTA); nstb = their number
 };
 
 __device__ __forceinline__ void tma_load_4d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2, int c3) {
@@ -72,7 +73,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ C
 
     if (threadIdx.x == 0) {
         for (int r = 0; r < 2 * MAX_ROWS; ++r) { mbar_init(&full_a[r], 1); mbar_init(&empty_a[r], 1); }
-        for (int s = 0; s < NSTB; ++s) { mbar_init(&full_b[s], 1); mbar_init(&empty_b[s], 1); }
+        for (int s = 0; s < (p.w_res ? 1 : NSTB); ++s) { mbar_init(&full_b[s], 1); mbar_init(&empty_b[s], 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], CEPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -89,6 +90,14 @@ k_conv_tc(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ C
         // ===================== TMA producer =====================
         if (elect_one()) {
             uint32_t a_phase = 0; int aset = 0; int bs = 0; uint32_t b_phase = 0;
+            if (p.w_res && (int)blockIdx.x < nitems) {                      // the whole filter bank once (items_c == 1: tile = all output channels)
+                const int ntaps = p.kh * p.kw * p.NC;
+                mbar_expect_tx(&full_b[0], (uint32_t)ntaps * b_tx);
+                for (int ti = 0; ti < ntaps; ++ti) {
+                    tma_load_2d(b_base + ti * b_stage, &tm_w_hi, &full_b[0], 0, ti * p.Cout);
+                    tma_load_2d(b_base + ti * b_stage + b_plane, &tm_w_lo, &full_b[0], 0, ti * p.Cout);
+                }
+            }
             for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
                 const int ct = item % p.items_c; int rest = item / p.items_c;
                 const int ws = rest % p.items_w, hp = (rest / p.items_w) % p.items_h, n = rest / (p.items_w * p.items_h);
@@ -105,7 +114,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ C
                             tma_load_4d(aset_base + r_loaded * a_row, &tm_x_hi, &fa[r_loaded], cc * 32, w0, h0 + r_loaded, n);
                             tma_load_4d(aset_base + r_loaded * a_row + a_plane, &tm_x_lo, &fa[r_loaded], cc * 32, w0, h0 + r_loaded, n);
                         }
-                        for (int kx = 0; kx < p.kw; ++kx) {
+                        for (int kx = 0; kx < p.kw && !p.w_res; ++kx) {
                             mbar_wait(&empty_b[bs], b_phase ^ 1);
                             mbar_expect_tx(&full_b[bs], b_tx);
                             const int wrow = ((ky * p.kw + kx) * p.NC + cc) * p.Cout + ct * CT;
@@ -127,6 +136,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ C
         const uint32_t idesc = idesc_f16(0, 0, 128, CT), idesc2 = idesc_f16(0, 0, 128, 2 * CT);
         const bool merged = 2 * CT <= 256;
         uint32_t a_phase = 0; int aset = 0; int bs = 0; uint32_t b_phase = 0; int acc = 0; uint32_t acc_phase = 0;
+        if (p.w_res && (int)blockIdx.x < nitems) mbar_wait(&full_b[0], 0);   // resident filter bank has landed
         for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
             mbar_wait(&tempty[acc], acc_phase ^ 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -138,10 +148,10 @@ k_conv_tc(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ C
                     if (ky == 0) mbar_wait(&fa[0], a_phase);
                     mbar_wait(&fa[ky + 1], a_phase);
                     for (int kx = 0; kx < p.kw; ++kx) {
-                        mbar_wait(&full_b[bs], b_phase);
+                        if (!p.w_res) mbar_wait(&full_b[bs], b_phase);
                         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                         if (elect_one()) {
-                            const uint32_t sb = smem_u32(b_base + bs * b_stage);
+                            const uint32_t sb = smem_u32(b_base + (p.w_res ? ((ky * p.kw + kx) * p.NC + cc) : bs) * b_stage);
                             const uint64_t b_hi = umma_desc_sw64(sb), b_lo = umma_desc_sw64(sb + b_plane);
                             const bool first = (cc | ky | kx) == 0;
 #pragma unroll
@@ -162,7 +172,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ C
                                     }
                                 }
                             }
-                            umma_commit(&empty_b[bs]);
+                            if (!p.w_res) umma_commit(&empty_b[bs]);
                             if (kx == p.kw - 1) {
                                 // input row buffers whose last reader (for this chunk) was this tap row: row ky (and kh when ky == kh-1)
                                 umma_commit(&ea[ky]);
@@ -170,7 +180,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ C
                             }
                         }
                         __syncwarp();
-                        if (++bs == NSTB) { bs = 0; b_phase ^= 1; }
+                        if (!p.w_res && ++bs == NSTB) { bs = 0; b_phase ^= 1; }
                     }
                 }
                 if (ASETS == 2) { if (++aset == 2) { aset = 0; a_phase ^= 1; } }
@@ -288,10 +298,22 @@ inline bool make_map_nhwc(CUtensorMap *map, const __half *base, uint64_t N, uint
 // output-channel tile, weight-ring depth and input-row buffering for a layer; returns the dynamic shared memory the kernel needs.
 // Preference: two sets of input rows (the next item's rows load under the current item's MMAs: with one set the issuer stalled for a
 // TMA round trip at every item boundary), then as deep a weight ring as still fits (a tap's tile feeds only 12 MMAs).
-inline size_t conv_tc_plan(int kh, int kw, int cout, int *ct_out, int *nstb_out, int *a_row_bytes, int *a_sets_out = nullptr) {
+// `nc` (32-channel input chunks; 0 = unknown) lets the planner keep the whole filter bank resident when it fits next to two sets of
+// input rows and the tile covers all output channels: cfg2's conv2 (3 x 3 x 32 -> 64) = 72 KB of weights + 144 KB of rows.
+inline size_t conv_tc_plan(int kh, int kw, int cout, int *ct_out, int *nstb_out, int *a_row_bytes, int *a_sets_out = nullptr, int nc = 0,
+                           int *w_res_out = nullptr) {
     const int ct = cout <= 128 ? cout : (cout % 128 == 0 ? 128 : (cout % 64 == 0 ? 64 : 32));
     const int plane = ((TW + kw - 1) * PIX_B + 1023) & ~1023;
     const size_t rows = (size_t)(kh + 1) * 2 * plane, stage = (size_t)2 * ct * PIX_B, fixed = 512 + 1024, cap = 227 * 1024;
+    if (w_res_out) *w_res_out = 0;
+    if (nc > 0 && w_res_out && ct == cout && 2 * rows + (size_t)kh * kw * nc * stage + fixed <= cap) {
+        if (ct_out) *ct_out = ct;
+        if (nstb_out) *nstb_out = kh * kw * nc;
+        if (a_row_bytes) *a_row_bytes = plane;
+        if (a_sets_out) *a_sets_out = 2;
+        *w_res_out = 1;
+        return 2 * rows + (size_t)kh * kw * nc * stage + fixed;
+    }
     int a_sets = 2, nstb = MAX_STB;
     if (2 * rows + 4 * stage + fixed > cap) a_sets = 1;
     while (nstb > 4 && a_sets * rows + nstb * stage + fixed > cap) --nstb;

@@ -501,8 +501,9 @@ struct Exec {
         if (dry) return;
         if (!x.hi) LAUNCH(m, tc::k_split_f16, grid1d(M * K / 4, 256, m->sm_count), 256, 0, st, x.p, a_hi, a_lo, M * K / 4, ws->d_flag);
         CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
-        if (!tc::make_map_2d(&ta_hi, a_hi, (uint64_t)M, (uint64_t)K, tc::BM, tc::BK) || !tc::make_map_2d(&ta_lo, a_lo, (uint64_t)M, (uint64_t)K, tc::BM, tc::BK) ||
-            !tc::make_map_2d(&tb_hi, w.b_hi, (uint64_t)N, (uint64_t)K, 128, tc::BK) || !tc::make_map_2d(&tb_lo, w.b_lo, (uint64_t)N, (uint64_t)K, 128, tc::BK))
+        const uint32_t bkh = tc::BK;      // 64-byte operand rows; 128-byte rows (BKH = 64, two deeper stages) measured 0.1233 vs 0.1209 ms on cfg2's projection
+        if (!tc::make_map_2d(&ta_hi, a_hi, (uint64_t)M, (uint64_t)K, tc::BM, bkh) || !tc::make_map_2d(&ta_lo, a_lo, (uint64_t)M, (uint64_t)K, tc::BM, bkh) ||
+            !tc::make_map_2d(&tb_hi, w.b_hi, (uint64_t)N, (uint64_t)K, 128, bkh) || !tc::make_map_2d(&tb_lo, w.b_lo, (uint64_t)N, (uint64_t)K, 128, bkh))
             throw CudaError("cuTensorMapEncodeTiled failed");
         tc::GemmTcParams gp; gp.c = y; gp.bias = w.bias; gp.M = (int)M; gp.N = N; gp.K = K; gp.ldc = N; gp.act = act;
         gp.lab = am ? am->lab : nullptr; gp.conf = am ? am->conf : nullptr; gp.temperature = am ? am->temperature : 1.f;
@@ -513,8 +514,10 @@ struct Exec {
         // (profiles/r02_*), and it leaves less L2 bandwidth to the kernels of the other batches in flight.  KB_GEMM_BN=128 forces it.
         const bool force128 = getenv("KB_GEMM_BN") && atoi(getenv("KB_GEMM_BN")) == 128;
         const bool wide = am || (N > 128 && !force128);
-        // 2-CTA clusters with the weight tile multicast for wide outputs with at least a few tiles per cluster (KB_GEMM_MC=0 turns it off)
-        const bool mc = !am && wide && tiles_m >= 4 && !(getenv("KB_GEMM_MC") && atoi(getenv("KB_GEMM_MC")) == 0);
+        // KB_GEMM_MC=1: 2-CTA clusters with the weight tile multicast for wide outputs (a third fewer bytes from L2 per k-block).  Measured
+        // on cfg2's projection in both rounds (TF32 planes: 0.241 vs 0.239 ms; fp16 planes: 0.1217 vs 0.1210 ms): no gain - the L2 -> SM
+        // feed is not what holds the mainloop at 57 % tensor-pipe activity - so it stays an option, bit-identical to the default.
+        const bool mc = !am && wide && tiles_m >= 4 && getenv("KB_GEMM_MC") && atoi(getenv("KB_GEMM_MC")) == 1;
         if (mc) {
             const int npairs = ((tiles_m + 1) / 2) * ((N + 255) / 256);
             cudaLaunchConfig_t cfg = {};
@@ -967,7 +970,8 @@ struct Exec {
             cp.items_h = (int)((dconv.h + 1) / 2);
             cp.items_w = (int)((dconv.w + ctc::TW - 1) / ctc::TW);
             cp.sN = dconv.h * dconv.w * dconv.c; cp.sH = dconv.w * dconv.c; cp.sW = dconv.c;
-            const size_t smem = ctc::conv_tc_plan(w.s_th, w.s_tw, c0.cout, &cp.CT, &cp.nstb, &cp.a_row_bytes, &cp.a_sets);
+            const bool wres_ok = !(getenv("KB_CONV_WRES") && atoi(getenv("KB_CONV_WRES")) == 0);
+            const size_t smem = ctc::conv_tc_plan(w.s_th, w.s_tw, c0.cout, &cp.CT, &cp.nstb, &cp.a_row_bytes, &cp.a_sets, wres_ok ? cs / 32 : 0, &cp.w_res);
             cp.NC = cs / 32; cp.items_c = c0.cout / cp.CT;
             cp.acc_sets = 8 * cp.CT <= 512 ? 2 : 1;
             CUtensorMap tx_hi, tx_lo, tw_hi, tw_lo;
@@ -1019,7 +1023,8 @@ struct Exec {
             cp.items_w = (int)((dconv.w + ctc::TW - 1) / ctc::TW);
             if (fd) { cp.sN = dpost.w * dpost.h * dpost.c; cp.sW = dpost.h * dpost.c; cp.sH = dpost.c; }
             else { cp.sN = dpost.h * dpost.w * dpost.c; cp.sH = dpost.w * dpost.c; cp.sW = dpost.c; }
-            const size_t smem = ctc::conv_tc_plan(c0.kh, c0.kw, c0.cout, &cp.CT, &cp.nstb, &cp.a_row_bytes, &cp.a_sets);
+            const bool wres_ok = !(getenv("KB_CONV_WRES") && atoi(getenv("KB_CONV_WRES")) == 0);
+            const size_t smem = ctc::conv_tc_plan(c0.kh, c0.kw, c0.cout, &cp.CT, &cp.nstb, &cp.a_row_bytes, &cp.a_sets, wres_ok ? c0.cin / 32 : 0, &cp.w_res);
             cp.NC = c0.cin / 32; cp.items_c = c0.cout / cp.CT;
             cp.acc_sets = 8 * cp.CT <= 512 ? 2 : 1;
             CUtensorMap tx_hi, tx_lo, tw_hi, tw_lo;

@@ -43,11 +43,13 @@ constexpr int A_TILE = BM * BK * 2;                                       // byt
 // BNT = 128: TWO accumulator sets (2 x (128 + 128) columns), 6 stages x 32 KB: the epilogue of tile i runs under the MMAs of tile
 // i + 1.  Round 1 ran everything on the first shape: ncu showed the tensor pipe 49.8 % active with the MMA warp parked on `tempty`
 // for the whole epilogue of each of the 800 tiles of cfg2's projection.
-template <int BNT> struct GemmCfg {
+// BKH = K elements per pipeline stage: 32 (64-byte rows, SWIZZLE_64B) or 64 (128-byte rows, SWIZZLE_128B, two deeper stages)
+template <int BNT, int BKH = 32> struct GemmCfg {
     static constexpr int ACC_SETS = BNT == 128 ? 2 : 1;
-    static constexpr int B_TILE = BNT * BK * 2;
+    static constexpr int A_TILE = BM * BKH * 2;
+    static constexpr int B_TILE = BNT * BKH * 2;
     static constexpr int STAGE_BYTES = 2 * A_TILE + 2 * B_TILE;
-    static constexpr int STAGES = BNT == 128 ? 6 : 4;
+    static constexpr int STAGES = BKH == 64 ? (BNT == 128 ? 3 : 2) : (BNT == 128 ? 6 : 4);
     static constexpr int RED_BYTES = 4 * 2 * 32 * 4 * 4 + 256 * 4;          // arg-max epilogue: per (lane quarter, half, lane) 4 words, + the bias row
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + RED_BYTES;
 };
@@ -171,16 +173,18 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volat
 
 // MODE 0: C = A B^T + bias (+ activation).  MODE 1 (BNT = 256, N <= 256, one n-tile): the recognition head - logits are never
 // written; each row's arg-max label and softmax confidence are (rpred.py:226 softmax, ctc_decoder.py:65 max over classes).
-// CL = 2 (BNT = 256, MODE 0): clusters of two CTAs work on vertically adjacent tiles (same weight columns) and each CTA loads only its
-// half of the weight tile, multicast into both CTAs' stage buffers: a third fewer bytes from L2 per k-block (A 16 KB + B 16 KB instead
-// of 16 + 32).  The mainloop of the one-CTA kernel is bound by the aggregate L2 -> SM feed (cfg2's projection pulls 944 MB = 7.7 TB/s
-// through L2 at 0.122 ms while the MMAs of a k-block take 786 cycles), not by the tensor pipe.
-template <int BNT, int MODE, int CL = 1>
+// CL = 2 (BNT = 256, MODE 0; KB_GEMM_MC=1): clusters of two CTAs work on vertically adjacent tiles (same weight columns) and each CTA
+// loads only its half of the weight tile, multicast into both CTAs' stage buffers: a third fewer bytes from L2 per k-block (A 16 KB +
+// B 16 KB instead of 16 + 32; cfg2's projection otherwise pulls 944 MB = 7.7 TB/s through L2).  Measured: bit-identical results and
+// the same 0.121 ms - the L2 feed is not the limiter - so the one-CTA launch stays the default.
+template <int BNT, int MODE, int CL = 1, int BKH = 32>
 __global__ void __launch_bounds__(THREADS, 1)
 k_gemm_tc(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
           const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo, GemmTcParams p) {
-    using Cfg = GemmCfg<BNT>;
+    using Cfg = GemmCfg<BNT, BKH>;
+    constexpr int A_TILE = Cfg::A_TILE, BK = BKH;
     constexpr int STAGES = Cfg::STAGES, STAGE_BYTES = Cfg::STAGE_BYTES, B_TILE = Cfg::B_TILE, ACC_SETS = Cfg::ACC_SETS;
+    auto udesc = [](uint32_t a) { return BKH == 64 ? umma_desc_sw128(a) : umma_desc_sw64(a); };
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = smem_align1024(smem_raw);
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + STAGES * STAGE_BYTES);
@@ -253,8 +257,8 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ C
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 if (elect_one()) {
                     const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
-                    const uint64_t a_hi = umma_desc_sw64(sa), a_lo = umma_desc_sw64(sa + A_TILE);
-                    const uint64_t b_hi = umma_desc_sw64(sa + 2 * A_TILE), b_lo = umma_desc_sw64(sa + 2 * A_TILE + B_TILE);
+                    const uint64_t a_hi = udesc(sa), a_lo = udesc(sa + A_TILE);
+                    const uint64_t b_hi = udesc(sa + 2 * A_TILE), b_lo = udesc(sa + 2 * A_TILE + B_TILE);
 #pragma unroll
                     for (int k = 0; k < BK / 16; ++k) {
                         const uint64_t adv = (uint64_t)((k * 16 * 2) >> 4);     // 32 bytes per K=16 step inside the 64B swizzle atom

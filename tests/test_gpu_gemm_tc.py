@@ -49,14 +49,13 @@ def test_gemm_tc_special_values_and_no_bias():
 
 @pytest.mark.parametrize('M,N,K', [(1000, 2048, 768), (600, 200, 96), (129 + 512, 513, 64), (12800, 2048, 768)])
 def test_gemm_tc_weight_multicast_clusters(M, N, K, monkeypatch):
-    """Default for wide outputs: pairs of vertically adjacent tiles on 2-CTA clusters, each CTA multicasting half of the weight tile
-    (odd tile counts included: the partner CTA then works on an all-padding tile).  Same MMAs in the same order as the one-CTA kernel
-    (KB_GEMM_MC=0): bit-identical results."""
+    """KB_GEMM_MC=1: pairs of vertically adjacent tiles on 2-CTA clusters, each CTA multicasting half of the weight tile (odd tile counts
+    included: the partner CTA then works on an all-padding tile).  Same MMAs in the same order as the one-CTA kernel: bit-identical."""
     rng = np.random.default_rng(M + N + K)
     a = rng.standard_normal((M, K)).astype(np.float32)
     b = (rng.standard_normal((N, K)) / np.sqrt(K)).astype(np.float32)
     bias = rng.standard_normal(N).astype(np.float32)
-    got = gemm(a, b, bias, True)
-    monkeypatch.setenv('KB_GEMM_MC', '0')
     ref = gemm(a, b, bias, True)
+    monkeypatch.setenv('KB_GEMM_MC', '1')
+    got = gemm(a, b, bias, True)
     assert np.array_equal(got, ref)

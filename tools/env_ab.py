@@ -1,4 +1,4 @@
-"""Stand-alone GPU diagnostic: cfg2 per-stage times with the weight-multicast GEMM clusters on (default) and off (KB_GEMM_MC=0)."""
+"""Stand-alone GPU diagnostic: cfg2 per-stage times under an environment switch given on the command line (values 1 and 0 alternating)."""
 import os
 import sys
 
@@ -16,8 +16,10 @@ rec = kb.TorchSeqRecognizer(m, device='cuda:0')
 x = torch.rand(64, 1, 48, 800).cuda()
 lens = torch.full((64,), 800)
 outs = {}
-for mode in ('1', '0', '1', '0'):
-    os.environ['KB_GEMM_MC'] = mode
+VAR = sys.argv[1]
+VALS = sys.argv[2:4] if len(sys.argv) >= 4 else ['1', '0']
+for mode in (VALS[0], VALS[1], VALS[0], VALS[1]):
+    os.environ[VAR] = mode
     outs[mode], _ = m.nn(x, lens)
     for _ in range(3):
         rec._recognize_raw(x, lens, want_probs=False)
@@ -28,5 +30,5 @@ for mode in ('1', '0', '1', '0'):
         for k, v in m.last_timing():
             acc[k] = acc.get(k, 0.0) + v / 20
     m.set_timing(False)
-    print(f'KB_GEMM_MC={mode}:', {k: round(v, 4) for k, v in acc.items()}, 'sum', round(sum(acc.values()), 4), file=sys.stderr)
-print('logits identical with / without multicast:', bool(torch.equal(outs['0'], outs['1'])), file=sys.stderr)
+    print(f'{VAR}={mode}:', {k: round(v, 4) for k, v in acc.items()}, 'sum', round(sum(acc.values()), 4), file=sys.stderr)
+print('logits identical for both values:', bool(torch.equal(outs[VALS[0]], outs[VALS[1]])), 'max rel diff', float((outs[VALS[0]] - outs[VALS[1]]).abs().max() / outs[VALS[1]].abs().max()), file=sys.stderr)
