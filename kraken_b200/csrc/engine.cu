@@ -141,6 +141,7 @@ struct kb_model {
     bool timing = false;
     int sm_count = 148;
     int max_clusters8 = -1;          // co-resident 8-CTA clusters of the recurrence kernel (queried once)
+    int max_clusters_tc = -1;        // ... of the tcgen05 recurrence
     int fuse_mask = 7;               // bit 0: stencil+pool group, bit 1: tcgen05 conv group, bit 2: stride-2 conv via space-to-depth
     bool keep_fp32 = false;          // KB_KEEP_FP32=1: fused producers also write the fp32 tensor their plane-only consumer ignores (taps)
     bool force_ffma = false;         // second attempt of a call whose first attempt raised the flag: fp32 CUDA-core kernels only
@@ -731,7 +732,7 @@ struct Exec {
                     ltc::LstmTcParams tp;
                     tp.gx = lp.gx; tp.wpk = (const uint16_t *)w.wpk; tp.out = (lplanes && !m->keep_fp32) ? nullptr : lp.out; tp.lens = lp.lens; tp.nseq = lp.nseq; tp.T = lp.T;
                     tp.out_hi = full.hi; tp.out_lo = full.lo;
-                    tp.dbg = 0; tp.handoff = 0; tp.dbgbuf = nullptr; tp.hid = hid; tp.dirs = dirs; tp.U = hid; tp.q2 = lp.q2; tp.s_outer = lp.s_outer; tp.s_inner = lp.s_inner; tp.step = lp.step;
+                    tp.dbg = 0; tp.lpc = 0; tp.dbgbuf = nullptr; tp.hid = hid; tp.dirs = dirs; tp.U = hid; tp.q2 = lp.q2; tp.s_outer = lp.s_outer; tp.s_inner = lp.s_inner; tp.step = lp.step;
                     int snl = lp.nseq * dirs >= 64 * 2 * sm ? 64 : lp.nseq * dirs >= 16 * 4 * sm ? 32 : 16;      // fill the SMs first, then grow the CTAs
                     if (getenv("KB_LSTM_SNL")) snl = atoi(getenv("KB_LSTM_SNL"));
                     if (snl != 64 && snl != 32) snl = 16;
@@ -746,21 +747,40 @@ struct Exec {
                     ltc::LstmTcParams tp;
                     tp.gx = lp.gx; tp.wpk = (const uint16_t *)w.wpk; tp.out = (lplanes && !m->keep_fp32) ? nullptr : lp.out; tp.lens = lp.lens; tp.nseq = lp.nseq; tp.T = lp.T;
                     tp.out_hi = full.hi; tp.out_lo = full.lo;
-                    tp.dbg = getenv("KB_LSTM_DBG") ? atoi(getenv("KB_LSTM_DBG")) : 0; tp.handoff = getenv("KB_LSTM_HANDOFF") ? atoi(getenv("KB_LSTM_HANDOFF")) : 0; tp.hid = hid; tp.dirs = dirs; tp.U = lp.U; tp.q2 = lp.q2; tp.s_outer = lp.s_outer; tp.s_inner = lp.s_inner; tp.step = lp.step;
+                    tp.dbg = getenv("KB_LSTM_DBG") ? atoi(getenv("KB_LSTM_DBG")) : 0; tp.hid = hid; tp.dirs = dirs; tp.U = lp.U; tp.q2 = lp.q2; tp.s_outer = lp.s_outer; tp.s_inner = lp.s_inner; tp.step = lp.step;
                     // lines per cluster: 16 (two groups of 8); KB_LSTM_GL=16 selects 32 (two groups of 16: half the SMs per batch, but
                     // the longer epilogue stretches the per-step latency chain by 1.7x)
                     int gl = 8;                                  // measured on cfg2: 32 lines per cluster = 0.54 ms vs 0.31 ms, and no e2e gain
                     if (getenv("KB_LSTM_GL")) gl = atoi(getenv("KB_LSTM_GL")) == 16 ? 16 : 8;
                     const int nl = 2 * gl;
+                    // Lines per cluster.  Measured on cfg2 (tools/rec_ab.py): 16, 12 and 10 lines per cluster all take 0.30 ms - the time step
+                    // is a latency chain (~500 MMAs + ~800 epilogue + ~1100-1300 remote delivery), not a function of the bytes sent - so a
+                    // synchronous call gains nothing from spreading over more clusters and every call keeps full clusters (fewest SMs per
+                    // batch).  KB_LSTM_LPC overrides (ragged last cluster / tests).
+                    int lpc = nl;
+                    if (gl == 8) {
+                        if (m->max_clusters_tc < 0) {
+                            cudaLaunchConfig_t q = {};
+                            q.gridDim = dim3(ltc::LCS * 32, 1, 1); q.blockDim = dim3(ltc::LTHREADS, 1, 1); q.dynamicSmemBytes = ltc::ClusterCfg<8>::SMEM_BYTES;
+                            cudaLaunchAttribute qa[1]; qa[0].id = cudaLaunchAttributeClusterDimension;
+                            qa[0].val.clusterDim.x = ltc::LCS; qa[0].val.clusterDim.y = 1; qa[0].val.clusterDim.z = 1;
+                            q.attrs = qa; q.numAttrs = 1;
+                            int ncl = 0;
+                            if (cudaOccupancyMaxActiveClusters(&ncl, ltc::k_lstm_rec_tc<8>, &q) != cudaSuccess) { cudaGetLastError(); ncl = 8; }
+                            m->max_clusters_tc = std::max(ncl, 1);
+                        }
+                        if (getenv("KB_LSTM_LPC")) lpc = std::min(nl, std::max(1, atoi(getenv("KB_LSTM_LPC"))));
+                    }
+                    tp.lpc = lpc;
                     cudaLaunchConfig_t tcfg = {};
-                    tcfg.gridDim = dim3((unsigned)(ltc::LCS * ((lp.nseq + nl - 1) / nl)), (unsigned)dirs, 1);
+                    tcfg.gridDim = dim3((unsigned)(ltc::LCS * ((lp.nseq + lpc - 1) / lpc)), (unsigned)dirs, 1);
                     tcfg.blockDim = dim3(ltc::LTHREADS, 1, 1);
                     tcfg.dynamicSmemBytes = gl == 16 ? ltc::ClusterCfg<16>::SMEM_BYTES : ltc::ClusterCfg<8>::SMEM_BYTES; tcfg.stream = st;
                     cudaLaunchAttribute tat[1];
                     tat[0].id = cudaLaunchAttributeClusterDimension;
                     tat[0].val.clusterDim.x = ltc::LCS; tat[0].val.clusterDim.y = 1; tat[0].val.clusterDim.z = 1;
                     tcfg.attrs = tat; tcfg.numAttrs = 1;
-                    if (getenv("KB_DEBUG")) fprintf(stderr, "[kb] %s: tcgen05 recurrence, %u clusters of 8 CTAs x %d lines, T=%d\n", n.name.c_str(), tcfg.gridDim.x / 8 * dirs, nl, lp.T);
+                    if (getenv("KB_DEBUG")) fprintf(stderr, "[kb] %s: tcgen05 recurrence, %u clusters of 8 CTAs x %d lines (max co-resident %d), T=%d\n", n.name.c_str(), tcfg.gridDim.x / 8 * dirs, lpc, m->max_clusters_tc, lp.T);
                     tp.dbgbuf = nullptr;
                     if (tp.dbg & 1) { CK(cudaMalloc((void **)&tp.dbgbuf, 96 * sizeof(long long))); CK(cudaMemset(tp.dbgbuf, 0, 96 * sizeof(long long))); }
                     if (gl == 16) CK(cudaLaunchKernelEx(&tcfg, ltc::k_lstm_rec_tc<16>, tp));

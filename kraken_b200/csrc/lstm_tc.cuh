@@ -52,9 +52,7 @@ template <int GL> struct ClusterCfg {                    // GL = lines per group
     static constexpr int B_BUF_B = 32 * CH_B;            // bytes per (group, buffer): K = 256 = 32 chunks
     static constexpr int SRC_B = 4 * CH_B;               // bytes one source CTA contributes to a buffer (its 4 k-chunks)
     static constexpr int HALF_B = 4 * SRC_B;             // bytes the four source CTAs of a K half deliver
-    static constexpr int SX_BYTES = NG * 2 * SRC_B;     // bulk hand-off: this CTA's outgoing piece per group, double buffered, laid out as in the operand
-    static constexpr int WB_B = 2 * LPW * 16;            // bytes an epilogue warp contributes to a k-chunk: [h1 of its lines | h2s of its lines] x 16 B
-    static constexpr int SMEM_BYTES = NG * 2 * B_BUF_B + SX_BYTES + 512 + 1024;
+    static constexpr int SMEM_BYTES = NG * 2 * B_BUF_B + 512 + 1024;
     static constexpr int N1 = 2 * GL;                    // N of both products (W2s x the same operand rows; only its h1 columns are read)
     static constexpr int GSTRIDE = 4 * N1;               // TMEM columns per group: D1a @0, D1b @N1, D2a @2 N1, D2b @3 N1
     static constexpr int TM_A0 = NG * GSTRIDE;           // A: W1 @TM_A0 (128 columns), W2s @TM_A0 + 128
@@ -65,7 +63,7 @@ struct LstmTcParams {
     __half *out_hi, *out_lo;         // optional fp16 operand planes of the output for a tensor-core consumer (out may then be NULL)
     int nseq, T, hid, dirs, U;
     int q2; long long s_outer, s_inner, step;
-    int handoff;                     // 0: st.async from registers (16-byte packets), 1: staged in shared memory + one 1 KB bulk copy per destination
+    int lpc;                         // lines per cluster (<= NL): group 0 takes ceil(lpc / 2) of them, group 1 the rest; fewer lines = fewer bytes through DSMEM per step
     int dbg; long long *dbgbuf;      // KB_LSTM_DBG: bit 0 = clock64 stamps of steps 100..103 of cluster 0 into dbgbuf[step][group][12]
 };
 
@@ -102,12 +100,6 @@ __device__ __forceinline__ void st_async_v4(uint32_t raddr, uint4 v, uint32_t rm
     asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];"
                  ::"r"(raddr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "r"(rmbar) : "memory");
 }
-// shared::cta -> (remote) shared::cluster bulk copy, byte-counted by the destination's mbarrier: one packet stream and ONE transaction
-// count update per block instead of one per 16 bytes
-__device__ __forceinline__ void bulk_s2s(uint32_t dst_cluster, uint32_t src_cta, uint32_t bytes, uint32_t mbar_cluster) {
-    asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(dst_cluster), "r"(src_cta), "r"(bytes), "r"(mbar_cluster) : "memory");
-}
 // K-major operand WITHOUT swizzle: core matrices (8 rows x 16 bytes, 128 contiguous bytes) `lbo` bytes apart along K and `sbo`
 // bytes apart along M/N.  The h operand uses it because one 16-byte store = 8 unit slots of one line = one row of a core matrix.
 __device__ __forceinline__ uint64_t umma_desc_nosw(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
@@ -117,6 +109,16 @@ __device__ __forceinline__ uint64_t umma_desc_nosw(uint32_t saddr, uint32_t lbo,
     d |= (uint64_t)(sbo >> 4) << 32;
     d |= (uint64_t)1 << 46;                           // descriptor version (sm_100); layout type 0 = no swizzle
     return d;
+}
+// non-suspending poll (mbarrier.test_wait): try_wait may park the warp for an implementation-defined time
+__device__ __forceinline__ void mbar_wait_poll(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "PW_%=:\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra PD_%=;\n\t"
+        "bra PW_%=;\n\t"
+        "PD_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
 // gate non-linearities on the SFU: ex2.approx + rcp, absolute error ~1e-7 (the CUDA-core kernel keeps expf/tanhf)
 __device__ __forceinline__ float rcp_fast(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }   // MUFU.RCP, no IEEE fix-up path
@@ -174,8 +176,7 @@ __global__ void __launch_bounds__(LTHREADS, 1) k_lstm_rec_tc(LstmTcParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = smem_align1024(smem_raw);
     uint8_t *sB = smem;                                   // [group][buffer][k-chunk][row = (warp half, plane, line)][8 unit slots] fp16, no swizzle
-    uint8_t *sx = sB + NG * 2 * B_BUF_B;                  // [group][2][k-chunk of this CTA][row][8 unit slots]: outgoing piece (bulk hand-off)
-    uint64_t *bars = reinterpret_cast<uint64_t *>(sx + Cfg::SX_BYTES);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sB + NG * 2 * B_BUF_B);
     uint64_t *b_half = bars /* [group][buffer][K half] */, *mma_done = bars + 8 /* [group] */, *acc_free = bars + 10 /* [group] */;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 12);
 
@@ -190,7 +191,8 @@ __global__ void __launch_bounds__(LTHREADS, 1) k_lstm_rec_tc(LstmTcParams p) {
         for (int g = 0; g < NG; ++g) { mbar_init(&mma_done[g], 1); mbar_init(&acc_free[g], 2 * 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         for (int g = 0; g < NG; ++g)
-            for (int hf = 0; hf < 2; ++hf) mbar_expect_tx(&b_half[(g * 2 + 1) * 2 + hf], Cfg::HALF_B);   // buffer 1 of each group receives h_0 at the end of step 0
+            for (int hf = 0; hf < 2; ++hf)       // buffer 1 of each group receives h_0 at the end of step 0
+                mbar_expect_tx(&b_half[(g * 2 + 1) * 2 + hf], (uint32_t)(4 * 4 * 32 * (g ? p.lpc - ((p.lpc + 1) >> 1) : ((p.lpc + 1) >> 1))));
     }
     for (int i = threadIdx.x; i < NG * 2 * B_BUF_B / 16; i += LTHREADS) reinterpret_cast<uint4 *>(sB)[i] = make_uint4(0, 0, 0, 0);   // h_{-1} = 0
     if (warp == 0) {
@@ -225,9 +227,11 @@ __global__ void __launch_bounds__(LTHREADS, 1) k_lstm_rec_tc(LstmTcParams p) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 
+    // lines of this cluster: [chunk * lpc, chunk * lpc + lpc), group 0 the first ceil(lpc / 2), group 1 the rest (<= GL each)
+    const int lpc = p.lpc, nl0 = (lpc + 1) >> 1;
     int maxlen = 0;                                       // uniform across the cluster (both groups run the same number of steps)
-    for (int lb = 0; lb < NL; ++lb) {
-        const int q = chunk * NL + lb;
+    for (int lb = 0; lb < lpc; ++lb) {
+        const int q = chunk * lpc + lb;
         if (q < p.nseq) maxlen = max(maxlen, p.lens ? min(max(p.lens[q], 0), p.T) : p.T);
     }
     const bool dbg_cta = (p.dbg & 1) && blockIdx.x == 0 && blockIdx.y == 0;
@@ -240,6 +244,7 @@ __global__ void __launch_bounds__(LTHREADS, 1) k_lstm_rec_tc(LstmTcParams p) {
         // mbarrier polling competed with the epilogue warps' shuffles for the MIO pipe.
         const int g = warp;
         const uint32_t id1 = idesc_f16(0, 0, 128, N1);
+        const uint32_t half_bytes = (uint32_t)(4 * 4 * 32 * (g ? lpc - nl0 : nl0));     // 4 source CTAs x 4 k-chunks x (h1 + h2s row) per real line slot
         for (int s = 0; s < maxlen; ++s) {
             const int cur = s & 1;
             const long long d_w0 = dbg_cta ? clock64() : 0;
@@ -254,9 +259,12 @@ __global__ void __launch_bounds__(LTHREADS, 1) k_lstm_rec_tc(LstmTcParams p) {
 #pragma unroll 1
             for (int half = 0; half < 2; ++half) {
                 uint64_t *bh = &b_half[(g * 2 + cur) * 2 + half];
-                if (s > 0) mbar_wait(bh, (uint32_t)(((s - 1) >> 1) & 1));     // default acquire.cta: an acquire.cluster wait costs a CCTL.IVALL per step
+                if (s > 0) {                                                  // default acquire.cta: an acquire.cluster wait costs a CCTL.IVALL per step
+                    if (p.dbg & 2) mbar_wait_poll(bh, (uint32_t)(((s - 1) >> 1) & 1));
+                    else mbar_wait(bh, (uint32_t)(((s - 1) >> 1) & 1));
+                }
                 if (half == 1) d_w1 = dbg_cta ? clock64() : 0;
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // st.async writes (generic proxy) -> UMMA reads (async proxy)
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // st.async writes (generic proxy) -> UMMA reads (async proxy); measured: ~60 cycles per step
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 if (elect_one()) {
                     const uint32_t b0 = smem_u32(sB + (g * 2 + cur) * B_BUF_B) + (uint32_t)(half * 16 * CH_B);
@@ -268,7 +276,7 @@ __global__ void __launch_bounds__(LTHREADS, 1) k_lstm_rec_tc(LstmTcParams p) {
                         umma_f16_ts(dacc, abase + (uint32_t)(jj * 8), bd, id1, jj ? 1u : 0u);                               // W1  x [h1 | h2s]
                         umma_f16_ts(dacc + (uint32_t)(2 * N1), abase + 128u + (uint32_t)(jj * 8), bd, id1, jj ? 1u : 0u);   // W2s x [h1 | ..]
                     }
-                    if (s + 2 < maxlen) mbar_expect_tx(bh, Cfg::HALF_B);      // refilled during step s+1 (nobody can send that before receiving our h_s)
+                    if (s + 2 < maxlen) mbar_expect_tx(bh, half_bytes);       // refilled during step s+1 (nobody can send that before receiving our h_s)
                 }
                 __syncwarp();
             }
@@ -291,14 +299,18 @@ __global__ void __launch_bounds__(LTHREADS, 1) k_lstm_rec_tc(LstmTcParams p) {
         const int slot = 8 * q + jq, u = (int)rank * p.U + slot;
         const bool uvalid = slot < p.U && u < hid;
         // after the transposes this thread updates unit `u` of lines (first line of the warp) + 4 t + gate
-        const int line0 = chunk * NL + g * GL + LPW * sw2;
+        const int nlg = g ? lpc - nl0 : nl0;              // real line slots of this group
+        const int line0 = chunk * lpc + (g ? nl0 : 0) + LPW * sw2;
         int clen[NT]; long long ooff[NT]; bool cval[NT]; float cst[NT];
         const long long ostride = (long long)(dir ? -1 : 1) * p.step * OC;
 #pragma unroll
+        bool slot_live[NT];
+#pragma unroll
         for (int t = 0; t < NT; ++t) {
             const int ql = line0 + 4 * t + gate;
-            cval[t] = ql < p.nseq && uvalid;
-            clen[t] = ql < p.nseq ? min(max(p.lens ? p.lens[ql] : p.T, 0), p.T) : 0;
+            slot_live[t] = LPW * sw2 + 4 * t + gate < nlg;
+            cval[t] = slot_live[t] && ql < p.nseq && uvalid;
+            clen[t] = (slot_live[t] && ql < p.nseq) ? min(max(p.lens ? p.lens[ql] : p.T, 0), p.T) : 0;
             const int qq = ql < p.nseq ? ql : 0;
             const long long cbase = (long long)(qq / p.q2) * p.s_outer + (long long)(qq % p.q2) * p.s_inner;
             cst[t] = 0.f;
@@ -315,7 +327,7 @@ __global__ void __launch_bounds__(LTHREADS, 1) k_lstm_rec_tc(LstmTcParams p) {
 #pragma unroll
         for (int i = 0; i < LPW; ++i) {
             const int ql = line0 + i;
-            const bool v = ql < p.nseq && uvalid;
+            const bool v = LPW * sw2 + i < nlg && ql < p.nseq && uvalid;
             glen[i] = v ? min(max(p.lens ? p.lens[ql] : p.T, 0), p.T) : 0;
             const int qq = ql < p.nseq ? ql : 0;
             const long long gb = (long long)(qq / p.q2) * p.s_outer + (long long)(qq % p.q2) * p.s_inner;
@@ -334,7 +346,6 @@ __global__ void __launch_bounds__(LTHREADS, 1) k_lstm_rec_tc(LstmTcParams p) {
         // gate non-linearity without divergence: sigmoid(x) for i, f, o; tanh(x) = 2*sigmoid(2x) - 1 for the candidate gate
         const float act_k = gate == 2 ? 2.f : 1.f;
         const bool dbg_w = dbg_cta && q == 0 && sw2 == 0 && lane == 0;
-        const bool bulk = p.handoff == 1;
         // whole 8-slot rows of this quarter are real units and 16-byte aligned in the output planes (hid 256: always)
         const bool vec_planes = p.out_hi && 8 * q + 7 < p.U && (int)rank * p.U + 8 * q + 7 < hid && (OC & 7) == 0 &&
                                 ((dir * hid + (int)rank * p.U + 8 * q) & 7) == 0 &&
@@ -346,7 +357,8 @@ __global__ void __launch_bounds__(LTHREADS, 1) k_lstm_rec_tc(LstmTcParams p) {
 #pragma unroll
             for (int i = 0; i < LPW; ++i) gxv[i] = gxn[i];
             const long long e_top = dbg_w ? clock64() : 0;
-            mbar_wait(&mma_done[g], (uint32_t)(s & 1));
+            if (p.dbg & 4) mbar_wait_poll(&mma_done[g], (uint32_t)(s & 1));
+            else mbar_wait(&mma_done[g], (uint32_t)(s & 1));
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const long long e_done = dbg_w ? clock64() : 0;
             // group columns: D1a = W1 x rows (K half 0) @0, D1b (K half 1) @N1, D2a = W2s x rows @2 N1, D2b @3 N1; within the warp's
@@ -390,33 +402,17 @@ __global__ void __launch_bounds__(LTHREADS, 1) k_lstm_rec_tc(LstmTcParams p) {
                 const __half h1 = __float2half_rn(h);
                 const __half h2 = __float2half_rn((h - __half2float(h1)) * X2_SCALE);
                 hv[t] = h; hh1[t] = h1; hh2[t] = h2; wr[t] = cval[t] && live;
-                if (bulk) {                                 // both fp16 planes of h straight into the staged piece: [k-chunk q][row][unit slot]
-                    __half *cx = reinterpret_cast<__half *>(sx + (size_t)((g * 2 + (s & 1)) * Cfg::SRC_B + q * CH_B + sw2 * Cfg::WB_B));
-                    cx[(4 * t + gate) * 8 + jq] = h1;
-                    cx[(LPW + 4 * t + gate) * 8 + jq] = h2;
-                }
-                if (!bulk) gather_rows8(h1, h2, lane, row1[t], row2[t]);
+                gather_rows8(h1, h2, lane, row1[t], row2[t]);
             }
             const long long e_cell = dbg_w ? clock64() : 0;
-            if (bulk) {
-                // generic writes -> the bulk copy engine (async proxy); then the group's 8 warps have staged the piece and warp wi sends
-                // all of it to CTA wi: 8 packets streams of 1 KB and 8 transaction-count updates per destination buffer instead of 512
-                // 16-byte packets (measured: the st.async hand-off is packet-rate bound, ~1300 cycles from send to the last arrival)
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                named_bar(1 + g, 256);
-                if (s + 1 < maxlen && lane == 0) {
-                    const uint32_t wi = (uint32_t)((sw2 << 2) | q);
-                    bulk_s2s(mapa32(smem_u32(sB), wi) + (uint32_t)((g * 2 + nxt) * B_BUF_B) + (uint32_t)rank * (uint32_t)Cfg::SRC_B,
-                             smem_u32(sx + (size_t)(g * 2 + (s & 1)) * Cfg::SRC_B), (uint32_t)Cfg::SRC_B,
-                             mapa32(smem_u32(b_half), wi) + (uint32_t)(((g * 2 + nxt) * 2) + (int)(rank >> 2)) * 8u);
-                }
-            } else if (s + 1 < maxlen) {
+            if (s + 1 < maxlen) {
                 const uint32_t boff = (uint32_t)((g * 2 + nxt) * B_BUF_B), bar = dstBar + (uint32_t)((g * 2 + nxt) * 2) * 8u;
 #pragma unroll
-                for (int t = 0; t < NT; ++t) {
-                    st_async_v4(dstB + boff + (uint32_t)(4 * t * 16), row1[t], bar);
-                    st_async_v4(dstB + boff + (uint32_t)((LPW + 4 * t) * 16), row2[t], bar);
-                }
+                for (int t = 0; t < NT; ++t)
+                    if (slot_live[t]) {                     // only the group's real line slots travel (and are counted by the receivers)
+                        st_async_v4(dstB + boff + (uint32_t)(4 * t * 16), row1[t], bar);
+                        st_async_v4(dstB + boff + (uint32_t)((LPW + 4 * t) * 16), row2[t], bar);
+                    }
             }
             const long long e_sent = dbg_w ? clock64() : 0;
             // h to HBM and the gx prefetch come AFTER the hand-off: nothing on the critical path waits for them
@@ -426,14 +422,6 @@ __global__ void __launch_bounds__(LTHREADS, 1) k_lstm_rec_tc(LstmTcParams p) {
                     if (p.out) p.out[ooff[t]] = hv[t];
                     if (p.out_hi) {
                         if (vec_planes) {
-                            if (bulk) {                     // the staged piece holds the complete rows (this warp wrote them before the barrier)
-                                const uint8_t *cx = sx + (size_t)((g * 2 + (s & 1)) * Cfg::SRC_B + q * CH_B + sw2 * Cfg::WB_B);
-                                if (jq == 0) row1[t] = *reinterpret_cast<const uint4 *>(cx + (4 * t + gate) * 16);
-                                else if (jq == 1) row2[t] = *reinterpret_cast<const uint4 *>(cx + (LPW + 4 * t + gate) * 16);
-                            }
-                            // every lane of the line holds the complete 16-byte rows: one lane stores the h1 row, another the h2s row
-                            // (8 sectors per warp and step instead of 64 scattered 2-byte stores that clogged the LSU queue the
-                            // st.async hand-off and the shuffles of the other group share)
                             if (jq == 0) *reinterpret_cast<uint4 *>(p.out_hi + ooff[t]) = row1[t];
                             else if (jq == 1) *reinterpret_cast<uint4 *>(p.out_lo + ooff[t] - 1) = row2[t];
                         } else { p.out_hi[ooff[t]] = hh1[t]; p.out_lo[ooff[t]] = hh2[t]; }

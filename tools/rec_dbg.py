@@ -1,6 +1,6 @@
-"""Stand-alone GPU diagnostic: the clustered tcgen05 recurrence of cfg2 at different numbers of lines per cluster (KB_LSTM_LPC): device
-time of the stage, logits error against the CUDA-core recurrence, and the KB_LSTM_DBG timeline of the default choice.
-Usage: python tools/rec_ab.py 2> log"""
+"""Stand-alone GPU diagnostic: the clustered recurrence of cfg2 under the KB_LSTM_DBG bits (1: clock64 timeline of steps 100..103, 2:
+issuer polls its h barriers with test_wait instead of try_wait, 4: epilogue polls mma_done); device time of the stage and the logits
+against the first run per setting.  Usage: python tools/rec_dbg.py 2> log"""
 import os
 import sys
 
@@ -17,15 +17,13 @@ m.init_weights()
 rec = kb.TorchSeqRecognizer(m, device='cuda:0')
 x = torch.rand(64, 1, 48, 800).cuda()
 lens = torch.full((64,), 800)
-os.environ['KB_LSTM_TC'] = '0'
-ref, _ = m.nn(x, lens)
-os.environ.pop('KB_LSTM_TC')
-for mode in ('16', '12', '10', '8', '16', '10', ''):
-    if mode:
-        os.environ['KB_LSTM_LPC'] = mode
-    else:
-        os.environ.pop('KB_LSTM_LPC', None)
+import numpy as np
+ref = None
+for mode in ('0', '2', '4', '0', '2', '4'):
+    os.environ['KB_LSTM_DBG'] = mode
     out, _ = m.nn(x, lens)
+    if ref is None:
+        ref = out
     err = float((out - ref).abs().max() / ref.abs().max())
     for _ in range(3):
         rec._recognize_raw(x, lens, want_probs=False)
@@ -36,7 +34,6 @@ for mode in ('16', '12', '10', '8', '16', '10', ''):
         for k, v in m.last_timing():
             acc[k] = acc.get(k, 0.0) + v / 20
     m.set_timing(False)
-    print(f'lines per cluster {mode or "default"}: rec {acc["L_5.rec"]:.4f} ms, sum {sum(acc.values()):.4f} ms, logits vs CUDA-core recurrence {err:.2e}', file=sys.stderr)
+    print(f'KB_LSTM_DBG={mode}: rec {acc["L_5.rec"]:.4f} ms, logits vs the first run {err:.2e}', file=sys.stderr)
 os.environ['KB_LSTM_DBG'] = '1'
-os.environ['KB_DEBUG'] = '1'
 rec._recognize_raw(x, lens, want_probs=False)
