@@ -17,6 +17,7 @@
 #include "conv_tc.cuh"
 #include "lstm_tc.cuh"
 #include "line_prep.cuh"
+#include "conv1_tc.cuh"
 #include "vgsl_plan.hpp"
 
 namespace kb {
@@ -53,6 +54,7 @@ struct LeafWeights {
     __half *c_hi = nullptr, *c_lo = nullptr;  // [tap][chunk][Cout][32] fp16 operand planes for the tcgen05 convolution
     int s2d = 0, s_th = 0, s_tw = 0, s_py = 0, s_px = 0, s_cs = 0;   // stride-2 conv as space-to-depth stride-1 conv: block taps, block padding, channels
     void *wpk = nullptr;                      // W_hh as fp16 operand planes of the tcgen05 recurrences
+    __half *c1_pk = nullptr;                  // first-layer 3x3 conv on tcgen05 (conv1_tc.cuh): [b1 rows | b2s rows] x K16 operand
     float *peep = nullptr;                    // ocropy cell: peephole vectors [dir][ip, fp, op][h]
     std::vector<std::vector<float>> legacy_host;   // legacy cells rewritten as (W_ih, W_hh, b_ih, b_hh) per direction
     float *whh_t = nullptr; int whh_ncp = 0;  // hidden > 256: W_hh^T [dir][k = h][gate column (unit, gate) padded to 64] for the per-step GEMM
@@ -251,6 +253,8 @@ static void set_kernel_attributes() {
     CK(cudaFuncSetAttribute(tc::k_gemm_tc<256, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::GemmCfg<256>::SMEM_BYTES));
     CK(cudaFuncSetAttribute((tc::k_gemm_tc<256, 0, 2>), cudaFuncAttributeMaxDynamicSharedMemorySize, tc::GemmCfg<256>::SMEM_BYTES));
     CK(cudaFuncSetAttribute(ctc::k_conv_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CK(cudaFuncSetAttribute(c1tc::k_conv1_tc<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c1tc::conv1_tc_smem(32)));
+    CK(cudaFuncSetAttribute(c1tc::k_conv1_tc<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c1tc::conv1_tc_smem(16)));
     CK(cudaFuncSetAttribute(ltc::k_lstm_rec_tc<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, ltc::ClusterCfg<8>::SMEM_BYTES));
     CK(cudaFuncSetAttribute(ltc::k_lstm_rec_tc<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, ltc::ClusterCfg<16>::SMEM_BYTES));
     CK(cudaFuncSetAttribute(ltc::k_lstm_rec_tc_small<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, ltc::SmallCfg<64>::SMEM_BYTES));
@@ -264,7 +268,7 @@ static void finalize_weights(kb_model *m) {
     for (size_t li = 0; li < m->plan->leaf_nodes.size(); ++li) {
         const Node &n = *m->plan->leaf_nodes[li];
         LeafWeights &w = m->lw[li];
-        w.wt = w.bias = w.aux = nullptr; w.b_hi = w.b_lo = w.c_hi = w.c_lo = nullptr; w.wpk = nullptr; w.whh_t = nullptr;
+        w.wt = w.bias = w.aux = nullptr; w.b_hi = w.b_lo = w.c_hi = w.c_lo = nullptr; w.wpk = nullptr; w.whh_t = nullptr; w.c1_pk = nullptr;
         auto need = [&](int slots) {
             for (int s = 0; s < slots; ++s)
                 if ((int)w.loaded.size() <= s || !w.loaded[s]) throw SpecError("weights of layer " + n.name + " not loaded (missing tensor for nn." + n.path + ")");
@@ -281,6 +285,10 @@ static void finalize_weights(kb_model *m) {
                             wt[(size_t)((ky * n.kw + kx) * n.cin + ci) * ncp + co] = src[(((size_t)co * n.cin + ci) * n.kh + ky) * n.kw + kx];
             w.wt = upload(m, wt); w.bias = upload(m, w.host[1]); w.ncp = ncp; w.K = K; w.ncols = n.cout;
             if (n.kh == 1 && n.kw == 1) upload_split(m, src, w);          // [Cout][Cin] is already K-major
+            if (n.cin == 1 && n.kh == 3 && n.kw == 3 && n.sy == 1 && n.sx == 1 && n.dy == 1 && n.dx == 1 && (n.cout == 16 || n.cout == 32)) {
+                std::vector<__half> pk;
+                if (c1tc::pack_conv1_weights(src, n.cout, pk)) w.c1_pk = upload_half(m, pk);
+            }
             if (n.cin % 32 == 0 && n.sy == 1 && n.sx == 1 && n.dy == 1 && n.dx == 1 && n.cout % 32 == 0 && n.kh + 1 <= ctc::MAX_ROWS &&
                 n.kh * n.kw > 1) {
                 // tcgen05 convolution operand: [tap][32-channel chunk][Cout][32] fp16 planes
@@ -908,7 +916,19 @@ struct Exec {
                 const int tw = 2 * ppb + c0.kw - 1, th = c0.kh + 1;
                 const size_t smem = ((size_t)((th * tw + 3) & ~3) + (size_t)c0.kh * c0.kw * c0.cout) * sizeof(float);
                 if (smem > 48 * 1024) throw Unsupported(c0.name + ": filter bank too large for the fused stencil kernel");
-                if (c0.kh == 3 && c0.kw == 3 && (w.ncp % 4) == 0 && !(getenv("KB_CONV1") && strcmp(getenv("KB_CONV1"), "generic") == 0)) {
+                const char *c1env = getenv("KB_CONV1");
+                if (w.c1_pk && m->use_tc && !m->force_ffma && !(c1env && (strcmp(c1env, "generic") == 0 || strcmp(c1env, "ffma") == 0))) {
+                    // tcgen05 version: the nine taps are one K16 step (conv1_tc.cuh).  Tile shape with the smaller padding waste.
+                    c1tc::Conv1TcParams tp;
+                    tp.x = cur.p; tp.wpk = w.c1_pk; tp.bias = w.bias; tp.y = cp.y; tp.y_hi = cp.y_hi; tp.y_lo = cp.y_lo; tp.flag = ws->d_flag;
+                    tp.N = cp.N; tp.H = cp.H; tp.W = cp.W; tp.Cout = cp.Cout; tp.Hp = cp.Hp; tp.Wp = cp.Wp; tp.act = cp.act;
+                    const long long w128 = (long long)((cp.Wp + 127) / 128) * 128 * cp.Hp, w64 = (long long)((cp.Wp + 63) / 64) * 64 * ((cp.Hp + 1) / 2) * 2;
+                    if (w64 < w128) { tp.tpw = 64; tp.tph = 2; } else { tp.tpw = 128; tp.tph = 1; }
+                    tp.tiles_w = (cp.Wp + tp.tpw - 1) / tp.tpw; tp.tiles_h = (cp.Hp + tp.tph - 1) / tp.tph;
+                    const long long ntiles = (long long)tp.N * tp.tiles_w * tp.tiles_h;
+                    if (cp.Cout == 32) LAUNCH(m, c1tc::k_conv1_tc<32>, (unsigned)std::min<long long>(ntiles, 2LL * m->sm_count), c1tc::C1_THREADS, c1tc::conv1_tc_smem(32), st, tp);
+                    else LAUNCH(m, c1tc::k_conv1_tc<16>, (unsigned)std::min<long long>(ntiles, 2LL * m->sm_count), c1tc::C1_THREADS, c1tc::conv1_tc_smem(16), st, tp);
+                } else if (c0.kh == 3 && c0.kw == 3 && (w.ncp % 4) == 0 && !(c1env && strcmp(c1env, "generic") == 0)) {
                     // register-resident 3x3 filter bank, strips of 8 pooled rows per block
                     constexpr int RP = 8;
                     dim3 grid3((unsigned)((dpool.w + ppb - 1) / ppb), (unsigned)((dpool.h + RP - 1) / RP), (unsigned)dpool.n);
