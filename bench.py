@@ -359,7 +359,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--cpu-steps', type=int, default=6)
-    ap.add_argument('--inflight', type=int, default=4, help='pipeline slots (batches in flight from the one host thread) of the e2e arm')
+    ap.add_argument('--inflight', type=int, default=6, help='pipeline slots (batches in flight from the one host thread) of the e2e arm')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-numa-bind', action='store_true')
     ap.add_argument('--no-extra', action='store_true', help='skip the cfg3 / cfg5 side measurements')
