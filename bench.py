@@ -6,11 +6,14 @@ Workload (config.workload "cfg2"): VGSL [1,48,0,1 Cr3,3,32 Mp2,2 Cr3,3,64 Mp2,2 
 weights (reference init distributions), one step = ONE batch of 64 synthetic 48x800 lines through
 `kb_recognize` (net -> softmax -> arg-max -> CTC collapse -> label tuples on the host).
 
-  value  lines/s with the line batch already resident in HBM (device pointers), decoded labels returned to the host.
-  e2e    the same call with pinned HOST buffers: H2D of the 64x48x800 fp32 batch and D2H of the label block are
-         inside the timed region.
-  roofline      the dominant kernel stage of the step, timed with CUDA events on the launching stream inside the
-                timed region (kb_set_timing), against MEASURED_PEAKS.json.
+  value  lines/s with the line batches already resident in HBM, K steps through the asynchronous pipeline (kb_recognize_async / kb_wait:
+         `--inflight` batches in flight on ONE handle from ONE host thread), decoded labels returned to the host.
+  serial the same K steps one synchronous kb_recognize at a time, per-stage CUDA events on (the source of `roofline`).
+  e2e    the pipeline with pinned HOST buffers: H2D of the 64x48x800 fp32 batch and D2H of the label block are inside the timed region
+         (e2e_u8: uint8 lines, a quarter of the bytes; scale / invert / pad on the device).
+  roofline      the dominant kernel stage of the serial step, timed with CUDA events on the launching stream inside the timed region
+                (kb_set_timing), against MEASURED_PEAKS.json; per-stage fractions beside it.
+  cfg5 / cfg3   side measurements (BASELINE configs[4] and [2]) in the same line.
   cpu_baseline  the oracle (torch-CPU restatement of the reference, `kind: "port"`; the reference is a Python package
                 whose dependencies are not installed on the GPU box) on all host cores, bounded sample.
   --impl reference   times that same CPU implementation as its own arm.
@@ -571,7 +574,7 @@ def main():
             with open(os.path.join(ROOT, 'profiles', tf_name)) as fh:
                 tj = json.load(fh)
             kmap = {'L_5.rec': ('k_lstm_rec_tc<8>', 0), 'L_5.xproj': ('k_gemm_tc<', 0), 'O_6': ('k_gemm_tc<', 1),
-                    'C_2+Mp_3+S_4': ('k_conv_tc', 0), 'C_0+Mp_1': ('k_conv1_pool33', 0)}
+                    'C_2+Mp_3+S_4': ('k_conv_tc', 0), 'C_0+Mp_1': ('k_conv1_', 0)}
             if dom in kmap:
                 hits = [v for k_, v in tj.items() if kmap[dom][0] in k_]
                 if hits:
