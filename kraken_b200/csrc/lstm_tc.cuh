@@ -1,31 +1,29 @@
 // lstm_tc.cuh - LSTM recurrence on tcgen05 tensor cores (sm_100a): k_lstm_rec_tc<GL> for hidden sizes 129..256 (clusters of 8 CTAs)
-// and k_lstm_rec_tc_small<NLS> for hidden sizes <= 32 (one CTA).  DESIGN.md 4.2 has the measured history (v1..v6).
+// and k_lstm_rec_tc_small<NLS> for hidden sizes <= 32 (one CTA).  DESIGN.md 4.2 has the measured history (v1..v9) and what bounds it.
 //
-// Same contract as k_lstm_rec (kernels.cuh): per-pixel gate pre-activations gx in, hidden states out (fp32 and / or the fp16
-// operand planes of a tensor-core consumer), packed-sequence semantics, one direction per blockIdx.y.  The CUDA-core kernel is at
-// the 3-register-FFMA issue limit, so W_hh . h_{t-1} moves to the tensor cores:
+// Same contract as k_lstm_rec (kernels.cuh): per-pixel gate pre-activations gx in, hidden states out (fp32 and / or the fp16 operand
+// planes of a tensor-core consumer), packed-sequence semantics, one direction per blockIdx.y.  The CUDA-core kernel is at the
+// 3-register-FFMA issue limit, so W_hh . h_{t-1} moves to the tensor cores:
 //
-//   cluster of 8 CTAs = 2 groups x GL sequences of one direction for all time steps; CTA r owns unit slots [32r, 32r+32) (padded,
-//   any hid <= 256), i.e. 128 gate rows ordered unit-major (row = 4*slot + gate: a unit's gates sit in 4 adjacent TMEM lanes).
+//   cluster of 8 CTAs = 2 groups x GL sequences of one direction for all time steps; CTA r owns unit slots [32r, 32r+32) (padded, any
+//   hid <= 256), i.e. 128 gate rows ordered unit-major (row = 4*slot + gate: a unit's gates sit in 4 adjacent TMEM lanes).
 //
 //   Operand precision: fp16 pairs with a power-of-two scale on the second term give 22 significand bits,
 //       x = x1 + x2s * 2^-11,   x1 = fp16(x),   x2s = fp16((x - x1) * 2^11)        (|error| <= 2^-23 |x|)
-//   (a first attempt with bf16 x bf16 / fp16 x bf16 mixed-format MMAs faulted with "illegal instruction": A and B of one
-//   kind::f16 MMA must share a format.)
-//   A = W1 and W2s planes of the CTA's 128 gate rows x K = 256, resident in TENSOR MEMORY for the whole kernel (row = TMEM lane,
-//       two fp16 per 32-bit column, 2 x 128 columns; written once with tcgen05.st).  With A in shared memory every MMA re-read
-//       its 4 KB slice: 128 KB per step, measured 1158 cycles to issue the 32 MMAs.
-//   B (per group, double buffered): h_{t-1} planes as swizzle-free core matrices [k-chunk of 8 unit slots][h1 lines | h2s lines]
-//       [8 slots] fp16: the block a (CTA, TMEM lane quarter) produces is contiguous, so the hand-off is ONE
-//       cp.async.bulk.shared::cluster per destination CTA, byte-counted by the destination's mbarrier (no cluster barrier, no
-//       "buffer free" handshake thanks to the double buffer; the outgoing chunk is staged double-buffered as well).
-//   D: per group and step 32 MMAs   W1 x [h1|h2s]  (M128 x N 2GL x K16)   and   W2s x [h1]  (N16)   into FOUR independent TMEM
-//       accumulator chains (k-atoms {0,1} / {2,3} x {W1, W2s}), issued round-robin (one chain of dependent tiny MMAs costs
-//       ~125 cycles per MMA).  Every fp32 accumulator element sees only 8 accumulations.
+//   (a first attempt with bf16 x bf16 / fp16 x bf16 mixed-format MMAs faulted with "illegal instruction": A and B of one kind::f16
+//   MMA must share a format.)
+//   A = W1 and W2s planes of the CTA's 128 gate rows x K = 256, resident in TENSOR MEMORY for the whole kernel (row = TMEM lane, two
+//       fp16 per 32-bit column, 2 x 128 columns; written once with tcgen05.st).  With A in shared memory every MMA re-read its 4 KB
+//       slice: 128 KB per step, measured 1158 cycles to issue the 32 MMAs.
+//   B (per group, double buffered): h_{t-1} planes as swizzle-free core matrices [k-chunk of 8 unit slots][row = (warp half, plane,
+//       line)][8 slots] fp16; every 16-byte row is written REMOTELY by the CTA that computed it (st.async from registers, byte-counted
+//       by the destination's mbarrier: no cluster barrier, no "buffer free" handshake thanks to the double buffer).
+//   D: per group and step 32 MMAs   W1 x [h1|h2s]   and   W2s x [h1|..]   (M128 x N 2GL x K16) into FOUR TMEM accumulator chains
+//       (product x K half), interleaved by the group's one issuer warp.  Every fp32 accumulator element sees only 8 accumulations.
 //       pre = D1[:, h1] + 2^-11 (D1[:, h2s] + D2[:, h1])                               (dropped: W2*h2 ~ 2^-24)
 //   epilogue: 16 warps = 2 groups x 4 TMEM lane quarters x 2: tcgen05.ld -> + gx (prefetched a step ahead) -> SFU sigmoid / tanh
-//       (ex2.approx + rcp.approx, ~1e-7) -> gates regrouped through shared memory -> fp32 cell update -> h_t to HBM and, as the two
-//       scaled fp16 planes, into the outgoing chunk.  The two groups run as independent ping-pong pipelines sharing the MMA warp.
+//       (ex2.approx + rcp.approx, ~1e-7) -> gates regrouped by quad shuffles -> fp32 cell update -> 8-lane gather of the line's
+//       16-byte operand rows -> st.async to the 8 CTAs; h_t to HBM (row stores).  The two groups alternate on the tensor pipe.
 #pragma once
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>

@@ -300,6 +300,8 @@ FUSE_SPECS = [
     ('[1,8,0,1 Cr3,3,6 Gn2 Cr3,3,32 Gn32 Mp2,2 S1(1x0)1,3 O1c11]', 8, (90,)),                         # scalar GN fallback (C % 4 != 0), G == C
     ('[1,16,0,1 Cr3,3,32 Gn8 Cr3,3,64,2,2 Gn8 S1(1x0)1,3 Lbx40 O1c11]', 16, (301, 78)),                # stride-2 conv on tcgen05: planes from GroupNorm (s2d store)
     ('[1,15,0,1 Cr3,3,32 Cr5,3,64,2,2 Cr3,3,32,2,2 S1(1x0)1,3 O1c9]', 15, (131, 64)),                  # ... planes from k_s2d_planes, odd H, 5x3 filter, chained
+    ('[1,11,0,1 Cr3,3,16 Mp2,2 S1(1x0)1,3 Lbx24 O1c9]', 11, (77, 259)),                                # first layer on tcgen05: Cout 16, odd H / W, fp32 output (no plane consumer)
+    ('[1,34,0,1 Cl3,3,32 Do0.1,2 Mp2,2 Cr3,3,32 Mp2,2 S1(1x0)1,3 O1c9]', 34, (1030, 129)),             # ... linear activation, dropout in between, 128 x 1 and 64 x 2 tiles, planes out
 ]
 
 
@@ -326,6 +328,9 @@ def test_fused_groups_and_conv_tc(spec, h, widths):
             with env(KB_FUSE=0, KB_GEMM='ffma'):
                 out2, _ = m.nn(x.cuda(), sl)
             assert rel_err(out2, ref) <= TIGHT
+            with env(KB_CONV1='ffma'):                   # the CUDA-core stencil behind the same fused group
+                out3, _ = m.nn(x.cuda(), sl)
+            assert rel_err(out3, ref) <= TIGHT
 
 
 @pytest.mark.parametrize('hid', [256, 200, 136])
@@ -559,6 +564,29 @@ def test_lstm_hidden_sizes_above_256(spec, n, h, w):
         assert ol.tolist() == rl.tolist()
         _, _, _, ref_dec = vo.rec_predict(om, x, lens)
         assert triples(kb.TorchSeqRecognizer(m, device='cuda:0').predict_labels(x, lens)) == triples(ref_dec)
+
+
+@pytest.mark.parametrize('lpc', [1, 3, 7, 10, 13])
+def test_tensor_core_recurrence_lines_per_cluster(lpc):
+    """KB_LSTM_LPC: fewer than 16 lines per cluster (uneven groups, empty second group, ragged last cluster) - same results."""
+    spec = '[1,16,0,1 Cr3,3,32 Mp2,2 S1(1x0)1,3 Lbx256 O1c30]'
+    om = vo.OracleModel(spec)
+    wts = om.init_like_reference(52)
+    g = torch.Generator().manual_seed(52)
+    n, w = 23, 120
+    lens = torch.randint(16, w + 1, (n,), generator=g)
+    lens[0] = w
+    x = torch.rand(n, 1, 16, w, generator=g)
+    for i, l in enumerate(lens.tolist()):
+        x[i, ..., l:] = 0
+    ref, rl = om.forward(x, lens)
+    m = kb.TorchVGSLModel(vgsl=spec)
+    m.load_state_dict(wts)
+    m.to('cuda:0')
+    with env(KB_LSTM_LPC=lpc):
+        out, ol = m.nn(x.cuda(), lens)
+    assert rel_err(out, ref) <= TIGHT, (lpc, rel_err(out, ref))
+    assert ol.tolist() == rl.tolist()
 
 
 def test_generic_recurrence_matches_resident_kernels():
