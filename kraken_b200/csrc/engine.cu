@@ -255,8 +255,9 @@ static void set_kernel_attributes() {
     CK(cudaFuncSetAttribute(ctc::k_conv_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     CK(cudaFuncSetAttribute(c1tc::k_conv1_tc<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c1tc::conv1_tc_smem(32)));
     CK(cudaFuncSetAttribute(c1tc::k_conv1_tc<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c1tc::conv1_tc_smem(16)));
-    CK(cudaFuncSetAttribute(ltc::k_lstm_rec_tc<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, ltc::ClusterCfg<8>::SMEM_BYTES));
-    CK(cudaFuncSetAttribute(ltc::k_lstm_rec_tc<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, ltc::ClusterCfg<16>::SMEM_BYTES));
+    CK(cudaFuncSetAttribute((ltc::k_lstm_rec_tc<8, 2>), cudaFuncAttributeMaxDynamicSharedMemorySize, (ltc::ClusterCfg<8, 2>::SMEM_BYTES)));
+    CK(cudaFuncSetAttribute((ltc::k_lstm_rec_tc<8, 3>), cudaFuncAttributeMaxDynamicSharedMemorySize, (ltc::ClusterCfg<8, 3>::SMEM_BYTES)));
+    CK(cudaFuncSetAttribute((ltc::k_lstm_rec_tc<16, 2>), cudaFuncAttributeMaxDynamicSharedMemorySize, (ltc::ClusterCfg<16, 2>::SMEM_BYTES)));
     CK(cudaFuncSetAttribute(ltc::k_lstm_rec_tc_small<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, ltc::SmallCfg<64>::SMEM_BYTES));
     CK(cudaFuncSetAttribute(ltc::k_lstm_rec_tc_small<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, ltc::SmallCfg<32>::SMEM_BYTES));
     CK(cudaFuncSetAttribute(ltc::k_lstm_rec_tc_small<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, ltc::SmallCfg<16>::SMEM_BYTES));
@@ -760,21 +761,29 @@ struct Exec {
                     // the longer epilogue stretches the per-step latency chain by 1.7x)
                     int gl = 8;                                  // measured on cfg2: 32 lines per cluster = 0.54 ms vs 0.31 ms, and no e2e gain
                     if (getenv("KB_LSTM_GL")) gl = atoi(getenv("KB_LSTM_GL")) == 16 ? 16 : 8;
-                    const int nl = 2 * gl;
+                    // Groups of 8 lines per cluster.  Two (16 lines on 8 SMs, the groups alternating on the tensor pipe) give the shortest
+                    // recurrence (cfg2: 0.311 ms) and are what a synchronous call gets.  Three free-running groups (24 lines on 8 SMs) take
+                    // 0.356 ms but a third fewer SMs, which is worth +6.5 % lines/s when several batches are in flight (bench.py, r02):
+                    // the asynchronous slots use that.  KB_LSTM_NG=2|3 overrides.  DESIGN.md 4.2.
+                    int ng = (gl == 8 && ws->index > 0 && (lp.nseq + 23) / 24 < (lp.nseq + 15) / 16) ? 3 : 2;      // only where it saves clusters
+                    if (gl == 8 && getenv("KB_LSTM_NG")) ng = atoi(getenv("KB_LSTM_NG")) == 3 ? 3 : 2;
+                    tp.alt = getenv("KB_LSTM_ALT") ? atoi(getenv("KB_LSTM_ALT")) : (ng == 2);
+                    const int nl = ng * gl;
                     // Lines per cluster.  Measured on cfg2 (tools/rec_ab.py): 16, 12 and 10 lines per cluster all take 0.30 ms - the time step
                     // is a latency chain (~500 MMAs + ~800 epilogue + ~1100-1300 remote delivery), not a function of the bytes sent - so a
                     // synchronous call gains nothing from spreading over more clusters and every call keeps full clusters (fewest SMs per
                     // batch).  KB_LSTM_LPC overrides (ragged last cluster / tests).
-                    int lpc = nl;
+                    int lpc = (lp.nseq + ((lp.nseq + nl - 1) / nl) - 1) / std::max(1, (lp.nseq + nl - 1) / nl);      // the same number of clusters, evenly filled
+                    lpc = std::min(nl, std::max(1, lpc));
                     if (gl == 8) {
                         if (m->max_clusters_tc < 0) {
                             cudaLaunchConfig_t q = {};
-                            q.gridDim = dim3(ltc::LCS * 32, 1, 1); q.blockDim = dim3(ltc::LTHREADS, 1, 1); q.dynamicSmemBytes = ltc::ClusterCfg<8>::SMEM_BYTES;
+                            q.gridDim = dim3(ltc::LCS * 32, 1, 1); q.blockDim = dim3(ltc::LTHREADS, 1, 1); q.dynamicSmemBytes = ltc::ClusterCfg<8, 2>::SMEM_BYTES;
                             cudaLaunchAttribute qa[1]; qa[0].id = cudaLaunchAttributeClusterDimension;
                             qa[0].val.clusterDim.x = ltc::LCS; qa[0].val.clusterDim.y = 1; qa[0].val.clusterDim.z = 1;
                             q.attrs = qa; q.numAttrs = 1;
                             int ncl = 0;
-                            if (cudaOccupancyMaxActiveClusters(&ncl, ltc::k_lstm_rec_tc<8>, &q) != cudaSuccess) { cudaGetLastError(); ncl = 8; }
+                            if (cudaOccupancyMaxActiveClusters(&ncl, ltc::k_lstm_rec_tc<8, 2>, &q) != cudaSuccess) { cudaGetLastError(); ncl = 8; }
                             m->max_clusters_tc = std::max(ncl, 1);
                         }
                         if (getenv("KB_LSTM_LPC")) lpc = std::min(nl, std::max(1, atoi(getenv("KB_LSTM_LPC"))));
@@ -782,8 +791,8 @@ struct Exec {
                     tp.lpc = lpc;
                     cudaLaunchConfig_t tcfg = {};
                     tcfg.gridDim = dim3((unsigned)(ltc::LCS * ((lp.nseq + lpc - 1) / lpc)), (unsigned)dirs, 1);
-                    tcfg.blockDim = dim3(ltc::LTHREADS, 1, 1);
-                    tcfg.dynamicSmemBytes = gl == 16 ? ltc::ClusterCfg<16>::SMEM_BYTES : ltc::ClusterCfg<8>::SMEM_BYTES; tcfg.stream = st;
+                    tcfg.blockDim = dim3(ltc::lthreads(ng), 1, 1);
+                    tcfg.dynamicSmemBytes = gl == 16 ? ltc::ClusterCfg<16, 2>::SMEM_BYTES : (ng == 3 ? ltc::ClusterCfg<8, 3>::SMEM_BYTES : ltc::ClusterCfg<8, 2>::SMEM_BYTES); tcfg.stream = st;
                     cudaLaunchAttribute tat[1];
                     tat[0].id = cudaLaunchAttributeClusterDimension;
                     tat[0].val.clusterDim.x = ltc::LCS; tat[0].val.clusterDim.y = 1; tat[0].val.clusterDim.z = 1;
@@ -791,8 +800,9 @@ struct Exec {
                     if (getenv("KB_DEBUG")) fprintf(stderr, "[kb] %s: tcgen05 recurrence, %u clusters of 8 CTAs x %d lines (max co-resident %d), T=%d\n", n.name.c_str(), tcfg.gridDim.x / 8 * dirs, lpc, m->max_clusters_tc, lp.T);
                     tp.dbgbuf = nullptr;
                     if (tp.dbg & 1) { CK(cudaMalloc((void **)&tp.dbgbuf, 96 * sizeof(long long))); CK(cudaMemset(tp.dbgbuf, 0, 96 * sizeof(long long))); }
-                    if (gl == 16) CK(cudaLaunchKernelEx(&tcfg, ltc::k_lstm_rec_tc<16>, tp));
-                    else CK(cudaLaunchKernelEx(&tcfg, ltc::k_lstm_rec_tc<8>, tp));
+                    if (gl == 16) CK(cudaLaunchKernelEx(&tcfg, ltc::k_lstm_rec_tc<16, 2>, tp));
+                    else if (ng == 3) CK(cudaLaunchKernelEx(&tcfg, ltc::k_lstm_rec_tc<8, 3>, tp));
+                    else CK(cudaLaunchKernelEx(&tcfg, ltc::k_lstm_rec_tc<8, 2>, tp));
                     if (tp.dbg & 1) {
                         long long hb[96];
                         CK(cudaMemcpy(hb, tp.dbgbuf, sizeof(hb), cudaMemcpyDeviceToHost));

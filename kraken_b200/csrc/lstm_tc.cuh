@@ -35,14 +35,14 @@ namespace ltc {
 
 using namespace kb::tc;
 
-constexpr int NG = 2;                                    // independent line groups per cluster (own issuers, barriers, accumulators, epilogue warps)
+constexpr int NG_MAX = 3;                                // independent line groups per cluster (own issuer, barriers, accumulators, epilogue warps): 2 or 3
 constexpr int LCS = 8;                                   // cluster size
 constexpr int A_PLANE_ELEMS = 128 * 256;                 // fp16 elements of one W plane of a CTA: [128 gate rows][K = 256], row-major
 constexpr int EW = 4;                                    // epilogue warps per TMEM lane quarter: 2 per group (latency hiding: v3 with 1 was 2x slower)
-constexpr int N_ISSUE = 2;                               // MMA issuer warps: one per group
-constexpr int LTHREADS = (N_ISSUE + 4 * EW) * 32;        // warps 0..1: MMA issuers (warp 0 also owns the TMEM allocation); warps 2..17: epilogue
+constexpr int lthreads(int ng) { return (ng + 8 * ng) * 32; }   // warps 0..NG-1: MMA issuers (warp 0 also owns the TMEM allocation); then 8 epilogue warps per group
+constexpr int LTHREADS = lthreads(2);
 constexpr int TM_COLS = 512;
-template <int GL> struct ClusterCfg {                    // GL = lines per group: 8 (16 lines per cluster) or 16 (32 lines per cluster)
+template <int GL, int NG = 2> struct ClusterCfg {        // GL = lines per group (8 or 16), NG groups: 16 / 24 / 32 lines per cluster
     static constexpr int NL = NG * GL;                   // lines per cluster
     static constexpr int LPW = GL / 2;                   // lines per epilogue warp (two warps per TMEM lane quarter and group)
     static constexpr int NT = LPW / 4;                   // 4x4 gate transposes (= cells) per thread and step
@@ -54,6 +54,8 @@ template <int GL> struct ClusterCfg {                    // GL = lines per group
     static constexpr int N1 = 2 * GL;                    // N of both products (W2s x the same operand rows; only its h1 columns are read)
     static constexpr int GSTRIDE = 4 * N1;               // TMEM columns per group: D1a @0, D1b @N1, D2a @2 N1, D2b @3 N1
     static constexpr int TM_A0 = NG * GSTRIDE;           // A: W1 @TM_A0 (128 columns), W2s @TM_A0 + 128
+    static constexpr int THREADS = lthreads(NG);
+    static_assert(NG * GSTRIDE + 256 <= 512, "accumulators + W_hh planes must fit the 512 TMEM columns");
 };
 
 struct LstmTcParams {
@@ -61,6 +63,7 @@ struct LstmTcParams {
     __half *out_hi, *out_lo;         // optional fp16 operand planes of the output for a tensor-core consumer (out may then be NULL)
     int nseq, T, hid, dirs, U;
     int q2; long long s_outer, s_inner, step;
+    int alt;                         // 1: the groups take turns on the tensor pipe (see the issuer loop)
     int lpc;                         // lines per cluster (<= NL): group 0 takes ceil(lpc / 2) of them, group 1 the rest; fewer lines = fewer bytes through DSMEM per step
     int dbg; long long *dbgbuf;      // KB_LSTM_DBG: bit 0 = clock64 stamps of steps 100..103 of cluster 0 into dbgbuf[step][group][12]
 };
@@ -166,17 +169,18 @@ __device__ __forceinline__ void gather_rows8(__half h1, __half h2, int lane, uin
 //   acc_free[g]                8 arrivals: the group's epilogue warps have read the accumulators of the previous step.
 //   mma_done[g]                tcgen05.commit of the group's issuer: accumulators complete.  Also read (not consumed) by the OTHER
 //                              group's issuer: the groups alternate on the tensor pipe.
-template <int GL>
-__global__ void __launch_bounds__(LTHREADS, 1) k_lstm_rec_tc(LstmTcParams p) {
-    using Cfg = ClusterCfg<GL>;
+template <int GL, int NG>
+__global__ void __launch_bounds__(lthreads(NG), 1) k_lstm_rec_tc(LstmTcParams p) {
+    using Cfg = ClusterCfg<GL, NG>;
+    constexpr int N_ISSUE = NG, LTHREADS = Cfg::THREADS;
     constexpr int NL = Cfg::NL, CH_B = Cfg::CH_B, B_BUF_B = Cfg::B_BUF_B, LPW = Cfg::LPW, NT = Cfg::NT;
     constexpr int TM_A0 = Cfg::TM_A0, GSTRIDE = Cfg::GSTRIDE, N1 = Cfg::N1;
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = smem_align1024(smem_raw);
     uint8_t *sB = smem;                                   // [group][buffer][k-chunk][row = (warp half, plane, line)][8 unit slots] fp16, no swizzle
     uint64_t *bars = reinterpret_cast<uint64_t *>(sB + NG * 2 * B_BUF_B);
-    uint64_t *b_half = bars /* [group][buffer][K half] */, *mma_done = bars + 8 /* [group] */, *acc_free = bars + 10 /* [group] */;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 12);
+    uint64_t *b_half = bars /* [group][buffer][K half] */, *mma_done = bars + 4 * NG /* [group] */, *acc_free = bars + 5 * NG /* [group] */;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 6 * NG);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint32_t rank;
@@ -185,12 +189,12 @@ __global__ void __launch_bounds__(LTHREADS, 1) k_lstm_rec_tc(LstmTcParams p) {
     const int hid = p.hid, GC = p.dirs * 4 * hid, OC = p.dirs * hid;
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < 8; ++i) mbar_init(&b_half[i], 1);
+        for (int i = 0; i < 4 * NG; ++i) mbar_init(&b_half[i], 1);
         for (int g = 0; g < NG; ++g) { mbar_init(&mma_done[g], 1); mbar_init(&acc_free[g], 2 * 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         for (int g = 0; g < NG; ++g)
             for (int hf = 0; hf < 2; ++hf)       // buffer 1 of each group receives h_0 at the end of step 0
-                mbar_expect_tx(&b_half[(g * 2 + 1) * 2 + hf], (uint32_t)(4 * 4 * 32 * (g ? p.lpc - ((p.lpc + 1) >> 1) : ((p.lpc + 1) >> 1))));
+                mbar_expect_tx(&b_half[(g * 2 + 1) * 2 + hf], (uint32_t)(4 * 4 * 32 * max(0, min((p.lpc + NG - 1) / NG, p.lpc - g * ((p.lpc + NG - 1) / NG)))));
     }
     for (int i = threadIdx.x; i < NG * 2 * B_BUF_B / 16; i += LTHREADS) reinterpret_cast<uint4 *>(sB)[i] = make_uint4(0, 0, 0, 0);   // h_{-1} = 0
     if (warp == 0) {
@@ -225,8 +229,8 @@ __global__ void __launch_bounds__(LTHREADS, 1) k_lstm_rec_tc(LstmTcParams p) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 
-    // lines of this cluster: [chunk * lpc, chunk * lpc + lpc), group 0 the first ceil(lpc / 2), group 1 the rest (<= GL each)
-    const int lpc = p.lpc, nl0 = (lpc + 1) >> 1;
+    // lines of this cluster: [chunk * lpc, chunk * lpc + lpc), ceil(lpc / NG) (<= GL) per group, the last group(s) take what is left
+    const int lpc = p.lpc, lper = (lpc + NG - 1) / NG;
     int maxlen = 0;                                       // uniform across the cluster (both groups run the same number of steps)
     for (int lb = 0; lb < lpc; ++lb) {
         const int q = chunk * lpc + lb;
@@ -242,17 +246,20 @@ __global__ void __launch_bounds__(LTHREADS, 1) k_lstm_rec_tc(LstmTcParams p) {
         // mbarrier polling competed with the epilogue warps' shuffles for the MIO pipe.
         const int g = warp;
         const uint32_t id1 = idesc_f16(0, 0, 128, N1);
-        const uint32_t half_bytes = (uint32_t)(4 * 4 * 32 * (g ? lpc - nl0 : nl0));     // 4 source CTAs x 4 k-chunks x (h1 + h2s row) per real line slot
+        const uint32_t half_bytes = (uint32_t)(4 * 4 * 32 * max(0, min(lper, lpc - g * lper)));     // 4 source CTAs x 4 k-chunks x (h1 + h2s row) per real line slot
         for (int s = 0; s < maxlen; ++s) {
             const int cur = s & 1;
             const long long d_w0 = dbg_cta ? clock64() : 0;
             if (s > 0) mbar_wait(&acc_free[g], (uint32_t)((s - 1) & 1));    // complete long before h_{s-1} can arrive
-            // The two groups take turns on the tensor pipe: g0(s), g1(s), g0(s+1), ...  Left alone they fall into lock-step (both
-            // start at step 0, and whoever is behind catches up while the other queues on the shared pipe / DSMEM port), and then
-            // both wait for the same resource at the same time and idle together.  The other group's mma_done barrier is only READ
-            // here (parity wait, no arrival).
-            if (g == 0) { if (s > 0) mbar_wait(&mma_done[1], (uint32_t)((s - 1) & 1)); }
-            else mbar_wait(&mma_done[0], (uint32_t)(s & 1));
+            // Alternation: with two groups the tensor pipe is handed from one group to the other - g0(s), g1(s), g0(s+1), ... (the other
+            // group's mma_done barrier is only READ here: parity wait, no arrival).  Left alone two groups fall into lock-step (both
+            // start at step 0, and whoever is behind catches up while the other queues on the shared pipe / DSMEM port) and idle
+            // together: 0.326 vs 0.311 ms on cfg2.  With three groups the same hand-over serialises them into 3 x 1370 cycles per step
+            // (0.467 ms); free-running they settle at 0.356 ms (p.alt = 0).
+            if (p.alt) {
+                if (g == 0) { if (s > 0) mbar_wait(&mma_done[NG - 1], (uint32_t)((s - 1) & 1)); }
+                else mbar_wait(&mma_done[g - 1], (uint32_t)(s & 1));
+            }
             long long d_w1 = 0;
 #pragma unroll 1
             for (int half = 0; half < 2; ++half) {
@@ -280,7 +287,7 @@ __global__ void __launch_bounds__(LTHREADS, 1) k_lstm_rec_tc(LstmTcParams p) {
             }
             if (elect_one()) {
                 umma_commit(&mma_done[g]);
-                if (dbg_cta && s >= 100 && s < 104) {
+                if (dbg_cta && g < 2 && s >= 100 && s < 104) {
                     long long *d = p.dbgbuf + ((s - 100) * 2 + g) * 12;
                     d[0] = d_w0; d[1] = d_w1; d[2] = clock64();
                 }
@@ -297,8 +304,8 @@ __global__ void __launch_bounds__(LTHREADS, 1) k_lstm_rec_tc(LstmTcParams p) {
         const int slot = 8 * q + jq, u = (int)rank * p.U + slot;
         const bool uvalid = slot < p.U && u < hid;
         // after the transposes this thread updates unit `u` of lines (first line of the warp) + 4 t + gate
-        const int nlg = g ? lpc - nl0 : nl0;              // real line slots of this group
-        const int line0 = chunk * lpc + (g ? nl0 : 0) + LPW * sw2;
+        const int nlg = max(0, min(lper, lpc - g * lper));    // real line slots of this group
+        const int line0 = chunk * lpc + g * lper + LPW * sw2;
         int clen[NT]; long long ooff[NT]; bool cval[NT]; float cst[NT];
         const long long ostride = (long long)(dir ? -1 : 1) * p.step * OC;
 #pragma unroll
@@ -343,7 +350,7 @@ __global__ void __launch_bounds__(LTHREADS, 1) k_lstm_rec_tc(LstmTcParams p) {
         const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * GSTRIDE + 2 * LPW * sw2);
         // gate non-linearity without divergence: sigmoid(x) for i, f, o; tanh(x) = 2*sigmoid(2x) - 1 for the candidate gate
         const float act_k = gate == 2 ? 2.f : 1.f;
-        const bool dbg_w = dbg_cta && q == 0 && sw2 == 0 && lane == 0;
+        const bool dbg_w = dbg_cta && g < 2 && q == 0 && sw2 == 0 && lane == 0;
         // whole 8-slot rows of this quarter are real units and 16-byte aligned in the output planes (hid 256: always)
         const bool vec_planes = p.out_hi && 8 * q + 7 < p.U && (int)rank * p.U + 8 * q + 7 < hid && (OC & 7) == 0 &&
                                 ((dir * hid + (int)rank * p.U + 8 * q) & 7) == 0 &&

@@ -589,6 +589,33 @@ def test_tensor_core_recurrence_lines_per_cluster(lpc):
     assert ol.tolist() == rl.tolist()
 
 
+@pytest.mark.parametrize('ng,alt,lpc', [(3, 0, None), (3, 1, None), (3, 0, 17), (3, 0, 5), (2, 0, None)])
+def test_tensor_core_recurrence_groups_per_cluster(ng, alt, lpc):
+    """KB_LSTM_NG=3: three groups of 8 lines per cluster (what the asynchronous slots use), free-running or alternating on the tensor
+    pipe, full / ragged / thin clusters - same results as the oracle."""
+    spec = '[1,16,0,1 Cr3,3,32 Mp2,2 S1(1x0)1,3 Lbx256 O1c30]'
+    om = vo.OracleModel(spec)
+    wts = om.init_like_reference(53)
+    g = torch.Generator().manual_seed(53)
+    n, w = 53, 96
+    lens = torch.randint(16, w + 1, (n,), generator=g)
+    lens[0] = w
+    x = torch.rand(n, 1, 16, w, generator=g)
+    for i, l in enumerate(lens.tolist()):
+        x[i, ..., l:] = 0
+    ref, rl = om.forward(x, lens)
+    m = kb.TorchVGSLModel(vgsl=spec)
+    m.load_state_dict(wts)
+    m.to('cuda:0')
+    kw = dict(KB_LSTM_NG=ng, KB_LSTM_ALT=alt)
+    if lpc:
+        kw['KB_LSTM_LPC'] = lpc
+    with env(**kw):
+        out, ol = m.nn(x.cuda(), lens)
+    assert rel_err(out, ref) <= TIGHT, (ng, alt, lpc, rel_err(out, ref))
+    assert ol.tolist() == rl.tolist()
+
+
 def test_generic_recurrence_matches_resident_kernels():
     """KB_LSTM_GENERIC=1 forces the per-step path for sizes the resident-weight kernels take: same results."""
     spec = '[1,16,0,1 Cr3,3,32 Mp2,2 S1(1x0)1,3 Lbx200 O1c30]'

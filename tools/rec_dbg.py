@@ -1,4 +1,5 @@
-"""Stand-alone GPU diagnostic: the clustered recurrence of cfg2 under the KB_LSTM_DBG bits (1: clock64 timeline of steps 100..103, 2:
+"""Stand-alone GPU diagnostic: the clustered recurrence of cfg2 with 2 / 3 groups per cluster (KB_LSTM_NG), with and without the
+hand-over of the tensor pipe between groups (KB_LSTM_ALT) and under the KB_LSTM_DBG bits (1: clock64 timeline of steps 100..103, 2:
 issuer polls its h barriers with test_wait instead of try_wait, 4: epilogue polls mma_done); device time of the stage and the logits
 against the first run per setting.  Usage: python tools/rec_dbg.py 2> log"""
 import os
@@ -19,7 +20,9 @@ x = torch.rand(64, 1, 48, 800).cuda()
 lens = torch.full((64,), 800)
 import numpy as np
 ref = None
-for mode in ('0', '2', '4', '0', '2', '4'):
+for ng, alt, mode in (('2', '1', '0'), ('2', '0', '0'), ('2', '1', '2'), ('2', '1', '4'), ('3', '1', '0'), ('3', '0', '0'), ('3', '0', '2'), ('3', '0', '4')):
+    os.environ['KB_LSTM_NG'] = ng
+    os.environ['KB_LSTM_ALT'] = alt
     os.environ['KB_LSTM_DBG'] = mode
     out, _ = m.nn(x, lens)
     if ref is None:
@@ -34,6 +37,6 @@ for mode in ('0', '2', '4', '0', '2', '4'):
         for k, v in m.last_timing():
             acc[k] = acc.get(k, 0.0) + v / 20
     m.set_timing(False)
-    print(f'KB_LSTM_DBG={mode}: rec {acc["L_5.rec"]:.4f} ms, logits vs the first run {err:.2e}', file=sys.stderr)
+    print(f'NG={ng} ALT={alt} KB_LSTM_DBG={mode}: rec {acc["L_5.rec"]:.4f} ms, logits vs the first run {err:.2e}', file=sys.stderr)
 os.environ['KB_LSTM_DBG'] = '1'
 rec._recognize_raw(x, lens, want_probs=False)
