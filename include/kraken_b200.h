@@ -48,7 +48,7 @@
 extern "C" {
 #endif
 
-#define KB_ABI_VERSION 3
+#define KB_ABI_VERSION 4
 
 enum {
     KB_OK = 0,
@@ -165,6 +165,31 @@ int  kb_recognize_records(kb_model *m, const void *lines, int dtype, int lines_o
                           const int32_t *widths, const int16_t *invert_max, float temperature, const int32_t *orig_widths, int32_t padding,
                           uint32_t *codepoints, int32_t *starts, int32_t *ends, float *confs, int32_t *counts, int32_t max_out,
                           int32_t *out_lens, void *stream);
+
+/* ---- forced alignment of known transcriptions (the `return_logits` consumer) -------------------------------------
+ * Replaces, per batch of lines, the numeric part of `ForcedAlignmentTaskModel.predict` (kraken/tasks/align.py:104-137):
+ *     emission = record.logits.squeeze().log_softmax(0).T      align.py:119  (record.logits = the (C, T) softmax output of
+ *                                                              kraken/lib/vgsl/rpred.py:226-227,200 - the second softmax is the reference's)
+ *     get_trellis (align.py:170-191), backtrack (:194-229), merge_repeats (:232-249), `_scale_val` of the borders (:128-132)
+ * Everything stays on the device between the network and the segments; the probabilities are never copied to the host.
+ * lines / dtype / widths / invert_max / temperature: as kb_recognize_records.
+ * tokens: the label sequences `codec.encode(text)` of all lines, concatenated; tok_off (n + 1): tok_off[i] .. tok_off[i + 1] are line
+ *   i's labels (tok_off[0] = 0).  A line without labels is an error (KB_ERR_ARG; the reference raises IndexError on it).
+ * orig_widths (n, or NULL) / padding: NULL = segment borders in output frames [start, end); otherwise `_scale_val(border, 0, width)`
+ *   positions in the original line image, with net_scale / in_scale as align.py:128 and rpred.py:185-187 set them.
+ * Outputs (host, caller allocated, max_seg >= the longest label sequence): seg_token [n * max_seg] = index INTO THE LINE'S LABEL SEQUENCE
+ *   (merge_repeats labels a segment ground_truth[token_index]), seg_start / seg_end, seg_score = mean frame probability of the run;
+ *   seg_counts [n] = number of segments, or -1: fewer output frames than 2 * len(labels) - the reference emits an empty record
+ *   (align.py:113-117), or -2: the backtrack ran out of frames - ValueError('Failed to align') (align.py:228).  out_lens (n, optional).   */
+int  kb_forced_align(kb_model *m, const void *lines, int dtype, int lines_on_device, int32_t n, int32_t h, int32_t w,
+                     const int32_t *widths, const int16_t *invert_max, float temperature, const int32_t *tokens, const int32_t *tok_off,
+                     const int32_t *orig_widths, int32_t padding, int32_t *seg_token, int32_t *seg_start, int32_t *seg_end,
+                     float *seg_score, int32_t *seg_counts, int32_t max_seg, int32_t *out_lens, void *stream);
+/* The same from probabilities the caller already holds (records produced with `return_logits`): probs (n, c, t) float32, host or
+ * device; lens (n, or NULL = t): valid frames per line, as `record.logits` is cut (rpred.py:200).  No model handle: runs on `device`. */
+int  kb_forced_align_probs(const float *probs, int probs_on_device, int32_t n, int32_t c, int32_t t, const int32_t *lens,
+                           const int32_t *tokens, const int32_t *tok_off, int32_t *seg_token, int32_t *seg_start, int32_t *seg_end,
+                           float *seg_score, int32_t *seg_counts, int32_t max_seg, int device, void *stream);
 
 /* ---- bbox line extraction + the PIL half of the input transforms on the device ----------------------------
  * Replaces, for bbox lines of horizontal text, `im.crop(box)` (kraken/lib/segmentation.py:1631-1643) and the image half of

@@ -64,6 +64,8 @@ _SIGS = {
     'kb_recognize_u8': (C.c_int, [_vp, _vp, C.c_int, _i32, _i32, _i32, _vp, _vp, _f, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, C.c_int, _vp]),
     'kb_model_set_codec': (C.c_int, [_vp, _vp, _i32]),
     'kb_recognize_records': (C.c_int, [_vp, _vp, C.c_int, C.c_int, _i32, _i32, _i32, _vp, _vp, _f, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp]),
+    'kb_forced_align': (C.c_int, [_vp, _vp, C.c_int, C.c_int, _i32, _i32, _i32, _vp, _vp, _f, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp]),
+    'kb_forced_align_probs': (C.c_int, [_vp, C.c_int, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, C.c_int, _vp]),
     'kb_line_width': (_i32, [_i32, _i32, _i32, _i32]),
     'kb_prepare_lines_u8': (C.c_int, [_vp, _vp, C.c_int, _i32, _i32, _i32, _i32, _vp, _i32, _i32, _vp, _i32, _vp, _vp, _vp]),
     'kb_set_pipeline_depth': (C.c_int, [_vp, _i32]),

@@ -18,6 +18,7 @@
 #include "lstm_tc.cuh"
 #include "line_prep.cuh"
 #include "conv1_tc.cuh"
+#include "align.cuh"
 #include "vgsl_plan.hpp"
 
 namespace kb {
@@ -1300,6 +1301,7 @@ static int guarded(F &&f) {
     catch (const ShapeError &e) { return fail(KB_ERR_SHAPE, e.what()); }
     catch (const Unsupported &e) { return fail(KB_ERR_UNSUPPORTED, e.what()); }
     catch (const CudaError &e) { cudaGetLastError(); return fail(KB_ERR_CUDA, e.what()); }
+    catch (const std::invalid_argument &e) { return fail(KB_ERR_ARG, e.what()); }
     catch (const std::bad_alloc &) { return fail(KB_ERR_STATE, "out of host memory"); }
     catch (const std::exception &e) { return fail(KB_ERR_STATE, e.what()); }
 }
@@ -1459,6 +1461,92 @@ static void recognize_enqueue(kb_model *m, Workspace *ws, const RecognizeArgs &a
     }
     decode_enqueue(n, T, a.max_out, d_lab, d_conf, d_lens, st, ws->arena, &ws->pinned, &ws->pinned_cap, &m->launches, rx);
     t_dec.reset();
+}
+
+// Forced alignment (kraken/tasks/align.py:111-137): forward -> probabilities (N, C, T) in the arena -> k_forced_align -> segments to the
+// caller's host arrays.  `tokens` / `tok_off`: the label sequences, concatenated.  See csrc/align.cuh.
+struct AlignArgs {
+    const float *lines; int lines_on_device; int n, h, w; const int32_t *widths; float temperature;
+    const int32_t *tokens, *tok_off; int jmax, max_seg;
+    const int32_t *orig_widths; int padding;
+    int32_t *seg_token, *seg_start, *seg_end; float *seg_score; int32_t *seg_counts;
+};
+static size_t align_bytes(int n, int C, int T, int jmax, int max_seg, int ntok) {
+    return (size_t)n * (T + 1) * (jmax + 1) * 4 + (size_t)n * T * 20 + (size_t)n * max_seg * 16 + (size_t)n * 32 + (size_t)(ntok + n + 1) * 4 + 16 * 256;
+}
+// probabilities (N, C, T) on the device -> segments in the caller's host arrays (enqueue only; the caller synchronises the stream)
+static void align_from_probs(const float *dp, const AlignArgs &a, const std::vector<int32_t> &olens, int T, int C, Arena &ar, cudaStream_t st, int64_t *launches) {
+    const int n = a.n, ntok = a.tok_off[n];
+    const size_t per = (size_t)n * a.max_seg;
+    fa::AlignParams p;
+    p.probs = dp; p.N = n; p.C = C; p.T = T; p.Jmax = a.jmax; p.max_seg = a.max_seg;
+    int *d_lens = (int *)ar.alloc((size_t)n * 4), *d_tok = (int *)ar.alloc((size_t)std::max(ntok, 1) * 4), *d_off = (int *)ar.alloc((size_t)(n + 1) * 4);
+    CK(cudaMemcpyAsync(d_lens, olens.data(), (size_t)n * 4, cudaMemcpyHostToDevice, st));
+    if (ntok) CK(cudaMemcpyAsync(d_tok, a.tokens, (size_t)ntok * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d_off, a.tok_off, (size_t)(n + 1) * 4, cudaMemcpyHostToDevice, st));
+    p.lens = d_lens; p.tokens = d_tok; p.tok_off = d_off;
+    p.trellis = (float *)ar.alloc((size_t)n * (T + 1) * (a.jmax + 1) * 4);
+    p.fmax = (float *)ar.alloc((size_t)n * T * 4); p.flse = (float *)ar.alloc((size_t)n * T * 4); p.fe0 = (float *)ar.alloc((size_t)n * T * 4);
+    p.ptok = (int *)ar.alloc((size_t)n * T * 4); p.pprob = (float *)ar.alloc((size_t)n * T * 4);
+    p.seg_token = (int *)ar.alloc(per * 4); p.seg_start = (int *)ar.alloc(per * 4); p.seg_end = (int *)ar.alloc(per * 4);
+    p.seg_score = (float *)ar.alloc(per * 4); p.seg_count = (int *)ar.alloc((size_t)n * 4);
+    p.scale = nullptr; p.maxv = nullptr; p.padding = a.padding;
+    if (a.orig_widths) {                                     // `_scale_val` of the borders, scales as in recognize_enqueue (align.py:128-132)
+        std::vector<double> sc((size_t)2 * n); std::vector<int> mv((size_t)n);
+        for (int i = 0; i < n; ++i) {
+            const int wi = a.widths ? a.widths[i] : a.w;
+            if (olens[i] <= 0 || wi - 2 * a.padding == 0) throw ShapeError("forced alignment: empty line or line no wider than its padding");
+            sc[(size_t)2 * i] = (double)wi / (double)olens[i];
+            sc[(size_t)2 * i + 1] = (double)a.orig_widths[i] / (double)(wi - 2 * a.padding);
+            mv[(size_t)i] = a.orig_widths[i];
+        }
+        double *d_sc = (double *)ar.alloc((size_t)2 * n * sizeof(double));
+        int *d_mv = (int *)ar.alloc((size_t)n * sizeof(int));
+        CK(cudaMemcpyAsync(d_sc, sc.data(), (size_t)2 * n * sizeof(double), cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(d_mv, mv.data(), (size_t)n * sizeof(int), cudaMemcpyHostToDevice, st));
+        CK(cudaStreamSynchronize(st));                       // the staging vectors go out of scope below
+        p.scale = d_sc; p.maxv = d_mv;
+    }
+    CK(cudaMemsetAsync(p.seg_token, 0, per * 4, st)); CK(cudaMemsetAsync(p.seg_start, 0, per * 4, st));
+    CK(cudaMemsetAsync(p.seg_end, 0, per * 4, st)); CK(cudaMemsetAsync(p.seg_score, 0, per * 4, st));
+    fa::k_forced_align<<<(unsigned)n, 256, fa::align_smem(a.jmax), st>>>(p);
+    CK(cudaPeekAtLastError());
+    if (launches) ++*launches;
+    CK(cudaMemcpyAsync(a.seg_token, p.seg_token, per * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(a.seg_start, p.seg_start, per * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(a.seg_end, p.seg_end, per * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(a.seg_score, p.seg_score, per * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(a.seg_counts, p.seg_count, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+}
+static void align_enqueue(kb_model *m, Workspace *ws, const AlignArgs &a, cudaStream_t st, int T, int C, std::vector<int32_t> &olens) {
+    const int n = a.n;
+    const size_t extra = (size_t)n * C * T * 4 + align_bytes(n, C, T, a.jmax, a.max_seg, a.tok_off[n]);
+    ForwardResult r = forward_impl(m, ws, a.lines, a.lines_on_device, n, a.h, a.w, a.widths, st, extra);
+    StageTimer t_al(ws, st, "align", true);
+    const long long rows = (long long)n * T;
+    olens.resize(n);
+    for (int i = 0; i < n; ++i) olens[i] = r.lens.has ? r.lens.v[i] : T;
+    float *dp = (float *)ws->arena.alloc((size_t)n * C * T * 4);
+    const size_t psm = (size_t)32 * (C + 1) * 4;
+    if (psm <= 48 * 1024) LAUNCH(m, k_probs_nct, dim3((unsigned)((T + 31) / 32), (unsigned)n), 256, psm, st, r.y.p, dp, T, C, a.temperature);
+    else LAUNCH(m, k_probs_nct_simple, (unsigned)((rows + 7) / 8), 256, 0, st, r.y.p, dp, n, T, C, a.temperature);
+    align_from_probs(dp, a, olens, T, C, ws->arena, st, &m->launches);
+}
+
+// argument checks shared by the two alignment entry points; returns the longest label sequence or throws
+static int align_check_tokens(int n, const int32_t *tokens, const int32_t *tok_off, int max_seg) {
+    if (tok_off[0] != 0) throw std::invalid_argument("tok_off[0] must be 0");
+    int jmax = 0;
+    for (int i = 0; i < n; ++i) {
+        const int j = tok_off[i + 1] - tok_off[i];
+        // an empty transcription: the reference indexes tokens[-1] of an empty tensor (align.py:204) and raises IndexError
+        if (j <= 0) throw std::invalid_argument("index -1 is out of bounds for dimension 0 with size 0 (line " + std::to_string(i) + " has no labels)");
+        jmax = std::max(jmax, j);
+    }
+    if (!tokens) throw std::invalid_argument("NULL argument");
+    if (max_seg < jmax) throw std::invalid_argument("max_seg must be at least the longest label sequence");
+    if (fa::align_smem(jmax) > 48 * 1024) throw Unsupported("label sequences longer than 6000 are not supported");
+    return jmax;
 }
 
 static void recognition_dims(kb_model *m, int n, int h, int w, int *T, int *C) {
@@ -1740,6 +1828,72 @@ int kb_recognize_records(kb_model *m, const void *lines, int dtype, int lines_on
         if (dtype == KB_DTYPE_U8) { f32 = stage_u8_lines(m, m->ws0(), (const uint8_t *)lines, lines_on_device, n, h, w, widths, invert_max, (cudaStream_t)stream); on_dev = 1; }
         return recognize_locked(m, f32, on_dev, n, h, w, widths, temperature, (int32_t *)codepoints, starts, ends, confs, counts, max_out, out_lens,
                                 nullptr, 0, stream, orig_widths, padding);
+    });
+}
+
+/* ---- forced alignment ----------------------------------------------------------------------------------------------------------- */
+int kb_forced_align(kb_model *m, const void *lines, int dtype, int lines_on_device, int32_t n, int32_t h, int32_t w,
+                    const int32_t *widths, const int16_t *invert_max, float temperature, const int32_t *tokens, const int32_t *tok_off,
+                    const int32_t *orig_widths, int32_t padding, int32_t *seg_token, int32_t *seg_start, int32_t *seg_end,
+                    float *seg_score, int32_t *seg_counts, int32_t max_seg, int32_t *out_lens, void *stream) {
+    if (!m || !lines || !tok_off || !seg_token || !seg_start || !seg_end || !seg_score || !seg_counts) return fail(KB_ERR_ARG, "NULL argument");
+    if (dtype != KB_DTYPE_F32 && dtype != KB_DTYPE_U8) return fail(KB_ERR_ARG, "dtype must be KB_DTYPE_F32 or KB_DTYPE_U8");
+    if (!(temperature > 0.f)) return fail(KB_ERR_ARG, "temperature must be positive");
+    if (n <= 0 || h <= 0 || w <= 0) return fail(KB_ERR_SHAPE, "empty input batch");
+    if (padding < 0) return fail(KB_ERR_ARG, "padding must be non-negative");
+    std::lock_guard<std::mutex> lk(m->mu);
+    return guarded([&]() {
+        DeviceGuard dguard;
+        ensure_ready(m);
+        cudaStream_t st = (cudaStream_t)stream;
+        Workspace *ws = m->ws0();
+        ws->timing = m->timing;
+        const float *f32 = (const float *)lines; int on_dev = lines_on_device;
+        if (dtype == KB_DTYPE_U8) { f32 = stage_u8_lines(m, ws, (const uint8_t *)lines, lines_on_device, n, h, w, widths, invert_max, st); on_dev = 1; }
+        const int jmax = align_check_tokens(n, tokens, tok_off, max_seg);
+        int T, C;
+        recognition_dims(m, n, h, w, &T, &C);
+        for (int i = 0; i < tok_off[n]; ++i)
+            if (tokens[i] < 0 || tokens[i] >= C) throw ShapeError("label " + std::to_string(tokens[i]) + " outside the model's " + std::to_string(C) + " classes");
+        std::vector<int32_t> olens;
+        AlignArgs a{f32, on_dev, n, h, w, widths, temperature, tokens, tok_off, jmax, max_seg, orig_widths, padding,
+                    seg_token, seg_start, seg_end, seg_score, seg_counts};
+        run_with_range_fallback(m, ws, st, [&]() { align_enqueue(m, ws, a, st, T, C, olens); });
+        if (out_lens) for (int i = 0; i < n; ++i) out_lens[i] = olens[i];
+        collect_timing(ws);
+        return (int)KB_OK;
+    });
+}
+
+int kb_forced_align_probs(const float *probs, int probs_on_device, int32_t n, int32_t c, int32_t t, const int32_t *lens,
+                          const int32_t *tokens, const int32_t *tok_off, int32_t *seg_token, int32_t *seg_start, int32_t *seg_end,
+                          float *seg_score, int32_t *seg_counts, int32_t max_seg, int device, void *stream) {
+    if (!probs || !tok_off || !seg_token || !seg_start || !seg_end || !seg_score || !seg_counts) return fail(KB_ERR_ARG, "NULL argument");
+    if (n <= 0 || c <= 0 || t <= 0) return fail(KB_ERR_ARG, "invalid sizes");
+    return guarded([&]() {
+        const int jmax = align_check_tokens(n, tokens, tok_off, max_seg);
+        for (int i = 0; i < tok_off[n]; ++i)
+            if (tokens[i] < 0 || tokens[i] >= c) throw ShapeError("label " + std::to_string(tokens[i]) + " outside the " + std::to_string(c) + " classes");
+        int cnt = 0;
+        if (cudaGetDeviceCount(&cnt) != cudaSuccess || cnt == 0) { cudaGetLastError(); throw CudaError("no CUDA device available: kraken_b200 has no CPU fallback"); }
+        DeviceGuard dguard;
+        CK(cudaSetDevice(device));
+        cudaStream_t st = (cudaStream_t)stream;
+        std::vector<int32_t> olens((size_t)n);
+        for (int i = 0; i < n; ++i) olens[i] = lens ? std::min(std::max(lens[i], 0), t) : t;
+        Arena ar;
+        const size_t in_bytes = (size_t)n * c * t * 4;
+        const size_t total = (probs_on_device ? 0 : in_bytes + 256) + align_bytes(n, c, t, jmax, max_seg, tok_off[n]) + 8192;
+        CK(cudaMalloc((void **)&ar.base, total)); ar.cap = total;
+        try {
+            const float *dp = probs;
+            if (!probs_on_device) { float *b = (float *)ar.alloc(in_bytes); CK(cudaMemcpyAsync(b, probs, in_bytes, cudaMemcpyHostToDevice, st)); dp = b; }
+            AlignArgs a{nullptr, 0, n, 1, t, nullptr, 1.f, tokens, tok_off, jmax, max_seg, nullptr, 0, seg_token, seg_start, seg_end, seg_score, seg_counts};
+            align_from_probs(dp, a, olens, t, c, ar, st, nullptr);
+            CK(cudaStreamSynchronize(st));
+        } catch (...) { cudaFree(ar.base); throw; }
+        cudaFree(ar.base);
+        return (int)KB_OK;
     });
 }
 

@@ -40,7 +40,7 @@ def test_library_was_built_from_the_sources_in_the_tree():
 
 def test_abi_version_and_device_count():
     import kraken_b200
-    assert kraken_b200.lib.kb_abi_version() == 3
+    assert kraken_b200.lib.kb_abi_version() == 4
     assert kraken_b200.device_count() >= 0
 
 
