@@ -18,7 +18,7 @@ from ._lib import check, lib
 from .models import KrakenInputException, TorchSeqRecognizer
 from .vgsl import _as_f32, _on_device, _ptr, _stream_for
 
-__all__ = ['forced_align', 'forced_align_probs', 'TOO_SHORT', 'FAILED']
+__all__ = ['forced_align', 'forced_align_probs', 'align_records', 'TOO_SHORT', 'FAILED']
 
 TOO_SHORT = -1
 FAILED = -2
@@ -124,3 +124,21 @@ def forced_align_probs(probs, labels: Sequence[Sequence[int]], lens=None, device
             raise ValueError('Failed to align')
         out.append([] if k == TOO_SHORT else [(int(seg_tok[i, j]), int(seg_s[i, j]), int(seg_e[i, j]), float(seg_score[i, j])) for j in range(k)])
     return out
+
+
+def align_records(logits: Sequence, labels: Sequence[Sequence[int]], device: int = 0) -> List[Optional[list]]:
+    """Aligns the records of one page in ONE engine call: `logits[i]` is record i's `logits` - (C, T_i) or (C, 1, T_i), every record
+    its own length, as kraken/lib/vgsl/rpred.py:200 cuts them - `labels[i]` its encoded transcription.  This is what replaces
+    align.py:119-122 inside the reference's per-record loop."""
+    ts = [torch.as_tensor(l).float().reshape(int(l.shape[0]), -1) for l in logits]
+    if not ts:
+        return []
+    c = int(ts[0].shape[0])
+    tmax = max(int(t.shape[1]) for t in ts)
+    dev = next((t.device for t in ts if t.is_cuda), torch.device('cpu'))
+    batch = torch.zeros((len(ts), c, tmax), dtype=torch.float32, device=dev)
+    for i, t in enumerate(ts):
+        if int(t.shape[0]) != c:
+            raise ValueError('records of different models in one call')
+        batch[i, :, :t.shape[1]] = t.to(dev)
+    return forced_align_probs(batch, labels, lens=[int(t.shape[1]) for t in ts], device=device)

@@ -1504,7 +1504,7 @@ static void align_from_probs(const float *dp, const AlignArgs &a, const std::vec
         int *d_mv = (int *)ar.alloc((size_t)n * sizeof(int));
         CK(cudaMemcpyAsync(d_sc, sc.data(), (size_t)2 * n * sizeof(double), cudaMemcpyHostToDevice, st));
         CK(cudaMemcpyAsync(d_mv, mv.data(), (size_t)n * sizeof(int), cudaMemcpyHostToDevice, st));
-        CK(cudaStreamSynchronize(st));                       // the staging vectors go out of scope below
+        // (pageable sources: cudaMemcpyAsync returns once they are staged, so the vectors may go out of scope)
         p.scale = d_sc; p.maxv = d_mv;
     }
     CK(cudaMemsetAsync(p.seg_token, 0, per * 4, st)); CK(cudaMemsetAsync(p.seg_start, 0, per * 4, st));

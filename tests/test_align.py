@@ -228,3 +228,7 @@ def test_gpu_forced_align_probs_equals_the_reference_goldens():
         st, segs = ao.align_line(p[:, :lens[i]], labels[i])
         assert st > 0 and [(s[0], s[1], s[2]) for s in got[i]] == [(s[0], s[1], s[2]) for s in segs]
         assert np.allclose([s[3] for s in got[i]], [s[3] for s in segs], rtol=1e-5, atol=1e-7)
+    # the per-record form: every record its own length
+    recs = [p[:, :l] for l in lens]
+    assert align.align_records(recs, labels) == got
+    assert align.align_records([r[:, None, :].cuda() for r in recs], labels) == got
