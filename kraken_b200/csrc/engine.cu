@@ -258,6 +258,7 @@ static void set_kernel_attributes() {
     CK(cudaFuncSetAttribute(c1tc::k_conv1_tc<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c1tc::conv1_tc_smem(16)));
     CK(cudaFuncSetAttribute((ltc::k_lstm_rec_tc<8, 2>), cudaFuncAttributeMaxDynamicSharedMemorySize, (ltc::ClusterCfg<8, 2>::SMEM_BYTES)));
     CK(cudaFuncSetAttribute((ltc::k_lstm_rec_tc<8, 3>), cudaFuncAttributeMaxDynamicSharedMemorySize, (ltc::ClusterCfg<8, 3>::SMEM_BYTES)));
+    CK(cudaFuncSetAttribute((ltc::k_lstm_rec_tc<8, 4, 1>), cudaFuncAttributeMaxDynamicSharedMemorySize, (ltc::ClusterCfg<8, 4, 1>::SMEM_BYTES)));
     CK(cudaFuncSetAttribute((ltc::k_lstm_rec_tc<16, 2>), cudaFuncAttributeMaxDynamicSharedMemorySize, (ltc::ClusterCfg<16, 2>::SMEM_BYTES)));
     CK(cudaFuncSetAttribute(ltc::k_lstm_rec_tc_small<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, ltc::SmallCfg<64>::SMEM_BYTES));
     CK(cudaFuncSetAttribute(ltc::k_lstm_rec_tc_small<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, ltc::SmallCfg<32>::SMEM_BYTES));
@@ -765,9 +766,10 @@ struct Exec {
                     // Groups of 8 lines per cluster.  Two (16 lines on 8 SMs, the groups alternating on the tensor pipe) give the shortest
                     // recurrence (cfg2: 0.311 ms) and are what a synchronous call gets.  Three free-running groups (24 lines on 8 SMs) take
                     // 0.356 ms but a third fewer SMs, which is worth +6.5 % lines/s when several batches are in flight (bench.py, r02):
-                    // the asynchronous slots use that.  KB_LSTM_NG=2|3 overrides.  DESIGN.md 4.2.
+                    // the asynchronous slots use that.  Four groups (one epilogue warp per TMEM lane quarter) take 0.52 ms: no gain, kept as a switch.
+                    // KB_LSTM_NG=2|3|4 overrides.  DESIGN.md 4.2.
                     int ng = (gl == 8 && ws->index > 0 && (lp.nseq + 23) / 24 < (lp.nseq + 15) / 16) ? 3 : 2;      // only where it saves clusters
-                    if (gl == 8 && getenv("KB_LSTM_NG")) ng = atoi(getenv("KB_LSTM_NG")) == 3 ? 3 : 2;
+                    if (gl == 8 && getenv("KB_LSTM_NG")) { const int e = atoi(getenv("KB_LSTM_NG")); ng = e == 3 || e == 4 ? e : 2; }     // 4: one epilogue warp per TMEM lane quarter and group
                     tp.alt = getenv("KB_LSTM_ALT") ? atoi(getenv("KB_LSTM_ALT")) : (ng == 2);
                     const int nl = ng * gl;
                     // Lines per cluster.  Measured on cfg2 (tools/rec_ab.py): 16, 12 and 10 lines per cluster all take 0.30 ms - the time step
@@ -792,8 +794,8 @@ struct Exec {
                     tp.lpc = lpc;
                     cudaLaunchConfig_t tcfg = {};
                     tcfg.gridDim = dim3((unsigned)(ltc::LCS * ((lp.nseq + lpc - 1) / lpc)), (unsigned)dirs, 1);
-                    tcfg.blockDim = dim3(ltc::lthreads(ng), 1, 1);
-                    tcfg.dynamicSmemBytes = gl == 16 ? ltc::ClusterCfg<16, 2>::SMEM_BYTES : (ng == 3 ? ltc::ClusterCfg<8, 3>::SMEM_BYTES : ltc::ClusterCfg<8, 2>::SMEM_BYTES); tcfg.stream = st;
+                    tcfg.blockDim = dim3(ltc::lthreads(ng, ng == 4 ? 1 : 2), 1, 1);
+                    tcfg.dynamicSmemBytes = gl == 16 ? ltc::ClusterCfg<16, 2>::SMEM_BYTES : (ng == 4 ? ltc::ClusterCfg<8, 4, 1>::SMEM_BYTES : ng == 3 ? ltc::ClusterCfg<8, 3>::SMEM_BYTES : ltc::ClusterCfg<8, 2>::SMEM_BYTES); tcfg.stream = st;
                     cudaLaunchAttribute tat[1];
                     tat[0].id = cudaLaunchAttributeClusterDimension;
                     tat[0].val.clusterDim.x = ltc::LCS; tat[0].val.clusterDim.y = 1; tat[0].val.clusterDim.z = 1;
@@ -802,6 +804,7 @@ struct Exec {
                     tp.dbgbuf = nullptr;
                     if (tp.dbg & 1) { CK(cudaMalloc((void **)&tp.dbgbuf, 96 * sizeof(long long))); CK(cudaMemset(tp.dbgbuf, 0, 96 * sizeof(long long))); }
                     if (gl == 16) CK(cudaLaunchKernelEx(&tcfg, ltc::k_lstm_rec_tc<16, 2>, tp));
+                    else if (ng == 4) CK(cudaLaunchKernelEx(&tcfg, ltc::k_lstm_rec_tc<8, 4, 1>, tp));
                     else if (ng == 3) CK(cudaLaunchKernelEx(&tcfg, ltc::k_lstm_rec_tc<8, 3>, tp));
                     else CK(cudaLaunchKernelEx(&tcfg, ltc::k_lstm_rec_tc<8, 2>, tp));
                     if (tp.dbg & 1) {

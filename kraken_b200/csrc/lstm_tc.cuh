@@ -35,16 +35,18 @@ namespace ltc {
 
 using namespace kb::tc;
 
-constexpr int NG_MAX = 3;                                // independent line groups per cluster (own issuer, barriers, accumulators, epilogue warps): 2 or 3
+constexpr int NG_MAX = 4;                                // independent line groups per cluster (own issuer, barriers, accumulators, epilogue warps): 2, 3 or 4
 constexpr int LCS = 8;                                   // cluster size
 constexpr int A_PLANE_ELEMS = 128 * 256;                 // fp16 elements of one W plane of a CTA: [128 gate rows][K = 256], row-major
 constexpr int EW = 4;                                    // epilogue warps per TMEM lane quarter: 2 per group (latency hiding: v3 with 1 was 2x slower)
-constexpr int lthreads(int ng) { return (ng + 8 * ng) * 32; }   // warps 0..NG-1: MMA issuers (warp 0 also owns the TMEM allocation); then 8 epilogue warps per group
+// warps 0..NG-1: MMA issuers (warp 0 also owns the TMEM allocation); then 4 EH epilogue warps per group (EH = 2: two warps per TMEM lane
+// quarter, each half of the group's lines; EH = 1: one warp per quarter with all of them - what lets four groups fit 1024 threads)
+constexpr int lthreads(int ng, int eh = 2) { return (ng + 4 * eh * ng) * 32; }
 constexpr int LTHREADS = lthreads(2);
 constexpr int TM_COLS = 512;
-template <int GL, int NG = 2> struct ClusterCfg {        // GL = lines per group (8 or 16), NG groups: 16 / 24 / 32 lines per cluster
+template <int GL, int NG = 2, int EH = 2> struct ClusterCfg {   // GL = lines per group (8 or 16), NG groups: 16 / 24 / 32 lines per cluster
     static constexpr int NL = NG * GL;                   // lines per cluster
-    static constexpr int LPW = GL / 2;                   // lines per epilogue warp (two warps per TMEM lane quarter and group)
+    static constexpr int LPW = GL / EH;                  // lines per epilogue warp (EH warps per TMEM lane quarter and group)
     static constexpr int NT = LPW / 4;                   // 4x4 gate transposes (= cells) per thread and step
     static constexpr int CH_B = 2 * GL * 16;             // bytes of one k-chunk (8 unit slots) of a group: rows [warp half][plane][line] x 16 B
     static constexpr int B_BUF_B = 32 * CH_B;            // bytes per (group, buffer): K = 256 = 32 chunks
@@ -54,7 +56,8 @@ template <int GL, int NG = 2> struct ClusterCfg {        // GL = lines per group
     static constexpr int N1 = 2 * GL;                    // N of both products (W2s x the same operand rows; only its h1 columns are read)
     static constexpr int GSTRIDE = 4 * N1;               // TMEM columns per group: D1a @0, D1b @N1, D2a @2 N1, D2b @3 N1
     static constexpr int TM_A0 = NG * GSTRIDE;           // A: W1 @TM_A0 (128 columns), W2s @TM_A0 + 128
-    static constexpr int THREADS = lthreads(NG);
+    static constexpr int THREADS = lthreads(NG, EH);
+    static_assert(LPW == 4 || LPW == 8, "an epilogue warp reads 4 or 8 accumulator columns per product");
     static_assert(NG * GSTRIDE + 256 <= 512, "accumulators + W_hh planes must fit the 512 TMEM columns");
 };
 
@@ -166,12 +169,12 @@ __device__ __forceinline__ void gather_rows8(__half h1, __half h2, int lane, uin
 //                              registers, 16 bytes per store) into this CTA's operand buffer.  Waited on by the group's issuer, which
 //                              re-arms it for the refill two steps later once it has passed it (nobody can send that refill before
 //                              receiving this CTA's h_s, which needs this step's MMAs).
-//   acc_free[g]                8 arrivals: the group's epilogue warps have read the accumulators of the previous step.
+//   acc_free[g]                4 EH arrivals: the group's epilogue warps have read the accumulators of the previous step.
 //   mma_done[g]                tcgen05.commit of the group's issuer: accumulators complete.  Also read (not consumed) by the OTHER
 //                              group's issuer: the groups alternate on the tensor pipe.
-template <int GL, int NG>
-__global__ void __launch_bounds__(lthreads(NG), 1) k_lstm_rec_tc(LstmTcParams p) {
-    using Cfg = ClusterCfg<GL, NG>;
+template <int GL, int NG, int EH = 2>
+__global__ void __launch_bounds__(lthreads(NG, EH), 1) k_lstm_rec_tc(LstmTcParams p) {
+    using Cfg = ClusterCfg<GL, NG, EH>;
     constexpr int N_ISSUE = NG, LTHREADS = Cfg::THREADS;
     constexpr int NL = Cfg::NL, CH_B = Cfg::CH_B, B_BUF_B = Cfg::B_BUF_B, LPW = Cfg::LPW, NT = Cfg::NT;
     constexpr int TM_A0 = Cfg::TM_A0, GSTRIDE = Cfg::GSTRIDE, N1 = Cfg::N1;
@@ -190,7 +193,7 @@ __global__ void __launch_bounds__(lthreads(NG), 1) k_lstm_rec_tc(LstmTcParams p)
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < 4 * NG; ++i) mbar_init(&b_half[i], 1);
-        for (int g = 0; g < NG; ++g) { mbar_init(&mma_done[g], 1); mbar_init(&acc_free[g], 2 * 4); }
+        for (int g = 0; g < NG; ++g) { mbar_init(&mma_done[g], 1); mbar_init(&acc_free[g], EH * 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         for (int g = 0; g < NG; ++g)
             for (int hf = 0; hf < 2; ++hf)       // buffer 1 of each group receives h_0 at the end of step 0
@@ -299,7 +302,7 @@ __global__ void __launch_bounds__(lthreads(NG), 1) k_lstm_rec_tc(LstmTcParams p)
         // A warp owns LPW lines of its group x the 8 unit slots of its TMEM lane quarter and never synchronises with another warp:
         // gate values are regrouped by quad shuffles, h leaves as st.async straight from registers.
         const int q = warp & 3;                            // TMEM lane quarter: unit slots 8q .. 8q+7
-        const int sw = (warp - N_ISSUE) >> 2, g = sw >> 1, sw2 = sw & 1;
+        const int sw = (warp - N_ISSUE) >> 2, g = sw / EH, sw2 = sw % EH;
         const int jq = lane >> 2, gate = lane & 3;         // unit slot within the quarter, gate of this thread's TMEM row
         const int slot = 8 * q + jq, u = (int)rank * p.U + slot;
         const bool uvalid = slot < p.U && u < hid;

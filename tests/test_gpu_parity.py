@@ -589,7 +589,7 @@ def test_tensor_core_recurrence_lines_per_cluster(lpc):
     assert ol.tolist() == rl.tolist()
 
 
-@pytest.mark.parametrize('ng,alt,lpc', [(3, 0, None), (3, 1, None), (3, 0, 17), (3, 0, 5), (2, 0, None)])
+@pytest.mark.parametrize('ng,alt,lpc', [(3, 0, None), (3, 1, None), (3, 0, 17), (3, 0, 5), (2, 0, None), (4, 0, None), (4, 1, None), (4, 0, 27), (4, 0, 6)])
 def test_tensor_core_recurrence_groups_per_cluster(ng, alt, lpc):
     """KB_LSTM_NG=3: three groups of 8 lines per cluster (what the asynchronous slots use), free-running or alternating on the tensor
     pipe, full / ragged / thin clusters - same results as the oracle."""

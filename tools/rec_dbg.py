@@ -20,7 +20,7 @@ x = torch.rand(64, 1, 48, 800).cuda()
 lens = torch.full((64,), 800)
 import numpy as np
 ref = None
-for ng, alt, mode in (('2', '1', '0'), ('2', '0', '0'), ('2', '1', '2'), ('2', '1', '4'), ('3', '1', '0'), ('3', '0', '0'), ('3', '0', '2'), ('3', '0', '4')):
+for ng, alt, mode in (('2', '1', '0'), ('3', '0', '0'), ('4', '0', '0'), ('4', '1', '0'), ('2', '1', '0'), ('3', '0', '0'), ('4', '0', '0')):
     os.environ['KB_LSTM_NG'] = ng
     os.environ['KB_LSTM_ALT'] = alt
     os.environ['KB_LSTM_DBG'] = mode
