@@ -110,6 +110,8 @@ def forced_align_probs(probs, labels: Sequence[Sequence[int]], lens=None, device
     tok_off[1:] = np.cumsum([len(lab) for lab in labels])
     tokens = np.ascontiguousarray(np.concatenate([np.asarray(lab, np.int32).reshape(-1) for lab in labels]), dtype=np.int32)
     ln = np.ascontiguousarray(torch.as_tensor(lens).cpu().numpy(), dtype=np.int32) if lens is not None else None
+    if ln is not None and ln.shape != (n,):
+        raise ValueError('lens must have one entry per batch element')
     stride = int(max(len(lab) for lab in labels))
     seg_tok = np.zeros((n, stride), np.int32); seg_s = np.zeros((n, stride), np.int32); seg_e = np.zeros((n, stride), np.int32)
     seg_score = np.zeros((n, stride), np.float32); counts = np.zeros(n, np.int32)

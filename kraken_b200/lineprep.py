@@ -72,6 +72,8 @@ def prepare_box_lines(model: TorchVGSLModel, page, boxes: Sequence[Sequence[int]
     widths = np.zeros(n, np.int32)
     inv = np.zeros(n, np.int16)
     on_dev = isinstance(arr, torch.Tensor) and arr.is_cuda
+    if on_dev and arr.device.index != net._device:                         # a page resident on another GPU: bring it to the model's
+        arr = arr.to(dev)
     if isinstance(arr, torch.Tensor) and not arr.is_cuda:
         arr = arr.numpy()
     ptr = arr.data_ptr() if on_dev else arr.ctypes.data

@@ -102,6 +102,12 @@ def test_wrapper_argument_errors():
         align.forced_align(rec, x, None)                                   # neither texts nor labels
     with pytest.raises(ValueError):
         align.forced_align(rec, x, None, texts=['a', 'b'])                 # no codec
+    with pytest.raises(ValueError):
+        align.forced_align_probs(torch.rand(2, 5, 9), [[1], [2]], lens=[9])          # one length per line
+    with pytest.raises(IndexError):
+        align.forced_align_probs(torch.rand(1, 5, 9), [[]])
+    with pytest.raises(ValueError):
+        align.forced_align_probs(torch.rand(2, 5, 9), [[1]])
 
 
 CFG2 = '[1,48,0,1 Cr3,3,32 Mp2,2 Cr3,3,64 Mp2,2 S1(1x0)1,3 Lbx256 O1c200]'
